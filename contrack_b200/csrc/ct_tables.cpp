@@ -1,0 +1,253 @@
+// ct_tables.cpp -- see ct_tables.h.  Pure host C++ (no CUDA), exact integer logic.
+#include "ct_tables.h"
+
+#include <algorithm>
+#include <climits>
+#include <unordered_map>
+
+namespace ctb {
+
+namespace {
+
+struct Box3 { int t0, t1, y0, y1, x0, x1; };      // half-open on every axis
+
+struct Piece {
+    long comp;                  // kept 2-D component this piece belongs to
+    int t, y0, y1, x0, x1;      // plane and tight 2-D bounding box (half-open)
+    int value;                  // current id (the reference's flag value of these pixels)
+    bool has_runs;              // runs[] materialised
+    std::vector<SubRun> runs;
+};
+
+enum Rel { OUTSIDE = 0, INSIDE = 1, PARTIAL = 2 };
+
+inline Rel classify(const Piece& p, const Box3& b) {
+    if (p.t < b.t0 || p.t >= b.t1) return OUTSIDE;
+    if (p.y0 >= b.y0 && p.y1 <= b.y1 && p.x0 >= b.x0 && p.x1 <= b.x1) return INSIDE;
+    if (p.y1 <= b.y0 || p.y0 >= b.y1 || p.x1 <= b.x0 || p.x0 >= b.x1) return OUTSIDE;
+    return PARTIAL;
+}
+
+inline void tight_box(Piece& p) {
+    int y0 = INT_MAX, y1 = 0, x0 = INT_MAX, x1 = 0;
+    for (const SubRun& r : p.runs) {
+        y0 = std::min(y0, r.y); y1 = std::max(y1, r.y + 1);
+        x0 = std::min(x0, r.x0); x1 = std::max(x1, r.x1);
+    }
+    p.y0 = y0; p.y1 = y1; p.x0 = x0; p.x1 = x1;
+}
+
+}  // namespace
+
+int track_tables(long T, int H, int W, int persistence,
+                 long ncomp, const int32_t* comp_t, const int32_t* comp_y0, const int32_t* comp_y1,
+                 const int32_t* comp_x0, const int32_t* comp_x1, const int32_t* comp_label,
+                 long nseg, const int32_t* seg_t, const int32_t* seg_y0, const int32_t* seg_y1,
+                 const int32_t* seg_a, const int32_t* seg_b,
+                 RunFetcher* fetcher, int32_t* comp_val, std::vector<Override>& overrides, TrackStats& stats) {
+    (void)H;
+    overrides.clear();
+    stats = TrackStats();
+    int nlabel = 0;
+    for (long c = 0; c < ncomp; ++c) nlabel = std::max(nlabel, (int)comp_label[c]);
+
+    // value of each whole component; pieces beyond ncomp only exist after a split
+    std::vector<int> value(comp_label, comp_label + ncomp);
+    std::vector<Piece> extra;                               // pieces created by splits (index ncomp + k)
+    std::vector<Piece> whole_runs;                          // whole components whose runs were materialised
+    std::unordered_map<long, int> whole_runs_idx;           // comp -> index in whole_runs
+    std::unordered_map<long, std::vector<long>> comp_pieces; // split comps -> piece ids (comp id itself = remainder)
+
+    auto make_piece = [&](long c) {
+        Piece p;
+        p.comp = c; p.t = comp_t[c]; p.y0 = comp_y0[c]; p.y1 = comp_y1[c]; p.x0 = comp_x0[c]; p.x1 = comp_x1[c];
+        p.value = value[c]; p.has_runs = false;
+        return p;
+    };
+
+    if (nseg > 0) {
+        // 3-D boxes of the ORIGINAL labels (find_objects before merging, contrack.py:753)
+        std::vector<Box3> box(nlabel + 1, Box3{INT_MAX, 0, INT_MAX, 0, INT_MAX, 0});
+        // CSR of components per original label (stable: first-pixel order)
+        std::vector<long> first(nlabel + 2, 0);
+        for (long c = 0; c < ncomp; ++c) {
+            Box3& b = box[comp_label[c]];
+            b.t0 = std::min(b.t0, (int)comp_t[c]); b.t1 = std::max(b.t1, (int)comp_t[c] + 1);
+            b.y0 = std::min(b.y0, (int)comp_y0[c]); b.y1 = std::max(b.y1, (int)comp_y1[c]);
+            b.x0 = std::min(b.x0, (int)comp_x0[c]); b.x1 = std::max(b.x1, (int)comp_x1[c]);
+            first[comp_label[c] + 1]++;
+        }
+        for (int v = 0; v <= nlabel; ++v) first[v + 1] += first[v];
+        std::vector<long> order(ncomp);
+        {
+            std::vector<long> pos(first.begin(), first.end() - 1);
+            for (long c = 0; c < ncomp; ++c) order[pos[comp_label[c]]++] = c;
+        }
+        // dynamic member lists (piece ids), created on first use from the CSR
+        std::unordered_map<int, std::vector<long>> members;
+        auto get_members = [&](int v) -> std::vector<long>& {
+            auto it = members.find(v);
+            if (it != members.end()) return it->second;
+            std::vector<long>& m = members[v];
+            m.assign(order.begin() + first[v], order.begin() + first[v + 1]);
+            return m;
+        };
+        auto piece_ref = [&](long pid) -> Piece* {           // only valid until `extra` / `whole_runs` grow
+            if (pid >= ncomp) return &extra[pid - ncomp];
+            auto it = whole_runs_idx.find(pid);
+            return it == whole_runs_idx.end() ? nullptr : &whole_runs[it->second];
+        };
+        auto piece_value = [&](long pid) -> int { return pid >= ncomp ? extra[pid - ncomp].value : value[pid]; };
+        auto piece_of = [&](long c, int y, int x) -> long {  // piece holding pixel (y, x) of component c
+            auto it = comp_pieces.find(c);
+            if (it == comp_pieces.end()) return c;
+            for (long pid : it->second) {
+                const Piece* p = piece_ref(pid);
+                for (const SubRun& r : p->runs)
+                    if (r.y == y && r.x0 <= x && x < r.x1) return pid;
+            }
+            return c;                                         // unreachable for consistent tables
+        };
+
+        int rc = 0;
+        auto do_event = [&](int hi, int lo) {
+            const Box3 b = box[hi];
+            std::vector<long> cur;
+            cur.swap(get_members(hi));
+            std::vector<long> stay;
+            std::vector<long> moved;
+            for (long pid : cur) {
+                Piece tmp;
+                Piece* pp = piece_ref(pid);
+                if (!pp) { tmp = make_piece(pid); pp = &tmp; }
+                Rel rel = classify(*pp, b);
+                if (rel == PARTIAL) {
+                    // materialise the row-runs of this piece
+                    if (!pp->has_runs) {
+                        Piece np_ = make_piece(pid);
+                        if (!fetcher || !fetcher->fetch(pid, np_.runs)) { rc = -1; stay.push_back(pid); continue; }
+                        np_.has_runs = true;
+                        whole_runs_idx[pid] = (int)whole_runs.size();
+                        whole_runs.push_back(std::move(np_));
+                        pp = &whole_runs.back();
+                    }
+                    std::vector<SubRun> in, out;
+                    for (const SubRun& r : pp->runs) {
+                        if (r.y < b.y0 || r.y >= b.y1 || r.x1 <= b.x0 || r.x0 >= b.x1) { out.push_back(r); continue; }
+                        int a = std::max(r.x0, b.x0), e = std::min(r.x1, b.x1);
+                        if (r.x0 < a) out.push_back(SubRun{r.y, r.x0, a});
+                        in.push_back(SubRun{r.y, a, e});
+                        if (e < r.x1) out.push_back(SubRun{r.y, e, r.x1});
+                    }
+                    if (in.empty()) rel = OUTSIDE;
+                    else if (out.empty()) rel = INSIDE;
+                    else {
+                        // split: the inside part becomes a new piece with value lo, the rest keeps hi
+                        Piece q;
+                        q.comp = pp->comp; q.t = pp->t; q.value = lo; q.has_runs = true; q.runs.swap(in);
+                        tight_box(q);
+                        pp->runs.swap(out);
+                        tight_box(*pp);
+                        long comp = pp->comp;
+                        long qid = ncomp + (long)extra.size();
+                        extra.push_back(std::move(q));        // may invalidate pp
+                        std::vector<long>& cp = comp_pieces[comp];
+                        if (cp.empty()) cp.push_back(comp);   // the whole-comp id now denotes the remainder
+                        cp.push_back(qid);
+                        moved.push_back(qid);
+                        stay.push_back(pid);
+                        stats.n_splits++;
+                        continue;
+                    }
+                }
+                if (rel == INSIDE) {
+                    if (pid >= ncomp) extra[pid - ncomp].value = lo; else value[pid] = lo;
+                    moved.push_back(pid);
+                } else {
+                    stay.push_back(pid);
+                }
+            }
+            get_members(hi).swap(stay);
+            std::vector<long>& ml = get_members(lo);
+            ml.insert(ml.end(), moved.begin(), moved.end());
+        };
+
+        for (long s = 0; s < nseg && rc == 0; ++s) {
+            const long a = seg_a[s], b = seg_b[s];
+            for (int y = seg_y0[s]; y < seg_y1[s]; ++y) {
+                long pa = piece_of(a, y, 0), pb = piece_of(b, y, W - 1);
+                int va = piece_value(pa), vb = piece_value(pb);
+                if (va != vb) {
+                    do_event(std::max(va, vb), std::min(va, vb));
+                    stats.n_events++;
+                }
+                // With both components unsplit every later row of the segment sees the same two pieces and no other
+                // event intervenes, so re-applying the (idempotent) merge changes nothing.
+                if (comp_pieces.find(a) == comp_pieces.end() && comp_pieces.find(b) == comp_pieces.end()) break;
+            }
+        }
+        if (rc != 0) return rc;
+    }
+
+    // persistence on the merged values (contrack.py:765-772): t-extent of all pixels that carry value v
+    std::vector<int> tmin(nlabel + 1, INT_MAX), tmax(nlabel + 1, -1);
+    for (long c = 0; c < ncomp; ++c) {
+        auto it = comp_pieces.find(c);
+        if (it != comp_pieces.end()) continue;                // split comps are handled through their pieces
+        int v = value[c];
+        tmin[v] = std::min(tmin[v], (int)comp_t[c]); tmax[v] = std::max(tmax[v], (int)comp_t[c]);
+    }
+    for (auto& kv : comp_pieces) {
+        for (long pid : kv.second) {
+            int v, t;
+            if (pid >= ncomp) { v = extra[pid - ncomp].value; t = extra[pid - ncomp].t; }
+            else { v = value[pid]; t = comp_t[pid]; }
+            tmin[v] = std::min(tmin[v], t); tmax[v] = std::max(tmax[v], t);
+        }
+    }
+    std::vector<int> fin(nlabel + 1, 0);
+    for (int v = 1; v <= nlabel; ++v) {
+        if (tmax[v] < 0) continue;
+        if ((tmax[v] + 1 - tmin[v]) < persistence) continue;
+        fin[v] = v;
+        stats.n_features++;
+    }
+    (void)T;
+    for (long c = 0; c < ncomp; ++c) comp_val[c] = fin[value[c]];
+    for (auto& kv : comp_pieces) {
+        comp_val[kv.first] = 0;
+        for (long pid : kv.second) {
+            const Piece* p = pid >= ncomp ? &extra[pid - ncomp] : &whole_runs[whole_runs_idx[pid]];
+            int v = fin[pid >= ncomp ? p->value : value[pid]];
+            if (v == 0) continue;
+            for (const SubRun& r : p->runs) overrides.push_back(Override{p->t, r.y, r.x0, r.x1, v});
+        }
+    }
+    return 0;
+}
+
+// ---- numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src: @TYPE@_pairwise_sum, PW_BLOCKSIZE 128) ----
+static double pairwise(const double* a, long n) {
+    if (n < 8) {
+        double res = 0.;
+        for (long i = 0; i < n; ++i) res += a[i];
+        return res;
+    } else if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        long i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    } else {
+        long n2 = n / 2;
+        n2 -= n2 % 8;
+        return pairwise(a, n2) + pairwise(a + n2, n - n2);
+    }
+}
+
+double numpy_pairwise_sum(const double* a, long n) { return 0. + pairwise(a, n); }
+
+}  // namespace ctb

@@ -1,0 +1,126 @@
+/* contrack_b200.h -- C-ABI of the B200-native ConTrack tracking path.
+ *
+ * The reference (steidani/ConTrack) has no FFI/plugin layer: its boundary is the Python class method
+ * contrack.run_contrack (contrack/contrack.py:583-796) plus calc_clim / calc_anom (contrack.py:458-581).
+ * Every entry point below names the reference lines it replaces.  Python owns every caller buffer, the library
+ * never frees caller memory, no exception crosses the ABI: functions return 0 on success or a negative
+ * ct_status; ct_last_error() gives the message (thread-local).
+ *
+ * Conventions: cubes are C-order (time, lat, lon); "dev" pointers are CUDA device pointers on the context's
+ * device, "host" pointers are ordinary host memory.  A context is bound to one GPU, is not re-entrant and must be
+ * used from one host thread at a time.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef CONTRACK_B200_H
+#define CONTRACK_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ct_ctx ct_ctx;
+
+enum ct_status {
+    CT_OK = 0,
+    CT_ERR_ARG = -1,        /* bad argument (also: unknown `op`, the reference's ValueError at contrack.py:658/673) */
+    CT_ERR_CUDA = -2,       /* CUDA runtime error, or no usable GPU */
+    CT_ERR_CAPACITY = -3,   /* a size exceeds what the index types support (H, W > 65535; > 2^31-1 row-runs) */
+    CT_ERR_NEARTIE = -4,    /* overlap decision within rounding distance of the threshold on rows whose area weights
+                               are not exactly summable and the exact resolver could not decide */
+    CT_ERR_INTERNAL = -5
+};
+
+enum ct_dtype { CT_F32 = 0, CT_F64 = 1 };
+/* gorl of run_contrack (contrack.py:649-656, 664-671): '>=' / 'ge', '<=' / 'le', '>' / 'gt', '<' / 'lt' */
+enum ct_op { CT_GE = 0, CT_LE = 1, CT_GT = 2, CT_LT = 3 };
+
+/* Debug/parity stages for ct_run_contrack(): which intermediate array is painted into `flag`.
+ * Values painted for stages 1-4 are (index of a representative row-run + 1): compare PARTITIONS with the oracle. */
+enum ct_stage {
+    CT_STAGE_FINAL = 0,     /* ds['flag'] of contrack.py:776-791, ids identical to the reference */
+    CT_STAGE_LABEL2D = 1,   /* after contrack.py:684-687 (per-plane 8-connected components, no seam) */
+    CT_STAGE_SEAM2D = 2,    /* after contrack.py:691-698 (same-row date-line merge) */
+    CT_STAGE_FILTERED = 3,  /* after contrack.py:706-742 (overlap filter), class id or 0 */
+    CT_STAGE_LABEL3D = 4    /* after contrack.py:748-751: the scipy 3-D label ids themselves (exact ids) */
+};
+
+int ct_version(void);
+const char* ct_last_error(void);
+
+/* One context per GPU; owns all scratch (bit planes, run tables, component tables). */
+int ct_create(int device, ct_ctx** out);
+void ct_destroy(ct_ctx* ctx);
+/* Runtime switches: key "tma" (1 = cp.async.bulk staged threshold kernel, 0 = plain coalesced loads),
+ * "paint_tma" (bulk-store paint kernel).  Returns CT_ERR_ARG for unknown keys. */
+int ct_set_option(ct_ctx* ctx, const char* key, long value);
+
+/* ---- run_contrack, contrack.py:646-772 -------------------------------------------------------------------------
+ * anom       [T,H,W] float32/float64 on the device (ds[variable] transposed to time,lat,lon: contrack.py:677-681)
+ * w_host     [H] float64 area weight per latitude row, computed by the caller with the reference's expression
+ *            (contrack.py:703-704; float32 values widened to float64)
+ * thr_host   threshold(s): thr_n == 1 (numeric branch, contrack.py:663-674) or thr_n == T (DataArray/dayofyear
+ *            branch already gathered per time step, contrack.py:648-661)
+ * thr_is_f32 1: compare in float32 against (float)thr (numpy weak-scalar rule for a Python number vs a float32
+ *            array); 0: compare in float64
+ * flag_dev   [T,H,W] int32 out.  n_features (may be NULL) receives contrack.py:793's count.
+ */
+int ct_run_contrack(ct_ctx* ctx, const void* anom_dev, int in_dtype, long T, int H, int W,
+                    const double* w_host, const double* thr_host, long thr_n, int thr_is_f32, int op,
+                    double overlap, int persistence, int twosided,
+                    int32_t* flag_dev, long* n_features, int stage, void* stream);
+
+/* Same call with HOST buffers: streams time chunks host->device (threshold kernel consumes them; the float cube is
+ * never resident), runs the table phases, then paints and streams flag chunks device->host.  `chunk_planes` <= 0
+ * picks a default.  Host buffers should be page-locked for full PCIe rate (the call works with pageable memory). */
+int ct_run_contrack_host(ct_ctx* ctx, const void* anom_host, int in_dtype, long T, int H, int W,
+                         const double* w_host, const double* thr_host, long thr_n, int thr_is_f32, int op,
+                         double overlap, int persistence, int twosided,
+                         int32_t* flag_host, long* n_features, long chunk_planes);
+
+/* ---- statistics of the last run on this context (for bench.py / tests) ------------------------------------------
+ * keys: "runs", "comps2d", "kept_comps", "labels3d", "features", "seam_segments", "seam_events", "seam_splits",
+ *       "sweeps", "neartie_resolved", "kernel_launches",
+ *       "ms_threshold", "ms_paint" (CUDA-event time of the two streaming kernels in the last run, microseconds*1000)
+ * returns the value, or -1 for an unknown key. */
+double ct_get_stat(ct_ctx* ctx, const char* key);
+
+/* ---- host-only table phase (no GPU needed): seam merge with the bounding boxes taken BEFORE merging
+ * (contrack.py:753-763) followed by the persistence filter (contrack.py:765-772), on component tables.
+ * comp_* arrays describe the kept 2-D components in first-pixel (t,y,x) order; comp_label[] is the scipy 3-D label
+ * (1..N) of each.  seg_* are the date-line contact segments in (t,y) order: rows y0..y1-1 of plane t whose pixel at
+ * x=0 belongs to component seg_a and whose pixel at x=W-1 belongs to component seg_b.
+ * run_ptr/run_y/run_x0/run_x1 (CSR over components, x1 exclusive) may be NULL if no component needs splitting;
+ * then a needed split returns CT_ERR_INTERNAL.
+ * Outputs: comp_val[ncomp] final id per component (0 = removed; components that were split get 0 here and their
+ * pieces are reported as overrides); ovr_* (capacity ovr_cap) receive (t,y,x0,x1,value) sub-runs; *n_ovr their count.
+ */
+int ct_track_tables(long T, int H, int W, int persistence,
+                    long ncomp, const int32_t* comp_t, const int32_t* comp_y0, const int32_t* comp_y1,
+                    const int32_t* comp_x0, const int32_t* comp_x1, const int32_t* comp_label,
+                    long nseg, const int32_t* seg_t, const int32_t* seg_y0, const int32_t* seg_y1,
+                    const int32_t* seg_a, const int32_t* seg_b,
+                    const int64_t* run_ptr, const int32_t* run_y, const int32_t* run_x0, const int32_t* run_x1,
+                    int32_t* comp_val, long ovr_cap, int32_t* ovr_t, int32_t* ovr_y, int32_t* ovr_x0,
+                    int32_t* ovr_x1, int32_t* ovr_val, long* n_ovr, long* n_features, long* n_events, long* n_splits);
+
+/* numpy's float64 pairwise summation (the order np.sum uses on a contiguous 1-D array) over a run-length encoded
+ * sequence: value[i] repeated count[i] times.  Used by the near-tie resolver; exported for the parity test. */
+double ct_numpy_pairwise_sum_rle(const double* value, const int64_t* count, long n);
+
+/* ---- calc_clim / calc_anom, contrack.py:458-581 (float32, tolerance parity) --------------------------------------
+ * z_dev [T,H,W] float32; group_host [T] int32 group index 0..G-1 of each time step (dayofyear rank);
+ * clim_dev [G,H,W] float32 out: group mean (skip-NaN) -> centred rolling mean (window, min_periods = window) ->
+ * NaN edges filled with the mean of the last `window` unsmoothed group means (contrack.py:483-489). */
+int ct_calc_clim(ct_ctx* ctx, const float* z_dev, long T, int H, int W, const int32_t* group_host, int G,
+                 int window, float* clim_dev, void* stream);
+/* anom_dev [T,H,W] float32 out = centred rolling mean over time (window `smooth`) of z[t] - clim[group[t]]
+ * (contrack.py:568-570). */
+int ct_calc_anom(ct_ctx* ctx, const float* z_dev, long T, int H, int W, const int32_t* group_host, int G,
+                 const float* clim_dev, int smooth, float* anom_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONTRACK_B200_H */

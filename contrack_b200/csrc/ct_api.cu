@@ -1,0 +1,709 @@
+// ct_api.cu -- C-ABI of the library (include/contrack_b200.h): context, device scratch, orchestration.
+//
+// ct_run_contrack = threshold_bits -> scans -> extract_runs -> ccl -> component / pair / date-line tables (all CUDA,
+// ct_kernels.cu) -> tables to the host -> ordered table phase (ct_host.cpp, ct_tables.cpp) -> per-component value back to
+// the device -> paint.  Reference: contrack/contrack.py:646-791.
+#include "../../include/contrack_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ct_host.h"
+#include "ct_kernels.h"
+#include "ct_tables.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CT_CUDA(expr)                                                                                                \
+    do {                                                                                                             \
+        cudaError_t e__ = (expr);                                                                                    \
+        if (e__ != cudaSuccess)                                                                                      \
+            return fail(CT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);   \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct ct_ctx {
+    int device = 0, sm_count = 148;
+    long opt_tma = 0, opt_paint_tma = 0;
+    // geometry of the last run
+    long T = 0; int H = 0, W = 0, Ww = 0;
+    long nruns = 0, ncomp = 0, npair = 0, nseam = 0, novr = 0;
+    // device scratch
+    DevBuf bits, row_cnt, seam_flag, row_ptr, seam_pos, scan_tmp, counters;
+    DevBuf run_x, run_row, parent, root_flag, rank, run_comp, run_val;
+    DevBuf c_t, c_y0, c_y1, c_x0, c_x1, c_E, c_S, c_nsp, c_cls, c_val;
+    DevBuf s_row, s_a, s_b;
+    DevBuf h_key, h_npix, h_nsp, h_E, h_S;
+    DevBuf p_a, p_b, p_npix, p_nsp, p_E, p_S;
+    DevBuf o_t, o_y, o_x0, o_x1, o_val;
+    DevBuf w_dev, special_dev, thr_dev;
+    DevBuf chunk_in[2], chunk_out[2];
+    // pinned host staging
+    PinBuf hp_counters, hp_tables, hp_val;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr, work_stream = nullptr;
+    std::map<std::string, double> stats;
+    std::vector<double> w_host;
+    long launches = 0;
+};
+
+namespace {
+
+struct DeviceRunSource : cth::RunSource {
+    ct_ctx* c;
+    cudaStream_t st;
+    bool plane_runs(long t, std::vector<cth::PlaneRun>& out) override {
+        out.clear();
+        const int H = c->H;
+        std::vector<uint32_t> rp(H + 1);
+        if (cudaMemcpyAsync(rp.data(), c->row_ptr.as<uint32_t>() + t * H, (H + 1) * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+        const uint32_t r0 = rp[0], n = rp[H] - rp[0];
+        if (n == 0) return true;
+        std::vector<uint32_t> rx(n), rc(n);
+        if (cudaMemcpyAsync(rx.data(), c->run_x.as<uint32_t>() + r0, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st)
+            != cudaSuccess) return false;
+        if (cudaMemcpyAsync(rc.data(), c->run_comp.as<uint32_t>() + r0, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st)
+            != cudaSuccess) return false;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+        out.resize(n);
+        int y = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            while (rp[y + 1] - r0 <= i) ++y;
+            out[i] = cth::PlaneRun{y, (int)(rx[i] & 0xffff), (int)(rx[i] >> 16), rc[i]};
+        }
+        return true;
+    }
+};
+
+// Rows whose weights can be summed exactly in float64 in ANY order (so atomics give numpy's value bit for bit):
+// all partial sums are multiples of 2^lb_min and bounded by W * sum|w| < 2^(53 + lb_min).  Rows with the lowest
+// set bits (the pole rows, cos(float32(pi/2)) ~ -4.4e-8) are taken out until that holds; their pixels are
+// accumulated separately and any decision that involves them is guarded (ct_host.cpp).
+void classify_rows(const double* w, int H, int W, std::vector<uint8_t>& special) {
+    special.assign(H, 0);
+    std::vector<int> lb(H, INT32_MAX);
+    std::vector<int> order;
+    for (int y = 0; y < H; ++y) {
+        const double a = std::fabs(w[y]);
+        if (a == 0.0) continue;
+        if (!std::isfinite(a)) { special[y] = 1; continue; }
+        int e;
+        const double m = std::frexp(a, &e);                           // a = m * 2^e, m in [0.5, 1)
+        unsigned long long mi = (unsigned long long)std::ldexp(m, 53);
+        lb[y] = e - 53 + __builtin_ctzll(mi);
+        order.push_back(y);
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return lb[a] < lb[b]; });
+    size_t first = 0;                                                 // order[first..] is the exact set
+    while (first < order.size()) {
+        double bound = 0.0;
+        for (size_t i = first; i < order.size(); ++i) bound += std::fabs(w[order[i]]) * (double)W;
+        const int lbmin = lb[order[first]];
+        if (bound < std::ldexp(1.0, 53 + lbmin)) break;
+        special[order[first]] = 1;
+        ++first;
+    }
+}
+
+uint32_t next_pow2(uint64_t v) {
+    uint64_t p = 1024;
+    while (p < v && p < (1ull << 31)) p <<= 1;
+    return (uint32_t)p;
+}
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int check_args(long T, int H, int W, const double* w_host, const double* thr_host, long thr_n, int in_dtype, int op) {
+    if (T < 0 || H <= 0 || W <= 0) return fail(CT_ERR_ARG, "bad shape T=%ld H=%d W=%d", T, H, W);
+    if (H > 65535 || W > 65535) return fail(CT_ERR_CAPACITY, "H and W must be <= 65535 (got %d x %d)", H, W);
+    if ((double)T * H >= 2147483647.0) return fail(CT_ERR_CAPACITY, "T*H must be < 2^31");
+    if (!w_host || !thr_host) return fail(CT_ERR_ARG, "null weight / threshold pointer");
+    if (thr_n != 1 && thr_n != T) return fail(CT_ERR_ARG, "thr_n must be 1 or T");
+    if (in_dtype != CT_F32 && in_dtype != CT_F64) return fail(CT_ERR_ARG, "in_dtype must be CT_F32 or CT_F64");
+    if (op < CT_GE || op > CT_LT) return fail(CT_ERR_ARG, " Please select from [>, >=, <, >=] for gorl");
+    return CT_OK;
+}
+
+// upload weights / special-row map / thresholds; size the row-indexed scratch
+int prepare(ct_ctx* c, long T, int H, int W, const double* w_host, const double* thr_host, long thr_n,
+            cudaStream_t st) {
+    c->T = T; c->H = H; c->W = W; c->Ww = (W + 31) / 32;
+    const long nrows = T * H;
+    c->w_host.assign(w_host, w_host + H);
+    std::vector<uint8_t> special;
+    classify_rows(w_host, H, W, special);
+    long nspecial = 0;
+    for (uint8_t s : special) nspecial += s;
+    c->stats["special_rows"] = (double)nspecial;
+    CT_CUDA(c->w_dev.ensure(H * sizeof(double)));
+    CT_CUDA(c->special_dev.ensure(H));
+    CT_CUDA(c->thr_dev.ensure(thr_n * sizeof(double)));
+    CT_CUDA(cudaMemcpyAsync(c->w_dev.p, w_host, H * sizeof(double), cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaMemcpyAsync(c->special_dev.p, special.data(), H, cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaMemcpyAsync(c->thr_dev.p, thr_host, thr_n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaStreamSynchronize(st));                               // `special` is a local
+    CT_CUDA(c->bits.ensure((size_t)nrows * c->Ww * sizeof(uint32_t)));
+    CT_CUDA(c->row_cnt.ensure((size_t)nrows * sizeof(uint32_t)));
+    CT_CUDA(c->seam_flag.ensure((size_t)nrows * sizeof(uint32_t)));
+    CT_CUDA(c->row_ptr.ensure((size_t)(nrows + 1) * sizeof(uint32_t)));
+    CT_CUDA(c->seam_pos.ensure((size_t)(nrows + 1) * sizeof(uint32_t)));
+    CT_CUDA(c->counters.ensure(64));
+    CT_CUDA(c->hp_counters.ensure(64));
+    for (auto& e : c->ev) if (!e) CT_CUDA(cudaEventCreate(&e));
+    c->launches = 0;
+    return CT_OK;
+}
+
+int launch_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long t0, long nt, long thr_n, int thr_is_f32,
+                     int op, cudaStream_t st) {
+    ctk::ThresholdArgs a;
+    a.anom = anom_dev; a.in_dtype = in_dtype; a.T = nt; a.H = c->H; a.W = c->W; a.Ww = c->Ww;
+    a.thr_dev = thr_n == 1 ? c->thr_dev.as<double>() : c->thr_dev.as<double>() + t0;
+    a.thr_n = thr_n; a.thr_is_f32 = thr_is_f32; a.op = op;
+    const long r0 = t0 * c->H;
+    a.bits = c->bits.as<uint32_t>() + (size_t)r0 * c->Ww;
+    a.row_cnt = c->row_cnt.as<uint32_t>() + r0;
+    a.seam_flag = c->seam_flag.as<uint32_t>() + r0;
+    a.variant = (int)c->opt_tma;
+    CT_CUDA(ctk::threshold_bits(a, c->sm_count, st));
+    c->launches += 1;
+    return CT_OK;
+}
+
+// Everything between the two cube-sized kernels.  On return c_val (value per component) and the override sub-runs are on
+// the device.
+int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int stage, long* n_features, cudaStream_t st) {
+    const long nrows = c->T * c->H;
+    const int H = c->H, W = c->W;
+    uint32_t* cnt_dev = c->counters.as<uint32_t>();
+    uint32_t* cnt_host = c->hp_counters.as<uint32_t>();
+
+    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(nrows > 1024 ? nrows : 1024) * sizeof(uint32_t)));
+    CT_CUDA(ctk::exclusive_scan_u32(c->row_cnt.as<uint32_t>(), c->row_ptr.as<uint32_t>(), nrows,
+                                    c->scan_tmp.as<uint32_t>(), st));
+    CT_CUDA(ctk::exclusive_scan_u32(c->seam_flag.as<uint32_t>(), c->seam_pos.as<uint32_t>(), nrows,
+                                    c->scan_tmp.as<uint32_t>(), st));
+    c->launches += 6;
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 0, c->row_ptr.as<uint32_t>() + nrows, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 1, c->seam_pos.as<uint32_t>() + nrows, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaStreamSynchronize(st));
+    const long R = cnt_host[0], nseam = cnt_host[1];
+    c->nruns = R; c->nseam = nseam;
+
+    // ---- runs + 2-D components ----
+    const size_t rb = (size_t)(R + 1) * sizeof(uint32_t);
+    CT_CUDA(c->run_x.ensure(rb)); CT_CUDA(c->run_row.ensure(rb)); CT_CUDA(c->parent.ensure(rb));
+    CT_CUDA(c->root_flag.ensure(rb)); CT_CUDA(c->rank.ensure(rb + 4)); CT_CUDA(c->run_comp.ensure(rb));
+    CT_CUDA(c->run_val.ensure(rb));
+    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(R > nrows ? R : nrows) * sizeof(uint32_t)));
+    CT_CUDA(ctk::extract_runs(c->bits.as<uint32_t>(), c->row_ptr.as<uint32_t>(), nrows, c->Ww, c->run_x.as<uint32_t>(),
+                              c->run_row.as<uint32_t>(), st));
+    CT_CUDA(ctk::ccl_init(c->parent.as<uint32_t>(), R, st));
+    CT_CUDA(ctk::ccl_union(c->row_ptr.as<uint32_t>(), c->run_x.as<uint32_t>(), c->run_row.as<uint32_t>(), R, H,
+                           c->parent.as<uint32_t>(), st));
+    CT_CUDA(ctk::ccl_flatten(c->parent.as<uint32_t>(), c->root_flag.as<uint32_t>(), R, st));
+    CT_CUDA(ctk::exclusive_scan_u32(c->root_flag.as<uint32_t>(), c->rank.as<uint32_t>(), R, c->scan_tmp.as<uint32_t>(),
+                                    st));
+    c->launches += 7;
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 2, c->rank.as<uint32_t>() + R, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaStreamSynchronize(st));
+    const long nc = cnt_host[2];
+    c->ncomp = nc;
+
+    // ---- component, date-line and pair tables ----
+    CT_CUDA(ctk::ccl_assign(c->parent.as<uint32_t>(), c->rank.as<uint32_t>(), c->run_comp.as<uint32_t>(), R, st));
+    const size_t cb4 = (size_t)(nc + 1) * 4, cb8 = (size_t)(nc + 1) * 8;
+    CT_CUDA(c->c_t.ensure(cb4)); CT_CUDA(c->c_y0.ensure(cb4)); CT_CUDA(c->c_y1.ensure(cb4));
+    CT_CUDA(c->c_x0.ensure(cb4)); CT_CUDA(c->c_x1.ensure(cb4)); CT_CUDA(c->c_E.ensure(cb8));
+    CT_CUDA(c->c_S.ensure(cb8)); CT_CUDA(c->c_nsp.ensure(cb4)); CT_CUDA(c->c_cls.ensure(cb4));
+    CT_CUDA(c->c_val.ensure(cb4));
+    ctk::CompTables ct;
+    ct.t = c->c_t.as<int32_t>(); ct.y0 = c->c_y0.as<int32_t>(); ct.y1 = c->c_y1.as<int32_t>();
+    ct.x0 = c->c_x0.as<int32_t>(); ct.x1 = c->c_x1.as<int32_t>(); ct.areaE = c->c_E.as<double>();
+    ct.areaS = c->c_S.as<double>(); ct.nsp = c->c_nsp.as<uint32_t>(); ct.cls = c->c_cls.as<uint32_t>();
+    CT_CUDA(ctk::comp_init(ct, nc, W, st));
+    CT_CUDA(ctk::comp_accumulate(c->run_x.as<uint32_t>(), c->run_row.as<uint32_t>(), c->run_comp.as<uint32_t>(), R, H,
+                                 c->w_dev.as<double>(), c->special_dev.as<uint8_t>(), ct, st));
+    const size_t sb = (size_t)(nseam + 1) * 4;
+    CT_CUDA(c->s_row.ensure(sb)); CT_CUDA(c->s_a.ensure(sb)); CT_CUDA(c->s_b.ensure(sb));
+    CT_CUDA(ctk::seam_rows(c->seam_flag.as<uint32_t>(), c->seam_pos.as<uint32_t>(), c->row_ptr.as<uint32_t>(),
+                           c->run_comp.as<uint32_t>(), nrows, c->s_row.as<uint32_t>(), c->s_a.as<uint32_t>(),
+                           c->s_b.as<uint32_t>(), ct.cls, st));
+    CT_CUDA(ctk::cls_flatten(ct.cls, nc, st));
+    c->launches += 5;
+
+    long np = 0;
+    uint64_t want = (uint64_t)nc * 4;
+    for (int attempt = 0;; ++attempt) {
+        ctk::PairTable pt;
+        pt.cap = next_pow2(want);
+        CT_CUDA(c->h_key.ensure((size_t)pt.cap * 8)); CT_CUDA(c->h_npix.ensure((size_t)pt.cap * 4));
+        CT_CUDA(c->h_nsp.ensure((size_t)pt.cap * 4)); CT_CUDA(c->h_E.ensure((size_t)pt.cap * 8));
+        CT_CUDA(c->h_S.ensure((size_t)pt.cap * 8));
+        pt.key = c->h_key.as<unsigned long long>(); pt.npix = c->h_npix.as<uint32_t>();
+        pt.nsp = c->h_nsp.as<uint32_t>(); pt.areaE = c->h_E.as<double>(); pt.areaS = c->h_S.as<double>();
+        pt.overflow = cnt_dev + 4;
+        const uint32_t out_cap = pt.cap;
+        CT_CUDA(c->p_a.ensure((size_t)out_cap * 4)); CT_CUDA(c->p_b.ensure((size_t)out_cap * 4));
+        CT_CUDA(c->p_npix.ensure((size_t)out_cap * 4)); CT_CUDA(c->p_nsp.ensure((size_t)out_cap * 4));
+        CT_CUDA(c->p_E.ensure((size_t)out_cap * 8)); CT_CUDA(c->p_S.ensure((size_t)out_cap * 8));
+        CT_CUDA(ctk::pairs_init(pt, st));
+        CT_CUDA(ctk::pairs_accumulate(c->row_ptr.as<uint32_t>(), c->run_x.as<uint32_t>(), c->run_row.as<uint32_t>(),
+                                      c->run_comp.as<uint32_t>(), R, H, c->w_dev.as<double>(),
+                                      c->special_dev.as<uint8_t>(), pt, st));
+        CT_CUDA(ctk::pairs_compact(pt, c->p_a.as<uint32_t>(), c->p_b.as<uint32_t>(), c->p_npix.as<uint32_t>(),
+                                   c->p_nsp.as<uint32_t>(), c->p_E.as<double>(), c->p_S.as<double>(), out_cap,
+                                   cnt_dev + 5, st));
+        c->launches += 3;
+        CT_CUDA(cudaMemcpyAsync(cnt_host + 4, cnt_dev + 4, 8, cudaMemcpyDeviceToHost, st));
+        CT_CUDA(cudaStreamSynchronize(st));
+        if (cnt_host[4] == 0 && (uint64_t)cnt_host[5] * 10 <= (uint64_t)pt.cap * 7) { np = cnt_host[5]; break; }
+        if (attempt >= 6 || pt.cap >= (1u << 31)) return fail(CT_ERR_CAPACITY, "pair table overflow");
+        want = (uint64_t)pt.cap * 4;                                  // too full: probing would crawl
+    }
+    c->npair = np;
+    CT_CUDA(cudaEventRecord(c->ev[2], st));
+
+    // ---- tables -> host ----
+    // layout in the pinned buffer: 9 component arrays, 6 pair arrays, 3 date-line arrays (8-byte arrays first)
+    const size_t ncp = (size_t)nc + 2, npp = (size_t)np + 2, nsp_ = (size_t)nseam + 2;
+    size_t bytes = ncp * (2 * 8 + 7 * 4) + npp * (2 * 8 + 4 * 4) + nsp_ * 3 * 4 + 256;
+    CT_CUDA(c->hp_tables.ensure(bytes));
+    char* base = c->hp_tables.as<char>();
+    size_t off = 0;
+    auto take = [&](size_t n, size_t elt) { void* p = base + off; off += ((n * elt + 15) / 16) * 16; return p; };
+    double* hE = (double*)take(ncp, 8); double* hS = (double*)take(ncp, 8);
+    double* hpE = (double*)take(npp, 8); double* hpS = (double*)take(npp, 8);
+    int32_t* ht = (int32_t*)take(ncp, 4); int32_t* hy0 = (int32_t*)take(ncp, 4); int32_t* hy1 = (int32_t*)take(ncp, 4);
+    int32_t* hx0 = (int32_t*)take(ncp, 4); int32_t* hx1 = (int32_t*)take(ncp, 4);
+    uint32_t* hnsp = (uint32_t*)take(ncp, 4); uint32_t* hcls = (uint32_t*)take(ncp, 4);
+    uint32_t* hpa = (uint32_t*)take(npp, 4); uint32_t* hpb = (uint32_t*)take(npp, 4);
+    uint32_t* hpn = (uint32_t*)take(npp, 4); uint32_t* hpnsp = (uint32_t*)take(npp, 4);
+    uint32_t* hsr = (uint32_t*)take(nsp_, 4); uint32_t* hsa = (uint32_t*)take(nsp_, 4);
+    uint32_t* hsb = (uint32_t*)take(nsp_, 4);
+    if (off > c->hp_tables.cap) return fail(CT_ERR_INTERNAL, "staging layout overflow");
+#define CT_D2H(dst, src, n, elt) \
+    if ((n) > 0) CT_CUDA(cudaMemcpyAsync(dst, (src).p, (size_t)(n) * (elt), cudaMemcpyDeviceToHost, st))
+    CT_D2H(hE, c->c_E, nc, 8); CT_D2H(hS, c->c_S, nc, 8); CT_D2H(ht, c->c_t, nc, 4); CT_D2H(hy0, c->c_y0, nc, 4);
+    CT_D2H(hy1, c->c_y1, nc, 4); CT_D2H(hx0, c->c_x0, nc, 4); CT_D2H(hx1, c->c_x1, nc, 4);
+    CT_D2H(hnsp, c->c_nsp, nc, 4); CT_D2H(hcls, c->c_cls, nc, 4);
+    CT_D2H(hpE, c->p_E, np, 8); CT_D2H(hpS, c->p_S, np, 8); CT_D2H(hpa, c->p_a, np, 4); CT_D2H(hpb, c->p_b, np, 4);
+    CT_D2H(hpn, c->p_npix, np, 4); CT_D2H(hpnsp, c->p_nsp, np, 4);
+    CT_D2H(hsr, c->s_row, nseam, 4); CT_D2H(hsa, c->s_a, nseam, 4); CT_D2H(hsb, c->s_b, nseam, 4);
+#undef CT_D2H
+    CT_CUDA(cudaStreamSynchronize(st));
+
+    // ---- ordered table phase on the host ----
+    const double t_host0 = now_ms();
+    cth::Tables tb;
+    tb.T = c->T; tb.H = H; tb.W = W;
+    tb.ncomp = nc; tb.comp_t = ht; tb.comp_y0 = hy0; tb.comp_y1 = hy1; tb.comp_x0 = hx0; tb.comp_x1 = hx1;
+    tb.comp_cls = hcls; tb.comp_areaE = hE; tb.comp_areaS = hS; tb.comp_nsp = hnsp;
+    tb.npair = np; tb.pair_a = hpa; tb.pair_b = hpb; tb.pair_npix = hpn; tb.pair_nsp = hpnsp;
+    tb.pair_areaE = hpE; tb.pair_areaS = hpS;
+    tb.nseam = nseam; tb.seam_row = hsr; tb.seam_a = hsa; tb.seam_b = hsb;
+    tb.w = c->w_host.data();
+    cth::Params pr;
+    pr.overlap = overlap; pr.persistence = persistence; pr.twosided = twosided; pr.stage = stage;
+    DeviceRunSource src;
+    src.c = c; src.st = st;
+    cth::Result res;
+    std::string err;
+    int rc = cth::host_phase(tb, pr, &src, res, err);
+    if (rc != 0) return fail(rc, "%s", err.c_str());
+    c->stats["ms_host_tables"] = now_ms() - t_host0;
+
+    // ---- values back to the device ----
+    const long novr = (long)res.overrides.size();
+    c->novr = novr;
+    CT_CUDA(c->hp_val.ensure((size_t)(nc + 1) * 4 + (size_t)(novr + 1) * 5 * 4));
+    int32_t* hv = c->hp_val.as<int32_t>();
+    if (nc) memcpy(hv, res.comp_val.data(), (size_t)nc * 4);
+    if (nc) CT_CUDA(cudaMemcpyAsync(c->c_val.p, hv, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+    if (novr) {
+        int32_t* ho = hv + nc + 1;
+        for (long i = 0; i < novr; ++i) {
+            const ctb::Override& o = res.overrides[i];
+            ho[i] = o.t; ho[novr + i] = o.y; ho[2 * novr + i] = o.x0; ho[3 * novr + i] = o.x1; ho[4 * novr + i] = o.val;
+        }
+        const size_t ob = (size_t)novr * 4;
+        CT_CUDA(c->o_t.ensure(ob)); CT_CUDA(c->o_y.ensure(ob)); CT_CUDA(c->o_x0.ensure(ob));
+        CT_CUDA(c->o_x1.ensure(ob)); CT_CUDA(c->o_val.ensure(ob));
+        CT_CUDA(cudaMemcpyAsync(c->o_t.p, ho, ob, cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaMemcpyAsync(c->o_y.p, ho + novr, ob, cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaMemcpyAsync(c->o_x0.p, ho + 2 * novr, ob, cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaMemcpyAsync(c->o_x1.p, ho + 3 * novr, ob, cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaMemcpyAsync(c->o_val.p, ho + 4 * novr, ob, cudaMemcpyHostToDevice, st));
+    }
+    CT_CUDA(ctk::run_values(c->run_comp.as<uint32_t>(), c->c_val.as<int32_t>(), c->run_val.as<int32_t>(), R, st));
+    c->launches += 1;
+
+    c->stats["runs"] = (double)R; c->stats["comps2d"] = (double)nc; c->stats["pairs"] = (double)np;
+    c->stats["seam_rows"] = (double)nseam; c->stats["kept_comps"] = (double)res.n_kept;
+    c->stats["labels3d"] = (double)res.n_labels3d; c->stats["features"] = (double)res.n_features;
+    c->stats["seam_events"] = (double)res.n_seam_events; c->stats["seam_splits"] = (double)res.n_seam_splits;
+    c->stats["neartie_resolved"] = (double)res.n_neartie; c->stats["override_runs"] = (double)novr;
+    if (n_features) *n_features = res.n_features;
+    return CT_OK;
+}
+
+// paint planes [t0, t0+nt) into `flag_dev` (which starts at plane t0)
+int launch_paint(ct_ctx* c, long t0, long nt, int32_t* flag_dev, cudaStream_t st) {
+    ctk::PaintArgs a;
+    const long r0 = t0 * c->H;
+    a.bits = c->bits.as<uint32_t>() + (size_t)r0 * c->Ww;
+    a.row_ptr = c->row_ptr.as<uint32_t>() + r0;
+    a.run_val = c->run_val.as<int32_t>();
+    a.nrows = nt * c->H; a.W = c->W; a.Ww = c->Ww; a.flag = flag_dev;
+    CT_CUDA(ctk::paint(a, c->sm_count, st));
+    c->launches += 1;
+    return CT_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ct_version(void) { return 100; }
+
+const char* ct_last_error(void) { return g_err.c_str(); }
+
+int ct_create(int device, ct_ctx** out) {
+    if (!out) return fail(CT_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(CT_ERR_CUDA, "no usable CUDA device (%s)", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(CT_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    CT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(CT_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    ct_ctx* c = new ct_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return CT_OK;
+}
+
+void ct_destroy(ct_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    DevBuf* bufs[] = {&c->bits, &c->row_cnt, &c->seam_flag, &c->row_ptr, &c->seam_pos, &c->scan_tmp, &c->counters,
+                      &c->run_x, &c->run_row, &c->parent, &c->root_flag, &c->rank, &c->run_comp, &c->run_val,
+                      &c->c_t, &c->c_y0, &c->c_y1, &c->c_x0, &c->c_x1, &c->c_E, &c->c_S, &c->c_nsp, &c->c_cls, &c->c_val,
+                      &c->s_row, &c->s_a, &c->s_b, &c->h_key, &c->h_npix, &c->h_nsp, &c->h_E, &c->h_S,
+                      &c->p_a, &c->p_b, &c->p_npix, &c->p_nsp, &c->p_E, &c->p_S,
+                      &c->o_t, &c->o_y, &c->o_x0, &c->o_x1, &c->o_val, &c->w_dev, &c->special_dev, &c->thr_dev,
+                      &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0], &c->chunk_out[1]};
+    for (DevBuf* b : bufs) b->release();
+    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release();
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->work_stream) cudaStreamDestroy(c->work_stream);
+    delete c;
+}
+
+int ct_set_option(ct_ctx* c, const char* key, long value) {
+    if (!c || !key) return fail(CT_ERR_ARG, "null argument");
+    if (!strcmp(key, "tma")) { c->opt_tma = value; return CT_OK; }
+    if (!strcmp(key, "paint_tma")) { c->opt_paint_tma = value; return CT_OK; }
+    return fail(CT_ERR_ARG, "unknown option '%s'", key);
+}
+
+int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H, int W, const double* w_host,
+                    const double* thr_host, long thr_n, int thr_is_f32, int op, double overlap, int persistence,
+                    int twosided, int32_t* flag_dev, long* n_features, int stage, void* stream) {
+    if (!c) return fail(CT_ERR_ARG, "null context");
+    int rc = check_args(T, H, W, w_host, thr_host, thr_n, in_dtype, op);
+    if (rc != CT_OK) return rc;
+    if (stage < CT_STAGE_FINAL || stage > CT_STAGE_LABEL3D) return fail(CT_ERR_ARG, "bad stage %d", stage);
+    if (n_features) *n_features = 0;
+    if (T == 0) return CT_OK;
+    if (!anom_dev || !flag_dev) return fail(CT_ERR_ARG, "null device pointer");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    c->stats.clear();
+    if ((rc = prepare(c, T, H, W, w_host, thr_host, thr_n, st)) != CT_OK) return rc;
+    CT_CUDA(cudaEventRecord(c->ev[0], st));
+    if ((rc = launch_threshold(c, anom_dev, in_dtype, 0, T, thr_n, thr_is_f32, op, st)) != CT_OK) return rc;
+    CT_CUDA(cudaEventRecord(c->ev[1], st));
+    if ((rc = table_phase(c, overlap, persistence, twosided, stage, n_features, st)) != CT_OK) return rc;
+    CT_CUDA(cudaEventRecord(c->ev[3], st));
+    if ((rc = launch_paint(c, 0, T, flag_dev, st)) != CT_OK) return rc;
+    if (c->novr) {
+        CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
+                                     c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), c->novr, H, W, 0, T, flag_dev, st));
+        c->launches += 1;
+    }
+    CT_CUDA(cudaEventRecord(c->ev[4], st));
+    CT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats["ms_threshold"] = ms;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats["ms_tables_gpu"] = ms;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stats["ms_tables_host_roundtrip"] = ms;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats["ms_paint"] = ms;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats["ms_total"] = ms;
+    c->stats["kernel_launches"] = (double)c->launches;
+    return CT_OK;
+}
+
+int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T, int H, int W, const double* w_host,
+                         const double* thr_host, long thr_n, int thr_is_f32, int op, double overlap, int persistence,
+                         int twosided, int32_t* flag_host, long* n_features, long chunk_planes) {
+    if (!c) return fail(CT_ERR_ARG, "null context");
+    int rc = check_args(T, H, W, w_host, thr_host, thr_n, in_dtype, op);
+    if (rc != CT_OK) return rc;
+    if (n_features) *n_features = 0;
+    if (T == 0) return CT_OK;
+    if (!anom_host || !flag_host) return fail(CT_ERR_ARG, "null host pointer");
+    CT_CUDA(cudaSetDevice(c->device));
+    if (!c->copy_stream) CT_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->work_stream) CT_CUDA(cudaStreamCreateWithFlags(&c->work_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = c->copy_stream, ws = c->work_stream;
+    c->stats.clear();
+    if ((rc = prepare(c, T, H, W, w_host, thr_host, thr_n, ws)) != CT_OK) return rc;
+    const size_t esz = in_dtype == CT_F64 ? 8 : 4;
+    const size_t plane = (size_t)H * W;
+    if (chunk_planes <= 0) {
+        chunk_planes = (long)((256u << 20) / (plane * esz));
+        if (chunk_planes < 1) chunk_planes = 1;
+    }
+    if (chunk_planes > T) chunk_planes = T;
+    const long nchunks = (T + chunk_planes - 1) / chunk_planes;
+    cudaEvent_t in_ready[2], in_free[2];
+    for (int i = 0; i < 2; ++i) {
+        CT_CUDA(cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming));
+        CT_CUDA(cudaEventCreateWithFlags(&in_free[i], cudaEventDisableTiming));
+        CT_CUDA(c->chunk_in[i].ensure((size_t)chunk_planes * plane * esz));
+    }
+    const double t0_ms = now_ms();
+    // ---- stream the cube in: copy chunk k+1 while chunk k is thresholded; the float cube is never resident ----
+    for (long k = 0; k < nchunks; ++k) {
+        const int s = (int)(k & 1);
+        const long t0 = k * chunk_planes, nt = (t0 + chunk_planes <= T) ? chunk_planes : T - t0;
+        if (k >= 2) CT_CUDA(cudaStreamWaitEvent(cs, in_free[s], 0));
+        CT_CUDA(cudaMemcpyAsync(c->chunk_in[s].p, (const char*)anom_host + (size_t)t0 * plane * esz,
+                                (size_t)nt * plane * esz, cudaMemcpyHostToDevice, cs));
+        CT_CUDA(cudaEventRecord(in_ready[s], cs));
+        CT_CUDA(cudaStreamWaitEvent(ws, in_ready[s], 0));
+        if ((rc = launch_threshold(c, c->chunk_in[s].p, in_dtype, t0, nt, thr_n, thr_is_f32, op, ws)) != CT_OK) return rc;
+        CT_CUDA(cudaEventRecord(in_free[s], ws));
+    }
+    CT_CUDA(cudaStreamSynchronize(ws));
+    const double t1_ms = now_ms();
+    c->chunk_in[0].release(); c->chunk_in[1].release();
+    if ((rc = table_phase(c, overlap, persistence, twosided, CT_STAGE_FINAL, n_features, ws)) != CT_OK) return rc;
+    CT_CUDA(cudaStreamSynchronize(ws));
+    const double t2_ms = now_ms();
+    // ---- paint chunk k+1 while chunk k travels back ----
+    const long out_planes = std::max(1L, std::min(T, (long)((256u << 20) / (plane * 4))));
+    const long nout = (T + out_planes - 1) / out_planes;
+    cudaEvent_t out_ready[2], out_free[2];
+    for (int i = 0; i < 2; ++i) {
+        CT_CUDA(cudaEventCreateWithFlags(&out_ready[i], cudaEventDisableTiming));
+        CT_CUDA(cudaEventCreateWithFlags(&out_free[i], cudaEventDisableTiming));
+        CT_CUDA(c->chunk_out[i].ensure((size_t)out_planes * plane * 4));
+    }
+    for (long k = 0; k < nout; ++k) {
+        const int s = (int)(k & 1);
+        const long t0 = k * out_planes, nt = (t0 + out_planes <= T) ? out_planes : T - t0;
+        if (k >= 2) CT_CUDA(cudaStreamWaitEvent(ws, out_free[s], 0));
+        int32_t* dst = c->chunk_out[s].as<int32_t>();
+        if ((rc = launch_paint(c, t0, nt, dst, ws)) != CT_OK) return rc;
+        if (c->novr) {
+            CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
+                                         c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), c->novr, H, W, t0, t0 + nt,
+                                         dst, ws));
+            c->launches += 1;
+        }
+        CT_CUDA(cudaEventRecord(out_ready[s], ws));
+        CT_CUDA(cudaStreamWaitEvent(cs, out_ready[s], 0));
+        CT_CUDA(cudaMemcpyAsync(flag_host + (size_t)t0 * plane, dst, (size_t)nt * plane * 4, cudaMemcpyDeviceToHost, cs));
+        CT_CUDA(cudaEventRecord(out_free[s], cs));
+    }
+    CT_CUDA(cudaStreamSynchronize(cs));
+    CT_CUDA(cudaStreamSynchronize(ws));
+    const double t3_ms = now_ms();
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(in_ready[i]); cudaEventDestroy(in_free[i]);
+        cudaEventDestroy(out_ready[i]); cudaEventDestroy(out_free[i]);
+    }
+    c->stats["ms_h2d_threshold"] = t1_ms - t0_ms;
+    c->stats["ms_tables"] = t2_ms - t1_ms;
+    c->stats["ms_paint_d2h"] = t3_ms - t2_ms;
+    c->stats["ms_total"] = t3_ms - t0_ms;
+    c->stats["kernel_launches"] = (double)c->launches;
+    return CT_OK;
+}
+
+double ct_get_stat(ct_ctx* c, const char* key) {
+    if (!c || !key) return -1;
+    auto it = c->stats.find(key);
+    return it == c->stats.end() ? -1 : it->second;
+}
+
+int ct_track_tables(long T, int H, int W, int persistence, long ncomp, const int32_t* comp_t, const int32_t* comp_y0,
+                    const int32_t* comp_y1, const int32_t* comp_x0, const int32_t* comp_x1, const int32_t* comp_label,
+                    long nseg, const int32_t* seg_t, const int32_t* seg_y0, const int32_t* seg_y1, const int32_t* seg_a,
+                    const int32_t* seg_b, const int64_t* run_ptr, const int32_t* run_y, const int32_t* run_x0,
+                    const int32_t* run_x1, int32_t* comp_val, long ovr_cap, int32_t* ovr_t, int32_t* ovr_y,
+                    int32_t* ovr_x0, int32_t* ovr_x1, int32_t* ovr_val, long* n_ovr, long* n_features, long* n_events,
+                    long* n_splits) {
+    struct CsrFetcher : ctb::RunFetcher {
+        const int64_t* ptr; const int32_t *y, *x0, *x1;
+        bool fetch(long comp, std::vector<ctb::SubRun>& out) override {
+            out.clear();
+            for (int64_t i = ptr[comp]; i < ptr[comp + 1]; ++i) out.push_back(ctb::SubRun{y[i], x0[i], x1[i]});
+            return !out.empty();
+        }
+    } fetcher;
+    fetcher.ptr = run_ptr; fetcher.y = run_y; fetcher.x0 = run_x0; fetcher.x1 = run_x1;
+    std::vector<ctb::Override> ovr;
+    ctb::TrackStats stats;
+    int rc = ctb::track_tables(T, H, W, persistence, ncomp, comp_t, comp_y0, comp_y1, comp_x0, comp_x1, comp_label, nseg,
+                               seg_t, seg_y0, seg_y1, seg_a, seg_b, run_ptr ? &fetcher : nullptr, comp_val, ovr, stats);
+    if (rc != 0) return fail(CT_ERR_INTERNAL, "a component must be split and no run table was supplied");
+    if (n_ovr) *n_ovr = (long)ovr.size();
+    if ((long)ovr.size() > ovr_cap) return fail(CT_ERR_CAPACITY, "override capacity %ld < %zu", ovr_cap, ovr.size());
+    for (size_t i = 0; i < ovr.size(); ++i) {
+        ovr_t[i] = ovr[i].t; ovr_y[i] = ovr[i].y; ovr_x0[i] = ovr[i].x0; ovr_x1[i] = ovr[i].x1; ovr_val[i] = ovr[i].val;
+    }
+    if (n_features) *n_features = stats.n_features;
+    if (n_events) *n_events = stats.n_events;
+    if (n_splits) *n_splits = stats.n_splits;
+    return CT_OK;
+}
+
+void ct_classify_rows(const double* w_host, int H, int W, uint8_t* special_out) {
+    std::vector<uint8_t> sp;
+    classify_rows(w_host, H, W, sp);
+    memcpy(special_out, sp.data(), (size_t)H);
+}
+
+int ct_host_tables(long T, int H, int W, const double* w_host, double overlap, int persistence, int twosided, int stage,
+                   long ncomp, const int32_t* comp_t, const int32_t* comp_y0, const int32_t* comp_y1,
+                   const int32_t* comp_x0, const int32_t* comp_x1, const uint32_t* comp_cls, const double* comp_areaE,
+                   const double* comp_areaS, const uint32_t* comp_nsp,
+                   long npair, const uint32_t* pair_a, const uint32_t* pair_b, const uint32_t* pair_npix,
+                   const uint32_t* pair_nsp, const double* pair_areaE, const double* pair_areaS,
+                   long nseam, const uint32_t* seam_row, const uint32_t* seam_a, const uint32_t* seam_b,
+                   const int64_t* plane_run_ptr, const int32_t* run_y, const int32_t* run_x0, const int32_t* run_x1,
+                   const uint32_t* run_comp,
+                   int32_t* comp_val, long ovr_cap, int32_t* ovr_t, int32_t* ovr_y, int32_t* ovr_x0, int32_t* ovr_x1,
+                   int32_t* ovr_val, long* n_ovr, long* stats8) {
+    struct ArraySource : cth::RunSource {
+        const int64_t* ptr; const int32_t *y, *x0, *x1; const uint32_t* comp;
+        bool plane_runs(long t, std::vector<cth::PlaneRun>& out) override {
+            out.clear();
+            for (int64_t i = ptr[t]; i < ptr[t + 1]; ++i) out.push_back(cth::PlaneRun{y[i], x0[i], x1[i], comp[i]});
+            return true;
+        }
+    } src;
+    src.ptr = plane_run_ptr; src.y = run_y; src.x0 = run_x0; src.x1 = run_x1; src.comp = run_comp;
+    cth::Tables tb;
+    tb.T = T; tb.H = H; tb.W = W; tb.w = w_host;
+    tb.ncomp = ncomp; tb.comp_t = comp_t; tb.comp_y0 = comp_y0; tb.comp_y1 = comp_y1; tb.comp_x0 = comp_x0;
+    tb.comp_x1 = comp_x1; tb.comp_cls = comp_cls; tb.comp_areaE = comp_areaE; tb.comp_areaS = comp_areaS;
+    tb.comp_nsp = comp_nsp;
+    tb.npair = npair; tb.pair_a = pair_a; tb.pair_b = pair_b; tb.pair_npix = pair_npix; tb.pair_nsp = pair_nsp;
+    tb.pair_areaE = pair_areaE; tb.pair_areaS = pair_areaS;
+    tb.nseam = nseam; tb.seam_row = seam_row; tb.seam_a = seam_a; tb.seam_b = seam_b;
+    cth::Params pr;
+    pr.overlap = overlap; pr.persistence = persistence; pr.twosided = twosided; pr.stage = stage;
+    cth::Result res;
+    std::string err;
+    int rc = cth::host_phase(tb, pr, plane_run_ptr ? &src : nullptr, res, err);
+    if (rc != 0) return fail(rc, "%s", err.c_str());
+    if (ncomp) memcpy(comp_val, res.comp_val.data(), (size_t)ncomp * 4);
+    if (n_ovr) *n_ovr = (long)res.overrides.size();
+    if ((long)res.overrides.size() > ovr_cap)
+        return fail(CT_ERR_CAPACITY, "override capacity %ld < %zu", ovr_cap, res.overrides.size());
+    for (size_t i = 0; i < res.overrides.size(); ++i) {
+        const ctb::Override& o = res.overrides[i];
+        ovr_t[i] = o.t; ovr_y[i] = o.y; ovr_x0[i] = o.x0; ovr_x1[i] = o.x1; ovr_val[i] = o.val;
+    }
+    if (stats8) {
+        stats8[0] = res.n_features; stats8[1] = res.n_kept; stats8[2] = res.n_labels3d; stats8[3] = res.n_seam_events;
+        stats8[4] = res.n_seam_splits; stats8[5] = res.n_neartie; stats8[6] = 0; stats8[7] = 0;
+    }
+    return CT_OK;
+}
+
+double ct_numpy_pairwise_sum_rle(const double* value, const int64_t* count, long n) {
+    std::vector<double> v;
+    for (long i = 0; i < n; ++i) v.insert(v.end(), (size_t)count[i], value[i]);
+    return ctb::numpy_pairwise_sum(v.data(), (long)v.size());
+}
+
+int ct_calc_clim(ct_ctx*, const float*, long, int, int, const int32_t*, int, int, float*, void*) {
+    return fail(CT_ERR_INTERNAL, "ct_calc_clim: not built yet");
+}
+
+int ct_calc_anom(ct_ctx*, const float*, long, int, int, const int32_t*, int, const float*, int, float*, void*) {
+    return fail(CT_ERR_INTERNAL, "ct_calc_anom: not built yet");
+}
+
+}  // extern "C"

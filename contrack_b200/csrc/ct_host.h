@@ -1,0 +1,61 @@
+// ct_host.h -- the strictly ordered part of run_contrack, on component tables (pure host C++, no CUDA).
+//
+// The CUDA kernels reduce the cube to tables (2-D components, date-line classes, adjacent-plane pair areas, date-line
+// rows).  This translation unit replays, on those tables and in the reference's order:
+//   step 3   contrack/contrack.py:706-742   time-sequential forward/backward overlap filter
+//   step 4a/b contrack.py:747-751           3-D labelling of the kept mask, ids in scipy's first-pixel order
+//   step 4c/d contrack.py:753-772           date-line merge through stale boxes + persistence (ct_tables.cpp)
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "ct_tables.h"
+
+namespace cth {
+
+struct PlaneRun { int y, x0, x1; uint32_t comp; };          // x1 exclusive; comp = global 2-D component id
+
+// Row-runs of one time plane in raster order (only needed for near-tie decisions and stale-box splits: rare).
+struct RunSource {
+    virtual bool plane_runs(long t, std::vector<PlaneRun>& out) = 0;
+    virtual ~RunSource() {}
+};
+
+struct Tables {
+    long T = 0; int H = 0, W = 0;
+    // 2-D components (8-connected, no date-line wrap) in global first-pixel order: id ascending <=> (t, y, x) ascending
+    long ncomp = 0;
+    const int32_t* comp_t = nullptr;
+    const int32_t *comp_y0 = nullptr, *comp_y1 = nullptr, *comp_x0 = nullptr, *comp_x1 = nullptr;   // half-open bbox
+    const uint32_t* comp_cls = nullptr;      // date-line class (contrack.py:691-698): smallest component id of the class
+    const double* comp_areaE = nullptr;      // sum of w[y] over pixels in exactly-summable rows
+    const double* comp_areaS = nullptr;      // ... over the other ("special", e.g. pole) rows
+    const uint32_t* comp_nsp = nullptr;      // pixel count in special rows
+    // pairs (a at plane t, b at plane t-1) with at least one common pixel
+    long npair = 0;
+    const uint32_t *pair_a = nullptr, *pair_b = nullptr, *pair_npix = nullptr, *pair_nsp = nullptr;
+    const double *pair_areaE = nullptr, *pair_areaS = nullptr;
+    // date-line rows: row = t*H + y, pixel x=0 belongs to component a, pixel x=W-1 to component b; sorted by row
+    long nseam = 0;
+    const uint32_t *seam_row = nullptr, *seam_a = nullptr, *seam_b = nullptr;
+    const double* w = nullptr;               // [H] area weight per row (contrack.py:703-704)
+};
+
+struct Params {
+    double overlap = 0.5;
+    int persistence = 1;
+    int twosided = 1;
+    int stage = 0;                           // ct_stage
+};
+
+struct Result {
+    std::vector<int32_t> comp_val;           // value painted for each component
+    std::vector<ctb::Override> overrides;    // sub-runs of split components (stage FINAL only)
+    long n_features = 0, n_kept = 0, n_labels3d = 0, n_seam_events = 0, n_seam_splits = 0, n_neartie = 0;
+};
+
+// returns 0, or a negative ct_status with `err` filled
+int host_phase(const Tables& tb, const Params& pr, RunSource* runs, Result& out, std::string& err);
+
+}  // namespace cth

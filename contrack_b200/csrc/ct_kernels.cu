@@ -1,0 +1,653 @@
+// ct_kernels.cu -- sm_100a kernels of the run_contrack path ("label once, then tables").
+//
+//   threshold_bits   contrack.py:648-674   anomaly cube -> 1 bit per cell (+ row-run counts, date-line flags)
+//   extract_runs                           bit rows -> row-runs (y, x0, x1) in raster order
+//   ccl_*            contrack.py:684-687   8-connected components of each plane = union-find over row-runs
+//   seam_rows/cls_*  contrack.py:691-698   same-row date-line classes on top of the components
+//   comp_*/pairs_*   contrack.py:717-719   area tables: per component, and per (component at t, component at t-1)
+//   paint            contrack.py:776-791   bit rows + per-run value -> int32 flag cube
+//
+// The two cube-sized kernels (threshold_bits: 4 B/cell read; paint: 4 B/cell write) are HBM-bound streaming kernels;
+// everything between them touches only bit rows (1/32 B/cell... 4/32 B per cell) and run/component tables.
+#include "ct_kernels.h"
+
+#include <cfloat>
+#include <climits>
+#include <cmath>
+
+namespace ctk {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t* total) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t n = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += n;
+    }
+    *total = __shfl_sync(FULL, inc, 31);
+    return inc - v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// threshold -> bits
+// ---------------------------------------------------------------------------------------------------------------
+template <typename TIn, bool F32CMP, int OP>
+__device__ __forceinline__ bool cmp_thr(TIn v, float thr_f, double thr_d) {
+    if (F32CMP) {
+        const float x = (float)v;
+        if (OP == 0) return x >= thr_f;
+        if (OP == 1) return x <= thr_f;
+        if (OP == 2) return x > thr_f;
+        return x < thr_f;
+    } else {
+        const double x = (double)v;
+        if (OP == 0) return x >= thr_d;
+        if (OP == 1) return x <= thr_d;
+        if (OP == 2) return x > thr_d;
+        return x < thr_d;
+    }
+}
+
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+
+// One warp per row; 8 independent 128-byte warp loads in flight per warp; ballot packs 32 cells into a mask word.
+template <typename TIn, bool F32CMP, int OP>
+__global__ void __launch_bounds__(256) k_threshold(const TIn* __restrict__ anom, long nrows, int H, int W, int Ww,
+                                                   const double* __restrict__ thr, long thr_n,
+                                                   uint32_t* __restrict__ bits, uint32_t* __restrict__ row_cnt,
+                                                   uint32_t* __restrict__ seam_flag) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const int last_word = (W - 1) >> 5, last_bit = (W - 1) & 31;
+    for (long row = warp0; row < nrows; row += nwarps) {
+        const double thr_d = thr[thr_n == 1 ? 0 : row / H];
+        const float thr_f = (float)thr_d;
+        const TIn* a = anom + row * (long)W;
+        uint32_t carry = 0, cnt = 0, first = 0, last = 0;
+        for (int k0 = 0; k0 < Ww; k0 += 32) {
+            uint32_t myword = 0;
+            const int kend = min(32, Ww - k0);
+            for (int j0 = 0; j0 < kend; j0 += 8) {
+                TIn v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int x = (k0 + j0 + j) * 32 + lane;
+                    v[j] = (x < W) ? ld_stream(a + x) : (TIn)NAN;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t m = __ballot_sync(FULL, cmp_thr<TIn, F32CMP, OP>(v[j], thr_f, thr_d));
+                    const int k = k0 + j0 + j;
+                    cnt += __popc(m & ~((m << 1) | carry));
+                    carry = m >> 31;
+                    if (lane == j0 + j) myword = m;
+                    if (k == 0) first = m & 1u;
+                    if (k == last_word) last = (m >> last_bit) & 1u;
+                }
+            }
+            if (lane < kend) bits[row * (long)Ww + k0 + lane] = myword;
+        }
+        if (lane == 0) { row_cnt[row] = cnt; seam_flag[row] = first & last; }
+    }
+}
+
+template <typename TIn, bool F32CMP>
+cudaError_t launch_threshold(const ThresholdArgs& a, int blocks, cudaStream_t st) {
+    const long nrows = a.T * a.H;
+#define CT_LAUNCH_THR(OPV)                                                                                          \
+    k_threshold<TIn, F32CMP, OPV><<<blocks, 256, 0, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww, a.thr_dev,      \
+                                                          a.thr_n, a.bits, a.row_cnt, a.seam_flag)
+    switch (a.op) {
+        case 0: CT_LAUNCH_THR(0); break;
+        case 1: CT_LAUNCH_THR(1); break;
+        case 2: CT_LAUNCH_THR(2); break;
+        case 3: CT_LAUNCH_THR(3); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef CT_LAUNCH_THR
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// exclusive scan (three small kernels; inputs are row/run-sized tables, a few tens of MB at most)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t wtot;
+    uint32_t ex = warp_excl_scan(v, lane, &wtot);
+    if (lane == 31) s_warp[wid] = wtot;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t x = lane < nw ? s_warp[lane] : 0, t;
+        uint32_t e = warp_excl_scan(x, lane, &t);
+        if (lane < nw) s_warp[lane] = e;
+        if (lane == 0) s_warp[32] = t;
+    }
+    __syncthreads();
+    ex += s_warp[wid];
+    *total = s_warp[32];
+    __syncthreads();
+    return ex;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, long n,
+                                                              uint32_t* __restrict__ sums) {
+    __shared__ uint32_t s_warp[33];
+    const long base = (long)blockIdx.x * SCAN_TILE + (long)threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) s += in[base + i];
+    uint32_t tot;
+    block_excl_scan(s, s_warp, &tot);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, long nb, uint32_t* total_out) {
+    __shared__ uint32_t s_warp[33];
+    uint32_t running = 0;
+    for (long b0 = 0; b0 < nb; b0 += 1024) {
+        const long i = b0 + threadIdx.x;
+        uint32_t v = i < nb ? sums[i] : 0, tot;
+        uint32_t ex = block_excl_scan(v, s_warp, &tot);
+        if (i < nb) sums[i] = running + ex;
+        running += tot;
+    }
+    if (threadIdx.x == 0) *total_out = running;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                             long n, const uint32_t* __restrict__ sums) {
+    __shared__ uint32_t s_warp[33];
+    const long base = (long)blockIdx.x * SCAN_TILE + (long)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan(s, s_warp, &tot) + sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bit rows -> row-runs
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_extract_runs(const uint32_t* __restrict__ bits,
+                                                      const uint32_t* __restrict__ row_ptr, long nrows, int Ww,
+                                                      uint32_t* __restrict__ run_x, uint32_t* __restrict__ run_row) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    uint16_t* rx = reinterpret_cast<uint16_t*>(run_x);
+    for (long row = warp0; row < nrows; row += nwarps) {
+        const uint32_t base = row_ptr[row];
+        if (row_ptr[row + 1] == base) continue;
+        const uint32_t* b = bits + row * (long)Ww;
+        uint32_t sbase = base, ebase = base, prev = 0;
+        for (int k0 = 0; k0 < Ww; k0 += 32) {
+            const int k = k0 + lane;
+            const uint32_t m = k < Ww ? b[k] : 0u;
+            uint32_t left = __shfl_up_sync(FULL, m, 1);
+            if (lane == 0) left = prev;
+            uint32_t right = __shfl_down_sync(FULL, m, 1);
+            if (lane == 31) right = (k + 1 < Ww) ? b[k + 1] : 0u;
+            uint32_t starts = m & ~((m << 1) | (left >> 31));
+            uint32_t ends = m & ~((m >> 1) | (right << 31));
+            uint32_t ts, te;
+            uint32_t is = sbase + warp_excl_scan(__popc(starts), lane, &ts);
+            uint32_t ie = ebase + warp_excl_scan(__popc(ends), lane, &te);
+            while (starts) {
+                const int bit = __ffs(starts) - 1;
+                starts &= starts - 1;
+                rx[2 * (size_t)is] = (uint16_t)(k * 32 + bit);
+                run_row[is] = (uint32_t)row;
+                ++is;
+            }
+            while (ends) {
+                const int bit = __ffs(ends) - 1;
+                ends &= ends - 1;
+                rx[2 * (size_t)ie + 1] = (uint16_t)(k * 32 + bit + 1);
+                ++ie;
+            }
+            sbase += ts; ebase += te;
+            prev = __shfl_sync(FULL, m, 31);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// union-find helpers (lock-free, smallest index is the root)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t uf_find(const uint32_t* parent, uint32_t x) {
+    const volatile uint32_t* p = parent;
+    while (true) {
+        const uint32_t q = p[x];
+        if (q == x) return x;
+        x = q;
+    }
+}
+
+__device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { const uint32_t t = a; a = b; b = t; }      // a > b: hang a below b
+        const uint32_t old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;                                                 // somebody re-parented a meanwhile: join that with b
+    }
+}
+
+__global__ void k_iota(uint32_t* p, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+
+// 8-connectivity between a run and the runs of the row above: [x0-1, x1+1) must meet [px0, px1).
+__global__ void __launch_bounds__(256) k_ccl_union(const uint32_t* __restrict__ row_ptr,
+                                                   const uint32_t* __restrict__ run_x,
+                                                   const uint32_t* __restrict__ run_row, long nruns, int H,
+                                                   uint32_t* parent) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nruns) return;
+    const uint32_t row = run_row[r];
+    if (row % (uint32_t)H == 0) return;
+    const uint32_t x = run_x[r];
+    const int x0 = x & 0xffff, x1 = x >> 16;
+    uint32_t lo = row_ptr[row - 1], hi = row_ptr[row];
+    const uint32_t end = hi;
+    while (lo < hi) {                                            // first run above with px1 >= x0
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((int)(run_x[mid] >> 16) >= x0) hi = mid; else lo = mid + 1;
+    }
+    for (uint32_t p = lo; p < end; ++p) {
+        if ((int)(run_x[p] & 0xffff) > x1) break;
+        uf_union(parent, (uint32_t)r, p);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_flatten(uint32_t* parent, uint32_t* __restrict__ root_flag, long nruns) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nruns) return;
+    const uint32_t root = uf_find(parent, (uint32_t)r);
+    root_flag[r] = root == (uint32_t)r ? 1u : 0u;
+    if (root != (uint32_t)r) parent[r] = root;
+}
+
+__global__ void __launch_bounds__(256) k_ccl_assign(const uint32_t* __restrict__ parent,
+                                                    const uint32_t* __restrict__ rank, uint32_t* __restrict__ run_comp,
+                                                    long nruns) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nruns) return;
+    // after k_ccl_flatten parent[r] is the root or one hop from it (a concurrent flatten may have left a short chain)
+    run_comp[r] = rank[uf_find(parent, (uint32_t)r)];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// component tables
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_comp_init(CompTables c, long ncomp, int W) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncomp) return;
+    c.t[i] = 0; c.y0[i] = INT_MAX; c.y1[i] = 0; c.x0[i] = W; c.x1[i] = 0;
+    c.areaE[i] = 0.0; c.areaS[i] = 0.0; c.nsp[i] = 0; c.cls[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) k_comp_accumulate(const uint32_t* __restrict__ run_x,
+                                                         const uint32_t* __restrict__ run_row,
+                                                         const uint32_t* __restrict__ run_comp, long nruns, int H,
+                                                         const double* __restrict__ w,
+                                                         const uint8_t* __restrict__ special, CompTables c) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nruns) return;
+    const uint32_t row = run_row[r], comp = run_comp[r];
+    const int t = (int)(row / (uint32_t)H), y = (int)(row % (uint32_t)H);
+    const uint32_t x = run_x[r];
+    const int x0 = x & 0xffff, x1 = x >> 16;
+    c.t[comp] = t;
+    atomicMin(&c.y0[comp], y);
+    atomicMax(&c.y1[comp], y + 1);
+    atomicMin(&c.x0[comp], x0);
+    atomicMax(&c.x1[comp], x1);
+    const double area = (double)(x1 - x0) * w[y];                // exact: < 2^16 times a float32-valued double
+    if (special[y]) { atomicAdd(&c.areaS[comp], area); atomicAdd(&c.nsp[comp], (uint32_t)(x1 - x0)); }
+    else atomicAdd(&c.areaE[comp], area);
+}
+
+__global__ void __launch_bounds__(256) k_seam_rows(const uint32_t* __restrict__ seam_flag,
+                                                   const uint32_t* __restrict__ seam_pos,
+                                                   const uint32_t* __restrict__ row_ptr,
+                                                   const uint32_t* __restrict__ run_comp, long nrows,
+                                                   uint32_t* __restrict__ seam_row, uint32_t* __restrict__ seam_a,
+                                                   uint32_t* __restrict__ seam_b, uint32_t* cls_parent) {
+    const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows || !seam_flag[row]) return;
+    const uint32_t a = run_comp[row_ptr[row]], b = run_comp[row_ptr[row + 1] - 1];
+    const uint32_t pos = seam_pos[row];
+    seam_row[pos] = (uint32_t)row; seam_a[pos] = a; seam_b[pos] = b;
+    if (a != b) uf_union(cls_parent, a, b);
+}
+
+__global__ void __launch_bounds__(256) k_cls_flatten(uint32_t* cls_parent, long ncomp) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncomp) return;
+    const uint32_t root = uf_find(cls_parent, (uint32_t)c);
+    if (root != (uint32_t)c) cls_parent[c] = root;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pair table
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pairs_init(PairTable p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.cap) return;
+    p.key[i] = PAIR_EMPTY; p.npix[i] = 0; p.nsp[i] = 0; p.areaE[i] = 0.0; p.areaS[i] = 0.0;
+    if (i == 0) *p.overflow = 0;
+}
+
+__device__ __forceinline__ uint32_t hash64(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (uint32_t)k;
+}
+
+__global__ void __launch_bounds__(256) k_pairs_accumulate(const uint32_t* __restrict__ row_ptr,
+                                                          const uint32_t* __restrict__ run_x,
+                                                          const uint32_t* __restrict__ run_row,
+                                                          const uint32_t* __restrict__ run_comp, long nruns, int H,
+                                                          const double* __restrict__ w,
+                                                          const uint8_t* __restrict__ special, PairTable pt) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nruns) return;
+    const uint32_t row = run_row[r];
+    if (row < (uint32_t)H) return;                               // plane 0 has no predecessor
+    const uint32_t prow = row - (uint32_t)H;
+    const uint32_t x = run_x[r];
+    const int x0 = x & 0xffff, x1 = x >> 16;
+    uint32_t lo = row_ptr[prow], hi = row_ptr[prow + 1];
+    const uint32_t end = hi;
+    while (lo < hi) {                                            // first run of the earlier plane with px1 > x0
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((int)(run_x[mid] >> 16) > x0) hi = mid; else lo = mid + 1;
+    }
+    const int y = (int)(row % (uint32_t)H);
+    const double wy = w[y];
+    const bool sp = special[y] != 0;
+    const unsigned long long ka = (unsigned long long)run_comp[r] << 32;
+    const uint32_t mask = pt.cap - 1;
+    for (uint32_t p = lo; p < end; ++p) {
+        const uint32_t px = run_x[p];
+        const int px0 = px & 0xffff, px1 = px >> 16;
+        if (px0 >= x1) break;
+        const int n = min(x1, px1) - max(x0, px0);
+        const unsigned long long key = ka | run_comp[p];
+        uint32_t slot = hash64(key) & mask;
+        bool found = false;
+        for (uint32_t probe = 0; probe <= mask; ++probe) {
+            unsigned long long k = *((volatile unsigned long long*)&pt.key[slot]);
+            if (k == PAIR_EMPTY) k = atomicCAS(&pt.key[slot], PAIR_EMPTY, key);
+            if (k == PAIR_EMPTY || k == key) { found = true; break; }
+            slot = (slot + 1) & mask;
+        }
+        if (!found) { *pt.overflow = 1; return; }
+        atomicAdd(&pt.npix[slot], (uint32_t)n);
+        const double area = (double)n * wy;
+        if (sp) { atomicAdd(&pt.areaS[slot], area); atomicAdd(&pt.nsp[slot], (uint32_t)n); }
+        else atomicAdd(&pt.areaE[slot], area);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pairs_compact(PairTable p, uint32_t* __restrict__ out_a,
+                                                       uint32_t* __restrict__ out_b, uint32_t* __restrict__ out_npix,
+                                                       uint32_t* __restrict__ out_nsp, double* __restrict__ out_E,
+                                                       double* __restrict__ out_S, uint32_t out_cap, uint32_t* count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.cap) return;
+    const unsigned long long k = p.key[i];
+    if (k == PAIR_EMPTY) return;
+    const uint32_t idx = atomicAdd(count, 1u);
+    if (idx >= out_cap) return;
+    out_a[idx] = (uint32_t)(k >> 32); out_b[idx] = (uint32_t)k;
+    out_npix[idx] = p.npix[i]; out_nsp[idx] = p.nsp[i]; out_E[idx] = p.areaE[i]; out_S[idx] = p.areaS[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// paint: bit rows + value per run -> int32 cube.  One warp per row, 1024 cells (32 mask words) per pass; a lane owns
+// four consecutive cells and stores them as one 16-byte streaming store.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_run_values(const uint32_t* __restrict__ run_comp,
+                                                    const int32_t* __restrict__ comp_val, int32_t* __restrict__ run_val,
+                                                    long nruns) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nruns) run_val[r] = comp_val[run_comp[r]];
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ row_ptr,
+                                               const int32_t* __restrict__ run_val, long nrows, int W, int Ww,
+                                               int32_t* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long row = warp0; row < nrows; row += nwarps) {
+        const uint32_t rbase = row_ptr[row];
+        const bool empty = row_ptr[row + 1] == rbase;
+        int32_t* out = flag + row * (long)W;
+        const uint32_t* b = bits + row * (long)Ww;
+        uint32_t prev = 0, running = rbase;
+        for (int k0 = 0; k0 < Ww; k0 += 32) {
+            const int k = k0 + lane;
+            const uint32_t m = (!empty && k < Ww) ? b[k] : 0u;
+            const bool any = __ballot_sync(FULL, m != 0) != 0;
+            uint32_t starts = 0, base = 0;
+            if (any) {
+                uint32_t left = __shfl_up_sync(FULL, m, 1);
+                if (lane == 0) left = prev;
+                starts = m & ~((m << 1) | (left >> 31));
+                uint32_t tot;
+                base = running + warp_excl_scan(__popc(starts), lane, &tot);
+                running += tot;
+                prev = __shfl_sync(FULL, m, 31);
+            } else {
+                prev = 0;
+            }
+            const int xbase = k0 * 32;
+            if (VEC4) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int x = xbase + (i * 32 + lane) * 4;
+                    int4 v = make_int4(0, 0, 0, 0);
+                    if (any) {
+                        const int src = 4 * i + (lane >> 3);
+                        const uint32_t mw = __shfl_sync(FULL, m, src);
+                        const uint32_t sw = __shfl_sync(FULL, starts, src);
+                        const uint32_t bw = __shfl_sync(FULL, base, src);
+                        const int off = (lane & 7) * 4;
+                        const uint32_t nib = (mw >> off) & 0xfu;
+                        if (nib) {
+                            int vv[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                vv[j] = 0;
+                                if ((nib >> j) & 1u) {
+                                    const uint32_t rank = bw + __popc(sw & ((2u << (off + j)) - 1u)) - 1u;
+                                    vv[j] = run_val[rank];
+                                }
+                            }
+                            v = make_int4(vv[0], vv[1], vv[2], vv[3]);
+                        }
+                    }
+                    if (x < W) __stcs(reinterpret_cast<int4*>(out + x), v);
+                }
+            } else {
+                for (int i = 0; i < 32; ++i) {
+                    const int x = xbase + i * 32 + lane;
+                    if (xbase + i * 32 >= W) break;
+                    int v = 0;
+                    if (any) {
+                        const uint32_t mw = __shfl_sync(FULL, m, i);
+                        const uint32_t sw = __shfl_sync(FULL, starts, i);
+                        const uint32_t bw = __shfl_sync(FULL, base, i);
+                        if ((mw >> lane) & 1u) v = run_val[bw + __popc(sw & ((2u << lane) - 1u)) - 1u];
+                    }
+                    if (x < W) __stcs(out + x, v);
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_paint_overrides(const int32_t* __restrict__ t, const int32_t* __restrict__ y,
+                                  const int32_t* __restrict__ x0, const int32_t* __restrict__ x1,
+                                  const int32_t* __restrict__ val, long n, int H, int W, long t_begin, long t_end,
+                                  int32_t* __restrict__ flag) {
+    const long i = blockIdx.x;                                   // one block per sub-run
+    if (i >= n || t[i] < t_begin || t[i] >= t_end) return;
+    int32_t* out = flag + ((long)(t[i] - t_begin) * H + y[i]) * (long)W;
+    for (int x = x0[i] + threadIdx.x; x < x1[i]; x += blockDim.x) out[x] = val[i];
+}
+
+inline unsigned blocks_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st) {
+    const long nrows = a.T * a.H;
+    if (nrows == 0) return cudaSuccess;
+    long want = (nrows + 7) / 8;
+    int blocks = (int)(want < (long)sm_count * 8 ? want : (long)sm_count * 8);
+    if (a.in_dtype == 1) return launch_threshold<double, false>(a, blocks, st);
+    if (a.thr_is_f32) return launch_threshold<float, true>(a, blocks, st);
+    return launch_threshold<float, false>(a, blocks, st);
+}
+
+size_t scan_tmp_elems(long n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 2; }
+
+cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st) {
+    if (n == 0) return cudaMemsetAsync(out, 0, sizeof(uint32_t), st);
+    const long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, tmp);
+    k_scan_sums<<<1, 1024, 0, st>>>(tmp, nb, out + n);
+    k_scan_final<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, tmp);
+    return cudaGetLastError();
+}
+
+cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long nrows, int Ww, uint32_t* run_x,
+                         uint32_t* run_row, cudaStream_t st) {
+    if (nrows == 0) return cudaSuccess;
+    k_extract_runs<<<blocks_for(nrows, 8), 256, 0, st>>>(bits, row_ptr, nrows, Ww, run_x, run_row);
+    return cudaGetLastError();
+}
+
+cudaError_t ccl_init(uint32_t* parent, long nruns, cudaStream_t st) {
+    if (nruns == 0) return cudaSuccess;
+    k_iota<<<blocks_for(nruns, 256), 256, 0, st>>>(parent, nruns);
+    return cudaGetLastError();
+}
+
+cudaError_t ccl_union(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row, long nruns, int H,
+                      uint32_t* parent, cudaStream_t st) {
+    if (nruns == 0) return cudaSuccess;
+    k_ccl_union<<<blocks_for(nruns, 256), 256, 0, st>>>(row_ptr, run_x, run_row, nruns, H, parent);
+    return cudaGetLastError();
+}
+
+cudaError_t ccl_flatten(uint32_t* parent, uint32_t* root_flag, long nruns, cudaStream_t st) {
+    if (nruns == 0) return cudaSuccess;
+    k_ccl_flatten<<<blocks_for(nruns, 256), 256, 0, st>>>(parent, root_flag, nruns);
+    return cudaGetLastError();
+}
+
+cudaError_t ccl_assign(const uint32_t* parent, const uint32_t* rank, uint32_t* run_comp, long nruns, cudaStream_t st) {
+    if (nruns == 0) return cudaSuccess;
+    k_ccl_assign<<<blocks_for(nruns, 256), 256, 0, st>>>(parent, rank, run_comp, nruns);
+    return cudaGetLastError();
+}
+
+cudaError_t comp_init(const CompTables& c, long ncomp, int W, cudaStream_t st) {
+    if (ncomp == 0) return cudaSuccess;
+    k_comp_init<<<blocks_for(ncomp, 256), 256, 0, st>>>(c, ncomp, W);
+    return cudaGetLastError();
+}
+
+cudaError_t comp_accumulate(const uint32_t* run_x, const uint32_t* run_row, const uint32_t* run_comp, long nruns, int H,
+                            const double* w_dev, const uint8_t* special_dev, const CompTables& c, cudaStream_t st) {
+    if (nruns == 0) return cudaSuccess;
+    k_comp_accumulate<<<blocks_for(nruns, 256), 256, 0, st>>>(run_x, run_row, run_comp, nruns, H, w_dev, special_dev, c);
+    return cudaGetLastError();
+}
+
+cudaError_t seam_rows(const uint32_t* seam_flag, const uint32_t* seam_pos, const uint32_t* row_ptr,
+                      const uint32_t* run_comp, long nrows, uint32_t* seam_row, uint32_t* seam_a, uint32_t* seam_b,
+                      uint32_t* cls_parent, cudaStream_t st) {
+    if (nrows == 0) return cudaSuccess;
+    k_seam_rows<<<blocks_for(nrows, 256), 256, 0, st>>>(seam_flag, seam_pos, row_ptr, run_comp, nrows, seam_row, seam_a,
+                                                        seam_b, cls_parent);
+    return cudaGetLastError();
+}
+
+cudaError_t cls_flatten(uint32_t* cls_parent, long ncomp, cudaStream_t st) {
+    if (ncomp == 0) return cudaSuccess;
+    k_cls_flatten<<<blocks_for(ncomp, 256), 256, 0, st>>>(cls_parent, ncomp);
+    return cudaGetLastError();
+}
+
+cudaError_t pairs_init(const PairTable& p, cudaStream_t st) {
+    k_pairs_init<<<blocks_for(p.cap, 256), 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t pairs_accumulate(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row,
+                             const uint32_t* run_comp, long nruns, int H, const double* w_dev,
+                             const uint8_t* special_dev, const PairTable& p, cudaStream_t st) {
+    if (nruns == 0) return cudaSuccess;
+    k_pairs_accumulate<<<blocks_for(nruns, 256), 256, 0, st>>>(row_ptr, run_x, run_row, run_comp, nruns, H, w_dev,
+                                                               special_dev, p);
+    return cudaGetLastError();
+}
+
+cudaError_t pairs_compact(const PairTable& p, uint32_t* out_a, uint32_t* out_b, uint32_t* out_npix, uint32_t* out_nsp,
+                          double* out_E, double* out_S, uint32_t out_cap, uint32_t* count_dev, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(count_dev, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    k_pairs_compact<<<blocks_for(p.cap, 256), 256, 0, st>>>(p, out_a, out_b, out_npix, out_nsp, out_E, out_S, out_cap,
+                                                            count_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t run_values(const uint32_t* run_comp, const int32_t* comp_val, int32_t* run_val, long nruns,
+                       cudaStream_t st) {
+    if (nruns == 0) return cudaSuccess;
+    k_run_values<<<blocks_for(nruns, 256), 256, 0, st>>>(run_comp, comp_val, run_val, nruns);
+    return cudaGetLastError();
+}
+
+cudaError_t paint(const PaintArgs& a, int sm_count, cudaStream_t st) {
+    if (a.nrows == 0) return cudaSuccess;
+    long want = (a.nrows + 7) / 8;
+    int blocks = (int)(want < (long)sm_count * 8 ? want : (long)sm_count * 8);
+    const bool vec = (a.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.flag) & 15) == 0);
+    if (vec) k_paint<true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
+    else k_paint<false><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
+    return cudaGetLastError();
+}
+
+cudaError_t paint_overrides(const int32_t* t, const int32_t* y, const int32_t* x0, const int32_t* x1,
+                            const int32_t* val, long n, int H, int W, long t_begin, long t_end, int32_t* flag,
+                            cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_paint_overrides<<<(unsigned)n, 128, 0, st>>>(t, y, x0, x1, val, n, H, W, t_begin, t_end, flag);
+    return cudaGetLastError();
+}
+
+}  // namespace ctk

@@ -1,0 +1,85 @@
+// ct_kernels.h -- launchers of the sm_100a kernels behind ct_run_contrack (definitions in ct_kernels.cu).
+// Every launcher enqueues on `st` and returns the cudaError_t of the launch (cudaGetLastError()).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ctk {
+
+constexpr uint64_t PAIR_EMPTY = ~0ull;
+
+struct ThresholdArgs {
+    const void* anom; int in_dtype;          // ct_dtype
+    long T; int H, W, Ww;                    // Ww = words of 32 mask bits per row
+    const double* thr_dev; long thr_n;       // thresholds on the device (1 or T values)
+    int thr_is_f32, op;                      // ct_op
+    uint32_t* bits;                          // [T*H*Ww] out
+    uint32_t* row_cnt;                       // [T*H] out: row-runs per row
+    uint32_t* seam_flag;                     // [T*H] out: 1 if the pixels at x=0 and x=W-1 are both set
+    int variant;                             // 0: 4-byte loads + ballot; 1: cp.async.bulk row staging (needs W % 4 == 0)
+};
+cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st);
+
+// out[0..n] = exclusive prefix sums of in[0..n-1] (out[n] = total).  `tmp` needs scan_tmp_elems(n) uint32.
+size_t scan_tmp_elems(long n);
+cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st);
+
+cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long nrows, int Ww, uint32_t* run_x,
+                         uint32_t* run_row, cudaStream_t st);
+
+// 2-D 8-connected components over row-runs (contrack.py:684-687): union-find with the smallest run index as root.
+cudaError_t ccl_init(uint32_t* parent, long nruns, cudaStream_t st);
+cudaError_t ccl_union(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row, long nruns, int H,
+                      uint32_t* parent, cudaStream_t st);
+cudaError_t ccl_flatten(uint32_t* parent, uint32_t* root_flag, long nruns, cudaStream_t st);
+// run_comp[r] = rank[parent[r]]  (rank = exclusive scan of root_flag)
+cudaError_t ccl_assign(const uint32_t* parent, const uint32_t* rank, uint32_t* run_comp, long nruns, cudaStream_t st);
+
+struct CompTables {
+    int32_t *t, *y0, *y1, *x0, *x1;          // [ncomp]
+    double *areaE, *areaS;
+    uint32_t *nsp, *cls;
+};
+cudaError_t comp_init(const CompTables& c, long ncomp, int W, cudaStream_t st);
+cudaError_t comp_accumulate(const uint32_t* run_x, const uint32_t* run_row, const uint32_t* run_comp, long nruns, int H,
+                            const double* w_dev, const uint8_t* special_dev, const CompTables& c, cudaStream_t st);
+
+// date-line rows (contrack.py:691-698): list (row, comp at x=0, comp at x=W-1) at position seam_pos[row]; class union
+cudaError_t seam_rows(const uint32_t* seam_flag, const uint32_t* seam_pos, const uint32_t* row_ptr,
+                      const uint32_t* run_comp, long nrows, uint32_t* seam_row, uint32_t* seam_a, uint32_t* seam_b,
+                      uint32_t* cls_parent, cudaStream_t st);
+cudaError_t cls_flatten(uint32_t* cls_parent, long ncomp, cudaStream_t st);
+
+struct PairTable {
+    unsigned long long* key;                 // [cap] (a << 32) | b, PAIR_EMPTY when free
+    uint32_t *npix, *nsp;                    // [cap]
+    double *areaE, *areaS;                   // [cap]
+    uint32_t cap;                            // power of two
+    uint32_t* overflow;                      // device flag
+};
+cudaError_t pairs_init(const PairTable& p, cudaStream_t st);
+// two-timestep intersection (contrack.py:717-719 on tables): for every run of plane t >= 1 the overlapping runs of
+// plane t-1 in the same row; pixel counts and areas accumulate per (comp_t, comp_t-1)
+cudaError_t pairs_accumulate(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row,
+                             const uint32_t* run_comp, long nruns, int H, const double* w_dev,
+                             const uint8_t* special_dev, const PairTable& p, cudaStream_t st);
+// compact occupied slots: out arrays sized >= number of pairs; *count_dev receives the number
+cudaError_t pairs_compact(const PairTable& p, uint32_t* out_a, uint32_t* out_b, uint32_t* out_npix, uint32_t* out_nsp,
+                          double* out_E, double* out_S, uint32_t out_cap, uint32_t* count_dev, cudaStream_t st);
+
+// run_val[r] = comp_val[run_comp[r]]
+cudaError_t run_values(const uint32_t* run_comp, const int32_t* comp_val, int32_t* run_val, long nruns,
+                       cudaStream_t st);
+
+struct PaintArgs {
+    const uint32_t* bits; const uint32_t* row_ptr; const int32_t* run_val;
+    long nrows; int W, Ww;
+    int32_t* flag;                           // [nrows * W] out
+};
+cudaError_t paint(const PaintArgs& a, int sm_count, cudaStream_t st);
+// sub-runs of planes [t_begin, t_end) only; `flag` starts at plane t_begin
+cudaError_t paint_overrides(const int32_t* t, const int32_t* y, const int32_t* x0, const int32_t* x1,
+                            const int32_t* val, long n, int H, int W, long t_begin, long t_end, int32_t* flag,
+                            cudaStream_t st);
+
+}  // namespace ctk

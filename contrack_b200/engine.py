@@ -1,0 +1,109 @@
+"""Host-side driver of the C-ABI library: owns one ``ct_ctx`` per GPU and moves numpy / torch buffers across the ABI.
+
+PyTorch is used only as plumbing (device memory, streams); every computation happens in the library's CUDA kernels and
+its native host table phase.  There is no CPU fallback: without the library or without a B200 the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ContrackLibError
+
+_STAT_KEYS = ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d', 'features', 'seam_events',
+              'seam_splits', 'neartie_resolved', 'override_runs', 'special_rows', 'kernel_launches', 'ms_threshold',
+              'ms_tables_gpu', 'ms_tables_host_roundtrip', 'ms_host_tables', 'ms_paint', 'ms_total', 'ms_h2d_threshold',
+              'ms_tables', 'ms_paint_d2h')
+
+
+def _is_torch(x):
+    return hasattr(x, 'data_ptr') and hasattr(x, 'device')
+
+
+class Engine(object):
+    """One context (scratch memory, streams) on one GPU."""
+
+    _cache = {}
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.ct_create(int(device), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    @classmethod
+    def get(cls, device=0):
+        e = cls._cache.get(device)
+        if e is None:
+            e = cls._cache[device] = Engine(device)
+        return e
+
+    def close(self):
+        if self.handle:
+            self.lib.ct_destroy(self.handle)
+            self.handle = None
+            Engine._cache.pop(self.device, None)
+
+    def set_option(self, key, value):
+        _lib.check(self.lib.ct_set_option(self.handle, key.encode(), int(value)))
+
+    def stats(self):
+        out = {}
+        for k in _STAT_KEYS:
+            v = self.lib.ct_get_stat(self.handle, k.encode())
+            if v >= 0:
+                out[k] = v
+        return out
+
+    # ------------------------------------------------------------------------------------------------------------
+    def run_contrack(self, anom, w, thresholds, thr_is_f32, op, overlap, persistence, twosided, stage=0, out=None,
+                     chunk_planes=0):
+        """anom: [T,H,W] C-contiguous float32/float64, numpy (host) or torch CUDA tensor (device).
+        Returns (flag, n_features); flag is int32 of the same kind (numpy / torch CUDA) as the input."""
+        T, H, W = (int(s) for s in anom.shape)
+        w = np.ascontiguousarray(w, np.float64)
+        thr = np.ascontiguousarray(np.atleast_1d(thresholds), np.float64)
+        if w.shape != (H,):
+            raise ValueError('weights must have shape (H,)')
+        nfeat = C.c_long(0)
+        if _is_torch(anom):
+            import torch
+            if not anom.is_cuda:
+                raise ValueError('torch input must live on a CUDA device (pass numpy for host data)')
+            if anom.device.index != self.device:
+                raise ValueError('input is on %s, engine on cuda:%d' % (anom.device, self.device))
+            if not anom.is_contiguous():
+                anom = anom.contiguous()
+            dt = {torch.float32: _lib.CT_F32, torch.float64: _lib.CT_F64}.get(anom.dtype)
+            if dt is None:
+                raise TypeError('input dtype must be float32 or float64')
+            if out is None:
+                out = torch.empty((T, H, W), dtype=torch.int32, device=anom.device)
+            stream = torch.cuda.current_stream(anom.device).cuda_stream
+            rc = self.lib.ct_run_contrack(self.handle, C.c_void_p(anom.data_ptr()), dt, T, H, W,
+                                          _lib.ptr(w, _lib._f64p), _lib.ptr(thr, _lib._f64p), len(thr), int(thr_is_f32),
+                                          int(op), float(overlap), int(persistence), int(bool(twosided)),
+                                          C.c_void_p(out.data_ptr()), C.byref(nfeat), int(stage), C.c_void_p(stream))
+            _lib.check(rc)
+            return out, nfeat.value
+        a = np.asarray(anom)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        a = np.ascontiguousarray(a)
+        dt = _lib.CT_F32 if a.dtype == np.float32 else _lib.CT_F64
+        if stage != 0:
+            raise ValueError('debug stages are only available for device-resident input')
+        if out is None:
+            out = np.empty((T, H, W), np.int32)
+        rc = self.lib.ct_run_contrack_host(self.handle, C.c_void_p(a.ctypes.data), dt, T, H, W, _lib.ptr(w, _lib._f64p),
+                                           _lib.ptr(thr, _lib._f64p), len(thr), int(thr_is_f32), int(op), float(overlap),
+                                           int(persistence), int(bool(twosided)), C.c_void_p(out.ctypes.data),
+                                           C.byref(nfeat), int(chunk_planes))
+        _lib.check(rc)
+        return out, nfeat.value
+
+
+__all__ = ['Engine', 'ContrackLibError']

@@ -105,6 +105,34 @@ int ct_track_tables(long T, int H, int W, int persistence,
                     int32_t* comp_val, long ovr_cap, int32_t* ovr_t, int32_t* ovr_y, int32_t* ovr_x0,
                     int32_t* ovr_x1, int32_t* ovr_val, long* n_ovr, long* n_features, long* n_events, long* n_splits);
 
+/* ---- host-only: the whole ordered table phase (no GPU needed) ------------------------------------------------------
+ * Replays contrack.py:706-772 on the tables the CUDA kernels produce: the time-sequential overlap filter (706-742), the
+ * 3-D labelling of the kept mask with scipy's first-pixel numbering (747-751), the date-line merge through stale boxes
+ * and the persistence filter (753-772).  Exposed so the ordered logic can be checked against the oracle without a GPU.
+ *   comp_*    2-D components (8-connected, no wrap) in global first-pixel order; comp_cls = smallest id of the same-row
+ *             date-line class (contrack.py:691-698); areaE / areaS / nsp: see ct_classify_rows
+ *   pair_*    (a at plane t, b at plane t-1) with common pixels: pixel count, areas, special-row pixel count
+ *   seam_*    rows (row = t*H + y, sorted) whose pixels at x=0 (component a) and x=W-1 (component b) are both set
+ *   plane_run_ptr/run_*  optional (may be NULL): all row-runs, raster order, CSR over planes [T+1]; needed only for
+ *             near-tie decisions on special rows and for stale-box splits
+ *   stats8    {features, kept 2-D comps, 3-D labels, seam events, seam splits, near-ties resolved, 0, 0}
+ */
+int ct_host_tables(long T, int H, int W, const double* w_host, double overlap, int persistence, int twosided, int stage,
+                   long ncomp, const int32_t* comp_t, const int32_t* comp_y0, const int32_t* comp_y1,
+                   const int32_t* comp_x0, const int32_t* comp_x1, const uint32_t* comp_cls, const double* comp_areaE,
+                   const double* comp_areaS, const uint32_t* comp_nsp,
+                   long npair, const uint32_t* pair_a, const uint32_t* pair_b, const uint32_t* pair_npix,
+                   const uint32_t* pair_nsp, const double* pair_areaE, const double* pair_areaS,
+                   long nseam, const uint32_t* seam_row, const uint32_t* seam_a, const uint32_t* seam_b,
+                   const int64_t* plane_run_ptr, const int32_t* run_y, const int32_t* run_x0, const int32_t* run_x1,
+                   const uint32_t* run_comp,
+                   int32_t* comp_val, long ovr_cap, int32_t* ovr_t, int32_t* ovr_y, int32_t* ovr_x0, int32_t* ovr_x1,
+                   int32_t* ovr_val, long* n_ovr, long* stats8);
+
+/* special_out[y] = 0 if row y belongs to the set of rows whose weights sum exactly in float64 in any order (areas of
+ * those rows accumulate in areaE and equal numpy's np.sum bit for bit), 1 otherwise (pole rows: areaS, nsp). */
+void ct_classify_rows(const double* w_host, int H, int W, uint8_t* special_out);
+
 /* numpy's float64 pairwise summation (the order np.sum uses on a contiguous 1-D array) over a run-length encoded
  * sequence: value[i] repeated count[i] times.  Used by the near-tie resolver; exported for the parity test. */
 double ct_numpy_pairwise_sum_rle(const double* value, const int64_t* count, long n);

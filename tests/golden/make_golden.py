@@ -33,7 +33,10 @@ def main():
     assert hashlib.sha256(a.tobytes()).hexdigest().startswith('8a8d1c01')
     lat = np.arange(90, -91, -1, dtype=np.float32)
     lon = np.arange(360, dtype=np.float32)
-    np.savez_compressed(os.path.join(HERE, 'anom_test.npz'), anom=a, latitude=lat, longitude=lon)
+    # the file's time axis: 11 daily steps, "days since 2016-10-02" 
+    time = np.datetime64('2016-10-02') + np.arange(11).astype('timedelta64[D]')
+    np.savez_compressed(os.path.join(HERE, 'anom_test.npz'), anom=a, time=time.astype('datetime64[ns]'), latitude=lat,
+                        longitude=lon)
 
     gold = {'fixture': [], 'synthetic': [], 'quirk': []}
     flags = {}

@@ -1,0 +1,179 @@
+"""Parity of the CUDA path (through the C-ABI library) with the oracle -- needs a B200 (`-m gpu`)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import contrack_oracle as oracle
+from _common import row_weights, sha_i4, same_partition
+from _synth import synth_cube, regular_grid
+
+pytestmark = pytest.mark.gpu
+
+OPS = {'>=': 0, 'ge': 0, '<=': 1, 'le': 1, '>': 2, 'gt': 2, '<': 3, 'lt': 3}
+
+
+@pytest.fixture(scope='module')
+def eng():
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from contrack_b200 import Engine
+    return Engine.get(0)
+
+
+def gpu_run(eng, x, lat, lon, thr, gorl, ov, pers, two, stage=0, thr_is_f32=True):
+    import torch
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    flag, n = eng.run_contrack(xd, row_weights(lat, lon), thr, thr_is_f32, OPS[gorl], ov, pers, two, stage=stage)
+    torch.cuda.synchronize()
+    return flag.cpu().numpy(), n
+
+
+@pytest.mark.parametrize('thr,ov,pers,two', [(150, .5, 5, False), (150, .5, 5, True), (160, .5, 5, True),
+                                             (100, .7, 3, True)])
+def test_fixture_bit_exact(eng, fixture_cube, golden, thr, ov, pers, two):
+    a, lat, lon = fixture_cube
+    f, n = gpu_run(eng, a, lat, lon, thr, '>=', ov, pers, two)
+    key = 'thr%d_ov%02d_p%d_%s' % (thr, int(ov * 10), pers, 'two' if two else 'one')
+    want = [r for r in golden['fixture'] if r['key'] == key][0]
+    assert f.dtype == np.int32 and f.shape == a.shape
+    assert sha_i4(f) == want['sha256']
+    assert n == len(want['ids'])
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'flags_fixture.npz'))[key]
+    assert np.array_equal(f, gold)
+
+
+def test_fixture_stages(eng, fixture_cube):
+    a, lat, lon = fixture_cube
+    st = {}
+    oracle.run_contrack(a, lat, lon, 150, '>=', .5, 5, True, stages=st)
+    f1, _ = gpu_run(eng, a, lat, lon, 150, '>=', .5, 5, True, stage=1)
+    assert same_partition(f1, st['label2d'])
+    f2, _ = gpu_run(eng, a, lat, lon, 150, '>=', .5, 5, True, stage=2)
+    assert same_partition(f2, st['label2d_seam'])
+    f3, _ = gpu_run(eng, a, lat, lon, 150, '>=', .5, 5, True, stage=3)
+    assert np.array_equal(f3 > 0, st['filtered'] > 0)
+    f4, _ = gpu_run(eng, a, lat, lon, 150, '>=', .5, 5, True, stage=4)
+    assert np.array_equal(f4, st['label3d'])
+
+
+def test_synthetic_golden(eng, golden):
+    for r in golden['synthetic']:
+        T, H, W = r['shape']
+        x = synth_cube(r['seed'], T, H, W, tuple(r['sigma']))
+        lat, lon = regular_grid(H, W)
+        f, _ = gpu_run(eng, x, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
+        assert sha_i4(f) == r['sha256'], r
+
+
+def test_stale_box_quirk_vectors(eng, golden):
+    lat, lon = regular_grid(24, 16)
+    for r in golden['quirk']:
+        T, H, W = r['shape']
+        x = synth_cube(r['seed'], T, H, W, tuple(r['sigma']))
+        f, _ = gpu_run(eng, x, lat, lon, r['threshold'], '>=', 0.0, r['persistence'], False)
+        assert sha_i4(f) == r['sha256'], r['seed']
+
+
+def test_stale_box_splits(eng):
+    lat, lon = regular_grid(24, 16)
+    for seed in [1396, 1933, 2136, 2257]:
+        x = synth_cube(seed, 12, 24, 16, (1.5, 2, 2))
+        f, _ = gpu_run(eng, x, lat, lon, 60, '>=', 0.0, 1, False)
+        assert eng.stats()['seam_splits'] > 0
+        assert np.array_equal(f, oracle.track_persistence((x >= 60).astype(int), 1)), seed
+
+
+@pytest.mark.parametrize('shape', [(12, 24, 16), (9, 33, 47), (7, 40, 130), (6, 19, 1031), (5, 64, 2052), (3, 1, 5),
+                                   (1, 8, 8), (2, 5, 1)])
+def test_random_cubes_odd_shapes(eng, shape):
+    T, H, W = shape
+    for seed in range(3):
+        x = synth_cube(100 * T + seed, T, H, W, (1.0, min(2, H / 4), min(3, W / 4)))
+        lat = (60 - np.arange(H) * 1.5).astype(np.float32) if H > 1 else np.array([10.0, 8.5], np.float32)[:H]
+        lon = (np.arange(W) * 0.25).astype(np.float32)
+        if H < 2 or W < 2:
+            # the reference cannot derive a resolution from a single coordinate: feed the weights directly
+            w = np.ones(H)
+            import torch
+            flag, _ = eng.run_contrack(torch.from_numpy(x).cuda(), w, 50, True, 0, 0.5, 1, True)
+            assert flag.shape == (T, H, W)
+            continue
+        for two, gorl, thr in [(True, '>=', 50), (False, '<', -40)]:
+            ref = oracle.run_contrack(x, lat, lon, thr, gorl, 0.4, 2, two)
+            f, _ = gpu_run(eng, x, lat, lon, thr, gorl, 0.4, 2, two)
+            assert np.array_equal(f, ref), (shape, seed, two)
+
+
+def test_ops_and_compare_precision(eng):
+    x = synth_cube(7, 8, 30, 64, (1.0, 2, 3))
+    lat, lon = regular_grid(30, 64)
+    v = float(x[3, 10, 20])                                      # a threshold that is an actual data value
+    for gorl in ['>=', 'ge', '<=', 'le', '>', 'gt', '<', 'lt']:
+        ref = oracle.run_contrack(x, lat, lon, v, gorl, 0.3, 1, True)
+        f, _ = gpu_run(eng, x, lat, lon, v, gorl, 0.3, 1, True)
+        assert np.array_equal(f, ref), gorl
+    thr = 150.7                                                  # float32(150.7) > 150.7: float32 vs float64 compare differ
+    x2 = x.copy()
+    x2[2, 5:9, 5:9] = np.float32(150.7)
+    ref32 = oracle.run_contrack(x2, lat, lon, thr, '>=', 0.0, 1, False)
+    ref64 = oracle.run_contrack(x2, lat, lon, np.float64(thr), '<=', 0.0, 1, False)
+    f32, _ = gpu_run(eng, x2, lat, lon, thr, '>=', 0.0, 1, False, thr_is_f32=True)
+    f64, _ = gpu_run(eng, x2, lat, lon, thr, '<=', 0.0, 1, False, thr_is_f32=False)
+    assert np.array_equal(f32, ref32) and np.array_equal(f64, ref64)
+
+
+def test_float64_input_and_nan(eng):
+    x = synth_cube(11, 10, 24, 48, (1.0, 2, 3)).astype(np.float64)
+    x[4, 3:6, :] = np.nan
+    lat, lon = regular_grid(24, 48)
+    ref = oracle.run_contrack(x, lat, lon, 40.0, '>=', 0.3, 2, True)
+    f, _ = gpu_run(eng, x, lat, lon, 40.0, '>=', 0.3, 2, True)
+    assert np.array_equal(f, ref)
+
+
+def test_per_timestep_thresholds(eng):
+    x = synth_cube(13, 10, 24, 48, (1.0, 2, 3))
+    lat, lon = regular_grid(24, 48)
+    thr = np.linspace(20, 80, 10)
+    ref = oracle.run_contrack(x, lat, lon, thr, '>=', 0.3, 2, True)
+    f, _ = gpu_run(eng, x, lat, lon, thr, '>=', 0.3, 2, True, thr_is_f32=False)
+    assert np.array_equal(f, ref)
+
+
+def test_empty_and_full_masks(eng):
+    lat, lon = regular_grid(24, 48)
+    x = np.zeros((6, 24, 48), np.float32)
+    f, n = gpu_run(eng, x, lat, lon, 1.0, '>=', 0.5, 1, True)
+    assert n == 0 and not f.any()
+    ref = oracle.run_contrack(x, lat, lon, -1.0, '>=', 0.5, 1, True)
+    f, n = gpu_run(eng, x, lat, lon, -1.0, '>=', 0.5, 1, True)
+    assert np.array_equal(f, ref) and n == 1
+
+
+def test_host_buffers_match_device(eng):
+    x = synth_cube(5, 24, 181, 360, (2.0, 4, 6))
+    lat, lon = regular_grid(181, 360)
+    w = row_weights(lat, lon)
+    ref = oracle.run_contrack(x, lat, lon, 150, 'ge', 0.7, 4, True)
+    f, n = eng.run_contrack(x, w, 150, True, 0, 0.7, 4, True, chunk_planes=5)      # numpy in -> numpy out, 5 chunks
+    assert isinstance(f, np.ndarray) and np.array_equal(f, ref)
+    assert n == len(np.unique(ref)) - 1
+
+
+def test_pole_rows_are_special(eng, fixture_cube):
+    a, lat, lon = fixture_cube
+    gpu_run(eng, a, lat, lon, 150, '>=', .5, 5, True)
+    assert eng.stats()['special_rows'] == 2        # cos(float32(pi/2)) rows: not exactly summable with the rest
+
+
+def test_medium_cube_against_oracle(eng):
+    # 0.25-degree rows (721 x 1440) for a few steps: the benchmark grid, oracle still finishes in seconds
+    x = synth_cube(2, 12, 721, 1440, (2.5, 24, 40))
+    lat = np.linspace(90, -90, 721).astype(np.float32)
+    lon = (np.arange(1440) * 0.25).astype(np.float32)
+    ref = oracle.run_contrack(x, lat, lon, 160, '>=', 0.5, 5, True, force=True)
+    w = oracle.weight_grid(lat, oracle.resolution(lat, True), oracle.resolution(lon, True), 1440)[:, 0].copy()
+    import torch
+    f, n = eng.run_contrack(torch.from_numpy(x).cuda(), w, 160, True, 0, 0.5, 5, True)
+    assert np.array_equal(f.cpu().numpy(), ref)

@@ -1,0 +1,65 @@
+"""The oracle against every pin the reference offers for this path -- CPU only."""
+import numpy as np
+import pytest
+
+from oracle import contrack_oracle as oracle
+from _common import sha_i4
+from _synth import synth_cube, regular_grid
+
+
+def test_reference_test_pins(fixture_cube):
+    # reference tests/test_contrack.py:83-91 (3 features) and 93-103 (28 lifecycle rows = (t, id) pairs)
+    a, lat, lon = fixture_cube
+    f = oracle.run_contrack(a, lat, lon, 150, '>=', 0.5, 5, twosided=False)
+    assert oracle.num_features(f) == 3
+    assert sum(len(np.unique(f[t])) - 1 for t in range(f.shape[0])) == 28
+    assert f.dtype == np.int32 and f.shape == a.shape
+
+
+def test_fixture_golden_hashes(fixture_cube, golden):
+    a, lat, lon = fixture_cube
+    for r in golden['fixture']:
+        f = oracle.run_contrack(a, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
+        assert sha_i4(f) == r['sha256'], r['key']
+        assert [int(i) for i in np.unique(f)[1:]] == r['ids']
+        assert int((f > 0).sum()) == r['nonzero']
+
+
+def test_survey_recorded_hashes(golden):
+    # sha256 prefixes recorded independently in SURVEY.md section 8(c)
+    want = {'thr150_ov05_p5_one': 'c392d20e9e2a626d', 'thr150_ov05_p5_two': '5c0d724cfe86d530',
+            'thr160_ov05_p5_two': '1cb7c70a5c95dcc9', 'thr100_ov07_p3_two': 'fde4c3db10975813'}
+    got = {r['key']: r['sha256'][:16] for r in golden['fixture']}
+    assert got == want
+
+
+def test_synthetic_golden(golden):
+    for r in golden['synthetic']:
+        T, H, W = r['shape']
+        x = synth_cube(r['seed'], T, H, W, tuple(r['sigma']))
+        lat, lon = regular_grid(H, W)
+        f = oracle.run_contrack(x, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
+        assert sha_i4(f) == r['sha256']
+
+
+def test_stale_box_quirk_vectors(golden):
+    for r in golden['quirk']:
+        T, H, W = r['shape']
+        x = synth_cube(r['seed'], T, H, W, tuple(r['sigma']))
+        f = oracle.track_persistence((x >= r['threshold']).astype(int), r['persistence'])
+        assert sha_i4(f) == r['sha256']
+        assert [int(i) for i in np.unique(f)[1:]] == r['ids']
+
+
+def test_bad_gorl_raises(fixture_cube):
+    a, lat, lon = fixture_cube
+    with pytest.raises(ValueError, match='Please select from'):
+        oracle.run_contrack(a, lat, lon, 150, '=>', 0.5, 5)
+
+
+def test_rolling_mean_convention():
+    x = np.arange(6, dtype=np.float32)[:, None]
+    r2 = oracle._rolling_mean_centered(x, 2)[:, 0]
+    assert np.isnan(r2[0]) and np.allclose(r2[1:], [0.5, 1.5, 2.5, 3.5, 4.5])
+    r3 = oracle._rolling_mean_centered(x, 3)[:, 0]
+    assert np.isnan(r3[0]) and np.isnan(r3[-1]) and np.allclose(r3[1:-1], [1, 2, 3, 4])

@@ -8,7 +8,13 @@ SRC       := contrack_b200/csrc
 OUT       := contrack_b200/lib
 LIB       := $(OUT)/libcontrack_b200.so
 
-all: $(LIB)
+SYNTH     := bench_support/libct_synth.so
+
+all: $(LIB) $(SYNTH)
+
+# benchmark tooling only (synthetic input generator); not linked into the product library
+$(SYNTH): bench_support/ct_synth.cu
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared -o $@ $< -lcudart_static -lpthread -ldl -lrt
 
 $(OUT)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) include/contrack_b200.h
 	@mkdir -p $(OUT)
@@ -22,6 +28,6 @@ $(LIB): $(OUT)/ct_kernels.o $(OUT)/ct_api.o $(OUT)/ct_host.o $(OUT)/ct_tables.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart_static -lpthread -ldl -lrt
 
 clean:
-	rm -rf $(OUT)
+	rm -rf $(OUT) $(SYNTH)
 
 .PHONY: all clean

@@ -1,0 +1,339 @@
+#!/usr/bin/env python3
+"""bench.py -- timesteps/s of run_contrack on a synthetic 721x1440 Z500-anomaly cube (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--T 10957] [--impl reference]
+
+One "step" = one complete run_contrack pass (threshold -> 2-D labelling -> overlap filter -> 3-D tracking -> persistence
+-> int32 flag cube) over the whole [T, 721, 1440] cube.  `value` = T*K / (CUDA-event time of K steps), inputs and
+outputs resident in HBM; `e2e` = the same pass through the host-buffer entry point (pinned host float32 in, int32 out,
+copies inside the timed region); `roofline` = the dominant kernel against MEASURED_PEAKS.json; `cpu_baseline` = the
+reference algorithm (oracle/: same scipy calls, same loops) on a bounded sub-cube on this box's host, 1 thread.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+H, W = 721, 1440
+SIGMA = (2.5, 24.0, 40.0)        # (2.5 steps, 6 deg, 10 deg) at 0.25 deg
+THRESHOLD, GORL, OVERLAP, PERSISTENCE, TWOSIDED = 160, '>=', 0.5, 5, True
+SEED = 2
+
+
+def grid():
+    lat = np.linspace(90, -90, H).astype(np.float32)
+    lon = (np.arange(W) * (360.0 / W)).astype(np.float32)
+    return lat, lon
+
+
+def reference_weights(lat, lon):
+    """contrack.py:703-704 with dlat = dlon = 0.25 (set_up(force=True) on the float32 linspace grid)."""
+    weight_lat = np.cos(lat * np.pi / 180)
+    w = np.array((111 * np.float32(0.25) * 111 * np.float32(0.25) * weight_lat)).astype(np.float32)
+    return w.astype(np.float64)
+
+
+_synth = None
+
+
+def synth_fill(out, t0, T_total, seed=SEED, season=False):
+    """Fill the CUDA float32 tensor out[nt, H, W] with planes [t0, t0+nt) of the synthetic cube (bench_support/)."""
+    global _synth
+    import torch
+    if _synth is None:
+        _synth = C.CDLL(os.path.join(ROOT, 'bench_support', 'libct_synth.so'))
+        _synth.ct_synth_fill.restype = C.c_int
+        _synth.ct_synth_fill.argtypes = [C.c_void_p, C.c_ulonglong, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int,
+                                         C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         C.c_void_p]
+    nt, h, w = out.shape
+    rc = _synth.ct_synth_fill(C.c_void_p(out.data_ptr()), seed, t0, nt, T_total, h, w, SIGMA[0],
+                              SIGMA[1] * h / 721.0, SIGMA[2] * w / 1440.0, 100.0, 60.0 if season else 0.0, 365.25,
+                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        raise RuntimeError('ct_synth_fill failed: cudaError %d' % rc)
+    return out
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured'
+    except Exception:
+        return 6650.0, 'fallback'
+
+
+def cpu_reference_run(x, lat, lon):
+    """The reference algorithm on the host (oracle restatement: same scipy.ndimage calls, same Python loops)."""
+    from oracle import contrack_oracle as oracle
+    t0 = time.perf_counter()
+    f = oracle.run_contrack(x, lat, lon, THRESHOLD, GORL, OVERLAP, PERSISTENCE, TWOSIDED, force=True)
+    return f, time.perf_counter() - t0
+
+
+def make_sample(T_sub, use_gpu):
+    """[T_sub, H, W] float32 host array of the benchmark's synthetic field (first T_sub planes of a T_sub-long cube)."""
+    if use_gpu:
+        import torch
+        d = torch.empty((T_sub, H, W), dtype=torch.float32, device='cuda')
+        synth_fill(d, 0, T_sub)
+        torch.cuda.synchronize()
+        return d.cpu().numpy()
+    from _synth import synth_cube
+    return synth_cube(SEED, T_sub, H, W, SIGMA)
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference itself cannot be imported here: xarray is
+    missing) on bounded samples of the same workload, one sample per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    try:
+        import torch
+        use_gpu = torch.cuda.is_available()
+    except Exception:
+        use_gpu = False
+    T_sub = args.cpu_T
+    lat, lon = grid()
+    x = make_sample(T_sub, use_gpu)
+    for _ in range(args.warmup):
+        cpu_reference_run(x, lat, lon)
+    t = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_reference_run(x, lat, lon)
+        t += dt
+    v = T_sub * args.steps / t
+    line = {'impl': 'reference', 'metric': 'timesteps/sec (721x1440 grid) run_contrack', 'value': v,
+            'unit': 'timesteps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32 compare / f64 areas / int32 labels', 'data': 'synthetic',
+            'config': workload_config(args.T, args.gpus),
+            'cpu_baseline': {'value': v, 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port',
+                             'host_cores': os.cpu_count(),
+                             'sample': '%d consecutive steps of the %dx%d cube as a standalone cube per step; the path '
+                                       'is single-threaded (1 core used of %d)' % (T_sub, H, W, os.cpu_count())},
+            'e2e': {'value': v, 'unit': 'timesteps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(T, n):
+    return {'workload': 'run_contrack on synthetic %dx%dx%d Z500 anomaly (seed %d, sigma %s cells), threshold=%d %s '
+                        'overlap=%.1f persistence=%d twosided=%s' % (T, H, W, SEED, SIGMA, THRESHOLD, GORL, OVERLAP,
+                                                                     PERSISTENCE, TWOSIDED),
+            'T': T, 'H': H, 'W': W, 'sharding': 'time x%d' % n,
+            'l2': 'inputs (%.1f GB) and outputs far exceed the 126 MB L2; no explicit flush' % (T * H * W * 4 / 1e9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--T', type=int, default=10957, help='time steps of the cube (BASELINE.json: 10957 daily steps)')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-T', type=int, default=0, help='time steps of the CPU-baseline sample')
+    ap.add_argument('--e2e-T', type=int, default=0, help='time steps of the end-to-end (host buffer) measurement')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--tma', type=int, default=-1)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        if not args.cpu_T:
+            args.cpu_T = 64
+        return run_reference_arm(args)
+    if not args.cpu_T:
+        args.cpu_T = 256
+
+    import torch
+    import torch.distributed as dist
+    from contrack_b200 import Engine
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the product path has no CPU fallback)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if world > 1:
+        raise SystemExit('multi-GPU sharding is not wired into bench.py yet')
+
+    T = args.T
+    lat, lon = grid()
+    w = reference_weights(lat, lon)
+    eng = Engine.get(local)
+    if args.tma >= 0:
+        eng.set_option('tma', args.tma)
+
+    anom = torch.empty((T, H, W), dtype=torch.float32, device='cuda')
+    t_gen = time.perf_counter()
+    synth_fill(anom, 0, T)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    flag = torch.empty((T, H, W), dtype=torch.int32, device='cuda')
+
+    def step():
+        return eng.run_contrack(anom, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=flag)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_thr, ms_paint, ms_host, ms_tab, ms_zero = [], [], [], [], []
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            _, nfeat = step()
+            s = eng.stats()
+            ms_thr.append(s['ms_threshold']); ms_paint.append(s['ms_paint']); ms_host.append(s['ms_host_tables'])
+            ms_tab.append(s['ms_tables_gpu'] + s['ms_tables_host_roundtrip'])
+            ms_zero.append(s.get('ms_zero_fill', 0.0))
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    stats = eng.stats()
+    value = T * args.steps / (ms / 1e3)
+    peak, peak_kind = measured_peak()
+    cells = T * H * W
+    thr_ms, paint_ms = float(np.mean(ms_thr)), float(np.mean(ms_paint))
+    dom = ('threshold_bits', thr_ms) if thr_ms >= paint_ms else ('paint', paint_ms)
+    achieved = cells * 4 / (dom[1] / 1e3) / 1e9
+    path_gbs = cells * 8 / (ms / args.steps / 1e3) / 1e9
+
+    line = {'metric': 'timesteps/sec (721x1440 grid) run_contrack', 'value': value, 'unit': 'timesteps/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32 compare / f64 areas / int32 labels', 'data': 'synthetic',
+            'config': workload_config(T, world),
+            'features': int(nfeat), 'gpu_launches': int(stats['kernel_launches']) * args.steps,
+            'clocks': clocks.summary(),
+            'roofline': {'bound': 'hbm', 'kernel': dom[0], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': None,
+                         'algorithmic_bytes_per_launch': cells * 4,
+                         'note': '4 B/cell (float32 read for threshold_bits, int32 write for paint) x %d cells per '
+                                 'launch / CUDA-event time of that kernel' % cells},
+            'roofline_path': {'achieved': path_gbs, 'frac': path_gbs / peak, 'unit': 'GB/s',
+                              'note': '8 B/cell (read anomaly once + write flag once) / whole step time'},
+            'breakdown_ms': {'threshold_bits': thr_ms, 'paint': paint_ms, 'tables_gpu_and_host': float(np.mean(ms_tab)),
+                             'host_table_phase': float(np.mean(ms_host)),
+                             'zero_fill_overlapped_with_tables': float(np.mean(ms_zero))},
+            'tables': {k: int(stats[k]) for k in ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d',
+                                                  'seam_events', 'seam_splits', 'neartie_resolved') if k in stats},
+            'synth_seconds': t_gen}
+
+    # ---- CPU baseline + parity on a bounded sample -------------------------------------------------------------------
+    if not args.no_cpu:
+        Ts = min(args.cpu_T, T)
+        sub = anom[:Ts].contiguous()
+        x = sub.cpu().numpy()
+        ref, dt = cpu_reference_run(x, lat, lon)
+        got, _ = eng.run_contrack(sub, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED)
+        line['cpu_baseline'] = {'value': Ts / dt, 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port',
+                                'host_cores': os.cpu_count(), 'seconds': dt,
+                                'sample': 'first %d steps of the cube as a standalone cube (the reference holds int64 '
+                                          'cubes and cannot run all %d steps on the host); single-threaded path: 1 core '
+                                          'used of %d' % (Ts, T, os.cpu_count()),
+                                'bit_exact_vs_gpu': bool(np.array_equal(got.cpu().numpy(), ref))}
+        del sub, got
+
+    # ---- end to end through the host-buffer entry point --------------------------------------------------------------
+    if not args.no_e2e:
+        del flag
+        avail = 0
+        try:
+            for ln in open('/proc/meminfo'):
+                if ln.startswith('MemAvailable'):
+                    avail = int(ln.split()[1]) * 1024
+        except Exception:
+            pass
+        Te = args.e2e_T or min(T, 2707)
+        per_plane = H * W * 8
+        if avail:
+            Te = max(16, min(Te, int(0.45 * avail // per_plane)))
+        xin = torch.empty((Te, H, W), dtype=torch.float32, pin_memory=True)
+        xin.copy_(anom[:Te])
+        fout = torch.empty((Te, H, W), dtype=torch.int32, pin_memory=True)
+        xin_np, fout_np = xin.numpy(), fout.numpy()
+        torch.cuda.synchronize()
+        eng.run_contrack(xin_np, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=fout_np)      # warm-up
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            _, nf = eng.run_contrack(xin_np, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=fout_np)
+        dt = time.perf_counter() - t0
+        s = eng.stats()
+        line['e2e'] = {'value': Te * n_e2e / dt, 'unit': 'timesteps/s', 'h2d_bytes_per_step': Te * H * W * 4,
+                       'd2h_bytes_per_step': Te * H * W * 4, 'T': Te, 'steps': n_e2e, 'features': int(nf),
+                       'ms_h2d_threshold': s.get('ms_h2d_threshold'), 'ms_tables': s.get('ms_tables'),
+                       'ms_paint_d2h': s.get('ms_paint_d2h'),
+                       'note': 'ct_run_contrack_host: pinned host float32 cube in, int32 flag cube out, chunked copies '
+                               'overlapped with the kernels; wall clock around the call'}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -88,12 +89,18 @@ struct ct_ctx {
     DevBuf c_t, c_y0, c_y1, c_x0, c_x1, c_E, c_S, c_nsp, c_cls, c_val;
     DevBuf s_row, s_a, s_b;
     DevBuf h_key, h_npix, h_nsp, h_E, h_S;
-    DevBuf p_a, p_b, p_npix, p_nsp, p_E, p_S;
+    DevBuf p_b, p_npix, p_nsp, p_E, p_S;
+    DevBuf k_conE, k_conS, k_fE, k_fS, k_nsp, pcnt, pfill, pptr;
+    DevBuf seg_start, seg_pos, g_t, g_y0, g_y1, g_a, g_b;
     DevBuf o_t, o_y, o_x0, o_x1, o_val;
     DevBuf w_dev, special_dev, thr_dev;
     DevBuf chunk_in[2], chunk_out[2];
     // pinned host staging
-    PinBuf hp_counters, hp_tables, hp_val;
+    PinBuf hp_counters, hp_tables, hp_val, hp_ovr;
+    cth::Result host_result;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_side[2] = {nullptr, nullptr};
+    long opt_overlap_zero = 1;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t copy_stream = nullptr, work_stream = nullptr;
     std::map<std::string, double> stats;
@@ -235,15 +242,14 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
     const int H = c->H, W = c->W;
     uint32_t* cnt_dev = c->counters.as<uint32_t>();
     uint32_t* cnt_host = c->hp_counters.as<uint32_t>();
+    auto U = [](DevBuf& b) { return b.as<uint32_t>(); };
 
     CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(nrows > 1024 ? nrows : 1024) * sizeof(uint32_t)));
-    CT_CUDA(ctk::exclusive_scan_u32(c->row_cnt.as<uint32_t>(), c->row_ptr.as<uint32_t>(), nrows,
-                                    c->scan_tmp.as<uint32_t>(), st));
-    CT_CUDA(ctk::exclusive_scan_u32(c->seam_flag.as<uint32_t>(), c->seam_pos.as<uint32_t>(), nrows,
-                                    c->scan_tmp.as<uint32_t>(), st));
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->row_cnt), U(c->row_ptr), nrows, U(c->scan_tmp), st));
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->seam_flag), U(c->seam_pos), nrows, U(c->scan_tmp), st));
     c->launches += 6;
-    CT_CUDA(cudaMemcpyAsync(cnt_host + 0, c->row_ptr.as<uint32_t>() + nrows, 4, cudaMemcpyDeviceToHost, st));
-    CT_CUDA(cudaMemcpyAsync(cnt_host + 1, c->seam_pos.as<uint32_t>() + nrows, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 0, U(c->row_ptr) + nrows, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 1, U(c->seam_pos) + nrows, 4, cudaMemcpyDeviceToHost, st));
     CT_CUDA(cudaStreamSynchronize(st));
     const long R = cnt_host[0], nseam = cnt_host[1];
     c->nruns = R; c->nseam = nseam;
@@ -254,132 +260,173 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
     CT_CUDA(c->root_flag.ensure(rb)); CT_CUDA(c->rank.ensure(rb + 4)); CT_CUDA(c->run_comp.ensure(rb));
     CT_CUDA(c->run_val.ensure(rb));
     CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(R > nrows ? R : nrows) * sizeof(uint32_t)));
-    CT_CUDA(ctk::extract_runs(c->bits.as<uint32_t>(), c->row_ptr.as<uint32_t>(), nrows, c->Ww, c->run_x.as<uint32_t>(),
-                              c->run_row.as<uint32_t>(), st));
-    CT_CUDA(ctk::ccl_init(c->parent.as<uint32_t>(), R, st));
-    CT_CUDA(ctk::ccl_union(c->row_ptr.as<uint32_t>(), c->run_x.as<uint32_t>(), c->run_row.as<uint32_t>(), R, H,
-                           c->parent.as<uint32_t>(), st));
-    CT_CUDA(ctk::ccl_flatten(c->parent.as<uint32_t>(), c->root_flag.as<uint32_t>(), R, st));
-    CT_CUDA(ctk::exclusive_scan_u32(c->root_flag.as<uint32_t>(), c->rank.as<uint32_t>(), R, c->scan_tmp.as<uint32_t>(),
-                                    st));
+    CT_CUDA(ctk::extract_runs(U(c->bits), U(c->row_ptr), nrows, c->Ww, U(c->run_x), U(c->run_row), st));
+    CT_CUDA(ctk::ccl_init(U(c->parent), R, st));
+    CT_CUDA(ctk::ccl_union(U(c->row_ptr), U(c->run_x), U(c->run_row), R, H, U(c->parent), st));
+    CT_CUDA(ctk::ccl_flatten(U(c->parent), U(c->root_flag), R, st));
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->root_flag), U(c->rank), R, U(c->scan_tmp), st));
     c->launches += 7;
-    CT_CUDA(cudaMemcpyAsync(cnt_host + 2, c->rank.as<uint32_t>() + R, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 2, U(c->rank) + R, 4, cudaMemcpyDeviceToHost, st));
     CT_CUDA(cudaStreamSynchronize(st));
     const long nc = cnt_host[2];
     c->ncomp = nc;
 
-    // ---- component, date-line and pair tables ----
-    CT_CUDA(ctk::ccl_assign(c->parent.as<uint32_t>(), c->rank.as<uint32_t>(), c->run_comp.as<uint32_t>(), R, st));
-    const size_t cb4 = (size_t)(nc + 1) * 4, cb8 = (size_t)(nc + 1) * 8;
+    // ---- component tables, date-line rows and classes ----
+    CT_CUDA(ctk::ccl_assign(U(c->parent), U(c->rank), U(c->run_comp), R, st));
+    const size_t cb4 = (size_t)(nc + 2) * 4, cb8 = (size_t)(nc + 2) * 8;
     CT_CUDA(c->c_t.ensure(cb4)); CT_CUDA(c->c_y0.ensure(cb4)); CT_CUDA(c->c_y1.ensure(cb4));
     CT_CUDA(c->c_x0.ensure(cb4)); CT_CUDA(c->c_x1.ensure(cb4)); CT_CUDA(c->c_E.ensure(cb8));
     CT_CUDA(c->c_S.ensure(cb8)); CT_CUDA(c->c_nsp.ensure(cb4)); CT_CUDA(c->c_cls.ensure(cb4));
     CT_CUDA(c->c_val.ensure(cb4));
+    CT_CUDA(c->k_conE.ensure(cb8)); CT_CUDA(c->k_conS.ensure(cb8)); CT_CUDA(c->k_fE.ensure(cb8));
+    CT_CUDA(c->k_fS.ensure(cb8)); CT_CUDA(c->k_nsp.ensure(cb4));
+    CT_CUDA(c->pcnt.ensure(cb4)); CT_CUDA(c->pfill.ensure(cb4)); CT_CUDA(c->pptr.ensure(cb4 + 4));
     ctk::CompTables ct;
     ct.t = c->c_t.as<int32_t>(); ct.y0 = c->c_y0.as<int32_t>(); ct.y1 = c->c_y1.as<int32_t>();
     ct.x0 = c->c_x0.as<int32_t>(); ct.x1 = c->c_x1.as<int32_t>(); ct.areaE = c->c_E.as<double>();
-    ct.areaS = c->c_S.as<double>(); ct.nsp = c->c_nsp.as<uint32_t>(); ct.cls = c->c_cls.as<uint32_t>();
+    ct.areaS = c->c_S.as<double>(); ct.nsp = U(c->c_nsp); ct.cls = U(c->c_cls);
+    ctk::ClassTables kt;
+    kt.conE = c->k_conE.as<double>(); kt.conS = c->k_conS.as<double>(); kt.fE = c->k_fE.as<double>();
+    kt.fS = c->k_fS.as<double>(); kt.nsp = U(c->k_nsp);
     CT_CUDA(ctk::comp_init(ct, nc, W, st));
-    CT_CUDA(ctk::comp_accumulate(c->run_x.as<uint32_t>(), c->run_row.as<uint32_t>(), c->run_comp.as<uint32_t>(), R, H,
-                                 c->w_dev.as<double>(), c->special_dev.as<uint8_t>(), ct, st));
-    const size_t sb = (size_t)(nseam + 1) * 4;
+    CT_CUDA(ctk::comp_accumulate(U(c->run_x), U(c->run_row), U(c->run_comp), R, H, c->w_dev.as<double>(),
+                                 c->special_dev.as<uint8_t>(), ct, st));
+    const size_t sb = (size_t)(nseam + 2) * 4;
     CT_CUDA(c->s_row.ensure(sb)); CT_CUDA(c->s_a.ensure(sb)); CT_CUDA(c->s_b.ensure(sb));
-    CT_CUDA(ctk::seam_rows(c->seam_flag.as<uint32_t>(), c->seam_pos.as<uint32_t>(), c->row_ptr.as<uint32_t>(),
-                           c->run_comp.as<uint32_t>(), nrows, c->s_row.as<uint32_t>(), c->s_a.as<uint32_t>(),
-                           c->s_b.as<uint32_t>(), ct.cls, st));
+    CT_CUDA(c->seg_start.ensure(sb)); CT_CUDA(c->seg_pos.ensure(sb + 4));
+    CT_CUDA(c->g_t.ensure(sb)); CT_CUDA(c->g_y0.ensure(sb)); CT_CUDA(c->g_y1.ensure(sb)); CT_CUDA(c->g_a.ensure(sb));
+    CT_CUDA(c->g_b.ensure(sb));
+    CT_CUDA(ctk::seam_rows(U(c->seam_flag), U(c->seam_pos), U(c->row_ptr), U(c->run_comp), nrows, U(c->s_row),
+                           U(c->s_a), U(c->s_b), ct.cls, st));
     CT_CUDA(ctk::cls_flatten(ct.cls, nc, st));
-    c->launches += 5;
+    ctk::SegTables sg;
+    sg.t = c->g_t.as<int32_t>(); sg.y0 = c->g_y0.as<int32_t>(); sg.y1 = c->g_y1.as<int32_t>();
+    sg.a = U(c->g_a); sg.b = U(c->g_b);
+    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(std::max(std::max(R, nrows), std::max(nc, nseam)) + 1) * 4));
+    CT_CUDA(ctk::seg_flags(U(c->s_row), U(c->s_a), U(c->s_b), nseam, H, U(c->seg_start), st));
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->seg_start), U(c->seg_pos), nseam, U(c->scan_tmp), st));
+    CT_CUDA(ctk::seg_write(U(c->s_row), U(c->s_a), U(c->s_b), U(c->seg_start), U(c->seg_pos), nseam, H, sg, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 3, U(c->seg_pos) + nseam, 4, cudaMemcpyDeviceToHost, st));
+    c->launches += 10;
 
+    // ---- adjacent-plane pairs: hash accumulate -> CSR over the plane-t component; class sums ----
     long np = 0;
     uint64_t want = (uint64_t)nc * 4;
+    ctk::PairCsr q;
     for (int attempt = 0;; ++attempt) {
         ctk::PairTable pt;
         pt.cap = next_pow2(want);
         CT_CUDA(c->h_key.ensure((size_t)pt.cap * 8)); CT_CUDA(c->h_npix.ensure((size_t)pt.cap * 4));
         CT_CUDA(c->h_nsp.ensure((size_t)pt.cap * 4)); CT_CUDA(c->h_E.ensure((size_t)pt.cap * 8));
         CT_CUDA(c->h_S.ensure((size_t)pt.cap * 8));
-        pt.key = c->h_key.as<unsigned long long>(); pt.npix = c->h_npix.as<uint32_t>();
-        pt.nsp = c->h_nsp.as<uint32_t>(); pt.areaE = c->h_E.as<double>(); pt.areaS = c->h_S.as<double>();
+        pt.key = c->h_key.as<unsigned long long>(); pt.npix = U(c->h_npix);
+        pt.nsp = U(c->h_nsp); pt.areaE = c->h_E.as<double>(); pt.areaS = c->h_S.as<double>();
         pt.overflow = cnt_dev + 4;
-        const uint32_t out_cap = pt.cap;
-        CT_CUDA(c->p_a.ensure((size_t)out_cap * 4)); CT_CUDA(c->p_b.ensure((size_t)out_cap * 4));
-        CT_CUDA(c->p_npix.ensure((size_t)out_cap * 4)); CT_CUDA(c->p_nsp.ensure((size_t)out_cap * 4));
-        CT_CUDA(c->p_E.ensure((size_t)out_cap * 8)); CT_CUDA(c->p_S.ensure((size_t)out_cap * 8));
+        CT_CUDA(c->p_b.ensure((size_t)pt.cap * 4)); CT_CUDA(c->p_npix.ensure((size_t)pt.cap * 4));
+        CT_CUDA(c->p_nsp.ensure((size_t)pt.cap * 4)); CT_CUDA(c->p_E.ensure((size_t)pt.cap * 8));
+        CT_CUDA(c->p_S.ensure((size_t)pt.cap * 8));
+        q.b = U(c->p_b); q.npix = U(c->p_npix); q.nsp = U(c->p_nsp); q.E = c->p_E.as<double>(); q.S = c->p_S.as<double>();
+        CT_CUDA(cudaMemsetAsync(kt.conE, 0, cb8, st)); CT_CUDA(cudaMemsetAsync(kt.conS, 0, cb8, st));
+        CT_CUDA(cudaMemsetAsync(kt.fE, 0, cb8, st)); CT_CUDA(cudaMemsetAsync(kt.fS, 0, cb8, st));
+        CT_CUDA(cudaMemsetAsync(kt.nsp, 0, cb4, st));
+        CT_CUDA(cudaMemsetAsync(c->pcnt.p, 0, cb4, st)); CT_CUDA(cudaMemsetAsync(c->pfill.p, 0, cb4, st));
+        CT_CUDA(cudaMemsetAsync(cnt_dev + 5, 0, 4, st));
+        CT_CUDA(ctk::class_sums(ct, kt, nc, st));
         CT_CUDA(ctk::pairs_init(pt, st));
-        CT_CUDA(ctk::pairs_accumulate(c->row_ptr.as<uint32_t>(), c->run_x.as<uint32_t>(), c->run_row.as<uint32_t>(),
-                                      c->run_comp.as<uint32_t>(), R, H, c->w_dev.as<double>(),
-                                      c->special_dev.as<uint8_t>(), pt, st));
-        CT_CUDA(ctk::pairs_compact(pt, c->p_a.as<uint32_t>(), c->p_b.as<uint32_t>(), c->p_npix.as<uint32_t>(),
-                                   c->p_nsp.as<uint32_t>(), c->p_E.as<double>(), c->p_S.as<double>(), out_cap,
-                                   cnt_dev + 5, st));
-        c->launches += 3;
+        CT_CUDA(ctk::pairs_accumulate(U(c->row_ptr), U(c->run_x), U(c->run_row), U(c->run_comp), R, H,
+                                      c->w_dev.as<double>(), c->special_dev.as<uint8_t>(), pt, st));
+        CT_CUDA(ctk::pairs_count(pt, ct.cls, kt, U(c->pcnt), cnt_dev + 5, st));
+        CT_CUDA(ctk::exclusive_scan_u32(U(c->pcnt), U(c->pptr), nc, U(c->scan_tmp), st));
+        CT_CUDA(ctk::pairs_fill(pt, U(c->pptr), U(c->pfill), q, st));
+        c->launches += 8;
         CT_CUDA(cudaMemcpyAsync(cnt_host + 4, cnt_dev + 4, 8, cudaMemcpyDeviceToHost, st));
         CT_CUDA(cudaStreamSynchronize(st));
         if (cnt_host[4] == 0 && (uint64_t)cnt_host[5] * 10 <= (uint64_t)pt.cap * 7) { np = cnt_host[5]; break; }
         if (attempt >= 6 || pt.cap >= (1u << 31)) return fail(CT_ERR_CAPACITY, "pair table overflow");
         want = (uint64_t)pt.cap * 4;                                  // too full: probing would crawl
     }
+    const long nseg = nseam ? cnt_host[3] : 0;
     c->npair = np;
     CT_CUDA(cudaEventRecord(c->ev[2], st));
 
-    // ---- tables -> host ----
-    // layout in the pinned buffer: 9 component arrays, 6 pair arrays, 3 date-line arrays (8-byte arrays first)
-    const size_t ncp = (size_t)nc + 2, npp = (size_t)np + 2, nsp_ = (size_t)nseam + 2;
-    size_t bytes = ncp * (2 * 8 + 7 * 4) + npp * (2 * 8 + 4 * 4) + nsp_ * 3 * 4 + 256;
+    // ---- tables -> pinned host memory (8-byte arrays first) ----
+    const size_t ncp = (size_t)nc + 2, npp = (size_t)np + 2, ngp = (size_t)nseg + 2;
+    const size_t bytes = ncp * (4 * 8 + 8 * 4) + npp * (2 * 8 + 3 * 4) + ngp * 5 * 4 + 512;
     CT_CUDA(c->hp_tables.ensure(bytes));
     char* base = c->hp_tables.as<char>();
     size_t off = 0;
     auto take = [&](size_t n, size_t elt) { void* p = base + off; off += ((n * elt + 15) / 16) * 16; return p; };
-    double* hE = (double*)take(ncp, 8); double* hS = (double*)take(ncp, 8);
-    double* hpE = (double*)take(npp, 8); double* hpS = (double*)take(npp, 8);
-    int32_t* ht = (int32_t*)take(ncp, 4); int32_t* hy0 = (int32_t*)take(ncp, 4); int32_t* hy1 = (int32_t*)take(ncp, 4);
-    int32_t* hx0 = (int32_t*)take(ncp, 4); int32_t* hx1 = (int32_t*)take(ncp, 4);
-    uint32_t* hnsp = (uint32_t*)take(ncp, 4); uint32_t* hcls = (uint32_t*)take(ncp, 4);
-    uint32_t* hpa = (uint32_t*)take(npp, 4); uint32_t* hpb = (uint32_t*)take(npp, 4);
-    uint32_t* hpn = (uint32_t*)take(npp, 4); uint32_t* hpnsp = (uint32_t*)take(npp, 4);
-    uint32_t* hsr = (uint32_t*)take(nsp_, 4); uint32_t* hsa = (uint32_t*)take(nsp_, 4);
-    uint32_t* hsb = (uint32_t*)take(nsp_, 4);
+    double* h_conE = (double*)take(ncp, 8); double* h_conS = (double*)take(ncp, 8);
+    double* h_fE = (double*)take(ncp, 8); double* h_fS = (double*)take(ncp, 8);
+    double* h_pE = (double*)take(npp, 8); double* h_pS = (double*)take(npp, 8);
+    int32_t* h_t = (int32_t*)take(ncp, 4); int32_t* h_y0 = (int32_t*)take(ncp, 4); int32_t* h_y1 = (int32_t*)take(ncp, 4);
+    int32_t* h_x0 = (int32_t*)take(ncp, 4); int32_t* h_x1 = (int32_t*)take(ncp, 4);
+    uint32_t* h_cls = (uint32_t*)take(ncp, 4); uint32_t* h_knsp = (uint32_t*)take(ncp, 4);
+    uint32_t* h_pptr = (uint32_t*)take(ncp, 4);
+    uint32_t* h_pb = (uint32_t*)take(npp, 4); uint32_t* h_pn = (uint32_t*)take(npp, 4);
+    uint32_t* h_pnsp = (uint32_t*)take(npp, 4);
+    int32_t* h_gt = (int32_t*)take(ngp, 4); int32_t* h_gy0 = (int32_t*)take(ngp, 4); int32_t* h_gy1 = (int32_t*)take(ngp, 4);
+    uint32_t* h_ga = (uint32_t*)take(ngp, 4); uint32_t* h_gb = (uint32_t*)take(ngp, 4);
     if (off > c->hp_tables.cap) return fail(CT_ERR_INTERNAL, "staging layout overflow");
 #define CT_D2H(dst, src, n, elt) \
     if ((n) > 0) CT_CUDA(cudaMemcpyAsync(dst, (src).p, (size_t)(n) * (elt), cudaMemcpyDeviceToHost, st))
-    CT_D2H(hE, c->c_E, nc, 8); CT_D2H(hS, c->c_S, nc, 8); CT_D2H(ht, c->c_t, nc, 4); CT_D2H(hy0, c->c_y0, nc, 4);
-    CT_D2H(hy1, c->c_y1, nc, 4); CT_D2H(hx0, c->c_x0, nc, 4); CT_D2H(hx1, c->c_x1, nc, 4);
-    CT_D2H(hnsp, c->c_nsp, nc, 4); CT_D2H(hcls, c->c_cls, nc, 4);
-    CT_D2H(hpE, c->p_E, np, 8); CT_D2H(hpS, c->p_S, np, 8); CT_D2H(hpa, c->p_a, np, 4); CT_D2H(hpb, c->p_b, np, 4);
-    CT_D2H(hpn, c->p_npix, np, 4); CT_D2H(hpnsp, c->p_nsp, np, 4);
-    CT_D2H(hsr, c->s_row, nseam, 4); CT_D2H(hsa, c->s_a, nseam, 4); CT_D2H(hsb, c->s_b, nseam, 4);
+    CT_D2H(h_conE, c->k_conE, nc, 8); CT_D2H(h_conS, c->k_conS, nc, 8); CT_D2H(h_fE, c->k_fE, nc, 8);
+    CT_D2H(h_fS, c->k_fS, nc, 8); CT_D2H(h_knsp, c->k_nsp, nc, 4);
+    CT_D2H(h_t, c->c_t, nc, 4); CT_D2H(h_y0, c->c_y0, nc, 4); CT_D2H(h_y1, c->c_y1, nc, 4);
+    CT_D2H(h_x0, c->c_x0, nc, 4); CT_D2H(h_x1, c->c_x1, nc, 4); CT_D2H(h_cls, c->c_cls, nc, 4);
+    CT_D2H(h_pptr, c->pptr, nc + 1, 4);
+    CT_D2H(h_pE, c->p_E, np, 8); CT_D2H(h_pS, c->p_S, np, 8); CT_D2H(h_pb, c->p_b, np, 4);
+    CT_D2H(h_pn, c->p_npix, np, 4); CT_D2H(h_pnsp, c->p_nsp, np, 4);
+    CT_D2H(h_gt, c->g_t, nseg, 4); CT_D2H(h_gy0, c->g_y0, nseg, 4); CT_D2H(h_gy1, c->g_y1, nseg, 4);
+    CT_D2H(h_ga, c->g_a, nseg, 4); CT_D2H(h_gb, c->g_b, nseg, 4);
 #undef CT_D2H
     CT_CUDA(cudaStreamSynchronize(st));
+    if (nc == 0) h_pptr[0] = 0;
+
+    if (const char* dump = getenv("CT_DUMP_TABLES")) {              // debugging aid: tables of this run as raw binary
+        if (FILE* f = fopen(dump, "wb")) {
+            long hdr[8] = {c->T, H, W, nc, np, nseg, 1, 0};
+            fwrite(hdr, sizeof(long), 8, f);
+            fwrite(c->w_host.data(), 8, H, f);
+            fwrite(h_t, 4, nc, f); fwrite(h_y0, 4, nc, f); fwrite(h_y1, 4, nc, f); fwrite(h_x0, 4, nc, f);
+            fwrite(h_x1, 4, nc, f); fwrite(h_cls, 4, nc, f); fwrite(h_conE, 8, nc, f); fwrite(h_conS, 8, nc, f);
+            fwrite(h_fE, 8, nc, f); fwrite(h_fS, 8, nc, f); fwrite(h_knsp, 4, nc, f); fwrite(h_pptr, 4, nc + 1, f);
+            fwrite(h_pb, 4, np, f); fwrite(h_pn, 4, np, f); fwrite(h_pnsp, 4, np, f);
+            fwrite(h_pE, 8, np, f); fwrite(h_pS, 8, np, f);
+            fwrite(h_gt, 4, nseg, f); fwrite(h_gy0, 4, nseg, f); fwrite(h_gy1, 4, nseg, f); fwrite(h_ga, 4, nseg, f);
+            fwrite(h_gb, 4, nseg, f);
+            fclose(f);
+        }
+    }
 
     // ---- ordered table phase on the host ----
     const double t_host0 = now_ms();
-    cth::Tables tb;
-    tb.T = c->T; tb.H = H; tb.W = W;
-    tb.ncomp = nc; tb.comp_t = ht; tb.comp_y0 = hy0; tb.comp_y1 = hy1; tb.comp_x0 = hx0; tb.comp_x1 = hx1;
-    tb.comp_cls = hcls; tb.comp_areaE = hE; tb.comp_areaS = hS; tb.comp_nsp = hnsp;
-    tb.npair = np; tb.pair_a = hpa; tb.pair_b = hpb; tb.pair_npix = hpn; tb.pair_nsp = hpnsp;
-    tb.pair_areaE = hpE; tb.pair_areaS = hpS;
-    tb.nseam = nseam; tb.seam_row = hsr; tb.seam_a = hsa; tb.seam_b = hsb;
+    cth::FastTables tb;
+    tb.T = c->T; tb.H = H; tb.W = W; tb.ncomp = nc;
+    tb.comp_t = h_t; tb.comp_y0 = h_y0; tb.comp_y1 = h_y1; tb.comp_x0 = h_x0; tb.comp_x1 = h_x1; tb.comp_cls = h_cls;
+    tb.cls_conE = h_conE; tb.cls_conS = h_conS; tb.cls_fE = h_fE; tb.cls_fS = h_fS; tb.cls_nsp = h_knsp;
+    tb.pair_ptr = h_pptr; tb.pair_b = h_pb; tb.pair_npix = h_pn; tb.pair_nsp = h_pnsp; tb.pair_E = h_pE; tb.pair_S = h_pS;
+    tb.nseg = nseg; tb.seg_t = h_gt; tb.seg_y0 = h_gy0; tb.seg_y1 = h_gy1; tb.seg_a = h_ga; tb.seg_b = h_gb;
     tb.w = c->w_host.data();
     cth::Params pr;
     pr.overlap = overlap; pr.persistence = persistence; pr.twosided = twosided; pr.stage = stage;
     DeviceRunSource src;
     src.c = c; src.st = st;
-    cth::Result res;
+    CT_CUDA(c->hp_val.ensure((size_t)(nc + 1) * 4));
+    int32_t* hv = c->hp_val.as<int32_t>();
+    cth::Result& res = c->host_result;
     std::string err;
-    int rc = cth::host_phase(tb, pr, &src, res, err);
+    int rc = cth::host_phase_fast(tb, pr, &src, hv, res, err);
     if (rc != 0) return fail(rc, "%s", err.c_str());
     c->stats["ms_host_tables"] = now_ms() - t_host0;
 
     // ---- values back to the device ----
     const long novr = (long)res.overrides.size();
     c->novr = novr;
-    CT_CUDA(c->hp_val.ensure((size_t)(nc + 1) * 4 + (size_t)(novr + 1) * 5 * 4));
-    int32_t* hv = c->hp_val.as<int32_t>();
-    if (nc) memcpy(hv, res.comp_val.data(), (size_t)nc * 4);
     if (nc) CT_CUDA(cudaMemcpyAsync(c->c_val.p, hv, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
     if (novr) {
-        int32_t* ho = hv + nc + 1;
+        CT_CUDA(c->hp_ovr.ensure((size_t)novr * 5 * 4));
+        int32_t* ho = c->hp_ovr.as<int32_t>();
         for (long i = 0; i < novr; ++i) {
             const ctb::Override& o = res.overrides[i];
             ho[i] = o.t; ho[novr + i] = o.y; ho[2 * novr + i] = o.x0; ho[3 * novr + i] = o.x1; ho[4 * novr + i] = o.val;
@@ -393,11 +440,12 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
         CT_CUDA(cudaMemcpyAsync(c->o_x1.p, ho + 3 * novr, ob, cudaMemcpyHostToDevice, st));
         CT_CUDA(cudaMemcpyAsync(c->o_val.p, ho + 4 * novr, ob, cudaMemcpyHostToDevice, st));
     }
-    CT_CUDA(ctk::run_values(c->run_comp.as<uint32_t>(), c->c_val.as<int32_t>(), c->run_val.as<int32_t>(), R, st));
+    CT_CUDA(ctk::run_values(U(c->run_comp), c->c_val.as<int32_t>(), c->run_val.as<int32_t>(), R, st));
     c->launches += 1;
 
     c->stats["runs"] = (double)R; c->stats["comps2d"] = (double)nc; c->stats["pairs"] = (double)np;
-    c->stats["seam_rows"] = (double)nseam; c->stats["kept_comps"] = (double)res.n_kept;
+    c->stats["seam_rows"] = (double)nseam; c->stats["seam_segments"] = (double)nseg;
+    c->stats["kept_comps"] = (double)res.n_kept;
     c->stats["labels3d"] = (double)res.n_labels3d; c->stats["features"] = (double)res.n_features;
     c->stats["seam_events"] = (double)res.n_seam_events; c->stats["seam_splits"] = (double)res.n_seam_splits;
     c->stats["neartie_resolved"] = (double)res.n_neartie; c->stats["override_runs"] = (double)novr;
@@ -406,13 +454,13 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
 }
 
 // paint planes [t0, t0+nt) into `flag_dev` (which starts at plane t0)
-int launch_paint(ct_ctx* c, long t0, long nt, int32_t* flag_dev, cudaStream_t st) {
+int launch_paint(ct_ctx* c, long t0, long nt, int32_t* flag_dev, int sparse, cudaStream_t st) {
     ctk::PaintArgs a;
     const long r0 = t0 * c->H;
     a.bits = c->bits.as<uint32_t>() + (size_t)r0 * c->Ww;
     a.row_ptr = c->row_ptr.as<uint32_t>() + r0;
     a.run_val = c->run_val.as<int32_t>();
-    a.nrows = nt * c->H; a.W = c->W; a.Ww = c->Ww; a.flag = flag_dev;
+    a.nrows = nt * c->H; a.W = c->W; a.Ww = c->Ww; a.flag = flag_dev; a.sparse = sparse;
     CT_CUDA(ctk::paint(a, c->sm_count, st));
     c->launches += 1;
     return CT_OK;
@@ -455,11 +503,15 @@ void ct_destroy(ct_ctx* c) {
                       &c->run_x, &c->run_row, &c->parent, &c->root_flag, &c->rank, &c->run_comp, &c->run_val,
                       &c->c_t, &c->c_y0, &c->c_y1, &c->c_x0, &c->c_x1, &c->c_E, &c->c_S, &c->c_nsp, &c->c_cls, &c->c_val,
                       &c->s_row, &c->s_a, &c->s_b, &c->h_key, &c->h_npix, &c->h_nsp, &c->h_E, &c->h_S,
-                      &c->p_a, &c->p_b, &c->p_npix, &c->p_nsp, &c->p_E, &c->p_S,
+                      &c->p_b, &c->p_npix, &c->p_nsp, &c->p_E, &c->p_S,
+                      &c->k_conE, &c->k_conS, &c->k_fE, &c->k_fS, &c->k_nsp, &c->pcnt, &c->pfill, &c->pptr,
+                      &c->seg_start, &c->seg_pos, &c->g_t, &c->g_y0, &c->g_y1, &c->g_a, &c->g_b,
                       &c->o_t, &c->o_y, &c->o_x0, &c->o_x1, &c->o_val, &c->w_dev, &c->special_dev, &c->thr_dev,
                       &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0], &c->chunk_out[1]};
     for (DevBuf* b : bufs) b->release();
-    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release();
+    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release();
+    for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->work_stream) cudaStreamDestroy(c->work_stream);
@@ -470,6 +522,7 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!c || !key) return fail(CT_ERR_ARG, "null argument");
     if (!strcmp(key, "tma")) { c->opt_tma = value; return CT_OK; }
     if (!strcmp(key, "paint_tma")) { c->opt_paint_tma = value; return CT_OK; }
+    if (!strcmp(key, "overlap_zero")) { c->opt_overlap_zero = value; return CT_OK; }
     return fail(CT_ERR_ARG, "unknown option '%s'", key);
 }
 
@@ -490,9 +543,26 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     CT_CUDA(cudaEventRecord(c->ev[0], st));
     if ((rc = launch_threshold(c, anom_dev, in_dtype, 0, T, thr_n, thr_is_f32, op, st)) != CT_OK) return rc;
     CT_CUDA(cudaEventRecord(c->ev[1], st));
-    if ((rc = table_phase(c, overlap, persistence, twosided, stage, n_features, st)) != CT_OK) return rc;
+    // The table phase is latency-bound (small kernels, three host round trips, the ordered host pass): the zero fill of
+    // the flag cube -- most of the 4 B/cell the path has to write -- runs under it on a side stream; afterwards only the
+    // cells of row-runs are painted.
+    const int sparse = c->opt_overlap_zero ? 1 : 0;
+    if (sparse) {
+        if (!c->side_stream) CT_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        for (auto& e : c->ev_side) if (!e) CT_CUDA(cudaEventCreate(&e));
+        CT_CUDA(cudaEventRecord(c->ev_side[0], st));
+        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+        CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T * H * W, c->sm_count, c->side_stream));
+        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+        c->launches += 1;
+    }
+    if ((rc = table_phase(c, overlap, persistence, twosided, stage, n_features, st)) != CT_OK) {
+        if (sparse) cudaStreamSynchronize(c->side_stream);
+        return rc;
+    }
+    if (sparse) CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
     CT_CUDA(cudaEventRecord(c->ev[3], st));
-    if ((rc = launch_paint(c, 0, T, flag_dev, st)) != CT_OK) return rc;
+    if ((rc = launch_paint(c, 0, T, flag_dev, sparse, st)) != CT_OK) return rc;
     if (c->novr) {
         CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
                                      c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), c->novr, H, W, 0, T, flag_dev, st));
@@ -506,6 +576,7 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stats["ms_tables_host_roundtrip"] = ms;
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats["ms_paint"] = ms;
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats["ms_total"] = ms;
+    if (sparse) { CT_CUDA(cudaEventElapsedTime(&ms, c->ev_side[0], c->ev_side[1])); c->stats["ms_zero_fill"] = ms; }
     c->stats["kernel_launches"] = (double)c->launches;
     return CT_OK;
 }
@@ -572,7 +643,7 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
         const long t0 = k * out_planes, nt = (t0 + out_planes <= T) ? out_planes : T - t0;
         if (k >= 2) CT_CUDA(cudaStreamWaitEvent(ws, out_free[s], 0));
         int32_t* dst = c->chunk_out[s].as<int32_t>();
-        if ((rc = launch_paint(c, t0, nt, dst, ws)) != CT_OK) return rc;
+        if ((rc = launch_paint(c, t0, nt, dst, 0, ws)) != CT_OK) return rc;
         if (c->novr) {
             CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
                                          c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), c->novr, H, W, t0, t0 + nt,

@@ -7,6 +7,9 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace cth {
 
@@ -15,9 +18,9 @@ namespace {
 // contrack.py:721-742 -- reciprocal, then multiply (two roundings), then the keep/kill cascade.
 inline bool kill_decision(double areacon, double fwd, double bwd, double ov, bool twosided, double* fb_out,
                           double* ff_out) {
-    volatile double inv = 1.0 / areacon;
-    volatile double fb = inv * bwd;
-    volatile double ff = inv * fwd;
+    const double inv = 1.0 / areacon;      // three separately rounded operations (-ffp-contract=off, no fast-math)
+    const double fb = inv * bwd;
+    const double ff = inv * fwd;
     *fb_out = fb; *ff_out = ff;
     bool kill = false;
     if (twosided) {
@@ -29,8 +32,6 @@ inline bool kill_decision(double areacon, double fwd, double bwd, double ov, boo
     }
     return kill;
 }
-
-struct Acc { double conE, conS, fE, fS, bE, bS; uint64_t nsp; };
 
 // One fetched plane: runs in raster order + row offsets.
 struct Plane {
@@ -65,16 +66,17 @@ private:
 
 // numpy-order sums for one date-line class at plane t (contrack.py:717-719): np.sum over the boolean-gathered weights in
 // raster order.  `kept` holds the already-final keep state of plane t-1.
-bool exact_class_sums(PlaneCache& pc, const Tables& tb, const std::vector<uint8_t>& kept, long t, uint32_t rep,
-                      double* areacon, double* fwd, double* bwd) {
+// Cold path (near-tie decisions only): kept out of line.
+__attribute__((noinline)) bool exact_class_sums(PlaneCache& pc, const uint32_t* comp_cls, const double* w, const std::vector<uint8_t>& kept,
+                      long t, uint32_t rep, double* areacon, double* fwd, double* bwd) {
     const Plane* cur = pc.get(t);
     const Plane* nxt = pc.get(t + 1);
     const Plane* prv = pc.get(t - 1);
     if (!cur || !nxt || !prv) return false;
     std::vector<double> con, f, b;
     for (const PlaneRun& r : cur->runs) {
-        if (tb.comp_cls[r.comp] != rep) continue;
-        const double wy = tb.w[r.y];
+        if (comp_cls[r.comp] != rep) continue;
+        const double wy = w[r.y];
         con.insert(con.end(), (size_t)(r.x1 - r.x0), wy);
         for (int i = nxt->row_ptr[r.y]; i < nxt->row_ptr[r.y + 1]; ++i) {
             const PlaneRun& q = nxt->runs[i];
@@ -95,10 +97,9 @@ bool exact_class_sums(PlaneCache& pc, const Tables& tb, const std::vector<uint8_
 }
 
 struct SplitFetcher : ctb::RunFetcher {
-    PlaneCache* pc; const Tables* tb; const std::vector<long>* kept_ids;
-    bool fetch(long k, std::vector<ctb::SubRun>& out) override {
-        long c = (*kept_ids)[k];
-        const Plane* p = pc->get(tb->comp_t[c]);
+    PlaneCache* pc; const int32_t* comp_t;
+    bool fetch(long c, std::vector<ctb::SubRun>& out) override {
+        const Plane* p = pc->get(comp_t[c]);
         if (!p) return false;
         out.clear();
         for (const PlaneRun& r : p->runs)
@@ -109,150 +110,210 @@ struct SplitFetcher : ctb::RunFetcher {
 
 }  // namespace
 
-int host_phase(const Tables& tb, const Params& pr, RunSource* runs, Result& out, std::string& err) {
-    const long T = tb.T, nc = tb.ncomp, np = tb.npair;
-    out = Result();
-    out.comp_val.assign(nc, 0);
-    if (pr.stage == 1) { for (long c = 0; c < nc; ++c) out.comp_val[c] = (int32_t)(c + 1); return 0; }
-    if (pr.stage == 2) { for (long c = 0; c < nc; ++c) out.comp_val[c] = (int32_t)(tb.comp_cls[c] + 1); return 0; }
+int host_phase_fast(const FastTables& tb, const Params& pr, RunSource* runs, int32_t* comp_val, Result& out,
+                    std::string& err) {
+    const long T = tb.T, nc = tb.ncomp;
+    out.overrides.clear();
+    out.n_features = out.n_kept = out.n_labels3d = out.n_seam_events = out.n_seam_splits = out.n_neartie = 0;
+    if (pr.stage == 1) { for (long c = 0; c < nc; ++c) comp_val[c] = (int32_t)(c + 1); return 0; }
+    if (pr.stage == 2) { for (long c = 0; c < nc; ++c) comp_val[c] = (int32_t)(tb.comp_cls[c] + 1); return 0; }
 
     PlaneCache pc(runs, tb.H);
+    const bool timing = getenv("CT_HOST_TIMING") != nullptr;
+    auto tnow = [] {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    double tm0 = tnow();
+    auto lap = [&](const char* what) {
+        if (timing) { double t = tnow(); fprintf(stderr, "  host_phase %-10s %.3f ms\n", what, t - tm0); tm0 = t; }
+    };
 
-    // components per plane
-    std::vector<long> plane_ptr(T + 2, 0);
-    for (long c = 0; c < nc; ++c) {
-        if (tb.comp_t[c] < 0 || tb.comp_t[c] >= T || (c > 0 && tb.comp_t[c] < tb.comp_t[c - 1])) {
-            err = "component table not sorted by time"; return -5;
-        }
-        plane_ptr[tb.comp_t[c] + 1]++;
-    }
-    for (long t = 0; t < T; ++t) plane_ptr[t + 1] += plane_ptr[t];
-
-    // pairs bucketed by their plane-t component (a); forward sums per plane-(t-1) component (b)
-    std::vector<uint32_t> pa_ptr(nc + 1, 0), pa_idx(np);
-    std::vector<double> fE(nc, 0.0), fS(nc, 0.0);
-    std::vector<uint32_t> fnsp(nc, 0);
-    for (long p = 0; p < np; ++p) {
-        if (tb.pair_a[p] >= nc || tb.pair_b[p] >= nc) { err = "pair table out of range"; return -5; }
-        pa_ptr[tb.pair_a[p] + 1]++;
-        const uint32_t b = tb.pair_b[p];
-        fE[b] += tb.pair_areaE[p]; fS[b] += tb.pair_areaS[p]; fnsp[b] += tb.pair_nsp[p];
-    }
-    for (long c = 0; c < nc; ++c) pa_ptr[c + 1] += pa_ptr[c];
-    {
-        std::vector<uint32_t> pos(pa_ptr.begin(), pa_ptr.end() - 1);
-        for (long p = 0; p < np; ++p) pa_idx[pos[tb.pair_a[p]]++] = (uint32_t)p;
-    }
-
-    for (long c = 0; c < nc; ++c) {
-        const long rep = (long)tb.comp_cls[c];
-        if (rep > c || rep < plane_ptr[tb.comp_t[c]]) {
-            err = "class representative is not the smallest id of its class (component " + std::to_string(c) + ")";
-            return -5;
-        }
-    }
+    // buffers live across calls (one set per host thread): see ct_tables.cpp
+    struct Workspace {
+        std::vector<uint8_t> kept, verdict;
+        std::vector<double> bE, bS;
+        std::vector<uint32_t> bn, parent;
+        std::vector<int32_t> label, seg_a32, seg_b32;
+    };
+    static thread_local Workspace tls_ws;
+    Workspace& ws = tls_ws;                      // one TLS lookup; raw pointers below keep it out of the loops
+    ws.kept.assign(nc, 1);
+    ws.verdict.resize(nc); ws.bE.resize(nc); ws.bS.resize(nc); ws.bn.resize(nc);
+    ws.parent.resize(nc); ws.label.assign(nc, 0);
+    std::vector<uint8_t>& kept = ws.kept;
+    uint8_t* const verdict = ws.verdict.data();
+    double* const bE = ws.bE.data();
+    double* const bS = ws.bS.data();
+    uint32_t* const bn = ws.bn.data();
+    uint32_t* const parent = ws.parent.data();
+    int32_t* const label = ws.label.data();
+    std::vector<int32_t>&seg_a32 = ws.seg_a32, &seg_b32 = ws.seg_b32;
 
     // ---- step 3: contrack.py:706-742.  Plane t reads plane t-1 AFTER it was filtered and plane t+1 BEFORE. ----
-    std::vector<uint8_t> kept(nc, 1);
-    std::vector<Acc> acc(nc);
+    // (local copies of the table pointers: the byte-typed `kept` / `verdict` stores may alias anything otherwise)
+    const int32_t* const comp_t = tb.comp_t;
+    const uint32_t* const comp_cls = tb.comp_cls;
+    const uint32_t* const pair_ptr = tb.pair_ptr;
+    const uint32_t* const pair_b = tb.pair_b;
+    const uint32_t* const pair_nsp = tb.pair_nsp;
+    const double* const pair_E = tb.pair_E;
+    const double* const pair_S = tb.pair_S;
+    uint8_t* const keptp = kept.data();
     const bool two = pr.twosided != 0;
-    const double band = 1e-9;
-    for (long t = 1; t + 1 < T; ++t) {
-        const long c0 = plane_ptr[t], c1 = plane_ptr[t + 1];
+    const double band = 1e-9, ov = pr.overlap;
+    long c0 = 0;
+    while (c0 < nc && comp_t[c0] < 1) ++c0;                          // plane 0 is never filtered
+    while (c0 < nc) {
+        const long t = comp_t[c0];
+        long c1 = c0;
+        while (c1 < nc && comp_t[c1] == t) ++c1;
+        if (c1 < nc && comp_t[c1] < t) { err = "component table not sorted by time"; return -5; }
+        if (t + 1 >= T) break;                                       // neither is the last plane
         for (long c = c0; c < c1; ++c) {
-            const uint32_t rep = tb.comp_cls[c];
-            if (rep == c) acc[rep] = Acc{0, 0, 0, 0, 0, 0, 0};
-            Acc& a = acc[rep];
-            a.conE += tb.comp_areaE[c]; a.conS += tb.comp_areaS[c]; a.nsp += tb.comp_nsp[c];
-            a.fE += fE[c]; a.fS += fS[c]; a.nsp += fnsp[c];
-            for (uint32_t k = pa_ptr[c]; k < pa_ptr[c + 1]; ++k) {
-                const uint32_t p = pa_idx[k];
-                if (!kept[tb.pair_b[p]]) continue;
-                a.bE += tb.pair_areaE[p]; a.bS += tb.pair_areaS[p]; a.nsp += tb.pair_nsp[p];
+            const long rep = (long)comp_cls[c];
+            // rep must lie in [c0, c].  Written as ONE unsigned comparison on purpose: g++ 13.3 folds the natural
+            // `rep > c || rep < c0` to `true` in the peeled first iteration (c == c0), where it reads
+            // (rep > c0) | (c0 > rep) -- dom2: "Relation adjustment ... combine to produce [1, 1]" (forgets rep == c0).
+            if ((unsigned long)(rep - c0) > (unsigned long)(c - c0)) {
+                err = "class representative is not the smallest id of its class"; return -5;
             }
+            double e = 0.0, s2 = 0.0;
+            uint32_t n = 0;
+            for (uint32_t k = pair_ptr[c]; k < pair_ptr[c + 1]; ++k) {
+                if (!keptp[pair_b[k]]) continue;
+                e += pair_E[k]; s2 += pair_S[k]; n += pair_nsp[k];
+            }
+            if (rep == c) { bE[c] = e; bS[c] = s2; bn[c] = n; }
+            else { bE[rep] += e; bS[rep] += s2; bn[rep] += n; }
         }
         for (long c = c0; c < c1; ++c) {
-            if (tb.comp_cls[c] != c) continue;
-            Acc& a = acc[c];
-            double areacon = a.conE + a.conS, fwd = a.fE + a.fS, bwd = a.bE + a.bS;
+            if ((long)comp_cls[c] != c) continue;
+            const double areacon = tb.cls_conE[c] + tb.cls_conS[c], fwd = tb.cls_fE[c] + tb.cls_fS[c];
+            const double bwd = bE[c] + bS[c];
             double fb, ff;
-            bool kill = kill_decision(areacon, fwd, bwd, pr.overlap, two, &fb, &ff);
-            if (a.nsp > 0) {
+            bool kill = kill_decision(areacon, fwd, bwd, ov, two, &fb, &ff);
+            if (tb.cls_nsp[c] + bn[c] > 0) {
                 // Sums that include special-row weights are not exactly summable: numpy's pairwise order decides the
                 // last bits.  Only a fraction within rounding distance of `overlap` can flip the decision.
-                bool near = (std::fabs(ff - pr.overlap) <= band) || (two && std::fabs(fb - pr.overlap) <= band);
+                const bool near = (std::fabs(ff - ov) <= band) || (two && std::fabs(fb - ov) <= band);
                 if (near) {
                     double ac2, f2, b2;
-                    if (!exact_class_sums(pc, tb, kept, t, (uint32_t)c, &ac2, &f2, &b2)) {
+                    if (!exact_class_sums(pc, comp_cls, tb.w, kept, t, (uint32_t)c, &ac2, &f2, &b2)) {
                         err = "near-tie overlap decision on special rows and no run source to resolve it"; return -4;
                     }
-                    kill = kill_decision(ac2, f2, b2, pr.overlap, two, &fb, &ff);
+                    kill = kill_decision(ac2, f2, b2, ov, two, &fb, &ff);
                     out.n_neartie++;
                 }
             }
-            a.nsp = kill ? 1 : 0;                      // reuse as the class verdict
+            verdict[c] = kill ? 1 : 0;
         }
-        for (long c = c0; c < c1; ++c) kept[c] = acc[tb.comp_cls[c]].nsp ? 0 : 1;
+        for (long c = c0; c < c1; ++c) keptp[c] = verdict[comp_cls[c]] ? 0 : 1;
+        c0 = c1;
     }
-    for (long c = 0; c < nc; ++c) out.n_kept += kept[c];
+    long nkept = 0;
+    for (long c = 0; c < nc; ++c) nkept += kept[c];
+    out.n_kept = nkept;
+    lap("step3");
     if (pr.stage == 3) {
-        for (long c = 0; c < nc; ++c) out.comp_val[c] = kept[c] ? (int32_t)(tb.comp_cls[c] + 1) : 0;
+        for (long c = 0; c < nc; ++c) comp_val[c] = kept[c] ? (int32_t)(tb.comp_cls[c] + 1) : 0;
         return 0;
     }
 
     // ---- step 4a/b: contrack.py:747-751.  3-D components = kept 2-D components joined by common pixels in adjacent
-    // planes; scipy numbers them by first pixel in (t, y, x) order = rank of the smallest member id. ----
-    std::vector<uint32_t> parent(nc);
-    for (long c = 0; c < nc; ++c) parent[c] = (uint32_t)c;
+    // planes; scipy numbers them by first pixel in (t, y, x) order = rank of the smallest member id.  Partners of c are in
+    // the plane before, so they have smaller ids and were processed already. ----
     auto find = [&](uint32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
-    for (long p = 0; p < np; ++p) {
-        const uint32_t a = tb.pair_a[p], b = tb.pair_b[p];
-        if (!kept[a] || !kept[b] || tb.pair_npix[p] == 0) continue;
-        uint32_t ra = find(a), rb = find(b);
-        if (ra == rb) continue;
-        if (ra < rb) parent[rb] = ra; else parent[ra] = rb;
-    }
-    std::vector<int32_t> label(nc, 0);
-    int32_t nlab = 0;
-    for (long c = 0; c < nc; ++c) if (kept[c] && parent[c] == (uint32_t)c) label[c] = ++nlab;
-    for (long c = 0; c < nc; ++c) if (kept[c]) label[c] = label[find((uint32_t)c)];
-    out.n_labels3d = nlab;
-    if (pr.stage == 4) { for (long c = 0; c < nc; ++c) out.comp_val[c] = label[c]; return 0; }
-
-    // ---- step 4c/d on the kept components (ct_tables.cpp) ----
-    std::vector<long> kept_ids;
-    kept_ids.reserve(out.n_kept);
-    std::vector<int32_t> kidx(nc, -1);
-    for (long c = 0; c < nc; ++c) if (kept[c]) { kidx[c] = (int32_t)kept_ids.size(); kept_ids.push_back(c); }
-    const long nk = (long)kept_ids.size();
-    std::vector<int32_t> kt(nk), ky0(nk), ky1(nk), kx0(nk), kx1(nk), klab(nk), kval(nk, 0);
-    for (long k = 0; k < nk; ++k) {
-        const long c = kept_ids[k];
-        kt[k] = tb.comp_t[c]; ky0[k] = tb.comp_y0[c]; ky1[k] = tb.comp_y1[c]; kx0[k] = tb.comp_x0[c];
-        kx1[k] = tb.comp_x1[c]; klab[k] = label[c];
-    }
-    std::vector<int32_t> st, sy0, sy1, sa, sb;
-    for (long s = 0; s < tb.nseam; ++s) {
-        const uint32_t a = tb.seam_a[s], b = tb.seam_b[s];
-        if (a >= nc || b >= nc) { err = "seam table out of range"; return -5; }
-        if (!kept[a] || !kept[b]) continue;
-        const int32_t t = (int32_t)(tb.seam_row[s] / tb.H), y = (int32_t)(tb.seam_row[s] % tb.H);
-        if (!st.empty() && st.back() == t && sy1.back() == y && sa.back() == kidx[a] && sb.back() == kidx[b]) {
-            sy1.back() = y + 1;
-        } else {
-            st.push_back(t); sy0.push_back(y); sy1.push_back(y + 1); sa.push_back(kidx[a]); sb.push_back(kidx[b]);
+    for (long c = 0; c < nc; ++c) {
+        parent[c] = (uint32_t)c;
+        if (!kept[c]) continue;
+        uint32_t m = (uint32_t)c;
+        for (uint32_t k = tb.pair_ptr[c]; k < tb.pair_ptr[c + 1]; ++k) {
+            const uint32_t b = tb.pair_b[k];
+            if (b >= (uint32_t)c) { err = "pair table: partner is not in an earlier plane"; return -5; }
+            if (!kept[b] || tb.pair_npix[k] == 0) continue;
+            const uint32_t r = find(b);
+            if (r == m) continue;
+            if (r < m) { parent[m] = r; m = r; } else parent[r] = m;
         }
     }
+    int32_t nlab = 0;
+    for (long c = 0; c < nc; ++c) {
+        if (!kept[c]) continue;
+        const uint32_t r = find((uint32_t)c);
+        label[c] = (r == (uint32_t)c) ? ++nlab : label[r];
+    }
+    out.n_labels3d = nlab;
+    lap("link3d");
+    if (pr.stage == 4) { memcpy(comp_val, label, (size_t)nc * 4); return 0; }
+
+    // ---- step 4c/d (ct_tables.cpp): removed components carry label 0 and are skipped there ----
+    seg_a32.resize(tb.nseg); seg_b32.resize(tb.nseg);
+    for (long s = 0; s < tb.nseg; ++s) {
+        if (tb.seg_a[s] >= (uint32_t)nc || tb.seg_b[s] >= (uint32_t)nc) { err = "seam table out of range"; return -5; }
+        seg_a32[s] = (int32_t)tb.seg_a[s]; seg_b32[s] = (int32_t)tb.seg_b[s];
+    }
     SplitFetcher fetcher;
-    fetcher.pc = &pc; fetcher.tb = &tb; fetcher.kept_ids = &kept_ids;
+    fetcher.pc = &pc; fetcher.comp_t = tb.comp_t;
     ctb::TrackStats stats;
-    int rc = ctb::track_tables(T, tb.H, tb.W, pr.persistence, nk, kt.data(), ky0.data(), ky1.data(), kx0.data(),
-                               kx1.data(), klab.data(), (long)st.size(), st.data(), sy0.data(), sy1.data(), sa.data(),
-                               sb.data(), runs ? &fetcher : nullptr, kval.data(), out.overrides, stats);
+    int rc = ctb::track_tables(T, tb.H, tb.W, pr.persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0,
+                               tb.comp_x1, label, tb.nseg, tb.seg_t, tb.seg_y0, tb.seg_y1, seg_a32.data(),
+                               seg_b32.data(), runs ? &fetcher : nullptr, comp_val, out.overrides, stats);
     if (rc != 0) { err = "date-line merge needs to split a component and no run source is available"; return -5; }
-    for (long k = 0; k < nk; ++k) out.comp_val[kept_ids[k]] = kval[k];
+    lap("track");
     out.n_features = stats.n_features; out.n_seam_events = stats.n_events; out.n_seam_splits = stats.n_splits;
     return 0;
+}
+
+// Unsorted tables (tests, ct_host_tables) -> the fast layout.
+int host_phase(const Tables& tb, const Params& pr, RunSource* runs, Result& out, std::string& err) {
+    const long nc = tb.ncomp, np = tb.npair;
+    out = Result();
+    out.comp_val.assign(nc, 0);
+    for (long c = 0; c < nc; ++c)
+        if (tb.comp_cls[c] >= (uint32_t)nc) { err = "class table out of range"; return -5; }
+    std::vector<double> conE(nc, 0.0), conS(nc, 0.0), fE(nc, 0.0), fS(nc, 0.0);
+    std::vector<uint32_t> cnsp(nc, 0), pptr(nc + 1, 0), pb(np), pn(np), pnsp(np);
+    std::vector<double> pE(np), pS(np);
+    for (long c = 0; c < nc; ++c) {
+        const uint32_t rep = tb.comp_cls[c];
+        conE[rep] += tb.comp_areaE[c]; conS[rep] += tb.comp_areaS[c]; cnsp[rep] += tb.comp_nsp[c];
+    }
+    for (long p = 0; p < np; ++p) {
+        if (tb.pair_a[p] >= nc || tb.pair_b[p] >= nc) { err = "pair table out of range"; return -5; }
+        pptr[tb.pair_a[p] + 1]++;
+        const uint32_t rep = tb.comp_cls[tb.pair_b[p]];
+        fE[rep] += tb.pair_areaE[p]; fS[rep] += tb.pair_areaS[p]; cnsp[rep] += tb.pair_nsp[p];
+    }
+    for (long c = 0; c < nc; ++c) pptr[c + 1] += pptr[c];
+    {
+        std::vector<uint32_t> pos(pptr.begin(), pptr.end() - 1);
+        for (long p = 0; p < np; ++p) {
+            const uint32_t k = pos[tb.pair_a[p]]++;
+            pb[k] = tb.pair_b[p]; pn[k] = tb.pair_npix[p]; pnsp[k] = tb.pair_nsp[p];
+            pE[k] = tb.pair_areaE[p]; pS[k] = tb.pair_areaS[p];
+        }
+    }
+    std::vector<int32_t> st, sy0, sy1;
+    std::vector<uint32_t> sa, sb;
+    for (long s = 0; s < tb.nseam; ++s) {
+        const int32_t t = (int32_t)(tb.seam_row[s] / tb.H), y = (int32_t)(tb.seam_row[s] % tb.H);
+        if (!st.empty() && st.back() == t && sy1.back() == y && sa.back() == tb.seam_a[s] && sb.back() == tb.seam_b[s]) {
+            sy1.back() = y + 1;
+        } else {
+            st.push_back(t); sy0.push_back(y); sy1.push_back(y + 1); sa.push_back(tb.seam_a[s]); sb.push_back(tb.seam_b[s]);
+        }
+    }
+    FastTables ft;
+    ft.T = tb.T; ft.H = tb.H; ft.W = tb.W; ft.ncomp = nc; ft.comp_t = tb.comp_t; ft.comp_y0 = tb.comp_y0;
+    ft.comp_y1 = tb.comp_y1; ft.comp_x0 = tb.comp_x0; ft.comp_x1 = tb.comp_x1; ft.comp_cls = tb.comp_cls;
+    ft.cls_conE = conE.data(); ft.cls_conS = conS.data(); ft.cls_fE = fE.data(); ft.cls_fS = fS.data();
+    ft.cls_nsp = cnsp.data(); ft.pair_ptr = pptr.data(); ft.pair_b = pb.data(); ft.pair_npix = pn.data();
+    ft.pair_nsp = pnsp.data(); ft.pair_E = pE.data(); ft.pair_S = pS.data();
+    ft.nseg = (long)st.size(); ft.seg_t = st.data(); ft.seg_y0 = sy0.data(); ft.seg_y1 = sy1.data();
+    ft.seg_a = sa.data(); ft.seg_b = sb.data(); ft.w = tb.w;
+    for (long c = 0; c < nc; ++c)
+        if (c > 0 && tb.comp_t[c] < tb.comp_t[c - 1]) { err = "component table not sorted by time"; return -5; }
+    return host_phase_fast(ft, pr, runs, out.comp_val.data(), out, err);
 }
 
 }  // namespace cth

@@ -42,6 +42,29 @@ struct Tables {
     const double* w = nullptr;               // [H] area weight per row (contrack.py:703-704)
 };
 
+// The layout the CUDA kernels deliver (everything the ordered phase reads is sequential in memory):
+// class sums indexed by the representative component, pairs in CSR form over their plane-t component, date-line rows
+// already grouped into segments of consecutive rows with the same two components.
+struct FastTables {
+    long T = 0; int H = 0, W = 0;
+    long ncomp = 0;
+    const int32_t* comp_t = nullptr;
+    const int32_t *comp_y0 = nullptr, *comp_y1 = nullptr, *comp_x0 = nullptr, *comp_x1 = nullptr;
+    const uint32_t* comp_cls = nullptr;
+    // per class, stored at the representative's index: own area and forward overlap (all of plane t+1), E / S parts,
+    // and the number of special-row pixels in those two sums
+    const double *cls_conE = nullptr, *cls_conS = nullptr, *cls_fE = nullptr, *cls_fS = nullptr;
+    const uint32_t* cls_nsp = nullptr;
+    // pairs of component c with components of plane t-1: entries pair_ptr[c] .. pair_ptr[c+1]
+    const uint32_t* pair_ptr = nullptr;
+    const uint32_t *pair_b = nullptr, *pair_npix = nullptr, *pair_nsp = nullptr;
+    const double *pair_E = nullptr, *pair_S = nullptr;
+    long nseg = 0;
+    const int32_t *seg_t = nullptr, *seg_y0 = nullptr, *seg_y1 = nullptr;
+    const uint32_t *seg_a = nullptr, *seg_b = nullptr;
+    const double* w = nullptr;
+};
+
 struct Params {
     double overlap = 0.5;
     int persistence = 1;
@@ -50,12 +73,15 @@ struct Params {
 };
 
 struct Result {
-    std::vector<int32_t> comp_val;           // value painted for each component
+    std::vector<int32_t> comp_val;           // value painted for each component (host_phase only)
     std::vector<ctb::Override> overrides;    // sub-runs of split components (stage FINAL only)
     long n_features = 0, n_kept = 0, n_labels3d = 0, n_seam_events = 0, n_seam_splits = 0, n_neartie = 0;
 };
 
-// returns 0, or a negative ct_status with `err` filled
+// returns 0, or a negative ct_status with `err` filled.  `comp_val` [ncomp] receives the value painted per component.
+int host_phase_fast(const FastTables& tb, const Params& pr, RunSource* runs, int32_t* comp_val, Result& out,
+                    std::string& err);
+// same from the unsorted tables (converts, then calls host_phase_fast); result in out.comp_val
 int host_phase(const Tables& tb, const Params& pr, RunSource* runs, Result& out, std::string& err);
 
 }  // namespace cth

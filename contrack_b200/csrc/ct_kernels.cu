@@ -419,6 +419,67 @@ __global__ void __launch_bounds__(256) k_pairs_compact(PairTable p, uint32_t* __
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// tables in the layout the ordered host phase reads sequentially (ct_host.h: FastTables)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_class_sums(CompTables c, ClassTables k, long ncomp) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncomp) return;
+    const uint32_t rep = c.cls[i];
+    atomicAdd(&k.conE[rep], c.areaE[i]);
+    if (c.nsp[i]) { atomicAdd(&k.conS[rep], c.areaS[i]); atomicAdd(&k.nsp[rep], c.nsp[i]); }
+}
+
+// per occupied slot: count the pair for its plane-t component, add its area to the forward sums of the class of its
+// plane-(t-1) component
+__global__ void __launch_bounds__(256) k_pairs_count(PairTable p, const uint32_t* __restrict__ cls, ClassTables k,
+                                                     uint32_t* __restrict__ pcnt, uint32_t* __restrict__ total) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.cap) return;
+    const unsigned long long key = p.key[i];
+    if (key == PAIR_EMPTY) return;
+    atomicAdd(&pcnt[(uint32_t)(key >> 32)], 1u);
+    atomicAdd(total, 1u);
+    const uint32_t rep = cls[(uint32_t)key];
+    atomicAdd(&k.fE[rep], p.areaE[i]);
+    if (p.nsp[i]) { atomicAdd(&k.fS[rep], p.areaS[i]); atomicAdd(&k.nsp[rep], p.nsp[i]); }
+}
+
+__global__ void __launch_bounds__(256) k_pairs_fill(PairTable p, const uint32_t* __restrict__ pptr,
+                                                    uint32_t* __restrict__ pfill, PairCsr o) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.cap) return;
+    const unsigned long long key = p.key[i];
+    if (key == PAIR_EMPTY) return;
+    const uint32_t a = (uint32_t)(key >> 32);
+    const uint32_t pos = pptr[a] + atomicAdd(&pfill[a], 1u);
+    o.b[pos] = (uint32_t)key; o.npix[pos] = p.npix[i]; o.nsp[pos] = p.nsp[i]; o.E[pos] = p.areaE[i]; o.S[pos] = p.areaS[i];
+}
+
+// date-line rows -> segments of consecutive rows of one plane with the same two components
+__global__ void __launch_bounds__(256) k_seg_flags(const uint32_t* __restrict__ srow, const uint32_t* __restrict__ sa,
+                                                   const uint32_t* __restrict__ sb, long n, int H,
+                                                   uint32_t* __restrict__ start) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool st = i == 0;
+    if (!st) st = srow[i] != srow[i - 1] + 1 || (srow[i] % (uint32_t)H) == 0 || sa[i] != sa[i - 1] || sb[i] != sb[i - 1];
+    start[i] = st ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_seg_write(const uint32_t* __restrict__ srow, const uint32_t* __restrict__ sa,
+                                                   const uint32_t* __restrict__ sb, const uint32_t* __restrict__ start,
+                                                   const uint32_t* __restrict__ segpos, long n, int H, SegTables o) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t seg = segpos[i] + start[i] - 1;                 // inclusive scan - 1
+    const uint32_t row = srow[i];
+    if (start[i]) {
+        o.t[seg] = (int32_t)(row / (uint32_t)H); o.y0[seg] = (int32_t)(row % (uint32_t)H); o.a[seg] = sa[i]; o.b[seg] = sb[i];
+    }
+    if (i == n - 1 || start[i + 1]) o.y1[seg] = (int32_t)(row % (uint32_t)H) + 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // paint: bit rows + value per run -> int32 cube.  One warp per row, 1024 cells (32 mask words) per pass; a lane owns
 // four consecutive cells and stores them as one 16-byte streaming store.
 // ---------------------------------------------------------------------------------------------------------------
@@ -429,7 +490,15 @@ __global__ void __launch_bounds__(256) k_run_values(const uint32_t* __restrict__
     if (r < nruns) run_val[r] = comp_val[run_comp[r]];
 }
 
-template <bool VEC4>
+// streaming zero fill (16-byte stores); runs on a side stream while the table phase is busy
+__global__ void __launch_bounds__(256) k_zero_fill(int4* __restrict__ p, size_t n16, int32_t* __restrict__ tail, int ntail) {
+    const int4 z = make_int4(0, 0, 0, 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) __stcs(p + i, z);
+    if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = 0;
+}
+
+// SPARSE: the cube is already zero; only 4-cell groups that contain a set cell are written.
+template <bool VEC4, bool SPARSE>
 __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ row_ptr,
                                                const int32_t* __restrict__ run_val, long nrows, int W, int Ww,
                                                int32_t* __restrict__ flag) {
@@ -439,6 +508,7 @@ __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits
     for (long row = warp0; row < nrows; row += nwarps) {
         const uint32_t rbase = row_ptr[row];
         const bool empty = row_ptr[row + 1] == rbase;
+        if (SPARSE && empty) continue;
         int32_t* out = flag + row * (long)W;
         const uint32_t* b = bits + row * (long)Ww;
         uint32_t prev = 0, running = rbase;
@@ -457,6 +527,7 @@ __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits
                 prev = __shfl_sync(FULL, m, 31);
             } else {
                 prev = 0;
+                if (SPARSE) continue;
             }
             const int xbase = k0 * 32;
             if (VEC4) {
@@ -482,6 +553,8 @@ __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits
                                 }
                             }
                             v = make_int4(vv[0], vv[1], vv[2], vv[3]);
+                        } else if (SPARSE) {
+                            continue;
                         }
                     }
                     if (x < W) __stcs(reinterpret_cast<int4*>(out + x), v);
@@ -496,6 +569,7 @@ __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits
                         const uint32_t sw = __shfl_sync(FULL, starts, i);
                         const uint32_t bw = __shfl_sync(FULL, base, i);
                         if ((mw >> lane) & 1u) v = run_val[bw + __popc(sw & ((2u << lane) - 1u)) - 1u];
+                        else if (SPARSE) continue;
                     }
                     if (x < W) __stcs(out + x, v);
                 }
@@ -637,8 +711,54 @@ cudaError_t paint(const PaintArgs& a, int sm_count, cudaStream_t st) {
     long want = (a.nrows + 7) / 8;
     int blocks = (int)(want < (long)sm_count * 8 ? want : (long)sm_count * 8);
     const bool vec = (a.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.flag) & 15) == 0);
-    if (vec) k_paint<true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
-    else k_paint<false><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
+    if (a.sparse) {
+        if (vec) k_paint<true, true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
+        else k_paint<false, true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
+    } else {
+        if (vec) k_paint<true, false><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
+        else k_paint<false, false><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t zero_fill(int32_t* p, size_t n, int sm_count, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    // head up to 16-byte alignment is handled by shifting into the tail path only when misaligned (rare: cudaMalloc
+    // and torch allocations are 256/512-byte aligned)
+    if (reinterpret_cast<uintptr_t>(p) & 15) return cudaMemsetAsync(p, 0, n * 4, st);
+    const size_t n16 = n / 4;
+    k_zero_fill<<<sm_count * 8, 256, 0, st>>>(reinterpret_cast<int4*>(p), n16, p + n16 * 4, (int)(n - n16 * 4));
+    return cudaGetLastError();
+}
+
+cudaError_t class_sums(const CompTables& c, const ClassTables& k, long ncomp, cudaStream_t st) {
+    if (ncomp == 0) return cudaSuccess;
+    k_class_sums<<<blocks_for(ncomp, 256), 256, 0, st>>>(c, k, ncomp);
+    return cudaGetLastError();
+}
+
+cudaError_t pairs_count(const PairTable& p, const uint32_t* cls, const ClassTables& k, uint32_t* pcnt, uint32_t* total,
+                        cudaStream_t st) {
+    k_pairs_count<<<blocks_for(p.cap, 256), 256, 0, st>>>(p, cls, k, pcnt, total);
+    return cudaGetLastError();
+}
+
+cudaError_t pairs_fill(const PairTable& p, const uint32_t* pptr, uint32_t* pfill, const PairCsr& o, cudaStream_t st) {
+    k_pairs_fill<<<blocks_for(p.cap, 256), 256, 0, st>>>(p, pptr, pfill, o);
+    return cudaGetLastError();
+}
+
+cudaError_t seg_flags(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, long n, int H, uint32_t* start,
+                      cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_seg_flags<<<blocks_for(n, 256), 256, 0, st>>>(srow, sa, sb, n, H, start);
+    return cudaGetLastError();
+}
+
+cudaError_t seg_write(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, const uint32_t* start,
+                      const uint32_t* segpos, long n, int H, const SegTables& o, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_seg_write<<<blocks_for(n, 256), 256, 0, st>>>(srow, sa, sb, start, segpos, n, H, o);
     return cudaGetLastError();
 }
 

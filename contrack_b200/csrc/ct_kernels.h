@@ -67,6 +67,24 @@ cudaError_t pairs_accumulate(const uint32_t* row_ptr, const uint32_t* run_x, con
 cudaError_t pairs_compact(const PairTable& p, uint32_t* out_a, uint32_t* out_b, uint32_t* out_npix, uint32_t* out_nsp,
                           double* out_E, double* out_S, uint32_t out_cap, uint32_t* count_dev, cudaStream_t st);
 
+// ---- tables in the layout of cth::FastTables ----
+struct ClassTables { double *conE, *conS, *fE, *fS; uint32_t* nsp; };          // [ncomp], zero-initialised by caller
+struct PairCsr { uint32_t *b, *npix, *nsp; double *E, *S; };                   // [npair]
+struct SegTables { int32_t *t, *y0, *y1; uint32_t *a, *b; };                   // [nseg <= nseam]
+cudaError_t class_sums(const CompTables& c, const ClassTables& k, long ncomp, cudaStream_t st);
+// pcnt[a]++ per pair, *total = number of pairs, forward sums into the class of b (pcnt, total zeroed by caller)
+cudaError_t pairs_count(const PairTable& p, const uint32_t* cls, const ClassTables& k, uint32_t* pcnt, uint32_t* total,
+                        cudaStream_t st);
+// pptr = exclusive scan of pcnt; pfill zeroed by caller
+cudaError_t pairs_fill(const PairTable& p, const uint32_t* pptr, uint32_t* pfill, const PairCsr& o, cudaStream_t st);
+cudaError_t seg_flags(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, long n, int H, uint32_t* start,
+                      cudaStream_t st);
+// segpos = exclusive scan of start
+cudaError_t seg_write(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, const uint32_t* start,
+                      const uint32_t* segpos, long n, int H, const SegTables& o, cudaStream_t st);
+
+cudaError_t zero_fill(int32_t* p, size_t n, int sm_count, cudaStream_t st);
+
 // run_val[r] = comp_val[run_comp[r]]
 cudaError_t run_values(const uint32_t* run_comp, const int32_t* comp_val, int32_t* run_val, long nruns,
                        cudaStream_t st);
@@ -75,6 +93,7 @@ struct PaintArgs {
     const uint32_t* bits; const uint32_t* row_ptr; const int32_t* run_val;
     long nrows; int W, Ww;
     int32_t* flag;                           // [nrows * W] out
+    int sparse;                              // 1: `flag` is already zero, write only the cells of row-runs
 };
 cudaError_t paint(const PaintArgs& a, int sm_count, cudaStream_t st);
 // sub-runs of planes [t_begin, t_end) only; `flag` starts at plane t_begin

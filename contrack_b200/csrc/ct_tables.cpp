@@ -51,8 +51,21 @@ int track_tables(long T, int H, int W, int persistence,
     int nlabel = 0;
     for (long c = 0; c < ncomp; ++c) nlabel = std::max(nlabel, (int)comp_label[c]);
 
-    // value of each whole component; pieces beyond ncomp only exist after a split
-    std::vector<int> value(comp_label, comp_label + ncomp);
+    // Buffers live across calls (one set per host thread): a fresh multi-megabyte vector per call costs more in page
+    // faults than the work done on it.
+    struct Workspace {
+        std::vector<int> value, tmin, tmax, fin;
+        std::vector<Box3> box;
+        std::vector<long> first, order, pos;
+    };
+    static thread_local Workspace tls_ws;
+    Workspace& ws = tls_ws;                      // one TLS lookup, not one per access
+    std::vector<int>&value = ws.value, &tmin = ws.tmin, &tmax = ws.tmax, &fin = ws.fin;
+    std::vector<Box3>& box = ws.box;
+    std::vector<long>&first = ws.first, &order = ws.order, &pos = ws.pos;
+
+    // value of each whole component (0 = removed before this stage); pieces beyond ncomp only exist after a split
+    value.assign(comp_label, comp_label + ncomp);
     std::vector<Piece> extra;                               // pieces created by splits (index ncomp + k)
     std::vector<Piece> whole_runs;                          // whole components whose runs were materialised
     std::unordered_map<long, int> whole_runs_idx;           // comp -> index in whole_runs
@@ -67,10 +80,11 @@ int track_tables(long T, int H, int W, int persistence,
 
     if (nseg > 0) {
         // 3-D boxes of the ORIGINAL labels (find_objects before merging, contrack.py:753)
-        std::vector<Box3> box(nlabel + 1, Box3{INT_MAX, 0, INT_MAX, 0, INT_MAX, 0});
+        box.assign(nlabel + 1, Box3{INT_MAX, 0, INT_MAX, 0, INT_MAX, 0});
         // CSR of components per original label (stable: first-pixel order)
-        std::vector<long> first(nlabel + 2, 0);
+        first.assign(nlabel + 2, 0);
         for (long c = 0; c < ncomp; ++c) {
+            if (comp_label[c] == 0) continue;
             Box3& b = box[comp_label[c]];
             b.t0 = std::min(b.t0, (int)comp_t[c]); b.t1 = std::max(b.t1, (int)comp_t[c] + 1);
             b.y0 = std::min(b.y0, (int)comp_y0[c]); b.y1 = std::max(b.y1, (int)comp_y1[c]);
@@ -78,11 +92,9 @@ int track_tables(long T, int H, int W, int persistence,
             first[comp_label[c] + 1]++;
         }
         for (int v = 0; v <= nlabel; ++v) first[v + 1] += first[v];
-        std::vector<long> order(ncomp);
-        {
-            std::vector<long> pos(first.begin(), first.end() - 1);
-            for (long c = 0; c < ncomp; ++c) order[pos[comp_label[c]]++] = c;
-        }
+        order.resize(ncomp);
+        pos.assign(first.begin(), first.end() - 1);
+        for (long c = 0; c < ncomp; ++c) if (comp_label[c] != 0) order[pos[comp_label[c]]++] = c;
         // dynamic member lists (piece ids), created on first use from the CSR
         std::unordered_map<int, std::vector<long>> members;
         auto get_members = [&](int v) -> std::vector<long>& {
@@ -174,6 +186,7 @@ int track_tables(long T, int H, int W, int persistence,
 
         for (long s = 0; s < nseg && rc == 0; ++s) {
             const long a = seg_a[s], b = seg_b[s];
+            if (comp_label[a] == 0 || comp_label[b] == 0) continue;          // a removed component: pixel value 0
             for (int y = seg_y0[s]; y < seg_y1[s]; ++y) {
                 long pa = piece_of(a, y, 0), pb = piece_of(b, y, W - 1);
                 int va = piece_value(pa), vb = piece_value(pb);
@@ -190,11 +203,13 @@ int track_tables(long T, int H, int W, int persistence,
     }
 
     // persistence on the merged values (contrack.py:765-772): t-extent of all pixels that carry value v
-    std::vector<int> tmin(nlabel + 1, INT_MAX), tmax(nlabel + 1, -1);
+    tmin.assign(nlabel + 1, INT_MAX);
+    tmax.assign(nlabel + 1, -1);
+    const bool any_split = !comp_pieces.empty();
     for (long c = 0; c < ncomp; ++c) {
-        auto it = comp_pieces.find(c);
-        if (it != comp_pieces.end()) continue;                // split comps are handled through their pieces
         int v = value[c];
+        if (v == 0) continue;
+        if (any_split && comp_pieces.find(c) != comp_pieces.end()) continue;   // split comps: through their pieces
         tmin[v] = std::min(tmin[v], (int)comp_t[c]); tmax[v] = std::max(tmax[v], (int)comp_t[c]);
     }
     for (auto& kv : comp_pieces) {
@@ -205,7 +220,7 @@ int track_tables(long T, int H, int W, int persistence,
             tmin[v] = std::min(tmin[v], t); tmax[v] = std::max(tmax[v], t);
         }
     }
-    std::vector<int> fin(nlabel + 1, 0);
+    fin.assign(nlabel + 1, 0);
     for (int v = 1; v <= nlabel; ++v) {
         if (tmax[v] < 0) continue;
         if ((tmax[v] + 1 - tmin[v]) < persistence) continue;

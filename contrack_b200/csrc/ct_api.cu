@@ -625,7 +625,6 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
     }
     CT_CUDA(cudaStreamSynchronize(ws));
     const double t1_ms = now_ms();
-    c->chunk_in[0].release(); c->chunk_in[1].release();
     if ((rc = table_phase(c, overlap, persistence, twosided, CT_STAGE_FINAL, n_features, ws)) != CT_OK) return rc;
     CT_CUDA(cudaStreamSynchronize(ws));
     const double t2_ms = now_ms();

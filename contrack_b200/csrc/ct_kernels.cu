@@ -11,6 +11,7 @@
 // everything between them touches only bit rows (1/32 B/cell... 4/32 B per cell) and run/component tables.
 #include "ct_kernels.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -55,7 +56,10 @@ __device__ __forceinline__ bool cmp_thr(TIn v, float thr_f, double thr_d) {
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 
-// One warp per row; 8 independent 128-byte warp loads in flight per warp; ballot packs 32 cells into a mask word.
+// One warp per row.  A batch is 8 independent 128-byte warp loads (4 B per lane, fully coalesced); one ballot packs the
+// 32 compared cells into a mask word that lane (k mod 32) keeps.  Run starts, the row's run count and the two date-line
+// bits are derived once per 32 words from the kept words (lane-parallel), not per word: the inner loop is
+// LDG + FSETP + VOTE + SEL per 32 cells, so the kernel stays bound by HBM rather than by instruction issue.
 template <typename TIn, bool F32CMP, int OP>
 __global__ void __launch_bounds__(256) k_threshold(const TIn* __restrict__ anom, long nrows, int H, int W, int Ww,
                                                    const double* __restrict__ thr, long thr_n,
@@ -65,36 +69,193 @@ __global__ void __launch_bounds__(256) k_threshold(const TIn* __restrict__ anom,
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     const int last_word = (W - 1) >> 5, last_bit = (W - 1) & 31;
+    const int nfull = W >> 5;                                       // words whose 32 cells are all inside the row
     for (long row = warp0; row < nrows; row += nwarps) {
         const double thr_d = thr[thr_n == 1 ? 0 : row / H];
         const float thr_f = (float)thr_d;
         const TIn* a = anom + row * (long)W;
-        uint32_t carry = 0, cnt = 0, first = 0, last = 0;
+        uint32_t cnt = 0, carry_word = 0, first = 0, last = 0;
         for (int k0 = 0; k0 < Ww; k0 += 32) {
             uint32_t myword = 0;
             const int kend = min(32, Ww - k0);
             for (int j0 = 0; j0 < kend; j0 += 8) {
                 TIn v[8];
+                if (k0 + j0 + 8 <= nfull) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int x = (k0 + j0 + j) * 32 + lane;
-                    v[j] = (x < W) ? ld_stream(a + x) : (TIn)NAN;
+                    for (int j = 0; j < 8; ++j) v[j] = ld_stream(a + (k0 + j0 + j) * 32 + lane);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int x = (k0 + j0 + j) * 32 + lane;
+                        v[j] = (x < W) ? ld_stream(a + x) : (TIn)NAN;
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t m = __ballot_sync(FULL, cmp_thr<TIn, F32CMP, OP>(v[j], thr_f, thr_d));
-                    const int k = k0 + j0 + j;
-                    cnt += __popc(m & ~((m << 1) | carry));
-                    carry = m >> 31;
                     if (lane == j0 + j) myword = m;
-                    if (k == 0) first = m & 1u;
-                    if (k == last_word) last = (m >> last_bit) & 1u;
                 }
             }
             if (lane < kend) bits[row * (long)Ww + k0 + lane] = myword;
+            uint32_t prev = __shfl_up_sync(FULL, myword, 1);
+            if (lane == 0) prev = carry_word;
+            cnt += __popc(myword & ~((myword << 1) | (prev >> 31)));
+            carry_word = __shfl_sync(FULL, myword, 31);
+            if (k0 == 0) first = __shfl_sync(FULL, myword, 0) & 1u;
+            if (last_word >= k0 && last_word < k0 + 32) last = (__shfl_sync(FULL, myword, last_word - k0) >> last_bit) & 1u;
         }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
         if (lane == 0) { row_cnt[row] = cnt; seam_flag[row] = first & last; }
     }
+}
+
+// ---- variant 1: rows staged through shared memory by the bulk-copy engine (cp.async.bulk, SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Each warp runs its own ring of NS row buffers: lane 0 arms the stage's mbarrier and issues one bulk copy per row
+// (W * sizeof(TIn) bytes, a multiple of 16); the warp waits on the barrier's phase, compares the row out of shared memory
+// (lane-contiguous 4-byte reads, conflict free), and re-issues the buffer for the row NS steps ahead.  No load
+// instruction touches global memory, no register staging: NS * 8 rows per SM are in flight.
+template <typename TIn, bool F32CMP, int OP>
+__global__ void __launch_bounds__(256) k_threshold_bulk(const TIn* __restrict__ anom, long nrows, int H, int W, int Ww,
+                                                        const double* __restrict__ thr, long thr_n,
+                                                        uint32_t* __restrict__ bits, uint32_t* __restrict__ row_cnt,
+                                                        uint32_t* __restrict__ seam_flag, int NS, int stage_bytes) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + wid * NS;                   // [nw][NS]
+    unsigned char* stage0 = smem + ((nw * NS * 8 + 127) / 128) * 128 + (size_t)wid * NS * stage_bytes;
+    const long warp0 = (long)blockIdx.x * nw + wid;
+    const long nwarps = (long)gridDim.x * nw;
+    const uint32_t row_bytes = (uint32_t)(W * sizeof(TIn));
+    const int last_word = (W - 1) >> 5, last_bit = (W - 1) & 31;
+    const int nfull = W >> 5;
+    if (lane == 0) {
+        for (int s2 = 0; s2 < NS; ++s2) mbar_init(&bars[s2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int s2 = 0; s2 < NS; ++s2) {
+            const long r = warp0 + (long)s2 * nwarps;
+            if (r < nrows) {
+                mbar_expect_tx(&bars[s2], row_bytes);
+                bulk_g2s(stage0 + (size_t)s2 * stage_bytes, anom + r * (long)W, row_bytes, &bars[s2]);
+            }
+        }
+    }
+    int st = 0;
+    uint32_t phase = 0;
+    for (long row = warp0; row < nrows; row += nwarps) {
+        const double thr_d = thr[thr_n == 1 ? 0 : row / H];
+        const float thr_f = (float)thr_d;
+        mbar_wait(&bars[st], phase);
+        const TIn* a = reinterpret_cast<const TIn*>(stage0 + (size_t)st * stage_bytes);
+        uint32_t cnt = 0, carry_word = 0, first = 0, last = 0;
+        for (int k0 = 0; k0 < Ww; k0 += 32) {
+            uint32_t myword = 0;
+            const int kend = min(32, Ww - k0);
+            for (int j0 = 0; j0 < kend; j0 += 8) {
+                TIn v[8];
+                if (k0 + j0 + 8 <= nfull) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = a[(k0 + j0 + j) * 32 + lane];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int x = (k0 + j0 + j) * 32 + lane;
+                        v[j] = (x < W) ? a[x] : (TIn)NAN;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t m = __ballot_sync(FULL, cmp_thr<TIn, F32CMP, OP>(v[j], thr_f, thr_d));
+                    if (lane == j0 + j) myword = m;
+                }
+            }
+            if (lane < kend) bits[row * (long)Ww + k0 + lane] = myword;
+            uint32_t prev = __shfl_up_sync(FULL, myword, 1);
+            if (lane == 0) prev = carry_word;
+            cnt += __popc(myword & ~((myword << 1) | (prev >> 31)));
+            carry_word = __shfl_sync(FULL, myword, 31);
+            if (k0 == 0) first = __shfl_sync(FULL, myword, 0) & 1u;
+            if (last_word >= k0 && last_word < k0 + 32) last = (__shfl_sync(FULL, myword, last_word - k0) >> last_bit) & 1u;
+        }
+        // every lane has read its part of the buffer (the ballots above are warp-synchronous): hand it back
+        __syncwarp();
+        if (lane == 0) {
+            const long r = row + (long)NS * nwarps;
+            if (r < nrows) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bars[st], row_bytes);
+                bulk_g2s(stage0 + (size_t)st * stage_bytes, anom + r * (long)W, row_bytes, &bars[st]);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+        if (lane == 0) { row_cnt[row] = cnt; seam_flag[row] = first & last; }
+        if (++st == NS) { st = 0; phase ^= 1u; }
+    }
+}
+
+template <typename TIn, bool F32CMP>
+cudaError_t launch_threshold_bulk(const ThresholdArgs& a, int sm_count, cudaStream_t st) {
+    const long nrows = a.T * a.H;
+    const int nw = 8;
+    const int stage_bytes = (int)(((size_t)a.W * sizeof(TIn) + 127) / 128 * 128);
+    int NS = (200 * 1024 - 1024) / (nw * stage_bytes);
+    if (NS > 8) NS = 8;
+    const size_t smem = ((size_t)nw * NS * 8 + 127) / 128 * 128 + (size_t)nw * NS * stage_bytes;
+    int blocks = (int)std::min<long>((nrows + nw - 1) / nw, (long)sm_count);
+#define CT_LAUNCH_THRB(OPV)                                                                                         \
+    do {                                                                                                            \
+        cudaError_t e = cudaFuncSetAttribute(k_threshold_bulk<TIn, F32CMP, OPV>,                                    \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+        if (e != cudaSuccess) return e;                                                                             \
+        k_threshold_bulk<TIn, F32CMP, OPV><<<blocks, nw * 32, smem, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww, \
+                                                                          a.thr_dev, a.thr_n, a.bits, a.row_cnt,    \
+                                                                          a.seam_flag, NS, stage_bytes);            \
+    } while (0)
+    switch (a.op) {
+        case 0: CT_LAUNCH_THRB(0); break;
+        case 1: CT_LAUNCH_THRB(1); break;
+        case 2: CT_LAUNCH_THRB(2); break;
+        case 3: CT_LAUNCH_THRB(3); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef CT_LAUNCH_THRB
+    return cudaGetLastError();
+}
+
+// bulk staging needs 16-byte aligned rows and at least two row buffers per warp in shared memory
+template <typename TIn>
+bool bulk_ok(const ThresholdArgs& a) {
+    const size_t rb = (size_t)a.W * sizeof(TIn);
+    const size_t stage = (rb + 127) / 128 * 128;
+    return (rb % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.anom) & 15) == 0) && (8 * 2 * stage <= 199 * 1024);
 }
 
 template <typename TIn, bool F32CMP>
@@ -600,6 +761,13 @@ cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st
     if (nrows == 0) return cudaSuccess;
     long want = (nrows + 7) / 8;
     int blocks = (int)(want < (long)sm_count * 8 ? want : (long)sm_count * 8);
+    if (a.variant == 1) {
+        if (a.in_dtype == 1 && bulk_ok<double>(a)) return launch_threshold_bulk<double, false>(a, sm_count, st);
+        if (a.in_dtype == 0 && bulk_ok<float>(a)) {
+            if (a.thr_is_f32) return launch_threshold_bulk<float, true>(a, sm_count, st);
+            return launch_threshold_bulk<float, false>(a, sm_count, st);
+        }
+    }
     if (a.in_dtype == 1) return launch_threshold<double, false>(a, blocks, st);
     if (a.thr_is_f32) return launch_threshold<float, true>(a, blocks, st);
     return launch_threshold<float, false>(a, blocks, st);

@@ -177,3 +177,40 @@ def test_medium_cube_against_oracle(eng):
     import torch
     f, n = eng.run_contrack(torch.from_numpy(x).cuda(), w, 160, True, 0, 0.5, 5, True)
     assert np.array_equal(f.cpu().numpy(), ref)
+
+
+def test_bulk_copy_threshold_variant(eng, fixture_cube, golden):
+    """The cp.async.bulk staged threshold kernel (option tma=1) gives the same bits as the plain-load one."""
+    a, lat, lon = fixture_cube
+    eng.set_option('tma', 1)
+    try:
+        for r in golden['fixture']:
+            f, _ = gpu_run(eng, a, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
+            assert sha_i4(f) == r['sha256'], r['key']
+        x = synth_cube(2, 12, 721, 1440, (2.5, 24, 40))
+        la = np.linspace(90, -90, 721).astype(np.float32)
+        lo = (np.arange(1440) * 0.25).astype(np.float32)
+        ref = oracle.run_contrack(x, la, lo, 160, '>=', 0.5, 5, True, force=True)
+        w = oracle.weight_grid(la, oracle.resolution(la, True), oracle.resolution(lo, True), 1440)[:, 0].copy()
+        import torch
+        f, n = eng.run_contrack(torch.from_numpy(x).cuda(), w, 160, True, 0, 0.5, 5, True)
+        assert np.array_equal(f.cpu().numpy(), ref)
+        xd = synth_cube(11, 10, 24, 48, (1.0, 2, 3)).astype(np.float64)      # float64 rows, 384 bytes each
+        la2, lo2 = regular_grid(24, 48)
+        ref = oracle.run_contrack(xd, la2, lo2, 40.0, '<', 0.3, 2, True)
+        f, _ = gpu_run(eng, xd, la2, lo2, 40.0, '<', 0.3, 2, True)
+        assert np.array_equal(f, ref)
+    finally:
+        eng.set_option('tma', 0)
+
+
+def test_dense_paint_path(eng, fixture_cube, golden):
+    """overlap_zero=0: one dense paint kernel instead of zero fill + sparse paint."""
+    a, lat, lon = fixture_cube
+    eng.set_option('overlap_zero', 0)
+    try:
+        r = golden['fixture'][0]
+        f, _ = gpu_run(eng, a, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
+        assert sha_i4(f) == r['sha256']
+    finally:
+        eng.set_option('overlap_zero', 1)

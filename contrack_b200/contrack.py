@@ -347,8 +347,7 @@ class contrack(object):
         data, dims, sort = self._cube_tlatlon(variable)
         is_f32 = str(data.dtype).endswith('float32')
         if _is_dataarray(threshold):
-            thr_keys = _host(threshold['dayofyear'].data if hasattr(threshold['dayofyear'], 'data')
-                             else threshold.coords['dayofyear'])
+            thr_keys = _host(threshold['dayofyear'].data)
             thr_vals = _host(threshold.data)
             doy = time_group_keys(self.ds[self._time_name].data, 'dayofyear')
             pos = np.searchsorted(thr_keys, doy)

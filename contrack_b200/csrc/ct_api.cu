@@ -23,6 +23,14 @@
 #include "ct_kernels.h"
 #include "ct_tables.h"
 
+namespace cta {
+cudaError_t group_mean(const float* z, long HW, int G, const int32_t* gptr_dev, const int32_t* gidx_dev, float* gmean,
+                       cudaStream_t st);
+cudaError_t clim_smooth(const float* gmean, long HW, int G, int window, float* clim, cudaStream_t st);
+cudaError_t anom(const float* z, long HW, long T, const int32_t* group_dev, const float* clim, int smooth, float* out,
+                 cudaStream_t st);
+}  // namespace cta
+
 namespace {
 
 thread_local std::string g_err;
@@ -95,6 +103,7 @@ struct ct_ctx {
     DevBuf o_t, o_y, o_x0, o_x1, o_val;
     DevBuf w_dev, special_dev, thr_dev;
     DevBuf chunk_in[2], chunk_out[2];
+    DevBuf a_gptr, a_gidx, a_gmean, a_group;
     // pinned host staging
     PinBuf hp_counters, hp_tables, hp_val, hp_ovr;
     cth::Result host_result;
@@ -507,7 +516,8 @@ void ct_destroy(ct_ctx* c) {
                       &c->k_conE, &c->k_conS, &c->k_fE, &c->k_fS, &c->k_nsp, &c->pcnt, &c->pfill, &c->pptr,
                       &c->seg_start, &c->seg_pos, &c->g_t, &c->g_y0, &c->g_y1, &c->g_a, &c->g_b,
                       &c->o_t, &c->o_y, &c->o_x0, &c->o_x1, &c->o_val, &c->w_dev, &c->special_dev, &c->thr_dev,
-                      &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0], &c->chunk_out[1]};
+                      &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0], &c->chunk_out[1],
+                      &c->a_gptr, &c->a_gidx, &c->a_gmean, &c->a_group};
     for (DevBuf* b : bufs) b->release();
     c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
@@ -768,12 +778,47 @@ double ct_numpy_pairwise_sum_rle(const double* value, const int64_t* count, long
     return ctb::numpy_pairwise_sum(v.data(), (long)v.size());
 }
 
-int ct_calc_clim(ct_ctx*, const float*, long, int, int, const int32_t*, int, int, float*, void*) {
-    return fail(CT_ERR_INTERNAL, "ct_calc_clim: not built yet");
+int ct_calc_clim(ct_ctx* c, const float* z_dev, long T, int H, int W, const int32_t* group_host, int G, int window,
+                 float* clim_dev, void* stream) {
+    if (!c || !z_dev || !group_host || !clim_dev) return fail(CT_ERR_ARG, "null argument");
+    if (T <= 0 || H <= 0 || W <= 0 || G <= 0 || window <= 0) return fail(CT_ERR_ARG, "bad shape / window");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long HW = (long)H * W;
+    // members of every group, in time order
+    std::vector<int32_t> gptr(G + 1, 0), gidx(T);
+    for (long t = 0; t < T; ++t) {
+        if (group_host[t] < 0 || group_host[t] >= G) return fail(CT_ERR_ARG, "group index out of range at t=%ld", t);
+        gptr[group_host[t] + 1]++;
+    }
+    for (int g = 0; g < G; ++g) gptr[g + 1] += gptr[g];
+    {
+        std::vector<int32_t> pos(gptr.begin(), gptr.end() - 1);
+        for (long t = 0; t < T; ++t) gidx[pos[group_host[t]]++] = (int32_t)t;
+    }
+    CT_CUDA(c->a_gptr.ensure((size_t)(G + 1) * 4)); CT_CUDA(c->a_gidx.ensure((size_t)T * 4));
+    CT_CUDA(c->a_gmean.ensure((size_t)G * HW * 4));
+    CT_CUDA(cudaMemcpyAsync(c->a_gptr.p, gptr.data(), (size_t)(G + 1) * 4, cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaMemcpyAsync(c->a_gidx.p, gidx.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaStreamSynchronize(st));                               // gptr / gidx are locals
+    CT_CUDA(cta::group_mean(z_dev, HW, G, c->a_gptr.as<int32_t>(), c->a_gidx.as<int32_t>(), c->a_gmean.as<float>(), st));
+    CT_CUDA(cta::clim_smooth(c->a_gmean.as<float>(), HW, G, window, clim_dev, st));
+    return CT_OK;
 }
 
-int ct_calc_anom(ct_ctx*, const float*, long, int, int, const int32_t*, int, const float*, int, float*, void*) {
-    return fail(CT_ERR_INTERNAL, "ct_calc_anom: not built yet");
+int ct_calc_anom(ct_ctx* c, const float* z_dev, long T, int H, int W, const int32_t* group_host, int G,
+                 const float* clim_dev, int smooth, float* anom_dev, void* stream) {
+    if (!c || !z_dev || !group_host || !clim_dev || !anom_dev) return fail(CT_ERR_ARG, "null argument");
+    if (T <= 0 || H <= 0 || W <= 0 || G <= 0 || smooth <= 0) return fail(CT_ERR_ARG, "bad shape / smooth");
+    for (long t = 0; t < T; ++t)
+        if (group_host[t] < 0 || group_host[t] >= G) return fail(CT_ERR_ARG, "group index out of range at t=%ld", t);
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CT_CUDA(c->a_group.ensure((size_t)T * 4));
+    CT_CUDA(cudaMemcpyAsync(c->a_group.p, group_host, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaStreamSynchronize(st));                               // caller may free group_host after return
+    CT_CUDA(cta::anom(z_dev, (long)H * W, T, c->a_group.as<int32_t>(), clim_dev, smooth, anom_dev, st));
+    return CT_OK;
 }
 
 }  // extern "C"

@@ -61,6 +61,9 @@ class DataArray(object):
         return v if dtype is None else v.astype(dtype)
 
     def __getitem__(self, key):
+        if isinstance(key, str):                      # coordinate by name, as xarray does
+            c = self.coords[key]
+            return c if isinstance(c, DataArray) else DataArray(np.asarray(c), (key,), name=key)
         return self.values[key]
 
     def transpose(self, *dims):

@@ -106,4 +106,48 @@ class Engine(object):
         return out, nfeat.value
 
 
+    # ------------------------------------------------------------------------------------------------------------
+    def _to_device(self, x):
+        """(cuda float32 tensor, was_host)"""
+        import torch
+        if _is_torch(x):
+            if not x.is_cuda:
+                raise ValueError('torch input must live on a CUDA device (pass numpy for host data)')
+            return x.contiguous().float() if x.dtype != torch.float32 else x.contiguous(), False
+        a = np.ascontiguousarray(np.asarray(x), np.float32)
+        return torch.from_numpy(a).to('cuda:%d' % self.device), True
+
+    def calc_clim(self, z, group_index, ngroups, window):
+        """z [T,H,W] float32 (numpy or torch CUDA); group_index [T] int 0..ngroups-1.  Returns clim [G,H,W] of the same
+        kind as z (contrack.py:483-489)."""
+        import torch
+        zd, was_host = self._to_device(z)
+        T, H, W = (int(s) for s in zd.shape)
+        g = np.ascontiguousarray(group_index, np.int32)
+        if g.shape != (T,):
+            raise ValueError('group_index must have shape (T,)')
+        clim = torch.empty((int(ngroups), H, W), dtype=torch.float32, device=zd.device)
+        stream = torch.cuda.current_stream(zd.device).cuda_stream
+        _lib.check(self.lib.ct_calc_clim(self.handle, C.c_void_p(zd.data_ptr()), T, H, W, _lib.ptr(g, _lib._i32p),
+                                         int(ngroups), int(window), C.c_void_p(clim.data_ptr()), C.c_void_p(stream)))
+        return clim.cpu().numpy() if was_host else clim
+
+    def calc_anom(self, z, group_index, ngroups, clim, smooth, out=None):
+        """anom [T,H,W] = centred rolling mean (window `smooth`) of z[t] - clim[group_index[t]] (contrack.py:568-570)."""
+        import torch
+        zd, was_host = self._to_device(z)
+        cd, _ = self._to_device(clim)
+        T, H, W = (int(s) for s in zd.shape)
+        g = np.ascontiguousarray(group_index, np.int32)
+        if out is None or was_host:
+            outd = torch.empty((T, H, W), dtype=torch.float32, device=zd.device)
+        else:
+            outd = out
+        stream = torch.cuda.current_stream(zd.device).cuda_stream
+        _lib.check(self.lib.ct_calc_anom(self.handle, C.c_void_p(zd.data_ptr()), T, H, W, _lib.ptr(g, _lib._i32p),
+                                         int(ngroups), C.c_void_p(cd.data_ptr()), int(smooth), C.c_void_p(outd.data_ptr()),
+                                         C.c_void_p(stream)))
+        return outd.cpu().numpy() if was_host else outd
+
+
 __all__ = ['Engine', 'ContrackLibError']

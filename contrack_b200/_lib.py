@@ -50,6 +50,19 @@ _PROTOS = {
                        + [C.c_long, _u32p, _u32p, _u32p]
                        + [_i64p, _i32p, _i32p, _i32p, _u32p]
                        + [_i32p, C.c_long] + [_i32p] * 5 + [_longp, _longp]),
+    'ct_host_tables_fast': (C.c_int, [C.c_long, C.c_int, C.c_int, _f64p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_long]
+                            + [_i32p] * 5 + [_u32p] + [_f64p] * 4 + [_u32p] * 5 + [_f64p] * 2
+                            + [C.c_long] + [_i32p] * 3 + [_u32p] * 2 + [_p, _p]
+                            + [_i32p, C.c_long] + [_i32p] * 5 + [_longp, _longp]),
+    'ct_shard_threshold': (C.c_int, [_p, _p, C.c_int, C.c_long, C.c_int, C.c_int, _f64p, _f64p, C.c_long, C.c_int,
+                                     C.c_int, C.c_int, _p]),
+    'ct_shard_boundary_words': (C.c_long, [_p]),
+    'ct_shard_export_boundary': (C.c_int, [_p, _u32p, _p]),
+    'ct_shard_import_halo': (C.c_int, [_p, _u32p, _p]),
+    'ct_shard_tables': (C.c_int, [_p, _i32p, _p, _p]),
+    'ct_shard_plane_runs': (C.c_int, [_p, C.c_long, _longp, C.POINTER(_i32p), C.POINTER(_i32p), C.POINTER(_i32p),
+                                      C.POINTER(_u32p), _p]),
+    'ct_shard_paint': (C.c_int, [_p, _i32p, C.c_long] + [_i32p] * 5 + [_i32p, _p]),
     'ct_classify_rows': (None, [_f64p, C.c_int, C.c_int, _u8p]),
     'ct_numpy_pairwise_sum_rle': (C.c_double, [_f64p, _i64p, C.c_long]),
     'ct_calc_clim': (C.c_int, [_p, _p, C.c_long, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _p, _p]),

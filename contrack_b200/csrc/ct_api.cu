@@ -98,7 +98,7 @@ struct ct_ctx {
     DevBuf s_row, s_a, s_b;
     DevBuf h_key, h_npix, h_nsp, h_E, h_S;
     DevBuf p_b, p_npix, p_nsp, p_E, p_S;
-    DevBuf k_conE, k_conS, k_fE, k_fS, k_nsp, pcnt, pfill, pptr;
+    DevBuf k_conE, k_conS, k_fE, k_fS, k_nsp, k_fnsp, pcnt, pfill, pptr;
     DevBuf seg_start, seg_pos, g_t, g_y0, g_y1, g_a, g_b;
     DevBuf o_t, o_y, o_x0, o_x1, o_val;
     DevBuf w_dev, special_dev, thr_dev;
@@ -107,6 +107,11 @@ struct ct_ctx {
     // pinned host staging
     PinBuf hp_counters, hp_tables, hp_val, hp_ovr;
     cth::Result host_result;
+    cth::FastTables host_tb;                 // tables of the last tables_gpu() call (pointers into hp_tables)
+    long nseg = 0, halo_comps = 0;
+    int has_prev = 0;                        // sharded run: plane 0 of the scratch is the previous rank's last plane
+    PinBuf hp_plane;
+    int32_t* zero_started_for = nullptr;     // flag cube whose zero fill is in flight on the side stream
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_side[2] = {nullptr, nullptr};
     long opt_overlap_zero = 1;
@@ -244,9 +249,8 @@ int launch_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long t0, lon
     return CT_OK;
 }
 
-// Everything between the two cube-sized kernels.  On return c_val (value per component) and the override sub-runs are on
-// the device.
-int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int stage, long* n_features, cudaStream_t st) {
+// GPU half of the table phase: bit rows -> runs -> components -> tables, delivered in pinned host memory (c->host_tb).
+int tables_gpu(ct_ctx* c, cudaStream_t st) {
     const long nrows = c->T * c->H;
     const int H = c->H, W = c->W;
     uint32_t* cnt_dev = c->counters.as<uint32_t>();
@@ -288,7 +292,7 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
     CT_CUDA(c->c_S.ensure(cb8)); CT_CUDA(c->c_nsp.ensure(cb4)); CT_CUDA(c->c_cls.ensure(cb4));
     CT_CUDA(c->c_val.ensure(cb4));
     CT_CUDA(c->k_conE.ensure(cb8)); CT_CUDA(c->k_conS.ensure(cb8)); CT_CUDA(c->k_fE.ensure(cb8));
-    CT_CUDA(c->k_fS.ensure(cb8)); CT_CUDA(c->k_nsp.ensure(cb4));
+    CT_CUDA(c->k_fS.ensure(cb8)); CT_CUDA(c->k_nsp.ensure(cb4)); CT_CUDA(c->k_fnsp.ensure(cb4));
     CT_CUDA(c->pcnt.ensure(cb4)); CT_CUDA(c->pfill.ensure(cb4)); CT_CUDA(c->pptr.ensure(cb4 + 4));
     ctk::CompTables ct;
     ct.t = c->c_t.as<int32_t>(); ct.y0 = c->c_y0.as<int32_t>(); ct.y1 = c->c_y1.as<int32_t>();
@@ -296,7 +300,7 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
     ct.areaS = c->c_S.as<double>(); ct.nsp = U(c->c_nsp); ct.cls = U(c->c_cls);
     ctk::ClassTables kt;
     kt.conE = c->k_conE.as<double>(); kt.conS = c->k_conS.as<double>(); kt.fE = c->k_fE.as<double>();
-    kt.fS = c->k_fS.as<double>(); kt.nsp = U(c->k_nsp);
+    kt.fS = c->k_fS.as<double>(); kt.nsp = U(c->k_nsp); kt.fnsp = U(c->k_fnsp);
     CT_CUDA(ctk::comp_init(ct, nc, W, st));
     CT_CUDA(ctk::comp_accumulate(U(c->run_x), U(c->run_row), U(c->run_comp), R, H, c->w_dev.as<double>(),
                                  c->special_dev.as<uint8_t>(), ct, st));
@@ -337,7 +341,7 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
         q.b = U(c->p_b); q.npix = U(c->p_npix); q.nsp = U(c->p_nsp); q.E = c->p_E.as<double>(); q.S = c->p_S.as<double>();
         CT_CUDA(cudaMemsetAsync(kt.conE, 0, cb8, st)); CT_CUDA(cudaMemsetAsync(kt.conS, 0, cb8, st));
         CT_CUDA(cudaMemsetAsync(kt.fE, 0, cb8, st)); CT_CUDA(cudaMemsetAsync(kt.fS, 0, cb8, st));
-        CT_CUDA(cudaMemsetAsync(kt.nsp, 0, cb4, st));
+        CT_CUDA(cudaMemsetAsync(kt.nsp, 0, cb4, st)); CT_CUDA(cudaMemsetAsync(kt.fnsp, 0, cb4, st));
         CT_CUDA(cudaMemsetAsync(c->pcnt.p, 0, cb4, st)); CT_CUDA(cudaMemsetAsync(c->pfill.p, 0, cb4, st));
         CT_CUDA(cudaMemsetAsync(cnt_dev + 5, 0, 4, st));
         CT_CUDA(ctk::class_sums(ct, kt, nc, st));
@@ -360,7 +364,7 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
 
     // ---- tables -> pinned host memory (8-byte arrays first) ----
     const size_t ncp = (size_t)nc + 2, npp = (size_t)np + 2, ngp = (size_t)nseg + 2;
-    const size_t bytes = ncp * (4 * 8 + 8 * 4) + npp * (2 * 8 + 3 * 4) + ngp * 5 * 4 + 512;
+    const size_t bytes = ncp * (4 * 8 + 9 * 4) + npp * (2 * 8 + 3 * 4) + ngp * 5 * 4 + 512;
     CT_CUDA(c->hp_tables.ensure(bytes));
     char* base = c->hp_tables.as<char>();
     size_t off = 0;
@@ -371,6 +375,7 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
     int32_t* h_t = (int32_t*)take(ncp, 4); int32_t* h_y0 = (int32_t*)take(ncp, 4); int32_t* h_y1 = (int32_t*)take(ncp, 4);
     int32_t* h_x0 = (int32_t*)take(ncp, 4); int32_t* h_x1 = (int32_t*)take(ncp, 4);
     uint32_t* h_cls = (uint32_t*)take(ncp, 4); uint32_t* h_knsp = (uint32_t*)take(ncp, 4);
+    uint32_t* h_kfnsp = (uint32_t*)take(ncp, 4);
     uint32_t* h_pptr = (uint32_t*)take(ncp, 4);
     uint32_t* h_pb = (uint32_t*)take(npp, 4); uint32_t* h_pn = (uint32_t*)take(npp, 4);
     uint32_t* h_pnsp = (uint32_t*)take(npp, 4);
@@ -380,7 +385,7 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
 #define CT_D2H(dst, src, n, elt) \
     if ((n) > 0) CT_CUDA(cudaMemcpyAsync(dst, (src).p, (size_t)(n) * (elt), cudaMemcpyDeviceToHost, st))
     CT_D2H(h_conE, c->k_conE, nc, 8); CT_D2H(h_conS, c->k_conS, nc, 8); CT_D2H(h_fE, c->k_fE, nc, 8);
-    CT_D2H(h_fS, c->k_fS, nc, 8); CT_D2H(h_knsp, c->k_nsp, nc, 4);
+    CT_D2H(h_fS, c->k_fS, nc, 8); CT_D2H(h_knsp, c->k_nsp, nc, 4); CT_D2H(h_kfnsp, c->k_fnsp, nc, 4);
     CT_D2H(h_t, c->c_t, nc, 4); CT_D2H(h_y0, c->c_y0, nc, 4); CT_D2H(h_y1, c->c_y1, nc, 4);
     CT_D2H(h_x0, c->c_x0, nc, 4); CT_D2H(h_x1, c->c_x1, nc, 4); CT_D2H(h_cls, c->c_cls, nc, 4);
     CT_D2H(h_pptr, c->pptr, nc + 1, 4);
@@ -399,7 +404,9 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
             fwrite(c->w_host.data(), 8, H, f);
             fwrite(h_t, 4, nc, f); fwrite(h_y0, 4, nc, f); fwrite(h_y1, 4, nc, f); fwrite(h_x0, 4, nc, f);
             fwrite(h_x1, 4, nc, f); fwrite(h_cls, 4, nc, f); fwrite(h_conE, 8, nc, f); fwrite(h_conS, 8, nc, f);
+            for (long i = 0; i < nc; ++i) h_knsp[i] += h_kfnsp[i];   // dump format: one counter
             fwrite(h_fE, 8, nc, f); fwrite(h_fS, 8, nc, f); fwrite(h_knsp, 4, nc, f); fwrite(h_pptr, 4, nc + 1, f);
+            for (long i = 0; i < nc; ++i) h_knsp[i] -= h_kfnsp[i];
             fwrite(h_pb, 4, np, f); fwrite(h_pn, 4, np, f); fwrite(h_pnsp, 4, np, f);
             fwrite(h_pE, 8, np, f); fwrite(h_pS, 8, np, f);
             fwrite(h_gt, 4, nseg, f); fwrite(h_gy0, 4, nseg, f); fwrite(h_gy1, 4, nseg, f); fwrite(h_ga, 4, nseg, f);
@@ -408,15 +415,59 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
         }
     }
 
-    // ---- ordered table phase on the host ----
-    const double t_host0 = now_ms();
-    cth::FastTables tb;
+    cth::FastTables& tb = c->host_tb;
+    tb = cth::FastTables();
     tb.T = c->T; tb.H = H; tb.W = W; tb.ncomp = nc;
     tb.comp_t = h_t; tb.comp_y0 = h_y0; tb.comp_y1 = h_y1; tb.comp_x0 = h_x0; tb.comp_x1 = h_x1; tb.comp_cls = h_cls;
     tb.cls_conE = h_conE; tb.cls_conS = h_conS; tb.cls_fE = h_fE; tb.cls_fS = h_fS; tb.cls_nsp = h_knsp;
+    tb.cls_fnsp = h_kfnsp;
     tb.pair_ptr = h_pptr; tb.pair_b = h_pb; tb.pair_npix = h_pn; tb.pair_nsp = h_pnsp; tb.pair_E = h_pE; tb.pair_S = h_pS;
     tb.nseg = nseg; tb.seg_t = h_gt; tb.seg_y0 = h_gy0; tb.seg_y1 = h_gy1; tb.seg_a = h_ga; tb.seg_b = h_gb;
     tb.w = c->w_host.data();
+    c->nseg = nseg;
+    c->stats["runs"] = (double)R; c->stats["comps2d"] = (double)nc; c->stats["pairs"] = (double)np;
+    c->stats["seam_rows"] = (double)nseam; c->stats["seam_segments"] = (double)nseg;
+    return CT_OK;
+}
+
+// Upload the value of every component (and the override sub-runs) and resolve them to a value per row-run.
+int upload_values(ct_ctx* c, const int32_t* comp_val_pinned, const std::vector<ctb::Override>& overrides, cudaStream_t st) {
+    const long nc = c->ncomp, R = c->nruns;
+    const long novr = (long)overrides.size();
+    c->novr = novr;
+    if (nc) CT_CUDA(cudaMemcpyAsync(c->c_val.p, comp_val_pinned, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+    if (novr) {
+        CT_CUDA(c->hp_ovr.ensure((size_t)novr * 5 * 4));
+        int32_t* ho = c->hp_ovr.as<int32_t>();
+        for (long i = 0; i < novr; ++i) {
+            const ctb::Override& o = overrides[i];
+            ho[i] = o.t; ho[novr + i] = o.y; ho[2 * novr + i] = o.x0; ho[3 * novr + i] = o.x1; ho[4 * novr + i] = o.val;
+        }
+        const size_t ob = (size_t)novr * 4;
+        CT_CUDA(c->o_t.ensure(ob)); CT_CUDA(c->o_y.ensure(ob)); CT_CUDA(c->o_x0.ensure(ob));
+        CT_CUDA(c->o_x1.ensure(ob)); CT_CUDA(c->o_val.ensure(ob));
+        CT_CUDA(cudaMemcpyAsync(c->o_t.p, ho, ob, cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaMemcpyAsync(c->o_y.p, ho + novr, ob, cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaMemcpyAsync(c->o_x0.p, ho + 2 * novr, ob, cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaMemcpyAsync(c->o_x1.p, ho + 3 * novr, ob, cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaMemcpyAsync(c->o_val.p, ho + 4 * novr, ob, cudaMemcpyHostToDevice, st));
+    }
+    CT_CUDA(ctk::run_values(c->run_comp.as<uint32_t>(), c->c_val.as<int32_t>(), c->run_val.as<int32_t>(), R, st));
+    c->launches += 1;
+    c->stats["override_runs"] = (double)novr;
+    return CT_OK;
+}
+
+// Everything between the two cube-sized kernels.  On return the value per row-run and the override sub-runs are on the
+// device.
+int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int stage, long* n_features, cudaStream_t st) {
+    int rc0 = tables_gpu(c, st);
+    if (rc0 != CT_OK) return rc0;
+    const long nc = c->ncomp;
+    cth::FastTables& tb = c->host_tb;
+
+    // ---- ordered table phase on the host ----
+    const double t_host0 = now_ms();
     cth::Params pr;
     pr.overlap = overlap; pr.persistence = persistence; pr.twosided = twosided; pr.stage = stage;
     DeviceRunSource src;
@@ -430,34 +481,12 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
     c->stats["ms_host_tables"] = now_ms() - t_host0;
 
     // ---- values back to the device ----
-    const long novr = (long)res.overrides.size();
-    c->novr = novr;
-    if (nc) CT_CUDA(cudaMemcpyAsync(c->c_val.p, hv, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
-    if (novr) {
-        CT_CUDA(c->hp_ovr.ensure((size_t)novr * 5 * 4));
-        int32_t* ho = c->hp_ovr.as<int32_t>();
-        for (long i = 0; i < novr; ++i) {
-            const ctb::Override& o = res.overrides[i];
-            ho[i] = o.t; ho[novr + i] = o.y; ho[2 * novr + i] = o.x0; ho[3 * novr + i] = o.x1; ho[4 * novr + i] = o.val;
-        }
-        const size_t ob = (size_t)novr * 4;
-        CT_CUDA(c->o_t.ensure(ob)); CT_CUDA(c->o_y.ensure(ob)); CT_CUDA(c->o_x0.ensure(ob));
-        CT_CUDA(c->o_x1.ensure(ob)); CT_CUDA(c->o_val.ensure(ob));
-        CT_CUDA(cudaMemcpyAsync(c->o_t.p, ho, ob, cudaMemcpyHostToDevice, st));
-        CT_CUDA(cudaMemcpyAsync(c->o_y.p, ho + novr, ob, cudaMemcpyHostToDevice, st));
-        CT_CUDA(cudaMemcpyAsync(c->o_x0.p, ho + 2 * novr, ob, cudaMemcpyHostToDevice, st));
-        CT_CUDA(cudaMemcpyAsync(c->o_x1.p, ho + 3 * novr, ob, cudaMemcpyHostToDevice, st));
-        CT_CUDA(cudaMemcpyAsync(c->o_val.p, ho + 4 * novr, ob, cudaMemcpyHostToDevice, st));
-    }
-    CT_CUDA(ctk::run_values(U(c->run_comp), c->c_val.as<int32_t>(), c->run_val.as<int32_t>(), R, st));
-    c->launches += 1;
+    if ((rc = upload_values(c, hv, res.overrides, st)) != CT_OK) return rc;
 
-    c->stats["runs"] = (double)R; c->stats["comps2d"] = (double)nc; c->stats["pairs"] = (double)np;
-    c->stats["seam_rows"] = (double)nseam; c->stats["seam_segments"] = (double)nseg;
     c->stats["kept_comps"] = (double)res.n_kept;
     c->stats["labels3d"] = (double)res.n_labels3d; c->stats["features"] = (double)res.n_features;
     c->stats["seam_events"] = (double)res.n_seam_events; c->stats["seam_splits"] = (double)res.n_seam_splits;
-    c->stats["neartie_resolved"] = (double)res.n_neartie; c->stats["override_runs"] = (double)novr;
+    c->stats["neartie_resolved"] = (double)res.n_neartie;
     if (n_features) *n_features = res.n_features;
     return CT_OK;
 }
@@ -513,13 +542,13 @@ void ct_destroy(ct_ctx* c) {
                       &c->c_t, &c->c_y0, &c->c_y1, &c->c_x0, &c->c_x1, &c->c_E, &c->c_S, &c->c_nsp, &c->c_cls, &c->c_val,
                       &c->s_row, &c->s_a, &c->s_b, &c->h_key, &c->h_npix, &c->h_nsp, &c->h_E, &c->h_S,
                       &c->p_b, &c->p_npix, &c->p_nsp, &c->p_E, &c->p_S,
-                      &c->k_conE, &c->k_conS, &c->k_fE, &c->k_fS, &c->k_nsp, &c->pcnt, &c->pfill, &c->pptr,
+                      &c->k_conE, &c->k_conS, &c->k_fE, &c->k_fS, &c->k_nsp, &c->k_fnsp, &c->pcnt, &c->pfill, &c->pptr,
                       &c->seg_start, &c->seg_pos, &c->g_t, &c->g_y0, &c->g_y1, &c->g_a, &c->g_b,
                       &c->o_t, &c->o_y, &c->o_x0, &c->o_x1, &c->o_val, &c->w_dev, &c->special_dev, &c->thr_dev,
                       &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0], &c->chunk_out[1],
                       &c->a_gptr, &c->a_gidx, &c->a_gmean, &c->a_group};
     for (DevBuf* b : bufs) b->release();
-    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release();
+    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -550,6 +579,7 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     cudaStream_t st = (cudaStream_t)stream;
     c->stats.clear();
     if ((rc = prepare(c, T, H, W, w_host, thr_host, thr_n, st)) != CT_OK) return rc;
+    c->has_prev = 0;
     CT_CUDA(cudaEventRecord(c->ev[0], st));
     if ((rc = launch_threshold(c, anom_dev, in_dtype, 0, T, thr_n, thr_is_f32, op, st)) != CT_OK) return rc;
     CT_CUDA(cudaEventRecord(c->ev[1], st));
@@ -606,6 +636,7 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
     cudaStream_t cs = c->copy_stream, ws = c->work_stream;
     c->stats.clear();
     if ((rc = prepare(c, T, H, W, w_host, thr_host, thr_n, ws)) != CT_OK) return rc;
+    c->has_prev = 0;
     const size_t esz = in_dtype == CT_F64 ? 8 : 4;
     const size_t plane = (size_t)H * W;
     if (chunk_planes <= 0) {
@@ -769,6 +800,183 @@ int ct_host_tables(long T, int H, int W, const double* w_host, double overlap, i
         stats8[0] = res.n_features; stats8[1] = res.n_kept; stats8[2] = res.n_labels3d; stats8[3] = res.n_seam_events;
         stats8[4] = res.n_seam_splits; stats8[5] = res.n_neartie; stats8[6] = 0; stats8[7] = 0;
     }
+    return CT_OK;
+}
+
+int ct_host_tables_fast(long T, int H, int W, const double* w_host, double overlap, int persistence, int twosided,
+                        int stage, long ncomp, const int32_t* comp_t, const int32_t* comp_y0, const int32_t* comp_y1,
+                        const int32_t* comp_x0, const int32_t* comp_x1, const uint32_t* comp_cls,
+                        const double* cls_conE, const double* cls_conS, const double* cls_fE, const double* cls_fS,
+                        const uint32_t* cls_nsp, const uint32_t* pair_ptr, const uint32_t* pair_b,
+                        const uint32_t* pair_npix, const uint32_t* pair_nsp, const double* pair_E, const double* pair_S,
+                        long nseg, const int32_t* seg_t, const int32_t* seg_y0, const int32_t* seg_y1,
+                        const uint32_t* seg_a, const uint32_t* seg_b, ct_plane_runs_fn fetch, void* user,
+                        int32_t* comp_val, long ovr_cap, int32_t* ovr_t, int32_t* ovr_y, int32_t* ovr_x0, int32_t* ovr_x1,
+                        int32_t* ovr_val, long* n_ovr, long* stats8) {
+    struct CallbackSource : cth::RunSource {
+        ct_plane_runs_fn fn; void* user;
+        bool plane_runs(long t, std::vector<cth::PlaneRun>& out) override {
+            long n = 0;
+            const int32_t *y = nullptr, *x0 = nullptr, *x1 = nullptr;
+            const uint32_t* comp = nullptr;
+            if (fn(user, t, &n, &y, &x0, &x1, &comp) != 0) return false;
+            out.resize(n);
+            for (long i = 0; i < n; ++i) out[i] = cth::PlaneRun{y[i], x0[i], x1[i], comp[i]};
+            return true;
+        }
+    } src;
+    src.fn = fetch; src.user = user;
+    cth::FastTables tb;
+    tb.T = T; tb.H = H; tb.W = W; tb.w = w_host; tb.ncomp = ncomp;
+    tb.comp_t = comp_t; tb.comp_y0 = comp_y0; tb.comp_y1 = comp_y1; tb.comp_x0 = comp_x0; tb.comp_x1 = comp_x1;
+    tb.comp_cls = comp_cls; tb.cls_conE = cls_conE; tb.cls_conS = cls_conS; tb.cls_fE = cls_fE; tb.cls_fS = cls_fS;
+    tb.cls_nsp = cls_nsp; tb.pair_ptr = pair_ptr; tb.pair_b = pair_b; tb.pair_npix = pair_npix; tb.pair_nsp = pair_nsp;
+    tb.pair_E = pair_E; tb.pair_S = pair_S; tb.nseg = nseg; tb.seg_t = seg_t; tb.seg_y0 = seg_y0; tb.seg_y1 = seg_y1;
+    tb.seg_a = seg_a; tb.seg_b = seg_b;
+    cth::Params pr;
+    pr.overlap = overlap; pr.persistence = persistence; pr.twosided = twosided; pr.stage = stage;
+    cth::Result res;
+    std::string err;
+    int rc = cth::host_phase_fast(tb, pr, fetch ? &src : nullptr, comp_val, res, err);
+    if (rc != 0) return fail(rc, "%s", err.c_str());
+    if (n_ovr) *n_ovr = (long)res.overrides.size();
+    if ((long)res.overrides.size() > ovr_cap)
+        return fail(CT_ERR_CAPACITY, "override capacity %ld < %zu", ovr_cap, res.overrides.size());
+    for (size_t i = 0; i < res.overrides.size(); ++i) {
+        const ctb::Override& o = res.overrides[i];
+        ovr_t[i] = o.t; ovr_y[i] = o.y; ovr_x0[i] = o.x0; ovr_x1[i] = o.x1; ovr_val[i] = o.val;
+    }
+    if (stats8) {
+        stats8[0] = res.n_features; stats8[1] = res.n_kept; stats8[2] = res.n_labels3d; stats8[3] = res.n_seam_events;
+        stats8[4] = res.n_seam_splits; stats8[5] = res.n_neartie; stats8[6] = 0; stats8[7] = 0;
+    }
+    return CT_OK;
+}
+
+// ---- time-sharded run ----------------------------------------------------------------------------------------------
+int ct_shard_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long T_local, int H, int W, const double* w_host,
+                       const double* thr_host, long thr_n, int thr_is_f32, int op, int has_prev, void* stream) {
+    if (!c) return fail(CT_ERR_ARG, "null context");
+    int rc = check_args(T_local, H, W, w_host, thr_host, thr_n, in_dtype, op);
+    if (rc != CT_OK) return rc;
+    if (T_local <= 0 || !anom_dev) return fail(CT_ERR_ARG, "a rank needs at least one plane");
+    has_prev = has_prev ? 1 : 0;
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    c->stats.clear();
+    // thresholds are indexed by scratch plane: the halo plane gets a dummy entry
+    std::vector<double> thr(thr_host, thr_host + thr_n);
+    if (thr_n != 1 && has_prev) thr.insert(thr.begin(), 0.0);
+    if ((rc = prepare(c, T_local + has_prev, H, W, w_host, thr.data(), (long)thr.size(), st)) != CT_OK) return rc;
+    c->has_prev = has_prev;
+    CT_CUDA(cudaEventRecord(c->ev[0], st));
+    if ((rc = launch_threshold(c, anom_dev, in_dtype, has_prev, T_local, (long)thr.size(), thr_is_f32, op, st)) != CT_OK)
+        return rc;
+    CT_CUDA(cudaEventRecord(c->ev[1], st));
+    return CT_OK;
+}
+
+long ct_shard_boundary_words(ct_ctx* c) { return c ? (long)c->H * c->Ww : 0; }
+
+int ct_shard_export_boundary(ct_ctx* c, uint32_t* dst_dev, void* stream) {
+    if (!c || !dst_dev || c->T <= 0) return fail(CT_ERR_ARG, "null argument / no thresholded planes");
+    const size_t words = (size_t)c->H * c->Ww;
+    CT_CUDA(cudaMemcpyAsync(dst_dev, c->bits.as<uint32_t>() + (size_t)(c->T - 1) * words, words * 4,
+                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CT_OK;
+}
+
+int ct_shard_import_halo(ct_ctx* c, const uint32_t* src_dev, void* stream) {
+    if (!c || !src_dev) return fail(CT_ERR_ARG, "null argument");
+    if (!c->has_prev) return fail(CT_ERR_ARG, "this rank was set up without a previous rank");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t words = (size_t)c->H * c->Ww;
+    CT_CUDA(cudaMemcpyAsync(c->bits.p, src_dev, words * 4, cudaMemcpyDeviceToDevice, st));
+    CT_CUDA(ctk::row_stats(c->bits.as<uint32_t>(), c->H, c->W, c->Ww, c->row_cnt.as<uint32_t>(),
+                           c->seam_flag.as<uint32_t>(), st));
+    c->launches += 1;
+    return CT_OK;
+}
+
+int ct_shard_tables(ct_ctx* c, int32_t* flag_dev, void* stream, ct_shard_view* v) {
+    if (!c || !v) return fail(CT_ERR_ARG, "null argument");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    c->zero_started_for = nullptr;
+    if (flag_dev && c->opt_overlap_zero) {
+        if (!c->side_stream) CT_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        for (auto& e : c->ev_side) if (!e) CT_CUDA(cudaEventCreate(&e));
+        CT_CUDA(cudaEventRecord(c->ev_side[0], st));
+        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+        CT_CUDA(ctk::zero_fill(flag_dev, (size_t)(c->T - c->has_prev) * c->H * c->W, c->sm_count, c->side_stream));
+        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+        c->launches += 1;
+        c->zero_started_for = flag_dev;
+    }
+    int rc = tables_gpu(c, st);
+    if (rc != CT_OK) return rc;
+    const cth::FastTables& tb = c->host_tb;
+    long nh = 0;
+    if (c->has_prev) while (nh < tb.ncomp && tb.comp_t[nh] == 0) ++nh;
+    c->halo_comps = nh;
+    v->planes = c->T; v->ncomp = tb.ncomp; v->halo_comps = nh; v->npair = c->npair; v->nseg = tb.nseg; v->nruns = c->nruns;
+    v->comp_t = tb.comp_t; v->comp_y0 = tb.comp_y0; v->comp_y1 = tb.comp_y1; v->comp_x0 = tb.comp_x0;
+    v->comp_x1 = tb.comp_x1; v->comp_cls = tb.comp_cls; v->cls_conE = tb.cls_conE; v->cls_conS = tb.cls_conS;
+    v->cls_fE = tb.cls_fE; v->cls_fS = tb.cls_fS; v->cls_nsp = tb.cls_nsp; v->cls_fnsp = tb.cls_fnsp;
+    v->pair_ptr = tb.pair_ptr; v->pair_b = tb.pair_b; v->pair_npix = tb.pair_npix; v->pair_nsp = tb.pair_nsp;
+    v->pair_E = tb.pair_E; v->pair_S = tb.pair_S; v->seg_t = tb.seg_t; v->seg_y0 = tb.seg_y0; v->seg_y1 = tb.seg_y1;
+    v->seg_a = tb.seg_a; v->seg_b = tb.seg_b;
+    return CT_OK;
+}
+
+int ct_shard_plane_runs(ct_ctx* c, long local_plane, long* n, const int32_t** y, const int32_t** x0, const int32_t** x1,
+                        const uint32_t** comp, void* stream) {
+    if (!c || !n || !y || !x0 || !x1 || !comp) return fail(CT_ERR_ARG, "null argument");
+    if (local_plane < 0 || local_plane >= c->T) return fail(CT_ERR_ARG, "plane %ld outside 0..%ld", local_plane, c->T - 1);
+    CT_CUDA(cudaSetDevice(c->device));
+    DeviceRunSource src;
+    src.c = c; src.st = (cudaStream_t)stream;
+    std::vector<cth::PlaneRun> runs;
+    if (!src.plane_runs(local_plane, runs)) return fail(CT_ERR_CUDA, "could not fetch the runs of plane %ld", local_plane);
+    const size_t k = runs.size();
+    CT_CUDA(c->hp_plane.ensure((k + 1) * 16));
+    int32_t* py = c->hp_plane.as<int32_t>();
+    int32_t* px0 = py + k + 1; int32_t* px1 = px0 + k + 1; uint32_t* pc = reinterpret_cast<uint32_t*>(px1 + k + 1);
+    for (size_t i = 0; i < k; ++i) { py[i] = runs[i].y; px0[i] = runs[i].x0; px1[i] = runs[i].x1; pc[i] = runs[i].comp; }
+    *n = (long)k; *y = py; *x0 = px0; *x1 = px1; *comp = pc;
+    return CT_OK;
+}
+
+int ct_shard_paint(ct_ctx* c, const int32_t* comp_val_local, long novr, const int32_t* ovr_t, const int32_t* ovr_y,
+                   const int32_t* ovr_x0, const int32_t* ovr_x1, const int32_t* ovr_val, int32_t* flag_dev, void* stream) {
+    if (!c || !flag_dev || (c->ncomp && !comp_val_local)) return fail(CT_ERR_ARG, "null argument");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long nc = c->ncomp, T_own = c->T - c->has_prev;
+    CT_CUDA(c->hp_val.ensure((size_t)(nc + 1) * 4));
+    int32_t* hv = c->hp_val.as<int32_t>();
+    if (nc) memcpy(hv, comp_val_local, (size_t)nc * 4);
+    std::vector<ctb::Override> ovr((size_t)novr);
+    for (long i = 0; i < novr; ++i) ovr[i] = ctb::Override{ovr_t[i], ovr_y[i], ovr_x0[i], ovr_x1[i], ovr_val[i]};
+    int rc = upload_values(c, hv, ovr, st);
+    if (rc != CT_OK) return rc;
+    const int sparse = (c->zero_started_for == flag_dev && flag_dev) ? 1 : 0;
+    if (sparse) CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
+    CT_CUDA(cudaEventRecord(c->ev[3], st));
+    if ((rc = launch_paint(c, c->has_prev, T_own, flag_dev, sparse, st)) != CT_OK) return rc;
+    if (novr) {
+        CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
+                                     c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), novr, c->H, c->W, 0, T_own, flag_dev, st));
+        c->launches += 1;
+    }
+    CT_CUDA(cudaEventRecord(c->ev[4], st));
+    CT_CUDA(cudaStreamSynchronize(st));
+    c->zero_started_for = nullptr;
+    float ms = 0;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats["ms_threshold"] = ms;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats["ms_paint"] = ms;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats["ms_total"] = ms;
+    c->stats["kernel_launches"] = (double)c->launches;
     return CT_OK;
 }
 

@@ -192,7 +192,7 @@ int host_phase_fast(const FastTables& tb, const Params& pr, RunSource* runs, int
             const double bwd = bE[c] + bS[c];
             double fb, ff;
             bool kill = kill_decision(areacon, fwd, bwd, ov, two, &fb, &ff);
-            if (tb.cls_nsp[c] + bn[c] > 0) {
+            if (tb.cls_nsp[c] + (tb.cls_fnsp ? tb.cls_fnsp[c] : 0u) + bn[c] > 0) {
                 // Sums that include special-row weights are not exactly summable: numpy's pairwise order decides the
                 // last bits.  Only a fraction within rounding distance of `overlap` can flip the decision.
                 const bool near = (std::fabs(ff - ov) <= band) || (two && std::fabs(fb - ov) <= band);

@@ -54,7 +54,8 @@ struct FastTables {
     // per class, stored at the representative's index: own area and forward overlap (all of plane t+1), E / S parts,
     // and the number of special-row pixels in those two sums
     const double *cls_conE = nullptr, *cls_conS = nullptr, *cls_fE = nullptr, *cls_fS = nullptr;
-    const uint32_t* cls_nsp = nullptr;
+    const uint32_t* cls_nsp = nullptr;       // special-row pixels in the own-area sum (+ forward sum if cls_fnsp is null)
+    const uint32_t* cls_fnsp = nullptr;      // special-row pixels in the forward sum (optional)
     // pairs of component c with components of plane t-1: entries pair_ptr[c] .. pair_ptr[c+1]
     const uint32_t* pair_ptr = nullptr;
     const uint32_t *pair_b = nullptr, *pair_npix = nullptr, *pair_nsp = nullptr;

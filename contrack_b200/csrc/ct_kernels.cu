@@ -275,6 +275,29 @@ cudaError_t launch_threshold(const ThresholdArgs& a, int blocks, cudaStream_t st
     return cudaGetLastError();
 }
 
+// run count and date-line flag of bit rows that arrived from elsewhere (the halo plane of a time-sharded run)
+__global__ void __launch_bounds__(256) k_row_stats(const uint32_t* __restrict__ bits, long nrows, int W, int Ww,
+                                                   uint32_t* __restrict__ row_cnt, uint32_t* __restrict__ seam_flag) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const uint32_t* b = bits + row * (long)Ww;
+    uint32_t cnt = 0, carry_word = 0;
+    for (int k0 = 0; k0 < Ww; k0 += 32) {
+        const uint32_t m = (k0 + lane < Ww) ? b[k0 + lane] : 0u;
+        uint32_t prev = __shfl_up_sync(FULL, m, 1);
+        if (lane == 0) prev = carry_word;
+        cnt += __popc(m & ~((m << 1) | (prev >> 31)));
+        carry_word = __shfl_sync(FULL, m, 31);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+    if (lane == 0) {
+        row_cnt[row] = cnt;
+        seam_flag[row] = (b[0] & 1u) & ((b[(W - 1) >> 5] >> ((W - 1) & 31)) & 1u);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // exclusive scan (three small kernels; inputs are row/run-sized tables, a few tens of MB at most)
 // ---------------------------------------------------------------------------------------------------------------
@@ -602,7 +625,7 @@ __global__ void __launch_bounds__(256) k_pairs_count(PairTable p, const uint32_t
     atomicAdd(total, 1u);
     const uint32_t rep = cls[(uint32_t)key];
     atomicAdd(&k.fE[rep], p.areaE[i]);
-    if (p.nsp[i]) { atomicAdd(&k.fS[rep], p.areaS[i]); atomicAdd(&k.nsp[rep], p.nsp[i]); }
+    if (p.nsp[i]) { atomicAdd(&k.fS[rep], p.areaS[i]); atomicAdd(&k.fnsp[rep], p.nsp[i]); }
 }
 
 __global__ void __launch_bounds__(256) k_pairs_fill(PairTable p, const uint32_t* __restrict__ pptr,
@@ -771,6 +794,13 @@ cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st
     if (a.in_dtype == 1) return launch_threshold<double, false>(a, blocks, st);
     if (a.thr_is_f32) return launch_threshold<float, true>(a, blocks, st);
     return launch_threshold<float, false>(a, blocks, st);
+}
+
+cudaError_t row_stats(const uint32_t* bits, long nrows, int W, int Ww, uint32_t* row_cnt, uint32_t* seam_flag,
+                      cudaStream_t st) {
+    if (nrows == 0) return cudaSuccess;
+    k_row_stats<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(bits, nrows, W, Ww, row_cnt, seam_flag);
+    return cudaGetLastError();
 }
 
 size_t scan_tmp_elems(long n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 2; }

@@ -20,6 +20,10 @@ struct ThresholdArgs {
 };
 cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st);
 
+// row_cnt / seam_flag of existing bit rows (halo plane of a time-sharded run)
+cudaError_t row_stats(const uint32_t* bits, long nrows, int W, int Ww, uint32_t* row_cnt, uint32_t* seam_flag,
+                      cudaStream_t st);
+
 // out[0..n] = exclusive prefix sums of in[0..n-1] (out[n] = total).  `tmp` needs scan_tmp_elems(n) uint32.
 size_t scan_tmp_elems(long n);
 cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st);
@@ -68,7 +72,7 @@ cudaError_t pairs_compact(const PairTable& p, uint32_t* out_a, uint32_t* out_b, 
                           double* out_E, double* out_S, uint32_t out_cap, uint32_t* count_dev, cudaStream_t st);
 
 // ---- tables in the layout of cth::FastTables ----
-struct ClassTables { double *conE, *conS, *fE, *fS; uint32_t* nsp; };          // [ncomp], zero-initialised by caller
+struct ClassTables { double *conE, *conS, *fE, *fS; uint32_t *nsp, *fnsp; };   // [ncomp], zero-initialised by caller
 struct PairCsr { uint32_t *b, *npix, *nsp; double *E, *S; };                   // [npair]
 struct SegTables { int32_t *t, *y0, *y1; uint32_t *a, *b; };                   // [nseg <= nseam]
 cudaError_t class_sums(const CompTables& c, const ClassTables& k, long ncomp, cudaStream_t st);

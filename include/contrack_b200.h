@@ -129,6 +129,64 @@ int ct_host_tables(long T, int H, int W, const double* w_host, double overlap, i
                    int32_t* comp_val, long ovr_cap, int32_t* ovr_t, int32_t* ovr_y, int32_t* ovr_x0, int32_t* ovr_x1,
                    int32_t* ovr_val, long* n_ovr, long* stats8);
 
+/* The same ordered phase on tables that are already in the sequential layout the kernels deliver (class sums at the
+ * representative's index, pairs in CSR form over their plane-t component, date-line rows grouped into segments).  This is
+ * what a time-sharded run calls after gathering every rank's tables.  `fetch` (may be NULL) supplies the row-runs of one
+ * plane when a near-tie decision or a stale-box split needs them: it sets *n and four pointers that must stay valid until
+ * the next call; component ids in `comp` are the global ones; return 0 on success. */
+typedef int (*ct_plane_runs_fn)(void* user, long t, long* n, const int32_t** y, const int32_t** x0, const int32_t** x1,
+                                const uint32_t** comp);
+int ct_host_tables_fast(long T, int H, int W, const double* w_host, double overlap, int persistence, int twosided,
+                        int stage, long ncomp, const int32_t* comp_t, const int32_t* comp_y0, const int32_t* comp_y1,
+                        const int32_t* comp_x0, const int32_t* comp_x1, const uint32_t* comp_cls,
+                        const double* cls_conE, const double* cls_conS, const double* cls_fE, const double* cls_fS,
+                        const uint32_t* cls_nsp, const uint32_t* pair_ptr, const uint32_t* pair_b,
+                        const uint32_t* pair_npix, const uint32_t* pair_nsp, const double* pair_E, const double* pair_S,
+                        long nseg, const int32_t* seg_t, const int32_t* seg_y0, const int32_t* seg_y1,
+                        const uint32_t* seg_a, const uint32_t* seg_b, ct_plane_runs_fn fetch, void* user,
+                        int32_t* comp_val, long ovr_cap, int32_t* ovr_t, int32_t* ovr_y, int32_t* ovr_x0, int32_t* ovr_x1,
+                        int32_t* ovr_val, long* n_ovr, long* stats8);
+
+/* ---- time-sharded run (one context per rank / GPU) ---------------------------------------------------
+ * Rank r owns planes [t_begin, t_end) of the cube.  Per rank:
+ *   ct_shard_threshold      threshold the own planes (contrack.py:648-674); has_prev = 1 for every rank but the first
+ *   ct_shard_export_boundary / ct_shard_import_halo
+ *                           the bit rows (H * ceil(W/32) uint32) of the last own plane go to the next rank, which stores
+ *                           them as its plane 0 ("halo"): the ONE exchange of boundary planes (NCCL send/recv by the caller)
+ *   ct_shard_tables         table kernels over halo + own planes; the tables arrive in pinned host memory (ct_shard_view,
+ *                           valid until the next call on this context).  Component ids are rank-local; the first
+ *                           `halo_comps` components belong to the halo plane.  If flag_dev is given, its zero fill is
+ *                           started on a side stream so that it overlaps the gather and the ordered phase.
+ *   (caller)                all-gather the views, renumber to global ids, run ct_host_tables_fast on every rank
+ *   ct_shard_plane_runs     row-runs of one local plane (0 = halo plane if has_prev) for the ct_plane_runs_fn callback
+ *   ct_shard_paint          values of the local components -> flag planes of this rank (contrack.py:776-791)
+ */
+typedef struct ct_shard_view {
+    long planes;              /* own planes + has_prev */
+    long ncomp, halo_comps, npair, nseg, nruns;
+    const int32_t *comp_t, *comp_y0, *comp_y1, *comp_x0, *comp_x1;     /* comp_t: local plane index (halo plane = 0) */
+    const uint32_t* comp_cls;
+    const double *cls_conE, *cls_conS, *cls_fE, *cls_fS;
+    const uint32_t *cls_nsp, *cls_fnsp;
+    const uint32_t* pair_ptr;
+    const uint32_t *pair_b, *pair_npix, *pair_nsp;
+    const double *pair_E, *pair_S;
+    const int32_t *seg_t, *seg_y0, *seg_y1;
+    const uint32_t *seg_a, *seg_b;
+} ct_shard_view;
+
+int ct_shard_threshold(ct_ctx* ctx, const void* anom_dev, int in_dtype, long T_local, int H, int W,
+                       const double* w_host, const double* thr_host, long thr_n, int thr_is_f32, int op, int has_prev,
+                       void* stream);
+long ct_shard_boundary_words(ct_ctx* ctx);
+int ct_shard_export_boundary(ct_ctx* ctx, uint32_t* dst_dev, void* stream);
+int ct_shard_import_halo(ct_ctx* ctx, const uint32_t* src_dev, void* stream);
+int ct_shard_tables(ct_ctx* ctx, int32_t* flag_dev, void* stream, ct_shard_view* view);
+int ct_shard_plane_runs(ct_ctx* ctx, long local_plane, long* n, const int32_t** y, const int32_t** x0,
+                        const int32_t** x1, const uint32_t** comp, void* stream);
+int ct_shard_paint(ct_ctx* ctx, const int32_t* comp_val_local, long novr, const int32_t* ovr_t, const int32_t* ovr_y,
+                   const int32_t* ovr_x0, const int32_t* ovr_x1, const int32_t* ovr_val, int32_t* flag_dev, void* stream);
+
 /* special_out[y] = 0 if row y belongs to the set of rows whose weights sum exactly in float64 in any order (areas of
  * those rows accumulate in areaE and equal numpy's np.sum bit for bit), 1 otherwise (pole rows: areaS, nsp). */
 void ct_classify_rows(const double* w_host, int H, int W, uint8_t* special_out);

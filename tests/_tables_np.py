@@ -135,3 +135,40 @@ def host_tables(tb, overlap, persistence, twosided, stage=0, with_runs=True):
     for i in range(n_ovr.value):
         flag[ovr[0][i], ovr[1][i], ovr[2][i]:ovr[3][i]] = ovr[4][i]
     return flag, list(stats)
+
+
+def legacy_to_view(tb, has_prev, t_begin):
+    """The dict build_tables() returns -> a rank-local view in the layout of ct_shard_view (contrack_b200/sharded.py):
+    class sums at the representative, pairs in CSR form over the plane-t component, date-line rows as segments."""
+    nc = tb['ncomp']
+    cls = tb['cls'].astype(np.int64)
+    conE = np.bincount(cls, weights=tb['aE'], minlength=nc) if nc else np.zeros(0)
+    conS = np.bincount(cls, weights=tb['aS'], minlength=nc) if nc else np.zeros(0)
+    nsp = np.bincount(cls, weights=tb['nsp'].astype(float), minlength=nc).astype(np.uint32) if nc else np.zeros(0, np.uint32)
+    pa, pb = tb['pair_a'].astype(np.int64), tb['pair_b'].astype(np.int64)
+    rep_b = cls[pb] if len(pb) else np.zeros(0, np.int64)
+    fE = np.bincount(rep_b, weights=tb['pair_E'], minlength=nc) if nc else np.zeros(0)
+    fS = np.bincount(rep_b, weights=tb['pair_S'], minlength=nc) if nc else np.zeros(0)
+    fnsp = np.bincount(rep_b, weights=tb['pair_nsp'].astype(float), minlength=nc).astype(np.uint32) if nc else np.zeros(0, np.uint32)
+    order = np.argsort(pa, kind='stable')
+    ptr = np.zeros(nc + 1, np.uint32)
+    if nc:
+        ptr[1:] = np.cumsum(np.bincount(pa, minlength=nc))
+    segs = []
+    H = tb['H']
+    for row, a, b in zip(tb['seam_row'], tb['seam_a'], tb['seam_b']):
+        t, y = int(row) // H, int(row) % H
+        if segs and segs[-1][0] == t and segs[-1][2] == y and segs[-1][3] == a and segs[-1][4] == b:
+            segs[-1][2] = y + 1
+        else:
+            segs.append([t, y, y + 1, a, b])
+    nh = int((tb['comp_t'] == 0).sum()) if has_prev else 0
+    d = dict(planes=tb['T'], ncomp=nc, halo_comps=nh, npair=len(pa), nseg=len(segs), has_prev=int(has_prev),
+             t_begin=int(t_begin), comp_t=tb['comp_t'], comp_y0=tb['y0'], comp_y1=tb['y1'], comp_x0=tb['x0'],
+             comp_x1=tb['x1'], comp_cls=tb['cls'], cls_conE=conE, cls_conS=conS, cls_fE=fE, cls_fS=fS, cls_nsp=nsp,
+             cls_fnsp=fnsp, pair_ptr=ptr, pair_b=tb['pair_b'][order], pair_npix=tb['pair_npix'][order],
+             pair_nsp=tb['pair_nsp'][order], pair_E=tb['pair_E'][order], pair_S=tb['pair_S'][order],
+             seg_t=np.array([s[0] for s in segs], np.int32), seg_y0=np.array([s[1] for s in segs], np.int32),
+             seg_y1=np.array([s[2] for s in segs], np.int32), seg_a=np.array([s[3] for s in segs], np.uint32),
+             seg_b=np.array([s[4] for s in segs], np.uint32))
+    return d

@@ -218,8 +218,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    if world > 1:
-        raise SystemExit('multi-GPU sharding is not wired into bench.py yet')
+    from contrack_b200 import sharded
 
     T = args.T
     lat, lon = grid()
@@ -227,20 +226,30 @@ def main():
     eng = Engine.get(local)
     if args.tma >= 0:
         eng.set_option('tma', args.tma)
+    t_lo, t_hi = sharded.shard_bounds(T, world)[rank]
 
-    anom = torch.empty((T, H, W), dtype=torch.float32, device='cuda')
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    anom = torch.empty((t_hi - t_lo, H, W), dtype=torch.float32, device='cuda')
     t_gen = time.perf_counter()
-    synth_fill(anom, 0, T)
+    synth_fill(anom, t_lo, T)
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
-    flag = torch.empty((T, H, W), dtype=torch.int32, device='cuda')
+    flag = torch.empty((t_hi - t_lo, H, W), dtype=torch.int32, device='cuda')
 
     def step():
-        return eng.run_contrack(anom, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=flag)
+        if world == 1:
+            return eng.run_contrack(anom, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=flag)
+        f, n, _ = sharded.run_contrack_sharded(eng, anom, t_lo, T, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED,
+                                               out=flag)
+        return f, n
 
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms_thr, ms_paint, ms_host, ms_tab, ms_zero = [], [], [], [], []
     with ClockSampler(local) as clocks:
@@ -248,35 +257,40 @@ def main():
         for _ in range(args.steps):
             _, nfeat = step()
             s = eng.stats()
-            ms_thr.append(s['ms_threshold']); ms_paint.append(s['ms_paint']); ms_host.append(s['ms_host_tables'])
-            ms_tab.append(s['ms_tables_gpu'] + s['ms_tables_host_roundtrip'])
+            ms_thr.append(s['ms_threshold']); ms_paint.append(s['ms_paint']); ms_host.append(s.get('ms_host_tables', 0.0))
+            ms_tab.append(s.get('ms_tables_gpu', 0.0) + s.get('ms_tables_host_roundtrip', 0.0))
             ms_zero.append(s.get('ms_zero_fill', 0.0))
         ev1.record()
-        torch.cuda.synchronize()
+        barrier()
     ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t_ms = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        ms = float(t_ms.item())
     stats = eng.stats()
     value = T * args.steps / (ms / 1e3)
     peak, peak_kind = measured_peak()
-    cells = T * H * W
+    cells = (t_hi - t_lo) * H * W                      # cells one launch of the cube-sized kernels processes (this rank)
     thr_ms, paint_ms = float(np.mean(ms_thr)), float(np.mean(ms_paint))
     dom = ('threshold_bits', thr_ms) if thr_ms >= paint_ms else ('paint', paint_ms)
     achieved = cells * 4 / (dom[1] / 1e3) / 1e9
-    path_gbs = cells * 8 / (ms / args.steps / 1e3) / 1e9
+    path_gbs = T * H * W * 8 / (ms / args.steps / 1e3) / 1e9
 
     line = {'metric': 'timesteps/sec (721x1440 grid) run_contrack', 'value': value, 'unit': 'timesteps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32 compare / f64 areas / int32 labels', 'data': 'synthetic',
             'config': workload_config(T, world),
-            'features': int(nfeat), 'gpu_launches': int(stats['kernel_launches']) * args.steps,
+            'features': int(nfeat), 'gpu_launches': int(stats['kernel_launches']) * args.steps * world,
             'clocks': clocks.summary(),
             'roofline': {'bound': 'hbm', 'kernel': dom[0], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': None,
                          'algorithmic_bytes_per_launch': cells * 4,
                          'note': '4 B/cell (float32 read for threshold_bits, int32 write for paint) x %d cells per '
-                                 'launch / CUDA-event time of that kernel' % cells},
-            'roofline_path': {'achieved': path_gbs, 'frac': path_gbs / peak, 'unit': 'GB/s',
-                              'note': '8 B/cell (read anomaly once + write flag once) / whole step time'},
+                                 'launch (rank 0) / CUDA-event time of that kernel' % cells},
+            'roofline_path': {'achieved': path_gbs, 'frac': path_gbs / (peak * world), 'unit': 'GB/s',
+                              'note': '8 B/cell (read anomaly once + write flag once) x all cells / whole step time; '
+                                      'frac against %d x the per-GPU peak' % world},
             'breakdown_ms': {'threshold_bits': thr_ms, 'paint': paint_ms, 'tables_gpu_and_host': float(np.mean(ms_tab)),
                              'host_table_phase': float(np.mean(ms_host)),
                              'zero_fill_overlapped_with_tables': float(np.mean(ms_zero))},
@@ -284,8 +298,8 @@ def main():
                                                   'seam_events', 'seam_splits', 'neartie_resolved') if k in stats},
             'synth_seconds': t_gen}
 
-    # ---- CPU baseline + parity on a bounded sample -------------------------------------------------------------------
-    if not args.no_cpu:
+    # ---- CPU baseline + parity on a bounded sample (rank 0 of a single-GPU run only) ---------------------------------
+    if not args.no_cpu and world == 1:
         Ts = min(args.cpu_T, T)
         sub = anom[:Ts].contiguous()
         x = sub.cpu().numpy()
@@ -299,7 +313,7 @@ def main():
                                 'bit_exact_vs_gpu': bool(np.array_equal(got.cpu().numpy(), ref))}
         del sub, got
 
-    # ---- end to end through the host-buffer entry point --------------------------------------------------------------
+    # ---- end to end: host buffers in, host buffers out, copies inside the timed region --------------------------------
     if not args.no_e2e:
         del flag
         avail = 0
@@ -312,26 +326,61 @@ def main():
         Te = args.e2e_T or min(T, 2707)
         per_plane = H * W * 8
         if avail:
-            Te = max(16, min(Te, int(0.45 * avail // per_plane)))
-        xin = torch.empty((Te, H, W), dtype=torch.float32, pin_memory=True)
-        xin.copy_(anom[:Te])
-        fout = torch.empty((Te, H, W), dtype=torch.int32, pin_memory=True)
-        xin_np, fout_np = xin.numpy(), fout.numpy()
-        torch.cuda.synchronize()
-        eng.run_contrack(xin_np, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=fout_np)      # warm-up
+            Te = max(16 * world, min(Te, int(0.45 * avail // per_plane)))
         n_e2e = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            _, nf = eng.run_contrack(xin_np, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=fout_np)
-        dt = time.perf_counter() - t0
-        s = eng.stats()
-        line['e2e'] = {'value': Te * n_e2e / dt, 'unit': 'timesteps/s', 'h2d_bytes_per_step': Te * H * W * 4,
-                       'd2h_bytes_per_step': Te * H * W * 4, 'T': Te, 'steps': n_e2e, 'features': int(nf),
-                       'ms_h2d_threshold': s.get('ms_h2d_threshold'), 'ms_tables': s.get('ms_tables'),
-                       'ms_paint_d2h': s.get('ms_paint_d2h'),
-                       'note': 'ct_run_contrack_host: pinned host float32 cube in, int32 flag cube out, chunked copies '
-                               'overlapped with the kernels; wall clock around the call'}
-    print(json.dumps(line))
+        if world == 1:
+            xin = torch.empty((Te, H, W), dtype=torch.float32, pin_memory=True)
+            xin.copy_(anom[:Te])
+            fout = torch.empty((Te, H, W), dtype=torch.int32, pin_memory=True)
+            xin_np, fout_np = xin.numpy(), fout.numpy()
+            torch.cuda.synchronize()
+            eng.run_contrack(xin_np, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=fout_np)      # warm-up
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                _, nf = eng.run_contrack(xin_np, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=fout_np)
+            dt = time.perf_counter() - t0
+            s = eng.stats()
+            extra = {'ms_h2d_threshold': s.get('ms_h2d_threshold'), 'ms_tables': s.get('ms_tables'),
+                     'ms_paint_d2h': s.get('ms_paint_d2h'),
+                     'note': 'ct_run_contrack_host: pinned host float32 cube in, int32 flag cube out, chunked copies '
+                             'overlapped with the kernels; wall clock around the call'}
+        else:
+            # every rank holds its shard of a Te-step cube in pinned host memory; per step: H2D of the shard, the sharded
+            # run, D2H of the shard's flag planes
+            e_lo, e_hi = sharded.shard_bounds(Te, world)[rank]
+            dev_in = anom[:e_hi - e_lo]
+            synth_fill(dev_in, e_lo, Te)
+            xin = torch.empty((e_hi - e_lo, H, W), dtype=torch.float32, pin_memory=True)
+            xin.copy_(dev_in)
+            fout = torch.empty((e_hi - e_lo, H, W), dtype=torch.int32, pin_memory=True)
+            dev_out = torch.empty((e_hi - e_lo, H, W), dtype=torch.int32, device='cuda')
+
+            def e2e_step():
+                dev_in.copy_(xin, non_blocking=True)
+                _, n, _ = sharded.run_contrack_sharded(eng, dev_in, e_lo, Te, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE,
+                                                       TWOSIDED, out=dev_out)
+                fout.copy_(dev_out, non_blocking=True)
+                torch.cuda.synchronize()
+                return n
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                nf = e2e_step()
+            barrier()
+            dt = time.perf_counter() - t0
+            t_dt = torch.tensor([dt], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t_dt, op=dist.ReduceOp.MAX)
+            dt = float(t_dt.item())
+            extra = {'note': 'per rank: pinned host shard -> device, sharded run, flag shard -> pinned host; wall clock, '
+                             'max over ranks'}
+        line['e2e'] = dict({'value': Te * n_e2e / dt, 'unit': 'timesteps/s', 'h2d_bytes_per_step': Te * H * W * 4,
+                            'd2h_bytes_per_step': Te * H * W * 4, 'T': Te, 'steps': n_e2e, 'features': int(nf)}, **extra)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

@@ -111,7 +111,10 @@ struct ct_ctx {
     long nseg = 0, halo_comps = 0;
     int has_prev = 0;                        // sharded run: plane 0 of the scratch is the previous rank's last plane
     PinBuf hp_plane;
-    int32_t* zero_started_for = nullptr;     // flag cube whose zero fill is in flight on the side stream
+    int32_t* zero_started_for = nullptr;
+    int special_uniform = 0;
+    long opt_gpu_tables = 1;                 // step 3 + 3-D labels on the device (single-GPU path)
+    DevBuf l_parent, l_flag, l_rank, l_label, l_kept, l_accE, l_accS, l_accN;     // flag cube whose zero fill is in flight on the side stream
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_side[2] = {nullptr, nullptr};
     long opt_overlap_zero = 1;
@@ -182,6 +185,24 @@ void classify_rows(const double* w, int H, int W, std::vector<uint8_t>& special)
     }
 }
 
+// 1 if every special row carries the same weight (e.g. the two pole rows of a regular grid)
+int special_rows_uniform(const double* w, const std::vector<uint8_t>& special) {
+    bool have = false;
+    double v = 0.0;
+    for (size_t y = 0; y < special.size(); ++y) {
+        if (!special[y]) continue;
+        if (!have) { v = w[y]; have = true; }
+        else if (memcmp(&v, &w[y], sizeof v) != 0) return 0;
+    }
+    return 1;
+}
+
+int special_rows_uniform(const double* w, int H, int W) {
+    std::vector<uint8_t> sp;
+    classify_rows(w, H, W, sp);
+    return special_rows_uniform(w, sp);
+}
+
 uint32_t next_pow2(uint64_t v) {
     uint64_t p = 1024;
     while (p < v && p < (1ull << 31)) p <<= 1;
@@ -214,6 +235,7 @@ int prepare(ct_ctx* c, long T, int H, int W, const double* w_host, const double*
     long nspecial = 0;
     for (uint8_t s : special) nspecial += s;
     c->stats["special_rows"] = (double)nspecial;
+    c->special_uniform = special_rows_uniform(w_host, special);
     CT_CUDA(c->w_dev.ensure(H * sizeof(double)));
     CT_CUDA(c->special_dev.ensure(H));
     CT_CUDA(c->thr_dev.ensure(thr_n * sizeof(double)));
@@ -249,8 +271,8 @@ int launch_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long t0, lon
     return CT_OK;
 }
 
-// GPU half of the table phase: bit rows -> runs -> components -> tables, delivered in pinned host memory (c->host_tb).
-int tables_gpu(ct_ctx* c, cudaStream_t st) {
+// GPU half of the table phase: bit rows -> runs -> components -> tables (left on the device).
+int tables_build(ct_ctx* c, cudaStream_t st) {
     const long nrows = c->T * c->H;
     const int H = c->H, W = c->W;
     uint32_t* cnt_dev = c->counters.as<uint32_t>();
@@ -358,13 +380,21 @@ int tables_gpu(ct_ctx* c, cudaStream_t st) {
         if (attempt >= 6 || pt.cap >= (1u << 31)) return fail(CT_ERR_CAPACITY, "pair table overflow");
         want = (uint64_t)pt.cap * 4;                                  // too full: probing would crawl
     }
-    const long nseg = nseam ? cnt_host[3] : 0;
+    c->nseg = nseam ? cnt_host[3] : 0;
     c->npair = np;
-    CT_CUDA(cudaEventRecord(c->ev[2], st));
+    c->stats["runs"] = (double)R; c->stats["comps2d"] = (double)nc; c->stats["pairs"] = (double)np;
+    c->stats["seam_rows"] = (double)nseam; c->stats["seam_segments"] = (double)c->nseg;
+    return CT_OK;
+}
 
+// Tables -> pinned host memory (c->host_tb).  full = 0 copies only what steps 4c/4d need (component boxes, classes,
+// date-line segments); full = 1 adds the class sums and the pair CSR for the ordered host phase / the sharded gather.
+int tables_d2h(ct_ctx* c, int full, cudaStream_t st) {
+    const long nc = c->ncomp, np = full ? c->npair : 0, nseg = c->nseg;
+    const int H = c->H, W = c->W;
     // ---- tables -> pinned host memory (8-byte arrays first) ----
     const size_t ncp = (size_t)nc + 2, npp = (size_t)np + 2, ngp = (size_t)nseg + 2;
-    const size_t bytes = ncp * (4 * 8 + 9 * 4) + npp * (2 * 8 + 3 * 4) + ngp * 5 * 4 + 512;
+    const size_t bytes = ncp * (4 * 8 + 10 * 4) + npp * (2 * 8 + 3 * 4) + ngp * 5 * 4 + 512;
     CT_CUDA(c->hp_tables.ensure(bytes));
     char* base = c->hp_tables.as<char>();
     size_t off = 0;
@@ -384,11 +414,13 @@ int tables_gpu(ct_ctx* c, cudaStream_t st) {
     if (off > c->hp_tables.cap) return fail(CT_ERR_INTERNAL, "staging layout overflow");
 #define CT_D2H(dst, src, n, elt) \
     if ((n) > 0) CT_CUDA(cudaMemcpyAsync(dst, (src).p, (size_t)(n) * (elt), cudaMemcpyDeviceToHost, st))
-    CT_D2H(h_conE, c->k_conE, nc, 8); CT_D2H(h_conS, c->k_conS, nc, 8); CT_D2H(h_fE, c->k_fE, nc, 8);
-    CT_D2H(h_fS, c->k_fS, nc, 8); CT_D2H(h_knsp, c->k_nsp, nc, 4); CT_D2H(h_kfnsp, c->k_fnsp, nc, 4);
+    if (full) {
+        CT_D2H(h_conE, c->k_conE, nc, 8); CT_D2H(h_conS, c->k_conS, nc, 8); CT_D2H(h_fE, c->k_fE, nc, 8);
+        CT_D2H(h_fS, c->k_fS, nc, 8); CT_D2H(h_knsp, c->k_nsp, nc, 4); CT_D2H(h_kfnsp, c->k_fnsp, nc, 4);
+        CT_D2H(h_pptr, c->pptr, nc + 1, 4);
+    }
     CT_D2H(h_t, c->c_t, nc, 4); CT_D2H(h_y0, c->c_y0, nc, 4); CT_D2H(h_y1, c->c_y1, nc, 4);
     CT_D2H(h_x0, c->c_x0, nc, 4); CT_D2H(h_x1, c->c_x1, nc, 4); CT_D2H(h_cls, c->c_cls, nc, 4);
-    CT_D2H(h_pptr, c->pptr, nc + 1, 4);
     CT_D2H(h_pE, c->p_E, np, 8); CT_D2H(h_pS, c->p_S, np, 8); CT_D2H(h_pb, c->p_b, np, 4);
     CT_D2H(h_pn, c->p_npix, np, 4); CT_D2H(h_pnsp, c->p_nsp, np, 4);
     CT_D2H(h_gt, c->g_t, nseg, 4); CT_D2H(h_gy0, c->g_y0, nseg, 4); CT_D2H(h_gy1, c->g_y1, nseg, 4);
@@ -397,9 +429,10 @@ int tables_gpu(ct_ctx* c, cudaStream_t st) {
     CT_CUDA(cudaStreamSynchronize(st));
     if (nc == 0) h_pptr[0] = 0;
 
-    if (const char* dump = getenv("CT_DUMP_TABLES")) {              // debugging aid: tables of this run as raw binary
+    const char* dump = full ? getenv("CT_DUMP_TABLES") : nullptr;
+    if (dump) {              // debugging aid: tables of this run as raw binary
         if (FILE* f = fopen(dump, "wb")) {
-            long hdr[8] = {c->T, H, W, nc, np, nseg, 1, 0};
+            long hdr[8] = {c->T, (long)H, (long)W, nc, np, nseg, 1, 0};
             fwrite(hdr, sizeof(long), 8, f);
             fwrite(c->w_host.data(), 8, H, f);
             fwrite(h_t, 4, nc, f); fwrite(h_y0, 4, nc, f); fwrite(h_y1, 4, nc, f); fwrite(h_x0, 4, nc, f);
@@ -424,9 +457,62 @@ int tables_gpu(ct_ctx* c, cudaStream_t st) {
     tb.pair_ptr = h_pptr; tb.pair_b = h_pb; tb.pair_npix = h_pn; tb.pair_nsp = h_pnsp; tb.pair_E = h_pE; tb.pair_S = h_pS;
     tb.nseg = nseg; tb.seg_t = h_gt; tb.seg_y0 = h_gy0; tb.seg_y1 = h_gy1; tb.seg_a = h_ga; tb.seg_b = h_gb;
     tb.w = c->w_host.data();
-    c->nseg = nseg;
-    c->stats["runs"] = (double)R; c->stats["comps2d"] = (double)nc; c->stats["pairs"] = (double)np;
-    c->stats["seam_rows"] = (double)nseam; c->stats["seam_segments"] = (double)nseg;
+    tb.special_uniform = c->special_uniform;
+    return CT_OK;
+}
+
+int tables_gpu(ct_ctx* c, cudaStream_t st) {
+    int rc = tables_build(c, st);
+    if (rc != CT_OK) return rc;
+    CT_CUDA(cudaEventRecord(c->ev[2], st));
+    return tables_d2h(c, 1, st);
+}
+
+// Steps 3 and 4a/b on the device: Jacobi sweeps to the fixpoint of the keep/kill recurrence, then 3-D labels.
+// *nflag_out = verdicts that would need the exact (numpy-order) resolver: the caller then falls back to the host phase.
+int gpu_step3_link(ct_ctx* c, double overlap, int twosided, long* nflag_out, long* nlabels_out, cudaStream_t st) {
+    const long nc = c->ncomp;
+    uint32_t* cnt_dev = c->counters.as<uint32_t>();
+    uint32_t* cnt_host = c->hp_counters.as<uint32_t>();
+    CT_CUDA(c->l_parent.ensure((size_t)(nc + 2) * 4)); CT_CUDA(c->l_flag.ensure((size_t)(nc + 2) * 4));
+    CT_CUDA(c->l_rank.ensure((size_t)(nc + 2) * 4)); CT_CUDA(c->l_label.ensure((size_t)(nc + 2) * 4));
+    CT_CUDA(c->l_kept.ensure((size_t)nc + 16)); CT_CUDA(c->l_accE.ensure((size_t)(nc + 2) * 8));
+    CT_CUDA(c->l_accS.ensure((size_t)(nc + 2) * 8)); CT_CUDA(c->l_accN.ensure((size_t)(nc + 2) * 4));
+    ctk::Step3Tables t;
+    t.comp_t = c->c_t.as<int32_t>(); t.cls = c->c_cls.as<uint32_t>();
+    t.conE = c->k_conE.as<double>(); t.conS = c->k_conS.as<double>(); t.fE = c->k_fE.as<double>();
+    t.fS = c->k_fS.as<double>(); t.nsp = c->k_nsp.as<uint32_t>(); t.fnsp = c->k_fnsp.as<uint32_t>();
+    t.pair_ptr = c->pptr.as<uint32_t>(); t.pair_b = c->p_b.as<uint32_t>(); t.pair_npix = c->p_npix.as<uint32_t>();
+    t.pair_nsp = c->p_nsp.as<uint32_t>(); t.pair_E = c->p_E.as<double>(); t.pair_S = c->p_S.as<double>();
+    t.kept = c->l_kept.as<uint8_t>(); t.accE = c->l_accE.as<double>(); t.accS = c->l_accS.as<double>();
+    t.accN = c->l_accN.as<uint32_t>();
+    CT_CUDA(ctk::step3_init(t, nc, st));
+    c->launches += 1;
+    // counters 8..8+BATCH-1: "changed" per sweep of a batch; counter 7: near-tie flags of the latest sweep
+    const int BATCH = 4;
+    long sweeps = 0;
+    for (;;) {
+        CT_CUDA(cudaMemsetAsync(cnt_dev + 8, 0, BATCH * 4, st));
+        for (int i = 0; i < BATCH; ++i) {
+            CT_CUDA(cudaMemsetAsync(cnt_dev + 7, 0, 4, st));
+            CT_CUDA(ctk::step3_sweep(t, nc, c->T, overlap, twosided, c->special_uniform, cnt_dev + 8 + i, cnt_dev + 7, st));
+            c->launches += 2;
+        }
+        sweeps += BATCH;
+        CT_CUDA(cudaMemcpyAsync(cnt_host + 7, cnt_dev + 7, (1 + BATCH) * 4, cudaMemcpyDeviceToHost, st));
+        CT_CUDA(cudaStreamSynchronize(st));
+        if (cnt_host[8 + BATCH - 1] == 0) break;                     // the last sweep of the batch changed nothing
+        if (sweeps > c->T + BATCH) return fail(CT_ERR_INTERNAL, "step-3 sweeps did not converge");
+    }
+    c->stats["sweeps"] = (double)sweeps;
+    *nflag_out = cnt_host[7];
+    if (*nflag_out) return CT_OK;
+    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(nc + 1) * 4));
+    CT_CUDA(ctk::link3d(t, nc, c->l_parent.as<uint32_t>(), c->l_flag.as<uint32_t>(), c->l_rank.as<uint32_t>(),
+                        c->scan_tmp.as<uint32_t>(), c->l_label.as<int32_t>(), st));
+    c->launches += 7;
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 6, c->l_rank.as<uint32_t>() + nc, 4, cudaMemcpyDeviceToHost, st));
+    *nlabels_out = -1;                                               // valid after the caller's next synchronize: cnt_host[6]
     return CT_OK;
 }
 
@@ -461,10 +547,59 @@ int upload_values(ct_ctx* c, const int32_t* comp_val_pinned, const std::vector<c
 // Everything between the two cube-sized kernels.  On return the value per row-run and the override sub-runs are on the
 // device.
 int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int stage, long* n_features, cudaStream_t st) {
-    int rc0 = tables_gpu(c, st);
+    int rc0 = tables_build(c, st);
     if (rc0 != CT_OK) return rc0;
     const long nc = c->ncomp;
     cth::FastTables& tb = c->host_tb;
+    if (c->opt_gpu_tables && stage != CT_STAGE_LABEL2D && stage != CT_STAGE_SEAM2D) {
+        // ---- steps 3 and 4a/b on the device; the host only replays the (few) date-line events and persistence ----
+        long nflag = 0, nlab = 0;
+        if ((rc0 = gpu_step3_link(c, overlap, twosided, &nflag, &nlab, st)) != CT_OK) return rc0;
+        c->stats["neartie_flagged"] = (double)nflag;
+        if (nflag == 0) {
+            CT_CUDA(cudaEventRecord(c->ev[2], st));
+            CT_CUDA(c->hp_val.ensure((size_t)(nc + 1) * 8 + (size_t)nc + 64));
+            int32_t* hv = c->hp_val.as<int32_t>();
+            int32_t* hlabel = hv + nc + 1;
+            uint8_t* hkept = reinterpret_cast<uint8_t*>(hlabel + nc + 1);
+            if (nc) {
+                CT_CUDA(cudaMemcpyAsync(hlabel, c->l_label.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
+                CT_CUDA(cudaMemcpyAsync(hkept, c->l_kept.p, (size_t)nc, cudaMemcpyDeviceToHost, st));
+            }
+            if ((rc0 = tables_d2h(c, 0, st)) != CT_OK) return rc0;      // synchronizes
+            const double t_host0 = now_ms();
+            cth::Result& res = c->host_result;
+            res.overrides.clear();
+            res.n_neartie = 0; res.n_features = 0; res.n_seam_events = 0; res.n_seam_splits = 0;
+            res.n_labels3d = c->hp_counters.as<uint32_t>()[6];
+            long nkept = 0;
+            for (long i = 0; i < nc; ++i) nkept += hkept[tb.comp_cls[i]];
+            res.n_kept = nkept;
+            if (stage == CT_STAGE_FILTERED) {
+                for (long i = 0; i < nc; ++i) hv[i] = hkept[tb.comp_cls[i]] ? (int32_t)(tb.comp_cls[i] + 1) : 0;
+            } else if (stage == CT_STAGE_LABEL3D) {
+                if (nc) memcpy(hv, hlabel, (size_t)nc * 4);
+            } else {
+                DeviceRunSource src;
+                src.c = c; src.st = st;
+                std::string err;
+                int rc = cth::track_phase(tb, hlabel, persistence, &src, hv, res, err);
+                if (rc != 0) return fail(rc, "%s", err.c_str());
+            }
+            c->stats["ms_host_tables"] = now_ms() - t_host0;
+            int rc = upload_values(c, hv, res.overrides, st);
+            if (rc != CT_OK) return rc;
+            c->stats["kept_comps"] = (double)res.n_kept;
+            c->stats["labels3d"] = (double)res.n_labels3d; c->stats["features"] = (double)res.n_features;
+            c->stats["seam_events"] = (double)res.n_seam_events; c->stats["seam_splits"] = (double)res.n_seam_splits;
+            c->stats["neartie_resolved"] = 0.0;
+            if (n_features) *n_features = res.n_features;
+            return CT_OK;
+        }
+        // a verdict sits within rounding distance of `overlap` on rows that do not sum exactly: replay on the host
+    }
+    CT_CUDA(cudaEventRecord(c->ev[2], st));
+    if ((rc0 = tables_d2h(c, 1, st)) != CT_OK) return rc0;
 
     // ---- ordered table phase on the host ----
     const double t_host0 = now_ms();
@@ -546,7 +681,8 @@ void ct_destroy(ct_ctx* c) {
                       &c->seg_start, &c->seg_pos, &c->g_t, &c->g_y0, &c->g_y1, &c->g_a, &c->g_b,
                       &c->o_t, &c->o_y, &c->o_x0, &c->o_x1, &c->o_val, &c->w_dev, &c->special_dev, &c->thr_dev,
                       &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0], &c->chunk_out[1],
-                      &c->a_gptr, &c->a_gidx, &c->a_gmean, &c->a_group};
+                      &c->a_gptr, &c->a_gidx, &c->a_gmean, &c->a_group,
+                      &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN};
     for (DevBuf* b : bufs) b->release();
     c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
@@ -562,6 +698,7 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "tma")) { c->opt_tma = value; return CT_OK; }
     if (!strcmp(key, "paint_tma")) { c->opt_paint_tma = value; return CT_OK; }
     if (!strcmp(key, "overlap_zero")) { c->opt_overlap_zero = value; return CT_OK; }
+    if (!strcmp(key, "gpu_tables")) { c->opt_gpu_tables = value; return CT_OK; }
     return fail(CT_ERR_ARG, "unknown option '%s'", key);
 }
 
@@ -775,7 +912,7 @@ int ct_host_tables(long T, int H, int W, const double* w_host, double overlap, i
     } src;
     src.ptr = plane_run_ptr; src.y = run_y; src.x0 = run_x0; src.x1 = run_x1; src.comp = run_comp;
     cth::Tables tb;
-    tb.T = T; tb.H = H; tb.W = W; tb.w = w_host;
+    tb.T = T; tb.H = H; tb.W = W; tb.w = w_host; tb.special_uniform = special_rows_uniform(w_host, H, W);
     tb.ncomp = ncomp; tb.comp_t = comp_t; tb.comp_y0 = comp_y0; tb.comp_y1 = comp_y1; tb.comp_x0 = comp_x0;
     tb.comp_x1 = comp_x1; tb.comp_cls = comp_cls; tb.comp_areaE = comp_areaE; tb.comp_areaS = comp_areaS;
     tb.comp_nsp = comp_nsp;
@@ -827,7 +964,7 @@ int ct_host_tables_fast(long T, int H, int W, const double* w_host, double overl
     } src;
     src.fn = fetch; src.user = user;
     cth::FastTables tb;
-    tb.T = T; tb.H = H; tb.W = W; tb.w = w_host; tb.ncomp = ncomp;
+    tb.T = T; tb.H = H; tb.W = W; tb.w = w_host; tb.ncomp = ncomp; tb.special_uniform = special_rows_uniform(w_host, H, W);
     tb.comp_t = comp_t; tb.comp_y0 = comp_y0; tb.comp_y1 = comp_y1; tb.comp_x0 = comp_x0; tb.comp_x1 = comp_x1;
     tb.comp_cls = comp_cls; tb.cls_conE = cls_conE; tb.cls_conS = cls_conS; tb.cls_fE = cls_fE; tb.cls_fS = cls_fS;
     tb.cls_nsp = cls_nsp; tb.pair_ptr = pair_ptr; tb.pair_b = pair_b; tb.pair_npix = pair_npix; tb.pair_nsp = pair_nsp;

@@ -147,7 +147,6 @@ int host_phase_fast(const FastTables& tb, const Params& pr, RunSource* runs, int
     uint32_t* const bn = ws.bn.data();
     uint32_t* const parent = ws.parent.data();
     int32_t* const label = ws.label.data();
-    std::vector<int32_t>&seg_a32 = ws.seg_a32, &seg_b32 = ws.seg_b32;
 
     // ---- step 3: contrack.py:706-742.  Plane t reads plane t-1 AFTER it was filtered and plane t+1 BEFORE. ----
     // (local copies of the table pointers: the byte-typed `kept` / `verdict` stores may alias anything otherwise)
@@ -195,7 +194,9 @@ int host_phase_fast(const FastTables& tb, const Params& pr, RunSource* runs, int
             if (tb.cls_nsp[c] + (tb.cls_fnsp ? tb.cls_fnsp[c] : 0u) + bn[c] > 0) {
                 // Sums that include special-row weights are not exactly summable: numpy's pairwise order decides the
                 // last bits.  Only a fraction within rounding distance of `overlap` can flip the decision.
-                const bool near = (std::fabs(ff - ov) <= band) || (two && std::fabs(fb - ov) <= band);
+                // (a class that lies entirely in special rows of one common weight sums exactly in any order)
+                const bool exact = tb.special_uniform && tb.cls_conE[c] == 0.0 && tb.cls_fE[c] == 0.0 && bE[c] == 0.0;
+                const bool near = !exact && ((std::fabs(ff - ov) <= band) || (two && std::fabs(fb - ov) <= band));
                 if (near) {
                     double ac2, f2, b2;
                     if (!exact_class_sums(pc, comp_cls, tb.w, kept, t, (uint32_t)c, &ac2, &f2, &b2)) {
@@ -246,20 +247,29 @@ int host_phase_fast(const FastTables& tb, const Params& pr, RunSource* runs, int
     lap("link3d");
     if (pr.stage == 4) { memcpy(comp_val, label, (size_t)nc * 4); return 0; }
 
+    int rc = track_phase(tb, label, pr.persistence, runs, comp_val, out, err);
+    lap("track");
+    return rc;
+}
+
+int track_phase(const FastTables& tb, const int32_t* label, int persistence, RunSource* runs, int32_t* comp_val,
+                Result& out, std::string& err) {
     // ---- step 4c/d (ct_tables.cpp): removed components carry label 0 and are skipped there ----
+    const long nc = tb.ncomp;
+    static thread_local std::vector<int32_t> seg_a32, seg_b32;
     seg_a32.resize(tb.nseg); seg_b32.resize(tb.nseg);
     for (long s = 0; s < tb.nseg; ++s) {
         if (tb.seg_a[s] >= (uint32_t)nc || tb.seg_b[s] >= (uint32_t)nc) { err = "seam table out of range"; return -5; }
         seg_a32[s] = (int32_t)tb.seg_a[s]; seg_b32[s] = (int32_t)tb.seg_b[s];
     }
+    PlaneCache pc(runs, tb.H);
     SplitFetcher fetcher;
     fetcher.pc = &pc; fetcher.comp_t = tb.comp_t;
     ctb::TrackStats stats;
-    int rc = ctb::track_tables(T, tb.H, tb.W, pr.persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0,
+    int rc = ctb::track_tables(tb.T, tb.H, tb.W, persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0,
                                tb.comp_x1, label, tb.nseg, tb.seg_t, tb.seg_y0, tb.seg_y1, seg_a32.data(),
                                seg_b32.data(), runs ? &fetcher : nullptr, comp_val, out.overrides, stats);
     if (rc != 0) { err = "date-line merge needs to split a component and no run source is available"; return -5; }
-    lap("track");
     out.n_features = stats.n_features; out.n_seam_events = stats.n_events; out.n_seam_splits = stats.n_splits;
     return 0;
 }
@@ -310,7 +320,7 @@ int host_phase(const Tables& tb, const Params& pr, RunSource* runs, Result& out,
     ft.cls_nsp = cnsp.data(); ft.pair_ptr = pptr.data(); ft.pair_b = pb.data(); ft.pair_npix = pn.data();
     ft.pair_nsp = pnsp.data(); ft.pair_E = pE.data(); ft.pair_S = pS.data();
     ft.nseg = (long)st.size(); ft.seg_t = st.data(); ft.seg_y0 = sy0.data(); ft.seg_y1 = sy1.data();
-    ft.seg_a = sa.data(); ft.seg_b = sb.data(); ft.w = tb.w;
+    ft.seg_a = sa.data(); ft.seg_b = sb.data(); ft.w = tb.w; ft.special_uniform = tb.special_uniform;
     for (long c = 0; c < nc; ++c)
         if (c > 0 && tb.comp_t[c] < tb.comp_t[c - 1]) { err = "component table not sorted by time"; return -5; }
     return host_phase_fast(ft, pr, runs, out.comp_val.data(), out, err);

@@ -40,6 +40,7 @@ struct Tables {
     long nseam = 0;
     const uint32_t *seam_row = nullptr, *seam_a = nullptr, *seam_b = nullptr;
     const double* w = nullptr;               // [H] area weight per row (contrack.py:703-704)
+    int special_uniform = 0;                 // see FastTables
 };
 
 // The layout the CUDA kernels deliver (everything the ordered phase reads is sequential in memory):
@@ -64,6 +65,7 @@ struct FastTables {
     const int32_t *seg_t = nullptr, *seg_y0 = nullptr, *seg_y1 = nullptr;
     const uint32_t *seg_a = nullptr, *seg_b = nullptr;
     const double* w = nullptr;
+    int special_uniform = 0;                 // 1: all special rows carry the same weight (the two poles of a regular grid)
 };
 
 struct Params {
@@ -82,6 +84,10 @@ struct Result {
 // returns 0, or a negative ct_status with `err` filled.  `comp_val` [ncomp] receives the value painted per component.
 int host_phase_fast(const FastTables& tb, const Params& pr, RunSource* runs, int32_t* comp_val, Result& out,
                     std::string& err);
+// Steps 4c/4d only (date-line merge through stale boxes + persistence) for 3-D labels computed elsewhere (on the device):
+// uses tb's component boxes and segments; label[c] = 0 marks removed components.
+int track_phase(const FastTables& tb, const int32_t* label, int persistence, RunSource* runs, int32_t* comp_val,
+                Result& out, std::string& err);
 // same from the unsorted tables (converts, then calls host_phase_fast); result in out.comp_val
 int host_phase(const Tables& tb, const Params& pr, RunSource* runs, Result& out, std::string& err);
 

@@ -664,6 +664,107 @@ __global__ void __launch_bounds__(256) k_seg_write(const uint32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// step 3 on the device (contrack.py:706-742).  The keep/kill state of plane t depends on the FINAL state of plane t-1
+// only, so the recurrence has exactly one solution; Jacobi sweeps over all classes at once (state of the previous
+// sweep in, new state out) reach it: after sweep k every plane <= k is final, and in practice a handful of sweeps
+// suffice because a changed verdict rarely flips the verdict of its successors for more than a step or two.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool kill_decision_dev(double areacon, double fwd, double bwd, double ov, bool twosided,
+                                                  double* fb_out, double* ff_out) {
+    const double inv = __ddiv_rn(1.0, areacon);       // contrack.py:721-722: reciprocal, then multiply -- two roundings
+    const double fb = __dmul_rn(inv, bwd);
+    const double ff = __dmul_rn(inv, fwd);
+    *fb_out = fb; *ff_out = ff;
+    bool kill = false;
+    if (twosided) {
+        if (fb != 0 && ff != 0) { if ((fb < ov) || (ff < ov)) kill = true; }
+        if (fb != 0 && ff == 0) { if (fb < ov) kill = true; }
+        if (fb == 0 && ff != 0) { if (ff < ov) kill = true; }
+    } else {
+        if (ff < ov) kill = true;
+    }
+    return kill;
+}
+
+__global__ void __launch_bounds__(256) k_fill_u8(uint8_t* p, long n, uint8_t v) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// backward overlap with the components of plane t-1 that are currently kept, summed per class
+__global__ void __launch_bounds__(256) k_step3_acc(Step3Tables t, long ncomp, long T) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncomp) return;
+    const int tt = t.comp_t[c];
+    if (tt < 1 || tt + 1 >= T) return;
+    double e = 0.0, s2 = 0.0;
+    uint32_t n = 0;
+    const uint32_t k1 = t.pair_ptr[c + 1];
+    for (uint32_t k = t.pair_ptr[c]; k < k1; ++k) {
+        if (!t.kept[t.cls[t.pair_b[k]]]) continue;
+        e += t.pair_E[k]; s2 += t.pair_S[k]; n += t.pair_nsp[k];
+    }
+    const uint32_t rep = t.cls[c];
+    if (e != 0.0) atomicAdd(&t.accE[rep], e);
+    if (n) { atomicAdd(&t.accS[rep], s2); atomicAdd(&t.accN[rep], n); }
+}
+
+// one thread per class representative: verdict from the sums, reset of the accumulators, change / near-tie bookkeeping
+__global__ void __launch_bounds__(256) k_step3_decide(Step3Tables t, long ncomp, long T, double ov, int twosided,
+                                                      int special_uniform, uint32_t* __restrict__ changed,
+                                                      uint32_t* __restrict__ nflag) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncomp || t.cls[c] != (uint32_t)c) return;
+    const int tt = t.comp_t[c];
+    if (tt < 1 || tt + 1 >= T) return;
+    const double bE = t.accE[c], bS = t.accS[c];
+    const uint32_t bn = t.accN[c];
+    t.accE[c] = 0.0; t.accS[c] = 0.0; t.accN[c] = 0;
+    const double areacon = __dadd_rn(t.conE[c], t.conS[c]), fwd = __dadd_rn(t.fE[c], t.fS[c]), bwd = __dadd_rn(bE, bS);
+    double fb, ff;
+    const bool kill = kill_decision_dev(areacon, fwd, bwd, ov, twosided != 0, &fb, &ff);
+    if (t.nsp[c] + t.fnsp[c] + bn > 0) {
+        // sums with special-row weights are not exactly summable in general: a fraction within rounding distance of
+        // `overlap` must be decided in numpy's summation order (host).  Exception: a class that lies entirely in special
+        // rows of one common weight -- every sum is a small integer multiple of that weight, exact in any order.
+        const bool near = (fabs(ff - ov) <= 1e-9) || (twosided && fabs(fb - ov) <= 1e-9);
+        const bool exact = special_uniform && t.conE[c] == 0.0 && t.fE[c] == 0.0 && bE == 0.0;
+        if (near && !exact) atomicAdd(nflag, 1u);
+    }
+    const uint8_t nk = kill ? 0 : 1;
+    if (t.kept[c] != nk) { t.kept[c] = nk; *changed = 1u; }
+}
+
+// 3-D linking (contrack.py:747-751): kept components that share a pixel in adjacent planes
+__global__ void __launch_bounds__(256) k_link_union(Step3Tables t, long ncomp, uint32_t* parent) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncomp || !t.kept[t.cls[c]]) return;
+    const uint32_t k1 = t.pair_ptr[c + 1];
+    for (uint32_t k = t.pair_ptr[c]; k < k1; ++k) {
+        const uint32_t b = t.pair_b[k];
+        if (t.pair_npix[k] && t.kept[t.cls[b]]) uf_union(parent, (uint32_t)c, b);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_link_roots(Step3Tables t, long ncomp, uint32_t* parent,
+                                                    uint32_t* __restrict__ root_flag) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncomp) return;
+    if (!t.kept[t.cls[c]]) { root_flag[c] = 0; return; }
+    const uint32_t root = uf_find(parent, (uint32_t)c);
+    root_flag[c] = root == (uint32_t)c ? 1u : 0u;
+    if (root != (uint32_t)c) parent[c] = root;
+}
+
+// label = 1 + number of roots with a smaller id (scipy numbers 3-D components by first pixel); 0 for removed components
+__global__ void __launch_bounds__(256) k_link_labels(Step3Tables t, long ncomp, const uint32_t* __restrict__ parent,
+                                                     const uint32_t* __restrict__ rank, int32_t* __restrict__ label) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncomp) return;
+    label[c] = t.kept[t.cls[c]] ? (int32_t)(rank[uf_find(parent, (uint32_t)c)] + 1u) : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // paint: bit rows + value per run -> int32 cube.  One warp per row, 1024 cells (32 mask words) per pass; a lane owns
 // four consecutive cells and stores them as one 16-byte streaming store.
 // ---------------------------------------------------------------------------------------------------------------
@@ -957,6 +1058,35 @@ cudaError_t seg_write(const uint32_t* srow, const uint32_t* sa, const uint32_t* 
                       const uint32_t* segpos, long n, int H, const SegTables& o, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     k_seg_write<<<blocks_for(n, 256), 256, 0, st>>>(srow, sa, sb, start, segpos, n, H, o);
+    return cudaGetLastError();
+}
+
+cudaError_t step3_init(const Step3Tables& t, long ncomp, cudaStream_t st) {
+    if (ncomp == 0) return cudaSuccess;
+    k_fill_u8<<<blocks_for(ncomp, 256), 256, 0, st>>>(t.kept, ncomp, 1);
+    cudaError_t e = cudaMemsetAsync(t.accE, 0, (size_t)ncomp * 8, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(t.accS, 0, (size_t)ncomp * 8, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(t.accN, 0, (size_t)ncomp * 4, st);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t step3_sweep(const Step3Tables& t, long ncomp, long T, double overlap, int twosided, int special_uniform,
+                        uint32_t* changed, uint32_t* nflag, cudaStream_t st) {
+    if (ncomp == 0) return cudaSuccess;
+    k_step3_acc<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, T);
+    k_step3_decide<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, T, overlap, twosided, special_uniform, changed, nflag);
+    return cudaGetLastError();
+}
+
+cudaError_t link3d(const Step3Tables& t, long ncomp, uint32_t* parent, uint32_t* root_flag, uint32_t* rank,
+                   uint32_t* scan_tmp, int32_t* label, cudaStream_t st) {
+    if (ncomp == 0) return cudaMemsetAsync(rank, 0, 4, st);
+    k_iota<<<blocks_for(ncomp, 256), 256, 0, st>>>(parent, ncomp);
+    k_link_union<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, parent);
+    k_link_roots<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, parent, root_flag);
+    cudaError_t e = exclusive_scan_u32(root_flag, rank, ncomp, scan_tmp, st);
+    if (e != cudaSuccess) return e;
+    k_link_labels<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, parent, rank, label);
     return cudaGetLastError();
 }
 

@@ -214,3 +214,33 @@ def test_dense_paint_path(eng, fixture_cube, golden):
         assert sha_i4(f) == r['sha256']
     finally:
         eng.set_option('overlap_zero', 1)
+
+
+def test_near_tie_on_pole_rows_falls_back_to_exact_host_sums(eng, fixture_cube):
+    from _common import pole_tie_overlaps
+    a, lat, lon = fixture_cube
+    flagged = 0
+    for thr in (100, 150):
+        for ov in pole_tie_overlaps(a, lat, lon, thr):
+            for two in (True, False):
+                f, _ = gpu_run(eng, a, lat, lon, thr, '>=', ov, 1, two)
+                assert np.array_equal(f, oracle.run_contrack(a, lat, lon, thr, '>=', ov, 1, two)), (thr, ov, two)
+                flagged += eng.stats().get('neartie_flagged', 0)
+    assert flagged > 0
+
+
+def test_host_table_path_matches_device_table_path(eng, golden):
+    """gpu_tables=0: the ordered phase runs entirely on the host (the path the sharded run uses)."""
+    r = golden['synthetic'][0]
+    T, H, W = r['shape']
+    x = synth_cube(r['seed'], T, H, W, tuple(r['sigma']))
+    lat, lon = regular_grid(H, W)
+    eng.set_option('gpu_tables', 0)
+    try:
+        f, _ = gpu_run(eng, x, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
+        assert sha_i4(f) == r['sha256']
+        assert 'sweeps' not in eng.stats()
+    finally:
+        eng.set_option('gpu_tables', 1)
+    f, _ = gpu_run(eng, x, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
+    assert sha_i4(f) == r['sha256'] and eng.stats()['sweeps'] >= 1

@@ -85,3 +85,23 @@ def test_split_without_runs_is_an_error():
     assert st[4] > 0
     with pytest.raises(ContrackLibError):
         host_tables(tb, 0.0, 1, False, with_runs=False)
+
+
+def test_near_tie_on_pole_rows_uses_numpy_summation_order(fixture_cube):
+    """overlap placed exactly on a fraction of a class that mixes a pole row with ordinary rows (contrack.py:721-742)."""
+    from _common import pole_tie_overlaps
+    a, lat, lon = fixture_cube
+    w = row_weights(lat, lon)
+    ties = 0
+    for thr in (100, 150):
+        tb = build_tables(a >= thr, w)
+        vals = pole_tie_overlaps(a, lat, lon, thr)
+        assert vals
+        for ov in vals:
+            for two in (True, False):
+                f, st = host_tables(tb, ov, 1, two)
+                assert np.array_equal(f, oracle.run_contrack(a, lat, lon, thr, '>=', ov, 1, two)), (thr, ov, two)
+                ties += st[5]
+    assert ties > 0                          # the exact resolver really ran
+    with pytest.raises(Exception):           # and without row-runs the library refuses to guess
+        host_tables(build_tables(a >= 100, w), pole_tie_overlaps(a, lat, lon, 100)[0], 1, True, with_runs=False)

@@ -33,6 +33,19 @@ int main(int argc, char** argv) {
     pr.overlap = argc > 2 ? atof(argv[2]) : 0.51; pr.persistence = 5; pr.twosided = 1;
     vector<int32_t> val(nc + 1);
     printf("T %ld comps %ld pairs %ld segments %ld\n", T, nc, np, ng);
+    {   // steps 4c/4d alone, on the 3-D labels (what the host still does when step 3 / linking run on the device)
+        cth::Params p4 = pr; p4.stage = 4;
+        vector<int32_t> label(nc + 1);
+        cth::Result r; string err;
+        cth::host_phase_fast(tb, p4, nullptr, label.data(), r, err);
+        for (int i = 0; i < 6; i++) {
+            auto a = chrono::steady_clock::now();
+            int rc = cth::track_phase(tb, label.data(), pr.persistence, nullptr, val.data(), r, err);
+            auto b = chrono::steady_clock::now();
+            printf("track_phase rc %d features %ld events %ld: %.3f ms\n", rc, r.n_features, r.n_seam_events,
+                   chrono::duration<double, milli>(b - a).count());
+        }
+    }
     for (int i = 0; i < 6; i++) {
         cth::Result r; string err;
         auto a = chrono::steady_clock::now();

@@ -115,7 +115,9 @@ struct ct_ctx {
     int special_uniform = 0;
     long opt_gpu_tables = 1;                 // step 3 + 3-D labels on the device (single-GPU path)
     DevBuf l_parent, l_flag, l_rank, l_label, l_kept, l_accE, l_accS, l_accN;     // flag cube whose zero fill is in flight on the side stream
-    cudaStream_t side_stream = nullptr;
+    cudaStream_t side_stream = nullptr;      // zero fill (lowest priority)
+    cudaStream_t tbl_stream = nullptr;       // table phase (highest priority): must get onto the SMs between fill blocks
+    cudaEvent_t ev_tbl[2] = {nullptr, nullptr};
     cudaEvent_t ev_side[2] = {nullptr, nullptr};
     long opt_overlap_zero = 1;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -626,6 +628,17 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
     return CT_OK;
 }
 
+// side streams: zero fill at the lowest priority, table phase at the highest
+int ensure_streams(ct_ctx* c) {
+    int lo = 0, hi = 0;
+    CT_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    if (!c->side_stream) CT_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
+    if (!c->tbl_stream) CT_CUDA(cudaStreamCreateWithPriority(&c->tbl_stream, cudaStreamNonBlocking, hi));
+    for (auto& e : c->ev_side) if (!e) CT_CUDA(cudaEventCreate(&e));
+    for (auto& e : c->ev_tbl) if (!e) CT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return CT_OK;
+}
+
 // paint planes [t0, t0+nt) into `flag_dev` (which starts at plane t0)
 int launch_paint(ct_ctx* c, long t0, long nt, int32_t* flag_dev, int sparse, cudaStream_t st) {
     ctk::PaintArgs a;
@@ -687,6 +700,8 @@ void ct_destroy(ct_ctx* c) {
     c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    for (auto& e : c->ev_tbl) if (e) cudaEventDestroy(e);
+    if (c->tbl_stream) cudaStreamDestroy(c->tbl_stream);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->work_stream) cudaStreamDestroy(c->work_stream);
@@ -724,20 +739,26 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     // the flag cube -- most of the 4 B/cell the path has to write -- runs under it on a side stream; afterwards only the
     // cells of row-runs are painted.
     const int sparse = c->opt_overlap_zero ? 1 : 0;
+    cudaStream_t ts = st;
     if (sparse) {
-        if (!c->side_stream) CT_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-        for (auto& e : c->ev_side) if (!e) CT_CUDA(cudaEventCreate(&e));
+        if ((rc = ensure_streams(c)) != CT_OK) return rc;
         CT_CUDA(cudaEventRecord(c->ev_side[0], st));
         CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+        CT_CUDA(cudaStreamWaitEvent(c->tbl_stream, c->ev_side[0], 0));
         CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T * H * W, c->sm_count, c->side_stream));
         CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
         c->launches += 1;
+        ts = c->tbl_stream;
     }
-    if ((rc = table_phase(c, overlap, persistence, twosided, stage, n_features, st)) != CT_OK) {
-        if (sparse) cudaStreamSynchronize(c->side_stream);
+    if ((rc = table_phase(c, overlap, persistence, twosided, stage, n_features, ts)) != CT_OK) {
+        if (sparse) { cudaStreamSynchronize(c->side_stream); cudaStreamSynchronize(c->tbl_stream); }
         return rc;
     }
-    if (sparse) CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
+    if (sparse) {
+        CT_CUDA(cudaEventRecord(c->ev_tbl[0], ts));
+        CT_CUDA(cudaStreamWaitEvent(st, c->ev_tbl[0], 0));
+        CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
+    }
     CT_CUDA(cudaEventRecord(c->ev[3], st));
     if ((rc = launch_paint(c, 0, T, flag_dev, sparse, st)) != CT_OK) return rc;
     if (c->novr) {
@@ -1040,17 +1061,20 @@ int ct_shard_tables(ct_ctx* c, int32_t* flag_dev, void* stream, ct_shard_view* v
     CT_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     c->zero_started_for = nullptr;
+    int rc;
+    cudaStream_t ts = st;
     if (flag_dev && c->opt_overlap_zero) {
-        if (!c->side_stream) CT_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-        for (auto& e : c->ev_side) if (!e) CT_CUDA(cudaEventCreate(&e));
+        if ((rc = ensure_streams(c)) != CT_OK) return rc;
         CT_CUDA(cudaEventRecord(c->ev_side[0], st));
         CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+        CT_CUDA(cudaStreamWaitEvent(c->tbl_stream, c->ev_side[0], 0));
         CT_CUDA(ctk::zero_fill(flag_dev, (size_t)(c->T - c->has_prev) * c->H * c->W, c->sm_count, c->side_stream));
         CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
         c->launches += 1;
         c->zero_started_for = flag_dev;
+        ts = c->tbl_stream;
     }
-    int rc = tables_gpu(c, st);
+    rc = tables_gpu(c, ts);                                       // ends with a synchronize of ts
     if (rc != CT_OK) return rc;
     const cth::FastTables& tb = c->host_tb;
     long nh = 0;

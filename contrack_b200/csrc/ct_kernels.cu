@@ -371,17 +371,20 @@ __global__ void __launch_bounds__(256) k_extract_runs(const uint32_t* __restrict
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     uint16_t* rx = reinterpret_cast<uint16_t*>(run_x);
     for (long row = warp0; row < nrows; row += nwarps) {
-        const uint32_t base = row_ptr[row];
-        if (row_ptr[row + 1] == base) continue;
+        // everything a 64-word row needs is requested before anything is consumed: one memory latency per row
         const uint32_t* b = bits + row * (long)Ww;
+        const uint32_t base = row_ptr[row], next = row_ptr[row + 1];
+        uint32_t m = lane < Ww ? b[lane] : 0u;
+        uint32_t m_ahead = (32 + lane < Ww) ? b[32 + lane] : 0u;
+        if (next == base) continue;
         uint32_t sbase = base, ebase = base, prev = 0;
         for (int k0 = 0; k0 < Ww; k0 += 32) {
             const int k = k0 + lane;
-            const uint32_t m = k < Ww ? b[k] : 0u;
             uint32_t left = __shfl_up_sync(FULL, m, 1);
             if (lane == 0) left = prev;
             uint32_t right = __shfl_down_sync(FULL, m, 1);
-            if (lane == 31) right = (k + 1 < Ww) ? b[k + 1] : 0u;
+            const uint32_t ahead0 = __shfl_sync(FULL, m_ahead, 0);
+            if (lane == 31) right = ahead0;
             uint32_t starts = m & ~((m << 1) | (left >> 31));
             uint32_t ends = m & ~((m >> 1) | (right << 31));
             uint32_t ts, te;
@@ -402,6 +405,8 @@ __global__ void __launch_bounds__(256) k_extract_runs(const uint32_t* __restrict
             }
             sbase += ts; ebase += te;
             prev = __shfl_sync(FULL, m, 31);
+            m = m_ahead;
+            m_ahead = (k0 + 64 + lane < Ww) ? b[k0 + 64 + lane] : 0u;
         }
     }
 }
@@ -776,9 +781,17 @@ __global__ void __launch_bounds__(256) k_run_values(const uint32_t* __restrict__
 }
 
 // streaming zero fill (16-byte stores); runs on a side stream while the table phase is busy
+// Short-lived blocks (64 KB each) on purpose: the fill runs on a low-priority stream underneath the latency-bound
+// table kernels, which can only get onto an SM when a block of the fill retires.
+constexpr int ZERO_PER_THREAD = 16;
 __global__ void __launch_bounds__(256) k_zero_fill(int4* __restrict__ p, size_t n16, int32_t* __restrict__ tail, int ntail) {
     const int4 z = make_int4(0, 0, 0, 0);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) __stcs(p + i, z);
+    const size_t base = (size_t)blockIdx.x * (256 * ZERO_PER_THREAD) + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < ZERO_PER_THREAD; ++i) {
+        const size_t j = base + (size_t)i * 256;
+        if (j < n16) __stcs(p + j, z);
+    }
     if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = 0;
 }
 
@@ -918,7 +931,8 @@ cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32
 cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long nrows, int Ww, uint32_t* run_x,
                          uint32_t* run_row, cudaStream_t st) {
     if (nrows == 0) return cudaSuccess;
-    k_extract_runs<<<blocks_for(nrows, 8), 256, 0, st>>>(bits, row_ptr, nrows, Ww, run_x, run_row);
+    const long want = (nrows + 7) / 8;
+    k_extract_runs<<<(unsigned)std::min<long>(want, 148L * 16), 256, 0, st>>>(bits, row_ptr, nrows, Ww, run_x, run_row);
     return cudaGetLastError();
 }
 
@@ -1026,7 +1040,10 @@ cudaError_t zero_fill(int32_t* p, size_t n, int sm_count, cudaStream_t st) {
     // and torch allocations are 256/512-byte aligned)
     if (reinterpret_cast<uintptr_t>(p) & 15) return cudaMemsetAsync(p, 0, n * 4, st);
     const size_t n16 = n / 4;
-    k_zero_fill<<<sm_count * 8, 256, 0, st>>>(reinterpret_cast<int4*>(p), n16, p + n16 * 4, (int)(n - n16 * 4));
+    const size_t per_block = 256 * ZERO_PER_THREAD;
+    (void)sm_count;
+    k_zero_fill<<<(unsigned)((n16 + per_block - 1) / per_block + (n16 == 0)), 256, 0, st>>>(
+        reinterpret_cast<int4*>(p), n16, p + n16 * 4, (int)(n - n16 * 4));
     return cudaGetLastError();
 }
 

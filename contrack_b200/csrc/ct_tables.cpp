@@ -45,25 +45,25 @@ int track_tables(long T, int H, int W, int persistence,
                  long nseg, const int32_t* seg_t, const int32_t* seg_y0, const int32_t* seg_y1,
                  const int32_t* seg_a, const int32_t* seg_b,
                  RunFetcher* fetcher, int32_t* comp_val, std::vector<Override>& overrides, TrackStats& stats) {
-    (void)H;
+    (void)H; (void)T; (void)seg_t;
     overrides.clear();
     stats = TrackStats();
-    int nlabel = 0;
-    for (long c = 0; c < ncomp; ++c) nlabel = std::max(nlabel, (int)comp_label[c]);
 
     // Buffers live across calls (one set per host thread): a fresh multi-megabyte vector per call costs more in page
     // faults than the work done on it.
     struct Workspace {
-        std::vector<int> value, tmin, tmax, fin;
+        std::vector<int> value, tmin, tmax, fin, head;
+        std::vector<long> nxt;
         std::vector<Box3> box;
-        std::vector<long> first, order, pos;
     };
     static thread_local Workspace tls_ws;
     Workspace& ws = tls_ws;                      // one TLS lookup, not one per access
-    std::vector<int>&value = ws.value, &tmin = ws.tmin, &tmax = ws.tmax, &fin = ws.fin;
+    std::vector<int>&value = ws.value, &tmin = ws.tmin, &tmax = ws.tmax, &fin = ws.fin, &head = ws.head;
+    std::vector<long>& nxt = ws.nxt;
     std::vector<Box3>& box = ws.box;
-    std::vector<long>&first = ws.first, &order = ws.order, &pos = ws.pos;
 
+    int nlabel = 0;
+    for (long c = 0; c < ncomp; ++c) nlabel = std::max(nlabel, (int)comp_label[c]);
     // value of each whole component (0 = removed before this stage); pieces beyond ncomp only exist after a split
     value.assign(comp_label, comp_label + ncomp);
     std::vector<Piece> extra;                               // pieces created by splits (index ncomp + k)
@@ -78,32 +78,38 @@ int track_tables(long T, int H, int W, int persistence,
         return p;
     };
 
-    if (nseg > 0) {
-        // 3-D boxes of the ORIGINAL labels (find_objects before merging, contrack.py:753)
-        box.assign(nlabel + 1, Box3{INT_MAX, 0, INT_MAX, 0, INT_MAX, 0});
-        // CSR of components per original label (stable: first-pixel order)
-        first.assign(nlabel + 2, 0);
-        for (long c = 0; c < ncomp; ++c) {
-            if (comp_label[c] == 0) continue;
-            Box3& b = box[comp_label[c]];
-            b.t0 = std::min(b.t0, (int)comp_t[c]); b.t1 = std::max(b.t1, (int)comp_t[c] + 1);
-            b.y0 = std::min(b.y0, (int)comp_y0[c]); b.y1 = std::max(b.y1, (int)comp_y1[c]);
-            b.x0 = std::min(b.x0, (int)comp_x0[c]); b.x1 = std::max(b.x1, (int)comp_x1[c]);
-            first[comp_label[c] + 1]++;
+    // 3-D boxes of the ORIGINAL labels (find_objects before merging, contrack.py:753); their t-extent is also the
+    // persistence extent of every label no date-line event touches
+    box.assign(nlabel + 1, Box3{INT_MAX, 0, INT_MAX, 0, INT_MAX, 0});
+    for (long c = 0; c < ncomp; ++c) {
+        const int v = comp_label[c];
+        if (v == 0) continue;
+        Box3& b = box[v];
+        b.t0 = std::min(b.t0, (int)comp_t[c]); b.t1 = std::max(b.t1, (int)comp_t[c] + 1);
+        b.y0 = std::min(b.y0, (int)comp_y0[c]); b.y1 = std::max(b.y1, (int)comp_y1[c]);
+        b.x0 = std::min(b.x0, (int)comp_x0[c]); b.x1 = std::max(b.x1, (int)comp_x1[c]);
+    }
+    tmin.resize(nlabel + 1); tmax.resize(nlabel + 1);
+    for (int v = 0; v <= nlabel; ++v) { tmin[v] = box[v].t0; tmax[v] = box[v].t1 - 1; }
+
+    // does any date-line row join two different labels at all?  (usually only a few per cent of the segments do)
+    bool any_event = false;
+    for (long s = 0; s < nseg && !any_event; ++s) {
+        const int la = comp_label[seg_a[s]], lb = comp_label[seg_b[s]];
+        any_event = la != 0 && lb != 0 && la != lb;
+    }
+
+    if (any_event) {
+        // member lists of the labels: intrusive singly linked lists (head per value, next per piece); moving a piece from
+        // one value to another is an unlink + push, no allocation.  Order inside a list does not matter: every member is
+        // classified against the same stale box independently.
+        head.assign(nlabel + 1, -1);
+        nxt.assign(ncomp, -1);
+        for (long c = ncomp - 1; c >= 0; --c) {
+            const int v = comp_label[c];
+            if (v == 0) continue;
+            nxt[c] = head[v]; head[v] = (int)c;
         }
-        for (int v = 0; v <= nlabel; ++v) first[v + 1] += first[v];
-        order.resize(ncomp);
-        pos.assign(first.begin(), first.end() - 1);
-        for (long c = 0; c < ncomp; ++c) if (comp_label[c] != 0) order[pos[comp_label[c]]++] = c;
-        // dynamic member lists (piece ids), created on first use from the CSR
-        std::unordered_map<int, std::vector<long>> members;
-        auto get_members = [&](int v) -> std::vector<long>& {
-            auto it = members.find(v);
-            if (it != members.end()) return it->second;
-            std::vector<long>& m = members[v];
-            m.assign(order.begin() + first[v], order.begin() + first[v + 1]);
-            return m;
-        };
         auto piece_ref = [&](long pid) -> Piece* {           // only valid until `extra` / `whole_runs` grow
             if (pid >= ncomp) return &extra[pid - ncomp];
             auto it = whole_runs_idx.find(pid);
@@ -111,6 +117,7 @@ int track_tables(long T, int H, int W, int persistence,
         };
         auto piece_value = [&](long pid) -> int { return pid >= ncomp ? extra[pid - ncomp].value : value[pid]; };
         auto piece_of = [&](long c, int y, int x) -> long {  // piece holding pixel (y, x) of component c
+            if (comp_pieces.empty()) return c;
             auto it = comp_pieces.find(c);
             if (it == comp_pieces.end()) return c;
             for (long pid : it->second) {
@@ -122,22 +129,24 @@ int track_tables(long T, int H, int W, int persistence,
         };
 
         int rc = 0;
+        std::vector<long> moved;                              // heads are ints; extra pieces may exceed int only in theory
         auto do_event = [&](int hi, int lo) {
             const Box3 b = box[hi];
-            std::vector<long> cur;
-            cur.swap(get_members(hi));
-            std::vector<long> stay;
-            std::vector<long> moved;
-            for (long pid : cur) {
+            long pid = head[hi];
+            long prev = -1;
+            moved.clear();
+            while (pid >= 0) {
+                const long next = nxt[pid];
                 Piece tmp;
                 Piece* pp = piece_ref(pid);
                 if (!pp) { tmp = make_piece(pid); pp = &tmp; }
                 Rel rel = classify(*pp, b);
+                bool move_whole = false;
                 if (rel == PARTIAL) {
                     // materialise the row-runs of this piece
                     if (!pp->has_runs) {
                         Piece np_ = make_piece(pid);
-                        if (!fetcher || !fetcher->fetch(pid, np_.runs)) { rc = -1; stay.push_back(pid); continue; }
+                        if (!fetcher || !fetcher->fetch(pid, np_.runs)) { rc = -1; prev = pid; pid = next; continue; }
                         np_.has_runs = true;
                         whole_runs_idx[pid] = (int)whole_runs.size();
                         whole_runs.push_back(std::move(np_));
@@ -160,28 +169,32 @@ int track_tables(long T, int H, int W, int persistence,
                         tight_box(q);
                         pp->runs.swap(out);
                         tight_box(*pp);
-                        long comp = pp->comp;
-                        long qid = ncomp + (long)extra.size();
+                        const long comp = pp->comp;
+                        const long qid = ncomp + (long)extra.size();
                         extra.push_back(std::move(q));        // may invalidate pp
+                        nxt.push_back(-1);
                         std::vector<long>& cp = comp_pieces[comp];
                         if (cp.empty()) cp.push_back(comp);   // the whole-comp id now denotes the remainder
                         cp.push_back(qid);
                         moved.push_back(qid);
-                        stay.push_back(pid);
                         stats.n_splits++;
+                        prev = pid; pid = next;
                         continue;
                     }
                 }
-                if (rel == INSIDE) {
+                if (rel == INSIDE) move_whole = true;
+                if (move_whole) {
                     if (pid >= ncomp) extra[pid - ncomp].value = lo; else value[pid] = lo;
+                    if (prev < 0) head[hi] = (int)next; else nxt[prev] = next;      // unlink
                     moved.push_back(pid);
                 } else {
-                    stay.push_back(pid);
+                    prev = pid;
                 }
+                pid = next;
             }
-            get_members(hi).swap(stay);
-            std::vector<long>& ml = get_members(lo);
-            ml.insert(ml.end(), moved.begin(), moved.end());
+            for (long m : moved) { nxt[m] = head[lo]; head[lo] = (int)m; }
+            // the t-extents of both values are stale now: recomputed after all events
+            tmax[hi] = -2; tmax[lo] = -2;
         };
 
         for (long s = 0; s < nseg && rc == 0; ++s) {
@@ -196,30 +209,25 @@ int track_tables(long T, int H, int W, int persistence,
                 }
                 // With both components unsplit every later row of the segment sees the same two pieces and no other
                 // event intervenes, so re-applying the (idempotent) merge changes nothing.
-                if (comp_pieces.find(a) == comp_pieces.end() && comp_pieces.find(b) == comp_pieces.end()) break;
+                if (comp_pieces.empty() ||
+                    (comp_pieces.find(a) == comp_pieces.end() && comp_pieces.find(b) == comp_pieces.end())) break;
             }
         }
         if (rc != 0) return rc;
+
+        // t-extent of the values touched by events, from their current members
+        for (int v = 1; v <= nlabel; ++v) {
+            if (tmax[v] != -2) continue;
+            int lo = INT_MAX, hi = -1;
+            for (long pid = head[v]; pid >= 0; pid = nxt[pid]) {
+                const int t = pid >= ncomp ? extra[pid - ncomp].t : comp_t[pid];
+                lo = std::min(lo, t); hi = std::max(hi, t);
+            }
+            tmin[v] = lo; tmax[v] = hi;
+        }
     }
 
     // persistence on the merged values (contrack.py:765-772): t-extent of all pixels that carry value v
-    tmin.assign(nlabel + 1, INT_MAX);
-    tmax.assign(nlabel + 1, -1);
-    const bool any_split = !comp_pieces.empty();
-    for (long c = 0; c < ncomp; ++c) {
-        int v = value[c];
-        if (v == 0) continue;
-        if (any_split && comp_pieces.find(c) != comp_pieces.end()) continue;   // split comps: through their pieces
-        tmin[v] = std::min(tmin[v], (int)comp_t[c]); tmax[v] = std::max(tmax[v], (int)comp_t[c]);
-    }
-    for (auto& kv : comp_pieces) {
-        for (long pid : kv.second) {
-            int v, t;
-            if (pid >= ncomp) { v = extra[pid - ncomp].value; t = extra[pid - ncomp].t; }
-            else { v = value[pid]; t = comp_t[pid]; }
-            tmin[v] = std::min(tmin[v], t); tmax[v] = std::max(tmax[v], t);
-        }
-    }
     fin.assign(nlabel + 1, 0);
     for (int v = 1; v <= nlabel; ++v) {
         if (tmax[v] < 0) continue;
@@ -227,7 +235,6 @@ int track_tables(long T, int H, int W, int persistence,
         fin[v] = v;
         stats.n_features++;
     }
-    (void)T;
     for (long c = 0; c < ncomp; ++c) comp_val[c] = fin[value[c]];
     for (auto& kv : comp_pieces) {
         comp_val[kv.first] = 0;

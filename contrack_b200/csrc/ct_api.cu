@@ -87,7 +87,7 @@ struct PinBuf {
 
 struct ct_ctx {
     int device = 0, sm_count = 148;
-    long opt_tma = 0, opt_paint_tma = 0;
+    long opt_tma = 3, opt_paint_tma = 0;      // threshold kernel variant, see ctk::ThresholdArgs::variant
     // geometry of the last run
     long T = 0; int H = 0, W = 0, Ww = 0;
     long nruns = 0, ncomp = 0, npair = 0, nseam = 0, novr = 0;
@@ -113,6 +113,7 @@ struct ct_ctx {
     PinBuf hp_plane;
     int32_t* zero_started_for = nullptr;
     int special_uniform = 0;
+    long opt_paint_runs = 1;                 // sparse paint by runs (1) or by rows (0)
     long opt_gpu_tables = 1;                 // step 3 + 3-D labels on the device (single-GPU path)
     DevBuf l_parent, l_flag, l_rank, l_label, l_kept, l_accE, l_accS, l_accN;     // flag cube whose zero fill is in flight on the side stream
     cudaStream_t side_stream = nullptr;      // zero fill (lowest priority)
@@ -646,7 +647,9 @@ int launch_paint(ct_ctx* c, long t0, long nt, int32_t* flag_dev, int sparse, cud
     a.bits = c->bits.as<uint32_t>() + (size_t)r0 * c->Ww;
     a.row_ptr = c->row_ptr.as<uint32_t>() + r0;
     a.run_val = c->run_val.as<int32_t>();
-    a.nrows = nt * c->H; a.W = c->W; a.Ww = c->Ww; a.flag = flag_dev; a.sparse = sparse;
+    a.nrows = nt * c->H; a.W = c->W; a.Ww = c->Ww; a.flag = flag_dev;
+    a.sparse = sparse ? (c->opt_paint_runs ? 2 : 1) : 0;
+    a.run_x = c->run_x.as<uint32_t>(); a.run_row = c->run_row.as<uint32_t>(); a.row0 = r0;
     CT_CUDA(ctk::paint(a, c->sm_count, st));
     c->launches += 1;
     return CT_OK;
@@ -714,6 +717,7 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "paint_tma")) { c->opt_paint_tma = value; return CT_OK; }
     if (!strcmp(key, "overlap_zero")) { c->opt_overlap_zero = value; return CT_OK; }
     if (!strcmp(key, "gpu_tables")) { c->opt_gpu_tables = value; return CT_OK; }
+    if (!strcmp(key, "paint_runs")) { c->opt_paint_runs = value; return CT_OK; }
     return fail(CT_ERR_ARG, "unknown option '%s'", key);
 }
 

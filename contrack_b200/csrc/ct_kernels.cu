@@ -60,7 +60,7 @@ __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p);
 // 32 compared cells into a mask word that lane (k mod 32) keeps.  Run starts, the row's run count and the two date-line
 // bits are derived once per 32 words from the kept words (lane-parallel), not per word: the inner loop is
 // LDG + FSETP + VOTE + SEL per 32 cells, so the kernel stays bound by HBM rather than by instruction issue.
-template <typename TIn, bool F32CMP, int OP>
+template <typename TIn, bool F32CMP, int OP, int NB>
 __global__ void __launch_bounds__(256) k_threshold(const TIn* __restrict__ anom, long nrows, int H, int W, int Ww,
                                                    const double* __restrict__ thr, long thr_n,
                                                    uint32_t* __restrict__ bits, uint32_t* __restrict__ row_cnt,
@@ -78,20 +78,20 @@ __global__ void __launch_bounds__(256) k_threshold(const TIn* __restrict__ anom,
         for (int k0 = 0; k0 < Ww; k0 += 32) {
             uint32_t myword = 0;
             const int kend = min(32, Ww - k0);
-            for (int j0 = 0; j0 < kend; j0 += 8) {
-                TIn v[8];
-                if (k0 + j0 + 8 <= nfull) {
+            for (int j0 = 0; j0 < kend; j0 += NB) {
+                TIn v[NB];
+                if (k0 + j0 + NB <= nfull) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = ld_stream(a + (k0 + j0 + j) * 32 + lane);
+                    for (int j = 0; j < NB; ++j) v[j] = ld_stream(a + (k0 + j0 + j) * 32 + lane);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < NB; ++j) {
                         const int x = (k0 + j0 + j) * 32 + lane;
                         v[j] = (x < W) ? ld_stream(a + x) : (TIn)NAN;
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < NB; ++j) {
                     const uint32_t m = __ballot_sync(FULL, cmp_thr<TIn, F32CMP, OP>(v[j], thr_f, thr_d));
                     if (lane == j0 + j) myword = m;
                 }
@@ -140,7 +140,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // (lane-contiguous 4-byte reads, conflict free), and re-issues the buffer for the row NS steps ahead.  No load
 // instruction touches global memory, no register staging: NS * 8 rows per SM are in flight.
 template <typename TIn, bool F32CMP, int OP>
-__global__ void __launch_bounds__(256) k_threshold_bulk(const TIn* __restrict__ anom, long nrows, int H, int W, int Ww,
+__global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ anom, long nrows, int H, int W, int Ww,
                                                         const double* __restrict__ thr, long thr_n,
                                                         uint32_t* __restrict__ bits, uint32_t* __restrict__ row_cnt,
                                                         uint32_t* __restrict__ seam_flag, int NS, int stage_bytes) {
@@ -224,8 +224,9 @@ __global__ void __launch_bounds__(256) k_threshold_bulk(const TIn* __restrict__ 
 template <typename TIn, bool F32CMP>
 cudaError_t launch_threshold_bulk(const ThresholdArgs& a, int sm_count, cudaStream_t st) {
     const long nrows = a.T * a.H;
-    const int nw = 8;
     const int stage_bytes = (int)(((size_t)a.W * sizeof(TIn) + 127) / 128 * 128);
+    // variant 3: 16 warps per CTA when two row buffers per warp still fit (more warps to hide the LDS / ballot latency)
+    int nw = (a.variant == 3 && 16 * 2 * stage_bytes <= 199 * 1024) ? 16 : 8;
     int NS = (200 * 1024 - 1024) / (nw * stage_bytes);
     if (NS > 8) NS = 8;
     const size_t smem = ((size_t)nw * NS * 8 + 127) / 128 * 128 + (size_t)nw * NS * stage_bytes;
@@ -262,8 +263,16 @@ template <typename TIn, bool F32CMP>
 cudaError_t launch_threshold(const ThresholdArgs& a, int blocks, cudaStream_t st) {
     const long nrows = a.T * a.H;
 #define CT_LAUNCH_THR(OPV)                                                                                          \
-    k_threshold<TIn, F32CMP, OPV><<<blocks, 256, 0, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww, a.thr_dev,      \
-                                                          a.thr_n, a.bits, a.row_cnt, a.seam_flag)
+    do {                                                                                                            \
+        if (a.variant == 2)                                                                                         \
+            k_threshold<TIn, F32CMP, OPV, 16><<<blocks, 256, 0, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww,     \
+                                                                      a.thr_dev, a.thr_n, a.bits, a.row_cnt,        \
+                                                                      a.seam_flag);                                 \
+        else                                                                                                        \
+            k_threshold<TIn, F32CMP, OPV, 8><<<blocks, 256, 0, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww,      \
+                                                                     a.thr_dev, a.thr_n, a.bits, a.row_cnt,         \
+                                                                     a.seam_flag);                                  \
+    } while (0)
     switch (a.op) {
         case 0: CT_LAUNCH_THR(0); break;
         case 1: CT_LAUNCH_THR(1); break;
@@ -876,6 +885,38 @@ __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits
     }
 }
 
+// Sparse paint by runs (the cube is already zero): a warp takes 32 consecutive runs -- their (x0, x1), row and value come
+// in with coalesced loads -- and writes them one after the other, 32 cells per store instruction.  No bit rows, no
+// dependent gathers.  Runs of removed components (value 0) are skipped.
+__global__ void __launch_bounds__(256) k_paint_runs(const uint32_t* __restrict__ row_ptr, long r0, long nrows,
+                                                    const uint32_t* __restrict__ run_x,
+                                                    const uint32_t* __restrict__ run_row,
+                                                    const int32_t* __restrict__ run_val, int W,
+                                                    int32_t* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const long run_begin = row_ptr[r0], run_end = row_ptr[r0 + nrows];
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long base = run_begin + warp0 * 32; base < run_end; base += nwarps * 32) {
+        const long r = base + lane;
+        int x0 = 0, x1 = 0, v = 0;
+        long dst = 0;
+        if (r < run_end) {
+            const uint32_t x = run_x[r];
+            x0 = x & 0xffff; x1 = x >> 16; v = run_val[r];
+            dst = ((long)run_row[r] - r0) * (long)W;
+        }
+        uint32_t todo = __ballot_sync(FULL, v != 0);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int jx0 = __shfl_sync(FULL, x0, j), jx1 = __shfl_sync(FULL, x1, j), jv = __shfl_sync(FULL, v, j);
+            const long jdst = __shfl_sync(FULL, dst, j);
+            for (int xx = jx0 + lane; xx < jx1; xx += 32) flag[jdst + xx] = jv;
+        }
+    }
+}
+
 __global__ void k_paint_overrides(const int32_t* __restrict__ t, const int32_t* __restrict__ y,
                                   const int32_t* __restrict__ x0, const int32_t* __restrict__ x1,
                                   const int32_t* __restrict__ val, long n, int H, int W, long t_begin, long t_end,
@@ -898,16 +939,20 @@ cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st
     if (nrows == 0) return cudaSuccess;
     long want = (nrows + 7) / 8;
     int blocks = (int)(want < (long)sm_count * 8 ? want : (long)sm_count * 8);
-    if (a.variant == 1) {
+    if (a.variant == 1 || a.variant == 3) {
         if (a.in_dtype == 1 && bulk_ok<double>(a)) return launch_threshold_bulk<double, false>(a, sm_count, st);
         if (a.in_dtype == 0 && bulk_ok<float>(a)) {
             if (a.thr_is_f32) return launch_threshold_bulk<float, true>(a, sm_count, st);
             return launch_threshold_bulk<float, false>(a, sm_count, st);
         }
     }
-    if (a.in_dtype == 1) return launch_threshold<double, false>(a, blocks, st);
-    if (a.thr_is_f32) return launch_threshold<float, true>(a, blocks, st);
-    return launch_threshold<float, false>(a, blocks, st);
+    // no bulk staging possible (row bytes not a multiple of 16, or rows too long for shared memory): deep plain loads
+    ThresholdArgs b = a;
+    if (b.variant == 1) b.variant = 0;
+    if (b.variant == 3) b.variant = 2;
+    if (b.in_dtype == 1) return launch_threshold<double, false>(b, blocks, st);
+    if (b.thr_is_f32) return launch_threshold<float, true>(b, blocks, st);
+    return launch_threshold<float, false>(b, blocks, st);
 }
 
 cudaError_t row_stats(const uint32_t* bits, long nrows, int W, int Ww, uint32_t* row_cnt, uint32_t* seam_flag,
@@ -1024,7 +1069,10 @@ cudaError_t paint(const PaintArgs& a, int sm_count, cudaStream_t st) {
     long want = (a.nrows + 7) / 8;
     int blocks = (int)(want < (long)sm_count * 8 ? want : (long)sm_count * 8);
     const bool vec = (a.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.flag) & 15) == 0);
-    if (a.sparse) {
+    if (a.sparse == 2) {
+        k_paint_runs<<<sm_count * 8, 256, 0, st>>>(a.row_ptr - a.row0, a.row0, a.nrows, a.run_x, a.run_row, a.run_val, a.W,
+                                                   a.flag);
+    } else if (a.sparse) {
         if (vec) k_paint<true, true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
         else k_paint<false, true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
     } else {

@@ -16,7 +16,8 @@ struct ThresholdArgs {
     uint32_t* bits;                          // [T*H*Ww] out
     uint32_t* row_cnt;                       // [T*H] out: row-runs per row
     uint32_t* seam_flag;                     // [T*H] out: 1 if the pixels at x=0 and x=W-1 are both set
-    int variant;                             // 0: 4-byte loads + ballot; 1: cp.async.bulk row staging (needs W % 4 == 0)
+    int variant;                             // 0 / 2: 4-byte loads + ballot, 8 / 16 loads in flight per lane;
+                                             // 1 / 3: cp.async.bulk row staging, 8 / 16 warps per CTA (needs W % 4 == 0)
 };
 cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st);
 
@@ -113,7 +114,9 @@ struct PaintArgs {
     const uint32_t* bits; const uint32_t* row_ptr; const int32_t* run_val;
     long nrows; int W, Ww;
     int32_t* flag;                           // [nrows * W] out
-    int sparse;                              // 1: `flag` is already zero, write only the cells of row-runs
+    int sparse;                              // 0: dense; `flag` already zero: 1 = row-wise, cells of runs only; 2 = by runs
+    const uint32_t* run_x; const uint32_t* run_row;   // sparse == 2
+    long row0;                               // first row painted (row_ptr points at it)
 };
 cudaError_t paint(const PaintArgs& a, int sm_count, cudaStream_t st);
 // sub-runs of planes [t_begin, t_end) only; `flag` starts at plane t_begin

@@ -201,7 +201,7 @@ def test_bulk_copy_threshold_variant(eng, fixture_cube, golden):
         f, _ = gpu_run(eng, xd, la2, lo2, 40.0, '<', 0.3, 2, True)
         assert np.array_equal(f, ref)
     finally:
-        eng.set_option('tma', 0)
+        eng.set_option('tma', 3)
 
 
 def test_dense_paint_path(eng, fixture_cube, golden):
@@ -244,3 +244,29 @@ def test_host_table_path_matches_device_table_path(eng, golden):
         eng.set_option('gpu_tables', 1)
     f, _ = gpu_run(eng, x, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
     assert sha_i4(f) == r['sha256'] and eng.stats()['sweeps'] >= 1
+
+
+@pytest.mark.parametrize('opts', [{'tma': 0}, {'tma': 2}, {'tma': 1}, {'paint_runs': 0}, {'overlap_zero': 0, 'tma': 3},
+                                  {'gpu_tables': 0, 'paint_runs': 0}])
+def test_kernel_variants_give_identical_results(eng, fixture_cube, golden, opts):
+    """Every selectable kernel variant (load depth, bulk-copy staging with 16 warps, row-wise sparse paint, dense paint,
+    host table phase) must produce the same bytes."""
+    a, lat, lon = fixture_cube
+    defaults = {'tma': 3, 'paint_runs': 1, 'overlap_zero': 1, 'gpu_tables': 1}
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    try:
+        for r in golden['fixture'][:2]:
+            f, _ = gpu_run(eng, a, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
+            assert sha_i4(f) == r['sha256'], (opts, r['key'])
+        x = synth_cube(3, 6, 721, 1440, (2.0, 12, 20))
+        la = np.linspace(90, -90, 721).astype(np.float32)
+        lo = (np.arange(1440) * 0.25).astype(np.float32)
+        ref = oracle.run_contrack(x, la, lo, 150, '>=', 0.5, 2, True, force=True)
+        w = oracle.weight_grid(la, oracle.resolution(la, True), oracle.resolution(lo, True), 1440)[:, 0].copy()
+        import torch
+        f, n = eng.run_contrack(torch.from_numpy(x).cuda(), w, 150, True, 0, 0.5, 2, True)
+        assert np.array_equal(f.cpu().numpy(), ref), opts
+    finally:
+        for k in opts:
+            eng.set_option(k, defaults[k])

@@ -115,7 +115,9 @@ struct ct_ctx {
     int special_uniform = 0;
     long opt_paint_runs = 1;                 // sparse paint by runs (1) or by rows (0)
     long opt_gpu_tables = 1;                 // step 3 + 3-D labels on the device (single-GPU path)
-    DevBuf l_parent, l_flag, l_rank, l_label, l_kept, l_accE, l_accS, l_accN;     // flag cube whose zero fill is in flight on the side stream
+    DevBuf l_parent, l_flag, l_rank, l_label, l_kept, l_accE, l_accS, l_accN;
+    DevBuf b_t0, b_t1, b_y0, b_y1, b_x0, b_x1, b_cnt, b_fill, b_ptr, b_order, b_fin, b_mc, b_ml;
+    PinBuf hp_labels;     // flag cube whose zero fill is in flight on the side stream
     cudaStream_t side_stream = nullptr;      // zero fill (lowest priority)
     cudaStream_t tbl_stream = nullptr;       // table phase (highest priority): must get onto the SMs between fill blocks
     cudaEvent_t ev_tbl[2] = {nullptr, nullptr};
@@ -129,6 +131,8 @@ struct ct_ctx {
 };
 
 namespace {
+
+inline int W_of(const ct_ctx* c) { return c->W; }
 
 struct DeviceRunSource : cth::RunSource {
     ct_ctx* c;
@@ -515,7 +519,8 @@ int gpu_step3_link(ct_ctx* c, double overlap, int twosided, long* nflag_out, lon
                         c->scan_tmp.as<uint32_t>(), c->l_label.as<int32_t>(), st));
     c->launches += 7;
     CT_CUDA(cudaMemcpyAsync(cnt_host + 6, c->l_rank.as<uint32_t>() + nc, 4, cudaMemcpyDeviceToHost, st));
-    *nlabels_out = -1;                                               // valid after the caller's next synchronize: cnt_host[6]
+    CT_CUDA(cudaStreamSynchronize(st));
+    *nlabels_out = nc ? cnt_host[6] : 0;
     return CT_OK;
 }
 
@@ -524,7 +529,8 @@ int upload_values(ct_ctx* c, const int32_t* comp_val_pinned, const std::vector<c
     const long nc = c->ncomp, R = c->nruns;
     const long novr = (long)overrides.size();
     c->novr = novr;
-    if (nc) CT_CUDA(cudaMemcpyAsync(c->c_val.p, comp_val_pinned, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+    if (nc && comp_val_pinned)                                   // nullptr: c_val was already computed on the device
+        CT_CUDA(cudaMemcpyAsync(c->c_val.p, comp_val_pinned, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
     if (novr) {
         CT_CUDA(c->hp_ovr.ensure((size_t)novr * 5 * 4));
         int32_t* ho = c->hp_ovr.as<int32_t>();
@@ -559,6 +565,99 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
         long nflag = 0, nlab = 0;
         if ((rc0 = gpu_step3_link(c, overlap, twosided, &nflag, &nlab, st)) != CT_OK) return rc0;
         c->stats["neartie_flagged"] = (double)nflag;
+        if (nflag == 0 && stage == CT_STAGE_FINAL) {
+            // ---- steps 4c/4d: per-label boxes and member lists on the device; the host replays only the date-line events
+            // that join two different labels and applies the persistence rule per label ----
+            const size_t lb = (size_t)(nlab + 4) * 4;
+            DevBuf* lbufs[] = {&c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
+                               &c->b_fin};
+            for (DevBuf* b : lbufs) CT_CUDA(b->ensure(lb));
+            CT_CUDA(c->b_order.ensure((size_t)(nc + 1) * 4));
+            ctk::LabelDev ld;
+            ld.t0 = c->b_t0.as<int32_t>(); ld.t1 = c->b_t1.as<int32_t>(); ld.y0 = c->b_y0.as<int32_t>();
+            ld.y1 = c->b_y1.as<int32_t>(); ld.x0 = c->b_x0.as<int32_t>(); ld.x1 = c->b_x1.as<int32_t>();
+            ld.cnt = c->b_cnt.as<uint32_t>(); ld.fill = c->b_fill.as<uint32_t>(); ld.ptr = c->b_ptr.as<uint32_t>();
+            ld.order = c->b_order.as<uint32_t>();
+            ctk::CompTables ctd;
+            ctd.t = c->c_t.as<int32_t>(); ctd.y0 = c->c_y0.as<int32_t>(); ctd.y1 = c->c_y1.as<int32_t>();
+            ctd.x0 = c->c_x0.as<int32_t>(); ctd.x1 = c->c_x1.as<int32_t>(); ctd.areaE = nullptr; ctd.areaS = nullptr;
+            ctd.nsp = nullptr; ctd.cls = nullptr;
+            CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(nlab + 2) * 4));
+            CT_CUDA(ctk::label_tables(ctd, c->l_label.as<int32_t>(), nc, ld, nlab, c->scan_tmp.as<uint32_t>(), st));
+            c->launches += 6;
+            CT_CUDA(cudaEventRecord(c->ev[2], st));
+            const size_t nl1 = (size_t)nlab + 2;
+            CT_CUDA(c->hp_labels.ensure((nl1 * 7 + (size_t)nc * 2 + 16) * 4));
+            int32_t* hl = c->hp_labels.as<int32_t>();
+            int32_t *h_t0 = hl, *h_t1 = hl + nl1, *h_y0 = hl + 2 * nl1, *h_y1 = hl + 3 * nl1, *h_x0 = hl + 4 * nl1,
+                    *h_x1 = hl + 5 * nl1;
+            uint32_t* h_lptr = reinterpret_cast<uint32_t*>(hl + 6 * nl1);
+            uint32_t* h_lorder = reinterpret_cast<uint32_t*>(hl + 7 * nl1);
+            int32_t* hlabel = hl + 7 * nl1 + nc + 1;
+            const size_t lbytes = (size_t)(nlab + 1) * 4;
+            CT_CUDA(cudaMemcpyAsync(h_t0, ld.t0, lbytes, cudaMemcpyDeviceToHost, st));
+            CT_CUDA(cudaMemcpyAsync(h_t1, ld.t1, lbytes, cudaMemcpyDeviceToHost, st));
+            CT_CUDA(cudaMemcpyAsync(h_y0, ld.y0, lbytes, cudaMemcpyDeviceToHost, st));
+            CT_CUDA(cudaMemcpyAsync(h_y1, ld.y1, lbytes, cudaMemcpyDeviceToHost, st));
+            CT_CUDA(cudaMemcpyAsync(h_x0, ld.x0, lbytes, cudaMemcpyDeviceToHost, st));
+            CT_CUDA(cudaMemcpyAsync(h_x1, ld.x1, lbytes, cudaMemcpyDeviceToHost, st));
+            CT_CUDA(cudaMemcpyAsync(h_lptr, ld.ptr, lbytes + 4, cudaMemcpyDeviceToHost, st));
+            if (nc) {
+                CT_CUDA(cudaMemcpyAsync(h_lorder, ld.order, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
+                CT_CUDA(cudaMemcpyAsync(hlabel, c->l_label.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
+            }
+            if ((rc0 = tables_d2h(c, 0, st)) != CT_OK) return rc0;      // component boxes + segments; synchronizes
+            const double t_host0 = now_ms();
+            cth::Result& res = c->host_result;
+            res.n_neartie = 0; res.n_labels3d = nlab; res.n_kept = h_lptr[nlab + 1];
+            static thread_local std::vector<int32_t> sa32, sb32, fin, mc, ml;
+            sa32.resize(tb.nseg); sb32.resize(tb.nseg);
+            for (long i = 0; i < tb.nseg; ++i) { sa32[i] = (int32_t)tb.seg_a[i]; sb32[i] = (int32_t)tb.seg_b[i]; }
+            ctb::LabelTables lt;
+            lt.nlabel = (int)nlab; lt.t0 = h_t0; lt.t1 = h_t1; lt.y0 = h_y0; lt.y1 = h_y1; lt.x0 = h_x0; lt.x1 = h_x1;
+            lt.lptr = h_lptr; lt.lorder = h_lorder;
+            DeviceRunSource src;
+            src.c = c; src.st = st;
+            struct Fetch : ctb::RunFetcher {
+                cth::RunSource* src; const int32_t* comp_t; std::vector<cth::PlaneRun> buf;
+                bool fetch(long comp, std::vector<ctb::SubRun>& out) override {
+                    if (!src->plane_runs(comp_t[comp], buf)) return false;
+                    out.clear();
+                    for (const cth::PlaneRun& r : buf) if ((long)r.comp == comp) out.push_back(ctb::SubRun{r.y, r.x0, r.x1});
+                    return !out.empty();
+                }
+            } fetcher;
+            fetcher.src = &src; fetcher.comp_t = tb.comp_t;
+            ctb::TrackStats tstats;
+            int rc = ctb::track_tables_sparse(W_of(c), persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0,
+                                              tb.comp_x1, hlabel, lt, tb.nseg, tb.seg_y0, tb.seg_y1, sa32.data(),
+                                              sb32.data(), &fetcher, fin, mc, ml, res.overrides, tstats);
+            if (rc != 0) return fail(CT_ERR_INTERNAL, "date-line merge could not fetch the runs of a component to split");
+            res.n_features = tstats.n_features; res.n_seam_events = tstats.n_events; res.n_seam_splits = tstats.n_splits;
+            c->stats["ms_host_tables"] = now_ms() - t_host0;
+            // surviving value per label + the re-labelled components -> value per component on the device
+            const long nm = (long)mc.size();
+            CT_CUDA(c->hp_val.ensure(((size_t)nlab + 2 + 2 * (size_t)nm + 8) * 4));
+            int32_t* hv = c->hp_val.as<int32_t>();
+            memcpy(hv, fin.data(), (size_t)(nlab + 1) * 4);
+            if (nm) { memcpy(hv + nlab + 1, mc.data(), (size_t)nm * 4); memcpy(hv + nlab + 1 + nm, ml.data(), (size_t)nm * 4); }
+            CT_CUDA(c->b_mc.ensure((size_t)(nm + 1) * 4)); CT_CUDA(c->b_ml.ensure((size_t)(nm + 1) * 4));
+            CT_CUDA(cudaMemcpyAsync(c->b_fin.p, hv, (size_t)(nlab + 1) * 4, cudaMemcpyHostToDevice, st));
+            if (nm) {
+                CT_CUDA(cudaMemcpyAsync(c->b_mc.p, hv + nlab + 1, (size_t)nm * 4, cudaMemcpyHostToDevice, st));
+                CT_CUDA(cudaMemcpyAsync(c->b_ml.p, hv + nlab + 1 + nm, (size_t)nm * 4, cudaMemcpyHostToDevice, st));
+            }
+            CT_CUDA(ctk::final_values(c->l_label.as<int32_t>(), c->b_fin.as<int32_t>(), nc, c->b_mc.as<int32_t>(),
+                                      c->b_ml.as<int32_t>(), nm, c->c_val.as<int32_t>(), st));
+            c->launches += nm ? 2 : 1;
+            if ((rc = upload_values(c, nullptr, res.overrides, st)) != CT_OK) return rc;
+            c->stats["kept_comps"] = (double)res.n_kept;
+            c->stats["labels3d"] = (double)res.n_labels3d; c->stats["features"] = (double)res.n_features;
+            c->stats["seam_events"] = (double)res.n_seam_events; c->stats["seam_splits"] = (double)res.n_seam_splits;
+            c->stats["neartie_resolved"] = 0.0; c->stats["moved_comps"] = (double)nm;
+            if (n_features) *n_features = res.n_features;
+            return CT_OK;
+        }
         if (nflag == 0) {
             CT_CUDA(cudaEventRecord(c->ev[2], st));
             CT_CUDA(c->hp_val.ensure((size_t)(nc + 1) * 8 + (size_t)nc + 64));
@@ -582,12 +681,6 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
                 for (long i = 0; i < nc; ++i) hv[i] = hkept[tb.comp_cls[i]] ? (int32_t)(tb.comp_cls[i] + 1) : 0;
             } else if (stage == CT_STAGE_LABEL3D) {
                 if (nc) memcpy(hv, hlabel, (size_t)nc * 4);
-            } else {
-                DeviceRunSource src;
-                src.c = c; src.st = st;
-                std::string err;
-                int rc = cth::track_phase(tb, hlabel, persistence, &src, hv, res, err);
-                if (rc != 0) return fail(rc, "%s", err.c_str());
             }
             c->stats["ms_host_tables"] = now_ms() - t_host0;
             int rc = upload_values(c, hv, res.overrides, st);
@@ -698,9 +791,11 @@ void ct_destroy(ct_ctx* c) {
                       &c->o_t, &c->o_y, &c->o_x0, &c->o_x1, &c->o_val, &c->w_dev, &c->special_dev, &c->thr_dev,
                       &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0], &c->chunk_out[1],
                       &c->a_gptr, &c->a_gidx, &c->a_gmean, &c->a_group,
-                      &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN};
+                      &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN,
+                      &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
+                      &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml};
     for (DevBuf* b : bufs) b->release();
-    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release();
+    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     for (auto& e : c->ev_tbl) if (e) cudaEventDestroy(e);

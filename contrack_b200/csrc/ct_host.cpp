@@ -3,6 +3,7 @@
 #include "ct_host.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -266,9 +267,43 @@ int track_phase(const FastTables& tb, const int32_t* label, int persistence, Run
     SplitFetcher fetcher;
     fetcher.pc = &pc; fetcher.comp_t = tb.comp_t;
     ctb::TrackStats stats;
-    int rc = ctb::track_tables(tb.T, tb.H, tb.W, persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0,
+    int rc;
+    if (getenv("CT_TRACK_SPARSE")) {
+        // test hook: reduce the per-label tables here (the device does it in the product path) and run the sparse variant
+        int nlabel = 0;
+        for (long c = 0; c < nc; ++c) nlabel = std::max(nlabel, (int)label[c]);
+        std::vector<int32_t> t0(nlabel + 1, INT32_MAX), t1(nlabel + 1, 0), y0(nlabel + 1, INT32_MAX), y1(nlabel + 1, 0),
+            x0(nlabel + 1, INT32_MAX), x1(nlabel + 1, 0);
+        std::vector<uint32_t> lptr(nlabel + 2, 0), lorder(nc);
+        for (long c = 0; c < nc; ++c) {
+            const int v = label[c];
+            if (!v) continue;
+            t0[v] = std::min(t0[v], tb.comp_t[c]); t1[v] = std::max(t1[v], tb.comp_t[c] + 1);
+            y0[v] = std::min(y0[v], tb.comp_y0[c]); y1[v] = std::max(y1[v], tb.comp_y1[c]);
+            x0[v] = std::min(x0[v], tb.comp_x0[c]); x1[v] = std::max(x1[v], tb.comp_x1[c]);
+            lptr[v + 1]++;
+        }
+        for (int v = 0; v <= nlabel; ++v) lptr[v + 1] += lptr[v];
+        {
+            std::vector<uint32_t> pos(lptr.begin(), lptr.end() - 1);
+            for (long c = nc - 1; c >= 0; --c) if (label[c]) lorder[pos[label[c]]++] = (uint32_t)c;   // any order will do
+        }
+        ctb::LabelTables lt;
+        lt.nlabel = nlabel; lt.t0 = t0.data(); lt.t1 = t1.data(); lt.y0 = y0.data(); lt.y1 = y1.data();
+        lt.x0 = x0.data(); lt.x1 = x1.data(); lt.lptr = lptr.data(); lt.lorder = lorder.data();
+        std::vector<int32_t> fin, mc, ml;
+        rc = ctb::track_tables_sparse(tb.W, persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0, tb.comp_x1,
+                                      label, lt, tb.nseg, tb.seg_y0, tb.seg_y1, seg_a32.data(), seg_b32.data(),
+                                      runs ? &fetcher : nullptr, fin, mc, ml, out.overrides, stats);
+        if (rc == 0) {
+            for (long c = 0; c < nc; ++c) comp_val[c] = fin[label[c]];
+            for (size_t i = 0; i < mc.size(); ++i) comp_val[mc[i]] = fin[ml[i]];
+        }
+    } else {
+        rc = ctb::track_tables(tb.T, tb.H, tb.W, persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0,
                                tb.comp_x1, label, tb.nseg, tb.seg_t, tb.seg_y0, tb.seg_y1, seg_a32.data(),
                                seg_b32.data(), runs ? &fetcher : nullptr, comp_val, out.overrides, stats);
+    }
     if (rc != 0) { err = "date-line merge needs to split a component and no run source is available"; return -5; }
     out.n_features = stats.n_features; out.n_seam_events = stats.n_events; out.n_seam_splits = stats.n_splits;
     return 0;

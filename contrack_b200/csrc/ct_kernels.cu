@@ -778,6 +778,47 @@ __global__ void __launch_bounds__(256) k_link_labels(Step3Tables t, long ncomp, 
     label[c] = t.kept[t.cls[c]] ? (int32_t)(rank[uf_find(parent, (uint32_t)c)] + 1u) : 0;
 }
 
+// per-label tables for steps 4c/4d: 3-D box of every label, number of member components, members grouped by label
+__global__ void __launch_bounds__(256) k_label_init(LabelDev l, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    l.t0[i] = INT_MAX; l.t1[i] = 0; l.y0[i] = INT_MAX; l.y1[i] = 0; l.x0[i] = INT_MAX; l.x1[i] = 0;
+    l.cnt[i] = 0; l.fill[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_label_reduce(CompTables c, const int32_t* __restrict__ label, long ncomp,
+                                                      LabelDev l) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncomp) return;
+    const int v = label[i];
+    if (v == 0) return;
+    atomicMin(&l.t0[v], c.t[i]); atomicMax(&l.t1[v], c.t[i] + 1);
+    atomicMin(&l.y0[v], c.y0[i]); atomicMax(&l.y1[v], c.y1[i]);
+    atomicMin(&l.x0[v], c.x0[i]); atomicMax(&l.x1[v], c.x1[i]);
+    atomicAdd(&l.cnt[v], 1u);
+}
+
+__global__ void __launch_bounds__(256) k_label_fill(const int32_t* __restrict__ label, long ncomp, LabelDev l) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncomp) return;
+    const int v = label[i];
+    if (v == 0) return;
+    l.order[l.ptr[v] + atomicAdd(&l.fill[v], 1u)] = (uint32_t)i;
+}
+
+// value painted for a component = surviving value of its label; then the few re-labelled components
+__global__ void __launch_bounds__(256) k_final_values(const int32_t* __restrict__ label, const int32_t* __restrict__ fin,
+                                                      long ncomp, int32_t* __restrict__ val) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncomp) val[i] = fin[label[i]];
+}
+
+__global__ void k_apply_moves(const int32_t* __restrict__ comp, const int32_t* __restrict__ newlabel,
+                              const int32_t* __restrict__ fin, long n, int32_t* __restrict__ val) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) val[comp[i]] = fin[newlabel[i]];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // paint: bit rows + value per run -> int32 cube.  One warp per row, 1024 cells (32 mask words) per pass; a lane owns
 // four consecutive cells and stores them as one 16-byte streaming store.
@@ -1152,6 +1193,24 @@ cudaError_t link3d(const Step3Tables& t, long ncomp, uint32_t* parent, uint32_t*
     cudaError_t e = exclusive_scan_u32(root_flag, rank, ncomp, scan_tmp, st);
     if (e != cudaSuccess) return e;
     k_link_labels<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, parent, rank, label);
+    return cudaGetLastError();
+}
+
+cudaError_t label_tables(const CompTables& c, const int32_t* label, long ncomp, const LabelDev& l, long nlabel,
+                         uint32_t* scan_tmp, cudaStream_t st) {
+    // entries 0 .. nlabel (label 0 = removed, stays empty); ptr gets nlabel + 2 entries
+    k_label_init<<<blocks_for(nlabel + 1, 256), 256, 0, st>>>(l, nlabel + 1);
+    if (ncomp) k_label_reduce<<<blocks_for(ncomp, 256), 256, 0, st>>>(c, label, ncomp, l);
+    cudaError_t e = exclusive_scan_u32(l.cnt, l.ptr, nlabel + 1, scan_tmp, st);
+    if (e != cudaSuccess) return e;
+    if (ncomp) k_label_fill<<<blocks_for(ncomp, 256), 256, 0, st>>>(label, ncomp, l);
+    return cudaGetLastError();
+}
+
+cudaError_t final_values(const int32_t* label, const int32_t* fin, long ncomp, const int32_t* move_comp,
+                         const int32_t* move_label, long nmoves, int32_t* val, cudaStream_t st) {
+    if (ncomp) k_final_values<<<blocks_for(ncomp, 256), 256, 0, st>>>(label, fin, ncomp, val);
+    if (nmoves) k_apply_moves<<<blocks_for(nmoves, 256), 256, 0, st>>>(move_comp, move_label, fin, nmoves, val);
     return cudaGetLastError();
 }
 

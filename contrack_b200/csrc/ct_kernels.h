@@ -106,6 +106,17 @@ cudaError_t step3_sweep(const Step3Tables& t, long ncomp, long T, double overlap
 cudaError_t link3d(const Step3Tables& t, long ncomp, uint32_t* parent, uint32_t* root_flag, uint32_t* rank,
                    uint32_t* scan_tmp, int32_t* label, cudaStream_t st);
 
+// ---- per-label tables (boxes, member lists) and the final value per component ----
+struct LabelDev {
+    int32_t *t0, *t1, *y0, *y1, *x0, *x1;    // [nlabel + 1] half-open 3-D box of every label
+    uint32_t *cnt, *fill, *ptr, *order;      // cnt/fill [nlabel + 1], ptr [nlabel + 2], order [ncomp]
+};
+cudaError_t label_tables(const CompTables& c, const int32_t* label, long ncomp, const LabelDev& l, long nlabel,
+                         uint32_t* scan_tmp, cudaStream_t st);
+// val[c] = fin[label[c]], then val[move_comp[i]] = fin[move_label[i]]
+cudaError_t final_values(const int32_t* label, const int32_t* fin, long ncomp, const int32_t* move_comp,
+                         const int32_t* move_label, long nmoves, int32_t* val, cudaStream_t st);
+
 // run_val[r] = comp_val[run_comp[r]]
 cudaError_t run_values(const uint32_t* run_comp, const int32_t* comp_val, int32_t* run_val, long nruns,
                        cudaStream_t st);

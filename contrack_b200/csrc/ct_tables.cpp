@@ -248,6 +248,172 @@ int track_tables(long T, int H, int W, int persistence,
     return 0;
 }
 
+int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_t, const int32_t* comp_y0,
+                        const int32_t* comp_y1, const int32_t* comp_x0, const int32_t* comp_x1,
+                        const int32_t* comp_label, const LabelTables& lt,
+                        long nseg, const int32_t* seg_y0, const int32_t* seg_y1, const int32_t* seg_a,
+                        const int32_t* seg_b, RunFetcher* fetcher, std::vector<int32_t>& fin,
+                        std::vector<int32_t>& move_comp, std::vector<int32_t>& move_label,
+                        std::vector<Override>& overrides, TrackStats& stats) {
+    overrides.clear(); move_comp.clear(); move_label.clear();
+    stats = TrackStats();
+    const int nlabel = lt.nlabel;
+    std::unordered_map<long, int> moved_value;               // current value of the (few) re-labelled whole components
+    std::unordered_map<int, std::vector<long>> members;      // member pieces of the labels an event touched
+    std::vector<Piece> extra;                                // pieces created by splits (index ncomp + k)
+    std::vector<Piece> whole_runs;
+    std::unordered_map<long, int> whole_runs_idx;
+    std::unordered_map<long, std::vector<long>> comp_pieces;
+
+    static thread_local std::vector<uint8_t> moved_flag_tls;  // 1 for components listed in moved_value
+    std::vector<uint8_t>& moved_flag = moved_flag_tls;
+    moved_flag.assign(ncomp, 0);
+    auto value_of = [&](long c) -> int {
+        if (!moved_flag[c]) return comp_label[c];
+        return moved_value.find(c)->second;
+    };
+    auto make_piece = [&](long c) {
+        Piece p;
+        p.comp = c; p.t = comp_t[c]; p.y0 = comp_y0[c]; p.y1 = comp_y1[c]; p.x0 = comp_x0[c]; p.x1 = comp_x1[c];
+        p.value = value_of(c); p.has_runs = false;
+        return p;
+    };
+    auto get_members = [&](int v) -> std::vector<long>& {
+        auto it = members.find(v);
+        if (it != members.end()) return it->second;
+        std::vector<long>& m = members[v];
+        m.reserve(lt.lptr[v + 1] - lt.lptr[v]);
+        for (uint32_t k = lt.lptr[v]; k < lt.lptr[v + 1]; ++k) m.push_back((long)lt.lorder[k]);
+        return m;
+    };
+    auto piece_ref = [&](long pid) -> Piece* {
+        if (pid >= ncomp) return &extra[pid - ncomp];
+        auto it = whole_runs_idx.find(pid);
+        return it == whole_runs_idx.end() ? nullptr : &whole_runs[it->second];
+    };
+    auto piece_value = [&](long pid) -> int { return pid >= ncomp ? extra[pid - ncomp].value : value_of(pid); };
+    auto piece_of = [&](long c, int y, int x) -> long {
+        if (comp_pieces.empty()) return c;
+        auto it = comp_pieces.find(c);
+        if (it == comp_pieces.end()) return c;
+        for (long pid : it->second) {
+            const Piece* p = piece_ref(pid);
+            for (const SubRun& r : p->runs)
+                if (r.y == y && r.x0 <= x && x < r.x1) return pid;
+        }
+        return c;
+    };
+
+    int rc = 0;
+    auto do_event = [&](int hi, int lo) {
+        const Box3 b{lt.t0[hi], lt.t1[hi], lt.y0[hi], lt.y1[hi], lt.x0[hi], lt.x1[hi]};
+        std::vector<long> cur;
+        cur.swap(get_members(hi));
+        std::vector<long> stay, moved;
+        for (long pid : cur) {
+            Piece tmp;
+            Piece* pp = piece_ref(pid);
+            if (!pp) { tmp = make_piece(pid); pp = &tmp; }
+            Rel rel = classify(*pp, b);
+            if (rel == PARTIAL) {
+                if (!pp->has_runs) {
+                    Piece np_ = make_piece(pid);
+                    if (!fetcher || !fetcher->fetch(pid, np_.runs)) { rc = -1; stay.push_back(pid); continue; }
+                    np_.has_runs = true;
+                    whole_runs_idx[pid] = (int)whole_runs.size();
+                    whole_runs.push_back(std::move(np_));
+                    pp = &whole_runs.back();
+                }
+                std::vector<SubRun> in, out;
+                for (const SubRun& r : pp->runs) {
+                    if (r.y < b.y0 || r.y >= b.y1 || r.x1 <= b.x0 || r.x0 >= b.x1) { out.push_back(r); continue; }
+                    int a = std::max(r.x0, b.x0), e = std::min(r.x1, b.x1);
+                    if (r.x0 < a) out.push_back(SubRun{r.y, r.x0, a});
+                    in.push_back(SubRun{r.y, a, e});
+                    if (e < r.x1) out.push_back(SubRun{r.y, e, r.x1});
+                }
+                if (in.empty()) rel = OUTSIDE;
+                else if (out.empty()) rel = INSIDE;
+                else {
+                    Piece q;
+                    q.comp = pp->comp; q.t = pp->t; q.value = lo; q.has_runs = true; q.runs.swap(in);
+                    tight_box(q);
+                    pp->runs.swap(out);
+                    tight_box(*pp);
+                    const long comp = pp->comp;
+                    const long qid = ncomp + (long)extra.size();
+                    extra.push_back(std::move(q));
+                    std::vector<long>& cp = comp_pieces[comp];
+                    if (cp.empty()) cp.push_back(comp);
+                    cp.push_back(qid);
+                    moved.push_back(qid);
+                    stay.push_back(pid);
+                    stats.n_splits++;
+                    continue;
+                }
+            }
+            if (rel == INSIDE) {
+                if (pid >= ncomp) extra[pid - ncomp].value = lo; else { moved_value[pid] = lo; moved_flag[pid] = 1; }
+                if (Piece* w = (pid < ncomp ? piece_ref(pid) : nullptr)) w->value = lo;
+                moved.push_back(pid);
+            } else {
+                stay.push_back(pid);
+            }
+        }
+        get_members(hi).swap(stay);
+        std::vector<long>& ml = get_members(lo);
+        ml.insert(ml.end(), moved.begin(), moved.end());
+    };
+
+    for (long s = 0; s < nseg && rc == 0; ++s) {
+        const long a = seg_a[s], b = seg_b[s];
+        if (comp_label[a] == 0 || comp_label[b] == 0) continue;
+        if (comp_label[a] == comp_label[b] && members.empty()) continue;     // same label and nothing moved yet
+        for (int y = seg_y0[s]; y < seg_y1[s]; ++y) {
+            long pa = piece_of(a, y, 0), pb = piece_of(b, y, W - 1);
+            int va = piece_value(pa), vb = piece_value(pb);
+            if (va != vb) {
+                do_event(std::max(va, vb), std::min(va, vb));
+                stats.n_events++;
+            }
+            if (comp_pieces.empty() ||
+                (comp_pieces.find(a) == comp_pieces.end() && comp_pieces.find(b) == comp_pieces.end())) break;
+        }
+    }
+    if (rc != 0) return rc;
+
+    // persistence (contrack.py:765-772): untouched labels keep the t-extent of their box, touched ones are re-measured
+    fin.assign(nlabel + 1, 0);
+    for (int v = 1; v <= nlabel; ++v) {
+        const int lo = lt.t0[v], hi = lt.t1[v] - 1;
+        if (hi >= lo && (hi + 1 - lo) >= persistence) { fin[v] = v; stats.n_features++; }
+    }
+    for (auto& kv : members) {                               // labels an event touched: re-measure from their members
+        const int v = kv.first;
+        if (fin[v]) { fin[v] = 0; stats.n_features--; }
+        int lo = INT_MAX, hi = -1;
+        for (long pid : kv.second) {
+            const int t = pid >= ncomp ? extra[pid - ncomp].t : comp_t[pid];
+            lo = std::min(lo, t); hi = std::max(hi, t);
+        }
+        if (hi >= lo && hi >= 0 && (hi + 1 - lo) >= persistence) { fin[v] = v; stats.n_features++; }
+    }
+    for (auto& kv : moved_value) { move_comp.push_back((int32_t)kv.first); move_label.push_back(kv.second); }
+    for (auto& kv : comp_pieces) {
+        // a split component is painted piece by piece: its own value becomes 0
+        bool listed = false;
+        for (size_t i = 0; i < move_comp.size(); ++i) if (move_comp[i] == kv.first) { move_label[i] = 0; listed = true; }
+        if (!listed) { move_comp.push_back((int32_t)kv.first); move_label.push_back(0); }
+        for (long pid : kv.second) {
+            const Piece* p = pid >= ncomp ? &extra[pid - ncomp] : &whole_runs[whole_runs_idx[pid]];
+            const int v = fin[pid >= ncomp ? p->value : value_of(pid)];
+            if (v == 0) continue;
+            for (const SubRun& r : p->runs) overrides.push_back(Override{p->t, r.y, r.x0, r.x1, v});
+        }
+    }
+    return 0;
+}
+
 // ---- numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src: @TYPE@_pairwise_sum, PW_BLOCKSIZE 128) ----
 static double pairwise(const double* a, long n) {
     if (n < 8) {

@@ -31,6 +31,25 @@ int track_tables(long T, int H, int W, int persistence,
                  const int32_t* seg_a, const int32_t* seg_b,
                  RunFetcher* fetcher, int32_t* comp_val, std::vector<Override>& overrides, TrackStats& stats);
 
+// Same two steps when the per-label tables were already reduced elsewhere (on the device): 3-D boxes of the labels
+// (lt0..lx1, half-open, index = label), components grouped by label (lptr / lorder) and the segments.  Only labels that a
+// date-line event touches are visited.  Outputs: fin[label] = surviving value of every label (0 = removed by the
+// persistence filter), `moves` = (component, new label) for the components an event re-labelled (a split component gets
+// label 0 and its pieces come back as overrides).
+struct LabelTables {
+    int nlabel = 0;
+    const int32_t *t0 = nullptr, *t1 = nullptr, *y0 = nullptr, *y1 = nullptr, *x0 = nullptr, *x1 = nullptr;   // [nlabel+1]
+    const uint32_t* lptr = nullptr;      // [nlabel+2]: components of label v are lorder[lptr[v] .. lptr[v+1])
+    const uint32_t* lorder = nullptr;
+};
+int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_t, const int32_t* comp_y0,
+                        const int32_t* comp_y1, const int32_t* comp_x0, const int32_t* comp_x1,
+                        const int32_t* comp_label, const LabelTables& lt,
+                        long nseg, const int32_t* seg_y0, const int32_t* seg_y1, const int32_t* seg_a,
+                        const int32_t* seg_b, RunFetcher* fetcher, std::vector<int32_t>& fin,
+                        std::vector<int32_t>& move_comp, std::vector<int32_t>& move_label,
+                        std::vector<Override>& overrides, TrackStats& stats);
+
 // np.sum order on a contiguous float64 vector: 0 + pairwise(a, n) with 128-element blocks and 8 accumulators.
 double numpy_pairwise_sum(const double* a, long n);
 

@@ -130,7 +130,11 @@ int track_tables(long T, int H, int W, int persistence,
 
         int rc = 0;
         std::vector<long> moved;                              // heads are ints; extra pieces may exceed int only in theory
+        // after an event on `hi` all of its remaining members lie outside box[hi]: a repeat cannot move anything until new
+        // members arrive
+        std::vector<uint8_t> settled(nlabel + 1, 0);
         auto do_event = [&](int hi, int lo) {
+            if (settled[hi]) return;
             const Box3 b = box[hi];
             long pid = head[hi];
             long prev = -1;
@@ -193,6 +197,8 @@ int track_tables(long T, int H, int W, int persistence,
                 pid = next;
             }
             for (long m : moved) { nxt[m] = head[lo]; head[lo] = (int)m; }
+            settled[hi] = 1;
+            if (!moved.empty()) settled[lo] = 0;
             // the t-extents of both values are stale now: recomputed after all events
             tmax[hi] = -2; tmax[lo] = -2;
         };
@@ -258,40 +264,53 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
     overrides.clear(); move_comp.clear(); move_label.clear();
     stats = TrackStats();
     const int nlabel = lt.nlabel;
-    std::unordered_map<long, int> moved_value;               // current value of the (few) re-labelled whole components
-    std::unordered_map<int, std::vector<long>> members;      // member pieces of the labels an event touched
+
+    // Dense per-component / per-label state in buffers that live across calls; member lists are intrusive linked lists
+    // (head per value, next per piece) built from the device's grouping only for the labels an event touches.
+    struct Workspace {
+        std::vector<int> value, head, touched;
+        std::vector<long> nxt, log;
+        std::vector<uint8_t> built, settled;
+    };
+    static thread_local Workspace tls_ws;
+    Workspace& ws = tls_ws;
+    std::vector<int>&value = ws.value, &head = ws.head, &touched = ws.touched;
+    std::vector<long>&nxt = ws.nxt, &log = ws.log;
+    std::vector<uint8_t>&built = ws.built, &settled = ws.settled;
+    value.assign(comp_label, comp_label + ncomp);
+    head.assign(nlabel + 1, -1);
+    built.assign(nlabel + 1, 0);
+    settled.assign(nlabel + 1, 0);
+    nxt.resize(ncomp);
+    touched.clear(); log.clear();
+
     std::vector<Piece> extra;                                // pieces created by splits (index ncomp + k)
     std::vector<Piece> whole_runs;
     std::unordered_map<long, int> whole_runs_idx;
     std::unordered_map<long, std::vector<long>> comp_pieces;
 
-    static thread_local std::vector<uint8_t> moved_flag_tls;  // 1 for components listed in moved_value
-    std::vector<uint8_t>& moved_flag = moved_flag_tls;
-    moved_flag.assign(ncomp, 0);
-    auto value_of = [&](long c) -> int {
-        if (!moved_flag[c]) return comp_label[c];
-        return moved_value.find(c)->second;
-    };
     auto make_piece = [&](long c) {
         Piece p;
         p.comp = c; p.t = comp_t[c]; p.y0 = comp_y0[c]; p.y1 = comp_y1[c]; p.x0 = comp_x0[c]; p.x1 = comp_x1[c];
-        p.value = value_of(c); p.has_runs = false;
+        p.value = value[c]; p.has_runs = false;
         return p;
     };
-    auto get_members = [&](int v) -> std::vector<long>& {
-        auto it = members.find(v);
-        if (it != members.end()) return it->second;
-        std::vector<long>& m = members[v];
-        m.reserve(lt.lptr[v + 1] - lt.lptr[v]);
-        for (uint32_t k = lt.lptr[v]; k < lt.lptr[v + 1]; ++k) m.push_back((long)lt.lorder[k]);
-        return m;
+    auto ensure_built = [&](int v) {
+        if (built[v]) return;
+        built[v] = 1;
+        touched.push_back(v);
+        for (uint32_t k = lt.lptr[v]; k < lt.lptr[v + 1]; ++k) {
+            const long c = (long)lt.lorder[k];
+            nxt[c] = head[v]; head[v] = (int)c;
+        }
     };
     auto piece_ref = [&](long pid) -> Piece* {
         if (pid >= ncomp) return &extra[pid - ncomp];
+        if (whole_runs_idx.empty()) return nullptr;
         auto it = whole_runs_idx.find(pid);
         return it == whole_runs_idx.end() ? nullptr : &whole_runs[it->second];
     };
-    auto piece_value = [&](long pid) -> int { return pid >= ncomp ? extra[pid - ncomp].value : value_of(pid); };
+    auto piece_value = [&](long pid) -> int { return pid >= ncomp ? extra[pid - ncomp].value : value[pid]; };
     auto piece_of = [&](long c, int y, int x) -> long {
         if (comp_pieces.empty()) return c;
         auto it = comp_pieces.find(c);
@@ -305,20 +324,33 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
     };
 
     int rc = 0;
+    std::vector<long> moved;
+    // After an event on `hi` every member that is left lies outside box[hi]: until new members arrive (hi being the `lo`
+    // of another event) a repeated event on hi cannot move anything.
     auto do_event = [&](int hi, int lo) {
+        if (settled[hi]) return;
+        ensure_built(hi); ensure_built(lo);
         const Box3 b{lt.t0[hi], lt.t1[hi], lt.y0[hi], lt.y1[hi], lt.x0[hi], lt.x1[hi]};
-        std::vector<long> cur;
-        cur.swap(get_members(hi));
-        std::vector<long> stay, moved;
-        for (long pid : cur) {
-            Piece tmp;
+        long pid = head[hi], prev = -1;
+        moved.clear();
+        while (pid >= 0) {
+            const long next = nxt[pid];
+            Rel rel;
             Piece* pp = piece_ref(pid);
-            if (!pp) { tmp = make_piece(pid); pp = &tmp; }
-            Rel rel = classify(*pp, b);
+            if (!pp) {
+                // whole component, runs not materialised: classify on its box without building a Piece
+                const int t = comp_t[pid];
+                if (t < b.t0 || t >= b.t1) rel = OUTSIDE;
+                else if (comp_y0[pid] >= b.y0 && comp_y1[pid] <= b.y1 && comp_x0[pid] >= b.x0 && comp_x1[pid] <= b.x1) rel = INSIDE;
+                else if (comp_y1[pid] <= b.y0 || comp_y0[pid] >= b.y1 || comp_x1[pid] <= b.x0 || comp_x0[pid] >= b.x1) rel = OUTSIDE;
+                else rel = PARTIAL;
+            } else {
+                rel = classify(*pp, b);
+            }
             if (rel == PARTIAL) {
-                if (!pp->has_runs) {
+                if (!pp || !pp->has_runs) {
                     Piece np_ = make_piece(pid);
-                    if (!fetcher || !fetcher->fetch(pid, np_.runs)) { rc = -1; stay.push_back(pid); continue; }
+                    if (!fetcher || !fetcher->fetch(pid, np_.runs)) { rc = -1; prev = pid; pid = next; continue; }
                     np_.has_runs = true;
                     whole_runs_idx[pid] = (int)whole_runs.size();
                     whole_runs.push_back(std::move(np_));
@@ -343,32 +375,34 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
                     const long comp = pp->comp;
                     const long qid = ncomp + (long)extra.size();
                     extra.push_back(std::move(q));
+                    nxt.push_back(-1);
                     std::vector<long>& cp = comp_pieces[comp];
                     if (cp.empty()) cp.push_back(comp);
                     cp.push_back(qid);
                     moved.push_back(qid);
-                    stay.push_back(pid);
                     stats.n_splits++;
+                    prev = pid; pid = next;
                     continue;
                 }
             }
             if (rel == INSIDE) {
-                if (pid >= ncomp) extra[pid - ncomp].value = lo; else { moved_value[pid] = lo; moved_flag[pid] = 1; }
-                if (Piece* w = (pid < ncomp ? piece_ref(pid) : nullptr)) w->value = lo;
+                if (pid >= ncomp) extra[pid - ncomp].value = lo;
+                else { value[pid] = lo; log.push_back(pid); if (Piece* w = piece_ref(pid)) w->value = lo; }
+                if (prev < 0) head[hi] = (int)next; else nxt[prev] = next;      // unlink
                 moved.push_back(pid);
             } else {
-                stay.push_back(pid);
+                prev = pid;
             }
+            pid = next;
         }
-        get_members(hi).swap(stay);
-        std::vector<long>& ml = get_members(lo);
-        ml.insert(ml.end(), moved.begin(), moved.end());
+        for (long m : moved) { nxt[m] = head[lo]; head[lo] = (int)m; }
+        settled[hi] = 1;
+        if (!moved.empty()) settled[lo] = 0;
     };
 
     for (long s = 0; s < nseg && rc == 0; ++s) {
         const long a = seg_a[s], b = seg_b[s];
         if (comp_label[a] == 0 || comp_label[b] == 0) continue;
-        if (comp_label[a] == comp_label[b] && members.empty()) continue;     // same label and nothing moved yet
         for (int y = seg_y0[s]; y < seg_y1[s]; ++y) {
             long pa = piece_of(a, y, 0), pb = piece_of(b, y, W - 1);
             int va = piece_value(pa), vb = piece_value(pb);
@@ -388,25 +422,27 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
         const int lo = lt.t0[v], hi = lt.t1[v] - 1;
         if (hi >= lo && (hi + 1 - lo) >= persistence) { fin[v] = v; stats.n_features++; }
     }
-    for (auto& kv : members) {                               // labels an event touched: re-measure from their members
-        const int v = kv.first;
+    for (int v : touched) {
         if (fin[v]) { fin[v] = 0; stats.n_features--; }
         int lo = INT_MAX, hi = -1;
-        for (long pid : kv.second) {
+        for (long pid = head[v]; pid >= 0; pid = nxt[pid]) {
             const int t = pid >= ncomp ? extra[pid - ncomp].t : comp_t[pid];
             lo = std::min(lo, t); hi = std::max(hi, t);
         }
         if (hi >= lo && hi >= 0 && (hi + 1 - lo) >= persistence) { fin[v] = v; stats.n_features++; }
     }
-    for (auto& kv : moved_value) { move_comp.push_back((int32_t)kv.first); move_label.push_back(kv.second); }
+    std::sort(log.begin(), log.end());
+    log.erase(std::unique(log.begin(), log.end()), log.end());
+    for (long c : log)
+        if (value[c] != comp_label[c] && comp_pieces.find(c) == comp_pieces.end()) {
+            move_comp.push_back((int32_t)c); move_label.push_back(value[c]);
+        }
     for (auto& kv : comp_pieces) {
         // a split component is painted piece by piece: its own value becomes 0
-        bool listed = false;
-        for (size_t i = 0; i < move_comp.size(); ++i) if (move_comp[i] == kv.first) { move_label[i] = 0; listed = true; }
-        if (!listed) { move_comp.push_back((int32_t)kv.first); move_label.push_back(0); }
+        move_comp.push_back((int32_t)kv.first); move_label.push_back(0);
         for (long pid : kv.second) {
             const Piece* p = pid >= ncomp ? &extra[pid - ncomp] : &whole_runs[whole_runs_idx[pid]];
-            const int v = fin[pid >= ncomp ? p->value : value_of(pid)];
+            const int v = fin[pid >= ncomp ? p->value : value[pid]];
             if (v == 0) continue;
             for (const SubRun& r : p->runs) overrides.push_back(Override{p->t, r.y, r.x0, r.x1, v});
         }

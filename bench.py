@@ -341,9 +341,12 @@ def main():
             dt = time.perf_counter() - t0
             s = eng.stats()
             extra = {'ms_h2d_threshold': s.get('ms_h2d_threshold'), 'ms_tables': s.get('ms_tables'),
-                     'ms_paint_d2h': s.get('ms_paint_d2h'),
-                     'note': 'ct_run_contrack_host: pinned host float32 cube in, int32 flag cube out, chunked copies '
-                             'overlapped with the kernels; wall clock around the call'}
+                     'ms_paint_d2h': s.get('ms_paint_d2h'), 'host_threads': int(s.get('host_threads', 0)),
+                     'note': 'ct_run_contrack_host: pinned host float32 cube in (chunked copies overlapped with the '
+                             'threshold kernel), int32 flag cube out on the host; the result crosses PCIe as the row-run '
+                             'table (12 B per run) and host threads expand it into the zero-filled host cube; wall clock '
+                             'around the call'}
+            d2h = int(s.get('d2h_bytes', Te * H * W * 4))
         else:
             # every rank holds its shard of a Te-step cube in pinned host memory; per step: H2D of the shard, the sharded
             # run, D2H of the shard's flag planes
@@ -374,8 +377,9 @@ def main():
             dt = float(t_dt.item())
             extra = {'note': 'per rank: pinned host shard -> device, sharded run, flag shard -> pinned host; wall clock, '
                              'max over ranks'}
+            d2h = Te * H * W * 4
         line['e2e'] = dict({'value': Te * n_e2e / dt, 'unit': 'timesteps/s', 'h2d_bytes_per_step': Te * H * W * 4,
-                            'd2h_bytes_per_step': Te * H * W * 4, 'T': Te, 'steps': n_e2e, 'features': int(nf)}, **extra)
+                            'd2h_bytes_per_step': d2h, 'T': Te, 'steps': n_e2e, 'features': int(nf)}, **extra)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

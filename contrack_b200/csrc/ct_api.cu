@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ct_host.h"
@@ -115,6 +116,9 @@ struct ct_ctx {
     int special_uniform = 0;
     long opt_paint_runs = 1;                 // sparse paint by runs (1) or by rows (0)
     long opt_gpu_tables = 1;                 // step 3 + 3-D labels on the device (single-GPU path)
+    long opt_host_sparse = 1;                // host-buffer call: flag travels back as row-runs, not as a dense cube
+    long opt_host_threads = 0;               // host threads that zero / paint the host flag cube (0 = automatic)
+    PinBuf hp_runs;                          // row-run table of the last host-buffer call
     DevBuf l_parent, l_flag, l_rank, l_label, l_kept, l_accE, l_accS, l_accN;
     DevBuf b_t0, b_t1, b_y0, b_y1, b_x0, b_x1, b_cnt, b_fill, b_ptr, b_order, b_fin, b_mc, b_ml;
     PinBuf hp_labels;     // flag cube whose zero fill is in flight on the side stream
@@ -795,7 +799,7 @@ void ct_destroy(ct_ctx* c) {
                       &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
                       &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml};
     for (DevBuf* b : bufs) b->release();
-    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release();
+    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     for (auto& e : c->ev_tbl) if (e) cudaEventDestroy(e);
@@ -813,6 +817,8 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "overlap_zero")) { c->opt_overlap_zero = value; return CT_OK; }
     if (!strcmp(key, "gpu_tables")) { c->opt_gpu_tables = value; return CT_OK; }
     if (!strcmp(key, "paint_runs")) { c->opt_paint_runs = value; return CT_OK; }
+    if (!strcmp(key, "host_sparse")) { c->opt_host_sparse = value; return CT_OK; }
+    if (!strcmp(key, "host_threads")) { c->opt_host_threads = value; return CT_OK; }
     return fail(CT_ERR_ARG, "unknown option '%s'", key);
 }
 
@@ -909,6 +915,28 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
         CT_CUDA(c->chunk_in[i].ensure((size_t)chunk_planes * plane * esz));
     }
     const double t0_ms = now_ms();
+    // The flag cube is ~96 % zeros on fields like Z500 anomalies and PCIe is the bound of this entry point: instead of a
+    // dense cube (4 B/cell) the result travels back as the row-run table (12 B per run, ~1 % of the dense bytes) and host
+    // threads expand it into `flag_host`, which they zero-fill while the input chunks are still streaming in.
+    const size_t cells = (size_t)T * plane;
+    int nthreads = (int)c->opt_host_threads;
+    if (nthreads <= 0) {
+        const unsigned hc = std::thread::hardware_concurrency();
+        nthreads = hc >= 16 ? 8 : (hc >= 4 ? (int)hc / 2 : 1);
+    }
+    const bool want_sparse = c->opt_host_sparse != 0;
+    std::vector<std::thread> zero_threads;
+    if (want_sparse) {
+        const size_t per = ((cells + nthreads - 1) / nthreads + 1023) / 1024 * 1024;
+        for (int i = 0; i < nthreads; ++i) {
+            const size_t b = std::min(cells, per * i), e = std::min(cells, per * (i + 1));
+            if (e > b) zero_threads.emplace_back([=] { memset(flag_host + b, 0, (e - b) * sizeof(int32_t)); });
+        }
+    }
+    struct Joiner {
+        std::vector<std::thread>& v;
+        ~Joiner() { for (auto& t : v) if (t.joinable()) t.join(); }
+    } joiner{zero_threads};
     // ---- stream the cube in: copy chunk k+1 while chunk k is thresholded; the float cube is never resident ----
     for (long k = 0; k < nchunks; ++k) {
         const int s = (int)(k & 1);
@@ -926,39 +954,85 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
     if ((rc = table_phase(c, overlap, persistence, twosided, CT_STAGE_FINAL, n_features, ws)) != CT_OK) return rc;
     CT_CUDA(cudaStreamSynchronize(ws));
     const double t2_ms = now_ms();
-    // ---- paint chunk k+1 while chunk k travels back ----
-    const long out_planes = std::max(1L, std::min(T, (long)((256u << 20) / (plane * 4))));
-    const long nout = (T + out_planes - 1) / out_planes;
-    cudaEvent_t out_ready[2], out_free[2];
-    for (int i = 0; i < 2; ++i) {
-        CT_CUDA(cudaEventCreateWithFlags(&out_ready[i], cudaEventDisableTiming));
-        CT_CUDA(cudaEventCreateWithFlags(&out_free[i], cudaEventDisableTiming));
-        CT_CUDA(c->chunk_out[i].ensure((size_t)out_planes * plane * 4));
-    }
-    for (long k = 0; k < nout; ++k) {
-        const int s = (int)(k & 1);
-        const long t0 = k * out_planes, nt = (t0 + out_planes <= T) ? out_planes : T - t0;
-        if (k >= 2) CT_CUDA(cudaStreamWaitEvent(ws, out_free[s], 0));
-        int32_t* dst = c->chunk_out[s].as<int32_t>();
-        if ((rc = launch_paint(c, t0, nt, dst, 0, ws)) != CT_OK) return rc;
-        if (c->novr) {
-            CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
-                                         c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), c->novr, H, W, t0, t0 + nt,
-                                         dst, ws));
-            c->launches += 1;
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(in_ready[i]); cudaEventDestroy(in_free[i]); }
+    const long R = c->nruns;
+    size_t d2h_bytes = 0;
+    if (want_sparse && (size_t)R * 12 <= cells * 2) {
+        // ---- row-runs (x0|x1<<16, row, value) -> pinned host memory -> host threads paint the non-zero runs ----
+        CT_CUDA(c->hp_runs.ensure((size_t)(R + 1) * 12));
+        uint32_t* h_x = c->hp_runs.as<uint32_t>();
+        uint32_t* h_row = h_x + R;
+        int32_t* h_val = reinterpret_cast<int32_t*>(h_row + R);
+        if (R) {
+            CT_CUDA(cudaMemcpyAsync(h_x, c->run_x.p, (size_t)R * 4, cudaMemcpyDeviceToHost, ws));
+            CT_CUDA(cudaMemcpyAsync(h_row, c->run_row.p, (size_t)R * 4, cudaMemcpyDeviceToHost, ws));
+            CT_CUDA(cudaMemcpyAsync(h_val, c->run_val.p, (size_t)R * 4, cudaMemcpyDeviceToHost, ws));
         }
-        CT_CUDA(cudaEventRecord(out_ready[s], ws));
-        CT_CUDA(cudaStreamWaitEvent(cs, out_ready[s], 0));
-        CT_CUDA(cudaMemcpyAsync(flag_host + (size_t)t0 * plane, dst, (size_t)nt * plane * 4, cudaMemcpyDeviceToHost, cs));
-        CT_CUDA(cudaEventRecord(out_free[s], cs));
+        for (auto& t : zero_threads) t.join();                    // (normally long finished)
+        zero_threads.clear();
+        CT_CUDA(cudaStreamSynchronize(ws));
+        d2h_bytes = (size_t)R * 12;
+        const int np = (int)std::max(1L, std::min((long)nthreads, R / 4096 + 1));
+        std::vector<std::thread> painters;
+        const long per = (R + np - 1) / np;
+        for (int i = 0; i < np; ++i) {
+            const long b = std::min(R, per * i), e = std::min(R, per * (i + 1));
+            if (e <= b) continue;
+            painters.emplace_back([=] {
+                for (long r = b; r < e; ++r) {
+                    const int32_t v = h_val[r];
+                    if (v == 0) continue;
+                    const uint32_t x = h_x[r];
+                    int32_t* out = flag_host + (size_t)h_row[r] * W;
+                    for (uint32_t xx = x & 0xffff, x1 = x >> 16; xx < x1; ++xx) out[xx] = v;
+                }
+            });
+        }
+        for (auto& t : painters) t.join();
+        for (const ctb::Override& o : c->host_result.overrides) {  // pieces of components split at a stale box
+            int32_t* out = flag_host + ((size_t)o.t * H + o.y) * W;
+            for (int xx = o.x0; xx < o.x1; ++xx) out[xx] = o.val;
+        }
+        c->stats["host_sparse"] = 1.0;
+        c->stats["host_threads"] = (double)nthreads;
+    } else {
+        for (auto& t : zero_threads) t.join();
+        zero_threads.clear();
+        // ---- dense: paint chunk k+1 while chunk k travels back ----
+        const long out_planes = std::max(1L, std::min(T, (long)((256u << 20) / (plane * 4))));
+        const long nout = (T + out_planes - 1) / out_planes;
+        cudaEvent_t out_ready[2], out_free[2];
+        for (int i = 0; i < 2; ++i) {
+            CT_CUDA(cudaEventCreateWithFlags(&out_ready[i], cudaEventDisableTiming));
+            CT_CUDA(cudaEventCreateWithFlags(&out_free[i], cudaEventDisableTiming));
+            CT_CUDA(c->chunk_out[i].ensure((size_t)out_planes * plane * 4));
+        }
+        for (long k = 0; k < nout; ++k) {
+            const int s = (int)(k & 1);
+            const long t0 = k * out_planes, nt = (t0 + out_planes <= T) ? out_planes : T - t0;
+            if (k >= 2) CT_CUDA(cudaStreamWaitEvent(ws, out_free[s], 0));
+            int32_t* dst = c->chunk_out[s].as<int32_t>();
+            if ((rc = launch_paint(c, t0, nt, dst, 0, ws)) != CT_OK) return rc;
+            if (c->novr) {
+                CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
+                                             c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), c->novr, H, W, t0, t0 + nt,
+                                             dst, ws));
+                c->launches += 1;
+            }
+            CT_CUDA(cudaEventRecord(out_ready[s], ws));
+            CT_CUDA(cudaStreamWaitEvent(cs, out_ready[s], 0));
+            CT_CUDA(cudaMemcpyAsync(flag_host + (size_t)t0 * plane, dst, (size_t)nt * plane * 4, cudaMemcpyDeviceToHost, cs));
+            CT_CUDA(cudaEventRecord(out_free[s], cs));
+        }
+        CT_CUDA(cudaStreamSynchronize(cs));
+        CT_CUDA(cudaStreamSynchronize(ws));
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(out_ready[i]); cudaEventDestroy(out_free[i]); }
+        d2h_bytes = cells * 4;
+        c->stats["host_sparse"] = 0.0;
     }
-    CT_CUDA(cudaStreamSynchronize(cs));
-    CT_CUDA(cudaStreamSynchronize(ws));
     const double t3_ms = now_ms();
-    for (int i = 0; i < 2; ++i) {
-        cudaEventDestroy(in_ready[i]); cudaEventDestroy(in_free[i]);
-        cudaEventDestroy(out_ready[i]); cudaEventDestroy(out_free[i]);
-    }
+    c->stats["h2d_bytes"] = (double)(cells * esz);
+    c->stats["d2h_bytes"] = (double)d2h_bytes;
     c->stats["ms_h2d_threshold"] = t1_ms - t0_ms;
     c->stats["ms_tables"] = t2_ms - t1_ms;
     c->stats["ms_paint_d2h"] = t3_ms - t2_ms;

@@ -15,7 +15,8 @@ from ._lib import ContrackLibError
 _STAT_KEYS = ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d', 'features', 'seam_events',
               'seam_splits', 'neartie_resolved', 'override_runs', 'special_rows', 'kernel_launches', 'ms_threshold',
               'ms_tables_gpu', 'ms_tables_host_roundtrip', 'ms_host_tables', 'ms_paint', 'ms_total', 'ms_h2d_threshold',
-              'ms_tables', 'ms_paint_d2h', 'ms_zero_fill', 'seam_segments', 'sweeps', 'neartie_flagged')
+              'ms_tables', 'ms_paint_d2h', 'ms_zero_fill', 'seam_segments', 'sweeps', 'neartie_flagged', 'h2d_bytes',
+              'd2h_bytes', 'host_sparse', 'host_threads')
 
 
 def _is_torch(x):

@@ -52,8 +52,14 @@ const char* ct_last_error(void);
 /* One context per GPU; owns all scratch (bit planes, run tables, component tables). */
 int ct_create(int device, ct_ctx** out);
 void ct_destroy(ct_ctx* ctx);
-/* Runtime switches: key "tma" (1 = cp.async.bulk staged threshold kernel, 0 = plain coalesced loads),
- * "paint_tma" (bulk-store paint kernel).  Returns CT_ERR_ARG for unknown keys. */
+/* Runtime switches (defaults in brackets).  Returns CT_ERR_ARG for unknown keys.
+ *   "tma"          threshold kernel: 3 [default] / 1 = rows staged by cp.async.bulk (16 / 8 warps per CTA),
+ *                  0 / 2 = plain coalesced loads (8 / 16 in flight per lane)
+ *   "overlap_zero" [1] zero fill of the flag cube on a side stream under the table phase + sparse paint; 0 = dense paint
+ *   "paint_runs"   [1] sparse paint by row-runs; 0 = by bit rows
+ *   "gpu_tables"   [1] steps 3 / 4a / 4b on the device; 0 = the whole ordered phase on the host (what a sharded run uses)
+ *   "host_sparse"  [1] ct_run_contrack_host returns the result as row-runs expanded by host threads; 0 = dense copy
+ *   "host_threads" [0 = automatic] host threads used by ct_run_contrack_host */
 int ct_set_option(ct_ctx* ctx, const char* key, long value);
 
 /* ---- run_contrack, contrack.py:646-772 -------------------------------------------------------------------------
@@ -71,9 +77,13 @@ int ct_run_contrack(ct_ctx* ctx, const void* anom_dev, int in_dtype, long T, int
                     double overlap, int persistence, int twosided,
                     int32_t* flag_dev, long* n_features, int stage, void* stream);
 
-/* Same call with HOST buffers: streams time chunks host->device (threshold kernel consumes them; the float cube is
- * never resident), runs the table phases, then paints and streams flag chunks device->host.  `chunk_planes` <= 0
- * picks a default.  Host buffers should be page-locked for full PCIe rate (the call works with pageable memory). */
+/* Same call with HOST buffers: streams time chunks host->device (the threshold kernel consumes them; the float cube is
+ * never resident) and runs the table phases.  PCIe is the bound of this call, so the result does not travel back as a
+ * dense cube: host threads zero `flag_host` while the input streams in, the row-run table (x0|x1<<16, row, value: 12 B
+ * per run, ~1 % of the dense bytes on Z500-like fields) is copied device->host and the threads expand the runs of the
+ * surviving features into `flag_host` ("host_sparse" = 0, or a run table larger than half the cube, selects the dense
+ * paint + copy instead).  `chunk_planes` <= 0 picks a default.  Host buffers should be page-locked for full PCIe rate
+ * (the call works with pageable memory).  Stats "h2d_bytes" / "d2h_bytes" report what crossed PCIe. */
 int ct_run_contrack_host(ct_ctx* ctx, const void* anom_host, int in_dtype, long T, int H, int W,
                          const double* w_host, const double* thr_host, long thr_n, int thr_is_f32, int op,
                          double overlap, int persistence, int twosided,

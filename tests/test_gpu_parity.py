@@ -161,6 +161,39 @@ def test_host_buffers_match_device(eng):
     assert n == len(np.unique(ref)) - 1
 
 
+@pytest.mark.parametrize('sparse,threads', [(1, 0), (1, 1), (1, 3), (0, 0)])
+def test_host_buffer_result_formats(eng, sparse, threads):
+    """Host-buffer entry point: the flag cube crosses PCIe either as the row-run table that host threads expand
+    (host_sparse=1, any thread count) or as the dense cube (host_sparse=0); bytes must be identical, including the pieces
+    of components that the stale-box date-line merge splits (overrides), and the result buffer may hold garbage on entry."""
+    eng.set_option('host_sparse', sparse)
+    eng.set_option('host_threads', threads)
+    try:
+        x = synth_cube(9, 17, 181, 360, (1.5, 4, 6))
+        lat, lon = regular_grid(181, 360)
+        ref = oracle.run_contrack(x, lat, lon, 120, '>=', 0.3, 3, True)
+        out = np.full(x.shape, -7, np.int32)
+        f, n = eng.run_contrack(x, row_weights(lat, lon), 120, True, 0, 0.3, 3, True, out=out, chunk_planes=4)
+        assert f is out and np.array_equal(out, ref) and n == len(np.unique(ref)) - 1
+        st = eng.stats()
+        assert st['host_sparse'] == sparse and st['h2d_bytes'] == x.nbytes
+        assert st['d2h_bytes'] == (12 * st['runs'] if sparse else ref.size * 4)
+        la, lo = regular_grid(24, 16)
+        for seed in [1396, 1933]:
+            xs = synth_cube(seed, 12, 24, 16, (1.5, 2, 2))
+            out = np.full(xs.shape, 99, np.int32)
+            eng.run_contrack(xs, row_weights(la, lo), 60, True, 0, 0.0, 1, False, out=out)
+            assert eng.stats()['seam_splits'] > 0
+            assert np.array_equal(out, oracle.track_persistence((xs >= 60).astype(int), 1)), seed
+        z = np.zeros((3, 8, 8), np.float32)                       # no runs at all
+        out = np.full(z.shape, 5, np.int32)
+        eng.run_contrack(z, np.ones(8), 1.0, True, 0, 0.5, 1, True, out=out)
+        assert not out.any()
+    finally:
+        eng.set_option('host_sparse', 1)
+        eng.set_option('host_threads', 0)
+
+
 def test_pole_rows_are_special(eng, fixture_cube):
     a, lat, lon = fixture_cube
     gpu_run(eng, a, lat, lon, 150, '>=', .5, 5, True)

@@ -123,6 +123,17 @@ def measured_peak():
         return 6650.0, 'fallback'
 
 
+def ncu_traffic(kernel, cells):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/summarise_ncu.py), scaled from the captured launch to `cells` cells."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            d = json.load(f)
+        return d['kernels'][kernel]['bytes_per_cell'] * cells, d['source']
+    except Exception:
+        return None, None
+
+
 def cpu_reference_run(x, lat, lon):
     """The reference algorithm on the host (oracle restatement: same scipy.ndimage calls, same Python loops)."""
     from oracle import contrack_oracle as oracle
@@ -275,7 +286,17 @@ def main():
     dom = ('threshold_bits', thr_ms) if thr_ms >= paint_ms else ('paint', paint_ms)
     achieved = cells * 4 / (dom[1] / 1e3) / 1e9
     path_gbs = T * H * W * 8 / (ms / args.steps / 1e3) / 1e9
-
+    traffic, traffic_src = ncu_traffic(dom[0], cells)
+    # the same kernel timed alone (no table kernels beside it): two extra, untimed-for-`value` steps without the pipeline
+    iso = None
+    if world == 1:
+        eng.set_option('chunks', 1)
+        t_iso = []
+        for _ in range(2):
+            step()
+            t_iso.append(eng.stats()['ms_threshold'])
+        eng.set_option('chunks', 4)
+        iso = cells * 4 / (min(t_iso) / 1e3) / 1e9
     line = {'metric': 'timesteps/sec (721x1440 grid) run_contrack', 'value': value, 'unit': 'timesteps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
@@ -284,10 +305,15 @@ def main():
             'features': int(nfeat), 'gpu_launches': int(stats['kernel_launches']) * args.steps * world,
             'clocks': clocks.summary(),
             'roofline': {'bound': 'hbm', 'kernel': dom[0], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': None,
+                         'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': traffic,
+                         'traffic_note': 'DRAM read+write bytes per cell of this kernel in %s x %d cells' % (traffic_src, cells),
                          'algorithmic_bytes_per_launch': cells * 4,
-                         'note': '4 B/cell (float32 read for threshold_bits, int32 write for paint) x %d cells per '
-                                 'launch (rank 0) / CUDA-event time of that kernel' % cells},
+                         'note': '4 B/cell (float32 read for threshold_bits, int32 write for paint) x %d cells (rank 0) / '
+                                 'CUDA-event time of that kernel inside the timed steps, where the table kernels of the '
+                                 'previous time chunk run beside it (the cube is thresholded in %d chunk launches; '
+                                 'the time is first launch start -> last launch end)' % (cells, int(stats.get('chunks', 1))),
+                         'achieved_alone': iso, 'frac_alone': iso / peak if iso else None,
+                         'note_alone': 'same kernel as one launch with nothing beside it (option chunks=1), CUDA events'},
             'roofline_path': {'achieved': path_gbs, 'frac': path_gbs / (peak * world), 'unit': 'GB/s',
                               'note': '8 B/cell (read anomaly once + write flag once) x all cells / whole step time; '
                                       'frac against %d x the per-GPU peak' % world},

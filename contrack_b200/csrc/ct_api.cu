@@ -65,6 +65,24 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // grow to at least `bytes`, preserving the first `keep` bytes (copied on `st`); `hint` = expected final size
+    cudaError_t grow(size_t bytes, size_t keep, cudaStream_t st, size_t hint = 0) {
+        if (bytes <= cap) return cudaSuccess;
+        if (!p || keep == 0) {
+            cudaError_t e = ensure(hint > bytes ? hint : bytes);
+            return e == cudaSuccess ? e : ensure(bytes);
+        }
+        size_t want = std::max(bytes + bytes / 4 + 256, hint);
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&q, want); }
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(q, p, std::min(keep, cap), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(p);
+        p = q; cap = want;
+        return e;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
@@ -116,6 +134,10 @@ struct ct_ctx {
     int special_uniform = 0;
     long opt_paint_runs = 1;                 // sparse paint by runs (1) or by rows (0)
     long opt_gpu_tables = 1;                 // step 3 + 3-D labels on the device (single-GPU path)
+    long opt_chunks = 4;                     // time chunks of the pipelined run (tables of chunk k under threshold k+1)
+    long opt_chunk_min_planes = 128;         // ... but never fewer planes per chunk than this
+    long tb_planes = 0, tb_runs = 0, tb_comps = 0, tb_seams = 0, tb_segs = 0, tb_pairs = 0;   // tables built so far
+    std::vector<cudaEvent_t> ev_chunk;
     long opt_host_sparse = 1;                // host-buffer call: flag travels back as row-runs, not as a dense cube
     long opt_host_threads = 0;               // host threads that zero / paint the host flag cube (0 = automatic)
     PinBuf hp_runs;                          // row-run table of the last host-buffer call
@@ -282,51 +304,61 @@ int launch_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long t0, lon
     return CT_OK;
 }
 
-// GPU half of the table phase: bit rows -> runs -> components -> tables (left on the device).
-int tables_build(ct_ctx* c, cudaStream_t st) {
-    const long nrows = c->T * c->H;
+// GPU half of the table phase: bit rows -> runs -> components -> tables (left on the device), for the planes [p0, p1).
+// Chunks must be processed in time order; every table is indexed globally (rows, runs, components, pairs, date-line rows
+// and segments continue where the previous chunk stopped), so the result is identical to one pass over all planes.
+// Three host round trips per chunk (run count, component count, pair count) size the tables.
+void tables_begin(ct_ctx* c) {
+    c->tb_planes = c->tb_runs = c->tb_comps = c->tb_seams = c->tb_segs = c->tb_pairs = 0;
+}
+
+int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
     const int H = c->H, W = c->W;
+    const long r0 = p0 * H, r1 = p1 * H, n = r1 - r0;
+    if (p0 != c->tb_planes || p1 <= p0 || p1 > c->T) return fail(CT_ERR_INTERNAL, "table chunks out of order");
     uint32_t* cnt_dev = c->counters.as<uint32_t>();
     uint32_t* cnt_host = c->hp_counters.as<uint32_t>();
     auto U = [](DevBuf& b) { return b.as<uint32_t>(); };
+    // the first chunk of several sizes the tables for the whole cube (its density x all planes + 25 %)
+    const double scale = p0 == 0 && p1 < c->T ? 1.25 * (double)c->T / (double)(p1 - p0) : 0.0;
+    auto hint = [&](long elems, size_t elt) { return (size_t)((double)elems * scale) * elt; };
 
-    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(nrows > 1024 ? nrows : 1024) * sizeof(uint32_t)));
-    CT_CUDA(ctk::exclusive_scan_u32(U(c->row_cnt), U(c->row_ptr), nrows, U(c->scan_tmp), st));
-    CT_CUDA(ctk::exclusive_scan_u32(U(c->seam_flag), U(c->seam_pos), nrows, U(c->scan_tmp), st));
+    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(n > 1024 ? n : 1024) * sizeof(uint32_t)));
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->row_cnt) + r0, U(c->row_ptr) + r0, n, U(c->scan_tmp), st, (uint32_t)c->tb_runs));
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->seam_flag) + r0, U(c->seam_pos) + r0, n, U(c->scan_tmp), st,
+                                    (uint32_t)c->tb_seams));
     c->launches += 6;
-    CT_CUDA(cudaMemcpyAsync(cnt_host + 0, U(c->row_ptr) + nrows, 4, cudaMemcpyDeviceToHost, st));
-    CT_CUDA(cudaMemcpyAsync(cnt_host + 1, U(c->seam_pos) + nrows, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 0, U(c->row_ptr) + r1, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 1, U(c->seam_pos) + r1, 4, cudaMemcpyDeviceToHost, st));
     CT_CUDA(cudaStreamSynchronize(st));
-    const long R = cnt_host[0], nseam = cnt_host[1];
-    c->nruns = R; c->nseam = nseam;
+    const long Rb = c->tb_runs, Re = cnt_host[0], Sb = c->tb_seams, Se = cnt_host[1];
 
     // ---- runs + 2-D components ----
-    const size_t rb = (size_t)(R + 1) * sizeof(uint32_t);
-    CT_CUDA(c->run_x.ensure(rb)); CT_CUDA(c->run_row.ensure(rb)); CT_CUDA(c->parent.ensure(rb));
-    CT_CUDA(c->root_flag.ensure(rb)); CT_CUDA(c->rank.ensure(rb + 4)); CT_CUDA(c->run_comp.ensure(rb));
-    CT_CUDA(c->run_val.ensure(rb));
-    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(R > nrows ? R : nrows) * sizeof(uint32_t)));
-    CT_CUDA(ctk::extract_runs(U(c->bits), U(c->row_ptr), nrows, c->Ww, U(c->run_x), U(c->run_row), st));
-    CT_CUDA(ctk::ccl_init(U(c->parent), R, st));
-    CT_CUDA(ctk::ccl_union(U(c->row_ptr), U(c->run_x), U(c->run_row), R, H, U(c->parent), st));
-    CT_CUDA(ctk::ccl_flatten(U(c->parent), U(c->root_flag), R, st));
-    CT_CUDA(ctk::exclusive_scan_u32(U(c->root_flag), U(c->rank), R, U(c->scan_tmp), st));
+    {
+        DevBuf* rb[] = {&c->run_x, &c->run_row, &c->parent, &c->root_flag, &c->rank, &c->run_comp};
+        for (DevBuf* b : rb) CT_CUDA(b->grow((size_t)(Re + 2) * 4, (size_t)Rb * 4, st, hint(Re + 2, 4)));
+    }
+    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(std::max(Re - Rb, n)) * sizeof(uint32_t)));
+    CT_CUDA(ctk::extract_runs(U(c->bits), U(c->row_ptr), r0, n, c->Ww, U(c->run_x), U(c->run_row), st));
+    CT_CUDA(ctk::ccl_init(U(c->parent), Rb, Re, st));
+    CT_CUDA(ctk::ccl_union(U(c->row_ptr), U(c->run_x), U(c->run_row), Rb, Re, H, U(c->parent), st));
+    CT_CUDA(ctk::ccl_flatten(U(c->parent), U(c->root_flag), Rb, Re, st));
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->root_flag) + Rb, U(c->rank) + Rb, Re - Rb, U(c->scan_tmp), st,
+                                    (uint32_t)c->tb_comps));
     c->launches += 7;
-    CT_CUDA(cudaMemcpyAsync(cnt_host + 2, U(c->rank) + R, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 2, U(c->rank) + Re, 4, cudaMemcpyDeviceToHost, st));
     CT_CUDA(cudaStreamSynchronize(st));
-    const long nc = cnt_host[2];
-    c->ncomp = nc;
+    const long Cb = c->tb_comps, Ce = cnt_host[2];
 
     // ---- component tables, date-line rows and classes ----
-    CT_CUDA(ctk::ccl_assign(U(c->parent), U(c->rank), U(c->run_comp), R, st));
-    const size_t cb4 = (size_t)(nc + 2) * 4, cb8 = (size_t)(nc + 2) * 8;
-    CT_CUDA(c->c_t.ensure(cb4)); CT_CUDA(c->c_y0.ensure(cb4)); CT_CUDA(c->c_y1.ensure(cb4));
-    CT_CUDA(c->c_x0.ensure(cb4)); CT_CUDA(c->c_x1.ensure(cb4)); CT_CUDA(c->c_E.ensure(cb8));
-    CT_CUDA(c->c_S.ensure(cb8)); CT_CUDA(c->c_nsp.ensure(cb4)); CT_CUDA(c->c_cls.ensure(cb4));
-    CT_CUDA(c->c_val.ensure(cb4));
-    CT_CUDA(c->k_conE.ensure(cb8)); CT_CUDA(c->k_conS.ensure(cb8)); CT_CUDA(c->k_fE.ensure(cb8));
-    CT_CUDA(c->k_fS.ensure(cb8)); CT_CUDA(c->k_nsp.ensure(cb4)); CT_CUDA(c->k_fnsp.ensure(cb4));
-    CT_CUDA(c->pcnt.ensure(cb4)); CT_CUDA(c->pfill.ensure(cb4)); CT_CUDA(c->pptr.ensure(cb4 + 4));
+    CT_CUDA(ctk::ccl_assign(U(c->parent), U(c->rank), U(c->run_comp), Rb, Re, st));
+    {
+        DevBuf* b4[] = {&c->c_t, &c->c_y0, &c->c_y1, &c->c_x0, &c->c_x1, &c->c_nsp, &c->c_cls, &c->c_val,
+                        &c->k_nsp, &c->k_fnsp, &c->pcnt, &c->pfill, &c->pptr};
+        DevBuf* b8[] = {&c->c_E, &c->c_S, &c->k_conE, &c->k_conS, &c->k_fE, &c->k_fS};
+        for (DevBuf* b : b4) CT_CUDA(b->grow((size_t)(Ce + 3) * 4, (size_t)Cb * 4, st, hint(Ce + 3, 4)));
+        for (DevBuf* b : b8) CT_CUDA(b->grow((size_t)(Ce + 3) * 8, (size_t)Cb * 8, st, hint(Ce + 3, 8)));
+    }
     ctk::CompTables ct;
     ct.t = c->c_t.as<int32_t>(); ct.y0 = c->c_y0.as<int32_t>(); ct.y1 = c->c_y1.as<int32_t>();
     ct.x0 = c->c_x0.as<int32_t>(); ct.x1 = c->c_x1.as<int32_t>(); ct.areaE = c->c_E.as<double>();
@@ -334,68 +366,93 @@ int tables_build(ct_ctx* c, cudaStream_t st) {
     ctk::ClassTables kt;
     kt.conE = c->k_conE.as<double>(); kt.conS = c->k_conS.as<double>(); kt.fE = c->k_fE.as<double>();
     kt.fS = c->k_fS.as<double>(); kt.nsp = U(c->k_nsp); kt.fnsp = U(c->k_fnsp);
-    CT_CUDA(ctk::comp_init(ct, nc, W, st));
-    CT_CUDA(ctk::comp_accumulate(U(c->run_x), U(c->run_row), U(c->run_comp), R, H, c->w_dev.as<double>(),
+    CT_CUDA(ctk::comp_init(ct, Cb, Ce, W, st));
+    CT_CUDA(ctk::comp_accumulate(U(c->run_x), U(c->run_row), U(c->run_comp), Rb, Re, H, c->w_dev.as<double>(),
                                  c->special_dev.as<uint8_t>(), ct, st));
-    const size_t sb = (size_t)(nseam + 2) * 4;
-    CT_CUDA(c->s_row.ensure(sb)); CT_CUDA(c->s_a.ensure(sb)); CT_CUDA(c->s_b.ensure(sb));
-    CT_CUDA(c->seg_start.ensure(sb)); CT_CUDA(c->seg_pos.ensure(sb + 4));
-    CT_CUDA(c->g_t.ensure(sb)); CT_CUDA(c->g_y0.ensure(sb)); CT_CUDA(c->g_y1.ensure(sb)); CT_CUDA(c->g_a.ensure(sb));
-    CT_CUDA(c->g_b.ensure(sb));
-    CT_CUDA(ctk::seam_rows(U(c->seam_flag), U(c->seam_pos), U(c->row_ptr), U(c->run_comp), nrows, U(c->s_row),
+    {
+        DevBuf* sb[] = {&c->s_row, &c->s_a, &c->s_b, &c->seg_start, &c->seg_pos, &c->g_t, &c->g_y0, &c->g_y1, &c->g_a,
+                        &c->g_b};
+        for (DevBuf* b : sb) CT_CUDA(b->grow((size_t)(Se + 3) * 4, (size_t)Sb * 4, st, hint(Se + 3, 4)));
+    }
+    CT_CUDA(ctk::seam_rows(U(c->seam_flag), U(c->seam_pos), U(c->row_ptr), U(c->run_comp), r0, r1, U(c->s_row),
                            U(c->s_a), U(c->s_b), ct.cls, st));
-    CT_CUDA(ctk::cls_flatten(ct.cls, nc, st));
+    CT_CUDA(ctk::cls_flatten(ct.cls, Cb, Ce, st));
     ctk::SegTables sg;
     sg.t = c->g_t.as<int32_t>(); sg.y0 = c->g_y0.as<int32_t>(); sg.y1 = c->g_y1.as<int32_t>();
     sg.a = U(c->g_a); sg.b = U(c->g_b);
-    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(std::max(std::max(R, nrows), std::max(nc, nseam)) + 1) * 4));
-    CT_CUDA(ctk::seg_flags(U(c->s_row), U(c->s_a), U(c->s_b), nseam, H, U(c->seg_start), st));
-    CT_CUDA(ctk::exclusive_scan_u32(U(c->seg_start), U(c->seg_pos), nseam, U(c->scan_tmp), st));
-    CT_CUDA(ctk::seg_write(U(c->s_row), U(c->s_a), U(c->s_b), U(c->seg_start), U(c->seg_pos), nseam, H, sg, st));
-    CT_CUDA(cudaMemcpyAsync(cnt_host + 3, U(c->seg_pos) + nseam, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(std::max(std::max(Re - Rb, n), std::max(Ce - Cb, Se - Sb)) + 1) * 4));
+    CT_CUDA(ctk::seg_flags(U(c->s_row), U(c->s_a), U(c->s_b), Sb, Se, H, U(c->seg_start), st));
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->seg_start) + Sb, U(c->seg_pos) + Sb, Se - Sb, U(c->scan_tmp), st,
+                                    (uint32_t)c->tb_segs));
+    CT_CUDA(ctk::seg_write(U(c->s_row), U(c->s_a), U(c->s_b), U(c->seg_start), U(c->seg_pos), Sb, Se, H, sg, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 3, U(c->seg_pos) + Se, 4, cudaMemcpyDeviceToHost, st));
     c->launches += 10;
 
-    // ---- adjacent-plane pairs: hash accumulate -> CSR over the plane-t component; class sums ----
-    long np = 0;
-    uint64_t want = (uint64_t)nc * 4;
-    ctk::PairCsr q;
+    // ---- adjacent-plane pairs of this chunk's planes (the earlier plane may belong to the previous chunk): hash
+    // accumulate -> CSR over the plane-t component; class sums ----
+    const size_t o8 = (size_t)Cb * 8, o4 = (size_t)Cb * 4, n8 = (size_t)(Ce - Cb) * 8, n4 = (size_t)(Ce - Cb) * 4;
+    if (Ce > Cb) {
+        CT_CUDA(cudaMemsetAsync((char*)c->k_conE.p + o8, 0, n8, st)); CT_CUDA(cudaMemsetAsync((char*)c->k_conS.p + o8, 0, n8, st));
+        CT_CUDA(cudaMemsetAsync((char*)c->k_fE.p + o8, 0, n8, st)); CT_CUDA(cudaMemsetAsync((char*)c->k_fS.p + o8, 0, n8, st));
+        CT_CUDA(cudaMemsetAsync((char*)c->k_nsp.p + o4, 0, n4, st)); CT_CUDA(cudaMemsetAsync((char*)c->k_fnsp.p + o4, 0, n4, st));
+        CT_CUDA(cudaMemsetAsync((char*)c->pcnt.p + o4, 0, n4, st)); CT_CUDA(cudaMemsetAsync((char*)c->pfill.p + o4, 0, n4, st));
+    }
+    CT_CUDA(ctk::class_sums(ct, kt, Cb, Ce, st));
+    ctk::PairTable pt;
+    uint64_t want = (uint64_t)(Ce - Cb) * 4;
     for (int attempt = 0;; ++attempt) {
-        ctk::PairTable pt;
         pt.cap = next_pow2(want);
         CT_CUDA(c->h_key.ensure((size_t)pt.cap * 8)); CT_CUDA(c->h_npix.ensure((size_t)pt.cap * 4));
         CT_CUDA(c->h_nsp.ensure((size_t)pt.cap * 4)); CT_CUDA(c->h_E.ensure((size_t)pt.cap * 8));
         CT_CUDA(c->h_S.ensure((size_t)pt.cap * 8));
         pt.key = c->h_key.as<unsigned long long>(); pt.npix = U(c->h_npix);
         pt.nsp = U(c->h_nsp); pt.areaE = c->h_E.as<double>(); pt.areaS = c->h_S.as<double>();
-        pt.overflow = cnt_dev + 4;
-        CT_CUDA(c->p_b.ensure((size_t)pt.cap * 4)); CT_CUDA(c->p_npix.ensure((size_t)pt.cap * 4));
-        CT_CUDA(c->p_nsp.ensure((size_t)pt.cap * 4)); CT_CUDA(c->p_E.ensure((size_t)pt.cap * 8));
-        CT_CUDA(c->p_S.ensure((size_t)pt.cap * 8));
-        q.b = U(c->p_b); q.npix = U(c->p_npix); q.nsp = U(c->p_nsp); q.E = c->p_E.as<double>(); q.S = c->p_S.as<double>();
-        CT_CUDA(cudaMemsetAsync(kt.conE, 0, cb8, st)); CT_CUDA(cudaMemsetAsync(kt.conS, 0, cb8, st));
-        CT_CUDA(cudaMemsetAsync(kt.fE, 0, cb8, st)); CT_CUDA(cudaMemsetAsync(kt.fS, 0, cb8, st));
-        CT_CUDA(cudaMemsetAsync(kt.nsp, 0, cb4, st)); CT_CUDA(cudaMemsetAsync(kt.fnsp, 0, cb4, st));
-        CT_CUDA(cudaMemsetAsync(c->pcnt.p, 0, cb4, st)); CT_CUDA(cudaMemsetAsync(c->pfill.p, 0, cb4, st));
-        CT_CUDA(cudaMemsetAsync(cnt_dev + 5, 0, 4, st));
-        CT_CUDA(ctk::class_sums(ct, kt, nc, st));
+        pt.overflow = cnt_dev + 4; pt.count = cnt_dev + 5;
         CT_CUDA(ctk::pairs_init(pt, st));
-        CT_CUDA(ctk::pairs_accumulate(U(c->row_ptr), U(c->run_x), U(c->run_row), U(c->run_comp), R, H,
+        CT_CUDA(ctk::pairs_accumulate(U(c->row_ptr), U(c->run_x), U(c->run_row), U(c->run_comp), Rb, Re, H,
                                       c->w_dev.as<double>(), c->special_dev.as<uint8_t>(), pt, st));
-        CT_CUDA(ctk::pairs_count(pt, ct.cls, kt, U(c->pcnt), cnt_dev + 5, st));
-        CT_CUDA(ctk::exclusive_scan_u32(U(c->pcnt), U(c->pptr), nc, U(c->scan_tmp), st));
-        CT_CUDA(ctk::pairs_fill(pt, U(c->pptr), U(c->pfill), q, st));
-        c->launches += 8;
+        c->launches += 3;
         CT_CUDA(cudaMemcpyAsync(cnt_host + 4, cnt_dev + 4, 8, cudaMemcpyDeviceToHost, st));
         CT_CUDA(cudaStreamSynchronize(st));
-        if (cnt_host[4] == 0 && (uint64_t)cnt_host[5] * 10 <= (uint64_t)pt.cap * 7) { np = cnt_host[5]; break; }
+        if (cnt_host[4] == 0 && (uint64_t)cnt_host[5] * 10 <= (uint64_t)pt.cap * 7) break;
         if (attempt >= 6 || pt.cap >= (1u << 31)) return fail(CT_ERR_CAPACITY, "pair table overflow");
         want = (uint64_t)pt.cap * 4;                                  // too full: probing would crawl
     }
-    c->nseg = nseam ? cnt_host[3] : 0;
-    c->npair = np;
-    c->stats["runs"] = (double)R; c->stats["comps2d"] = (double)nc; c->stats["pairs"] = (double)np;
-    c->stats["seam_rows"] = (double)nseam; c->stats["seam_segments"] = (double)c->nseg;
+    const long Pb = c->tb_pairs, Pe = Pb + cnt_host[5];
+    {
+        DevBuf* b4[] = {&c->p_b, &c->p_npix, &c->p_nsp};
+        DevBuf* b8[] = {&c->p_E, &c->p_S};
+        for (DevBuf* b : b4) CT_CUDA(b->grow((size_t)(Pe + 2) * 4, (size_t)Pb * 4, st, hint(Pe + 2, 4)));
+        for (DevBuf* b : b8) CT_CUDA(b->grow((size_t)(Pe + 2) * 8, (size_t)Pb * 8, st, hint(Pe + 2, 8)));
+    }
+    ctk::PairCsr q;
+    q.b = U(c->p_b); q.npix = U(c->p_npix); q.nsp = U(c->p_nsp); q.E = c->p_E.as<double>(); q.S = c->p_S.as<double>();
+    CT_CUDA(ctk::pairs_count(pt, ct.cls, kt, U(c->pcnt), st));
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->pcnt) + Cb, U(c->pptr) + Cb, Ce - Cb, U(c->scan_tmp), st, (uint32_t)Pb));
+    CT_CUDA(ctk::pairs_fill(pt, U(c->pptr), U(c->pfill), q, st));
+    c->launches += 5;
+    c->tb_planes = p1; c->tb_runs = Re; c->tb_comps = Ce; c->tb_seams = Se; c->tb_pairs = Pe;
+    c->tb_segs = Se > Sb ? cnt_host[3] : c->tb_segs;
     return CT_OK;
+}
+
+int tables_finish(ct_ctx* c, cudaStream_t st) {
+    if (c->tb_planes != c->T) return fail(CT_ERR_INTERNAL, "tables cover %ld of %ld planes", c->tb_planes, c->T);
+    c->nruns = c->tb_runs; c->ncomp = c->tb_comps; c->npair = c->tb_pairs; c->nseam = c->tb_seams; c->nseg = c->tb_segs;
+    CT_CUDA(c->run_val.ensure((size_t)(c->nruns + 1) * 4));
+    (void)st;
+    c->stats["runs"] = (double)c->nruns; c->stats["comps2d"] = (double)c->ncomp; c->stats["pairs"] = (double)c->npair;
+    c->stats["seam_rows"] = (double)c->nseam; c->stats["seam_segments"] = (double)c->nseg;
+    return CT_OK;
+}
+
+int tables_build(ct_ctx* c, cudaStream_t st) {
+    tables_begin(c);
+    if (c->T > 0) {
+        int rc = tables_chunk(c, 0, c->T, st);
+        if (rc != CT_OK) return rc;
+    }
+    return tables_finish(c, st);
 }
 
 // Tables -> pinned host memory (c->host_tb).  full = 0 copies only what steps 4c/4d need (component boxes, classes,
@@ -497,6 +554,7 @@ int gpu_step3_link(ct_ctx* c, double overlap, int twosided, long* nflag_out, lon
     t.pair_nsp = c->p_nsp.as<uint32_t>(); t.pair_E = c->p_E.as<double>(); t.pair_S = c->p_S.as<double>();
     t.kept = c->l_kept.as<uint8_t>(); t.accE = c->l_accE.as<double>(); t.accS = c->l_accS.as<double>();
     t.accN = c->l_accN.as<uint32_t>();
+    const double t_g0 = now_ms();
     CT_CUDA(ctk::step3_init(t, nc, st));
     c->launches += 1;
     // counters 8..8+BATCH-1: "changed" per sweep of a batch; counter 7: near-tie flags of the latest sweep
@@ -516,6 +574,7 @@ int gpu_step3_link(ct_ctx* c, double overlap, int twosided, long* nflag_out, lon
         if (sweeps > c->T + BATCH) return fail(CT_ERR_INTERNAL, "step-3 sweeps did not converge");
     }
     c->stats["sweeps"] = (double)sweeps;
+    c->stats["ms_g_sweeps"] = now_ms() - t_g0;
     *nflag_out = cnt_host[7];
     if (*nflag_out) return CT_OK;
     CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(nc + 1) * 4));
@@ -525,6 +584,7 @@ int gpu_step3_link(ct_ctx* c, double overlap, int twosided, long* nflag_out, lon
     CT_CUDA(cudaMemcpyAsync(cnt_host + 6, c->l_rank.as<uint32_t>() + nc, 4, cudaMemcpyDeviceToHost, st));
     CT_CUDA(cudaStreamSynchronize(st));
     *nlabels_out = nc ? cnt_host[6] : 0;
+    c->stats["ms_g_link"] = now_ms() - t_g0 - c->stats["ms_g_sweeps"];
     return CT_OK;
 }
 
@@ -559,8 +619,9 @@ int upload_values(ct_ctx* c, const int32_t* comp_val_pinned, const std::vector<c
 
 // Everything between the two cube-sized kernels.  On return the value per row-run and the override sub-runs are on the
 // device.
-int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int stage, long* n_features, cudaStream_t st) {
-    int rc0 = tables_build(c, st);
+int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int stage, long* n_features, cudaStream_t st,
+                bool tables_built = false) {
+    int rc0 = tables_built ? CT_OK : tables_build(c, st);
     if (rc0 != CT_OK) return rc0;
     const long nc = c->ncomp;
     cth::FastTables& tb = c->host_tb;
@@ -610,8 +671,10 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
                 CT_CUDA(cudaMemcpyAsync(h_lorder, ld.order, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
                 CT_CUDA(cudaMemcpyAsync(hlabel, c->l_label.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
             }
+            const double t_lab0 = now_ms();
             if ((rc0 = tables_d2h(c, 0, st)) != CT_OK) return rc0;      // component boxes + segments; synchronizes
             const double t_host0 = now_ms();
+            c->stats["ms_g_labels_d2h"] = t_host0 - t_lab0;
             cth::Result& res = c->host_result;
             res.n_neartie = 0; res.n_labels3d = nlab; res.n_kept = h_lptr[nlab + 1];
             static thread_local std::vector<int32_t> sa32, sb32, fin, mc, ml;
@@ -733,7 +796,7 @@ int ensure_streams(ct_ctx* c) {
     if (!c->side_stream) CT_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
     if (!c->tbl_stream) CT_CUDA(cudaStreamCreateWithPriority(&c->tbl_stream, cudaStreamNonBlocking, hi));
     for (auto& e : c->ev_side) if (!e) CT_CUDA(cudaEventCreate(&e));
-    for (auto& e : c->ev_tbl) if (!e) CT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : c->ev_tbl) if (!e) CT_CUDA(cudaEventCreate(&e));
     return CT_OK;
 }
 
@@ -805,6 +868,7 @@ void ct_destroy(ct_ctx* c) {
     for (auto& e : c->ev_tbl) if (e) cudaEventDestroy(e);
     if (c->tbl_stream) cudaStreamDestroy(c->tbl_stream);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_chunk) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->work_stream) cudaStreamDestroy(c->work_stream);
     delete c;
@@ -817,6 +881,8 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "overlap_zero")) { c->opt_overlap_zero = value; return CT_OK; }
     if (!strcmp(key, "gpu_tables")) { c->opt_gpu_tables = value; return CT_OK; }
     if (!strcmp(key, "paint_runs")) { c->opt_paint_runs = value; return CT_OK; }
+    if (!strcmp(key, "chunks")) { c->opt_chunks = value < 1 ? 1 : value; return CT_OK; }
+    if (!strcmp(key, "chunk_min_planes")) { c->opt_chunk_min_planes = value < 1 ? 1 : value; return CT_OK; }
     if (!strcmp(key, "host_sparse")) { c->opt_host_sparse = value; return CT_OK; }
     if (!strcmp(key, "host_threads")) { c->opt_host_threads = value; return CT_OK; }
     return fail(CT_ERR_ARG, "unknown option '%s'", key);
@@ -837,28 +903,59 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     c->stats.clear();
     if ((rc = prepare(c, T, H, W, w_host, thr_host, thr_n, st)) != CT_OK) return rc;
     c->has_prev = 0;
-    CT_CUDA(cudaEventRecord(c->ev[0], st));
-    if ((rc = launch_threshold(c, anom_dev, in_dtype, 0, T, thr_n, thr_is_f32, op, st)) != CT_OK) return rc;
-    CT_CUDA(cudaEventRecord(c->ev[1], st));
-    // The table phase is latency-bound (small kernels, three host round trips, the ordered host pass): the zero fill of
-    // the flag cube -- most of the 4 B/cell the path has to write -- runs under it on a side stream; afterwards only the
-    // cells of row-runs are painted.
+    // Pipeline: the cube is thresholded in time chunks on `st`; the table kernels of chunk k (latency-bound, small) run
+    // on a high-priority stream while chunk k+1 is being thresholded (HBM-bound).  After the last chunk the zero fill of
+    // the flag cube -- most of the 4 B/cell the path has to write -- runs on a low-priority stream under the global part
+    // of the table phase (overlap filter, 3-D labels, date-line merge, persistence); afterwards only the cells of
+    // row-runs are painted.
     const int sparse = c->opt_overlap_zero ? 1 : 0;
+    long nchunk = sparse ? std::min<long>(c->opt_chunks, std::max<long>(1, T / c->opt_chunk_min_planes)) : 1;
+    const long cp = (T + nchunk - 1) / nchunk;
+    nchunk = (T + cp - 1) / cp;
     cudaStream_t ts = st;
     if (sparse) {
         if ((rc = ensure_streams(c)) != CT_OK) return rc;
+        ts = c->tbl_stream;
+        while ((long)c->ev_chunk.size() < nchunk) {
+            cudaEvent_t e;
+            CT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->ev_chunk.push_back(e);
+        }
+    }
+    const size_t plane_bytes = (size_t)H * W * (in_dtype == CT_F64 ? 8 : 4);
+    CT_CUDA(cudaEventRecord(c->ev[0], st));
+    for (long k = 0; k < nchunk; ++k) {
+        const long t0 = k * cp, nt = std::min(cp, T - t0);
+        if ((rc = launch_threshold(c, (const char*)anom_dev + (size_t)t0 * plane_bytes, in_dtype, t0, nt, thr_n, thr_is_f32,
+                                   op, st)) != CT_OK) return rc;
+        if (sparse) CT_CUDA(cudaEventRecord(c->ev_chunk[k], st));
+    }
+    CT_CUDA(cudaEventRecord(c->ev[1], st));
+    if (sparse) {
         CT_CUDA(cudaEventRecord(c->ev_side[0], st));
         CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-        CT_CUDA(cudaStreamWaitEvent(c->tbl_stream, c->ev_side[0], 0));
         CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T * H * W, c->sm_count, c->side_stream));
         CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
         c->launches += 1;
-        ts = c->tbl_stream;
     }
-    if ((rc = table_phase(c, overlap, persistence, twosided, stage, n_features, ts)) != CT_OK) {
+    const double t_h0 = now_ms();
+    tables_begin(c);
+    for (long k = 0; k < nchunk && rc == CT_OK; ++k) {
+        const long t0 = k * cp, nt = std::min(cp, T - t0);
+        if (sparse) CT_CUDA(cudaStreamWaitEvent(ts, c->ev_chunk[k], 0));
+        rc = tables_chunk(c, t0, t0 + nt, ts);
+    }
+    if (rc == CT_OK) rc = tables_finish(c, ts);
+    const double t_h1 = now_ms();
+    if (rc == CT_OK) rc = table_phase(c, overlap, persistence, twosided, stage, n_features, ts, true);
+    if (rc != CT_OK) {
         if (sparse) { cudaStreamSynchronize(c->side_stream); cudaStreamSynchronize(c->tbl_stream); }
+        cudaStreamSynchronize(st);
         return rc;
     }
+    c->stats["chunks"] = (double)nchunk;
+    c->stats["ms_h_chunks"] = t_h1 - t_h0;                           // host wall clock: chunk tables (ends in a sync)
+    c->stats["ms_h_global"] = now_ms() - t_h1;                       // ... global part (last uploads still in flight)
     if (sparse) {
         CT_CUDA(cudaEventRecord(c->ev_tbl[0], ts));
         CT_CUDA(cudaStreamWaitEvent(st, c->ev_tbl[0], 0));
@@ -879,7 +976,10 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stats["ms_tables_host_roundtrip"] = ms;
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats["ms_paint"] = ms;
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats["ms_total"] = ms;
-    if (sparse) { CT_CUDA(cudaEventElapsedTime(&ms, c->ev_side[0], c->ev_side[1])); c->stats["ms_zero_fill"] = ms; }
+    if (sparse) {
+        CT_CUDA(cudaEventElapsedTime(&ms, c->ev_side[0], c->ev_side[1])); c->stats["ms_zero_fill"] = ms;
+        CT_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev_tbl[0])); c->stats["ms_tables_after_threshold"] = ms;
+    }
     c->stats["kernel_launches"] = (double)c->launches;
     return CT_OK;
 }

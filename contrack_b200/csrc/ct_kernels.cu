@@ -343,9 +343,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __
     if (threadIdx.x == 0) sums[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, long nb, uint32_t* total_out) {
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, long nb, uint32_t* total_out, uint32_t base) {
     __shared__ uint32_t s_warp[33];
-    uint32_t running = 0;
+    uint32_t running = base;
     for (long b0 = 0; b0 < nb; b0 += 1024) {
         const long i = b0 + threadIdx.x;
         uint32_t v = i < nb ? sums[i] : 0, tot;
@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const uint32_t* __r
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_extract_runs(const uint32_t* __restrict__ bits,
                                                       const uint32_t* __restrict__ row_ptr, long nrows, int Ww,
-                                                      uint32_t* __restrict__ run_x, uint32_t* __restrict__ run_row) {
+                                                      uint32_t* __restrict__ run_x, uint32_t* __restrict__ run_row,
+                                                      long row0) {
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(256) k_extract_runs(const uint32_t* __restrict
                 const int bit = __ffs(starts) - 1;
                 starts &= starts - 1;
                 rx[2 * (size_t)is] = (uint16_t)(k * 32 + bit);
-                run_row[is] = (uint32_t)row;
+                run_row[is] = (uint32_t)(row0 + row);
                 ++is;
             }
             while (ends) {
@@ -444,18 +445,18 @@ __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t 
     }
 }
 
-__global__ void k_iota(uint32_t* p, long n) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = (uint32_t)i;
+__global__ void k_iota(uint32_t* p, long begin, long end) {
+    const long i = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < end) p[i] = (uint32_t)i;
 }
 
 // 8-connectivity between a run and the runs of the row above: [x0-1, x1+1) must meet [px0, px1).
 __global__ void __launch_bounds__(256) k_ccl_union(const uint32_t* __restrict__ row_ptr,
                                                    const uint32_t* __restrict__ run_x,
-                                                   const uint32_t* __restrict__ run_row, long nruns, int H,
-                                                   uint32_t* parent) {
-    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nruns) return;
+                                                   const uint32_t* __restrict__ run_row, long begin, long rend,
+                                                   int H, uint32_t* parent) {
+    const long r = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rend) return;
     const uint32_t row = run_row[r];
     if (row % (uint32_t)H == 0) return;
     const uint32_t x = run_x[r];
@@ -472,9 +473,10 @@ __global__ void __launch_bounds__(256) k_ccl_union(const uint32_t* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256) k_ccl_flatten(uint32_t* parent, uint32_t* __restrict__ root_flag, long nruns) {
-    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nruns) return;
+__global__ void __launch_bounds__(256) k_ccl_flatten(uint32_t* parent, uint32_t* __restrict__ root_flag, long begin,
+                                                     long end) {
+    const long r = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= end) return;
     const uint32_t root = uf_find(parent, (uint32_t)r);
     root_flag[r] = root == (uint32_t)r ? 1u : 0u;
     if (root != (uint32_t)r) parent[r] = root;
@@ -482,9 +484,9 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(uint32_t* parent, uint32_t*
 
 __global__ void __launch_bounds__(256) k_ccl_assign(const uint32_t* __restrict__ parent,
                                                     const uint32_t* __restrict__ rank, uint32_t* __restrict__ run_comp,
-                                                    long nruns) {
-    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nruns) return;
+                                                    long begin, long end) {
+    const long r = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= end) return;
     // after k_ccl_flatten parent[r] is the root or one hop from it (a concurrent flatten may have left a short chain)
     run_comp[r] = rank[uf_find(parent, (uint32_t)r)];
 }
@@ -492,20 +494,20 @@ __global__ void __launch_bounds__(256) k_ccl_assign(const uint32_t* __restrict__
 // ---------------------------------------------------------------------------------------------------------------
 // component tables
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_comp_init(CompTables c, long ncomp, int W) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ncomp) return;
+__global__ void __launch_bounds__(256) k_comp_init(CompTables c, long begin, long end, int W) {
+    const long i = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
     c.t[i] = 0; c.y0[i] = INT_MAX; c.y1[i] = 0; c.x0[i] = W; c.x1[i] = 0;
     c.areaE[i] = 0.0; c.areaS[i] = 0.0; c.nsp[i] = 0; c.cls[i] = (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(256) k_comp_accumulate(const uint32_t* __restrict__ run_x,
                                                          const uint32_t* __restrict__ run_row,
-                                                         const uint32_t* __restrict__ run_comp, long nruns, int H,
-                                                         const double* __restrict__ w,
+                                                         const uint32_t* __restrict__ run_comp, long begin, long end,
+                                                         int H, const double* __restrict__ w,
                                                          const uint8_t* __restrict__ special, CompTables c) {
-    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nruns) return;
+    const long r = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= end) return;
     const uint32_t row = run_row[r], comp = run_comp[r];
     const int t = (int)(row / (uint32_t)H), y = (int)(row % (uint32_t)H);
     const uint32_t x = run_x[r];
@@ -523,20 +525,21 @@ __global__ void __launch_bounds__(256) k_comp_accumulate(const uint32_t* __restr
 __global__ void __launch_bounds__(256) k_seam_rows(const uint32_t* __restrict__ seam_flag,
                                                    const uint32_t* __restrict__ seam_pos,
                                                    const uint32_t* __restrict__ row_ptr,
-                                                   const uint32_t* __restrict__ run_comp, long nrows,
-                                                   uint32_t* __restrict__ seam_row, uint32_t* __restrict__ seam_a,
-                                                   uint32_t* __restrict__ seam_b, uint32_t* cls_parent) {
-    const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= nrows || !seam_flag[row]) return;
+                                                   const uint32_t* __restrict__ run_comp, long row_begin,
+                                                   long row_end, uint32_t* __restrict__ seam_row,
+                                                   uint32_t* __restrict__ seam_a, uint32_t* __restrict__ seam_b,
+                                                   uint32_t* cls_parent) {
+    const long row = row_begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row_end || !seam_flag[row]) return;
     const uint32_t a = run_comp[row_ptr[row]], b = run_comp[row_ptr[row + 1] - 1];
     const uint32_t pos = seam_pos[row];
     seam_row[pos] = (uint32_t)row; seam_a[pos] = a; seam_b[pos] = b;
     if (a != b) uf_union(cls_parent, a, b);
 }
 
-__global__ void __launch_bounds__(256) k_cls_flatten(uint32_t* cls_parent, long ncomp) {
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncomp) return;
+__global__ void __launch_bounds__(256) k_cls_flatten(uint32_t* cls_parent, long begin, long end) {
+    const long c = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= end) return;
     const uint32_t root = uf_find(cls_parent, (uint32_t)c);
     if (root != (uint32_t)c) cls_parent[c] = root;
 }
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(256) k_pairs_init(PairTable p) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.cap) return;
     p.key[i] = PAIR_EMPTY; p.npix[i] = 0; p.nsp[i] = 0; p.areaE[i] = 0.0; p.areaS[i] = 0.0;
-    if (i == 0) *p.overflow = 0;
+    if (i == 0) { *p.overflow = 0; *p.count = 0; }
 }
 
 __device__ __forceinline__ uint32_t hash64(unsigned long long k) {
@@ -559,11 +562,11 @@ __device__ __forceinline__ uint32_t hash64(unsigned long long k) {
 __global__ void __launch_bounds__(256) k_pairs_accumulate(const uint32_t* __restrict__ row_ptr,
                                                           const uint32_t* __restrict__ run_x,
                                                           const uint32_t* __restrict__ run_row,
-                                                          const uint32_t* __restrict__ run_comp, long nruns, int H,
-                                                          const double* __restrict__ w,
+                                                          const uint32_t* __restrict__ run_comp, long begin, long rend,
+                                                          int H, const double* __restrict__ w,
                                                           const uint8_t* __restrict__ special, PairTable pt) {
-    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nruns) return;
+    const long r = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rend) return;
     const uint32_t row = run_row[r];
     if (row < (uint32_t)H) return;                               // plane 0 has no predecessor
     const uint32_t prow = row - (uint32_t)H;
@@ -590,7 +593,10 @@ __global__ void __launch_bounds__(256) k_pairs_accumulate(const uint32_t* __rest
         bool found = false;
         for (uint32_t probe = 0; probe <= mask; ++probe) {
             unsigned long long k = *((volatile unsigned long long*)&pt.key[slot]);
-            if (k == PAIR_EMPTY) k = atomicCAS(&pt.key[slot], PAIR_EMPTY, key);
+            if (k == PAIR_EMPTY) {
+                k = atomicCAS(&pt.key[slot], PAIR_EMPTY, key);
+                if (k == PAIR_EMPTY) atomicAdd(pt.count, 1u);       // a new pair
+            }
             if (k == PAIR_EMPTY || k == key) { found = true; break; }
             slot = (slot + 1) & mask;
         }
@@ -619,9 +625,9 @@ __global__ void __launch_bounds__(256) k_pairs_compact(PairTable p, uint32_t* __
 // ---------------------------------------------------------------------------------------------------------------
 // tables in the layout the ordered host phase reads sequentially (ct_host.h: FastTables)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_class_sums(CompTables c, ClassTables k, long ncomp) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ncomp) return;
+__global__ void __launch_bounds__(256) k_class_sums(CompTables c, ClassTables k, long begin, long end) {
+    const long i = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
     const uint32_t rep = c.cls[i];
     atomicAdd(&k.conE[rep], c.areaE[i]);
     if (c.nsp[i]) { atomicAdd(&k.conS[rep], c.areaS[i]); atomicAdd(&k.nsp[rep], c.nsp[i]); }
@@ -630,13 +636,12 @@ __global__ void __launch_bounds__(256) k_class_sums(CompTables c, ClassTables k,
 // per occupied slot: count the pair for its plane-t component, add its area to the forward sums of the class of its
 // plane-(t-1) component
 __global__ void __launch_bounds__(256) k_pairs_count(PairTable p, const uint32_t* __restrict__ cls, ClassTables k,
-                                                     uint32_t* __restrict__ pcnt, uint32_t* __restrict__ total) {
+                                                     uint32_t* __restrict__ pcnt) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.cap) return;
     const unsigned long long key = p.key[i];
     if (key == PAIR_EMPTY) return;
     atomicAdd(&pcnt[(uint32_t)(key >> 32)], 1u);
-    atomicAdd(total, 1u);
     const uint32_t rep = cls[(uint32_t)key];
     atomicAdd(&k.fE[rep], p.areaE[i]);
     if (p.nsp[i]) { atomicAdd(&k.fS[rep], p.areaS[i]); atomicAdd(&k.fnsp[rep], p.nsp[i]); }
@@ -655,26 +660,27 @@ __global__ void __launch_bounds__(256) k_pairs_fill(PairTable p, const uint32_t*
 
 // date-line rows -> segments of consecutive rows of one plane with the same two components
 __global__ void __launch_bounds__(256) k_seg_flags(const uint32_t* __restrict__ srow, const uint32_t* __restrict__ sa,
-                                                   const uint32_t* __restrict__ sb, long n, int H,
+                                                   const uint32_t* __restrict__ sb, long begin, long end, int H,
                                                    uint32_t* __restrict__ start) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    bool st = i == 0;
+    const long i = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    bool st = i == begin;                                          // a range starts at a plane boundary
     if (!st) st = srow[i] != srow[i - 1] + 1 || (srow[i] % (uint32_t)H) == 0 || sa[i] != sa[i - 1] || sb[i] != sb[i - 1];
     start[i] = st ? 1u : 0u;
 }
 
 __global__ void __launch_bounds__(256) k_seg_write(const uint32_t* __restrict__ srow, const uint32_t* __restrict__ sa,
                                                    const uint32_t* __restrict__ sb, const uint32_t* __restrict__ start,
-                                                   const uint32_t* __restrict__ segpos, long n, int H, SegTables o) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                                                   const uint32_t* __restrict__ segpos, long begin, long end, int H,
+                                                   SegTables o) {
+    const long i = begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
     const uint32_t seg = segpos[i] + start[i] - 1;                 // inclusive scan - 1
     const uint32_t row = srow[i];
     if (start[i]) {
         o.t[seg] = (int32_t)(row / (uint32_t)H); o.y0[seg] = (int32_t)(row % (uint32_t)H); o.a[seg] = sa[i]; o.b[seg] = sb[i];
     }
-    if (i == n - 1 || start[i + 1]) o.y1[seg] = (int32_t)(row % (uint32_t)H) + 1;
+    if (i == end - 1 || start[i + 1]) o.y1[seg] = (int32_t)(row % (uint32_t)H) + 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1005,73 +1011,79 @@ cudaError_t row_stats(const uint32_t* bits, long nrows, int W, int Ww, uint32_t*
 
 size_t scan_tmp_elems(long n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 2; }
 
-cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st) {
-    if (n == 0) return cudaMemsetAsync(out, 0, sizeof(uint32_t), st);
+cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st, uint32_t base) {
+    if (n == 0) {
+        k_scan_sums<<<1, 1024, 0, st>>>(tmp, 0, out, base);
+        return cudaGetLastError();
+    }
     const long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, tmp);
-    k_scan_sums<<<1, 1024, 0, st>>>(tmp, nb, out + n);
+    k_scan_sums<<<1, 1024, 0, st>>>(tmp, nb, out + n, base);
     k_scan_final<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, tmp);
     return cudaGetLastError();
 }
 
-cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long nrows, int Ww, uint32_t* run_x,
+cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww, uint32_t* run_x,
                          uint32_t* run_row, cudaStream_t st) {
     if (nrows == 0) return cudaSuccess;
     const long want = (nrows + 7) / 8;
-    k_extract_runs<<<(unsigned)std::min<long>(want, 148L * 16), 256, 0, st>>>(bits, row_ptr, nrows, Ww, run_x, run_row);
+    k_extract_runs<<<(unsigned)std::min<long>(want, 148L * 16), 256, 0, st>>>(bits + row0 * (long)Ww, row_ptr + row0,
+                                                                             nrows, Ww, run_x, run_row, row0);
     return cudaGetLastError();
 }
 
-cudaError_t ccl_init(uint32_t* parent, long nruns, cudaStream_t st) {
-    if (nruns == 0) return cudaSuccess;
-    k_iota<<<blocks_for(nruns, 256), 256, 0, st>>>(parent, nruns);
+cudaError_t ccl_init(uint32_t* parent, long begin, long end, cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    k_iota<<<blocks_for(end - begin, 256), 256, 0, st>>>(parent, begin, end);
     return cudaGetLastError();
 }
 
-cudaError_t ccl_union(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row, long nruns, int H,
-                      uint32_t* parent, cudaStream_t st) {
-    if (nruns == 0) return cudaSuccess;
-    k_ccl_union<<<blocks_for(nruns, 256), 256, 0, st>>>(row_ptr, run_x, run_row, nruns, H, parent);
+cudaError_t ccl_union(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row, long begin, long end,
+                      int H, uint32_t* parent, cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    k_ccl_union<<<blocks_for(end - begin, 256), 256, 0, st>>>(row_ptr, run_x, run_row, begin, end, H, parent);
     return cudaGetLastError();
 }
 
-cudaError_t ccl_flatten(uint32_t* parent, uint32_t* root_flag, long nruns, cudaStream_t st) {
-    if (nruns == 0) return cudaSuccess;
-    k_ccl_flatten<<<blocks_for(nruns, 256), 256, 0, st>>>(parent, root_flag, nruns);
+cudaError_t ccl_flatten(uint32_t* parent, uint32_t* root_flag, long begin, long end, cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    k_ccl_flatten<<<blocks_for(end - begin, 256), 256, 0, st>>>(parent, root_flag, begin, end);
     return cudaGetLastError();
 }
 
-cudaError_t ccl_assign(const uint32_t* parent, const uint32_t* rank, uint32_t* run_comp, long nruns, cudaStream_t st) {
-    if (nruns == 0) return cudaSuccess;
-    k_ccl_assign<<<blocks_for(nruns, 256), 256, 0, st>>>(parent, rank, run_comp, nruns);
+cudaError_t ccl_assign(const uint32_t* parent, const uint32_t* rank, uint32_t* run_comp, long begin, long end,
+                       cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    k_ccl_assign<<<blocks_for(end - begin, 256), 256, 0, st>>>(parent, rank, run_comp, begin, end);
     return cudaGetLastError();
 }
 
-cudaError_t comp_init(const CompTables& c, long ncomp, int W, cudaStream_t st) {
-    if (ncomp == 0) return cudaSuccess;
-    k_comp_init<<<blocks_for(ncomp, 256), 256, 0, st>>>(c, ncomp, W);
+cudaError_t comp_init(const CompTables& c, long begin, long end, int W, cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    k_comp_init<<<blocks_for(end - begin, 256), 256, 0, st>>>(c, begin, end, W);
     return cudaGetLastError();
 }
 
-cudaError_t comp_accumulate(const uint32_t* run_x, const uint32_t* run_row, const uint32_t* run_comp, long nruns, int H,
-                            const double* w_dev, const uint8_t* special_dev, const CompTables& c, cudaStream_t st) {
-    if (nruns == 0) return cudaSuccess;
-    k_comp_accumulate<<<blocks_for(nruns, 256), 256, 0, st>>>(run_x, run_row, run_comp, nruns, H, w_dev, special_dev, c);
+cudaError_t comp_accumulate(const uint32_t* run_x, const uint32_t* run_row, const uint32_t* run_comp, long begin, long end,
+                            int H, const double* w_dev, const uint8_t* special_dev, const CompTables& c, cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    k_comp_accumulate<<<blocks_for(end - begin, 256), 256, 0, st>>>(run_x, run_row, run_comp, begin, end, H, w_dev,
+                                                                    special_dev, c);
     return cudaGetLastError();
 }
 
 cudaError_t seam_rows(const uint32_t* seam_flag, const uint32_t* seam_pos, const uint32_t* row_ptr,
-                      const uint32_t* run_comp, long nrows, uint32_t* seam_row, uint32_t* seam_a, uint32_t* seam_b,
-                      uint32_t* cls_parent, cudaStream_t st) {
-    if (nrows == 0) return cudaSuccess;
-    k_seam_rows<<<blocks_for(nrows, 256), 256, 0, st>>>(seam_flag, seam_pos, row_ptr, run_comp, nrows, seam_row, seam_a,
-                                                        seam_b, cls_parent);
+                      const uint32_t* run_comp, long row_begin, long row_end, uint32_t* seam_row, uint32_t* seam_a,
+                      uint32_t* seam_b, uint32_t* cls_parent, cudaStream_t st) {
+    if (row_end <= row_begin) return cudaSuccess;
+    k_seam_rows<<<blocks_for(row_end - row_begin, 256), 256, 0, st>>>(seam_flag, seam_pos, row_ptr, run_comp, row_begin,
+                                                                      row_end, seam_row, seam_a, seam_b, cls_parent);
     return cudaGetLastError();
 }
 
-cudaError_t cls_flatten(uint32_t* cls_parent, long ncomp, cudaStream_t st) {
-    if (ncomp == 0) return cudaSuccess;
-    k_cls_flatten<<<blocks_for(ncomp, 256), 256, 0, st>>>(cls_parent, ncomp);
+cudaError_t cls_flatten(uint32_t* cls_parent, long begin, long end, cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    k_cls_flatten<<<blocks_for(end - begin, 256), 256, 0, st>>>(cls_parent, begin, end);
     return cudaGetLastError();
 }
 
@@ -1081,11 +1093,11 @@ cudaError_t pairs_init(const PairTable& p, cudaStream_t st) {
 }
 
 cudaError_t pairs_accumulate(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row,
-                             const uint32_t* run_comp, long nruns, int H, const double* w_dev,
+                             const uint32_t* run_comp, long begin, long end, int H, const double* w_dev,
                              const uint8_t* special_dev, const PairTable& p, cudaStream_t st) {
-    if (nruns == 0) return cudaSuccess;
-    k_pairs_accumulate<<<blocks_for(nruns, 256), 256, 0, st>>>(row_ptr, run_x, run_row, run_comp, nruns, H, w_dev,
-                                                               special_dev, p);
+    if (end <= begin) return cudaSuccess;
+    k_pairs_accumulate<<<blocks_for(end - begin, 256), 256, 0, st>>>(row_ptr, run_x, run_row, run_comp, begin, end, H,
+                                                                     w_dev, special_dev, p);
     return cudaGetLastError();
 }
 
@@ -1136,15 +1148,14 @@ cudaError_t zero_fill(int32_t* p, size_t n, int sm_count, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t class_sums(const CompTables& c, const ClassTables& k, long ncomp, cudaStream_t st) {
-    if (ncomp == 0) return cudaSuccess;
-    k_class_sums<<<blocks_for(ncomp, 256), 256, 0, st>>>(c, k, ncomp);
+cudaError_t class_sums(const CompTables& c, const ClassTables& k, long begin, long end, cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    k_class_sums<<<blocks_for(end - begin, 256), 256, 0, st>>>(c, k, begin, end);
     return cudaGetLastError();
 }
 
-cudaError_t pairs_count(const PairTable& p, const uint32_t* cls, const ClassTables& k, uint32_t* pcnt, uint32_t* total,
-                        cudaStream_t st) {
-    k_pairs_count<<<blocks_for(p.cap, 256), 256, 0, st>>>(p, cls, k, pcnt, total);
+cudaError_t pairs_count(const PairTable& p, const uint32_t* cls, const ClassTables& k, uint32_t* pcnt, cudaStream_t st) {
+    k_pairs_count<<<blocks_for(p.cap, 256), 256, 0, st>>>(p, cls, k, pcnt);
     return cudaGetLastError();
 }
 
@@ -1153,17 +1164,17 @@ cudaError_t pairs_fill(const PairTable& p, const uint32_t* pptr, uint32_t* pfill
     return cudaGetLastError();
 }
 
-cudaError_t seg_flags(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, long n, int H, uint32_t* start,
-                      cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    k_seg_flags<<<blocks_for(n, 256), 256, 0, st>>>(srow, sa, sb, n, H, start);
+cudaError_t seg_flags(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, long begin, long end, int H,
+                      uint32_t* start, cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    k_seg_flags<<<blocks_for(end - begin, 256), 256, 0, st>>>(srow, sa, sb, begin, end, H, start);
     return cudaGetLastError();
 }
 
 cudaError_t seg_write(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, const uint32_t* start,
-                      const uint32_t* segpos, long n, int H, const SegTables& o, cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    k_seg_write<<<blocks_for(n, 256), 256, 0, st>>>(srow, sa, sb, start, segpos, n, H, o);
+                      const uint32_t* segpos, long begin, long end, int H, const SegTables& o, cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    k_seg_write<<<blocks_for(end - begin, 256), 256, 0, st>>>(srow, sa, sb, start, segpos, begin, end, H, o);
     return cudaGetLastError();
 }
 
@@ -1187,7 +1198,7 @@ cudaError_t step3_sweep(const Step3Tables& t, long ncomp, long T, double overlap
 cudaError_t link3d(const Step3Tables& t, long ncomp, uint32_t* parent, uint32_t* root_flag, uint32_t* rank,
                    uint32_t* scan_tmp, int32_t* label, cudaStream_t st) {
     if (ncomp == 0) return cudaMemsetAsync(rank, 0, 4, st);
-    k_iota<<<blocks_for(ncomp, 256), 256, 0, st>>>(parent, ncomp);
+    k_iota<<<blocks_for(ncomp, 256), 256, 0, st>>>(parent, 0, ncomp);
     k_link_union<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, parent);
     k_link_roots<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, parent, root_flag);
     cudaError_t e = exclusive_scan_u32(root_flag, rank, ncomp, scan_tmp, st);

@@ -25,35 +25,41 @@ cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st
 cudaError_t row_stats(const uint32_t* bits, long nrows, int W, int Ww, uint32_t* row_cnt, uint32_t* seam_flag,
                       cudaStream_t st);
 
-// out[0..n] = exclusive prefix sums of in[0..n-1] (out[n] = total).  `tmp` needs scan_tmp_elems(n) uint32.
+// The table kernels work on index RANGES [begin, end) of the global row / run / component tables, so that the planes of a
+// cube can be processed in time chunks while later planes are still being thresholded (ct_api.cu: tables_chunk).
+//
+// out[0..n] = base + exclusive prefix sums of in[0..n-1] (out[n] = base + total).  `tmp` needs scan_tmp_elems(n) uint32.
 size_t scan_tmp_elems(long n);
-cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st);
+cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st,
+                               uint32_t base = 0);
 
-cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long nrows, int Ww, uint32_t* run_x,
+// rows [row0, row0 + nrows) of the GLOBAL bit rows / row_ptr -> run_x, run_row (global row numbers) at row_ptr[row]...
+cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww, uint32_t* run_x,
                          uint32_t* run_row, cudaStream_t st);
 
 // 2-D 8-connected components over row-runs (contrack.py:684-687): union-find with the smallest run index as root.
-cudaError_t ccl_init(uint32_t* parent, long nruns, cudaStream_t st);
-cudaError_t ccl_union(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row, long nruns, int H,
-                      uint32_t* parent, cudaStream_t st);
-cudaError_t ccl_flatten(uint32_t* parent, uint32_t* root_flag, long nruns, cudaStream_t st);
-// run_comp[r] = rank[parent[r]]  (rank = exclusive scan of root_flag)
-cudaError_t ccl_assign(const uint32_t* parent, const uint32_t* rank, uint32_t* run_comp, long nruns, cudaStream_t st);
+cudaError_t ccl_init(uint32_t* parent, long begin, long end, cudaStream_t st);
+cudaError_t ccl_union(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row, long begin, long end,
+                      int H, uint32_t* parent, cudaStream_t st);
+cudaError_t ccl_flatten(uint32_t* parent, uint32_t* root_flag, long begin, long end, cudaStream_t st);
+// run_comp[r] = rank[parent[r]]  (rank = base + exclusive scan of root_flag)
+cudaError_t ccl_assign(const uint32_t* parent, const uint32_t* rank, uint32_t* run_comp, long begin, long end,
+                       cudaStream_t st);
 
 struct CompTables {
     int32_t *t, *y0, *y1, *x0, *x1;          // [ncomp]
     double *areaE, *areaS;
     uint32_t *nsp, *cls;
 };
-cudaError_t comp_init(const CompTables& c, long ncomp, int W, cudaStream_t st);
-cudaError_t comp_accumulate(const uint32_t* run_x, const uint32_t* run_row, const uint32_t* run_comp, long nruns, int H,
-                            const double* w_dev, const uint8_t* special_dev, const CompTables& c, cudaStream_t st);
+cudaError_t comp_init(const CompTables& c, long begin, long end, int W, cudaStream_t st);
+cudaError_t comp_accumulate(const uint32_t* run_x, const uint32_t* run_row, const uint32_t* run_comp, long begin, long end,
+                            int H, const double* w_dev, const uint8_t* special_dev, const CompTables& c, cudaStream_t st);
 
 // date-line rows (contrack.py:691-698): list (row, comp at x=0, comp at x=W-1) at position seam_pos[row]; class union
 cudaError_t seam_rows(const uint32_t* seam_flag, const uint32_t* seam_pos, const uint32_t* row_ptr,
-                      const uint32_t* run_comp, long nrows, uint32_t* seam_row, uint32_t* seam_a, uint32_t* seam_b,
-                      uint32_t* cls_parent, cudaStream_t st);
-cudaError_t cls_flatten(uint32_t* cls_parent, long ncomp, cudaStream_t st);
+                      const uint32_t* run_comp, long row_begin, long row_end, uint32_t* seam_row, uint32_t* seam_a,
+                      uint32_t* seam_b, uint32_t* cls_parent, cudaStream_t st);
+cudaError_t cls_flatten(uint32_t* cls_parent, long begin, long end, cudaStream_t st);
 
 struct PairTable {
     unsigned long long* key;                 // [cap] (a << 32) | b, PAIR_EMPTY when free
@@ -61,12 +67,13 @@ struct PairTable {
     double *areaE, *areaS;                   // [cap]
     uint32_t cap;                            // power of two
     uint32_t* overflow;                      // device flag
+    uint32_t* count;                         // device counter: occupied slots (= pairs)
 };
 cudaError_t pairs_init(const PairTable& p, cudaStream_t st);
 // two-timestep intersection (contrack.py:717-719 on tables): for every run of plane t >= 1 the overlapping runs of
 // plane t-1 in the same row; pixel counts and areas accumulate per (comp_t, comp_t-1)
 cudaError_t pairs_accumulate(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row,
-                             const uint32_t* run_comp, long nruns, int H, const double* w_dev,
+                             const uint32_t* run_comp, long begin, long end, int H, const double* w_dev,
                              const uint8_t* special_dev, const PairTable& p, cudaStream_t st);
 // compact occupied slots: out arrays sized >= number of pairs; *count_dev receives the number
 cudaError_t pairs_compact(const PairTable& p, uint32_t* out_a, uint32_t* out_b, uint32_t* out_npix, uint32_t* out_nsp,
@@ -76,17 +83,16 @@ cudaError_t pairs_compact(const PairTable& p, uint32_t* out_a, uint32_t* out_b, 
 struct ClassTables { double *conE, *conS, *fE, *fS; uint32_t *nsp, *fnsp; };   // [ncomp], zero-initialised by caller
 struct PairCsr { uint32_t *b, *npix, *nsp; double *E, *S; };                   // [npair]
 struct SegTables { int32_t *t, *y0, *y1; uint32_t *a, *b; };                   // [nseg <= nseam]
-cudaError_t class_sums(const CompTables& c, const ClassTables& k, long ncomp, cudaStream_t st);
-// pcnt[a]++ per pair, *total = number of pairs, forward sums into the class of b (pcnt, total zeroed by caller)
-cudaError_t pairs_count(const PairTable& p, const uint32_t* cls, const ClassTables& k, uint32_t* pcnt, uint32_t* total,
-                        cudaStream_t st);
+cudaError_t class_sums(const CompTables& c, const ClassTables& k, long begin, long end, cudaStream_t st);
+// pcnt[a]++ per pair, forward sums into the class of b (pcnt zeroed by caller)
+cudaError_t pairs_count(const PairTable& p, const uint32_t* cls, const ClassTables& k, uint32_t* pcnt, cudaStream_t st);
 // pptr = exclusive scan of pcnt; pfill zeroed by caller
 cudaError_t pairs_fill(const PairTable& p, const uint32_t* pptr, uint32_t* pfill, const PairCsr& o, cudaStream_t st);
-cudaError_t seg_flags(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, long n, int H, uint32_t* start,
-                      cudaStream_t st);
-// segpos = exclusive scan of start
+cudaError_t seg_flags(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, long begin, long end, int H,
+                      uint32_t* start, cudaStream_t st);
+// segpos = base + exclusive scan of start
 cudaError_t seg_write(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, const uint32_t* start,
-                      const uint32_t* segpos, long n, int H, const SegTables& o, cudaStream_t st);
+                      const uint32_t* segpos, long begin, long end, int H, const SegTables& o, cudaStream_t st);
 
 cudaError_t zero_fill(int32_t* p, size_t n, int sm_count, cudaStream_t st);
 

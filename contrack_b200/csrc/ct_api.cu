@@ -140,6 +140,9 @@ struct ct_ctx {
     std::vector<cudaEvent_t> ev_chunk;
     long opt_host_sparse = 1;                // host-buffer call: flag travels back as row-runs, not as a dense cube
     long opt_host_threads = 0;               // host threads that zero / paint the host flag cube (0 = automatic)
+    DevBuf lc_st, lc_t, lc_label, lc_npix, lc_roll, lc_out, lc_bitmaps;    // run_lifecycle scratch
+    PinBuf hp_lc;
+    long lc_rows = 0;
     PinBuf hp_runs;                          // row-run table of the last host-buffer call
     DevBuf l_parent, l_flag, l_rank, l_label, l_kept, l_accE, l_accS, l_accN;
     DevBuf b_t0, b_t1, b_y0, b_y1, b_x0, b_x1, b_cnt, b_fill, b_ptr, b_order, b_fin, b_mc, b_ml;
@@ -860,9 +863,10 @@ void ct_destroy(ct_ctx* c) {
                       &c->a_gptr, &c->a_gidx, &c->a_gmean, &c->a_group,
                       &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN,
                       &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
-                      &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml};
+                      &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml,
+                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps};
     for (DevBuf* b : bufs) b->release();
-    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release();
+    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     for (auto& e : c->ev_tbl) if (e) cudaEventDestroy(e);
@@ -1411,6 +1415,129 @@ int ct_shard_paint(ct_ctx* c, const int32_t* comp_val_local, long novr, const in
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats["ms_paint"] = ms;
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats["ms_total"] = ms;
     c->stats["kernel_launches"] = (double)c->launches;
+    return CT_OK;
+}
+
+// ---- run_lifecycle (contrack.py:799-907) ---------------------------------------------------------------------------
+int ct_run_lifecycle(ct_ctx* c, const int32_t* flag_dev, const void* var_dev, int var_dtype, long T, int H, int W,
+                     const double* w_host, long* n_rows, void* stream) {
+    if (!c || !n_rows) return fail(CT_ERR_ARG, "null argument");
+    *n_rows = 0;
+    c->lc_rows = 0;
+    if (T < 0 || H <= 0 || W <= 0) return fail(CT_ERR_ARG, "bad shape T=%ld H=%d W=%d", T, H, W);
+    if (H > 65535 || W > 65535) return fail(CT_ERR_CAPACITY, "H and W must be <= 65535 (got %d x %d)", H, W);
+    if ((double)T * H >= 2147483647.0) return fail(CT_ERR_CAPACITY, "T*H must be < 2^31");
+    if (var_dtype != CT_F32 && var_dtype != CT_F64) return fail(CT_ERR_ARG, "var_dtype must be CT_F32 or CT_F64");
+    if (T == 0) return CT_OK;
+    if (!flag_dev || !var_dev || !w_host) return fail(CT_ERR_ARG, "null pointer");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    c->stats.clear();
+    c->T = T; c->H = H; c->W = W; c->Ww = (W + 31) / 32;
+    c->nruns = c->ncomp = c->npair = 0;                              // the run_contrack tables of this context are gone
+    const long nrows = T * H;
+    const int Ww = c->Ww;
+    auto U = [](DevBuf& b) { return b.as<uint32_t>(); };
+    CT_CUDA(c->w_dev.ensure(H * sizeof(double)));
+    CT_CUDA(cudaMemcpyAsync(c->w_dev.p, w_host, H * sizeof(double), cudaMemcpyHostToDevice, st));
+    CT_CUDA(c->bits.ensure((size_t)nrows * Ww * 4)); CT_CUDA(c->lc_st.ensure((size_t)nrows * Ww * 4));
+    CT_CUDA(c->row_cnt.ensure((size_t)nrows * 4)); CT_CUDA(c->row_ptr.ensure((size_t)(nrows + 1) * 4));
+    CT_CUDA(c->counters.ensure(64)); CT_CUDA(c->hp_counters.ensure(64));
+    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(nrows > 1024 ? nrows : 1024) * 4));
+    uint32_t* cnt_dev = c->counters.as<uint32_t>();
+    uint32_t* cnt_host = c->hp_counters.as<uint32_t>();
+    const double t0_ms = now_ms();
+    for (auto& e : c->ev) if (!e) CT_CUDA(cudaEventCreate(&e));
+    CT_CUDA(cudaEventRecord(c->ev[0], st));
+    CT_CUDA(ctl::lc_rows(flag_dev, nrows, W, Ww, U(c->bits), U(c->lc_st), U(c->row_cnt), c->sm_count, st));
+    CT_CUDA(cudaEventRecord(c->ev[1], st));
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->row_cnt), U(c->row_ptr), nrows, U(c->scan_tmp), st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host, U(c->row_ptr) + nrows, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaStreamSynchronize(st));                              // also: w_host may go away after the call
+    const long R = cnt_host[0];
+    long launches = 4;
+    CT_CUDA(c->run_x.ensure((size_t)(R + 1) * 4)); CT_CUDA(c->run_row.ensure((size_t)(R + 1) * 4));
+    CT_CUDA(c->run_val.ensure((size_t)(R + 1) * 4));
+    CT_CUDA(ctl::lc_extract(flag_dev, U(c->bits), U(c->lc_st), U(c->row_ptr), nrows, W, Ww, U(c->run_x), U(c->run_row),
+                            c->run_val.as<int32_t>(), st));
+    launches += 1;
+    ctl::EntryTable et;
+    uint64_t want = (uint64_t)R / 8 + 1024;
+    for (int attempt = 0;; ++attempt) {
+        et.cap = next_pow2(want);
+        CT_CUDA(c->h_key.ensure((size_t)et.cap * 8)); CT_CUDA(c->h_npix.ensure((size_t)et.cap * 4));
+        CT_CUDA(c->h_nsp.ensure((size_t)et.cap * 4));
+        et.key = c->h_key.as<unsigned long long>(); et.npix = U(c->h_npix); et.flags = U(c->h_nsp);
+        et.overflow = cnt_dev + 4; et.count = cnt_dev + 5; et.nroll = cnt_dev + 6;
+        CT_CUDA(ctl::lc_entries(U(c->run_x), U(c->run_row), c->run_val.as<int32_t>(), R, H, W, et, st));
+        launches += 2;
+        CT_CUDA(cudaMemcpyAsync(cnt_host + 4, cnt_dev + 4, 8, cudaMemcpyDeviceToHost, st));
+        CT_CUDA(cudaStreamSynchronize(st));
+        if (cnt_host[4] == 0 && (uint64_t)cnt_host[5] * 10 <= (uint64_t)et.cap * 7) break;
+        if (attempt >= 8 || et.cap >= (1u << 31)) return fail(CT_ERR_CAPACITY, "lifecycle entry table overflow");
+        want = (uint64_t)et.cap * 4;
+    }
+    const long ne = cnt_host[5];
+    CT_CUDA(c->lc_t.ensure((size_t)(ne + 1) * 4)); CT_CUDA(c->lc_label.ensure((size_t)(ne + 1) * 4));
+    CT_CUDA(c->lc_npix.ensure((size_t)(ne + 1) * 4)); CT_CUDA(c->lc_roll.ensure((size_t)(ne + 1) * 4));
+    CT_CUDA(c->lc_out.ensure((size_t)(ne + 1) * 5 * 8));
+    CT_CUDA(cudaMemsetAsync(cnt_dev + 7, 0, 4, st));
+    CT_CUDA(ctl::lc_compact(et, c->lc_t.as<int32_t>(), c->lc_label.as<int32_t>(), U(c->lc_npix), c->lc_roll.as<int32_t>(),
+                            cnt_dev + 7, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 6, cnt_dev + 6, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaStreamSynchronize(st));
+    const long nroll = cnt_host[6];
+    launches += 1;
+    if (nroll) {
+        CT_CUDA(c->lc_bitmaps.ensure((size_t)nroll * Ww * 4));
+        CT_CUDA(cudaMemsetAsync(c->lc_bitmaps.p, 0, (size_t)nroll * Ww * 4, st));
+        CT_CUDA(ctl::lc_roll(U(c->row_ptr), U(c->run_x), c->run_val.as<int32_t>(), c->lc_t.as<int32_t>(),
+                             c->lc_label.as<int32_t>(), c->lc_roll.as<int32_t>(), ne, H, W, Ww, U(c->lc_bitmaps), st));
+        launches += 1;
+    }
+    double* o = c->lc_out.as<double>();
+    const size_t ne1 = (size_t)ne + 1;
+    CT_CUDA(ctl::lc_sums(U(c->row_ptr), U(c->run_x), U(c->run_row), c->run_val.as<int32_t>(), var_dev, var_dtype == CT_F64,
+                         c->w_dev.as<double>(), c->lc_t.as<int32_t>(), c->lc_label.as<int32_t>(), U(c->lc_npix),
+                         c->lc_roll.as<int32_t>(), ne, H, W, o, o + ne1, o + 2 * ne1, o + 3 * ne1, o + 4 * ne1, st));
+    launches += ne ? 1 : 0;
+    CT_CUDA(cudaEventRecord(c->ev[2], st));
+    // results -> pinned host memory: 5 doubles, then t, label, npix, roll
+    CT_CUDA(c->hp_lc.ensure(ne1 * (5 * 8 + 4 * 4)));
+    char* hp = c->hp_lc.as<char>();
+    if (ne) {
+        CT_CUDA(cudaMemcpyAsync(hp, o, ne1 * 5 * 8, cudaMemcpyDeviceToHost, st));
+        CT_CUDA(cudaMemcpyAsync(hp + ne1 * 40, c->lc_t.p, (size_t)ne * 4, cudaMemcpyDeviceToHost, st));
+        CT_CUDA(cudaMemcpyAsync(hp + ne1 * 44, c->lc_label.p, (size_t)ne * 4, cudaMemcpyDeviceToHost, st));
+        CT_CUDA(cudaMemcpyAsync(hp + ne1 * 48, c->lc_npix.p, (size_t)ne * 4, cudaMemcpyDeviceToHost, st));
+        CT_CUDA(cudaMemcpyAsync(hp + ne1 * 52, c->lc_roll.p, (size_t)ne * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats["ms_lc_rows"] = ms;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats["ms_lc_tables_sums"] = ms;
+    c->stats["ms_total"] = now_ms() - t0_ms;
+    c->stats["runs"] = (double)R; c->stats["lc_rows"] = (double)ne; c->stats["lc_rolled"] = (double)nroll;
+    c->stats["kernel_launches"] = (double)launches;
+    c->lc_rows = ne;
+    *n_rows = ne;
+    return CT_OK;
+}
+
+int ct_lifecycle_fetch(ct_ctx* c, long cap, int32_t* t, int32_t* label, int32_t* npix, int32_t* roll, double* area,
+                       double* wsum, double* norm, double* sy, double* sx) {
+    if (!c) return fail(CT_ERR_ARG, "null context");
+    const long ne = c->lc_rows;
+    if (cap < ne) return fail(CT_ERR_CAPACITY, "capacity %ld < %ld rows", cap, ne);
+    if (ne == 0) return CT_OK;
+    if (!t || !label || !npix || !roll || !area || !wsum || !norm || !sy || !sx) return fail(CT_ERR_ARG, "null pointer");
+    const size_t ne1 = (size_t)ne + 1;
+    const char* hp = c->hp_lc.as<char>();
+    const double* o = reinterpret_cast<const double*>(hp);
+    memcpy(area, o, (size_t)ne * 8); memcpy(wsum, o + ne1, (size_t)ne * 8); memcpy(norm, o + 2 * ne1, (size_t)ne * 8);
+    memcpy(sy, o + 3 * ne1, (size_t)ne * 8); memcpy(sx, o + 4 * ne1, (size_t)ne * 8);
+    memcpy(t, hp + ne1 * 40, (size_t)ne * 4); memcpy(label, hp + ne1 * 44, (size_t)ne * 4);
+    memcpy(npix, hp + ne1 * 48, (size_t)ne * 4); memcpy(roll, hp + ne1 * 52, (size_t)ne * 4);
     return CT_OK;
 }
 

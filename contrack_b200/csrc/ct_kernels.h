@@ -142,3 +142,33 @@ cudaError_t paint_overrides(const int32_t* t, const int32_t* y, const int32_t* x
                             cudaStream_t st);
 
 }  // namespace ctk
+
+// ---- run_lifecycle kernels (ct_lifecycle.cu; reference contrack.py:799-907) -------------------------------------------
+namespace ctl {
+
+struct EntryTable {                          // hash set of (time step << 32 | flag id)
+    unsigned long long* key;                 // [cap], ctk::PAIR_EMPTY when free
+    uint32_t *npix, *flags;                  // [cap] cells; bit 0: touches column 0, bit 1: touches column W-1
+    uint32_t cap;                            // power of two
+    uint32_t *overflow, *count, *nroll;      // device counters
+};
+// flag cube -> non-zero bits / run-start bits [nrows * Ww] and runs per row
+cudaError_t lc_rows(const int32_t* flag, long nrows, int W, int Ww, uint32_t* nz, uint32_t* st, uint32_t* row_cnt,
+                    int sm_count, cudaStream_t stream);
+// -> row-runs in raster order: run_x = x0 | x1 << 16 (x1 exclusive), run_row, run_label (row_ptr = scan of row_cnt)
+cudaError_t lc_extract(const int32_t* flag, const uint32_t* nz, const uint32_t* st, const uint32_t* row_ptr, long nrows,
+                       int W, int Ww, uint32_t* run_x, uint32_t* run_row, int32_t* run_label, cudaStream_t stream);
+cudaError_t lc_entries(const uint32_t* run_x, const uint32_t* run_row, const int32_t* run_label, long nruns, int H, int W,
+                       const EntryTable& e, cudaStream_t stream);
+// occupied slots -> entry arrays (any order); out_roll = -1, or -(bitmap slot + 2) for entries that lc_roll must resolve
+cudaError_t lc_compact(const EntryTable& e, int32_t* out_t, int32_t* out_label, uint32_t* out_npix, int32_t* out_roll,
+                       uint32_t* fill_zeroed, cudaStream_t stream);
+cudaError_t lc_roll(const uint32_t* row_ptr, const uint32_t* run_x, const int32_t* run_label, const int32_t* ent_t,
+                    const int32_t* ent_label, int32_t* ent_roll, long nent, int H, int W, int Ww, uint32_t* bitmaps_zeroed,
+                    cudaStream_t stream);
+cudaError_t lc_sums(const uint32_t* row_ptr, const uint32_t* run_x, const uint32_t* run_row, const int32_t* run_label,
+                    const void* var, int var_is_f64, const double* w, const int32_t* ent_t, const int32_t* ent_label,
+                    const uint32_t* ent_npix, const int32_t* ent_roll, long nent, int H, int W, double* out_area,
+                    double* out_int, double* out_norm, double* out_sy, double* out_sx, cudaStream_t stream);
+
+}  // namespace ctl

@@ -17,7 +17,8 @@ _STAT_KEYS = ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d',
               'ms_tables_gpu', 'ms_tables_host_roundtrip', 'ms_host_tables', 'ms_paint', 'ms_total', 'ms_h2d_threshold',
               'ms_tables', 'ms_paint_d2h', 'ms_zero_fill', 'seam_segments', 'sweeps', 'neartie_flagged', 'h2d_bytes',
               'd2h_bytes', 'host_sparse', 'host_threads', 'chunks', 'ms_h_chunks', 'ms_h_global', 'ms_g_sweeps', 'ms_g_link',
-              'ms_g_labels_d2h', 'ms_tables_after_threshold', 'moved_comps')
+              'ms_g_labels_d2h', 'ms_tables_after_threshold', 'moved_comps', 'ms_lc_rows', 'ms_lc_tables_sums', 'lc_rows',
+              'lc_rolled')
 
 
 def _is_torch(x):
@@ -150,6 +151,47 @@ class Engine(object):
                                          int(ngroups), C.c_void_p(cd.data_ptr()), int(smooth), C.c_void_p(outd.data_ptr()),
                                          C.c_void_p(stream)))
         return outd.cpu().numpy() if was_host else outd
+
+    # ------------------------------------------------------------------------------------------------------------
+    def run_lifecycle(self, flag, var, w):
+        """flag [T,H,W] integer, var [T,H,W] float32/float64 (numpy or torch CUDA, C-order time/lat/lon), w [H] float64 row
+        weights.  Returns a dict of numpy arrays with one entry per (time step, flag id) in no particular order -- see
+        ct_run_lifecycle in include/contrack_b200.h (contrack.py:799-907)."""
+        import torch
+        dev = 'cuda:%d' % self.device
+
+        def to_dev(x, dtypes, default):
+            if _is_torch(x):
+                if not x.is_cuda:
+                    raise ValueError('torch input must live on a CUDA device (pass numpy for host data)')
+                t = x
+            else:
+                a = np.asarray(x)
+                t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            if t.dtype not in dtypes:
+                t = t.to(default)
+            return t.contiguous()
+        fd = to_dev(flag, (torch.int32,), torch.int32)
+        vd = to_dev(var, (torch.float32, torch.float64), torch.float64)
+        if fd.shape != vd.shape or fd.dim() != 3:
+            raise ValueError('flag and variable must both have shape (time, lat, lon)')
+        T, H, W = (int(s) for s in fd.shape)
+        w = np.ascontiguousarray(w, np.float64)
+        if w.shape != (H,):
+            raise ValueError('weights must have shape (H,)')
+        n = C.c_long(0)
+        stream = torch.cuda.current_stream(fd.device).cuda_stream
+        _lib.check(self.lib.ct_run_lifecycle(self.handle, C.c_void_p(fd.data_ptr()), C.c_void_p(vd.data_ptr()),
+                                             _lib.CT_F64 if vd.dtype == torch.float64 else _lib.CT_F32, T, H, W,
+                                             _lib.ptr(w, _lib._f64p), C.byref(n), C.c_void_p(stream)))
+        n = n.value
+        out = {k: np.zeros(n, np.int32) for k in ('t', 'label', 'npix', 'roll')}
+        out.update({k: np.zeros(n, np.float64) for k in ('area', 'wsum', 'norm', 'sy', 'sx')})
+        _lib.check(self.lib.ct_lifecycle_fetch(self.handle, n, *[_lib.ptr(out[k], _lib._i32p) for k in
+                                                                  ('t', 'label', 'npix', 'roll')],
+                                               *[_lib.ptr(out[k], _lib._f64p) for k in
+                                                 ('area', 'wsum', 'norm', 'sy', 'sx')]))
+        return out
 
 
 __all__ = ['Engine', 'ContrackLibError']

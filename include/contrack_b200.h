@@ -199,6 +199,22 @@ int ct_shard_plane_runs(ct_ctx* ctx, long local_plane, long* n, const int32_t** 
 int ct_shard_paint(ct_ctx* ctx, const int32_t* comp_val_local, long novr, const int32_t* ovr_t, const int32_t* ovr_y,
                    const int32_t* ovr_x0, const int32_t* ovr_x1, const int32_t* ovr_val, int32_t* flag_dev, void* stream);
 
+/* ---- run_lifecycle, contrack.py:799-907 -------------------------------------------------------------------------------
+ * flag_dev [T,H,W] int32 (ds[flag]), var_dev [T,H,W] float32/float64 (ds[variable]), w_host [H] the float32-valued area
+ * weights of contrack.py:847-848.  One result row per (time step, flag id != 0) that occurs in the cube, in no particular
+ * order (the caller sorts like contrack.py:907).  Every sum is accumulated in the order the reference's numpy / scipy calls
+ * use, so the float64 values are the reference's bit for bit:
+ *   area  = np.sum(weight_grid[flag[t] == id])                       (contrack.py:874, numpy pairwise order)
+ *   wsum  = np.sum(weight_grid[m] * variable[t][m])                   (contrack.py:875; intensity = wsum / area)
+ *   norm, sy, sx = the three sums of scipy.ndimage.center_of_mass(variable * weight_grid, flag, [id]) (contrack.py:886,
+ *           892): sequential np.bincount order over the plane rolled by -roll columns; centre = (sy / norm, sx / norm)
+ *   roll  = lon_roll of contrack.py:882-883 if the id touches both the first and the last longitude column, else -1
+ * Results stay in the context until the next call; ct_lifecycle_fetch copies them out (cap >= *n_rows). */
+int ct_run_lifecycle(ct_ctx* ctx, const int32_t* flag_dev, const void* var_dev, int var_dtype, long T, int H, int W,
+                     const double* w_host, long* n_rows, void* stream);
+int ct_lifecycle_fetch(ct_ctx* ctx, long cap, int32_t* t, int32_t* label, int32_t* npix, int32_t* roll, double* area,
+                       double* wsum, double* norm, double* sy, double* sx);
+
 /* special_out[y] = 0 if row y belongs to the set of rows whose weights sum exactly in float64 in any order (areas of
  * those rows accumulate in areaE and equal numpy's np.sum bit for bit), 1 otherwise (pole rows: areaS, nsp). */
 void ct_classify_rows(const double* w_host, int H, int W, uint8_t* special_out);

@@ -216,3 +216,63 @@ def calc_anom(z, groups, window=1, smooth=1):
     idx = np.searchsorted(keys, groups)
     dev = z - clim[idx]
     return _rolling_mean_centered(dev, smooth)
+
+
+def strftime_ymd_h(time_values):
+    """``ds[time].dt.strftime('%Y%m%d_%H')`` (contrack.py:862) for a datetime64 vector."""
+    t = np.asarray(time_values).astype('datetime64[h]')
+    out = []
+    for v in t:
+        s = str(v)                                   # 'YYYY-MM-DDTHH'
+        out.append(s[0:4] + s[5:7] + s[8:10] + '_' + s[11:13])
+    return out
+
+
+def run_lifecycle(flag, var, lat, lon, time_values, force=False):
+    """Restatement of contrack.py:799-907 on plain arrays: per (time step, flag id) size, area-weighted intensity and
+    centre of mass (with the longitude roll for contours that touch both the first and the last column).  Same numpy /
+    scipy calls as the reference (np.unique, np.sum over boolean-masked arrays, ndimage.center_of_mass, np.roll for
+    xarray's .roll(roll_coords=True)).  Returns the sorted list of tuples that the reference feeds to pd.DataFrame
+    (columns Flag, Date, Longitude, Latitude, Intensity, Size)."""
+    flag = np.asarray(flag)
+    var = np.asarray(var)
+    lat = np.asarray(lat)
+    lon = np.asarray(lon)
+    T, H, W = flag.shape
+    dlat, dlon = resolution(lat, force, 'latitude'), resolution(lon, force, 'longitude')
+    weight_lat = np.cos(lat * np.pi / 180)                                                      # contrack.py:847
+    wgrid = np.ones((H, W)) * np.array((111 * dlat * 111 * dlon * weight_lat)).astype(np.float32)[:, None]
+    dates = strftime_ymd_h(time_values)
+    block_id, time, intensity, size, com_lon, com_lat = [], [], [], [], [], []
+    for i_time in range(T):                                                                     # contrack.py:860
+        currentstep = dates[i_time]
+        f = flag[i_time]
+        v = var[i_time]
+        labels = np.unique(f)
+        labels = labels[labels != 0]
+        if len(labels) == 0:
+            continue
+        for label in labels:
+            areacon = np.sum(wgrid[f == label])                                                 # contrack.py:874
+            intensitycon = np.sum(wgrid[f == label] * v[f == label])
+            intensitycon = intensitycon / areacon
+            if label in f[:, 0] and label in f[:, -1]:                                          # contrack.py:880
+                yloc, xloc = np.where(f == label)
+                lon_roll = np.unique(xloc)[np.argmax(np.diff(np.unique(xloc))) + 1]
+                flag_roll = np.roll(f, -lon_roll, axis=1)
+                variable_roll = np.roll(v, -lon_roll, axis=1)
+                lon_rolled = np.roll(lon, -lon_roll)
+                center_of_mass = ndimage.center_of_mass(variable_roll * wgrid, flag_roll, [label])
+                comlatcon = int(lat[int(center_of_mass[0][0])])
+                comloncon = int(lon_rolled[int(center_of_mass[0][1])])
+            else:
+                center_of_mass = ndimage.center_of_mass(v * wgrid, f, [label])
+                comlatcon = int(lat[int(center_of_mass[0][0])])
+                comloncon = int(lon[int(center_of_mass[0][1])])
+            block_id.append(label)
+            time.append(str(currentstep))
+            intensity.append(round(intensitycon, 2))
+            size.append(round(areacon, 2))
+            com_lon.append(comloncon)
+            com_lat.append(comlatcon)
+    return sorted(list(zip(block_id, time, com_lon, com_lat, intensity, size)), key=lambda x: (x[0], x[1]))

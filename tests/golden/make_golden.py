@@ -8,6 +8,7 @@
    fixture and on seeded synthetic cubes: sha256 of the flag array as C-order '<i4', the ids, non-zero cell count.
    The four fixture rows are the values SURVEY.md section 8(c) recorded independently.
 3. flags_*.npz     -- full expected flag arrays (compressed) for the fixture cases.
+4. lifecycle_fixture.json -- the run_lifecycle table of the reference test's run on the fixture.
 """
 import hashlib, json, os, sys
 import numpy as np
@@ -49,6 +50,14 @@ def main():
                                     t_id_pairs=int(sum(len(np.unique(f[t])) - 1 for t in range(f.shape[0]))),
                                     sha256=sha(f)))
     np.savez_compressed(os.path.join(HERE, 'flags_fixture.npz'), **flags)
+
+    # run_lifecycle (contrack.py:799-907) on the reference test's own run (tests/test_contrack.py:93-103: 28 rows, 3 flags)
+    rows = oracle.run_lifecycle(flags['thr150_ov05_p5_one'], a, lat, lon, time)
+    assert len(rows) == 28 and len({r[0] for r in rows}) == 3
+    json.dump({'source': 'oracle.run_lifecycle on the reference fixture, run_contrack(150, >=, 0.5, 5, twosided=False); '
+                         'Intensity/Size as float.hex()',
+               'rows': [[int(r[0]), r[1], int(r[2]), int(r[3]), float(r[4]).hex(), float(r[5]).hex()] for r in rows]},
+              open(os.path.join(HERE, 'lifecycle_fixture.json'), 'w'), indent=0)
 
     # BASELINE.json configs[0]: synthetic 30x91x180, threshold 160, overlap 0.5, persistence 5, twosided
     for seed, T, H, W, sig, thr, gorl, ov, pers, two in [

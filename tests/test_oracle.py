@@ -63,3 +63,18 @@ def test_rolling_mean_convention():
     assert np.isnan(r2[0]) and np.allclose(r2[1:], [0.5, 1.5, 2.5, 3.5, 4.5])
     r3 = oracle._rolling_mean_centered(x, 3)[:, 0]
     assert np.isnan(r3[0]) and np.isnan(r3[-1]) and np.allclose(r3[1:-1], [1, 2, 3, 4])
+
+
+def test_lifecycle_reference_pins_and_golden(fixture_cube):
+    """reference tests/test_contrack.py:93-103: 3 unique flags, 28 rows; plus the committed table of this restatement."""
+    import json
+    import os
+    a, lat, lon = fixture_cube
+    time = np.datetime64('2016-10-02') + np.arange(11).astype('timedelta64[D]')
+    f = oracle.run_contrack(a, lat, lon, 150, '>=', 0.5, 5, twosided=False)
+    rows = oracle.run_lifecycle(f, a, lat, lon, time)
+    assert len(rows) == 28 and len({r[0] for r in rows}) == 3
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'lifecycle_fixture.json')))['rows']
+    got = [[int(r[0]), r[1], int(r[2]), int(r[3]), float(r[4]).hex(), float(r[5]).hex()] for r in rows]
+    assert got == gold
+    assert rows == sorted(rows, key=lambda x: (x[0], x[1]))

@@ -10,10 +10,14 @@ the xarray wrapper (``xr.where`` -> ``np.where``, ``ds[...]`` -> plain arrays) a
 compiled code the reference calls: ``scipy.ndimage.label`` / ``scipy.ndimage.find_objects`` (scipy is unpinned in
 the reference's requirements.txt:2; this image has scipy 1.18.1) and numpy.
 
-Parity status: "weakly pinned".  The reference's own tests pin only counts on its fixture
-(tests/test_contrack.py:83-103: 3 features, 28 lifecycle rows); ``tests/test_oracle.py`` checks those, plus the
-full-array sha256 values recorded in SURVEY.md section 8(c).  calc_clim/calc_anom: parity unpinned (the reference
-tests only check type/dims of calc_clim; xarray is not available to generate outputs).
+Parity status: PINNED for run_contrack / run_lifecycle.  The reference's own tests hold only counts on its fixture
+(tests/test_contrack.py:83-103: 3 features, 28 lifecycle rows); beyond those, tests/golden/make_reference_golden.py runs
+the UNMODIFIED reference source in the build container (under tests/golden/xr_shim, a stand-in for the labelled-array
+plumbing of xarray only) and records the sha256 of every flag cube and every lifecycle table it produces
+(tests/golden/reference_run.json: the fixture with 4 parameter sets, 9 synthetic runs, 14 stale-box quirk cubes, a
+non-default dimension order).  ``tests/test_oracle.py`` holds this restatement to all of them, bit for bit.
+calc_clim / calc_anom: pinned through pandas (the shim implements groupby / rolling with pandas, an interpretation of
+xarray's semantics, not xarray itself) within rtol 1e-5 / atol 4e-3 -- treat as "partially pinned".
 """
 from __future__ import annotations
 

@@ -25,3 +25,11 @@ def fixture_cube():
     import numpy as np
     d = np.load(os.path.join(ROOT, 'tests', 'golden', 'anom_test.npz'))
     return d['anom'], d['latitude'], d['longitude']
+
+
+@pytest.fixture(scope='session')
+def reference_run():
+    """Results of the unmodified reference source (tests/golden/make_reference_golden.py)."""
+    import json
+    with open(os.path.join(ROOT, 'tests', 'golden', 'reference_run.json')) as f:
+        return json.load(f)

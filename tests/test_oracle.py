@@ -78,3 +78,64 @@ def test_lifecycle_reference_pins_and_golden(fixture_cube):
     got = [[int(r[0]), r[1], int(r[2]), int(r[3]), float(r[4]).hex(), float(r[5]).hex()] for r in rows]
     assert got == gold
     assert rows == sorted(rows, key=lambda x: (x[0], x[1]))
+
+
+# ---- pins made by the UNMODIFIED reference source executing in the build container (tests/golden/reference_run.json,
+# ---- written by tests/golden/make_reference_golden.py under the xarray stand-in tests/golden/xr_shim) ----------------
+
+def _times(n, start='2000-01-01'):
+    return (np.datetime64(start) + np.arange(n).astype('timedelta64[D]')).astype('datetime64[ns]')
+
+
+def _thr(r):
+    return np.float64(r['threshold']) if r.get('threshold_is_np_float64') else (
+        int(r['threshold']) if float(r['threshold']).is_integer() else r['threshold'])
+
+
+def _life(rows):
+    return [[int(r[0]), r[1], int(r[2]), int(r[3]), float(r[4]).hex(), float(r[5]).hex()] for r in rows]
+
+
+def test_reference_run_fixture(fixture_cube, reference_run):
+    a, lat, lon = fixture_cube
+    time = _times(11, '2016-10-02')
+    for r in reference_run['fixture']:
+        f = oracle.run_contrack(a, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
+        assert sha_i4(f) == r['sha256'], r['key']
+        assert str(f.dtype) == r['dtype']
+        assert _life(oracle.run_lifecycle(f, a, lat, lon, time)) == r['lifecycle'], r['key']
+
+
+def test_reference_run_synthetic(reference_run):
+    for r in reference_run['synthetic']:
+        T, H, W = r['shape']
+        x = synth_cube(r['seed'], T, H, W, tuple(r['sigma']))
+        lat, lon = regular_grid(H, W)
+        f = oracle.run_contrack(x, lat, lon, _thr(r), r['gorl'], r['overlap'], r['persistence'], r['twosided'], force=True)
+        assert sha_i4(f) == r['sha256'], r
+        assert _life(oracle.run_lifecycle(f, x, lat, lon, _times(T), force=True)) == r['lifecycle']
+
+
+def test_reference_run_quirk(reference_run):
+    for r in reference_run['quirk']:
+        T, H, W = r['shape']
+        x = synth_cube(r['seed'], T, H, W, tuple(r['sigma']))
+        lat, lon = regular_grid(H, W)
+        f = oracle.run_contrack(x, lat, lon, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'],
+                                force=True)
+        assert sha_i4(f) == r['sha256'], r['seed']
+
+
+def test_reference_run_calc_clim_anom(reference_run):
+    """pandas-backed pin (the shim's groupby / rolling are an interpretation of xarray): float32, 1e-5 relative."""
+    import os
+    from contrack_b200.contrack import time_group_keys
+    for r in reference_run['anom']:
+        d = np.load(os.path.join(os.path.dirname(__file__), 'golden', r['file']))
+        g = time_group_keys(d['time'], r['groupby'])
+        keys, clim = oracle.calc_clim(d['z'], g, r['window'])
+        assert list(clim.shape) == r['clim_shape']
+        np.testing.assert_allclose(clim, d['clim'], rtol=1e-5, atol=4e-3)
+        an = oracle.calc_anom(d['z'], g, r['window'], r['smooth'])
+        assert np.array_equal(np.isnan(an), np.isnan(d['anom']))
+        np.testing.assert_allclose(an, d['anom'], rtol=1e-5, atol=4e-3)

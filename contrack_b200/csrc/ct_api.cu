@@ -22,6 +22,7 @@
 
 #include "ct_host.h"
 #include "ct_kernels.h"
+#include "ct_shard.h"
 #include "ct_tables.h"
 
 namespace cta {
@@ -157,6 +158,11 @@ struct ct_ctx {
     std::map<std::string, double> stats;
     std::vector<double> w_host;
     long launches = 0;
+    // time-sharded run: packed tables of all ranks -> global tables (ct_global_merge), plane runs served by the caller
+    DevBuf sh_desc;
+    PinBuf hp_desc;
+    ct_plane_runs_fn fetch_fn = nullptr;
+    void* fetch_user = nullptr;
 };
 
 namespace {
@@ -187,6 +193,21 @@ struct DeviceRunSource : cth::RunSource {
             while (rp[y + 1] - r0 <= i) ++y;
             out[i] = cth::PlaneRun{y, (int)(rx[i] & 0xffff), (int)(rx[i] >> 16), rc[i]};
         }
+        return true;
+    }
+};
+
+// Plane runs served by the caller (time-sharded run: the plane may live on another rank); component ids are global.
+struct CallbackRunSource : cth::RunSource {
+    ct_plane_runs_fn fn; void* user;
+    bool plane_runs(long t, std::vector<cth::PlaneRun>& out) override {
+        out.clear();
+        long n = 0;
+        const int32_t *y = nullptr, *x0 = nullptr, *x1 = nullptr;
+        const uint32_t* comp = nullptr;
+        if (!fn || fn(user, t, &n, &y, &x0, &x1, &comp) != 0) return false;
+        out.resize((size_t)n);
+        for (long i = 0; i < n; ++i) out[i] = cth::PlaneRun{y[i], x0[i], x1[i], comp[i]};
         return true;
     }
 };
@@ -686,8 +707,11 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
             ctb::LabelTables lt;
             lt.nlabel = (int)nlab; lt.t0 = h_t0; lt.t1 = h_t1; lt.y0 = h_y0; lt.y1 = h_y1; lt.x0 = h_x0; lt.x1 = h_x1;
             lt.lptr = h_lptr; lt.lorder = h_lorder;
-            DeviceRunSource src;
-            src.c = c; src.st = st;
+            DeviceRunSource dsrc;
+            dsrc.c = c; dsrc.st = st;
+            CallbackRunSource csrc;
+            csrc.fn = c->fetch_fn; csrc.user = c->fetch_user;
+            cth::RunSource& src = c->fetch_fn ? static_cast<cth::RunSource&>(csrc) : static_cast<cth::RunSource&>(dsrc);
             struct Fetch : ctb::RunFetcher {
                 cth::RunSource* src; const int32_t* comp_t; std::vector<cth::PlaneRun> buf;
                 bool fetch(long comp, std::vector<ctb::SubRun>& out) override {
@@ -771,13 +795,16 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
     const double t_host0 = now_ms();
     cth::Params pr;
     pr.overlap = overlap; pr.persistence = persistence; pr.twosided = twosided; pr.stage = stage;
-    DeviceRunSource src;
-    src.c = c; src.st = st;
+    DeviceRunSource dsrc;
+    dsrc.c = c; dsrc.st = st;
+    CallbackRunSource csrc;
+    csrc.fn = c->fetch_fn; csrc.user = c->fetch_user;
+    cth::RunSource* src = c->fetch_fn ? static_cast<cth::RunSource*>(&csrc) : static_cast<cth::RunSource*>(&dsrc);
     CT_CUDA(c->hp_val.ensure((size_t)(nc + 1) * 4));
     int32_t* hv = c->hp_val.as<int32_t>();
     cth::Result& res = c->host_result;
     std::string err;
-    int rc = cth::host_phase_fast(tb, pr, &src, hv, res, err);
+    int rc = cth::host_phase_fast(tb, pr, src, hv, res, err);
     if (rc != 0) return fail(rc, "%s", err.c_str());
     c->stats["ms_host_tables"] = now_ms() - t_host0;
 
@@ -864,9 +891,9 @@ void ct_destroy(ct_ctx* c) {
                       &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN,
                       &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
                       &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml,
-                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps};
+                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc};
     for (DevBuf* b : bufs) b->release();
-    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release();
+    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release(); c->hp_desc.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     for (auto& e : c->ev_tbl) if (e) cudaEventDestroy(e);
@@ -1415,6 +1442,216 @@ int ct_shard_paint(ct_ctx* c, const int32_t* comp_val_local, long novr, const in
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats["ms_paint"] = ms;
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats["ms_total"] = ms;
     c->stats["kernel_launches"] = (double)c->launches;
+    return CT_OK;
+}
+
+// ---- time-sharded run, device-resident tables ------------------------------------------------------------------------
+// counts8 = {0 (caller fills in t_shift), components, halo components, pairs, date-line segments, pairs of the halo
+//            components, segments of the halo plane, components of the last plane}
+int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts8, long* export_bytes) {
+    if (!c || !counts8 || !export_bytes) return fail(CT_ERR_ARG, "null argument");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    c->zero_started_for = nullptr;
+    int rc;
+    cudaStream_t ts = st;
+    if (flag_dev && c->opt_overlap_zero) {
+        if ((rc = ensure_streams(c)) != CT_OK) return rc;
+        CT_CUDA(cudaEventRecord(c->ev_side[0], st));
+        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+        CT_CUDA(cudaStreamWaitEvent(c->tbl_stream, c->ev_side[0], 0));
+        CT_CUDA(ctk::zero_fill(flag_dev, (size_t)(c->T - c->has_prev) * c->H * c->W, c->sm_count, c->side_stream));
+        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+        c->launches += 1;
+        c->zero_started_for = flag_dev;
+        ts = c->tbl_stream;
+    }
+    if ((rc = tables_build(c, ts)) != CT_OK) return rc;
+    uint32_t* cnt_dev = c->counters.as<uint32_t>();
+    uint32_t* cnt_host = c->hp_counters.as<uint32_t>();
+    CT_CUDA(cts::shard_counts(c->c_t.as<int32_t>(), c->ncomp, c->pptr.as<uint32_t>(), c->g_t.as<int32_t>(), c->nseg,
+                              c->has_prev, c->T - 1, cnt_dev + 12, ts));
+    c->launches += 1;
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 12, cnt_dev + 12, 16, cudaMemcpyDeviceToHost, ts));
+    CT_CUDA(cudaStreamSynchronize(ts));
+    c->halo_comps = cnt_host[12];
+    counts8[0] = 0; counts8[1] = c->ncomp; counts8[2] = cnt_host[12]; counts8[3] = c->npair; counts8[4] = c->nseg;
+    counts8[5] = cnt_host[13]; counts8[6] = cnt_host[14]; counts8[7] = cnt_host[15];
+    size_t off[cts::A_COUNT];
+    *export_bytes = (long)cts::layout(c->ncomp, c->npair, c->nseg, off);
+    return CT_OK;
+}
+
+int ct_shard_export_tables(ct_ctx* c, void* dst_dev, long cap_bytes, void* stream) {
+    if (!c || !dst_dev) return fail(CT_ERR_ARG, "null argument");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->zero_started_for ? c->tbl_stream : (cudaStream_t)stream;
+    size_t off[cts::A_COUNT];
+    const long nc = c->ncomp, np = c->npair, ns = c->nseg;
+    if ((long)cts::layout(nc, np, ns, off) > cap_bytes) return fail(CT_ERR_ARG, "export buffer too small");
+    char* d = (char*)dst_dev;
+    struct Src { int k; const DevBuf* b; long n; int elt; };
+    const Src src[] = {{cts::A_T, &c->c_t, nc, 4}, {cts::A_Y0, &c->c_y0, nc, 4}, {cts::A_Y1, &c->c_y1, nc, 4},
+                       {cts::A_X0, &c->c_x0, nc, 4}, {cts::A_X1, &c->c_x1, nc, 4}, {cts::A_CLS, &c->c_cls, nc, 4},
+                       {cts::A_CONE, &c->k_conE, nc, 8}, {cts::A_CONS, &c->k_conS, nc, 8}, {cts::A_FE, &c->k_fE, nc, 8},
+                       {cts::A_FS, &c->k_fS, nc, 8}, {cts::A_NSP, &c->k_nsp, nc, 4}, {cts::A_FNSP, &c->k_fnsp, nc, 4},
+                       {cts::A_PPTR, &c->pptr, nc + 1, 4}, {cts::A_PB, &c->p_b, np, 4}, {cts::A_PNPIX, &c->p_npix, np, 4},
+                       {cts::A_PNSP, &c->p_nsp, np, 4}, {cts::A_PE, &c->p_E, np, 8}, {cts::A_PS, &c->p_S, np, 8},
+                       {cts::A_GT, &c->g_t, ns, 4}, {cts::A_GY0, &c->g_y0, ns, 4}, {cts::A_GY1, &c->g_y1, ns, 4},
+                       {cts::A_GA, &c->g_a, ns, 4}, {cts::A_GB, &c->g_b, ns, 4}};
+    for (const Src& a : src) {
+        if (a.k == cts::A_PPTR && nc == 0) { CT_CUDA(cudaMemsetAsync(d + off[a.k], 0, 4, st)); continue; }
+        if (a.n > 0) CT_CUDA(cudaMemcpyAsync(d + off[a.k], a.b->p, (size_t)a.n * a.elt, cudaMemcpyDeviceToDevice, st));
+    }
+    // the collective that follows runs on the caller's stream
+    if (st != (cudaStream_t)stream) {
+        CT_CUDA(cudaEventRecord(c->ev_tbl[1], st));
+        CT_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_tbl[1], 0));
+    }
+    return CT_OK;
+}
+
+int ct_global_merge(ct_ctx* g, int nranks, const long* counts, const void* gathered_dev, long stride_bytes, long T_total,
+                    int H, int W, const double* w_host, void* stream) {
+    if (!g || !counts || !gathered_dev || !w_host || nranks < 1) return fail(CT_ERR_ARG, "null argument");
+    if (T_total <= 0 || H <= 0 || W <= 0 || H > 65535 || W > 65535) return fail(CT_ERR_ARG, "bad shape");
+    CT_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    g->stats.clear();
+    g->T = T_total; g->H = H; g->W = W; g->Ww = (W + 31) / 32;
+    g->w_host.assign(w_host, w_host + H);
+    {
+        std::vector<uint8_t> special;
+        classify_rows(w_host, H, W, special);
+        g->special_uniform = special_rows_uniform(w_host, special);
+    }
+    CT_CUDA(g->counters.ensure(64));
+    CT_CUDA(g->hp_counters.ensure(64));
+    for (auto& e : g->ev) if (!e) CT_CUDA(cudaEventCreate(&e));
+    g->launches = 0;
+    g->has_prev = 0; g->nruns = 0; g->nseam = 0; g->novr = 0;
+    // ---- per-rank descriptors ----
+    CT_CUDA(g->hp_desc.ensure((size_t)nranks * (sizeof(cts::RankDesc) + 3 * sizeof(long)) + 64));
+    cts::RankDesc* hd = g->hp_desc.as<cts::RankDesc>();
+    long* hb = reinterpret_cast<long*>(hd + nranks);
+    long NC = 0, NP = 0, NS = 0;
+    for (int r = 0; r < nranks; ++r) {
+        const long* k = counts + 8 * r;
+        cts::RankDesc& d = hd[r];
+        d.t_shift = k[0]; d.nc = k[1]; d.nh = k[2]; d.np = k[3]; d.ns = k[4]; d.e0 = k[5]; d.ns_h = k[6];
+        if (d.nc < 0 || d.nh < 0 || d.nh > d.nc || d.e0 < 0 || d.e0 > d.np || d.ns_h < 0 || d.ns_h > d.ns)
+            return fail(CT_ERR_ARG, "rank %d: inconsistent table counts", r);
+        if (r == 0 && d.nh) return fail(CT_ERR_ARG, "rank 0 cannot have halo components");
+        if (r > 0 && counts[8 * (r - 1) + 7] != d.nh)
+            return fail(CT_ERR_INTERNAL, "rank %d sees %ld components in its halo plane, rank %d has %ld in its last plane",
+                        r, d.nh, r - 1, counts[8 * (r - 1) + 7]);
+        d.src = (size_t)r * (size_t)stride_bytes;
+        if ((long)cts::layout(d.nc, d.np, d.ns, d.off) > stride_bytes) return fail(CT_ERR_ARG, "rank %d: stride too small", r);
+        d.comp_base = NC; d.pair_base = NP; d.seg_base = NS;
+        hb[r] = NC; hb[nranks + r] = NP; hb[2 * nranks + r] = NS;
+        NC += d.nc - d.nh; NP += d.np - d.e0; NS += d.ns - d.ns_h;
+    }
+    if (NC >= 2147483647L || NP >= 2147483647L) return fail(CT_ERR_CAPACITY, "global tables exceed 2^31 entries");
+    const size_t desc_bytes = (size_t)nranks * (sizeof(cts::RankDesc) + 3 * sizeof(long));
+    CT_CUDA(g->sh_desc.ensure(desc_bytes));
+    CT_CUDA(cudaMemcpyAsync(g->sh_desc.p, hd, desc_bytes, cudaMemcpyHostToDevice, st));
+    // ---- global tables ----
+    {
+        DevBuf* b4[] = {&g->c_t, &g->c_y0, &g->c_y1, &g->c_x0, &g->c_x1, &g->c_cls, &g->c_val, &g->k_nsp, &g->k_fnsp, &g->pptr};
+        DevBuf* b8[] = {&g->k_conE, &g->k_conS, &g->k_fE, &g->k_fS};
+        for (DevBuf* b : b4) CT_CUDA(b->ensure((size_t)(NC + 3) * 4));
+        for (DevBuf* b : b8) CT_CUDA(b->ensure((size_t)(NC + 3) * 8));
+        DevBuf* p4[] = {&g->p_b, &g->p_npix, &g->p_nsp};
+        DevBuf* p8[] = {&g->p_E, &g->p_S};
+        for (DevBuf* b : p4) CT_CUDA(b->ensure((size_t)(NP + 2) * 4));
+        for (DevBuf* b : p8) CT_CUDA(b->ensure((size_t)(NP + 2) * 8));
+        DevBuf* s4[] = {&g->g_t, &g->g_y0, &g->g_y1, &g->g_a, &g->g_b};
+        for (DevBuf* b : s4) CT_CUDA(b->ensure((size_t)(NS + 3) * 4));
+        CT_CUDA(g->run_val.ensure(16));
+    }
+    cts::GlobalTables gt;
+    gt.t = g->c_t.as<int32_t>(); gt.y0 = g->c_y0.as<int32_t>(); gt.y1 = g->c_y1.as<int32_t>();
+    gt.x0 = g->c_x0.as<int32_t>(); gt.x1 = g->c_x1.as<int32_t>(); gt.cls = g->c_cls.as<uint32_t>();
+    gt.conE = g->k_conE.as<double>(); gt.conS = g->k_conS.as<double>(); gt.fE = g->k_fE.as<double>();
+    gt.fS = g->k_fS.as<double>(); gt.nsp = g->k_nsp.as<uint32_t>(); gt.fnsp = g->k_fnsp.as<uint32_t>();
+    gt.pptr = g->pptr.as<uint32_t>();
+    gt.p_b = g->p_b.as<uint32_t>(); gt.p_npix = g->p_npix.as<uint32_t>(); gt.p_nsp = g->p_nsp.as<uint32_t>();
+    gt.p_E = g->p_E.as<double>(); gt.p_S = g->p_S.as<double>();
+    gt.g_t = g->g_t.as<int32_t>(); gt.g_y0 = g->g_y0.as<int32_t>(); gt.g_y1 = g->g_y1.as<int32_t>();
+    gt.g_a = g->g_a.as<uint32_t>(); gt.g_b = g->g_b.as<uint32_t>();
+    const cts::RankDesc* dd = g->sh_desc.as<cts::RankDesc>();
+    CT_CUDA(cts::merge((const char*)gathered_dev, dd, reinterpret_cast<const long*>(dd + nranks), nranks, NC, NP, NS, gt, st));
+    g->launches += 3;
+    g->ncomp = NC; g->npair = NP; g->nseg = NS;
+    g->stats["comps2d"] = (double)NC; g->stats["pairs"] = (double)NP; g->stats["seam_segments"] = (double)NS;
+    return CT_OK;
+}
+
+int ct_global_phase(ct_ctx* g, double overlap, int persistence, int twosided, ct_plane_runs_fn fetch, void* user,
+                    long* n_features, void* stream) {
+    if (!g) return fail(CT_ERR_ARG, "null context");
+    CT_CUDA(cudaSetDevice(g->device));
+    g->fetch_fn = fetch; g->fetch_user = user;
+    CT_CUDA(cudaEventRecord(g->ev[1], (cudaStream_t)stream));
+    int rc = table_phase(g, overlap, persistence, twosided, CT_STAGE_FINAL, n_features, (cudaStream_t)stream, true);
+    g->fetch_fn = nullptr; g->fetch_user = nullptr;
+    g->stats["kernel_launches"] = (double)g->launches;
+    return rc;
+}
+
+int ct_shard_paint_global(ct_ctx* c, ct_ctx* g, long comp_offset, long t_begin, int32_t* flag_dev, void* stream) {
+    if (!c || !g || !flag_dev) return fail(CT_ERR_ARG, "null argument");
+    if (c->device != g->device) return fail(CT_ERR_ARG, "shard and global context must live on the same device");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long T_own = c->T - c->has_prev;
+    if (c->ncomp && (comp_offset + c->ncomp > g->ncomp || comp_offset + c->halo_comps < 0))
+        return fail(CT_ERR_ARG, "component offset %ld does not fit the global tables", comp_offset);
+    // overrides (sub-runs of split components) of this rank's planes, in local time
+    std::vector<ctb::Override> ovr;
+    for (const ctb::Override& o : g->host_result.overrides)
+        if (o.t >= t_begin && o.t < t_begin + T_own) ovr.push_back(ctb::Override{(int32_t)(o.t - t_begin), o.y, o.x0, o.x1, o.val});
+    const long novr = (long)ovr.size();
+    c->novr = novr;
+    if (novr) {
+        CT_CUDA(c->hp_ovr.ensure((size_t)novr * 5 * 4));
+        int32_t* ho = c->hp_ovr.as<int32_t>();
+        for (long i = 0; i < novr; ++i) {
+            ho[i] = ovr[i].t; ho[novr + i] = ovr[i].y; ho[2 * novr + i] = ovr[i].x0; ho[3 * novr + i] = ovr[i].x1;
+            ho[4 * novr + i] = ovr[i].val;
+        }
+        const size_t ob = (size_t)novr * 4;
+        DevBuf* ob5[] = {&c->o_t, &c->o_y, &c->o_x0, &c->o_x1, &c->o_val};
+        for (int k = 0; k < 5; ++k) {
+            CT_CUDA(ob5[k]->ensure(ob));
+            CT_CUDA(cudaMemcpyAsync(ob5[k]->p, ho + (size_t)k * novr, ob, cudaMemcpyHostToDevice, st));
+        }
+    }
+    CT_CUDA(ctk::run_values(c->run_comp.as<uint32_t>(), g->c_val.as<int32_t>() + comp_offset, c->run_val.as<int32_t>(),
+                            c->nruns, st));
+    c->launches += 1;
+    const int sparse = (c->zero_started_for == flag_dev && flag_dev) ? 1 : 0;
+    if (sparse) CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
+    CT_CUDA(cudaEventRecord(c->ev[3], st));
+    int rc;
+    if ((rc = launch_paint(c, c->has_prev, T_own, flag_dev, sparse, st)) != CT_OK) return rc;
+    if (novr) {
+        CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
+                                     c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), novr, c->H, c->W, 0, T_own, flag_dev, st));
+        c->launches += 1;
+    }
+    CT_CUDA(cudaEventRecord(c->ev[4], st));
+    CT_CUDA(cudaStreamSynchronize(st));
+    c->zero_started_for = nullptr;
+    float ms = 0;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats["ms_threshold"] = ms;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats["ms_paint"] = ms;
+    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats["ms_total"] = ms;
+    if (sparse) { CT_CUDA(cudaEventElapsedTime(&ms, c->ev_side[0], c->ev_side[1])); c->stats["ms_zero_fill"] = ms; }
+    c->stats["kernel_launches"] = (double)(c->launches + g->launches);
+    for (const char* k : {"kept_comps", "labels3d", "features", "seam_events", "seam_splits", "neartie_resolved",
+                          "neartie_flagged", "sweeps", "ms_host_tables", "ms_g_sweeps", "ms_g_link", "ms_g_labels_d2h"})
+        if (g->stats.count(k)) c->stats[k] = g->stats[k];
     return CT_OK;
 }
 

@@ -4,10 +4,13 @@ SURVEY.md 8(e): every rank owns a contiguous range of time planes.  Thresholding
 are local; what crosses ranks is
   * ONE boundary plane per neighbour pair: the bit rows of a rank's last plane go to the next rank (130 KB at 721x1440),
     so that rank can build the (plane t, plane t-1) pair tables across the cut, and
-  * the component / class / pair / date-line tables (a few MB in total), all-gathered so that every rank replays the
-    ordered table phase (keep/kill scan in time order, 3-D numbering, stale-box date-line merge, persistence) on the
-    GLOBAL tables and obtains the same global ids -- this is the "global relabel" step; no rank-dependent numbering exists.
-The cube itself never moves.
+  * the component / class / pair / date-line tables (a few MB in total), all-gathered DEVICE to DEVICE (NCCL) and merged
+    by a kernel into global tables on every rank, which then replays the global part of the path (keep/kill recurrence,
+    3-D numbering, stale-box date-line merge, persistence) on its copy and obtains the same global ids -- this is the
+    "global relabel" step; no rank-dependent numbering exists.
+The cube itself never moves.  `run_contrack_sharded` is that path; `run_contrack_sharded_host` is the older variant that
+gathers the tables through the host and replays the ordered phase with ct_host_tables_fast (kept because its merge,
+`merge_views`, is the CPU-testable statement of the renumbering the merge kernel performs).
 """
 from __future__ import annotations
 
@@ -267,6 +270,25 @@ class Shard(object):
         self.view = view_to_dict(v, self.has_prev, self.t_begin)
         return self.view
 
+    def tables_dev(self):
+        """Table kernels; the tables stay on the device.  Returns (counts8 int64 array, export_bytes)."""
+        counts = (C.c_long * 8)()
+        nbytes = C.c_long(0)
+        _lib.check(self.lib.ct_shard_tables_dev(self.h, C.c_void_p(self.out.data_ptr()), self._stream(), counts,
+                                                C.byref(nbytes)))
+        k = np.array(list(counts), np.int64)
+        k[0] = self.t_begin - self.has_prev
+        self.counts = k
+        return k, int(nbytes.value)
+
+    def export_tables(self, dst):
+        _lib.check(self.lib.ct_shard_export_tables(self.h, C.c_void_p(dst.data_ptr()), int(dst.numel()), self._stream()))
+
+    def paint_global(self, g_handle, off):
+        _lib.check(self.lib.ct_shard_paint_global(self.h, g_handle, int(off), self.t_begin,
+                                                  C.c_void_p(self.out.data_ptr()), self._stream()))
+        return self.out
+
     def plane_runs(self, t_global, off):
         """Row-runs of one own plane with GLOBAL component ids."""
         n = C.c_long(0)
@@ -290,8 +312,8 @@ class Shard(object):
         return self.out
 
 
-def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, thr_is_f32, op, overlap, persistence,
-                         twosided, out=None, group=None):
+def run_contrack_sharded_host(engine, anom_local, t_begin, T_total, w, thresholds, thr_is_f32, op, overlap, persistence,
+                              twosided, out=None, group=None):
     """Collective over `group` (default: the world).  anom_local: torch CUDA tensor [T_local, H, W] holding planes
     [t_begin, t_begin + T_local) of the cube; `thresholds`: one value or T_local values (the local slice).
     Returns (flag_local int32 CUDA tensor, n_features, info dict)."""
@@ -331,6 +353,160 @@ def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, th
     info = dict(stats8=stats, ncomp_global=g['ncomp'], npair_global=g['npair'], nseg_global=g['nseg'],
                 table_bytes=[len(pack_view(v)) for v in views], halo_words=sh.boundary_words())
     return sh.out, int(stats[0]), info
+
+
+def _global_engine(engine):
+    """Second context on the same GPU that holds the merged global tables."""
+    g = getattr(engine, '_global', None)
+    if g is None:
+        g = engine._global = type(engine)(engine.device)
+    return g
+
+
+def comp_offsets(counts):
+    """Global id of local component 0 of every rank (see merge_views): own components before it minus its halo count."""
+    offs, base = [], 0
+    for k in counts:
+        offs.append(base - int(k[2]))
+        base += int(k[1]) - int(k[2])
+    return offs
+
+
+def global_phase(g_engine, counts, gathered, stride, T_total, H, W, w, overlap, persistence, twosided, fetch=None,
+                 stream=None):
+    """ct_global_merge + ct_global_phase on `g_engine`.  fetch(t) -> (y, x0, x1, comp_global) arrays.  Returns n_features."""
+    lib = g_engine.lib
+    flat = np.ascontiguousarray(np.asarray(counts, np.int64).reshape(-1))
+    w = np.ascontiguousarray(w, np.float64)
+    st = C.c_void_p(stream)
+    _lib.check(lib.ct_global_merge(g_engine.handle, len(flat) // 8, flat.ctypes.data_as(_lib._longp),
+                                   C.c_void_p(gathered.data_ptr()), int(stride), int(T_total), int(H), int(W),
+                                   _lib.ptr(w, _lib._f64p), st))
+    keep = {}
+
+    def _cb(user, t, n, y, x0, x1, comp):
+        try:
+            arrs = fetch(int(t))
+            arrs = (np.ascontiguousarray(arrs[0], np.int32), np.ascontiguousarray(arrs[1], np.int32),
+                    np.ascontiguousarray(arrs[2], np.int32), np.ascontiguousarray(arrs[3], np.uint32))
+            keep['a'] = arrs
+            n[0] = len(arrs[0])
+            y[0] = _lib.ptr(arrs[0], _lib._i32p); x0[0] = _lib.ptr(arrs[1], _lib._i32p)
+            x1[0] = _lib.ptr(arrs[2], _lib._i32p); comp[0] = _lib.ptr(arrs[3], _lib._u32p)
+            return 0
+        except Exception:                      # never let an exception cross the C boundary
+            import traceback
+            traceback.print_exc()
+            return -1
+
+    cb = _FETCH(_cb) if fetch is not None else C.cast(None, _FETCH)
+    nfeat = C.c_long(0)
+    _lib.check(lib.ct_global_phase(g_engine.handle, float(overlap), int(persistence), int(bool(twosided)),
+                                   C.cast(cb, C.c_void_p), None, C.byref(nfeat), st))
+    return int(nfeat.value)
+
+
+_bufs = {}
+
+
+def _buffer(key, nbytes, dev):
+    import torch
+    b = _bufs.get(key)
+    if b is None or b.numel() < nbytes or b.device != dev:
+        b = _bufs[key] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=dev)
+    return b
+
+
+def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, thr_is_f32, op, overlap, persistence,
+                         twosided, out=None, group=None):
+    """Collective over `group` (default: the world); tables travel device to device.  anom_local: torch CUDA tensor
+    [T_local, H, W] holding planes [t_begin, t_begin + T_local) of the cube; `thresholds`: one value or T_local values
+    (the local slice).  Returns (flag_local int32 CUDA tensor, n_features, info dict)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    grank = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    sh = Shard(engine, anom_local, t_begin, rank > 0, out)
+    g_eng = _global_engine(engine)
+    sh.threshold(w, thresholds, thr_is_f32, op)
+    # ---- the one halo exchange: last plane's bit rows -> next rank ----
+    send = sh.export_boundary()
+    recv = torch.empty_like(send)
+    ops = []
+    if rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, send, grank(rank + 1), group))
+    if rank > 0:
+        ops.append(dist.P2POp(dist.irecv, recv, grank(rank - 1), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if rank > 0:
+        sh.import_halo(recv)
+    # ---- local tables (device), all-gather of counts and packed tables ----
+    counts, nbytes = sh.tables_dev()
+    mine_k = torch.from_numpy(np.append(counts, nbytes)).to(sh.dev)
+    all_k = torch.empty((world, 9), dtype=torch.int64, device=sh.dev)
+    dist.all_gather_into_tensor(all_k, mine_k, group=group)
+    all_k = all_k.cpu().numpy()
+    stride = int(all_k[:, 8].max())
+    stride = (stride + 255) // 256 * 256
+    mine = _buffer(('mine', engine.device), stride, sh.dev)[:stride]
+    gathered = _buffer(('all', engine.device), stride * world, sh.dev)[:stride * world]
+    sh.export_tables(mine)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    offs = comp_offsets(all_k)
+    starts = [int(k[0]) + (1 if r > 0 else 0) for r, k in enumerate(all_k)]          # first own plane of every rank
+
+    def fetch(t):                                 # collective: every rank replays the same global phase
+        owner = max(r for r in range(world) if starts[r] <= t)
+        obj = [sh.plane_runs(t, offs[rank])] if rank == owner else [None]
+        dist.broadcast_object_list(obj, src=grank(owner), group=group)
+        return obj[0]
+
+    stream = torch.cuda.current_stream(sh.dev).cuda_stream
+    nfeat = global_phase(g_eng, all_k[:, :8], gathered, stride, T_total, sh.H, sh.W, w, overlap, persistence, twosided,
+                         fetch=fetch, stream=stream)
+    sh.paint_global(g_eng.handle, offs[rank])
+    info = dict(table_bytes=[int(b) for b in all_k[:, 8]], halo_words=sh.boundary_words(),
+                ncomp_global=int(sum(k[1] - k[2] for k in all_k)))
+    return sh.out, nfeat, info
+
+
+def run_contrack_sharded_local_dev(engines, anom_parts, T_total, w, thresholds, thr_is_f32, op, overlap, persistence,
+                                   twosided):
+    """The device-table sharded pipeline inside ONE process: `engines[r]` plays rank r (separate contexts on one GPU), the
+    all-gather is a concatenation.  Covers ct_shard_tables_dev / export / ct_global_merge / ct_global_phase /
+    ct_shard_paint_global on a single GPU."""
+    import torch
+    t_begin, shards = 0, []
+    thr = np.atleast_1d(np.asarray(thresholds, np.float64))
+    for r, (e, a) in enumerate(zip(engines, anom_parts)):
+        sh = Shard(e, a, t_begin, r > 0)
+        sh.threshold(w, thr if len(thr) == 1 else thr[t_begin:t_begin + sh.Tl], thr_is_f32, op)
+        t_begin += sh.Tl
+        shards.append(sh)
+    for r in range(1, len(shards)):
+        shards[r].import_halo(shards[r - 1].export_boundary())
+    ks = [sh.tables_dev() for sh in shards]
+    counts = np.stack([k for k, _ in ks])
+    stride = (max(n for _, n in ks) + 255) // 256 * 256
+    gathered = torch.zeros(stride * len(shards), dtype=torch.uint8, device=shards[0].dev)
+    for r, sh in enumerate(shards):
+        sh.export_tables(gathered[r * stride:(r + 1) * stride])
+    torch.cuda.synchronize()
+    offs = comp_offsets(counts)
+    starts = [sh.t_begin for sh in shards]
+
+    def fetch(t):
+        owner = max(r for r in range(len(shards)) if starts[r] <= t)
+        return shards[owner].plane_runs(t, offs[owner])
+
+    g_eng = _global_engine(engines[0])
+    stream = torch.cuda.current_stream(shards[0].dev).cuda_stream
+    nfeat = global_phase(g_eng, counts, gathered, stride, T_total, shards[0].H, shards[0].W, w, overlap, persistence,
+                         twosided, fetch=fetch, stream=stream)
+    outs = [sh.paint_global(g_eng.handle, offs[r]) for r, sh in enumerate(shards)]
+    return outs, nfeat, dict(counts=counts, offsets=offs, stride=stride)
 
 
 def run_contrack_sharded_local(engines, anom_parts, T_total, w, thresholds, thr_is_f32, op, overlap, persistence,

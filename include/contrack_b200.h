@@ -199,6 +199,29 @@ int ct_shard_plane_runs(ct_ctx* ctx, long local_plane, long* n, const int32_t** 
 int ct_shard_paint(ct_ctx* ctx, const int32_t* comp_val_local, long novr, const int32_t* ovr_t, const int32_t* ovr_y,
                    const int32_t* ovr_x0, const int32_t* ovr_x1, const int32_t* ovr_val, int32_t* flag_dev, void* stream);
 
+/* ---- time-sharded run with device-resident tables (the path bench.py --gpus N and sharded.run_contrack_sharded use) ----
+ * The rank-local tables never visit the host: every rank packs them into one device buffer, the caller all-gathers the
+ * buffers (NCCL), a merge kernel renumbers them into GLOBAL tables in a second context (`g`, same device), and the global
+ * part of contrack.py:706-772 (overlap filter, 3-D labels, date-line merge, persistence) runs on every rank's copy -- the
+ * "global relabel": every rank computes the same value for every component of the cube and paints its own planes.
+ *   ct_shard_tables_dev     table kernels over halo + own planes (tables stay on the device); zero fill of flag_dev starts
+ *                           on a side stream.  counts8 = {0 (caller: t_begin - has_prev), components, halo components,
+ *                           pairs, segments, pairs of halo components, segments of the halo plane, components of the last
+ *                           plane}; *export_bytes = size of this rank's packed tables
+ *   ct_shard_export_tables  pack the tables into dst_dev (cap_bytes >= export_bytes)
+ *   (caller)                all-gather counts8 and the packed tables (stride = max export_bytes)
+ *   ct_global_merge         gathered tables -> global tables of context g (counts: [nranks * 8], rank order)
+ *   ct_global_phase         contrack.py:706-772 on g's tables; `fetch` (may be NULL) serves the row-runs of a global plane
+ *                           with global component ids when a near-tie decision or a stale-box split needs them
+ *   ct_shard_paint_global   values of this rank's components (global id = local id + comp_offset) -> its flag planes */
+int ct_shard_tables_dev(ct_ctx* ctx, int32_t* flag_dev, void* stream, long* counts8, long* export_bytes);
+int ct_shard_export_tables(ct_ctx* ctx, void* dst_dev, long cap_bytes, void* stream);
+int ct_global_merge(ct_ctx* g, int nranks, const long* counts, const void* gathered_dev, long stride_bytes, long T_total,
+                    int H, int W, const double* w_host, void* stream);
+int ct_global_phase(ct_ctx* g, double overlap, int persistence, int twosided, ct_plane_runs_fn fetch, void* user,
+                    long* n_features, void* stream);
+int ct_shard_paint_global(ct_ctx* ctx, ct_ctx* g, long comp_offset, long t_begin, int32_t* flag_dev, void* stream);
+
 /* ---- run_lifecycle, contrack.py:799-907 -------------------------------------------------------------------------------
  * flag_dev [T,H,W] int32 (ds[flag]), var_dev [T,H,W] float32/float64 (ds[variable]), w_host [H] the float32-valued area
  * weights of contrack.py:847-848.  One result row per (time step, flag id != 0) that occurs in the cube, in no particular

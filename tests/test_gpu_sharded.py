@@ -33,6 +33,85 @@ def run_local(x, lat, lon, w, parts, thr, gorl, ov, pers, two):
             e.handle = None
 
 
+def run_local_dev(x, w, parts, thr, gorl, ov, pers, two, opts=None):
+    """Device-table variant (the one bench.py --gpus N uses): tables gathered device to device, merge kernel, global phase
+    on the device in a second context."""
+    import torch
+    from contrack_b200 import Engine, sharded
+    from contrack_b200._lib import GORL_TO_OP
+    engines = [Engine(0) for _ in parts]
+    try:
+        for k, v in (opts or {}).items():
+            for e in engines + [sharded._global_engine(engines[0])]:      # the global phase runs in engines[0]._global
+                e.set_option(k, v)
+        bounds = np.cumsum([0] + list(parts))
+        xs = [torch.from_numpy(np.ascontiguousarray(x[a:b])).cuda() for a, b in zip(bounds[:-1], bounds[1:])]
+        outs, n, info = sharded.run_contrack_sharded_local_dev(engines, xs, x.shape[0], w, thr, True, GORL_TO_OP[gorl],
+                                                               ov, pers, two)
+        torch.cuda.synchronize()
+        return np.concatenate([o.cpu().numpy() for o in outs]), n, info
+    finally:
+        for e in engines:
+            g = getattr(e, '_global', None)
+            for h in (e, g):
+                if h is not None and h.handle:
+                    h.lib.ct_destroy(h.handle)
+                    h.handle = None
+
+
+@pytest.mark.parametrize('parts', [(6, 5), (4, 3, 4), (1, 9, 1), (2, 2, 2, 2, 3), (11,)])
+def test_fixture_sharded_device_tables(fixture_cube, reference_run, parts):
+    a, lat, lon = fixture_cube
+    w = row_weights(lat, lon)
+    from _common import sha_i4
+    for r in reference_run['fixture']:
+        f, n, _ = run_local_dev(a, w, parts, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'])
+        assert sha_i4(f) == r['sha256'], (parts, r['key'])
+        assert n == len(r['ids'])
+
+
+def test_sharded_device_tables_quirks_and_synthetic(reference_run):
+    from _common import sha_i4
+    for r in reference_run['quirk'] + reference_run['synthetic']:
+        T, H, W = r['shape']
+        x = synth_cube(r['seed'], T, H, W, tuple(r['sigma']))
+        lat, lon = regular_grid(H, W)
+        w = row_weights(lat, lon)
+        thr = np.float64(r['threshold']) if r.get('threshold_is_np_float64') else r['threshold']
+        f32 = not r.get('threshold_is_np_float64')
+        for parts in [(T // 2, T - T // 2), (T // 3, T // 3, T - 2 * (T // 3))]:
+            import torch
+            from contrack_b200 import Engine, sharded
+            from contrack_b200._lib import GORL_TO_OP
+            engines = [Engine(0) for _ in parts]
+            bounds = np.cumsum([0] + list(parts))
+            xs = [torch.from_numpy(np.ascontiguousarray(x[a:b])).cuda() for a, b in zip(bounds[:-1], bounds[1:])]
+            outs, n, _ = sharded.run_contrack_sharded_local_dev(engines, xs, T, w, thr, f32, GORL_TO_OP[r['gorl']],
+                                                                r['overlap'], r['persistence'], r['twosided'])
+            f = np.concatenate([o.cpu().numpy() for o in outs])
+            for e in engines:
+                for h in (e, getattr(e, '_global', None)):
+                    if h is not None and h.handle:
+                        h.lib.ct_destroy(h.handle); h.handle = None
+            assert sha_i4(f) == r['sha256'], (r['seed'], parts)
+            assert n == len(r['ids'])
+
+
+def test_sharded_device_tables_host_fallbacks(fixture_cube):
+    """Near-ties on pole rows (exact host resolver, plane runs served through the callback) and the host table path."""
+    from _common import pole_tie_overlaps
+    a, lat, lon = fixture_cube
+    w = row_weights(lat, lon)
+    ovs = pole_tie_overlaps(a, lat, lon, 150)[:6] or [0.5]
+    for ov in ovs:
+        ref = oracle.run_contrack(a, lat, lon, 150, '>=', ov, 2, True)
+        f, n, _ = run_local_dev(a, w, (4, 4, 3), 150, '>=', ov, 2, True)
+        assert np.array_equal(f, ref), ov
+    ref = oracle.run_contrack(a, lat, lon, 150, '>=', 0.5, 5, True)
+    f, n, _ = run_local_dev(a, w, (6, 5), 150, '>=', 0.5, 5, True, opts={'gpu_tables': 0})
+    assert np.array_equal(f, ref)
+
+
 @pytest.mark.parametrize('parts', [(6, 5), (4, 3, 4), (1, 9, 1), (2, 2, 2, 2, 3)])
 def test_fixture_sharded_on_one_gpu(fixture_cube, golden, parts):
     a, lat, lon = fixture_cube
@@ -63,6 +142,8 @@ def test_sharded_benchmark_grid_with_poles():
     ref = oracle.run_contrack(x, lat, lon, 160, '>=', 0.5, 5, True, force=True)
     w = oracle.weight_grid(lat, oracle.resolution(lat, True), oracle.resolution(lon, True), 1440)[:, 0].copy()
     f, n, _ = run_local(x, lat, lon, w, (5, 4, 3), 160, '>=', 0.5, 5, True)
+    assert np.array_equal(f, ref)
+    f, n, _ = run_local_dev(x, w, (5, 4, 3), 160, '>=', 0.5, 5, True)
     assert np.array_equal(f, ref)
 
 

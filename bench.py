@@ -25,6 +25,10 @@ for p in (ROOT, os.path.join(ROOT, 'tests')):
 
 import numpy as np  # noqa: E402
 
+# NCCL prints its version banner on stdout under NCCL_DEBUG=VERSION/INFO; the driver wants ONE JSON line there
+if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO', ''):
+    os.environ['NCCL_DEBUG'] = 'WARN'
+
 H, W = 721, 1440
 SIGMA = (2.5, 24.0, 40.0)        # (2.5 steps, 6 deg, 10 deg) at 0.25 deg
 THRESHOLD, GORL, OVERLAP, PERSISTENCE, TWOSIDED = 160, '>=', 0.5, 5, True
@@ -227,7 +231,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (the product path has no CPU fallback)')
     torch.cuda.set_device(local)
+    real_stdout = None
     if world > 1:
+        # NCCL / c10d print banners on stdout ("NCCL version ..."); the driver wants exactly one JSON line there
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from contrack_b200 import sharded
 
@@ -251,11 +260,14 @@ def main():
     t_gen = time.perf_counter() - t_gen
     flag = torch.empty((t_hi - t_lo, H, W), dtype=torch.int32, device='cuda')
 
+    shard_info = []
+
     def step():
         if world == 1:
             return eng.run_contrack(anom, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=flag)
-        f, n, _ = sharded.run_contrack_sharded(eng, anom, t_lo, T, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED,
-                                               out=flag)
+        f, n, info = sharded.run_contrack_sharded(eng, anom, t_lo, T, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED,
+                                                  out=flag)
+        shard_info.append(info)
         return f, n
 
     for _ in range(args.warmup):
@@ -323,6 +335,12 @@ def main():
             'tables': {k: int(stats[k]) for k in ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d',
                                                   'seam_events', 'seam_splits', 'neartie_resolved') if k in stats},
             'synth_seconds': t_gen}
+    if world > 1 and shard_info:
+        last = shard_info[-args.steps:]
+        line['shard_ms'] = {k: float(np.mean([i['phase_ms'][k] for i in last])) for k in last[0]['phase_ms']}
+        line['shard_ms']['note'] = ('rank 0 host wall clock per phase of the sharded step (phases end where the host has to '
+                                    'wait: halo exchange, table counts, gathered counts, global phase, paint)')
+        line['shard_table_bytes'] = last[-1]['table_bytes']
 
     # ---- CPU baseline + parity on a bounded sample (rank 0 of a single-GPU run only) ---------------------------------
     if not args.no_cpu and world == 1:
@@ -407,7 +425,11 @@ def main():
         line['e2e'] = dict({'value': Te * n_e2e / dt, 'unit': 'timesteps/s', 'h2d_bytes_per_step': Te * H * W * 4,
                             'd2h_bytes_per_step': d2h, 'T': Te, 'steps': n_e2e, 'features': int(nf)}, **extra)
     if rank == 0:
-        print(json.dumps(line))
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(line) + '\n').encode())
+        else:
+            print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

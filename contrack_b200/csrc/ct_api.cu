@@ -159,10 +159,18 @@ struct ct_ctx {
     std::vector<double> w_host;
     long launches = 0;
     // time-sharded run: packed tables of all ranks -> global tables (ct_global_merge), plane runs served by the caller
-    DevBuf sh_desc;
+    DevBuf sh_desc, b_sla, b_slb;
     PinBuf hp_desc;
     ct_plane_runs_fn fetch_fn = nullptr;
     void* fetch_user = nullptr;
+    // ct_shard_begin: thresholding of the own planes is deferred to ct_shard_tables_dev (pipelined with the table kernels)
+    long opt_label_fast = 1;                  // steps 4c/4d at label granularity on the host (fallback: per component)
+    long opt_profile_tables = 0;              // debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"
+    std::vector<std::pair<std::string, cudaEvent_t>> prof;
+    size_t prof_used = 0;
+    const void* sh_anom = nullptr;
+    int sh_dtype = 0, sh_thr_is_f32 = 0, sh_op = 0, sh_deferred = 0;
+    long sh_thr_n = 0;
 };
 
 namespace {
@@ -332,6 +340,27 @@ int launch_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long t0, lon
 // Chunks must be processed in time order; every table is indexed globally (rows, runs, components, pairs, date-line rows
 // and segments continue where the previous chunk stopped), so the result is identical to one pass over all planes.
 // Three host round trips per chunk (run count, component count, pair count) size the tables.
+// debug profiling of the table kernels (option "profile_tables"): an event after every kernel group
+void prof_mark(ct_ctx* c, const char* name, cudaStream_t st) {
+    if (!c->opt_profile_tables) return;
+    if (c->prof_used == c->prof.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        c->prof.emplace_back(std::string(), e);
+    }
+    c->prof[c->prof_used].first = name;
+    cudaEventRecord(c->prof[c->prof_used].second, st);
+    c->prof_used++;
+}
+void prof_collect(ct_ctx* c) {                // after a synchronize: elapsed time between successive marks, summed by name
+    for (size_t i = 1; i < c->prof_used; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->prof[i - 1].second, c->prof[i].second) == cudaSuccess)
+            c->stats["ms_t_" + c->prof[i].first] += ms;
+    }
+    c->prof_used = 0;
+}
+
 void tables_begin(ct_ctx* c) {
     c->tb_planes = c->tb_runs = c->tb_comps = c->tb_seams = c->tb_segs = c->tb_pairs = 0;
 }
@@ -348,12 +377,14 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
     auto hint = [&](long elems, size_t elt) { return (size_t)((double)elems * scale) * elt; };
 
     CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(n > 1024 ? n : 1024) * sizeof(uint32_t)));
+    prof_mark(c, "start", st);
     CT_CUDA(ctk::exclusive_scan_u32(U(c->row_cnt) + r0, U(c->row_ptr) + r0, n, U(c->scan_tmp), st, (uint32_t)c->tb_runs));
     CT_CUDA(ctk::exclusive_scan_u32(U(c->seam_flag) + r0, U(c->seam_pos) + r0, n, U(c->scan_tmp), st,
                                     (uint32_t)c->tb_seams));
     c->launches += 6;
     CT_CUDA(cudaMemcpyAsync(cnt_host + 0, U(c->row_ptr) + r1, 4, cudaMemcpyDeviceToHost, st));
     CT_CUDA(cudaMemcpyAsync(cnt_host + 1, U(c->seam_pos) + r1, 4, cudaMemcpyDeviceToHost, st));
+    prof_mark(c, "row_scans", st);
     CT_CUDA(cudaStreamSynchronize(st));
     const long Rb = c->tb_runs, Re = cnt_host[0], Sb = c->tb_seams, Se = cnt_host[1];
 
@@ -364,13 +395,17 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
     }
     CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(std::max(Re - Rb, n)) * sizeof(uint32_t)));
     CT_CUDA(ctk::extract_runs(U(c->bits), U(c->row_ptr), r0, n, c->Ww, U(c->run_x), U(c->run_row), st));
+    prof_mark(c, "extract_runs", st);
     CT_CUDA(ctk::ccl_init(U(c->parent), Rb, Re, st));
     CT_CUDA(ctk::ccl_union(U(c->row_ptr), U(c->run_x), U(c->run_row), Rb, Re, H, U(c->parent), st));
+    prof_mark(c, "ccl_union", st);
     CT_CUDA(ctk::ccl_flatten(U(c->parent), U(c->root_flag), Rb, Re, st));
+    prof_mark(c, "ccl_flatten", st);
     CT_CUDA(ctk::exclusive_scan_u32(U(c->root_flag) + Rb, U(c->rank) + Rb, Re - Rb, U(c->scan_tmp), st,
                                     (uint32_t)c->tb_comps));
     c->launches += 7;
     CT_CUDA(cudaMemcpyAsync(cnt_host + 2, U(c->rank) + Re, 4, cudaMemcpyDeviceToHost, st));
+    prof_mark(c, "root_scan", st);
     CT_CUDA(cudaStreamSynchronize(st));
     const long Cb = c->tb_comps, Ce = cnt_host[2];
 
@@ -393,6 +428,7 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
     CT_CUDA(ctk::comp_init(ct, Cb, Ce, W, st));
     CT_CUDA(ctk::comp_accumulate(U(c->run_x), U(c->run_row), U(c->run_comp), Rb, Re, H, c->w_dev.as<double>(),
                                  c->special_dev.as<uint8_t>(), ct, st));
+    prof_mark(c, "comp_accumulate", st);
     {
         DevBuf* sb[] = {&c->s_row, &c->s_a, &c->s_b, &c->seg_start, &c->seg_pos, &c->g_t, &c->g_y0, &c->g_y1, &c->g_a,
                         &c->g_b};
@@ -410,6 +446,7 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
                                     (uint32_t)c->tb_segs));
     CT_CUDA(ctk::seg_write(U(c->s_row), U(c->s_a), U(c->s_b), U(c->seg_start), U(c->seg_pos), Sb, Se, H, sg, st));
     CT_CUDA(cudaMemcpyAsync(cnt_host + 3, U(c->seg_pos) + Se, 4, cudaMemcpyDeviceToHost, st));
+    prof_mark(c, "seam_segs", st);
     c->launches += 10;
 
     // ---- adjacent-plane pairs of this chunk's planes (the earlier plane may belong to the previous chunk): hash
@@ -422,6 +459,7 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
         CT_CUDA(cudaMemsetAsync((char*)c->pcnt.p + o4, 0, n4, st)); CT_CUDA(cudaMemsetAsync((char*)c->pfill.p + o4, 0, n4, st));
     }
     CT_CUDA(ctk::class_sums(ct, kt, Cb, Ce, st));
+    prof_mark(c, "class_sums", st);
     ctk::PairTable pt;
     uint64_t want = (uint64_t)(Ce - Cb) * 4;
     for (int attempt = 0;; ++attempt) {
@@ -436,6 +474,7 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
         CT_CUDA(ctk::pairs_accumulate(U(c->row_ptr), U(c->run_x), U(c->run_row), U(c->run_comp), Rb, Re, H,
                                       c->w_dev.as<double>(), c->special_dev.as<uint8_t>(), pt, st));
         c->launches += 3;
+        prof_mark(c, "pairs_accumulate", st);
         CT_CUDA(cudaMemcpyAsync(cnt_host + 4, cnt_dev + 4, 8, cudaMemcpyDeviceToHost, st));
         CT_CUDA(cudaStreamSynchronize(st));
         if (cnt_host[4] == 0 && (uint64_t)cnt_host[5] * 10 <= (uint64_t)pt.cap * 7) break;
@@ -454,6 +493,8 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
     CT_CUDA(ctk::pairs_count(pt, ct.cls, kt, U(c->pcnt), st));
     CT_CUDA(ctk::exclusive_scan_u32(U(c->pcnt) + Cb, U(c->pptr) + Cb, Ce - Cb, U(c->scan_tmp), st, (uint32_t)Pb));
     CT_CUDA(ctk::pairs_fill(pt, U(c->pptr), U(c->pfill), q, st));
+    prof_mark(c, "pairs_csr", st);
+    if (c->opt_profile_tables) { CT_CUDA(cudaStreamSynchronize(st)); prof_collect(c); }
     c->launches += 5;
     c->tb_planes = p1; c->tb_runs = Re; c->tb_comps = Ce; c->tb_seams = Se; c->tb_pairs = Pe;
     c->tb_segs = Se > Sb ? cnt_host[3] : c->tb_segs;
@@ -674,15 +715,22 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
             CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(nlab + 2) * 4));
             CT_CUDA(ctk::label_tables(ctd, c->l_label.as<int32_t>(), nc, ld, nlab, c->scan_tmp.as<uint32_t>(), st));
             c->launches += 6;
+            const long nsg = c->nseg;
+            CT_CUDA(c->b_sla.ensure((size_t)(nsg + 1) * 4)); CT_CUDA(c->b_slb.ensure((size_t)(nsg + 1) * 4));
+            CT_CUDA(ctk::seg_labels(c->g_a.as<uint32_t>(), c->g_b.as<uint32_t>(), c->l_label.as<int32_t>(), nsg,
+                                    c->b_sla.as<int32_t>(), c->b_slb.as<int32_t>(), st));
+            c->launches += nsg ? 1 : 0;
             CT_CUDA(cudaEventRecord(c->ev[2], st));
             const size_t nl1 = (size_t)nlab + 2;
-            CT_CUDA(c->hp_labels.ensure((nl1 * 7 + (size_t)nc * 2 + 16) * 4));
+            CT_CUDA(c->hp_labels.ensure((nl1 * 7 + (size_t)nc * 2 + 2 * (size_t)nsg + 16) * 4));
             int32_t* hl = c->hp_labels.as<int32_t>();
             int32_t *h_t0 = hl, *h_t1 = hl + nl1, *h_y0 = hl + 2 * nl1, *h_y1 = hl + 3 * nl1, *h_x0 = hl + 4 * nl1,
                     *h_x1 = hl + 5 * nl1;
             uint32_t* h_lptr = reinterpret_cast<uint32_t*>(hl + 6 * nl1);
             uint32_t* h_lorder = reinterpret_cast<uint32_t*>(hl + 7 * nl1);
             int32_t* hlabel = hl + 7 * nl1 + nc + 1;
+            int32_t* h_sla = hlabel + nc + 1;
+            int32_t* h_slb = h_sla + nsg;
             const size_t lbytes = (size_t)(nlab + 1) * 4;
             CT_CUDA(cudaMemcpyAsync(h_t0, ld.t0, lbytes, cudaMemcpyDeviceToHost, st));
             CT_CUDA(cudaMemcpyAsync(h_t1, ld.t1, lbytes, cudaMemcpyDeviceToHost, st));
@@ -690,6 +738,44 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
             CT_CUDA(cudaMemcpyAsync(h_y1, ld.y1, lbytes, cudaMemcpyDeviceToHost, st));
             CT_CUDA(cudaMemcpyAsync(h_x0, ld.x0, lbytes, cudaMemcpyDeviceToHost, st));
             CT_CUDA(cudaMemcpyAsync(h_x1, ld.x1, lbytes, cudaMemcpyDeviceToHost, st));
+            if (c->opt_label_fast) {
+                // ---- fast path: whole labels move; only the label boxes and the labels of the segment ends travel ----
+                if (nsg) {
+                    CT_CUDA(cudaMemcpyAsync(h_sla, c->b_sla.p, (size_t)nsg * 4, cudaMemcpyDeviceToHost, st));
+                    CT_CUDA(cudaMemcpyAsync(h_slb, c->b_slb.p, (size_t)nsg * 4, cudaMemcpyDeviceToHost, st));
+                }
+                const double t_f0 = now_ms();
+                CT_CUDA(cudaStreamSynchronize(st));
+                const double t_f1 = now_ms();
+                ctb::LabelTables lt;
+                lt.nlabel = (int)nlab; lt.t0 = h_t0; lt.t1 = h_t1; lt.y0 = h_y0; lt.y1 = h_y1; lt.x0 = h_x0; lt.x1 = h_x1;
+                static thread_local std::vector<int32_t> lab_fin;
+                ctb::TrackStats ts;
+                if (ctb::track_labels_fast(persistence, lt, nsg, h_sla, h_slb, lab_fin, ts) == 0) {
+                    cth::Result& res = c->host_result;
+                    res.overrides.clear();
+                    res.n_neartie = 0; res.n_labels3d = nlab; res.n_features = ts.n_features;
+                    res.n_seam_events = ts.n_events; res.n_seam_splits = 0;
+                    c->stats["ms_g_labels_d2h"] = t_f1 - t_f0;
+                    c->stats["ms_host_tables"] = now_ms() - t_f1;
+                    c->stats["ms_ht_events"] = ts.ms_events; c->stats["ms_ht_persist"] = ts.ms_persist;
+                    c->stats["ht_walked"] = (double)ts.n_walked; c->stats["label_fast"] = 1.0;
+                    CT_CUDA(c->hp_val.ensure(((size_t)nlab + 8) * 4));
+                    memcpy(c->hp_val.p, lab_fin.data(), (size_t)(nlab + 1) * 4);
+                    CT_CUDA(cudaMemcpyAsync(c->b_fin.p, c->hp_val.p, (size_t)(nlab + 1) * 4, cudaMemcpyHostToDevice, st));
+                    CT_CUDA(ctk::final_values(c->l_label.as<int32_t>(), c->b_fin.as<int32_t>(), nc, nullptr, nullptr, 0,
+                                              c->c_val.as<int32_t>(), st));
+                    c->launches += 1;
+                    int rcu;
+                    if ((rcu = upload_values(c, nullptr, res.overrides, st)) != CT_OK) return rcu;
+                    c->stats["labels3d"] = (double)nlab; c->stats["features"] = (double)res.n_features;
+                    c->stats["seam_events"] = (double)res.n_seam_events; c->stats["seam_splits"] = 0.0;
+                    c->stats["neartie_resolved"] = 0.0; c->stats["moved_comps"] = 0.0;
+                    if (n_features) *n_features = res.n_features;
+                    return CT_OK;
+                }
+                c->stats["label_fast"] = 0.0;         // a label straddles a stale box: replay per component below
+            }
             CT_CUDA(cudaMemcpyAsync(h_lptr, ld.ptr, lbytes + 4, cudaMemcpyDeviceToHost, st));
             if (nc) {
                 CT_CUDA(cudaMemcpyAsync(h_lorder, ld.order, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
@@ -729,6 +815,8 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
             if (rc != 0) return fail(CT_ERR_INTERNAL, "date-line merge could not fetch the runs of a component to split");
             res.n_features = tstats.n_features; res.n_seam_events = tstats.n_events; res.n_seam_splits = tstats.n_splits;
             c->stats["ms_host_tables"] = now_ms() - t_host0;
+            c->stats["ms_ht_init"] = tstats.ms_init; c->stats["ms_ht_events"] = tstats.ms_events;
+            c->stats["ms_ht_persist"] = tstats.ms_persist; c->stats["ht_walked"] = (double)tstats.n_walked;
             // surviving value per label + the re-labelled components -> value per component on the device
             const long nm = (long)mc.size();
             CT_CUDA(c->hp_val.ensure(((size_t)nlab + 2 + 2 * (size_t)nm + 8) * 4));
@@ -891,7 +979,7 @@ void ct_destroy(ct_ctx* c) {
                       &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN,
                       &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
                       &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml,
-                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc};
+                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb};
     for (DevBuf* b : bufs) b->release();
     c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release(); c->hp_desc.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
@@ -916,6 +1004,8 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "chunk_min_planes")) { c->opt_chunk_min_planes = value < 1 ? 1 : value; return CT_OK; }
     if (!strcmp(key, "host_sparse")) { c->opt_host_sparse = value; return CT_OK; }
     if (!strcmp(key, "host_threads")) { c->opt_host_threads = value; return CT_OK; }
+    if (!strcmp(key, "label_fast")) { c->opt_label_fast = value; return CT_OK; }
+    if (!strcmp(key, "profile_tables")) { c->opt_profile_tables = value; return CT_OK; }
     return fail(CT_ERR_ARG, "unknown option '%s'", key);
 }
 
@@ -1446,6 +1536,35 @@ int ct_shard_paint(ct_ctx* c, const int32_t* comp_val_local, long novr, const in
 }
 
 // ---- time-sharded run, device-resident tables ------------------------------------------------------------------------
+int ct_shard_begin(ct_ctx* c, const void* anom_dev, int in_dtype, long T_local, int H, int W, const double* w_host,
+                   const double* thr_host, long thr_n, int thr_is_f32, int op, int has_prev, uint32_t* boundary_dst_dev,
+                   void* stream) {
+    if (!c) return fail(CT_ERR_ARG, "null context");
+    int rc = check_args(T_local, H, W, w_host, thr_host, thr_n, in_dtype, op);
+    if (rc != CT_OK) return rc;
+    if (T_local <= 0 || !anom_dev) return fail(CT_ERR_ARG, "a rank needs at least one plane");
+    has_prev = has_prev ? 1 : 0;
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    c->stats.clear();
+    std::vector<double> thr(thr_host, thr_host + thr_n);
+    if (thr_n != 1 && has_prev) thr.insert(thr.begin(), 0.0);         // thresholds are indexed by scratch plane
+    if ((rc = prepare(c, T_local + has_prev, H, W, w_host, thr.data(), (long)thr.size(), st)) != CT_OK) return rc;
+    c->has_prev = has_prev;
+    c->sh_anom = anom_dev; c->sh_dtype = in_dtype; c->sh_thr_n = (long)thr.size(); c->sh_thr_is_f32 = thr_is_f32;
+    c->sh_op = op; c->sh_deferred = 1;
+    // the LAST own plane first: its bit rows are what the next rank is waiting for
+    const size_t plane_bytes = (size_t)H * W * (in_dtype == CT_F64 ? 8 : 4);
+    if ((rc = launch_threshold(c, (const char*)anom_dev + (size_t)(T_local - 1) * plane_bytes, in_dtype,
+                               has_prev + T_local - 1, 1, c->sh_thr_n, thr_is_f32, op, st)) != CT_OK) return rc;
+    if (boundary_dst_dev) {
+        const size_t words = (size_t)H * c->Ww;
+        CT_CUDA(cudaMemcpyAsync(boundary_dst_dev, c->bits.as<uint32_t>() + (size_t)(c->T - 1) * words, words * 4,
+                                cudaMemcpyDeviceToDevice, st));
+    }
+    return CT_OK;
+}
+
 // counts8 = {0 (caller fills in t_shift), components, halo components, pairs, date-line segments, pairs of the halo
 //            components, segments of the halo plane, components of the last plane}
 int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts8, long* export_bytes) {
@@ -1455,25 +1574,76 @@ int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts
     c->zero_started_for = nullptr;
     int rc;
     cudaStream_t ts = st;
-    if (flag_dev && c->opt_overlap_zero) {
-        if ((rc = ensure_streams(c)) != CT_OK) return rc;
+    const int side = flag_dev && c->opt_overlap_zero;
+    if (side && (rc = ensure_streams(c)) != CT_OK) return rc;
+    const long hp = c->has_prev, T_own = c->T - hp;
+    auto start_zero_fill = [&]() -> int {
         CT_CUDA(cudaEventRecord(c->ev_side[0], st));
         CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-        CT_CUDA(cudaStreamWaitEvent(c->tbl_stream, c->ev_side[0], 0));
-        CT_CUDA(ctk::zero_fill(flag_dev, (size_t)(c->T - c->has_prev) * c->H * c->W, c->sm_count, c->side_stream));
+        CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
         CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
         c->launches += 1;
         c->zero_started_for = flag_dev;
-        ts = c->tbl_stream;
+        return CT_OK;
+    };
+    const double t_h0 = now_ms();
+    const int deferred = c->sh_deferred;
+    if (c->sh_deferred) {
+        // ---- own planes thresholded in time chunks on `st`; the table kernels of chunk k (and of the halo plane) run on the
+        // high-priority stream while chunk k+1 is being thresholded; the zero fill follows the last threshold chunk ----
+        c->sh_deferred = 0;
+        long nchunk = side ? std::min<long>(c->opt_chunks, std::max<long>(1, T_own / c->opt_chunk_min_planes)) : 1;
+        const long cp = (T_own + nchunk - 1) / nchunk;
+        nchunk = (T_own + cp - 1) / cp;
+        if (side) {
+            ts = c->tbl_stream;
+            while ((long)c->ev_chunk.size() < nchunk) {
+                cudaEvent_t e;
+                CT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                c->ev_chunk.push_back(e);
+            }
+        }
+        const size_t plane_bytes = (size_t)c->H * c->W * (c->sh_dtype == CT_F64 ? 8 : 4);
+        CT_CUDA(cudaEventRecord(c->ev[0], st));
+        for (long k = 0; k < nchunk; ++k) {
+            const long t0 = k * cp, nt = std::min(cp, T_own - t0);
+            if ((rc = launch_threshold(c, (const char*)c->sh_anom + (size_t)t0 * plane_bytes, c->sh_dtype, hp + t0, nt,
+                                       c->sh_thr_n, c->sh_thr_is_f32, c->sh_op, st)) != CT_OK) return rc;
+            if (side) CT_CUDA(cudaEventRecord(c->ev_chunk[k], st));
+        }
+        CT_CUDA(cudaEventRecord(c->ev[1], st));
+        if (side && (rc = start_zero_fill()) != CT_OK) return rc;
+        tables_begin(c);
+        for (long k = 0; k < nchunk; ++k) {
+            const long t0 = k * cp, nt = std::min(cp, T_own - t0);
+            if (side) CT_CUDA(cudaStreamWaitEvent(ts, c->ev_chunk[k], 0));
+            if ((rc = tables_chunk(c, k == 0 ? 0 : hp + t0, hp + t0 + nt, ts)) != CT_OK) return rc;
+            if (k < 8) { char key[16]; snprintf(key, sizeof key, "ms_h_c%ld", k); c->stats[key] = now_ms() - t_h0; }
+        }
+        if ((rc = tables_finish(c, ts)) != CT_OK) return rc;
+        c->stats["chunks"] = (double)nchunk;
+    } else {
+        if (side) {
+            if ((rc = start_zero_fill()) != CT_OK) return rc;
+            CT_CUDA(cudaStreamWaitEvent(c->tbl_stream, c->ev_side[0], 0));
+            ts = c->tbl_stream;
+        }
+        if ((rc = tables_build(c, ts)) != CT_OK) return rc;
     }
-    if ((rc = tables_build(c, ts)) != CT_OK) return rc;
     uint32_t* cnt_dev = c->counters.as<uint32_t>();
     uint32_t* cnt_host = c->hp_counters.as<uint32_t>();
     CT_CUDA(cts::shard_counts(c->c_t.as<int32_t>(), c->ncomp, c->pptr.as<uint32_t>(), c->g_t.as<int32_t>(), c->nseg,
                               c->has_prev, c->T - 1, cnt_dev + 12, ts));
     c->launches += 1;
     CT_CUDA(cudaMemcpyAsync(cnt_host + 12, cnt_dev + 12, 16, cudaMemcpyDeviceToHost, ts));
+    if (side) CT_CUDA(cudaEventRecord(c->ev_tbl[0], ts));
     CT_CUDA(cudaStreamSynchronize(ts));
+    c->stats["ms_h_chunks"] = now_ms() - t_h0;
+    if (side && deferred) {
+        float ms = 0;
+        CT_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev_tbl[0])); c->stats["ms_tables_after_threshold"] = ms;
+        CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats["ms_threshold"] = ms;
+    }
     c->halo_comps = cnt_host[12];
     counts8[0] = 0; counts8[1] = c->ncomp; counts8[2] = cnt_host[12]; counts8[3] = c->npair; counts8[4] = c->nseg;
     counts8[5] = cnt_host[13]; counts8[6] = cnt_host[14]; counts8[7] = cnt_host[15];

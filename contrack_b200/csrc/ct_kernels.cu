@@ -819,6 +819,14 @@ __global__ void __launch_bounds__(256) k_final_values(const int32_t* __restrict_
     if (i < ncomp) val[i] = fin[label[i]];
 }
 
+// labels of the two components of every date-line segment (0 = removed)
+__global__ void __launch_bounds__(256) k_seg_labels(const uint32_t* __restrict__ seg_a, const uint32_t* __restrict__ seg_b,
+                                                    const int32_t* __restrict__ label, long nseg,
+                                                    int32_t* __restrict__ la, int32_t* __restrict__ lb) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nseg) { la[i] = label[seg_a[i]]; lb[i] = label[seg_b[i]]; }
+}
+
 __global__ void k_apply_moves(const int32_t* __restrict__ comp, const int32_t* __restrict__ newlabel,
                               const int32_t* __restrict__ fin, long n, int32_t* __restrict__ val) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1215,6 +1223,13 @@ cudaError_t label_tables(const CompTables& c, const int32_t* label, long ncomp, 
     cudaError_t e = exclusive_scan_u32(l.cnt, l.ptr, nlabel + 1, scan_tmp, st);
     if (e != cudaSuccess) return e;
     if (ncomp) k_label_fill<<<blocks_for(ncomp, 256), 256, 0, st>>>(label, ncomp, l);
+    return cudaGetLastError();
+}
+
+cudaError_t seg_labels(const uint32_t* seg_a, const uint32_t* seg_b, const int32_t* label, long nseg, int32_t* la,
+                       int32_t* lb, cudaStream_t st) {
+    if (nseg == 0) return cudaSuccess;
+    k_seg_labels<<<blocks_for(nseg, 256), 256, 0, st>>>(seg_a, seg_b, label, nseg, la, lb);
     return cudaGetLastError();
 }
 

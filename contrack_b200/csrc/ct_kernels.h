@@ -119,6 +119,9 @@ struct LabelDev {
 };
 cudaError_t label_tables(const CompTables& c, const int32_t* label, long ncomp, const LabelDev& l, long nlabel,
                          uint32_t* scan_tmp, cudaStream_t st);
+// la[s] / lb[s] = label of the component at x = 0 / x = W-1 of date-line segment s
+cudaError_t seg_labels(const uint32_t* seg_a, const uint32_t* seg_b, const int32_t* label, long nseg, int32_t* la,
+                       int32_t* lb, cudaStream_t st);
 // val[c] = fin[label[c]], then val[move_comp[i]] = fin[move_label[i]]
 cudaError_t final_values(const int32_t* label, const int32_t* fin, long ncomp, const int32_t* move_comp,
                          const int32_t* move_label, long nmoves, int32_t* val, cudaStream_t st);

@@ -2,6 +2,7 @@
 #include "ct_tables.h"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <unordered_map>
 
@@ -264,6 +265,10 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
     overrides.clear(); move_comp.clear(); move_label.clear();
     stats = TrackStats();
     const int nlabel = lt.nlabel;
+    auto clock_ms = []() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    const double t_0 = clock_ms();
 
     // Dense per-component / per-label state in buffers that live across calls; member lists are intrusive linked lists
     // (head per value, next per piece) built from the device's grouping only for the labels an event touches.
@@ -335,6 +340,7 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
         moved.clear();
         while (pid >= 0) {
             const long next = nxt[pid];
+            stats.n_walked++;
             Rel rel;
             Piece* pp = piece_ref(pid);
             if (!pp) {
@@ -400,6 +406,7 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
         if (!moved.empty()) settled[lo] = 0;
     };
 
+    const double t_1 = clock_ms();
     for (long s = 0; s < nseg && rc == 0; ++s) {
         const long a = seg_a[s], b = seg_b[s];
         if (comp_label[a] == 0 || comp_label[b] == 0) continue;
@@ -415,6 +422,7 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
         }
     }
     if (rc != 0) return rc;
+    const double t_2 = clock_ms();
 
     // persistence (contrack.py:765-772): untouched labels keep the t-extent of their box, touched ones are re-measured
     fin.assign(nlabel + 1, 0);
@@ -447,6 +455,83 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
             for (const SubRun& r : p->runs) overrides.push_back(Override{p->t, r.y, r.x0, r.x1, v});
         }
     }
+    stats.ms_init = t_1 - t_0; stats.ms_events = t_2 - t_1; stats.ms_persist = clock_ms() - t_2;
+    return 0;
+}
+
+int track_labels_fast(int persistence, const LabelTables& lt, long nseg, const int32_t* seg_la, const int32_t* seg_lb,
+                      std::vector<int32_t>& lab_fin, TrackStats& stats) {
+    stats = TrackStats();
+    const int nlabel = lt.nlabel;
+    auto clock_ms = []() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    const double t_0 = clock_ms();
+    // value[L]: id the members of label L carry now; class lists (labels by current value) exist only for touched values
+    struct Workspace { std::vector<int> value, head, nxt, touched; std::vector<uint8_t> built, settled; };
+    static thread_local Workspace tls_ws;
+    Workspace& ws = tls_ws;
+    std::vector<int>&value = ws.value, &head = ws.head, &nxt = ws.nxt, &touched = ws.touched;
+    std::vector<uint8_t>&built = ws.built, &settled = ws.settled;
+    value.resize(nlabel + 1); head.resize(nlabel + 1); nxt.resize(nlabel + 1);
+    built.assign(nlabel + 1, 0); settled.assign(nlabel + 1, 0);
+    touched.clear();
+    auto val_of = [&](int L) { return built[L] ? value[L] : L; };
+    auto ensure_built = [&](int v) {                      // class v starts with label v alone
+        if (built[v]) return;
+        built[v] = 1; value[v] = v; head[v] = v; nxt[v] = -1;
+        touched.push_back(v);
+    };
+    for (long s = 0; s < nseg; ++s) {
+        const int la = seg_la[s], lb = seg_lb[s];
+        if (la == 0 || lb == 0) continue;
+        const int va = val_of(la), vb = val_of(lb);
+        if (va == vb) continue;
+        stats.n_events++;
+        const int hi = std::max(va, vb), lo = std::min(va, vb);
+        ensure_built(hi); ensure_built(lo);
+        if (settled[hi]) continue;
+        const Box3 b{lt.t0[hi], lt.t1[hi], lt.y0[hi], lt.y1[hi], lt.x0[hi], lt.x1[hi]};
+        int L = head[hi], prev = -1;
+        bool moved = false;
+        while (L >= 0) {
+            const int next = nxt[L];
+            stats.n_walked++;
+            const bool inside = lt.t0[L] >= b.t0 && lt.t1[L] <= b.t1 && lt.y0[L] >= b.y0 && lt.y1[L] <= b.y1 &&
+                                lt.x0[L] >= b.x0 && lt.x1[L] <= b.x1;
+            const bool outside = lt.t1[L] <= b.t0 || lt.t0[L] >= b.t1 || lt.y1[L] <= b.y0 || lt.y0[L] >= b.y1 ||
+                                 lt.x1[L] <= b.x0 || lt.x0[L] >= b.x1;
+            if (inside) {
+                if (prev < 0) head[hi] = next; else nxt[prev] = next;
+                nxt[L] = head[lo]; head[lo] = L; value[L] = lo;
+                moved = true;
+            } else if (outside) {
+                prev = L;
+            } else {
+                return 1;                                 // members of L may be on both sides of the box: per-component replay
+            }
+            L = next;
+        }
+        settled[hi] = 1;
+        if (moved) settled[lo] = 0;
+    }
+    const double t_1 = clock_ms();
+    // persistence (contrack.py:765-772): the t-extent of a value's bounding box, gaps included
+    lab_fin.resize(nlabel + 1);
+    lab_fin[0] = 0;
+    for (int v = 1; v <= nlabel; ++v) {
+        const bool keep = lt.t1[v] > lt.t0[v] && (lt.t1[v] - lt.t0[v]) >= persistence;
+        lab_fin[v] = keep ? v : 0;
+        stats.n_features += keep && !built[v];
+    }
+    for (int v : touched) {
+        int lo = INT_MAX, hi = 0;
+        for (int L = head[v]; L >= 0; L = nxt[L]) { lo = std::min(lo, lt.t0[L]); hi = std::max(hi, lt.t1[L]); }
+        const bool keep = hi > lo && (hi - lo) >= persistence;
+        stats.n_features += keep;
+        for (int L = head[v]; L >= 0; L = nxt[L]) lab_fin[L] = keep ? v : 0;
+    }
+    stats.ms_init = 0; stats.ms_events = t_1 - t_0; stats.ms_persist = clock_ms() - t_1;
     return 0;
 }
 

@@ -21,7 +21,11 @@ struct RunFetcher {
     virtual ~RunFetcher() {}
 };
 
-struct TrackStats { long n_features = 0, n_events = 0, n_splits = 0; };
+struct TrackStats {
+    long n_features = 0, n_events = 0, n_splits = 0;
+    long n_walked = 0;                       // members visited by date-line events (track_tables_sparse)
+    double ms_init = 0, ms_events = 0, ms_persist = 0;
+};
 
 // Returns 0 on success, -1 if a split was needed but the fetcher was missing/failed.
 int track_tables(long T, int H, int W, int persistence,
@@ -49,6 +53,15 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
                         const int32_t* seg_b, RunFetcher* fetcher, std::vector<int32_t>& fin,
                         std::vector<int32_t>& move_comp, std::vector<int32_t>& move_label,
                         std::vector<Override>& overrides, TrackStats& stats);
+
+// The same two steps at LABEL granularity: a date-line event relabels the members of value `hi` that lie inside the stale
+// box of label hi; when every 3-D label that currently carries `hi` is either completely inside or completely outside that
+// box, whole labels move and no component has to be looked at.  seg_la / seg_lb: label of the component at x = 0 / x = W-1
+// of every segment (0 = removed), segments in (t, y) order.  Output lab_fin[label] = value painted for every component of
+// that label (0 = removed by the persistence filter).  Returns 0 on success, 1 if some label lies partly inside a box --
+// the caller then replays the events per component with track_tables_sparse (nothing has been written).
+int track_labels_fast(int persistence, const LabelTables& lt, long nseg, const int32_t* seg_la, const int32_t* seg_lb,
+                      std::vector<int32_t>& lab_fin, TrackStats& stats);
 
 // np.sum order on a contiguous float64 vector: 0 + pairwise(a, n) with 128-element blocks and 8 accumulators.
 double numpy_pairwise_sum(const double* a, long n);

@@ -251,6 +251,19 @@ class Shard(object):
                                                self.W, _lib.ptr(w, _lib._f64p), _lib.ptr(thr, _lib._f64p), len(thr),
                                                int(thr_is_f32), int(op), self.has_prev, self._stream()))
 
+    def begin(self, w, thresholds, thr_is_f32, op):
+        """ct_shard_begin: thresholds only the last own plane and returns its bit rows (int32 CUDA tensor) for the next
+        rank; the other planes are thresholded inside tables_dev(), pipelined with the table kernels."""
+        import torch
+        w = np.ascontiguousarray(w, np.float64)
+        thr = np.ascontiguousarray(np.atleast_1d(thresholds), np.float64)
+        words = self.H * ((self.W + 31) // 32)
+        t = torch.empty(words, dtype=torch.int32, device=self.dev)
+        _lib.check(self.lib.ct_shard_begin(self.h, C.c_void_p(self.anom.data_ptr()), self.dtype, self.Tl, self.H, self.W,
+                                           _lib.ptr(w, _lib._f64p), _lib.ptr(thr, _lib._f64p), len(thr), int(thr_is_f32),
+                                           int(op), self.has_prev, C.c_void_p(t.data_ptr()), self._stream()))
+        return t
+
     def boundary_words(self):
         return int(self.lib.ct_shard_boundary_words(self.h))
 
@@ -422,15 +435,18 @@ def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, th
     """Collective over `group` (default: the world); tables travel device to device.  anom_local: torch CUDA tensor
     [T_local, H, W] holding planes [t_begin, t_begin + T_local) of the cube; `thresholds`: one value or T_local values
     (the local slice).  Returns (flag_local int32 CUDA tensor, n_features, info dict)."""
+    import time
     import torch
     import torch.distributed as dist
+    tm = [('start', time.perf_counter())]
+    mark = lambda name: tm.append((name, time.perf_counter()))          # noqa: E731  host wall clock between phases
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     grank = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
     sh = Shard(engine, anom_local, t_begin, rank > 0, out)
     g_eng = _global_engine(engine)
-    sh.threshold(w, thresholds, thr_is_f32, op)
-    # ---- the one halo exchange: last plane's bit rows -> next rank ----
-    send = sh.export_boundary()
+    # ---- the one halo exchange: the last plane is thresholded first, its bit rows go to the next rank ----
+    send = sh.begin(w, thresholds, thr_is_f32, op)
+    mark('boundary_plane')
     recv = torch.empty_like(send)
     ops = []
     if rank + 1 < world:
@@ -442,8 +458,10 @@ def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, th
             req.wait()
     if rank > 0:
         sh.import_halo(recv)
-    # ---- local tables (device), all-gather of counts and packed tables ----
+    mark('halo_exchange')
+    # ---- own planes: threshold chunks + table kernels pipelined (device); all-gather of counts and packed tables ----
     counts, nbytes = sh.tables_dev()
+    mark('local_tables')
     mine_k = torch.from_numpy(np.append(counts, nbytes)).to(sh.dev)
     all_k = torch.empty((world, 9), dtype=torch.int64, device=sh.dev)
     dist.all_gather_into_tensor(all_k, mine_k, group=group)
@@ -454,6 +472,7 @@ def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, th
     gathered = _buffer(('all', engine.device), stride * world, sh.dev)[:stride * world]
     sh.export_tables(mine)
     dist.all_gather_into_tensor(gathered, mine, group=group)
+    mark('gather_launch')
     offs = comp_offsets(all_k)
     starts = [int(k[0]) + (1 if r > 0 else 0) for r, k in enumerate(all_k)]          # first own plane of every rank
 
@@ -466,28 +485,37 @@ def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, th
     stream = torch.cuda.current_stream(sh.dev).cuda_stream
     nfeat = global_phase(g_eng, all_k[:, :8], gathered, stride, T_total, sh.H, sh.W, w, overlap, persistence, twosided,
                          fetch=fetch, stream=stream)
+    mark('global_phase')
     sh.paint_global(g_eng.handle, offs[rank])
+    mark('paint')
     info = dict(table_bytes=[int(b) for b in all_k[:, 8]], halo_words=sh.boundary_words(),
-                ncomp_global=int(sum(k[1] - k[2] for k in all_k)))
+                ncomp_global=int(sum(k[1] - k[2] for k in all_k)),
+                phase_ms={b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(tm[:-1], tm[1:])})
     return sh.out, nfeat, info
 
 
 def run_contrack_sharded_local_dev(engines, anom_parts, T_total, w, thresholds, thr_is_f32, op, overlap, persistence,
-                                   twosided):
+                                   twosided, outs=None):
     """The device-table sharded pipeline inside ONE process: `engines[r]` plays rank r (separate contexts on one GPU), the
     all-gather is a concatenation.  Covers ct_shard_tables_dev / export / ct_global_merge / ct_global_phase /
     ct_shard_paint_global on a single GPU."""
     import torch
-    t_begin, shards = 0, []
+    t_begin, shards, edges = 0, [], []
     thr = np.atleast_1d(np.asarray(thresholds, np.float64))
     for r, (e, a) in enumerate(zip(engines, anom_parts)):
-        sh = Shard(e, a, t_begin, r > 0)
-        sh.threshold(w, thr if len(thr) == 1 else thr[t_begin:t_begin + sh.Tl], thr_is_f32, op)
+        sh = Shard(e, a, t_begin, r > 0, outs[r] if outs is not None else None)
+        edges.append(sh.begin(w, thr if len(thr) == 1 else thr[t_begin:t_begin + sh.Tl], thr_is_f32, op))
         t_begin += sh.Tl
         shards.append(sh)
     for r in range(1, len(shards)):
-        shards[r].import_halo(shards[r - 1].export_boundary())
-    ks = [sh.tables_dev() for sh in shards]
+        shards[r].import_halo(edges[r - 1])
+    import time
+    torch.cuda.synchronize()
+    ks, ms_tables = [], []
+    for sh in shards:
+        t0 = time.perf_counter()
+        ks.append(sh.tables_dev())
+        ms_tables.append(1e3 * (time.perf_counter() - t0))
     counts = np.stack([k for k, _ in ks])
     stride = (max(n for _, n in ks) + 255) // 256 * 256
     gathered = torch.zeros(stride * len(shards), dtype=torch.uint8, device=shards[0].dev)
@@ -503,10 +531,17 @@ def run_contrack_sharded_local_dev(engines, anom_parts, T_total, w, thresholds, 
 
     g_eng = _global_engine(engines[0])
     stream = torch.cuda.current_stream(shards[0].dev).cuda_stream
+    t0 = time.perf_counter()
     nfeat = global_phase(g_eng, counts, gathered, stride, T_total, shards[0].H, shards[0].W, w, overlap, persistence,
                          twosided, fetch=fetch, stream=stream)
-    outs = [sh.paint_global(g_eng.handle, offs[r]) for r, sh in enumerate(shards)]
-    return outs, nfeat, dict(counts=counts, offsets=offs, stride=stride)
+    ms_global = 1e3 * (time.perf_counter() - t0)
+    outs, ms_paint = [], []
+    for r, sh in enumerate(shards):
+        t0 = time.perf_counter()
+        outs.append(sh.paint_global(g_eng.handle, offs[r]))
+        ms_paint.append(1e3 * (time.perf_counter() - t0))
+    return outs, nfeat, dict(counts=counts, offsets=offs, stride=stride, ms_tables=ms_tables, ms_global=ms_global,
+                             ms_paint=ms_paint, global_stats=g_eng.stats())
 
 
 def run_contrack_sharded_local(engines, anom_parts, T_total, w, thresholds, thr_is_f32, op, overlap, persistence,

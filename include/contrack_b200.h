@@ -204,6 +204,11 @@ int ct_shard_paint(ct_ctx* ctx, const int32_t* comp_val_local, long novr, const 
  * buffers (NCCL), a merge kernel renumbers them into GLOBAL tables in a second context (`g`, same device), and the global
  * part of contrack.py:706-772 (overlap filter, 3-D labels, date-line merge, persistence) runs on every rank's copy -- the
  * "global relabel": every rank computes the same value for every component of the cube and paints its own planes.
+ *   ct_shard_begin          like ct_shard_threshold, but only the LAST own plane is thresholded now and its bit rows are
+ *                           copied to boundary_dst_dev (may be NULL): the next rank gets its halo before anything else is
+ *                           computed.  The own planes are thresholded by ct_shard_tables_dev, in time chunks, with the table
+ *                           kernels of one chunk running beside the thresholding of the next (options "chunks",
+ *                           "chunk_min_planes").  Call ct_shard_import_halo between the two when has_prev.
  *   ct_shard_tables_dev     table kernels over halo + own planes (tables stay on the device); zero fill of flag_dev starts
  *                           on a side stream.  counts8 = {0 (caller: t_begin - has_prev), components, halo components,
  *                           pairs, segments, pairs of halo components, segments of the halo plane, components of the last
@@ -214,6 +219,9 @@ int ct_shard_paint(ct_ctx* ctx, const int32_t* comp_val_local, long novr, const 
  *   ct_global_phase         contrack.py:706-772 on g's tables; `fetch` (may be NULL) serves the row-runs of a global plane
  *                           with global component ids when a near-tie decision or a stale-box split needs them
  *   ct_shard_paint_global   values of this rank's components (global id = local id + comp_offset) -> its flag planes */
+int ct_shard_begin(ct_ctx* ctx, const void* anom_dev, int in_dtype, long T_local, int H, int W, const double* w_host,
+                   const double* thr_host, long thr_n, int thr_is_f32, int op, int has_prev, uint32_t* boundary_dst_dev,
+                   void* stream);
 int ct_shard_tables_dev(ct_ctx* ctx, int32_t* flag_dev, void* stream, long* counts8, long* export_bytes);
 int ct_shard_export_tables(ct_ctx* ctx, void* dst_dev, long cap_bytes, void* stream);
 int ct_global_merge(ct_ctx* g, int nranks, const long* counts, const void* gathered_dev, long stride_bytes, long T_total,

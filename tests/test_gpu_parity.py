@@ -315,12 +315,13 @@ def test_chunked_table_pipeline(eng, chunks):
 @pytest.mark.parametrize('opts', [{'tma': 0}, {'tma': 2}, {'tma': 1}, {'paint_runs': 0}, {'overlap_zero': 0, 'tma': 3},
                                   {'gpu_tables': 0, 'paint_runs': 0}, {'chunks': 4, 'chunk_min_planes': 1},
                                   {'chunks': 64, 'chunk_min_planes': 1, 'gpu_tables': 0},
-                                  {'chunks': 3, 'chunk_min_planes': 2, 'tma': 0}])
+                                  {'chunks': 3, 'chunk_min_planes': 2, 'tma': 0}, {'label_fast': 0}])
 def test_kernel_variants_give_identical_results(eng, fixture_cube, golden, opts):
     """Every selectable kernel variant (load depth, bulk-copy staging with 16 warps, row-wise sparse paint, dense paint,
     host table phase) must produce the same bytes."""
     a, lat, lon = fixture_cube
-    defaults = {'tma': 3, 'paint_runs': 1, 'overlap_zero': 1, 'gpu_tables': 1, 'chunks': 4, 'chunk_min_planes': 128}
+    defaults = {'tma': 3, 'paint_runs': 1, 'overlap_zero': 1, 'gpu_tables': 1, 'chunks': 4, 'chunk_min_planes': 128,
+                'label_fast': 1}
     for k, v in opts.items():
         eng.set_option(k, v)
     try:
@@ -338,3 +339,36 @@ def test_kernel_variants_give_identical_results(eng, fixture_cube, golden, opts)
     finally:
         for k in opts:
             eng.set_option(k, defaults[k])
+
+
+def test_label_granular_track_matches_component_replay(eng, reference_run):
+    """Steps 4c/4d (date-line merge through stale boxes + persistence): the label-granular host pass (default) and the
+    per-component replay must agree, on the reference's own outputs for the stale-box cubes and on random cubes with many
+    date-line events; the per-component replay must still be reached when a label straddles a stale box."""
+    import torch
+    fast_used, fallback_used = 0, 0
+    cases = [(r['seed'], tuple(r['shape']), tuple(r['sigma']), r['threshold'], r['sha256']) for r in reference_run['quirk']]
+    cases += [(s, (16, 24, 16), (1.5, 2, 2), 60, None) for s in range(2000, 2040)]
+    for seed, shape, sigma, thr, want in cases:
+        x = synth_cube(seed, *shape, sigma)
+        lat, lon = regular_grid(shape[1], shape[2])
+        w = row_weights(lat, lon)
+        xd = torch.from_numpy(x).cuda()
+        out = {}
+        for lf in (1, 0):
+            eng.set_option('label_fast', lf)
+            try:
+                f, n = eng.run_contrack(xd, w, thr, True, 0, 0.0, 1, False)
+            finally:
+                eng.set_option('label_fast', 1)
+            out[lf] = (f.cpu().numpy(), n)
+            if lf == 1:
+                used = eng.stats().get('label_fast', -1)
+                fast_used += used == 1
+                fallback_used += used == 0
+        assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1], seed
+        if want is not None:
+            assert sha_i4(out[1][0]) == want, seed
+        else:
+            assert np.array_equal(out[1][0], oracle.run_contrack(x, lat, lon, thr, '>=', 0.0, 1, False)), seed
+    assert fast_used > 0 and fallback_used > 0, (fast_used, fallback_used)

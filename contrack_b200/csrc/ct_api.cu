@@ -112,7 +112,7 @@ struct ct_ctx {
     long T = 0; int H = 0, W = 0, Ww = 0;
     long nruns = 0, ncomp = 0, npair = 0, nseam = 0, novr = 0;
     // device scratch
-    DevBuf bits, row_cnt, seam_flag, row_ptr, seam_pos, scan_tmp, counters;
+    DevBuf bits, row_cnt, seam_flag, row_ptr, seam_pos, scan_tmp, counters, slots;
     DevBuf run_x, run_row, parent, root_flag, rank, run_comp, run_val;
     DevBuf c_t, c_y0, c_y1, c_x0, c_x1, c_E, c_S, c_nsp, c_cls, c_val;
     DevBuf s_row, s_a, s_b;
@@ -164,6 +164,7 @@ struct ct_ctx {
     ct_plane_runs_fn fetch_fn = nullptr;
     void* fetch_user = nullptr;
     // ct_shard_begin: thresholding of the own planes is deferred to ct_shard_tables_dev (pipelined with the table kernels)
+    long opt_fused_runs = 1;                  // row-runs come out of the threshold kernel (0: re-extracted from the bit rows)
     long opt_label_fast = 1;                  // steps 4c/4d at label granularity on the host (fallback: per component)
     long opt_profile_tables = 0;              // debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"
     std::vector<std::pair<std::string, cudaEvent_t>> prof;
@@ -313,8 +314,10 @@ int prepare(ct_ctx* c, long T, int H, int W, const double* w_host, const double*
     CT_CUDA(c->seam_flag.ensure((size_t)nrows * sizeof(uint32_t)));
     CT_CUDA(c->row_ptr.ensure((size_t)(nrows + 1) * sizeof(uint32_t)));
     CT_CUDA(c->seam_pos.ensure((size_t)(nrows + 1) * sizeof(uint32_t)));
-    CT_CUDA(c->counters.ensure(64));
-    CT_CUDA(c->hp_counters.ensure(64));
+    CT_CUDA(c->slots.ensure((size_t)nrows * ctk::RUN_SLOTS_PER_ROW * sizeof(uint32_t)));
+    CT_CUDA(c->counters.ensure(128));
+    CT_CUDA(c->hp_counters.ensure(128));
+    CT_CUDA(cudaMemsetAsync(c->counters.as<uint32_t>() + 16, 0, 4, st));            // "a row has more runs than slots"
     for (auto& e : c->ev) if (!e) CT_CUDA(cudaEventCreate(&e));
     c->launches = 0;
     return CT_OK;
@@ -330,6 +333,8 @@ int launch_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long t0, lon
     a.bits = c->bits.as<uint32_t>() + (size_t)r0 * c->Ww;
     a.row_cnt = c->row_cnt.as<uint32_t>() + r0;
     a.seam_flag = c->seam_flag.as<uint32_t>() + r0;
+    a.slots = c->slots.as<uint32_t>() + (size_t)r0 * ctk::RUN_SLOTS_PER_ROW;
+    a.overflow = c->counters.as<uint32_t>() + 16;
     a.variant = (int)c->opt_tma;
     CT_CUDA(ctk::threshold_bits(a, c->sm_count, st));
     c->launches += 1;
@@ -384,6 +389,7 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
     c->launches += 6;
     CT_CUDA(cudaMemcpyAsync(cnt_host + 0, U(c->row_ptr) + r1, 4, cudaMemcpyDeviceToHost, st));
     CT_CUDA(cudaMemcpyAsync(cnt_host + 1, U(c->seam_pos) + r1, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 16, cnt_dev + 16, 4, cudaMemcpyDeviceToHost, st));
     prof_mark(c, "row_scans", st);
     CT_CUDA(cudaStreamSynchronize(st));
     const long Rb = c->tb_runs, Re = cnt_host[0], Sb = c->tb_seams, Se = cnt_host[1];
@@ -394,7 +400,13 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
         for (DevBuf* b : rb) CT_CUDA(b->grow((size_t)(Re + 2) * 4, (size_t)Rb * 4, st, hint(Re + 2, 4)));
     }
     CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(std::max(Re - Rb, n)) * sizeof(uint32_t)));
-    CT_CUDA(ctk::extract_runs(U(c->bits), U(c->row_ptr), r0, n, c->Ww, U(c->run_x), U(c->run_row), st));
+    if (c->opt_fused_runs) {
+        CT_CUDA(ctk::compact_runs(U(c->slots), U(c->bits), U(c->row_ptr), r0, n, c->Ww, cnt_host[16] != 0, U(c->run_x),
+                                  U(c->run_row), st));
+        if (cnt_host[16]) { c->launches += 1; c->stats["slot_overflow"] = 1.0; }
+    } else {
+        CT_CUDA(ctk::extract_runs(U(c->bits), U(c->row_ptr), r0, n, c->Ww, U(c->run_x), U(c->run_row), st));
+    }
     prof_mark(c, "extract_runs", st);
     CT_CUDA(ctk::ccl_init(U(c->parent), Rb, Re, st));
     CT_CUDA(ctk::ccl_union(U(c->row_ptr), U(c->run_x), U(c->run_row), Rb, Re, H, U(c->parent), st));
@@ -979,7 +991,7 @@ void ct_destroy(ct_ctx* c) {
                       &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN,
                       &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
                       &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml,
-                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb};
+                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots};
     for (DevBuf* b : bufs) b->release();
     c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release(); c->hp_desc.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
@@ -1004,6 +1016,7 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "chunk_min_planes")) { c->opt_chunk_min_planes = value < 1 ? 1 : value; return CT_OK; }
     if (!strcmp(key, "host_sparse")) { c->opt_host_sparse = value; return CT_OK; }
     if (!strcmp(key, "host_threads")) { c->opt_host_threads = value; return CT_OK; }
+    if (!strcmp(key, "fused_runs")) { c->opt_fused_runs = value; return CT_OK; }
     if (!strcmp(key, "label_fast")) { c->opt_label_fast = value; return CT_OK; }
     if (!strcmp(key, "profile_tables")) { c->opt_profile_tables = value; return CT_OK; }
     return fail(CT_ERR_ARG, "unknown option '%s'", key);
@@ -1445,7 +1458,7 @@ int ct_shard_import_halo(ct_ctx* c, const uint32_t* src_dev, void* stream) {
     const size_t words = (size_t)c->H * c->Ww;
     CT_CUDA(cudaMemcpyAsync(c->bits.p, src_dev, words * 4, cudaMemcpyDeviceToDevice, st));
     CT_CUDA(ctk::row_stats(c->bits.as<uint32_t>(), c->H, c->W, c->Ww, c->row_cnt.as<uint32_t>(),
-                           c->seam_flag.as<uint32_t>(), st));
+                           c->seam_flag.as<uint32_t>(), c->slots.as<uint32_t>(), c->counters.as<uint32_t>() + 16, st));
     c->launches += 1;
     return CT_OK;
 }
@@ -1695,8 +1708,8 @@ int ct_global_merge(ct_ctx* g, int nranks, const long* counts, const void* gathe
         classify_rows(w_host, H, W, special);
         g->special_uniform = special_rows_uniform(w_host, special);
     }
-    CT_CUDA(g->counters.ensure(64));
-    CT_CUDA(g->hp_counters.ensure(64));
+    CT_CUDA(g->counters.ensure(128));
+    CT_CUDA(g->hp_counters.ensure(128));
     for (auto& e : g->ev) if (!e) CT_CUDA(cudaEventCreate(&e));
     g->launches = 0;
     g->has_prev = 0; g->nruns = 0; g->nseam = 0; g->novr = 0;

@@ -21,6 +21,7 @@ namespace ctk {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int RUN_SLOTS = ctk::RUN_SLOTS_PER_ROW;
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t* total) {
     uint32_t inc = v;
@@ -31,6 +32,39 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_
     }
     *total = __shfl_sync(FULL, inc, 31);
     return inc - v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// row-runs straight from the mask words a warp holds (lane j = word k of the row, `left` = the word before it): the i-th
+// run of the row goes to the row's slot i as two uint16 halves (x0 | x1 << 16, x1 exclusive).  A run ends where a 0 follows
+// a 1, so only the LEFT neighbour is needed and the ends come out in the order of the starts.  Rows with more than
+// RUN_SLOTS runs keep only the first RUN_SLOTS here; the table phase re-extracts those rows from the bit rows.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_runs(uint32_t w, uint32_t left, int k, int lane, uint32_t& sbase, uint32_t& ebase,
+                                          uint16_t* __restrict__ slot16) {
+    const uint32_t edge = (w << 1) | (left >> 31);
+    uint32_t starts = w & ~edge, falls = ~w & edge;
+    if (!__any_sync(FULL, (starts | falls) != 0u)) return;
+    uint32_t ts, te;
+    uint32_t is = sbase + warp_excl_scan(__popc(starts), lane, &ts);
+    uint32_t ie = ebase + warp_excl_scan(__popc(falls), lane, &te);
+    while (starts) {
+        const int bit = __ffs(starts) - 1;
+        starts &= starts - 1;
+        if (is < (uint32_t)RUN_SLOTS) slot16[2 * is] = (uint16_t)(k * 32 + bit);
+        ++is;
+    }
+    while (falls) {
+        const int bit = __ffs(falls) - 1;
+        falls &= falls - 1;
+        if (ie < (uint32_t)RUN_SLOTS) slot16[2 * ie + 1] = (uint16_t)(k * 32 + bit);
+        ++ie;
+    }
+    sbase += ts; ebase += te;
+}
+// a run that reaches the end of a row whose last word fills lane 31 of the last group has no word behind it: close it
+__device__ __forceinline__ void emit_close(uint32_t carry_word, int W, int lane, uint32_t ebase, uint16_t* __restrict__ slot16) {
+    if ((carry_word >> 31) && lane == 0 && ebase < (uint32_t)RUN_SLOTS) slot16[2 * ebase + 1] = (uint16_t)W;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -64,7 +98,8 @@ template <typename TIn, bool F32CMP, int OP, int NB>
 __global__ void __launch_bounds__(256) k_threshold(const TIn* __restrict__ anom, long nrows, int H, int W, int Ww,
                                                    const double* __restrict__ thr, long thr_n,
                                                    uint32_t* __restrict__ bits, uint32_t* __restrict__ row_cnt,
-                                                   uint32_t* __restrict__ seam_flag) {
+                                                   uint32_t* __restrict__ seam_flag, uint32_t* __restrict__ slots,
+                                                   uint32_t* __restrict__ overflow) {
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -74,7 +109,8 @@ __global__ void __launch_bounds__(256) k_threshold(const TIn* __restrict__ anom,
         const double thr_d = thr[thr_n == 1 ? 0 : row / H];
         const float thr_f = (float)thr_d;
         const TIn* a = anom + row * (long)W;
-        uint32_t cnt = 0, carry_word = 0, first = 0, last = 0;
+        uint32_t cnt = 0, carry_word = 0, first = 0, last = 0, sb = 0, eb = 0;
+        uint16_t* slot16 = reinterpret_cast<uint16_t*>(slots + row * (long)RUN_SLOTS);
         for (int k0 = 0; k0 < Ww; k0 += 32) {
             uint32_t myword = 0;
             const int kend = min(32, Ww - k0);
@@ -100,13 +136,18 @@ __global__ void __launch_bounds__(256) k_threshold(const TIn* __restrict__ anom,
             uint32_t prev = __shfl_up_sync(FULL, myword, 1);
             if (lane == 0) prev = carry_word;
             cnt += __popc(myword & ~((myword << 1) | (prev >> 31)));
+            emit_runs(myword, prev, k0 + lane, lane, sb, eb, slot16);
             carry_word = __shfl_sync(FULL, myword, 31);
             if (k0 == 0) first = __shfl_sync(FULL, myword, 0) & 1u;
             if (last_word >= k0 && last_word < k0 + 32) last = (__shfl_sync(FULL, myword, last_word - k0) >> last_bit) & 1u;
         }
+        emit_close(carry_word, W, lane, eb, slot16);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
-        if (lane == 0) { row_cnt[row] = cnt; seam_flag[row] = first & last; }
+        if (lane == 0) {
+            row_cnt[row] = cnt; seam_flag[row] = first & last;
+            if (cnt > (uint32_t)RUN_SLOTS) *overflow = 1u;
+        }
     }
 }
 
@@ -130,9 +171,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// the cube is read exactly once: mark its lines evict-first so that the (small, re-used) tables of the table kernels that
+// run beside this kernel stay in L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
 // Each warp runs its own ring of NS row buffers: lane 0 arms the stage's mbarrier and issues one bulk copy per row
@@ -143,7 +191,8 @@ template <typename TIn, bool F32CMP, int OP>
 __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ anom, long nrows, int H, int W, int Ww,
                                                         const double* __restrict__ thr, long thr_n,
                                                         uint32_t* __restrict__ bits, uint32_t* __restrict__ row_cnt,
-                                                        uint32_t* __restrict__ seam_flag, int NS, int stage_bytes) {
+                                                        uint32_t* __restrict__ seam_flag, uint32_t* __restrict__ slots,
+                                                        uint32_t* __restrict__ overflow, int NS, int stage_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + wid * NS;                   // [nw][NS]
@@ -153,6 +202,7 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
     const uint32_t row_bytes = (uint32_t)(W * sizeof(TIn));
     const int last_word = (W - 1) >> 5, last_bit = (W - 1) & 31;
     const int nfull = W >> 5;
+    const uint64_t pol = l2_evict_first_policy();
     if (lane == 0) {
         for (int s2 = 0; s2 < NS; ++s2) mbar_init(&bars[s2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -163,7 +213,7 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
             const long r = warp0 + (long)s2 * nwarps;
             if (r < nrows) {
                 mbar_expect_tx(&bars[s2], row_bytes);
-                bulk_g2s(stage0 + (size_t)s2 * stage_bytes, anom + r * (long)W, row_bytes, &bars[s2]);
+                bulk_g2s_hint(stage0 + (size_t)s2 * stage_bytes, anom + r * (long)W, row_bytes, &bars[s2], pol);
             }
         }
     }
@@ -174,7 +224,8 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
         const float thr_f = (float)thr_d;
         mbar_wait(&bars[st], phase);
         const TIn* a = reinterpret_cast<const TIn*>(stage0 + (size_t)st * stage_bytes);
-        uint32_t cnt = 0, carry_word = 0, first = 0, last = 0;
+        uint32_t cnt = 0, carry_word = 0, first = 0, last = 0, sb = 0, eb = 0;
+        uint16_t* slot16 = reinterpret_cast<uint16_t*>(slots + row * (long)RUN_SLOTS);
         for (int k0 = 0; k0 < Ww; k0 += 32) {
             uint32_t myword = 0;
             const int kend = min(32, Ww - k0);
@@ -200,6 +251,7 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
             uint32_t prev = __shfl_up_sync(FULL, myword, 1);
             if (lane == 0) prev = carry_word;
             cnt += __popc(myword & ~((myword << 1) | (prev >> 31)));
+            emit_runs(myword, prev, k0 + lane, lane, sb, eb, slot16);
             carry_word = __shfl_sync(FULL, myword, 31);
             if (k0 == 0) first = __shfl_sync(FULL, myword, 0) & 1u;
             if (last_word >= k0 && last_word < k0 + 32) last = (__shfl_sync(FULL, myword, last_word - k0) >> last_bit) & 1u;
@@ -211,12 +263,16 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
             if (r < nrows) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&bars[st], row_bytes);
-                bulk_g2s(stage0 + (size_t)st * stage_bytes, anom + r * (long)W, row_bytes, &bars[st]);
+                bulk_g2s_hint(stage0 + (size_t)st * stage_bytes, anom + r * (long)W, row_bytes, &bars[st], pol);
             }
         }
+        emit_close(carry_word, W, lane, eb, slot16);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
-        if (lane == 0) { row_cnt[row] = cnt; seam_flag[row] = first & last; }
+        if (lane == 0) {
+            row_cnt[row] = cnt; seam_flag[row] = first & last;
+            if (cnt > (uint32_t)RUN_SLOTS) *overflow = 1u;
+        }
         if (++st == NS) { st = 0; phase ^= 1u; }
     }
 }
@@ -238,7 +294,8 @@ cudaError_t launch_threshold_bulk(const ThresholdArgs& a, int sm_count, cudaStre
         if (e != cudaSuccess) return e;                                                                             \
         k_threshold_bulk<TIn, F32CMP, OPV><<<blocks, nw * 32, smem, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww, \
                                                                           a.thr_dev, a.thr_n, a.bits, a.row_cnt,    \
-                                                                          a.seam_flag, NS, stage_bytes);            \
+                                                                          a.seam_flag, a.slots, a.overflow, NS,     \
+                                                                          stage_bytes);                             \
     } while (0)
     switch (a.op) {
         case 0: CT_LAUNCH_THRB(0); break;
@@ -267,11 +324,11 @@ cudaError_t launch_threshold(const ThresholdArgs& a, int blocks, cudaStream_t st
         if (a.variant == 2)                                                                                         \
             k_threshold<TIn, F32CMP, OPV, 16><<<blocks, 256, 0, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww,     \
                                                                       a.thr_dev, a.thr_n, a.bits, a.row_cnt,        \
-                                                                      a.seam_flag);                                 \
+                                                                      a.seam_flag, a.slots, a.overflow);            \
         else                                                                                                        \
             k_threshold<TIn, F32CMP, OPV, 8><<<blocks, 256, 0, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww,      \
                                                                      a.thr_dev, a.thr_n, a.bits, a.row_cnt,         \
-                                                                     a.seam_flag);                                  \
+                                                                     a.seam_flag, a.slots, a.overflow);             \
     } while (0)
     switch (a.op) {
         case 0: CT_LAUNCH_THR(0); break;
@@ -286,24 +343,29 @@ cudaError_t launch_threshold(const ThresholdArgs& a, int blocks, cudaStream_t st
 
 // run count and date-line flag of bit rows that arrived from elsewhere (the halo plane of a time-sharded run)
 __global__ void __launch_bounds__(256) k_row_stats(const uint32_t* __restrict__ bits, long nrows, int W, int Ww,
-                                                   uint32_t* __restrict__ row_cnt, uint32_t* __restrict__ seam_flag) {
+                                                   uint32_t* __restrict__ row_cnt, uint32_t* __restrict__ seam_flag,
+                                                   uint32_t* __restrict__ slots, uint32_t* __restrict__ overflow) {
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= nrows) return;
     const uint32_t* b = bits + row * (long)Ww;
-    uint32_t cnt = 0, carry_word = 0;
+    uint32_t cnt = 0, carry_word = 0, sb = 0, eb = 0;
+    uint16_t* slot16 = reinterpret_cast<uint16_t*>(slots + row * (long)RUN_SLOTS);
     for (int k0 = 0; k0 < Ww; k0 += 32) {
         const uint32_t m = (k0 + lane < Ww) ? b[k0 + lane] : 0u;
         uint32_t prev = __shfl_up_sync(FULL, m, 1);
         if (lane == 0) prev = carry_word;
         cnt += __popc(m & ~((m << 1) | (prev >> 31)));
+        emit_runs(m, prev, k0 + lane, lane, sb, eb, slot16);
         carry_word = __shfl_sync(FULL, m, 31);
     }
+    emit_close(carry_word, W, lane, eb, slot16);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
     if (lane == 0) {
         row_cnt[row] = cnt;
         seam_flag[row] = (b[0] & 1u) & ((b[(W - 1) >> 5] >> ((W - 1) & 31)) & 1u);
+        if (cnt > (uint32_t)RUN_SLOTS) *overflow = 1u;
     }
 }
 
@@ -372,6 +434,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const uint32_t* __r
 // ---------------------------------------------------------------------------------------------------------------
 // bit rows -> row-runs
 // ---------------------------------------------------------------------------------------------------------------
+// rows with at most RUN_SLOTS runs: the threshold kernel left their runs in the row's slots -> dense run tables
+__global__ void __launch_bounds__(256) k_compact_runs(const uint4* __restrict__ slots, const uint32_t* __restrict__ row_ptr,
+                                                      long nrows, uint32_t* __restrict__ run_x,
+                                                      uint32_t* __restrict__ run_row, long row0) {
+    static_assert(RUN_SLOTS == 8, "two uint4 per row");
+    const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const uint32_t base = row_ptr[row], n = row_ptr[row + 1] - base;
+    if (n == 0 || n > (uint32_t)RUN_SLOTS) return;
+    const uint4 a = slots[2 * row];
+    const uint32_t v0[4] = {a.x, a.y, a.z, a.w};
+    const uint32_t r = (uint32_t)(row0 + row);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if ((uint32_t)i < n) { run_x[base + i] = v0[i]; run_row[base + i] = r; }
+    if (n > 4) {
+        const uint4 b = slots[2 * row + 1];
+        const uint32_t v1[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if ((uint32_t)(4 + i) < n) { run_x[base + 4 + i] = v1[i]; run_row[base + 4 + i] = r; }
+    }
+}
+
+// MIN_RUNS > 0: only rows with more than MIN_RUNS runs (the ones the slots could not hold)
+template <int MIN_RUNS>
 __global__ void __launch_bounds__(256) k_extract_runs(const uint32_t* __restrict__ bits,
                                                       const uint32_t* __restrict__ row_ptr, long nrows, int Ww,
                                                       uint32_t* __restrict__ run_x, uint32_t* __restrict__ run_row,
@@ -384,6 +470,7 @@ __global__ void __launch_bounds__(256) k_extract_runs(const uint32_t* __restrict
         // everything a 64-word row needs is requested before anything is consumed: one memory latency per row
         const uint32_t* b = bits + row * (long)Ww;
         const uint32_t base = row_ptr[row], next = row_ptr[row + 1];
+        if (MIN_RUNS > 0 && next - base <= (uint32_t)MIN_RUNS) continue;
         uint32_t m = lane < Ww ? b[lane] : 0u;
         uint32_t m_ahead = (32 + lane < Ww) ? b[32 + lane] : 0u;
         if (next == base) continue;
@@ -1011,9 +1098,9 @@ cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st
 }
 
 cudaError_t row_stats(const uint32_t* bits, long nrows, int W, int Ww, uint32_t* row_cnt, uint32_t* seam_flag,
-                      cudaStream_t st) {
+                      uint32_t* slots, uint32_t* overflow, cudaStream_t st) {
     if (nrows == 0) return cudaSuccess;
-    k_row_stats<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(bits, nrows, W, Ww, row_cnt, seam_flag);
+    k_row_stats<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(bits, nrows, W, Ww, row_cnt, seam_flag, slots, overflow);
     return cudaGetLastError();
 }
 
@@ -1035,8 +1122,21 @@ cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long row
                          uint32_t* run_row, cudaStream_t st) {
     if (nrows == 0) return cudaSuccess;
     const long want = (nrows + 7) / 8;
-    k_extract_runs<<<(unsigned)std::min<long>(want, 148L * 16), 256, 0, st>>>(bits + row0 * (long)Ww, row_ptr + row0,
-                                                                             nrows, Ww, run_x, run_row, row0);
+    k_extract_runs<0><<<(unsigned)std::min<long>(want, 148L * 16), 256, 0, st>>>(bits + row0 * (long)Ww, row_ptr + row0,
+                                                                                nrows, Ww, run_x, run_row, row0);
+    return cudaGetLastError();
+}
+
+cudaError_t compact_runs(const uint32_t* slots, const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww,
+                         int overflow, uint32_t* run_x, uint32_t* run_row, cudaStream_t st) {
+    if (nrows == 0) return cudaSuccess;
+    k_compact_runs<<<blocks_for(nrows, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(slots + row0 * (long)RUN_SLOTS),
+                                                           row_ptr + row0, nrows, run_x, run_row, row0);
+    if (overflow) {
+        const long want = (nrows + 7) / 8;
+        k_extract_runs<RUN_SLOTS><<<(unsigned)std::min<long>(want, 148L * 16), 256, 0, st>>>(
+            bits + row0 * (long)Ww, row_ptr + row0, nrows, Ww, run_x, run_row, row0);
+    }
     return cudaGetLastError();
 }
 

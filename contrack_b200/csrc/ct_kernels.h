@@ -7,6 +7,7 @@
 namespace ctk {
 
 constexpr uint64_t PAIR_EMPTY = ~0ull;
+constexpr int RUN_SLOTS_PER_ROW = 8;       // runs per row the threshold kernel leaves in the row's slots (32 bytes per row)
 
 struct ThresholdArgs {
     const void* anom; int in_dtype;          // ct_dtype
@@ -16,6 +17,8 @@ struct ThresholdArgs {
     uint32_t* bits;                          // [T*H*Ww] out
     uint32_t* row_cnt;                       // [T*H] out: row-runs per row
     uint32_t* seam_flag;                     // [T*H] out: 1 if the pixels at x=0 and x=W-1 are both set
+    uint32_t* slots;                         // [T*H*RUN_SLOTS_PER_ROW] out: first runs of every row, x0 | x1 << 16
+    uint32_t* overflow;                      // device flag, set if a row has more runs than slots
     int variant;                             // 0 / 2: 4-byte loads + ballot, 8 / 16 loads in flight per lane;
                                              // 1 / 3: cp.async.bulk row staging, 8 / 16 warps per CTA (needs W % 4 == 0)
 };
@@ -23,7 +26,7 @@ cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st
 
 // row_cnt / seam_flag of existing bit rows (halo plane of a time-sharded run)
 cudaError_t row_stats(const uint32_t* bits, long nrows, int W, int Ww, uint32_t* row_cnt, uint32_t* seam_flag,
-                      cudaStream_t st);
+                      uint32_t* slots, uint32_t* overflow, cudaStream_t st);
 
 // The table kernels work on index RANGES [begin, end) of the global row / run / component tables, so that the planes of a
 // cube can be processed in time chunks while later planes are still being thresholded (ct_api.cu: tables_chunk).
@@ -36,6 +39,11 @@ cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32
 // rows [row0, row0 + nrows) of the GLOBAL bit rows / row_ptr -> run_x, run_row (global row numbers) at row_ptr[row]...
 cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww, uint32_t* run_x,
                          uint32_t* run_row, cudaStream_t st);
+
+// the same from the row slots the threshold kernel filled; rows with more runs than slots are re-extracted from the bit rows
+// when `overflow` is set
+cudaError_t compact_runs(const uint32_t* slots, const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww,
+                         int overflow, uint32_t* run_x, uint32_t* run_row, cudaStream_t st);
 
 // 2-D 8-connected components over row-runs (contrack.py:684-687): union-find with the smallest run index as root.
 cudaError_t ccl_init(uint32_t* parent, long begin, long end, cudaStream_t st);

@@ -315,13 +315,13 @@ def test_chunked_table_pipeline(eng, chunks):
 @pytest.mark.parametrize('opts', [{'tma': 0}, {'tma': 2}, {'tma': 1}, {'paint_runs': 0}, {'overlap_zero': 0, 'tma': 3},
                                   {'gpu_tables': 0, 'paint_runs': 0}, {'chunks': 4, 'chunk_min_planes': 1},
                                   {'chunks': 64, 'chunk_min_planes': 1, 'gpu_tables': 0},
-                                  {'chunks': 3, 'chunk_min_planes': 2, 'tma': 0}, {'label_fast': 0}])
+                                  {'chunks': 3, 'chunk_min_planes': 2, 'tma': 0}, {'label_fast': 0}, {'fused_runs': 0}, {'fused_runs': 0, 'tma': 0}])
 def test_kernel_variants_give_identical_results(eng, fixture_cube, golden, opts):
     """Every selectable kernel variant (load depth, bulk-copy staging with 16 warps, row-wise sparse paint, dense paint,
     host table phase) must produce the same bytes."""
     a, lat, lon = fixture_cube
     defaults = {'tma': 3, 'paint_runs': 1, 'overlap_zero': 1, 'gpu_tables': 1, 'chunks': 4, 'chunk_min_planes': 128,
-                'label_fast': 1}
+                'label_fast': 1, 'fused_runs': 1}
     for k, v in opts.items():
         eng.set_option(k, v)
     try:
@@ -372,3 +372,35 @@ def test_label_granular_track_matches_component_replay(eng, reference_run):
         else:
             assert np.array_equal(out[1][0], oracle.run_contrack(x, lat, lon, thr, '>=', 0.0, 1, False)), seed
     assert fast_used > 0 and fallback_used > 0, (fast_used, fallback_used)
+
+
+@pytest.mark.parametrize('tma', [3, 0])
+@pytest.mark.parametrize('W', [1440, 1024, 2048, 96, 33])
+def test_runs_from_threshold_kernel_edge_cases(eng, W, tma):
+    """Row-runs come out of the threshold kernel (8 slots per row): rows with more runs than slots (noise), runs that end
+    exactly at the row end when the row fills whole 32-word groups (W = 1024, 2048), full rows, alternating cells."""
+    import torch
+    T, H = 5, 40
+    rng = np.random.default_rng(W)
+    x = rng.standard_normal((T, H, W)).astype(np.float32) * 100           # white noise: hundreds of runs per row
+    x[1, 3, :] = 500                                                       # a full row
+    x[1, 5, W - 7:] = 500                                                  # run that reaches the row end
+    x[2, 7, ::2] = 500; x[2, 7, 1::2] = -500                               # alternating cells: W / 2 runs
+    x[3, :, :] = -500                                                      # empty plane ...
+    x[3, 10:14, W - 40 if W > 40 else 0:] = 500                            # ... with one block touching the right border
+    x[3, 10:14, :3] = 500                                                  # and the left one (date-line class)
+    lat, lon = regular_grid(H, W)
+    w = row_weights(lat, lon)
+    ref = oracle.run_contrack(x, lat, lon, 120, '>=', 0.2, 1, True)
+    eng.set_option('tma', tma)
+    try:
+        f, n = eng.run_contrack(torch.from_numpy(x).cuda(), w, 120, True, 0, 0.2, 1, True)
+        st = eng.stats()
+        eng.set_option('fused_runs', 0)
+        f0, n0 = eng.run_contrack(torch.from_numpy(x).cuda(), w, 120, True, 0, 0.2, 1, True)
+    finally:
+        eng.set_option('tma', 3); eng.set_option('fused_runs', 1)
+    assert np.array_equal(f.cpu().numpy(), ref) and n == len(np.unique(ref)) - 1
+    assert np.array_equal(f0.cpu().numpy(), ref)
+    if W >= 96:
+        assert st.get('slot_overflow', 0) == 1

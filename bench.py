@@ -237,7 +237,12 @@ def main():
         sys.stdout.flush()
         real_stdout = os.dup(1)
         os.dup2(2, 1)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        opts = None
+        try:                                   # NCCL kernels must not queue behind the cube-sized zero-fill grid
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local), pg_options=opts)
     from contrack_b200 import sharded
 
     T = args.T
@@ -341,6 +346,9 @@ def main():
         line['shard_ms']['note'] = ('rank 0 host wall clock per phase of the sharded step (phases end where the host has to '
                                     'wait: halo exchange, table counts, gathered counts, global phase, paint)')
         line['shard_table_bytes'] = last[-1]['table_bytes']
+        every = [None] * world
+        dist.all_gather_object(every, {k: round(v, 3) for k, v in line['shard_ms'].items() if k != 'note'})
+        line['shard_ms_all_ranks'] = every
 
     # ---- CPU baseline + parity on a bounded sample (rank 0 of a single-GPU run only) ---------------------------------
     if not args.no_cpu and world == 1:

@@ -430,8 +430,37 @@ def _buffer(key, nbytes, dev):
     return b
 
 
+_hp_streams = {}
+
+
+def high_priority_stream(device):
+    """The sharded step runs on a high-priority stream: its zero fill (a cube-sized grid on a lowest-priority side stream)
+    would otherwise sit in front of the small table / merge / paint kernels and of the NCCL kernels in the block scheduler.
+    Create the process group with ProcessGroupNCCL.Options(is_high_priority_stream=True) for the same reason."""
+    import torch
+    s = _hp_streams.get(device)
+    if s is None:
+        s = _hp_streams[device] = torch.cuda.Stream(device=device, priority=-1)
+    return s
+
+
 def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, thr_is_f32, op, overlap, persistence,
                          twosided, out=None, group=None):
+    """Collective over `group` (default: the world); see _run_contrack_sharded.  Work is enqueued on a high-priority stream
+    that is ordered after the caller's current stream; the call returns after the flag planes of this rank are written."""
+    import torch
+    dev = anom_local.device
+    hp = high_priority_stream(dev)
+    hp.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(hp):
+        res = _run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, thr_is_f32, op, overlap,
+                                    persistence, twosided, out, group)
+    torch.cuda.current_stream(dev).wait_stream(hp)
+    return res
+
+
+def _run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, thr_is_f32, op, overlap, persistence,
+                          twosided, out=None, group=None):
     """Collective over `group` (default: the world); tables travel device to device.  anom_local: torch CUDA tensor
     [T_local, H, W] holding planes [t_begin, t_begin + T_local) of the cube; `thresholds`: one value or T_local values
     (the local slice).  Returns (flag_local int32 CUDA tensor, n_features, info dict)."""

@@ -15,6 +15,7 @@ try:
     d = json.load(open("gpurun_out/${TAG}.json"))
     print({k: d.get(k) for k in ("value", "ms_per_step", "n_gpus", "features", "breakdown_ms", "shard_ms")})
     print("e2e", d.get("e2e", {}).get("value"))
+    for r in d.get("shard_ms_all_ranks", []): print(r)
 except Exception as e:
     print("no json:", e)
 PY

@@ -70,6 +70,10 @@ _PROTOS = {
     'ct_global_merge': (C.c_int, [_p, C.c_int, _longp, _p, C.c_long, C.c_long, C.c_int, C.c_int, _f64p, _p]),
     'ct_global_phase': (C.c_int, [_p, C.c_double, C.c_int, C.c_int, _p, _p, _longp, _p]),
     'ct_shard_paint_global': (C.c_int, [_p, _p, C.c_long, C.c_long, _p, _p]),
+    'ct_quantile_time': (C.c_int, [_p, _p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _p, _p]),
+    'ct_flag_count': (C.c_int, [_p, _p, C.c_long, C.c_int, C.c_int, C.c_int, _p, _p]),
+    'ct_divide_f32': (C.c_int, [_p, _p, C.c_size_t, C.c_float, _p, _p]),
+    'ct_gather_planes': (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int, C.c_int, _p, _p]),
     'ct_classify_rows': (None, [_f64p, C.c_int, C.c_int, _u8p]),
     'ct_numpy_pairwise_sum_rle': (C.c_double, [_f64p, _i64p, C.c_long]),
     'ct_calc_clim': (C.c_int, [_p, _p, C.c_long, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _p, _p]),

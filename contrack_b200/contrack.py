@@ -284,8 +284,39 @@ class contrack(object):
         return np.ascontiguousarray(np.broadcast_to(w, lat.shape), np.float64)
 
     # ---- calc_clim / calc_anom (contrack.py:458-581) ---------------------------------------------------------------
+    def calculate_gph_from_gp(self, gp_name='z', gp_unit='m**2 s**-2', gph_name='z_height'):
+        """contrack.py:386-425: geopotential height = geopotential / 9.80665 (float32 division on the device)."""
+        g = 9.80665
+        if self.ds[gp_name].attrs['units'] != gp_unit:
+            raise ValueError('Geopotential unit should be {} not {}'.format(gp_unit, self.ds[gp_name].attrs['units']))
+        a = self.ds[gp_name]
+        data = a.data
+        if str(data.dtype).endswith('float32'):
+            out = self._engine().divide(data if hasattr(data, 'is_cuda') else np.ascontiguousarray(data), g)
+        else:                                          # float64 input: numpy semantics are a plain float64 division
+            out = data / g
+        self.ds[gph_name] = self._variable(tuple(a.dims), out, {
+            'units': 'm', 'long_name': 'Geopotential Height', 'standard_name': 'geopotential height',
+            'history': 'Calculated from {} with g={}'.format(gp_name, g)})
+        logger.info('Calculating GPH from GP... DONE')
+
     def calc_mean(self, variable):
-        raise NotImplementedError('calc_mean is outside the tracking path (contrack.py:428-455)')
+        """contrack.py:428-455: mean along time (NaN skipped); float64 accumulation, float32 result."""
+        if not variable:
+            variable = 'z'
+        elif variable not in self.variables:
+            logger.warning("\n Variable '{}' not found. Select from {}.".format(variable, self.variables))
+            return None
+        if not hasattr(self, '_time_name'):
+            self.set_up(write=False)
+        data, dims, sort = self._cube_tlatlon(variable)
+        T = int(data.shape[0])
+        m = self._engine().calc_clim(data, np.zeros(T, np.int32), 1, 1)[0]
+        rest = [d for d in dims if d != self._time_name]
+        if rest != [self._latitude_name, self._longitude_name]:
+            m = m.permute(1, 0) if hasattr(m, 'permute') else m.T
+        return _ds.DataArray(m, tuple(rest), coords={d: self.ds[d] for d in rest if d in self.ds},
+                             attrs=dict(self.ds[variable].attrs), name=variable)
 
     def _groups(self, groupby):
         keys = time_group_keys(self.ds[self._time_name].data, groupby)
@@ -306,15 +337,30 @@ class contrack(object):
     def calc_anom(self, variable, window=1, smooth=1, groupby='dayofyear', clim=None):
         logger.info("Set up dimensions...")
         self._ensure_set_up()
-        if clim is not None:
-            raise NotImplementedError('external climatologies (contrack.py:551-565) are outside the tracking path')
-        logger.info('Calculating climatological mean from {}...'.format(variable))
         data, dims, sort = self._cube_tlatlon(variable)
-        uniq, gidx = self._groups(groupby)
         eng = self._engine()
-        clim_mean = eng.calc_clim(data, gidx, len(uniq), int(window))
-        clim_txt = 'from {} with running window time steps {}'.format(variable, window)
-        anom = eng.calc_anom(data, gidx, len(uniq), clim_mean, int(smooth))
+        if clim is None:
+            logger.info('Calculating climatological mean from {}...'.format(variable))
+            uniq, gidx = self._groups(groupby)
+            clim_mean = eng.calc_clim(data, gidx, len(uniq), int(window))
+            clim_txt = 'from {} with running window time steps {}'.format(variable, window)
+            ngroups = len(uniq)
+        else:
+            # contrack.py:551-565: a climatology that already has the `groupby` dimension, regridded to the grid of the
+            # input by nearest neighbour (xarray's reindex(method='nearest') = pandas Index.get_indexer)
+            logger.info('Reading climatological mean from {}...'.format(clim))
+            if isinstance(clim, str):
+                if xr is None:
+                    raise IOError('xarray is not installed: cannot open {}'.format(clim))
+                clim_da = xr.open_dataarray(clim)
+            else:
+                clim_da = clim
+            clim_txt = clim
+            if groupby not in clim_da.dims:
+                raise ValueError("the climatology needs the dimension '{}' (contrack.py:562 groups it by time, which the "
+                                 "reindex at :565 cannot handle)".format(groupby))
+            clim_mean, ngroups, gidx = self._regrid_climatology(clim_da, groupby, eng)
+        anom = eng.calc_anom(data, gidx, ngroups, clim_mean, int(smooth))
         if sort != [0, 1, 2]:
             inv = list(np.argsort(sort))
             anom = anom.permute(*inv).contiguous() if hasattr(anom, 'permute') else np.ascontiguousarray(
@@ -327,6 +373,66 @@ class contrack(object):
             'history': ' '.join(['Calculated from {} with input attributes:', 'smoothing time steps = {},',
                                  'climatology = {}.']).format(variable, smooth, clim_txt)})
         logger.info('Calculating Anomaly... DONE')
+
+    def _regrid_climatology(self, clim_da, groupby, eng):
+        """(clim [G, H, W] on this dataset's grid, G, group index of every time step) for an external climatology."""
+        import pandas as pd
+        cdims = tuple(clim_da.dims)
+        order = [cdims.index(d) for d in (groupby, self._latitude_name, self._longitude_name)]
+        cdata = clim_da.data
+        if order != [0, 1, 2]:
+            cdata = cdata.permute(*order).contiguous() if hasattr(cdata, 'permute') else np.ascontiguousarray(
+                np.transpose(np.asarray(cdata), order))
+        lat_c = _host(clim_da[self._latitude_name].data)
+        lon_c = _host(clim_da[self._longitude_name].data)
+        iy = pd.Index(lat_c).get_indexer(pd.Index(_host(self.ds[self._latitude_name].data)), method='nearest')
+        ix = pd.Index(lon_c).get_indexer(pd.Index(_host(self.ds[self._longitude_name].data)), method='nearest')
+        regridded = eng.gather_planes(cdata, iy, ix)
+        keys = _host(clim_da[groupby].data)
+        tkeys = time_group_keys(self.ds[self._time_name].data, groupby)
+        srt = np.argsort(keys, kind='stable')
+        pos = np.searchsorted(keys[srt], tkeys)
+        bad = (pos >= len(keys)) | (keys[srt][np.minimum(pos, len(keys) - 1)] != tkeys)
+        if bad.any():
+            raise KeyError('the climatology has no entry for {} {}'.format(groupby, sorted(set(tkeys[bad].tolist()))[:5]))
+        return regridded, len(keys), srt[pos].astype(np.int32)
+
+    def quantile(self, variable, q, latitude=None):
+        """ds[variable].sel(latitude=slice(a, b)).quantile(q, dim=time) of README.rst:150-151 on the device: float64
+        DataArray ('quantile', lat, lon).  `latitude` = slice(a, b) in coordinate values, label based and inclusive like
+        xarray's .sel (order as the coordinate runs: slice(80, 50) on a north-to-south axis)."""
+        self._ensure_set_up()
+        data, dims, sort = self._cube_tlatlon(variable)
+        lat = _host(self.ds[self._latitude_name].data)
+        y0, y1 = 0, len(lat)
+        if latitude is not None:
+            import pandas as pd
+            sl = pd.Index(lat).slice_indexer(latitude.start, latitude.stop)
+            y0, y1 = sl.start, sl.stop
+        qa = np.atleast_1d(np.asarray(q, np.float64))
+        out = self._engine().quantile_time(data, qa, y0, y1)
+        coords = {'quantile': _ds.DataArray(qa, ('quantile',)),
+                  self._latitude_name: _ds.DataArray(lat[y0:y1], (self._latitude_name,)),
+                  self._longitude_name: self.ds[self._longitude_name]}
+        return _ds.DataArray(out, ('quantile', self._latitude_name, self._longitude_name), coords=coords, name=variable)
+
+    def quantile_threshold(self, variable, q, latitude=None):
+        """README.rst:150-151: float(ds[variable].sel(latitude=...).quantile([q], dim='time').mean()) -- the objective
+        threshold recommended for run_contrack.  The per-grid-point quantiles come from the device (numpy's values bit for
+        bit); the final mean over the band is numpy's own nanmean on the host."""
+        qf = self.quantile(variable, [q], latitude)
+        return float(np.nanmean(qf.values))
+
+    def blocking_frequency(self, flag='flag', greater_than=1):
+        """README.rst:161: xr.where(ds[flag] > 1, 1, 0).sum(dim='time') / ntime * 100 -> DataArray (lat, lon) float64."""
+        self._ensure_set_up()
+        data, dims, sort = self._cube_tlatlon(flag)
+        cnt = self._engine().flag_count(data, greater_than)
+        ntime = int(data.shape[0])
+        cnt64 = cnt.double() if hasattr(cnt, 'is_cuda') else cnt.astype(np.int64)      # numpy: int64 / int -> float64
+        freq = cnt64 / ntime * 100
+        return _ds.DataArray(freq, (self._latitude_name, self._longitude_name),
+                             coords={d: self.ds[d] for d in (self._latitude_name, self._longitude_name)}, name=flag)
 
     def _variable(self, dims, data, attrs):
         if xr is not None and isinstance(self.ds, xr.Dataset):

@@ -33,6 +33,15 @@ cudaError_t anom(const float* z, long HW, long T, const int32_t* group_dev, cons
                  cudaStream_t st);
 }  // namespace cta
 
+namespace cte {
+cudaError_t quantile_time(const float* x, long T, int H, int W, int y0, int y1, const double* q_dev, int nq, double* out,
+                          cudaStream_t st);
+cudaError_t flag_count(const int32_t* flag, long T, int H, int W, int v, int32_t* count, int sm_count, cudaStream_t st);
+cudaError_t divide_f32(const float* in, size_t n, float g, float* out, cudaStream_t st);
+cudaError_t gather_planes(const float* src, int G, int Hs, int Ws, const int32_t* iy_dev, const int32_t* ix_dev, int H, int W,
+                          float* dst, cudaStream_t st);
+}  // namespace cte
+
 namespace {
 
 thread_local std::string g_err;
@@ -159,7 +168,7 @@ struct ct_ctx {
     std::vector<double> w_host;
     long launches = 0;
     // time-sharded run: packed tables of all ranks -> global tables (ct_global_merge), plane runs served by the caller
-    DevBuf sh_desc, b_sla, b_slb;
+    DevBuf sh_desc, b_sla, b_slb, x_q, x_idx;
     PinBuf hp_desc;
     ct_plane_runs_fn fetch_fn = nullptr;
     void* fetch_user = nullptr;
@@ -991,7 +1000,7 @@ void ct_destroy(ct_ctx* c) {
                       &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN,
                       &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
                       &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml,
-                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots};
+                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots, &c->x_q, &c->x_idx};
     for (DevBuf* b : bufs) b->release();
     c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release(); c->hp_desc.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
@@ -2007,6 +2016,55 @@ int ct_calc_anom(ct_ctx* c, const float* z_dev, long T, int H, int W, const int3
     CT_CUDA(cudaMemcpyAsync(c->a_group.p, group_host, (size_t)T * 4, cudaMemcpyHostToDevice, st));
     CT_CUDA(cudaStreamSynchronize(st));                               // caller may free group_host after return
     CT_CUDA(cta::anom(z_dev, (long)H * W, T, c->a_group.as<int32_t>(), clim_dev, smooth, anom_dev, st));
+    return CT_OK;
+}
+
+// ---- callers either side of the path: ct_extras.cu -------------------------------------------------------
+int ct_quantile_time(ct_ctx* c, const float* x_dev, long T, int H, int W, int y0, int y1, const double* q_host, int nq,
+                     double* out_dev, void* stream) {
+    if (!c || !x_dev || !q_host || !out_dev) return fail(CT_ERR_ARG, "null argument");
+    if (T <= 0 || H <= 0 || W <= 0 || y0 < 0 || y1 > H || y0 >= y1 || nq <= 0) return fail(CT_ERR_ARG, "bad shape / row range");
+    for (int i = 0; i < nq; ++i)
+        if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0)) return fail(CT_ERR_ARG, "Quantiles must be in the range [0, 1]");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CT_CUDA(c->x_q.ensure((size_t)nq * 8));
+    CT_CUDA(cudaMemcpyAsync(c->x_q.p, q_host, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaStreamSynchronize(st));                               // q_host may be a temporary of the caller
+    CT_CUDA(cte::quantile_time(x_dev, T, H, W, y0, y1, c->x_q.as<double>(), nq, out_dev, st));
+    return CT_OK;
+}
+
+int ct_flag_count(ct_ctx* c, const int32_t* flag_dev, long T, int H, int W, int greater_than, int32_t* count_dev,
+                  void* stream) {
+    if (!c || !flag_dev || !count_dev) return fail(CT_ERR_ARG, "null argument");
+    if (T < 0 || H <= 0 || W <= 0) return fail(CT_ERR_ARG, "bad shape");
+    CT_CUDA(cudaSetDevice(c->device));
+    CT_CUDA(cte::flag_count(flag_dev, T, H, W, greater_than, count_dev, c->sm_count, (cudaStream_t)stream));
+    return CT_OK;
+}
+
+int ct_divide_f32(ct_ctx* c, const float* in_dev, size_t n, float divisor, float* out_dev, void* stream) {
+    if (!c || !in_dev || !out_dev) return fail(CT_ERR_ARG, "null argument");
+    CT_CUDA(cudaSetDevice(c->device));
+    CT_CUDA(cte::divide_f32(in_dev, n, divisor, out_dev, (cudaStream_t)stream));
+    return CT_OK;
+}
+
+int ct_gather_planes(ct_ctx* c, const float* src_dev, int G, int Hs, int Ws, const int32_t* iy_host, const int32_t* ix_host,
+                     int H, int W, float* dst_dev, void* stream) {
+    if (!c || !src_dev || !iy_host || !ix_host || !dst_dev) return fail(CT_ERR_ARG, "null argument");
+    if (G <= 0 || Hs <= 0 || Ws <= 0 || H <= 0 || W <= 0 || H > 65535) return fail(CT_ERR_ARG, "bad shape");
+    for (int y = 0; y < H; ++y) if (iy_host[y] < 0 || iy_host[y] >= Hs) return fail(CT_ERR_ARG, "row index out of range");
+    for (int x = 0; x < W; ++x) if (ix_host[x] < 0 || ix_host[x] >= Ws) return fail(CT_ERR_ARG, "column index out of range");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CT_CUDA(c->x_idx.ensure((size_t)(H + W) * 4));
+    int32_t* d = c->x_idx.as<int32_t>();
+    CT_CUDA(cudaMemcpyAsync(d, iy_host, (size_t)H * 4, cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaMemcpyAsync(d + H, ix_host, (size_t)W * 4, cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaStreamSynchronize(st));
+    CT_CUDA(cte::gather_planes(src_dev, G, Hs, Ws, d, d + H, H, W, dst_dev, st));
     return CT_OK;
 }
 

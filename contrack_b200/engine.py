@@ -154,6 +154,64 @@ class Engine(object):
                                          C.c_void_p(stream)))
         return outd.cpu().numpy() if was_host else outd
 
+    # ---- callers either side of the path (ct_extras.cu) -----------------------------------------------
+    def quantile_time(self, x, q, y0=0, y1=None):
+        """np.nanquantile(x[:, y0:y1, :], q, axis=0) ('linear') of a float32 cube (numpy or torch CUDA): float64
+        [len(q), y1-y0, W], same kind as x (README.rst:150-151)."""
+        import torch
+        xd, was_host = self._to_device(x)
+        T, H, W = (int(s) for s in xd.shape)
+        y1 = H if y1 is None else int(y1)
+        qa = np.ascontiguousarray(np.atleast_1d(q), np.float64)
+        if ((qa < 0) | (qa > 1) | np.isnan(qa)).any():
+            raise ValueError('Quantiles must be in the range [0, 1]')
+        out = torch.empty((len(qa), y1 - int(y0), W), dtype=torch.float64, device=xd.device)
+        stream = torch.cuda.current_stream(xd.device).cuda_stream
+        _lib.check(self.lib.ct_quantile_time(self.handle, C.c_void_p(xd.data_ptr()), T, H, W, int(y0), y1,
+                                             _lib.ptr(qa, _lib._f64p), len(qa), C.c_void_p(out.data_ptr()),
+                                             C.c_void_p(stream)))
+        return out.cpu().numpy() if was_host else out
+
+    def flag_count(self, flag, greater_than=1):
+        """(flag > greater_than).sum(axis=0) as int32 [H, W] (README.rst:161)."""
+        import torch
+        if _is_torch(flag):
+            if not flag.is_cuda:
+                raise ValueError('torch input must live on a CUDA device (pass numpy for host data)')
+            fd, was_host = flag.contiguous().to(torch.int32), False
+        else:
+            fd, was_host = torch.from_numpy(np.ascontiguousarray(np.asarray(flag), np.int32)).to('cuda:%d' % self.device), True
+        T, H, W = (int(s) for s in fd.shape)
+        out = torch.empty((H, W), dtype=torch.int32, device=fd.device)
+        stream = torch.cuda.current_stream(fd.device).cuda_stream
+        _lib.check(self.lib.ct_flag_count(self.handle, C.c_void_p(fd.data_ptr()), T, H, W, int(greater_than),
+                                          C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+        return out.cpu().numpy() if was_host else out
+
+    def divide(self, x, divisor):
+        """x / float32(divisor) in float32 (contrack.py:417-419)."""
+        import torch
+        xd, was_host = self._to_device(x)
+        out = torch.empty_like(xd)
+        stream = torch.cuda.current_stream(xd.device).cuda_stream
+        _lib.check(self.lib.ct_divide_f32(self.handle, C.c_void_p(xd.data_ptr()), int(xd.numel()), float(np.float32(divisor)),
+                                          C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+        return out.cpu().numpy() if was_host else out
+
+    def gather_planes(self, src, iy, ix):
+        """dst[g, y, x] = src[g, iy[y], ix[x]] (nearest-neighbour regrid with the caller's index maps, contrack.py:565)."""
+        import torch
+        sd, was_host = self._to_device(src)
+        G, Hs, Ws = (int(s) for s in sd.shape)
+        iy = np.ascontiguousarray(iy, np.int32)
+        ix = np.ascontiguousarray(ix, np.int32)
+        out = torch.empty((G, len(iy), len(ix)), dtype=torch.float32, device=sd.device)
+        stream = torch.cuda.current_stream(sd.device).cuda_stream
+        _lib.check(self.lib.ct_gather_planes(self.handle, C.c_void_p(sd.data_ptr()), G, Hs, Ws, _lib.ptr(iy, _lib._i32p),
+                                             _lib.ptr(ix, _lib._i32p), len(iy), len(ix), C.c_void_p(out.data_ptr()),
+                                             C.c_void_p(stream)))
+        return out.cpu().numpy() if was_host else out
+
     # ------------------------------------------------------------------------------------------------------------
     def run_lifecycle(self, flag, var, w):
         """flag [T,H,W] integer, var [T,H,W] float32/float64 (numpy or torch CUDA, C-order time/lat/lon), w [H] float64 row

@@ -265,6 +265,23 @@ int ct_calc_clim(ct_ctx* ctx, const float* z_dev, long T, int H, int W, const in
 int ct_calc_anom(ct_ctx* ctx, const float* z_dev, long T, int H, int W, const int32_t* group_host, int G,
                  const float* clim_dev, int smooth, float* anom_dev, void* stream);
 
+/* ---- callers either side of the path -------------------------------------------------------------------
+ * ct_quantile_time   README.rst:150-151: ds[var].sel(latitude=band).quantile(q, dim='time') -- numpy's nanquantile with the
+ *                    'linear' method along time for every grid point of rows [y0, y1): out_dev [nq, y1-y0, W] float64, bit
+ *                    for bit what numpy returns for a float32 input and float64 q (exact order statistics by radix select;
+ *                    the interpolation in numpy's operation order).  NaN are skipped; all-NaN points give NaN.
+ * ct_flag_count      README.rst:161: xr.where(flag > greater_than, 1, 0).sum(dim='time') -> count_dev [H, W] int32
+ * ct_divide_f32      contrack.py:417-419 (calculate_gph_from_gp): out = in / divisor in float32 (IEEE division)
+ * ct_gather_planes   contrack.py:565 (clim.reindex(lat, lon, method='nearest')): dst[g, y, x] = src[g, iy[y], ix[x]]; the
+ *                    nearest-neighbour index maps come from the caller (pandas Index.get_indexer, as xarray does) */
+int ct_quantile_time(ct_ctx* ctx, const float* x_dev, long T, int H, int W, int y0, int y1, const double* q_host, int nq,
+                     double* out_dev, void* stream);
+int ct_flag_count(ct_ctx* ctx, const int32_t* flag_dev, long T, int H, int W, int greater_than, int32_t* count_dev,
+                  void* stream);
+int ct_divide_f32(ct_ctx* ctx, const float* in_dev, size_t n, float divisor, float* out_dev, void* stream);
+int ct_gather_planes(ct_ctx* ctx, const float* src_dev, int G, int Hs, int Ws, const int32_t* iy_host, const int32_t* ix_host,
+                     int H, int W, float* dst_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -280,3 +280,54 @@ def run_lifecycle(flag, var, lat, lon, time_values, force=False):
             com_lon.append(comloncon)
             com_lat.append(comlatcon)
     return sorted(list(zip(block_id, time, com_lon, com_lat, intensity, size)), key=lambda x: (x[0], x[1]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Callers either side of the path: the README's recipes, restated with the same numpy / pandas calls
+# xarray makes.
+# ---------------------------------------------------------------------------------------------------------------
+
+def quantile_time(x, q):
+    """README.rst:150-151 ``ds[var].quantile(q, dim='time')``: xarray (Variable.quantile) calls
+    ``np.nanquantile(data, q float64 array, axis=time, method='linear')`` for float data."""
+    return np.nanquantile(np.asarray(x), np.atleast_1d(np.asarray(q, dtype=np.float64)), axis=0)
+
+
+def label_slice(coord, start, stop):
+    """positions selected by ``.sel(dim=slice(start, stop))`` (label based, both ends inclusive): pandas slice_indexer."""
+    import pandas as pd
+    return pd.Index(np.asarray(coord)).slice_indexer(start, stop)
+
+
+def quantile_threshold(x, lat, q, lat_start, lat_stop):
+    """README.rst:151 ``ds[var].sel(latitude=slice(a, b)).quantile([q], dim='time').mean()`` as a Python float."""
+    sl = label_slice(lat, lat_start, lat_stop)
+    return float(np.nanmean(quantile_time(np.asarray(x)[:, sl, :], [q])))
+
+
+def blocking_frequency(flag, greater_than=1):
+    """README.rst:161 ``xr.where(flag > 1, 1, 0).sum(dim='time') / ntime * 100``."""
+    flag = np.asarray(flag)
+    return np.where(flag > greater_than, 1, 0).sum(axis=0) / flag.shape[0] * 100
+
+
+def gph_from_gp(gp):
+    """contrack.py:417-419 ``data / g`` with g = 9.80665 (float32 data stay float32)."""
+    return np.asarray(gp) / 9.80665
+
+
+def nearest_index(src_coord, dst_coord):
+    """``reindex(..., method='nearest')`` (contrack.py:565): pandas Index.get_indexer, which xarray delegates to."""
+    import pandas as pd
+    return pd.Index(np.asarray(src_coord)).get_indexer(pd.Index(np.asarray(dst_coord)), method='nearest')
+
+
+def calc_anom_external(z, time_keys, clim, clim_keys, clim_lat, clim_lon, lat, lon, smooth=1):
+    """contrack.py:551-570 with a supplied climatology [G, Hc, Wc] that has the group dimension: nearest-neighbour
+    regrid, ``z.groupby(key) - clim``, centred rolling mean over time."""
+    clim = np.asarray(clim)[:, nearest_index(clim_lat, lat)][:, :, nearest_index(clim_lon, lon)]
+    clim_keys = np.asarray(clim_keys)
+    order = np.argsort(clim_keys, kind='stable')
+    pos = order[np.searchsorted(clim_keys[order], np.asarray(time_keys))]
+    dev = np.asarray(z) - clim[pos]
+    return _rolling_mean_centered(dev, smooth)

@@ -149,6 +149,34 @@ def main():
                                 anom_attrs=dict(c.ds['anom'].attrs)))
         print('anom', seed, clim.shape, an.dtype, int(np.isnan(an).sum()))
 
+    # calculate_gph_from_gp (contrack.py:386-425) and calc_anom with a supplied climatology on a coarser grid (551-565)
+    rng = np.random.default_rng(21)
+    T, H, W = 40, 9, 16
+    t = days(T, '2001-02-20')
+    la, lo = regular_grid(H, W)
+    gp = (53000 + 900 * rng.standard_normal((T, H, W))).astype(np.float32)
+    c = contrack()
+    ds = xr.Dataset({'z': (('time', 'latitude', 'longitude'), gp, {'units': 'm**2 s**-2', 'long_name': 'Geopotential'})},
+                    coords={'time': t, 'latitude': la, 'longitude': lo})
+    c.read_xarray(ds)
+    c.set_up(force=True)
+    c.calculate_gph_from_gp(gp_name='z', gp_unit='m**2 s**-2', gph_name='z_height')
+    gph = np.asarray(c.ds['z_height'].data)
+    Hc, Wc = 5, 7
+    clat = np.linspace(90, -90, Hc).astype(np.float32)
+    clon = (np.arange(Wc) * (360.0 / Wc)).astype(np.float32)
+    cdoy = np.arange(1, 367)
+    cl = (5400 + 60 * np.cos(2 * np.pi * cdoy / 366.0)[:, None, None] + 20 * rng.standard_normal((366, Hc, Wc))).astype(np.float32)
+    clim_da = xr.DataArray(cl, ('dayofyear', 'latitude', 'longitude'),
+                           coords={'dayofyear': cdoy, 'latitude': clat, 'longitude': clon})
+    c.calc_anom('z_height', smooth=3, clim=clim_da)
+    an = np.asarray(c.ds['anom'].data)
+    np.savez_compressed(os.path.join(HERE, 'gph_extclim_ref.npz'), gp=gp, time=t, gph=gph, clim=cl, clim_lat=clat,
+                        clim_lon=clon, clim_doy=cdoy, anom=an)
+    out['gph_extclim'] = dict(file='gph_extclim_ref.npz', shape=[T, H, W], smooth=3, gph_dtype=str(gph.dtype),
+                              gph_attrs=dict(c.ds['z_height'].attrs), nan_anom=int(np.isnan(an).sum()))
+    print('gph / external clim', gph.dtype, an.dtype, int(np.isnan(an).sum()))
+
     json.dump(out, open(os.path.join(HERE, 'reference_run.json'), 'w'), indent=0)
     print('wrote reference_run.json')
 

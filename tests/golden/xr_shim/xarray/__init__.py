@@ -158,6 +158,17 @@ class DataArray(object):
         return DataArray(out.astype(self.data.dtype), dims, {d: c for d, c in self.coords.items() if d != dim},
                          self.attrs, self.name)
 
+    def reindex(self, method=None, **indexers):
+        """DataArray.reindex(dim=new_coord, method='nearest'): pandas Index.get_indexer per dimension (what xarray does)."""
+        data, coords = self.data, dict(self.coords)
+        for d, new in indexers.items():
+            new = np.asarray(new.data if _is_da(new) else new)
+            idx = pd.Index(np.asarray(self._coord(d).data)).get_indexer(pd.Index(new), method=method)
+            assert (idx >= 0).all(), 'shim: reindex without fill values only'
+            data = np.take(data, idx, axis=self.dims.index(d))
+            coords[d] = DataArray(new, (d,), name=d)
+        return DataArray(data, self.dims, coords, self.attrs, self.name)
+
     def fillna(self, other):
         o = other.data if _is_da(other) else other
         return DataArray(np.where(np.isnan(self.data), o, self.data).astype(self.data.dtype), self.dims, self.coords,

@@ -139,3 +139,30 @@ def test_reference_run_calc_clim_anom(reference_run):
         an = oracle.calc_anom(d['z'], g, r['window'], r['smooth'])
         assert np.array_equal(np.isnan(an), np.isnan(d['anom']))
         np.testing.assert_allclose(an, d['anom'], rtol=1e-5, atol=4e-3)
+
+
+def test_reference_run_gph_and_external_climatology(reference_run):
+    import os
+    from contrack_b200.contrack import time_group_keys
+    r = reference_run['gph_extclim']
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', r['file']))
+    gph = oracle.gph_from_gp(d['gp'])
+    assert gph.dtype == np.float32 and np.array_equal(gph, d['gph'])                   # float32 division: bit exact
+    T, H, W = r['shape']
+    lat, lon = regular_grid(H, W)
+    an = oracle.calc_anom_external(d['gph'], time_group_keys(d['time'], 'dayofyear'), d['clim'], d['clim_doy'],
+                                   d['clim_lat'], d['clim_lon'], lat, lon, r['smooth'])
+    assert np.array_equal(np.isnan(an), np.isnan(d['anom'])) and int(np.isnan(an).sum()) == r['nan_anom']
+    np.testing.assert_allclose(an, d['anom'], rtol=1e-5, atol=4e-3)
+
+
+def test_readme_recipes_restated():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((50, 7, 9)).astype(np.float32)
+    lat = np.linspace(90, -90, 7).astype(np.float32)
+    thr = oracle.quantile_threshold(x, lat, 0.9, 80, 20)
+    sl = oracle.label_slice(lat, 80, 20)
+    assert (sl.start, sl.stop) == (1, 3)
+    assert thr == float(np.mean(np.quantile(x[:, 1:3].astype(np.float32), np.array([0.9]), axis=0)))
+    f = (rng.random((20, 4, 5)) * 4).astype(np.int32)
+    assert np.array_equal(oracle.blocking_frequency(f), (f > 1).sum(0) / 20 * 100)

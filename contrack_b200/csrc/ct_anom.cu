@@ -55,7 +55,17 @@ __global__ void __launch_bounds__(256) k_group_mean(const float* __restrict__ z,
 #pragma unroll
     for (int i = 0; i < V; ++i) { sum[i] = 0.0; cnt[i] = 0; }
     const int e = gptr[g + 1];
-    for (int k = gptr[g]; k < e; ++k) {
+    int k = gptr[g];
+    for (; k + 4 <= e; k += 4) {                       // four planes in flight per thread (same summation order)
+        float v[4][V];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load_stream<V>(z + (long)gidx[k + u] * HW + cell, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < V; ++i) if (v[u][i] == v[u][i]) { sum[i] += (double)v[u][i]; ++cnt[i]; }
+    }
+    for (; k < e; ++k) {
         float v[V];
         load_stream<V>(z + (long)gidx[k] * HW + cell, v);
 #pragma unroll
@@ -154,6 +164,84 @@ __global__ void __launch_bounds__(256) k_anom(const float* __restrict__ z, long 
     store_stream<V>(anom + t * HW + cell, out);
 }
 
+// The same arithmetic with the time axis cut into chunks that start where the group index wraps (one chunk per year for a
+// day-of-year climatology): grid (chunk, cell group), chunk fastest, so the blocks that are resident together are the SAME
+// cells in all years, walking the groups in step -- clim[g] is fetched from HBM once and then served from L2 to the other
+// years, instead of once per year (4 B/cell saved); z[t-1] .. of the window was read by the same thread one step earlier.
+template <int V>
+__global__ void __launch_bounds__(256) k_anom_chunks(const float* __restrict__ z, long HW, long T,
+                                                     const int32_t* __restrict__ chunk_start, const int32_t* __restrict__ group,
+                                                     const float* __restrict__ clim, int smooth, float* __restrict__ anom) {
+    const long cell = ((long)blockIdx.y * blockDim.x + threadIdx.x) * V;
+    if (cell >= HW) return;
+    const long t0 = chunk_start[blockIdx.x], t1 = chunk_start[blockIdx.x + 1];
+    const int left = smooth / 2;
+    if (smooth == 1) {
+#pragma unroll 4
+        for (long t = t0; t < t1; ++t) {
+            float zv[V], cv[V], out[V];
+            load_stream<V>(z + t * HW + cell, zv);
+            load<V>(clim + (long)group[t] * HW + cell, cv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) out[i] = zv[i] - cv[i];
+            store_stream<V>(anom + t * HW + cell, out);
+        }
+        return;
+    }
+    if (smooth == 2) {
+        // window {t-1, t}: the previous deviation stays in registers, every plane is loaded once; same summation order as
+        // the generic loop below (0 + dev[t-1] + dev[t] in float64, divided by 2, rounded once)
+        float prev[V];
+        if (t0 >= 1) {
+            float zv[V], cv[V];
+            load<V>(z + (t0 - 1) * HW + cell, zv);
+            load<V>(clim + (long)group[t0 - 1] * HW + cell, cv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) prev[i] = zv[i] - cv[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) prev[i] = NAN;                  // out[0] = NaN: the window is incomplete
+        }
+#pragma unroll 4
+        for (long t = t0; t < t1; ++t) {
+            float zv[V], cv[V], out[V];
+            load_stream<V>(z + t * HW + cell, zv);
+            load<V>(clim + (long)group[t] * HW + cell, cv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float d = zv[i] - cv[i];
+                out[i] = (t == 0) ? NAN : (float)((0.0 + (double)prev[i] + (double)d) / 2);
+                prev[i] = d;
+            }
+            store_stream<V>(anom + t * HW + cell, out);
+        }
+        return;
+    }
+    // deviations of the window in a register ring would need a compile-time size: re-read instead (L1 / L2 hits)
+    for (long t = t0; t < t1; ++t) {
+        const long a = t - left, b = a + smooth;
+        float out[V];
+        if (a < 0 || b > T) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) out[i] = NAN;
+        } else {
+            double sum[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) sum[i] = 0.0;
+            for (long k = a; k < b; ++k) {
+                float zv[V], cv[V];
+                load<V>(z + k * HW + cell, zv);
+                load<V>(clim + (long)group[k] * HW + cell, cv);
+#pragma unroll
+                for (int i = 0; i < V; ++i) sum[i] += (double)(zv[i] - cv[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) out[i] = (float)(sum[i] / smooth);
+        }
+        store_stream<V>(anom + t * HW + cell, out);
+    }
+}
+
 inline unsigned blocks_for(long n, int per) { return (unsigned)((n + per - 1) / per); }
 
 }  // namespace
@@ -182,6 +270,18 @@ cudaError_t anom(const float* z, long HW, long T, const int32_t* group_dev, cons
         if (v4) k_anom<4><<<dim3(blocks_for(HW, 1024), nt), 256, 0, st>>>(z, HW, T, t0, group_dev, clim, smooth, out);
         else k_anom<1><<<dim3(blocks_for(HW, 256), nt), 256, 0, st>>>(z, HW, T, t0, group_dev, clim, smooth, out);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t anom_chunks(const float* z, long HW, long T, const int32_t* chunk_start_dev, int nchunks, const int32_t* group_dev,
+                        const float* clim, int smooth, float* out, cudaStream_t st) {
+    const bool v4 = HW % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(clim) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (nchunks <= 0) return cudaSuccess;
+    if (v4) k_anom_chunks<4><<<dim3((unsigned)nchunks, blocks_for(HW, 1024)), 256, 0, st>>>(z, HW, T, chunk_start_dev, group_dev,
+                                                                                         clim, smooth, out);
+    else k_anom_chunks<1><<<dim3((unsigned)nchunks, blocks_for(HW, 256)), 256, 0, st>>>(z, HW, T, chunk_start_dev, group_dev,
+                                                                                      clim, smooth, out);
     return cudaGetLastError();
 }
 

@@ -31,6 +31,8 @@ cudaError_t group_mean(const float* z, long HW, int G, const int32_t* gptr_dev, 
 cudaError_t clim_smooth(const float* gmean, long HW, int G, int window, float* clim, cudaStream_t st);
 cudaError_t anom(const float* z, long HW, long T, const int32_t* group_dev, const float* clim, int smooth, float* out,
                  cudaStream_t st);
+cudaError_t anom_chunks(const float* z, long HW, long T, const int32_t* chunk_start_dev, int nchunks, const int32_t* group_dev,
+                        const float* clim, int smooth, float* out, cudaStream_t st);
 }  // namespace cta
 
 namespace cte {
@@ -2012,10 +2014,33 @@ int ct_calc_anom(ct_ctx* c, const float* z_dev, long T, int H, int W, const int3
         if (group_host[t] < 0 || group_host[t] >= G) return fail(CT_ERR_ARG, "group index out of range at t=%ld", t);
     CT_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CT_CUDA(c->a_group.ensure((size_t)T * 4));
-    CT_CUDA(cudaMemcpyAsync(c->a_group.p, group_host, (size_t)T * 4, cudaMemcpyHostToDevice, st));
-    CT_CUDA(cudaStreamSynchronize(st));                               // caller may free group_host after return
-    CT_CUDA(cta::anom(z_dev, (long)H * W, T, c->a_group.as<int32_t>(), clim_dev, smooth, anom_dev, st));
+    // time chunks: a new chunk where the group index wraps (a new year of a day-of-year climatology); long chunks are cut
+    // so that there are enough of them to fill the machine, at most 4096
+    std::vector<int32_t> cs;
+    cs.push_back(0);
+    for (long t = 1; t < T; ++t) if (group_host[t] < group_host[t - 1]) cs.push_back((int32_t)t);
+    cs.push_back((int32_t)T);
+    if (T >= 2147483647L) return fail(CT_ERR_CAPACITY, "T must be < 2^31");
+    while ((long)cs.size() - 1 < 24 && (long)cs.size() - 1 < T) {       // few cycles: halve every chunk
+        std::vector<int32_t> h;
+        for (size_t i = 0; i + 1 < cs.size(); ++i) {
+            h.push_back(cs[i]);
+            if (cs[i + 1] - cs[i] > 1) h.push_back(cs[i] + (cs[i + 1] - cs[i]) / 2);
+        }
+        h.push_back((int32_t)T);
+        if (h.size() == cs.size()) break;
+        cs.swap(h);
+    }
+    const int nchunks = (int)cs.size() - 1;
+    CT_CUDA(c->a_group.ensure((size_t)(T + nchunks + 2) * 4));
+    int32_t* gdev = c->a_group.as<int32_t>();
+    CT_CUDA(cudaMemcpyAsync(gdev, group_host, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaMemcpyAsync(gdev + T, cs.data(), (size_t)(nchunks + 1) * 4, cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaStreamSynchronize(st));                               // caller may free group_host after return; cs is local
+    if (nchunks <= 65535)
+        CT_CUDA(cta::anom_chunks(z_dev, (long)H * W, T, gdev + T, nchunks, gdev, clim_dev, smooth, anom_dev, st));
+    else
+        CT_CUDA(cta::anom(z_dev, (long)H * W, T, gdev, clim_dev, smooth, anom_dev, st));
     return CT_OK;
 }
 

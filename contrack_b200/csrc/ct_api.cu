@@ -147,7 +147,8 @@ struct ct_ctx {
     long opt_paint_runs = 1;                 // sparse paint by runs (1) or by rows (0)
     long opt_gpu_tables = 1;                 // step 3 + 3-D labels on the device (single-GPU path)
     long opt_chunks = 4;                     // time chunks of the pipelined run (tables of chunk k under threshold k+1)
-    long opt_chunk_min_planes = 128;         // ... but never fewer planes per chunk than this
+    long opt_chunk_min_planes = 1024;        // ... but never fewer planes per chunk than this (launch latency of ~45 small
+                                             // kernels and 3 host round trips per chunk)
     long tb_planes = 0, tb_runs = 0, tb_comps = 0, tb_seams = 0, tb_segs = 0, tb_pairs = 0;   // tables built so far
     std::vector<cudaEvent_t> ev_chunk;
     long opt_host_sparse = 1;                // host-buffer call: flag travels back as row-runs, not as a dense cube

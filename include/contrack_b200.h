@@ -59,7 +59,7 @@ void ct_destroy(ct_ctx* ctx);
  *   "paint_runs"   [1] sparse paint by row-runs; 0 = by bit rows
  *   "gpu_tables"   [1] steps 3 / 4a / 4b on the device; 0 = the whole ordered phase on the host (what a sharded run uses)
  *   "chunks"       [4] time chunks of ct_run_contrack's pipeline (table kernels of chunk k run while chunk k+1 is being
- *                  thresholded); "chunk_min_planes" [128] = smallest chunk
+ *                  thresholded); "chunk_min_planes" [1024] = smallest chunk
  *   "host_sparse"  [1] ct_run_contrack_host returns the result as row-runs expanded by host threads; 0 = dense copy
  *   "host_threads" [0 = automatic] host threads used by ct_run_contrack_host */
 int ct_set_option(ct_ctx* ctx, const char* key, long value);

@@ -309,7 +309,7 @@ def test_chunked_table_pipeline(eng, chunks):
         assert np.array_equal(f4, st['label3d'])
     finally:
         eng.set_option('chunks', 4)
-        eng.set_option('chunk_min_planes', 128)
+        eng.set_option('chunk_min_planes', 1024)
 
 
 @pytest.mark.parametrize('opts', [{'tma': 0}, {'tma': 2}, {'tma': 1}, {'paint_runs': 0}, {'overlap_zero': 0, 'tma': 3},
@@ -320,7 +320,7 @@ def test_kernel_variants_give_identical_results(eng, fixture_cube, golden, opts)
     """Every selectable kernel variant (load depth, bulk-copy staging with 16 warps, row-wise sparse paint, dense paint,
     host table phase) must produce the same bytes."""
     a, lat, lon = fixture_cube
-    defaults = {'tma': 3, 'paint_runs': 1, 'overlap_zero': 1, 'gpu_tables': 1, 'chunks': 4, 'chunk_min_planes': 128,
+    defaults = {'tma': 3, 'paint_runs': 1, 'overlap_zero': 1, 'gpu_tables': 1, 'chunks': 4, 'chunk_min_planes': 1024,
                 'label_fast': 1, 'fused_runs': 1}
     for k, v in opts.items():
         eng.set_option(k, v)

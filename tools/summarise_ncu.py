@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Summaries of the ncu outputs that tools/profile_step.sh leaves in gpurun_out/ -> profiles/ (run on the build box).
 
-  python tools/summarise_ncu.py <tag>      e.g. r1b  ->  profiles/<tag>_ncu_full_T512.csv, profiles/<tag>_launches_T10957.csv,
-                                                         profiles/<tag>_launch_shares_T10957.txt, profiles/ncu_traffic.json
+  python tools/summarise_ncu.py <tag>   e.g. r1c -> profiles/<tag>_ncu_full.csv, profiles/<tag>_launches_T10957.csv,
+                                                    profiles/<tag>_launch_shares_T10957.txt, profiles/ncu_traffic.json
 """
 import collections
 import csv
@@ -17,44 +17,58 @@ OUT = os.path.join(ROOT, 'gpurun_out')
 PROF = os.path.join(ROOT, 'profiles')
 METRICS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
            'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
-           'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size',
-           'launch__block_size', 'smsp__inst_executed.sum', 'lts__t_sectors_srcunit_tex_op_read.sum',
+           'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+           'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum',
+           'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sectors_srcunit_tex_op_read.sum',
            'lts__t_sectors_srcunit_tex_op_write.sum']
+T_PROF, H, W = 1461, 721, 1440        # tools/profile_step.sh
 
 
 def to_bytes(v, unit):
     return float(v) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
 
 
+def short(name):
+    return name.split('(')[0].replace('void ', '').replace('<unnamed>::', '')
+
+
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
-    T_prof, H, W = 512, 721, 1440
-    raw = subprocess.run(['ncu', '-i', os.path.join(OUT, 'prof_T%d.ncu-rep' % T_prof), '--page', 'raw', '--csv'],
+    tag = sys.argv[1] if len(sys.argv) > 1 else 'r1c'
+    raw = subprocess.run(['ncu', '-i', os.path.join(OUT, '%s_full.ncu-rep' % tag), '--page', 'raw', '--csv'],
                          capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units = rows[0], rows[1]
-    idx = [head.index(m) for m in METRICS]
-    with open(os.path.join(PROF, '%s_ncu_full_T%d.csv' % (tag, T_prof)), 'w', newline='') as f:
-        wr = csv.writer(f)
-        wr.writerow(METRICS)
-        wr.writerow([units[i] for i in idx])
-        for r in rows[2:]:
-            wr.writerow([r[i] for i in idx])
-    cells = T_prof * H * W
-    traffic = {}
-    ir, iw, ik = head.index('dram__bytes_read.sum'), head.index('dram__bytes_write.sum'), head.index('Kernel Name')
-    it = head.index('gpu__time_duration.sum')
+    metrics = [m for m in METRICS if m in head]
+    idx = [head.index(m) for m in metrics]
+    # the target runs every kernel twice (warm-up pass + second pass): keep the second instance of each kernel
+    last = collections.OrderedDict()
     for r in rows[2:]:
-        name = 'threshold_bits' if 'k_threshold' in r[ik] else 'zero_fill' if 'k_zero_fill' in r[ik] else 'paint'
+        last[short(r[head.index('Kernel Name')])] = r
+    with open(os.path.join(PROF, '%s_ncu_full.csv' % tag), 'w', newline='') as f:
+        wr = csv.writer(f)
+        wr.writerow(['# ncu --set full --clock-control none, tools/prof_target.py %d (cube %dx%dx%d, %.2f GB float32); second '
+                     'instance of every kernel' % (T_PROF, T_PROF, H, W, T_PROF * H * W * 4 / 1e9)])
+        wr.writerow(metrics)
+        wr.writerow([units[i] for i in idx])
+        for r in last.values():
+            wr.writerow([short(r[i]) if i == idx[0] else r[i] for i in idx])
+    cells = T_PROF * H * W
+    traffic = {}
+    ir, iw, it = head.index('dram__bytes_read.sum'), head.index('dram__bytes_write.sum'), head.index('gpu__time_duration.sum')
+    names = {'k_threshold': 'threshold_bits', 'k_zero_fill': 'zero_fill', 'k_paint': 'paint', 'k_anom': 'calc_anom',
+             'k_group_mean': 'group_mean', 'k_clim_smooth': 'clim_smooth', 'k_flag_count': 'flag_count',
+             'k_compact_runs': 'compact_runs'}
+    for k, r in last.items():
+        name = next((v for p, v in names.items() if p in k), k)
         rd, wrb = to_bytes(r[ir], units[ir]), to_bytes(r[iw], units[iw])
-        traffic[name] = {'kernel': r[ik].split('(')[0].replace('void ', ''), 'cells': cells, 'dram_read_bytes': rd,
-                         'dram_write_bytes': wrb, 'bytes_per_cell': (rd + wrb) / cells,
-                         'duration_us_under_ncu': float(r[it])}
+        traffic[name] = {'kernel': k, 'cells': cells, 'dram_read_bytes': rd, 'dram_write_bytes': wrb,
+                         'bytes_per_cell': (rd + wrb) / cells, 'duration_ms_under_ncu': float(r[it]),
+                         'dram_gbs_under_ncu': (rd + wrb) / float(r[it]) / 1e6}
     with open(os.path.join(PROF, 'ncu_traffic.json'), 'w') as f:
-        json.dump({'source': '%s_ncu_full_T%d.csv (ncu --set full, T=%d x %d x %d)' % (tag, T_prof, T_prof, H, W),
-                   'kernels': traffic}, f, indent=1)
+        json.dump({'source': '%s_ncu_full.csv (ncu --set full, T=%d x %d x %d)' % (tag, T_PROF, H, W), 'kernels': traffic}, f,
+                  indent=1)
     # launch list: keep the csv, add a per-kernel share table of the LAST step (the first is the warm-up)
-    src = os.path.join(OUT, 'launches_T10957.csv')
+    src = os.path.join(OUT, '%s_launches_T10957.csv' % tag)
     lines = [ln for ln in open(src) if not ln.startswith('==')]
     with open(os.path.join(PROF, '%s_launches_T10957.csv' % tag), 'w') as f:
         f.writelines(lines)
@@ -62,12 +76,13 @@ def main():
     h = rows[0]
     kn, mv = h.index('Kernel Name'), h.index('Metric Value')
     body = [r for r in rows[1:] if len(r) > mv]
+    # bench.py: warm-up step, timed step, then two single-launch steps (chunks=1) for `achieved_alone`: the timed step is
+    # the second group of threshold launches (4 chunk launches each)
     thr = [i for i, r in enumerate(body) if 'k_threshold' in r[kn]]
-    step = body[thr[-1]:] if thr else body
+    step = body[thr[4]:thr[8]] if len(thr) >= 9 else body[thr[-1]:] if thr else body
     agg = collections.OrderedDict()
     for r in step:
-        k = r[kn].split('(')[0].replace('void ', '').replace('<unnamed>::', '')
-        a = agg.setdefault(k, [0, 0.0])
+        a = agg.setdefault(short(r[kn]), [0, 0.0])
         a[0] += 1
         a[1] += float(r[mv].replace(',', ''))
     tot = sum(a[1] for a in agg.values())

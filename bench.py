@@ -213,6 +213,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--tma', type=int, default=-1)
+    ap.add_argument('--opt', action='append', default=[], help='engine option key=value (ct_set_option), repeatable')
     args = ap.parse_args()
     if args.impl == 'reference':
         if not args.cpu_T:
@@ -251,6 +252,9 @@ def main():
     eng = Engine.get(local)
     if args.tma >= 0:
         eng.set_option('tma', args.tma)
+    for kv in args.opt:
+        k, v = kv.split('=')
+        eng.set_option(k, int(v))
     t_lo, t_hi = sharded.shard_bounds(T, world)[rank]
 
     def barrier():

@@ -176,6 +176,8 @@ struct ct_ctx {
     ct_plane_runs_fn fetch_fn = nullptr;
     void* fetch_user = nullptr;
     // ct_shard_begin: thresholding of the own planes is deferred to ct_shard_tables_dev (pipelined with the table kernels)
+    long opt_fill_split = 100;                // per cent of the planes in the first of the two zero-fill launches
+    long opt_shard_fill_late = 1;             // sharded run: zero fill starts after the local tables (1) / after the threshold (0)
     long opt_fused_runs = 1;                  // row-runs come out of the threshold kernel (0: re-extracted from the bit rows)
     long opt_label_fast = 1;                  // steps 4c/4d at label granularity on the host (fallback: per component)
     long opt_profile_tables = 0;              // debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"
@@ -1028,6 +1030,8 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "chunk_min_planes")) { c->opt_chunk_min_planes = value < 1 ? 1 : value; return CT_OK; }
     if (!strcmp(key, "host_sparse")) { c->opt_host_sparse = value; return CT_OK; }
     if (!strcmp(key, "host_threads")) { c->opt_host_threads = value; return CT_OK; }
+    if (!strcmp(key, "fill_split")) { c->opt_fill_split = value < 1 ? 1 : value > 100 ? 100 : value; return CT_OK; }
+    if (!strcmp(key, "shard_fill_late")) { c->opt_shard_fill_late = value; return CT_OK; }
     if (!strcmp(key, "fused_runs")) { c->opt_fused_runs = value; return CT_OK; }
     if (!strcmp(key, "label_fast")) { c->opt_label_fast = value; return CT_OK; }
     if (!strcmp(key, "profile_tables")) { c->opt_profile_tables = value; return CT_OK; }
@@ -1077,12 +1081,22 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
         if (sparse) CT_CUDA(cudaEventRecord(c->ev_chunk[k], st));
     }
     CT_CUDA(cudaEventRecord(c->ev[1], st));
+    // The zero fill is split in two launches: the sparse paint of the first part can start as soon as the values are known
+    // and runs beside the fill of the second part (the paint is bound by latency, the fill by bandwidth).
+    const long T_a = sparse ? std::min<long>(T, std::max<long>(1, (T * c->opt_fill_split) / 100)) : T;
     if (sparse) {
+        const size_t plane_cells = (size_t)H * W;
         CT_CUDA(cudaEventRecord(c->ev_side[0], st));
         CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-        CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T * H * W, c->sm_count, c->side_stream));
-        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+        CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_a * plane_cells, c->sm_count, c->side_stream));
+        CT_CUDA(cudaEventRecord(c->ev_tbl[1], c->side_stream));
         c->launches += 1;
+        if (T_a < T) {
+            CT_CUDA(ctk::zero_fill(flag_dev + (size_t)T_a * plane_cells, (size_t)(T - T_a) * plane_cells, c->sm_count,
+                                   c->side_stream));
+            c->launches += 1;
+        }
+        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
     }
     const double t_h0 = now_ms();
     tables_begin(c);
@@ -1105,10 +1119,16 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     if (sparse) {
         CT_CUDA(cudaEventRecord(c->ev_tbl[0], ts));
         CT_CUDA(cudaStreamWaitEvent(st, c->ev_tbl[0], 0));
-        CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
+        CT_CUDA(cudaStreamWaitEvent(st, c->ev_tbl[1], 0));           // first part of the cube is zero
     }
     CT_CUDA(cudaEventRecord(c->ev[3], st));
-    if ((rc = launch_paint(c, 0, T, flag_dev, sparse, st)) != CT_OK) return rc;
+    if ((rc = launch_paint(c, 0, T_a, flag_dev, sparse, st)) != CT_OK) return rc;
+    if (T_a < T) {
+        CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));          // ... now all of it
+        if ((rc = launch_paint(c, T_a, T - T_a, flag_dev + (size_t)T_a * H * W, sparse, st)) != CT_OK) return rc;
+    } else if (sparse) {
+        CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
+    }
     if (c->novr) {
         CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
                                      c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), c->novr, H, W, 0, T, flag_dev, st));
@@ -1218,14 +1238,24 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
         zero_threads.clear();
         CT_CUDA(cudaStreamSynchronize(ws));
         d2h_bytes = (size_t)R * 12;
-        const int np = (int)std::max(1L, std::min((long)nthreads, R / 4096 + 1));
+        // the painters are bound by cache / TLB misses on the 4 B/cell host cube (every run lands on another page): all
+        // cores, and the destination of the run 16 ahead is prefetched while the current one is written
+        int npaint = (int)c->opt_host_threads;
+        if (npaint <= 0) npaint = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+        const int np = (int)std::max(1L, std::min((long)npaint, R / 4096 + 1));
         std::vector<std::thread> painters;
         const long per = (R + np - 1) / np;
         for (int i = 0; i < np; ++i) {
             const long b = std::min(R, per * i), e = std::min(R, per * (i + 1));
             if (e <= b) continue;
             painters.emplace_back([=] {
+                constexpr long AHEAD = 16;
                 for (long r = b; r < e; ++r) {
+                    if (r + AHEAD < e && h_val[r + AHEAD] != 0) {
+                        const int32_t* p = flag_host + (size_t)h_row[r + AHEAD] * W + (h_x[r + AHEAD] & 0xffff);
+                        __builtin_prefetch(p, 1, 0);
+                        __builtin_prefetch(p + 16, 1, 0);
+                    }
                     const int32_t v = h_val[r];
                     if (v == 0) continue;
                     const uint32_t x = h_x[r];
@@ -1240,7 +1270,7 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
             for (int xx = o.x0; xx < o.x1; ++xx) out[xx] = o.val;
         }
         c->stats["host_sparse"] = 1.0;
-        c->stats["host_threads"] = (double)nthreads;
+        c->stats["host_threads"] = (double)np;
     } else {
         for (auto& t : zero_threads) t.join();
         zero_threads.clear();
@@ -1637,7 +1667,8 @@ int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts
             if (side) CT_CUDA(cudaEventRecord(c->ev_chunk[k], st));
         }
         CT_CUDA(cudaEventRecord(c->ev[1], st));
-        if (side && (rc = start_zero_fill()) != CT_OK) return rc;
+        const bool fill_late = side && c->opt_shard_fill_late;
+        if (side && !fill_late && (rc = start_zero_fill()) != CT_OK) return rc;
         tables_begin(c);
         for (long k = 0; k < nchunk; ++k) {
             const long t0 = k * cp, nt = std::min(cp, T_own - t0);
@@ -1646,6 +1677,16 @@ int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts
             if (k < 8) { char key[16]; snprintf(key, sizeof key, "ms_h_c%ld", k); c->stats[key] = now_ms() - t_h0; }
         }
         if ((rc = tables_finish(c, ts)) != CT_OK) return rc;
+        if (fill_late) {
+            // the fill runs under the gather and the global phase instead of under the local table kernels (which are bound
+            // by memory latency and run ~2.3x slower beside a kernel that saturates HBM)
+            CT_CUDA(cudaEventRecord(c->ev_side[0], ts));
+            CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+            CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
+            CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+            c->launches += 1;
+            c->zero_started_for = flag_dev;
+        }
         c->stats["chunks"] = (double)nchunk;
     } else {
         if (side) {

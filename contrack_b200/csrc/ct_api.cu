@@ -1,8 +1,11 @@
 // ct_api.cu -- C-ABI of the library (include/contrack_b200.h): context, device scratch, orchestration.
 //
-// ct_run_contrack = threshold_bits -> scans -> extract_runs -> ccl -> component / pair / date-line tables (all CUDA,
-// ct_kernels.cu) -> tables to the host -> ordered table phase (ct_host.cpp, ct_tables.cpp) -> per-component value back to
-// the device -> paint.  Reference: contrack/contrack.py:646-791.
+// ct_run_contrack = threshold (bits + row-runs in row slots) -> scans -> compact runs -> ccl -> component / pair / date-line
+// tables -> step 3 sweeps + 3-D labels + label boxes (all CUDA, ct_kernels.cu) -> label boxes to the host -> date-line
+// merge + persistence per label (ct_tables.cpp; exact per-component / all-host replays as fallbacks, ct_host.cpp) -> value
+// per label / component / run back on the device -> zero fill + sparse paint.  Reference: contrack/contrack.py:646-791.
+// The time-sharded entry points (ct_shard_*, ct_global_*) run the same kernels per rank and merge the rank tables on the
+// device (ct_shard.cu); ct_extras.cu / ct_anom.cu / ct_lifecycle.cu hold the callers either side of the path.
 #include "../../include/contrack_b200.h"
 
 #include <cuda_runtime.h>

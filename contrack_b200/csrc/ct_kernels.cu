@@ -1,11 +1,14 @@
 // ct_kernels.cu -- sm_100a kernels of the run_contrack path ("label once, then tables").
 //
-//   threshold_bits   contrack.py:648-674   anomaly cube -> 1 bit per cell (+ row-run counts, date-line flags)
-//   extract_runs                           bit rows -> row-runs (y, x0, x1) in raster order
+//   threshold_bits   contrack.py:648-674   anomaly cube -> 1 bit per cell, row-run counts, date-line flags and the first 8
+//                                          row-runs of every row (x0 | x1 << 16) in the row's slots
+//   compact_runs                           row slots -> row-runs (y, x0, x1) in raster order (extract_runs: from bit rows,
+//                                          for rows with more runs than slots)
 //   ccl_*            contrack.py:684-687   8-connected components of each plane = union-find over row-runs
 //   seam_rows/cls_*  contrack.py:691-698   same-row date-line classes on top of the components
 //   comp_*/pairs_*   contrack.py:717-719   area tables: per component, and per (component at t, component at t-1)
-//   paint            contrack.py:776-791   bit rows + per-run value -> int32 flag cube
+//   step3_* / link_* / label_*  contrack.py:706-751  overlap filter (Jacobi sweeps), 3-D labels, label boxes, on the tables
+//   paint            contrack.py:776-791   per-run value -> int32 flag cube (zero fill + cells of runs, or dense)
 //
 // The two cube-sized kernels (threshold_bits: 4 B/cell read; paint: 4 B/cell write) are HBM-bound streaming kernels;
 // everything between them touches only bit rows (1/32 B/cell... 4/32 B per cell) and run/component tables.

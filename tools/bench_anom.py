@@ -49,6 +49,15 @@ ms, (f, n) = timed(lambda: eng.run_contrack(anom, w, 160, True, 0, 0.5, 5, True,
 out['run_contrack'] = {'ms': ms, 'gbs': cells * 8 / ms / 1e6, 'features': int(n), 'timesteps_per_s': T / ms * 1e3}
 ms, cnt = timed(lambda: eng.flag_count(flag, 1))
 out['blocking_frequency'] = {'ms': ms, 'gbs': cells * 4 / ms / 1e6}
+t0 = time.perf_counter()
+res = eng.run_lifecycle(flag, anom, w)
+torch.cuda.synchronize()
+t1 = time.perf_counter()
+res = eng.run_lifecycle(flag, anom, w)
+torch.cuda.synchronize()
+ms = (time.perf_counter() - t1) * 1e3
+out['run_lifecycle'] = {'ms': ms, 'first_call_ms': (t1 - t0) * 1e3, 'rows': int(len(res['t'])), 'gbs': cells * 8 / ms / 1e6,
+                        'stats': {k: v for k, v in eng.stats().items() if k.startswith('ms_lc') or k.startswith('lc_')}}
 tot = out['calc_clim']['ms'] + out['calc_anom']['ms'] + out['run_contrack']['ms']
 out['config3_total'] = {'ms': tot, 'timesteps_per_s': T / tot * 1e3, 'gbs': cells * 20 / tot / 1e6,
                         'frac_of_peak': cells * 20 / tot / 1e6 / out['peak_gbs'], 'bytes_per_cell': 20}

@@ -292,6 +292,18 @@ int track_phase(const FastTables& tb, const int32_t* label, int persistence, Run
         lt.nlabel = nlabel; lt.t0 = t0.data(); lt.t1 = t1.data(); lt.y0 = y0.data(); lt.y1 = y1.data();
         lt.x0 = x0.data(); lt.x1 = x1.data(); lt.lptr = lptr.data(); lt.lorder = lorder.data();
         std::vector<int32_t> fin, mc, ml;
+        if (getenv("CT_TRACK_LABELS")) {
+            // test hook: the label-granular pass of the product path; returns 1 when a label straddles a stale box
+            std::vector<int32_t> sla(tb.nseg), slb(tb.nseg), lab_fin;
+            for (long s = 0; s < tb.nseg; ++s) { sla[s] = label[seg_a32[s]]; slb[s] = label[seg_b32[s]]; }
+            if (ctb::track_labels_fast(persistence, lt, tb.nseg, sla.data(), slb.data(), lab_fin, stats) == 0) {
+                for (long c = 0; c < nc; ++c) comp_val[c] = lab_fin[label[c]];
+                out.overrides.clear();
+                out.n_features = stats.n_features; out.n_seam_events = stats.n_events; out.n_seam_splits = 0;
+                out.n_neartie += 1000000;           // marker for the test: the fast pass produced this result
+                return 0;
+            }
+        }
         rc = ctb::track_tables_sparse(tb.W, persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0, tb.comp_x1,
                                       label, lt, tb.nseg, tb.seg_y0, tb.seg_y1, seg_a32.data(), seg_b32.data(),
                                       runs ? &fetcher : nullptr, fin, mc, ml, out.overrides, stats);

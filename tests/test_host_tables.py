@@ -132,3 +132,34 @@ def test_sparse_track_variant(monkeypatch, fixture_cube, golden):
         f, _ = host_tables(build_tables(a >= r['threshold'], row_weights(la, lo)), r['overlap'], r['persistence'],
                            r['twosided'])
         assert sha_i4(f) == r['sha256']
+
+
+def test_label_granular_track_variant(monkeypatch, fixture_cube, golden, reference_run):
+    """track_labels_fast (the product path's date-line merge + persistence at label granularity) through the all-host
+    entry point: same results as the reference, and the per-component replay takes over when a label straddles a box."""
+    monkeypatch.setenv('CT_TRACK_SPARSE', '1')
+    monkeypatch.setenv('CT_TRACK_LABELS', '1')
+    lat, lon = regular_grid(24, 16)
+    w = row_weights(lat, lon)
+    fast, slow = 0, 0
+    for r in reference_run['quirk']:
+        x = synth_cube(r['seed'], 12, 24, 16, (1.5, 2, 2))
+        f, st = host_tables(build_tables(x >= 60, w), 0.0, r['persistence'], False)
+        assert sha_i4(f) == r['sha256'], r['seed']
+        fast += st[5] >= 1000000
+        slow += st[5] < 1000000
+    for seed in SPLIT_SEEDS + list(range(1000, 1060)):
+        x = synth_cube(seed, 12, 24, 16, (1.5, 2, 2))
+        tb = build_tables(x >= 60, w)
+        f, st = host_tables(tb, 0.0, 1, False)
+        assert np.array_equal(f, oracle.track_persistence((x >= 60).astype(int), 1)), seed
+        fast += st[5] >= 1000000
+        slow += st[5] < 1000000
+        f, st = host_tables(tb, 0.5, 2, True)
+        assert np.array_equal(f, oracle.run_contrack(x, lat, lon, 60, '>=', 0.5, 2, True)), seed
+    assert fast > 10 and slow > 0, (fast, slow)
+    a, la, lo = fixture_cube
+    for r in golden['fixture']:
+        f, st = host_tables(build_tables(a >= r['threshold'], row_weights(la, lo)), r['overlap'], r['persistence'],
+                            r['twosided'])
+        assert sha_i4(f) == r['sha256'] and st[0] == len(r['ids'])

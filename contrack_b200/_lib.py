@@ -65,6 +65,7 @@ _PROTOS = {
     'ct_shard_paint': (C.c_int, [_p, _i32p, C.c_long] + [_i32p] * 5 + [_i32p, _p]),
     'ct_shard_begin': (C.c_int, [_p, _p, C.c_int, C.c_long, C.c_int, C.c_int, _f64p, _f64p, C.c_long, C.c_int,
                                  C.c_int, C.c_int, _p, _p]),
+    'ct_shard_launch_threshold': (C.c_int, [_p, _p, _p]),
     'ct_shard_tables_dev': (C.c_int, [_p, _p, _p, _longp, _longp]),
     'ct_shard_export_tables': (C.c_int, [_p, _p, C.c_long, _p]),
     'ct_global_merge': (C.c_int, [_p, C.c_int, _longp, _p, C.c_long, C.c_long, C.c_int, C.c_int, _f64p, _p]),

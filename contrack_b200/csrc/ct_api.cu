@@ -189,6 +189,11 @@ struct ct_ctx {
     const void* sh_anom = nullptr;
     int sh_dtype = 0, sh_thr_is_f32 = 0, sh_op = 0, sh_deferred = 0;
     long sh_thr_n = 0;
+    long sh_nchunk = 0, sh_cp = 0;            // chunking chosen by ct_shard_launch_threshold
+    int sh_side = 0;
+    int32_t* sh_flag = nullptr;
+    cudaEvent_t ev_halo = nullptr;           // halo plane imported (ct_shard_import_halo may run on another stream)
+    int halo_event_set = 0;
 };
 
 namespace {
@@ -1017,6 +1022,7 @@ void ct_destroy(ct_ctx* c) {
     if (c->tbl_stream) cudaStreamDestroy(c->tbl_stream);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_chunk) if (e) cudaEventDestroy(e);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->work_stream) cudaStreamDestroy(c->work_stream);
     delete c;
@@ -1505,6 +1511,9 @@ int ct_shard_import_halo(ct_ctx* c, const uint32_t* src_dev, void* stream) {
     CT_CUDA(ctk::row_stats(c->bits.as<uint32_t>(), c->H, c->W, c->Ww, c->row_cnt.as<uint32_t>(),
                            c->seam_flag.as<uint32_t>(), c->slots.as<uint32_t>(), c->counters.as<uint32_t>() + 16, st));
     c->launches += 1;
+    if (!c->ev_halo) CT_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    CT_CUDA(cudaEventRecord(c->ev_halo, st));
+    c->halo_event_set = 1;
     return CT_OK;
 }
 
@@ -1610,7 +1619,7 @@ int ct_shard_begin(ct_ctx* c, const void* anom_dev, int in_dtype, long T_local, 
     if ((rc = prepare(c, T_local + has_prev, H, W, w_host, thr.data(), (long)thr.size(), st)) != CT_OK) return rc;
     c->has_prev = has_prev;
     c->sh_anom = anom_dev; c->sh_dtype = in_dtype; c->sh_thr_n = (long)thr.size(); c->sh_thr_is_f32 = thr_is_f32;
-    c->sh_op = op; c->sh_deferred = 1;
+    c->sh_op = op; c->sh_deferred = 1; c->halo_event_set = 0;
     // the LAST own plane first: its bit rows are what the next rank is waiting for
     const size_t plane_bytes = (size_t)H * W * (in_dtype == CT_F64 ? 8 : 4);
     if ((rc = launch_threshold(c, (const char*)anom_dev + (size_t)(T_local - 1) * plane_bytes, in_dtype,
@@ -1625,53 +1634,70 @@ int ct_shard_begin(ct_ctx* c, const void* anom_dev, int in_dtype, long T_local, 
 
 // counts8 = {0 (caller fills in t_shift), components, halo components, pairs, date-line segments, pairs of the halo
 //            components, segments of the halo plane, components of the last plane}
-int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts8, long* export_bytes) {
-    if (!c || !counts8 || !export_bytes) return fail(CT_ERR_ARG, "null argument");
+// first half of ct_shard_tables_dev when the caller wants the halo exchange to run beside the thresholding: enqueue the
+// threshold chunks of the own planes (and, unless the fill starts late, the zero fill) and return
+int ct_shard_launch_threshold(ct_ctx* c, int32_t* flag_dev, void* stream) {
+    if (!c) return fail(CT_ERR_ARG, "null context");
+    if (c->sh_deferred != 1) return fail(CT_ERR_ARG, "ct_shard_launch_threshold follows ct_shard_begin");
     CT_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    c->zero_started_for = nullptr;
     int rc;
-    cudaStream_t ts = st;
     const int side = flag_dev && c->opt_overlap_zero;
     if (side && (rc = ensure_streams(c)) != CT_OK) return rc;
     const long hp = c->has_prev, T_own = c->T - hp;
-    auto start_zero_fill = [&]() -> int {
+    long nchunk = side ? std::min<long>(c->opt_chunks, std::max<long>(1, T_own / c->opt_chunk_min_planes)) : 1;
+    const long cp = (T_own + nchunk - 1) / nchunk;
+    nchunk = (T_own + cp - 1) / cp;
+    if (side) {
+        while ((long)c->ev_chunk.size() < nchunk) {
+            cudaEvent_t e;
+            CT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->ev_chunk.push_back(e);
+        }
+    }
+    const size_t plane_bytes = (size_t)c->H * c->W * (c->sh_dtype == CT_F64 ? 8 : 4);
+    CT_CUDA(cudaEventRecord(c->ev[0], st));
+    for (long k = 0; k < nchunk; ++k) {
+        const long t0 = k * cp, nt = std::min(cp, T_own - t0);
+        if ((rc = launch_threshold(c, (const char*)c->sh_anom + (size_t)t0 * plane_bytes, c->sh_dtype, hp + t0, nt,
+                                   c->sh_thr_n, c->sh_thr_is_f32, c->sh_op, st)) != CT_OK) return rc;
+        if (side) CT_CUDA(cudaEventRecord(c->ev_chunk[k], st));
+    }
+    CT_CUDA(cudaEventRecord(c->ev[1], st));
+    c->zero_started_for = nullptr;
+    if (side && !c->opt_shard_fill_late) {
         CT_CUDA(cudaEventRecord(c->ev_side[0], st));
         CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
         CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
         CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
         c->launches += 1;
         c->zero_started_for = flag_dev;
-        return CT_OK;
-    };
+    }
+    c->sh_nchunk = nchunk; c->sh_cp = cp; c->sh_side = side; c->sh_flag = flag_dev;
+    c->sh_deferred = 2;
+    return CT_OK;
+}
+
+int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts8, long* export_bytes) {
+    if (!c || !counts8 || !export_bytes) return fail(CT_ERR_ARG, "null argument");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    cudaStream_t ts = st;
+    const long hp = c->has_prev, T_own = c->T - hp;
     const double t_h0 = now_ms();
     const int deferred = c->sh_deferred;
-    if (c->sh_deferred) {
-        // ---- own planes thresholded in time chunks on `st`; the table kernels of chunk k (and of the halo plane) run on the
-        // high-priority stream while chunk k+1 is being thresholded; the zero fill follows the last threshold chunk ----
+    int side = flag_dev && c->opt_overlap_zero;
+    if (deferred == 1 && (rc = ct_shard_launch_threshold(c, flag_dev, stream)) != CT_OK) return rc;
+    if (deferred) {
+        // ---- own planes were thresholded in time chunks on `st`; the table kernels of chunk k (and of the halo plane) run
+        // on the high-priority stream while chunk k+1 is being thresholded ----
+        if (c->sh_flag != flag_dev) return fail(CT_ERR_ARG, "flag_dev differs from the one given to ct_shard_launch_threshold");
         c->sh_deferred = 0;
-        long nchunk = side ? std::min<long>(c->opt_chunks, std::max<long>(1, T_own / c->opt_chunk_min_planes)) : 1;
-        const long cp = (T_own + nchunk - 1) / nchunk;
-        nchunk = (T_own + cp - 1) / cp;
-        if (side) {
-            ts = c->tbl_stream;
-            while ((long)c->ev_chunk.size() < nchunk) {
-                cudaEvent_t e;
-                CT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                c->ev_chunk.push_back(e);
-            }
-        }
-        const size_t plane_bytes = (size_t)c->H * c->W * (c->sh_dtype == CT_F64 ? 8 : 4);
-        CT_CUDA(cudaEventRecord(c->ev[0], st));
-        for (long k = 0; k < nchunk; ++k) {
-            const long t0 = k * cp, nt = std::min(cp, T_own - t0);
-            if ((rc = launch_threshold(c, (const char*)c->sh_anom + (size_t)t0 * plane_bytes, c->sh_dtype, hp + t0, nt,
-                                       c->sh_thr_n, c->sh_thr_is_f32, c->sh_op, st)) != CT_OK) return rc;
-            if (side) CT_CUDA(cudaEventRecord(c->ev_chunk[k], st));
-        }
-        CT_CUDA(cudaEventRecord(c->ev[1], st));
-        const bool fill_late = side && c->opt_shard_fill_late;
-        if (side && !fill_late && (rc = start_zero_fill()) != CT_OK) return rc;
+        side = c->sh_side;
+        const long nchunk = c->sh_nchunk, cp = c->sh_cp;
+        if (side) ts = c->tbl_stream;
+        if (hp && c->halo_event_set) CT_CUDA(cudaStreamWaitEvent(ts, c->ev_halo, 0));
         tables_begin(c);
         for (long k = 0; k < nchunk; ++k) {
             const long t0 = k * cp, nt = std::min(cp, T_own - t0);
@@ -1680,7 +1706,7 @@ int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts
             if (k < 8) { char key[16]; snprintf(key, sizeof key, "ms_h_c%ld", k); c->stats[key] = now_ms() - t_h0; }
         }
         if ((rc = tables_finish(c, ts)) != CT_OK) return rc;
-        if (fill_late) {
+        if (side && c->opt_shard_fill_late) {
             // the fill runs under the gather and the global phase instead of under the local table kernels (which are bound
             // by memory latency and run ~2.3x slower beside a kernel that saturates HBM)
             CT_CUDA(cudaEventRecord(c->ev_side[0], ts));
@@ -1692,11 +1718,19 @@ int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts
         }
         c->stats["chunks"] = (double)nchunk;
     } else {
+        c->zero_started_for = nullptr;
         if (side) {
-            if ((rc = start_zero_fill()) != CT_OK) return rc;
+            if ((rc = ensure_streams(c)) != CT_OK) return rc;
+            CT_CUDA(cudaEventRecord(c->ev_side[0], st));
+            CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+            CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
+            CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+            c->launches += 1;
+            c->zero_started_for = flag_dev;
             CT_CUDA(cudaStreamWaitEvent(c->tbl_stream, c->ev_side[0], 0));
             ts = c->tbl_stream;
         }
+        if (hp && c->halo_event_set) CT_CUDA(cudaStreamWaitEvent(ts, c->ev_halo, 0));
         if ((rc = tables_build(c, ts)) != CT_OK) return rc;
     }
     uint32_t* cnt_dev = c->counters.as<uint32_t>();

@@ -264,6 +264,10 @@ class Shard(object):
                                            int(op), self.has_prev, C.c_void_p(t.data_ptr()), self._stream()))
         return t
 
+    def launch_threshold(self):
+        """Enqueue the thresholding of the own planes now (optional; tables_dev() does it otherwise)."""
+        _lib.check(self.lib.ct_shard_launch_threshold(self.h, C.c_void_p(self.out.data_ptr()), self._stream()))
+
     def boundary_words(self):
         return int(self.lib.ct_shard_boundary_words(self.h))
 
@@ -431,6 +435,16 @@ def _buffer(key, nbytes, dev):
 
 
 _hp_streams = {}
+_aux_streams = {}
+
+
+def aux_stream(device):
+    """Second high-priority stream: the halo exchange runs on it beside the thresholding of the own planes."""
+    import torch
+    s = _aux_streams.get(device)
+    if s is None:
+        s = _aux_streams[device] = torch.cuda.Stream(device=device, priority=-1)
+    return s
 
 
 def high_priority_stream(device):
@@ -475,18 +489,25 @@ def _run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, t
     g_eng = _global_engine(engine)
     # ---- the one halo exchange: the last plane is thresholded first, its bit rows go to the next rank ----
     send = sh.begin(w, thresholds, thr_is_f32, op)
+    main = torch.cuda.current_stream(sh.dev)
+    boundary_ready = torch.cuda.Event()
+    boundary_ready.record(main)
+    sh.launch_threshold()                          # the own planes are being thresholded while the halo travels
     mark('boundary_plane')
     recv = torch.empty_like(send)
-    ops = []
-    if rank + 1 < world:
-        ops.append(dist.P2POp(dist.isend, send, grank(rank + 1), group))
-    if rank > 0:
-        ops.append(dist.P2POp(dist.irecv, recv, grank(rank - 1), group))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    if rank > 0:
-        sh.import_halo(recv)
+    aux = aux_stream(sh.dev)
+    with torch.cuda.stream(aux):
+        aux.wait_event(boundary_ready)
+        ops = []
+        if rank + 1 < world:
+            ops.append(dist.P2POp(dist.isend, send, grank(rank + 1), group))
+        if rank > 0:
+            ops.append(dist.P2POp(dist.irecv, recv, grank(rank - 1), group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if rank > 0:
+            sh.import_halo(recv)                   # on `aux`; the table kernels wait for its event
     mark('halo_exchange')
     # ---- own planes: threshold chunks + table kernels pipelined (device); all-gather of counts and packed tables ----
     counts, nbytes = sh.tables_dev()
@@ -516,6 +537,7 @@ def _run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, t
                          fetch=fetch, stream=stream)
     mark('global_phase')
     sh.paint_global(g_eng.handle, offs[rank])
+    main.wait_stream(aux)                          # (long finished; keeps `send` / `recv` alive until then)
     mark('paint')
     info = dict(table_bytes=[int(b) for b in all_k[:, 8]], halo_words=sh.boundary_words(),
                 ncomp_global=int(sum(k[1] - k[2] for k in all_k)),

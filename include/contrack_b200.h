@@ -222,6 +222,9 @@ int ct_shard_paint(ct_ctx* ctx, const int32_t* comp_val_local, long novr, const 
 int ct_shard_begin(ct_ctx* ctx, const void* anom_dev, int in_dtype, long T_local, int H, int W, const double* w_host,
                    const double* thr_host, long thr_n, int thr_is_f32, int op, int has_prev, uint32_t* boundary_dst_dev,
                    void* stream);
+/* optional, between ct_shard_begin and ct_shard_tables_dev: enqueue the thresholding of the own planes now, so that the
+ * halo exchange (on another stream; ct_shard_import_halo may be given that stream) runs beside it */
+int ct_shard_launch_threshold(ct_ctx* ctx, int32_t* flag_dev, void* stream);
 int ct_shard_tables_dev(ct_ctx* ctx, int32_t* flag_dev, void* stream, long* counts8, long* export_bytes);
 int ct_shard_export_tables(ct_ctx* ctx, void* dst_dev, long cap_bytes, void* stream);
 int ct_global_merge(ct_ctx* g, int nranks, const long* counts, const void* gathered_dev, long stride_bytes, long T_total,

@@ -197,7 +197,8 @@ def workload_config(T, n):
     return {'workload': 'run_contrack on synthetic %dx%dx%d Z500 anomaly (seed %d, sigma %s cells), threshold=%d %s '
                         'overlap=%.1f persistence=%d twosided=%s' % (T, H, W, SEED, SIGMA, THRESHOLD, GORL, OVERLAP,
                                                                      PERSISTENCE, TWOSIDED),
-            'T': T, 'H': H, 'W': W, 'sharding': 'time x%d' % n,
+            'T': T, 'H': H, 'W': W, 'sharding': 'time x%d' % n, 'threshold': THRESHOLD, 'overlap': OVERLAP,
+            'persistence': PERSISTENCE,
             'l2': 'inputs (%.1f GB) and outputs far exceed the 126 MB L2; no explicit flush' % (T * H * W * 4 / 1e9)}
 
 
@@ -206,7 +207,10 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--T', type=int, default=10957, help='time steps of the cube (BASELINE.json: 10957 daily steps)')
+    ap.add_argument('--T', type=int, default=0, help='time steps of the cube (default 10957: BASELINE.json configs[2..3])')
+    ap.add_argument('--config', type=int, default=0, choices=[0, 2, 5],
+                    help='BASELINE.json configs[i-1]: 2 = 2707 steps; 5 = 43828 steps, overlap 0.7, persistence 20, threshold = '
+                         '90th percentile of the 80N-50N band (needs >= 4 GPUs)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-T', type=int, default=0, help='time steps of the CPU-baseline sample')
     ap.add_argument('--e2e-T', type=int, default=0, help='time steps of the end-to-end (host buffer) measurement')
@@ -215,6 +219,11 @@ def main():
     ap.add_argument('--tma', type=int, default=-1)
     ap.add_argument('--opt', action='append', default=[], help='engine option key=value (ct_set_option), repeatable')
     args = ap.parse_args()
+    global THRESHOLD, OVERLAP, PERSISTENCE
+    if not args.T:
+        args.T = {0: 10957, 2: 2707, 5: 43828}[args.config]
+    if args.config == 5:
+        OVERLAP, PERSISTENCE = 0.7, 20
     if args.impl == 'reference':
         if not args.cpu_T:
             args.cpu_T = 64
@@ -268,6 +277,19 @@ def main():
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
     flag = torch.empty((t_hi - t_lo, H, W), dtype=torch.int32, device='cuda')
+    thr_note = None
+    if args.config == 5:
+        # README.rst:150-151: anom.sel(latitude=slice(80, 50)).quantile([0.9], dim='time').mean(), computed once before the
+        # timed region.  The cube is time-sharded, so every rank takes the quantile over ITS time steps and the ranks' band
+        # means are averaged: a harness-side stand-in for the global quantile (the field is stationary in time).
+        y0, y1 = int(round((90 - 80) / 0.25)), int(round((90 - 50) / 0.25)) + 1
+        q = eng.quantile_time(anom, [0.9], y0, y1)
+        m = torch.nanmean(q).reshape(1)
+        if world > 1:
+            dist.all_reduce(m)
+            m /= world
+        THRESHOLD = float(m.item())
+        thr_note = '90th percentile over time per grid point of the 80N-50N band, band mean, averaged over the time shards'
 
     shard_info = []
 
@@ -344,6 +366,9 @@ def main():
             'tables': {k: int(stats[k]) for k in ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d',
                                                   'seam_events', 'seam_splits', 'neartie_resolved') if k in stats},
             'synth_seconds': t_gen}
+    if thr_note:
+        line['config']['threshold_value'] = THRESHOLD
+        line['config']['threshold_note'] = thr_note
     if world > 1 and shard_info:
         last = shard_info[-args.steps:]
         line['shard_ms'] = {k: float(np.mean([i['phase_ms'][k] for i in last])) for k in last[0]['phase_ms']}
@@ -359,6 +384,7 @@ def main():
         Ts = min(args.cpu_T, T)
         sub = anom[:Ts].contiguous()
         x = sub.cpu().numpy()
+        cpu_reference_run(np.ascontiguousarray(x[:min(8, Ts)]), lat, lon)          # warm-up (imports, allocator)
         ref, dt = cpu_reference_run(x, lat, lon)
         got, _ = eng.run_contrack(sub, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED)
         line['cpu_baseline'] = {'value': Ts / dt, 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port',
@@ -368,6 +394,11 @@ def main():
                                           'used of %d' % (Ts, T, os.cpu_count()),
                                 'bit_exact_vs_gpu': bool(np.array_equal(got.cpu().numpy(), ref))}
         del sub, got
+        # the reference's step 3 walks every label slot of the CUBE for every plane (O(T^2)): a shorter sample is faster
+        # per step, the full cube would be slower than either
+        Ts2 = min(64, T)
+        _, dt2 = cpu_reference_run(np.ascontiguousarray(x[:Ts2]), lat, lon)
+        line['cpu_baseline']['shorter_sample'] = {'steps': Ts2, 'value': Ts2 / dt2}
 
     # ---- end to end: host buffers in, host buffers out, copies inside the timed region --------------------------------
     if not args.no_e2e:

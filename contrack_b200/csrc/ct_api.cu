@@ -174,7 +174,7 @@ struct ct_ctx {
     std::vector<double> w_host;
     long launches = 0;
     // time-sharded run: packed tables of all ranks -> global tables (ct_global_merge), plane runs served by the caller
-    DevBuf sh_desc, b_sla, b_slb, x_q, x_idx;
+    DevBuf sh_desc, b_sla, b_slb, x_q, x_idx, ovf_rows;
     PinBuf hp_desc;
     ct_plane_runs_fn fetch_fn = nullptr;
     void* fetch_user = nullptr;
@@ -423,9 +423,14 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
     }
     CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(std::max(Re - Rb, n)) * sizeof(uint32_t)));
     if (c->opt_fused_runs) {
-        CT_CUDA(ctk::compact_runs(U(c->slots), U(c->bits), U(c->row_ptr), r0, n, c->Ww, cnt_host[16] != 0, U(c->run_x),
+        uint32_t* ovf = nullptr;
+        if (cnt_host[16]) {                                      // some row of the cube has more runs than slots
+            CT_CUDA(c->ovf_rows.ensure((size_t)n * 4));
+            ovf = U(c->ovf_rows);
+            c->launches += 1; c->stats["slot_overflow"] = 1.0;
+        }
+        CT_CUDA(ctk::compact_runs(U(c->slots), U(c->bits), U(c->row_ptr), r0, n, c->Ww, ovf, cnt_dev + 17, U(c->run_x),
                                   U(c->run_row), st));
-        if (cnt_host[16]) { c->launches += 1; c->stats["slot_overflow"] = 1.0; }
     } else {
         CT_CUDA(ctk::extract_runs(U(c->bits), U(c->row_ptr), r0, n, c->Ww, U(c->run_x), U(c->run_row), st));
     }
@@ -1013,7 +1018,7 @@ void ct_destroy(ct_ctx* c) {
                       &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN,
                       &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
                       &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml,
-                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots, &c->x_q, &c->x_idx};
+                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots, &c->x_q, &c->x_idx, &c->ovf_rows};
     for (DevBuf* b : bufs) b->release();
     c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release(); c->hp_desc.release();
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
@@ -1762,6 +1767,11 @@ int ct_shard_export_tables(ct_ctx* c, void* dst_dev, long cap_bytes, void* strea
     size_t off[cts::A_COUNT];
     const long nc = c->ncomp, np = c->npair, ns = c->nseg;
     if ((long)cts::layout(nc, np, ns, off) > cap_bytes) return fail(CT_ERR_ARG, "export buffer too small");
+    if (st != (cudaStream_t)stream) {
+        // whatever the caller's stream still does to dst (e.g. the fill of a fresh torch.zeros) comes first
+        CT_CUDA(cudaEventRecord(c->ev[5], (cudaStream_t)stream));
+        CT_CUDA(cudaStreamWaitEvent(st, c->ev[5], 0));
+    }
     char* d = (char*)dst_dev;
     struct Src { int k; const DevBuf* b; long n; int elt; };
     const Src src[] = {{cts::A_T, &c->c_t, nc, 4}, {cts::A_Y0, &c->c_y0, nc, 4}, {cts::A_Y1, &c->c_y1, nc, 4},

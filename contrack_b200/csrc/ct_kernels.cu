@@ -440,12 +440,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const uint32_t* __r
 // rows with at most RUN_SLOTS runs: the threshold kernel left their runs in the row's slots -> dense run tables
 __global__ void __launch_bounds__(256) k_compact_runs(const uint4* __restrict__ slots, const uint32_t* __restrict__ row_ptr,
                                                       long nrows, uint32_t* __restrict__ run_x,
-                                                      uint32_t* __restrict__ run_row, long row0) {
+                                                      uint32_t* __restrict__ run_row, long row0,
+                                                      uint32_t* __restrict__ ovf_rows, uint32_t* __restrict__ ovf_count) {
     static_assert(RUN_SLOTS == 8, "two uint4 per row");
     const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
     const uint32_t base = row_ptr[row], n = row_ptr[row + 1] - base;
-    if (n == 0 || n > (uint32_t)RUN_SLOTS) return;
+    if (n == 0) return;
+    if (n > (uint32_t)RUN_SLOTS) {                     // the slots hold only the first runs: list the row for re-extraction
+        if (ovf_rows) ovf_rows[atomicAdd(ovf_count, 1u)] = (uint32_t)row;
+        return;
+    }
     const uint4 a = slots[2 * row];
     const uint32_t v0[4] = {a.x, a.y, a.z, a.w};
     const uint32_t r = (uint32_t)(row0 + row);
@@ -459,21 +464,23 @@ __global__ void __launch_bounds__(256) k_compact_runs(const uint4* __restrict__ 
     }
 }
 
-// MIN_RUNS > 0: only rows with more than MIN_RUNS runs (the ones the slots could not hold)
+// MIN_RUNS > 0: only the rows listed in ovf_rows[0 .. *ovf_count) (the ones the slots could not hold)
 template <int MIN_RUNS>
 __global__ void __launch_bounds__(256) k_extract_runs(const uint32_t* __restrict__ bits,
                                                       const uint32_t* __restrict__ row_ptr, long nrows, int Ww,
                                                       uint32_t* __restrict__ run_x, uint32_t* __restrict__ run_row,
-                                                      long row0) {
+                                                      long row0, const uint32_t* __restrict__ ovf_rows,
+                                                      const uint32_t* __restrict__ ovf_count) {
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     uint16_t* rx = reinterpret_cast<uint16_t*>(run_x);
-    for (long row = warp0; row < nrows; row += nwarps) {
+    const long nwork = MIN_RUNS > 0 ? (long)*ovf_count : nrows;
+    for (long wi = warp0; wi < nwork; wi += nwarps) {
+        const long row = MIN_RUNS > 0 ? (long)ovf_rows[wi] : wi;
         // everything a 64-word row needs is requested before anything is consumed: one memory latency per row
         const uint32_t* b = bits + row * (long)Ww;
         const uint32_t base = row_ptr[row], next = row_ptr[row + 1];
-        if (MIN_RUNS > 0 && next - base <= (uint32_t)MIN_RUNS) continue;
         uint32_t m = lane < Ww ? b[lane] : 0u;
         uint32_t m_ahead = (32 + lane < Ww) ? b[32 + lane] : 0u;
         if (next == base) continue;
@@ -1126,20 +1133,23 @@ cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long row
     if (nrows == 0) return cudaSuccess;
     const long want = (nrows + 7) / 8;
     k_extract_runs<0><<<(unsigned)std::min<long>(want, 148L * 16), 256, 0, st>>>(bits + row0 * (long)Ww, row_ptr + row0,
-                                                                                nrows, Ww, run_x, run_row, row0);
+                                                                                nrows, Ww, run_x, run_row, row0, nullptr,
+                                                                                nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t compact_runs(const uint32_t* slots, const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww,
-                         int overflow, uint32_t* run_x, uint32_t* run_row, cudaStream_t st) {
+                         uint32_t* ovf_rows, uint32_t* ovf_count, uint32_t* run_x, uint32_t* run_row, cudaStream_t st) {
     if (nrows == 0) return cudaSuccess;
-    k_compact_runs<<<blocks_for(nrows, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(slots + row0 * (long)RUN_SLOTS),
-                                                           row_ptr + row0, nrows, run_x, run_row, row0);
-    if (overflow) {
-        const long want = (nrows + 7) / 8;
-        k_extract_runs<RUN_SLOTS><<<(unsigned)std::min<long>(want, 148L * 16), 256, 0, st>>>(
-            bits + row0 * (long)Ww, row_ptr + row0, nrows, Ww, run_x, run_row, row0);
+    if (ovf_rows) {
+        cudaError_t e = cudaMemsetAsync(ovf_count, 0, 4, st);
+        if (e != cudaSuccess) return e;
     }
+    k_compact_runs<<<blocks_for(nrows, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(slots + row0 * (long)RUN_SLOTS),
+                                                           row_ptr + row0, nrows, run_x, run_row, row0, ovf_rows, ovf_count);
+    if (ovf_rows)
+        k_extract_runs<RUN_SLOTS><<<148 * 2, 256, 0, st>>>(bits + row0 * (long)Ww, row_ptr + row0, nrows, Ww, run_x, run_row,
+                                                           row0, ovf_rows, ovf_count);
     return cudaGetLastError();
 }
 

@@ -40,10 +40,10 @@ cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32
 cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww, uint32_t* run_x,
                          uint32_t* run_row, cudaStream_t st);
 
-// the same from the row slots the threshold kernel filled; rows with more runs than slots are re-extracted from the bit rows
-// when `overflow` is set
+// the same from the row slots the threshold kernel filled; when ovf_rows is given ([nrows] scratch + a device counter), rows
+// with more runs than slots are listed there and re-extracted from their bit rows
 cudaError_t compact_runs(const uint32_t* slots, const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww,
-                         int overflow, uint32_t* run_x, uint32_t* run_row, cudaStream_t st);
+                         uint32_t* ovf_rows, uint32_t* ovf_count, uint32_t* run_x, uint32_t* run_row, cudaStream_t st);
 
 // 2-D 8-connected components over row-runs (contrack.py:684-687): union-find with the smallest run index as root.
 cudaError_t ccl_init(uint32_t* parent, long begin, long end, cudaStream_t st);

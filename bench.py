@@ -82,7 +82,7 @@ class ClockSampler(object):
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -92,7 +92,7 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append([c.strip() for c in line.split(',')] + [time.time()])
 
     def __exit__(self, *a):
         if self.proc:
@@ -103,9 +103,16 @@ class ClockSampler(object):
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """Samples inside [t0, t1] (the timed region); when the region is shorter than the sampling period, the samples of
+        the whole window the sampler was running (warm-up + timed steps, the same load) and `window` says so."""
+        rows, window = self.rows, 'sampler lifetime'
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 - 0.02 <= r[-1] <= t1 + 0.02]
+            rows, window = (inside, 'timed region') if inside else (self.rows, 'warm-up + timed region (timed region '
+                                                                    'shorter than the 20 ms sampling period)')
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -114,9 +121,9 @@ class ClockSampler(object):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         if not sm:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0, 'window': window}
         return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'window': window}
 
 
 def measured_peak():
@@ -301,21 +308,23 @@ def main():
         shard_info.append(info)
         return f, n
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms_thr, ms_paint, ms_host, ms_tab, ms_zero = [], [], [], [], []
     with ClockSampler(local) as clocks:
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        t_timed0 = time.time()
         ev0.record()
         for _ in range(args.steps):
             _, nfeat = step()
-            s = eng.stats()
-            ms_thr.append(s['ms_threshold']); ms_paint.append(s['ms_paint']); ms_host.append(s.get('ms_host_tables', 0.0))
-            ms_tab.append(s.get('ms_tables_gpu', 0.0) + s.get('ms_tables_host_roundtrip', 0.0))
-            ms_zero.append(s.get('ms_zero_fill', 0.0))
+            st = lambda k: max(0.0, eng.lib.ct_get_stat(eng.handle, k))          # noqa: E731  (five cheap look-ups per step)
+            ms_thr.append(st(b'ms_threshold')); ms_paint.append(st(b'ms_paint')); ms_host.append(st(b'ms_host_tables'))
+            ms_tab.append(st(b'ms_tables_gpu') + st(b'ms_tables_host_roundtrip'))
+            ms_zero.append(st(b'ms_zero_fill'))
         ev1.record()
         barrier()
+        t_timed1 = time.time()
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t_ms = torch.tensor([ms], dtype=torch.float64, device='cuda')
@@ -346,7 +355,7 @@ def main():
             'dtype': 'f32 compare / f64 areas / int32 labels', 'data': 'synthetic',
             'config': workload_config(T, world),
             'features': int(nfeat), 'gpu_launches': int(stats['kernel_launches']) * args.steps * world,
-            'clocks': clocks.summary(),
+            'clocks': clocks.summary(t_timed0, t_timed1),
             'roofline': {'bound': 'hbm', 'kernel': dom[0], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': traffic,
                          'traffic_note': 'DRAM read+write bytes per cell of this kernel in %s x %d cells' % (traffic_src, cells),

@@ -171,7 +171,8 @@ struct ct_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t copy_stream = nullptr, work_stream = nullptr;
     std::map<std::string, double> stats;
-    std::vector<double> w_host;
+    std::vector<double> w_host, thr_cached;
+    long nspecial_cached = 0;
     long launches = 0;
     // time-sharded run: packed tables of all ranks -> global tables (ct_global_merge), plane runs served by the caller
     DevBuf sh_desc, b_sla, b_slb, x_q, x_idx, ovf_rows;
@@ -315,22 +316,34 @@ int check_args(long T, int H, int W, const double* w_host, const double* thr_hos
 // upload weights / special-row map / thresholds; size the row-indexed scratch
 int prepare(ct_ctx* c, long T, int H, int W, const double* w_host, const double* thr_host, long thr_n,
             cudaStream_t st) {
+    // weights / special-row map / thresholds of the previous call are still on the device: a repeated call with the same
+    // grid and thresholds (time stepping, benchmarks) skips the classification, three uploads and a synchronize
+    const bool same = c->H == H && c->W == W && (long)c->w_host.size() == H && (long)c->thr_cached.size() == thr_n &&
+                      c->w_dev.p && c->special_dev.p && c->thr_dev.p &&
+                      memcmp(c->w_host.data(), w_host, (size_t)H * 8) == 0 &&
+                      memcmp(c->thr_cached.data(), thr_host, (size_t)thr_n * 8) == 0;
     c->T = T; c->H = H; c->W = W; c->Ww = (W + 31) / 32;
     const long nrows = T * H;
-    c->w_host.assign(w_host, w_host + H);
-    std::vector<uint8_t> special;
-    classify_rows(w_host, H, W, special);
-    long nspecial = 0;
-    for (uint8_t s : special) nspecial += s;
-    c->stats["special_rows"] = (double)nspecial;
-    c->special_uniform = special_rows_uniform(w_host, special);
-    CT_CUDA(c->w_dev.ensure(H * sizeof(double)));
-    CT_CUDA(c->special_dev.ensure(H));
-    CT_CUDA(c->thr_dev.ensure(thr_n * sizeof(double)));
-    CT_CUDA(cudaMemcpyAsync(c->w_dev.p, w_host, H * sizeof(double), cudaMemcpyHostToDevice, st));
-    CT_CUDA(cudaMemcpyAsync(c->special_dev.p, special.data(), H, cudaMemcpyHostToDevice, st));
-    CT_CUDA(cudaMemcpyAsync(c->thr_dev.p, thr_host, thr_n * sizeof(double), cudaMemcpyHostToDevice, st));
-    CT_CUDA(cudaStreamSynchronize(st));                               // `special` is a local
+    if (same) {
+        c->stats["special_rows"] = (double)c->nspecial_cached;
+    } else {
+        c->w_host.assign(w_host, w_host + H);
+        c->thr_cached.assign(thr_host, thr_host + thr_n);
+        std::vector<uint8_t> special;
+        classify_rows(w_host, H, W, special);
+        long nspecial = 0;
+        for (uint8_t s : special) nspecial += s;
+        c->nspecial_cached = nspecial;
+        c->stats["special_rows"] = (double)nspecial;
+        c->special_uniform = special_rows_uniform(w_host, special);
+        CT_CUDA(c->w_dev.ensure(H * sizeof(double)));
+        CT_CUDA(c->special_dev.ensure(H));
+        CT_CUDA(c->thr_dev.ensure(thr_n * sizeof(double)));
+        CT_CUDA(cudaMemcpyAsync(c->w_dev.p, w_host, H * sizeof(double), cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaMemcpyAsync(c->special_dev.p, special.data(), H, cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaMemcpyAsync(c->thr_dev.p, thr_host, thr_n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CT_CUDA(cudaStreamSynchronize(st));                           // `special` is a local
+    }
     CT_CUDA(c->bits.ensure((size_t)nrows * c->Ww * sizeof(uint32_t)));
     CT_CUDA(c->row_cnt.ensure((size_t)nrows * sizeof(uint32_t)));
     CT_CUDA(c->seam_flag.ensure((size_t)nrows * sizeof(uint32_t)));

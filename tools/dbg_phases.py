@@ -1,5 +1,7 @@
-import sys, numpy as np, torch
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+"""Per-phase stats of full-size single-GPU steps for a few chunk counts (debug aid)."""
+import os, sys, numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import bench
 from contrack_b200 import Engine
 eng = Engine.get(0)

@@ -375,7 +375,7 @@ def test_label_granular_track_matches_component_replay(eng, reference_run):
 
 
 @pytest.mark.parametrize('tma', [3, 0])
-@pytest.mark.parametrize('W', [1440, 1024, 2048, 96, 33])
+@pytest.mark.parametrize('W', [1440, 1024, 2048, 96, 33, 1028, 36])
 def test_runs_from_threshold_kernel_edge_cases(eng, W, tma):
     """Row-runs come out of the threshold kernel (8 slots per row): rows with more runs than slots (noise), runs that end
     exactly at the row end when the row fills whole 32-word groups (W = 1024, 2048), full rows, alternating cells."""

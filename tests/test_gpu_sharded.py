@@ -157,3 +157,21 @@ def test_sharded_torchrun_two_gpus():
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(' ok') >= 2
+
+
+def test_sharded_device_tables_empty_shards(fixture_cube):
+    """A rank whose planes hold no component at all, components only on one side of a cut, and an empty cube."""
+    a, lat, lon = fixture_cube
+    w = row_weights(lat, lon)
+    x = a.copy()
+    x[:5] = -1000.0                                   # the first shard of (5, 6) is empty
+    for parts in [(5, 6), (3, 2, 6), (4, 7)]:
+        f, n, _ = run_local_dev(x, w, parts, 150, '>=', 0.5, 2, True)
+        ref = oracle.run_contrack(x, lat, lon, 150, '>=', 0.5, 2, True)
+        assert np.array_equal(f, ref) and n == len(np.unique(ref)) - 1, parts
+    x[:] = -1000.0
+    f, n, _ = run_local_dev(x, w, (4, 7), 150, '>=', 0.5, 2, True)
+    assert n == 0 and not f.any()
+    x[:] = 1000.0                                     # one component per plane covering everything
+    f, n, _ = run_local_dev(x, w, (6, 5), 150, '>=', 0.5, 2, True)
+    assert np.array_equal(f, oracle.run_contrack(x, lat, lon, 150, '>=', 0.5, 2, True))

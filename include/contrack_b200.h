@@ -61,7 +61,9 @@ void ct_destroy(ct_ctx* ctx);
  *   "chunks"       [4] time chunks of ct_run_contrack's pipeline (table kernels of chunk k run while chunk k+1 is being
  *                  thresholded); "chunk_min_planes" [1024] = smallest chunk
  *   "host_sparse"  [1] ct_run_contrack_host returns the result as row-runs expanded by host threads; 0 = dense copy
- *   "host_threads" [0 = automatic] host threads used by ct_run_contrack_host */
+ *   "host_threads" [0 = automatic] host threads used by ct_run_contrack_host
+ *   "host_out_zeroed" [0] 1 = the caller guarantees that flag_host is all zero on entry (fresh calloc / np.zeros pages): the
+ *                  zeroing pass, which competes with the host-to-device copy for host memory bandwidth, is skipped */
 int ct_set_option(ct_ctx* ctx, const char* key, long value);
 
 /* ---- run_contrack, contrack.py:646-772 -------------------------------------------------------------------------

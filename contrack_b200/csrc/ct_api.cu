@@ -183,6 +183,8 @@ struct ct_ctx {
     void* fetch_user = nullptr;
     // ct_shard_begin: thresholding of the own planes is deferred to ct_shard_tables_dev (pipelined with the table kernels)
     long opt_fill_split = 100;                // per cent of the planes in the first of the two zero-fill launches
+    long opt_shard_fill_defer_ms = 2;         // ... and not before the export when the fill is shorter than this (ms)
+    int fill_pending = 0;
     long opt_shard_fill_late = 1;             // sharded run: zero fill starts after the local tables (1) / after the threshold (0)
     long opt_fused_runs = 1;                  // row-runs come out of the threshold kernel (0: re-extracted from the bit rows)
     long opt_label_fast = 1;                  // steps 4c/4d at label granularity on the host (fallback: per component)
@@ -1062,6 +1064,7 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "host_zero_threads")) { c->opt_host_zero_threads = value; return CT_OK; }
     if (!strcmp(key, "host_out_zeroed")) { c->opt_host_out_zeroed = value; return CT_OK; }
     if (!strcmp(key, "fill_split")) { c->opt_fill_split = value < 1 ? 1 : value > 100 ? 100 : value; return CT_OK; }
+    if (!strcmp(key, "shard_fill_defer_ms")) { c->opt_shard_fill_defer_ms = value; return CT_OK; }
     if (!strcmp(key, "shard_fill_late")) { c->opt_shard_fill_late = value; return CT_OK; }
     if (!strcmp(key, "fused_runs")) { c->opt_fused_runs = value; return CT_OK; }
     if (!strcmp(key, "label_fast")) { c->opt_label_fast = value; return CT_OK; }
@@ -1644,7 +1647,7 @@ int ct_shard_begin(ct_ctx* c, const void* anom_dev, int in_dtype, long T_local, 
     if ((rc = prepare(c, T_local + has_prev, H, W, w_host, thr.data(), (long)thr.size(), st)) != CT_OK) return rc;
     c->has_prev = has_prev;
     c->sh_anom = anom_dev; c->sh_dtype = in_dtype; c->sh_thr_n = (long)thr.size(); c->sh_thr_is_f32 = thr_is_f32;
-    c->sh_op = op; c->sh_deferred = 1; c->halo_event_set = 0;
+    c->sh_op = op; c->sh_deferred = 1; c->halo_event_set = 0; c->fill_pending = 0;
     // the LAST own plane first: its bit rows are what the next rank is waiting for
     const size_t plane_bytes = (size_t)H * W * (in_dtype == CT_F64 ? 8 : 4);
     if ((rc = launch_threshold(c, (const char*)anom_dev + (size_t)(T_local - 1) * plane_bytes, in_dtype,
@@ -1733,13 +1736,20 @@ int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts
         if ((rc = tables_finish(c, ts)) != CT_OK) return rc;
         if (side && c->opt_shard_fill_late) {
             // the fill runs under the gather and the global phase instead of under the local table kernels (which are bound
-            // by memory latency and run ~2.3x slower beside a kernel that saturates HBM)
-            CT_CUDA(cudaEventRecord(c->ev_side[0], ts));
-            CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-            CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
-            CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
-            c->launches += 1;
+            // by memory latency and run ~2.3x slower beside a kernel that saturates HBM).  A short fill (small shard) is held
+            // back a little longer, until the tables are exported: the small collective that gathers the table sizes and the
+            // host round trip behind it then run on an idle memory system, and the fill still fits under the global phase.
+            const double fill_ms_est = (double)T_own * c->H * c->W * 4.0 / 6.5e9;
             c->zero_started_for = flag_dev;
+            if (fill_ms_est > (double)c->opt_shard_fill_defer_ms) {
+                CT_CUDA(cudaEventRecord(c->ev_side[0], ts));
+                CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+                CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
+                CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+                c->launches += 1;
+            } else {
+                c->fill_pending = 1;
+            }
         }
         c->stats["chunks"] = (double)nchunk;
     } else {
@@ -1787,6 +1797,15 @@ int ct_shard_export_tables(ct_ctx* c, void* dst_dev, long cap_bytes, void* strea
     size_t off[cts::A_COUNT];
     const long nc = c->ncomp, np = c->npair, ns = c->nseg;
     if ((long)cts::layout(nc, np, ns, off) > cap_bytes) return fail(CT_ERR_ARG, "export buffer too small");
+    if (c->fill_pending) {                                           // deferred zero fill of a small shard (see above)
+        const long T_own = c->T - c->has_prev;
+        c->fill_pending = 0;
+        CT_CUDA(cudaEventRecord(c->ev_side[0], st));
+        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+        CT_CUDA(ctk::zero_fill(c->zero_started_for, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
+        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+        c->launches += 1;
+    }
     if (st != (cudaStream_t)stream) {
         // whatever the caller's stream still does to dst (e.g. the fill of a fresh torch.zeros) comes first
         CT_CUDA(cudaEventRecord(c->ev[5], (cudaStream_t)stream));
@@ -1933,6 +1952,14 @@ int ct_shard_paint_global(ct_ctx* c, ct_ctx* g, long comp_offset, long t_begin, 
     CT_CUDA(ctk::run_values(c->run_comp.as<uint32_t>(), g->c_val.as<int32_t>() + comp_offset, c->run_val.as<int32_t>(),
                             c->nruns, st));
     c->launches += 1;
+    if (c->fill_pending) {                                           // the tables were never exported: fill now
+        c->fill_pending = 0;
+        CT_CUDA(cudaEventRecord(c->ev_side[0], st));
+        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+        CT_CUDA(ctk::zero_fill(c->zero_started_for, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
+        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+        c->launches += 1;
+    }
     const int sparse = (c->zero_started_for == flag_dev && flag_dev) ? 1 : 0;
     if (sparse) CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
     CT_CUDA(cudaEventRecord(c->ev[3], st));

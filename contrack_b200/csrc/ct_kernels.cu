@@ -222,13 +222,15 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
     }
     int st = 0;
     uint32_t phase = 0;
+    const double thr_one = thr[0];                                   // the usual case: one threshold for the whole cube
     for (long row = warp0; row < nrows; row += nwarps) {
-        const double thr_d = thr[thr_n == 1 ? 0 : row / H];
+        const double thr_d = thr_n == 1 ? thr_one : thr[row / H];
         const float thr_f = (float)thr_d;
         mbar_wait(&bars[st], phase);
         const TIn* a = reinterpret_cast<const TIn*>(stage0 + (size_t)st * stage_bytes);
-        uint32_t cnt = 0, carry_word = 0, first = 0, last = 0, sb = 0, eb = 0;
+        uint32_t carry_word = 0, first = 0, last = 0, sb = 0, eb = 0;
         uint16_t* slot16 = reinterpret_cast<uint16_t*>(slots + row * (long)RUN_SLOTS);
+        uint32_t* brow = bits + row * (long)Ww;
         for (int k0 = 0; k0 < Ww; k0 += 32) {
             uint32_t myword = 0;
             const int kend = min(32, Ww - k0);
@@ -250,11 +252,10 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
                     if (lane == j0 + j) myword = m;
                 }
             }
-            if (lane < kend) bits[row * (long)Ww + k0 + lane] = myword;
+            if (lane < kend) brow[k0 + lane] = myword;
             uint32_t prev = __shfl_up_sync(FULL, myword, 1);
             if (lane == 0) prev = carry_word;
-            cnt += __popc(myword & ~((myword << 1) | (prev >> 31)));
-            emit_runs(myword, prev, k0 + lane, lane, sb, eb, slot16);
+            emit_runs(myword, prev, k0 + lane, lane, sb, eb, slot16);   // sb: run starts of the row so far (warp-uniform)
             carry_word = __shfl_sync(FULL, myword, 31);
             if (k0 == 0) first = __shfl_sync(FULL, myword, 0) & 1u;
             if (last_word >= k0 && last_word < k0 + 32) last = (__shfl_sync(FULL, myword, last_word - k0) >> last_bit) & 1u;
@@ -270,11 +271,9 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
             }
         }
         emit_close(carry_word, W, lane, eb, slot16);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
         if (lane == 0) {
-            row_cnt[row] = cnt; seam_flag[row] = first & last;
-            if (cnt > (uint32_t)RUN_SLOTS) *overflow = 1u;
+            row_cnt[row] = sb; seam_flag[row] = first & last;
+            if (sb > (uint32_t)RUN_SLOTS) *overflow = 1u;
         }
         if (++st == NS) { st = 0; phase ^= 1u; }
     }

@@ -363,8 +363,12 @@ int prepare(ct_ctx* c, long T, int H, int W, const double* w_host, const double*
 }
 
 int launch_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long t0, long nt, long thr_n, int thr_is_f32,
-                     int op, cudaStream_t st) {
+                     int op, cudaStream_t st, int all_bits = 1) {
     ctk::ThresholdArgs a;
+    // the bit rows are read by: run extraction from bits (fused_runs = 0), the paint variants that go by bit rows or are
+    // dense, the boundary export of a shard and the host-buffer call's dense fallback -- callers that need none of these
+    // pass all_bits = 0 and only rows with more runs than slots get their bit row
+    a.bits_overflow_only = (!all_bits && c->opt_fused_runs && c->opt_paint_runs && c->opt_overlap_zero) ? 1 : 0;
     a.anom = anom_dev; a.in_dtype = in_dtype; a.T = nt; a.H = c->H; a.W = c->W; a.Ww = c->Ww;
     a.thr_dev = thr_n == 1 ? c->thr_dev.as<double>() : c->thr_dev.as<double>() + t0;
     a.thr_n = thr_n; a.thr_is_f32 = thr_is_f32; a.op = op;
@@ -1111,7 +1115,7 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     for (long k = 0; k < nchunk; ++k) {
         const long t0 = k * cp, nt = std::min(cp, T - t0);
         if ((rc = launch_threshold(c, (const char*)anom_dev + (size_t)t0 * plane_bytes, in_dtype, t0, nt, thr_n, thr_is_f32,
-                                   op, st)) != CT_OK) return rc;
+                                   op, st, /*all_bits=*/0)) != CT_OK) return rc;
         if (sparse) CT_CUDA(cudaEventRecord(c->ev_chunk[k], st));
     }
     CT_CUDA(cudaEventRecord(c->ev[1], st));
@@ -1688,7 +1692,7 @@ int ct_shard_launch_threshold(ct_ctx* c, int32_t* flag_dev, void* stream) {
     for (long k = 0; k < nchunk; ++k) {
         const long t0 = k * cp, nt = std::min(cp, T_own - t0);
         if ((rc = launch_threshold(c, (const char*)c->sh_anom + (size_t)t0 * plane_bytes, c->sh_dtype, hp + t0, nt,
-                                   c->sh_thr_n, c->sh_thr_is_f32, c->sh_op, st)) != CT_OK) return rc;
+                                   c->sh_thr_n, c->sh_thr_is_f32, c->sh_op, st, /*all_bits=*/side ? 0 : 1)) != CT_OK) return rc;
         if (side) CT_CUDA(cudaEventRecord(c->ev_chunk[k], st));
     }
     CT_CUDA(cudaEventRecord(c->ev[1], st));

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
                                                         const double* __restrict__ thr, long thr_n,
                                                         uint32_t* __restrict__ bits, uint32_t* __restrict__ row_cnt,
                                                         uint32_t* __restrict__ seam_flag, uint32_t* __restrict__ slots,
-                                                        uint32_t* __restrict__ overflow, int NS, int stage_bytes) {
+                                                        uint32_t* __restrict__ overflow, int NS, int stage_bytes, int bits_mode) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + wid * NS;                   // [nw][NS]
@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
         uint32_t carry_word = 0, first = 0, last = 0, sb = 0, eb = 0;
         uint16_t* slot16 = reinterpret_cast<uint16_t*>(slots + row * (long)RUN_SLOTS);
         uint32_t* brow = bits + row * (long)Ww;
+        uint32_t kept0 = 0, kept1 = 0;                               // bits_mode 1: the row's words wait for the run count
         for (int k0 = 0; k0 < Ww; k0 += 32) {
             uint32_t myword = 0;
             const int kend = min(32, Ww - k0);
@@ -252,7 +253,9 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
                     if (lane == j0 + j) myword = m;
                 }
             }
-            if (lane < kend) brow[k0 + lane] = myword;
+            if (bits_mode == 0) { if (lane < kend) brow[k0 + lane] = myword; }
+            else if (k0 == 0) kept0 = myword;
+            else kept1 = myword;
             uint32_t prev = __shfl_up_sync(FULL, myword, 1);
             if (lane == 0) prev = carry_word;
             emit_runs(myword, prev, k0 + lane, lane, sb, eb, slot16);   // sb: run starts of the row so far (warp-uniform)
@@ -271,6 +274,10 @@ __global__ void __launch_bounds__(512) k_threshold_bulk(const TIn* __restrict__ 
             }
         }
         emit_close(carry_word, W, lane, eb, slot16);
+        if (bits_mode != 0 && sb > (uint32_t)RUN_SLOTS) {            // only rows the slots cannot hold need their bit row
+            if (lane < Ww) brow[lane] = kept0;
+            if (32 + lane < Ww) brow[32 + lane] = kept1;
+        }
         if (lane == 0) {
             row_cnt[row] = sb; seam_flag[row] = first & last;
             if (sb > (uint32_t)RUN_SLOTS) *overflow = 1u;
@@ -297,7 +304,8 @@ cudaError_t launch_threshold_bulk(const ThresholdArgs& a, int sm_count, cudaStre
         k_threshold_bulk<TIn, F32CMP, OPV><<<blocks, nw * 32, smem, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww, \
                                                                           a.thr_dev, a.thr_n, a.bits, a.row_cnt,    \
                                                                           a.seam_flag, a.slots, a.overflow, NS,     \
-                                                                          stage_bytes);                             \
+                                                                          stage_bytes,                              \
+                                                                          (a.bits_overflow_only && a.Ww <= 64) ? 1 : 0); \
     } while (0)
     switch (a.op) {
         case 0: CT_LAUNCH_THRB(0); break;

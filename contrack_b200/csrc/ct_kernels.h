@@ -19,6 +19,8 @@ struct ThresholdArgs {
     uint32_t* seam_flag;                     // [T*H] out: 1 if the pixels at x=0 and x=W-1 are both set
     uint32_t* slots;                         // [T*H*RUN_SLOTS_PER_ROW] out: first runs of every row, x0 | x1 << 16
     uint32_t* overflow;                      // device flag, set if a row has more runs than slots
+    int bits_overflow_only = 0;              // 1: bit rows are written only for rows with more runs than slots (nothing else
+                                             // reads them when the runs come from the slots and the paint goes by runs)
     int variant;                             // 0 / 2: 4-byte loads + ballot, 8 / 16 loads in flight per lane;
                                              // 1 / 3: cp.async.bulk row staging, 8 / 16 warps per CTA (needs W % 4 == 0)
 };

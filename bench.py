@@ -365,6 +365,8 @@ def main():
                                  'previous time chunk run beside it (the cube is thresholded in %d chunk launches; '
                                  'the time is first launch start -> last launch end)' % (cells, int(stats.get('chunks', 1))),
                          'achieved_alone': iso, 'frac_alone': iso / peak if iso else None,
+                         'peak_note': 'peak = copy bandwidth of MEASURED_PEAKS.json (a read+write mix); a pure read stream such '
+                                      'as this kernel alone can exceed it',
                          'note_alone': 'same kernel as one launch with nothing beside it (option chunks=1), CUDA events'},
             'roofline_path': {'achieved': path_gbs, 'frac': path_gbs / (peak * world), 'unit': 'GB/s',
                               'note': '8 B/cell (read anomaly once + write flag once) x all cells / whole step time; '

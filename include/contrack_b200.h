@@ -61,6 +61,13 @@ void ct_destroy(ct_ctx* ctx);
  *   "chunks"       [4] time chunks of ct_run_contrack's pipeline (table kernels of chunk k run while chunk k+1 is being
  *                  thresholded); "chunk_min_planes" [1024] = smallest chunk
  *   "host_sparse"  [1] ct_run_contrack_host returns the result as row-runs expanded by host threads; 0 = dense copy
+ *   "fused_runs"   [1] row-runs come out of the threshold kernel (8 slots per row); 0 = re-extracted from the bit rows
+ *   "label_fast"   [1] date-line merge + persistence at label granularity on the host; 0 = always the per-component replay
+ *   "shard_fill_late" [1] sharded run: zero fill after the local tables (0 = right after the threshold);
+ *                  "shard_fill_defer_ms" [2] = fills shorter than this wait until the tables are exported
+ *   "fill_split"   [100] per cent of the planes in the first of two zero-fill launches (the paint of that part starts early)
+ *   "profile_tables" [0] debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"
+ *   "host_zero_threads" [0 = automatic: 6] threads of the host-buffer call's zeroing pass
  *   "host_threads" [0 = automatic] host threads used by ct_run_contrack_host
  *   "host_out_zeroed" [0] 1 = the caller guarantees that flag_host is all zero on entry (fresh calloc / np.zeros pages): the
  *                  zeroing pass, which competes with the host-to-device copy for host memory bandwidth, is skipped */

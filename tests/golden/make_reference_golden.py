@@ -126,6 +126,29 @@ def main():
     f = np.asarray(c.ds['flag'].data)
     out['dim_order'] = dict(dims=list(c.ds['flag'].dims), shape=list(f.shape), sha256=sha_i4(f))
 
+    # more of the parameter space, held against the oracle only (tests/test_oracle.py): extreme overlaps, persistence 1 and
+    # longer than the cube, every gorl spelling, a 2-degree grid with pole rows, float64 input
+    out['oracle_only'] = []
+    for seed, T, H, W, sig, thr, gorl, ov, pers, two, f64 in [
+            (21, 16, 91, 180, (1.5, 3, 5), 120, '>=', 0.0, 1, True, False),
+            (21, 16, 91, 180, (1.5, 3, 5), 120, '>=', 1.0, 1, True, False),
+            (21, 16, 91, 180, (1.5, 3, 5), 120, 'ge', 0.99, 2, False, False),
+            (22, 12, 91, 180, (1.5, 3, 5), -120, 'lt', 0.5, 3, True, False),
+            (22, 12, 91, 180, (1.5, 3, 5), -120, '<=', 0.5, 30, True, False),
+            (23, 25, 46, 90, (2.0, 1.5, 2), 90, 'gt', 0.3, 6, True, True),
+            (24, 10, 181, 360, (1.0, 6, 10), 140, '>=', 0.6, 2, False, False),
+            (25, 3, 46, 90, (0.5, 1.5, 2), 80, '>', 0.5, 1, True, False),
+            (26, 2, 46, 90, (0.5, 1.5, 2), 80, '>', 0.5, 1, True, False)]:      # (one time step: the reference's set_up raises)
+        x = synth_cube(seed, T, H, W, sig)
+        if f64:
+            x = x.astype(np.float64)
+        la, lo = regular_grid(H, W)
+        f, rows, _ = reference_run(x, la, lo, days(T, '2000-01-01'), thr, gorl, ov, pers, two, lifecycle=T > 1, force=True)
+        out['oracle_only'].append(dict(seed=seed, shape=[T, H, W], sigma=list(sig), threshold=float(thr), gorl=gorl, overlap=ov,
+                                       persistence=pers, twosided=two, float64=f64, dtype=str(f.dtype),
+                                       ids=[int(i) for i in np.unique(f)[1:]], sha256=sha_i4(f), lifecycle=rows))
+    print('oracle_only', len(out['oracle_only']), [len(r['ids']) for r in out['oracle_only']])
+
     # calc_clim / calc_anom (pandas-backed groupby / rolling in the shim: an interpretation of xarray)
     for seed, nyear, H, W, window, smooth, groupby in [(11, 3, 5, 8, 31, 2, 'dayofyear'), (12, 2, 5, 8, 5, 3, 'dayofyear'),
                                                        (13, 2, 5, 8, 1, 1, 'month')]:

@@ -166,3 +166,18 @@ def test_readme_recipes_restated():
     assert thr == float(np.mean(np.quantile(x[:, 1:3].astype(np.float32), np.array([0.9]), axis=0)))
     f = (rng.random((20, 4, 5)) * 4).astype(np.int32)
     assert np.array_equal(oracle.blocking_frequency(f), (f > 1).sum(0) / 20 * 100)
+
+
+def test_reference_run_wider_parameter_space(reference_run):
+    """Extreme overlaps, persistence 1 and longer than the cube, every gorl spelling, pole rows, float64 input, 2- and
+    3-step cubes: outputs of the unmodified reference (tests/golden/make_reference_golden.py, key 'oracle_only')."""
+    for r in reference_run['oracle_only']:
+        T, H, W = r['shape']
+        x = synth_cube(r['seed'], T, H, W, tuple(r['sigma']))
+        if r['float64']:
+            x = x.astype(np.float64)
+        lat, lon = regular_grid(H, W)
+        f = oracle.run_contrack(x, lat, lon, _thr(r), r['gorl'], r['overlap'], r['persistence'], r['twosided'], force=True)
+        assert sha_i4(f) == r['sha256'] and str(f.dtype) == r['dtype'], r
+        assert [int(i) for i in np.unique(f)[1:]] == r['ids']
+        assert _life(oracle.run_lifecycle(f, x, lat, lon, _times(T), force=True)) == r['lifecycle'], r

@@ -247,6 +247,9 @@ class contrack(object):
                     logging.warning(errmsg)
                 else:
                     raise ValueError(errmsg)
+        elif len(delta) == 0:
+            # a dimension with a single entry: the reference evaluates delta[0] here (contrack.py:371)
+            raise IndexError('index 0 is out of bounds for axis 0 with size 0')
         elif len(delta) == 1 and delta[0] == 0:
             raise ValueError('Two equivalent values found for dimension {}.'.format(dim))
         elif len(delta) == 1 and delta[0] < np.zeros((), delta.dtype):

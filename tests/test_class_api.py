@@ -152,3 +152,14 @@ def test_calc_clim_and_anom_via_class():
     from contrack_b200.contrack import time_group_keys
     ref = oracle.calc_anom(z, time_group_keys(time, 'dayofyear'), 31, 2)
     np.testing.assert_allclose(np.asarray(c['anom']), ref, rtol=1e-5, atol=4e-3, equal_nan=True)
+
+
+def test_single_time_step_raises_like_the_reference():
+    # contrack.py:371 evaluates delta[0] of an empty difference vector: IndexError in set_up (observed by running the
+    # reference on a one-step cube, tests/golden/make_reference_golden.py)
+    ds = Dataset({'anom': (('time', 'latitude', 'longitude'), np.zeros((1, 4, 6), np.float32))},
+                 coords={'time': np.array(['2000-01-01'], 'datetime64[ns]'), 'latitude': np.linspace(60, 30, 4).astype(np.float32),
+                         'longitude': np.arange(6, dtype=np.float32) * 60})
+    c = contrack(ds=ds)
+    with pytest.raises(IndexError):
+        c.set_up()

@@ -2,7 +2,7 @@
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-ffp-contract=off --fmad=true
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-ffp-contract=off --fmad=false
 CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -ffp-contract=off
 SRC       := contrack_b200/csrc
 OUT       := contrack_b200/lib

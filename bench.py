@@ -25,9 +25,9 @@ for p in (ROOT, os.path.join(ROOT, 'tests')):
 
 import numpy as np  # noqa: E402
 
-# NCCL prints its version banner on stdout under NCCL_DEBUG=VERSION/INFO; the driver wants ONE JSON line there
-if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO', ''):
-    os.environ['NCCL_DEBUG'] = 'WARN'
+# NCCL_DEBUG / NCCL_DEBUG_FILE are left exactly as the caller set them.  Under NCCL_DEBUG=INFO|VERSION without a
+# NCCL_DEBUG_FILE NCCL logs to stdout: in a multi-rank run file descriptor 1 is therefore pointed at stderr while the
+# job runs and the ONE JSON line is written to the real stdout at the end (see main()).
 
 H, W = 721, 1440
 SIGMA = (2.5, 24.0, 40.0)        # (2.5 steps, 6 deg, 10 deg) at 0.25 deg
@@ -51,22 +51,42 @@ def reference_weights(lat, lon):
 _synth = None
 
 
-def synth_fill(out, t0, T_total, seed=SEED, season=False):
-    """Fill the CUDA float32 tensor out[nt, H, W] with planes [t0, t0+nt) of the synthetic cube (bench_support/)."""
+def synth_lib():
     global _synth
-    import torch
     if _synth is None:
         _synth = C.CDLL(os.path.join(ROOT, 'bench_support', 'libct_synth.so'))
         _synth.ct_synth_fill.restype = C.c_int
         _synth.ct_synth_fill.argtypes = [C.c_void_p, C.c_ulonglong, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int,
                                          C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.c_void_p]
+        _synth.ct_checksum_i32.restype = C.c_int
+        _synth.ct_checksum_i32.argtypes = [C.c_void_p, C.c_size_t, C.c_ulonglong, C.c_void_p, C.c_void_p]
+    return _synth
+
+
+def synth_fill(out, t0, T_total, seed=SEED, season=False):
+    """Fill the CUDA float32 tensor out[nt, H, W] with planes [t0, t0+nt) of the synthetic cube (bench_support/)."""
+    import torch
+    synth_lib()
     nt, h, w = out.shape
     rc = _synth.ct_synth_fill(C.c_void_p(out.data_ptr()), seed, t0, nt, T_total, h, w, SIGMA[0],
                               SIGMA[1] * h / 721.0, SIGMA[2] * w / 1440.0, 100.0, 60.0 if season else 0.0, 365.25,
                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
         raise RuntimeError('ct_synth_fill failed: cudaError %d' % rc)
+    return out
+
+
+def flag_checksum(flag, index0):
+    """64-bit position-weighted checksum of an int32 CUDA tensor taken as cells index0.. of the whole cube (additive over
+    disjoint parts: the sum over the time shards modulo 2^64 is the checksum of the cube)."""
+    import torch
+    synth_lib()
+    out = torch.zeros(1, dtype=torch.int64, device=flag.device)
+    rc = _synth.ct_checksum_i32(C.c_void_p(flag.data_ptr()), flag.numel(), index0, C.c_void_p(out.data_ptr()),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        raise RuntimeError('ct_checksum_i32 failed: cudaError %d' % rc)
     return out
 
 
@@ -153,16 +173,20 @@ def cpu_reference_run(x, lat, lon):
     return f, time.perf_counter() - t0
 
 
-def make_sample(T_sub, use_gpu):
+def make_sample(T_sub, use_gpu, season=False):
     """[T_sub, H, W] float32 host array of the benchmark's synthetic field (first T_sub planes of a T_sub-long cube)."""
     if use_gpu:
         import torch
         d = torch.empty((T_sub, H, W), dtype=torch.float32, device='cuda')
-        synth_fill(d, 0, T_sub)
+        synth_fill(d, 0, T_sub, season=season)
         torch.cuda.synchronize()
         return d.cpu().numpy()
     from _synth import synth_cube
-    return synth_cube(SEED, T_sub, H, W, SIGMA)
+    x = synth_cube(SEED, T_sub, H, W, SIGMA)
+    if season:
+        lat = np.linspace(90, -90, H)[None, :, None] * np.pi / 180
+        x = (x + 5500.0 + 60.0 * np.sin(lat) * np.cos(2 * np.pi * np.arange(T_sub)[:, None, None] / 365.25)).astype(np.float32)
+    return x
 
 
 def run_reference_arm(args):
@@ -178,19 +202,27 @@ def run_reference_arm(args):
         use_gpu = False
     T_sub = args.cpu_T
     lat, lon = grid()
-    x = make_sample(T_sub, use_gpu)
+    x = make_sample(T_sub, use_gpu, season=(args.config == 3))
+
+    def one():
+        if args.config != 3:
+            return cpu_reference_run(x, lat, lon)[1]
+        from oracle import contrack_oracle as oracle
+        doy, _, _ = day_groups(T_sub)
+        t0 = time.perf_counter()
+        a = oracle.calc_anom(x, doy, window=31, smooth=2)
+        return time.perf_counter() - t0 + cpu_reference_run(a, lat, lon)[1]
     for _ in range(args.warmup):
-        cpu_reference_run(x, lat, lon)
+        one()
     t = 0.0
     for _ in range(args.steps):
-        _, dt = cpu_reference_run(x, lat, lon)
-        t += dt
+        t += one()
     v = T_sub * args.steps / t
     line = {'impl': 'reference', 'metric': 'timesteps/sec (721x1440 grid) run_contrack', 'value': v,
             'unit': 'timesteps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32 compare / f64 areas / int32 labels', 'data': 'synthetic',
-            'config': workload_config(args.T, args.gpus),
+            'config': workload_config(args.T, args.gpus, args.config),
             'cpu_baseline': {'value': v, 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port',
                              'host_cores': os.cpu_count(),
                              'sample': '%d consecutive steps of the %dx%d cube as a standalone cube per step; the path '
@@ -200,13 +232,62 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config(T, n):
-    return {'workload': 'run_contrack on synthetic %dx%dx%d Z500 anomaly (seed %d, sigma %s cells), threshold=%d %s '
-                        'overlap=%.1f persistence=%d twosided=%s' % (T, H, W, SEED, SIGMA, THRESHOLD, GORL, OVERLAP,
-                                                                     PERSISTENCE, TWOSIDED),
+def workload_config(T, n, config=0):
+    pre = 'calc_anom(smooth=2, window=31, groupby=dayofyear) + ' if config == 3 else ''
+    return {'workload': '%srun_contrack on synthetic %dx%dx%d Z500 %s (seed %d, sigma %s cells), threshold=%s %s '
+                        'overlap=%.1f persistence=%d twosided=%s' % (pre, T, H, W, 'height (anomaly + seasonal cycle)'
+                                                                     if config == 3 else 'anomaly', SEED, SIGMA,
+                                                                     THRESHOLD, GORL, OVERLAP, PERSISTENCE, TWOSIDED),
+            'baseline_config': {0: 'configs[2]/[3] (10957 steps)', 2: 'configs[1]', 3: 'configs[2]', 5: 'configs[4]'}[config],
             'T': T, 'H': H, 'W': W, 'sharding': 'time x%d' % n, 'threshold': THRESHOLD, 'overlap': OVERLAP,
             'persistence': PERSISTENCE,
             'l2': 'inputs (%.1f GB) and outputs far exceed the 126 MB L2; no explicit flush' % (T * H * W * 4 / 1e9)}
+
+
+def day_groups(T):
+    """(group index per time step, number of groups) of a daily axis that starts on 1981-01-01 (README.rst:112-117)."""
+    from contrack_b200.contrack import time_group_keys
+    times = (np.datetime64('1981-01-01') + np.arange(T).astype('timedelta64[D]')).astype('datetime64[ns]')
+    doy = time_group_keys(times, 'dayofyear')
+    uniq, gidx = np.unique(doy, return_inverse=True)
+    return doy, gidx.astype(np.int32), len(uniq)
+
+
+def parity_block(eng, world, rank, w, lat, lon, run_shard):
+    """Bit-exactness against the oracle on a standalone cube that is cut at EVERY rank boundary: Tp = max(128, 32 x ranks)
+    planes of the benchmark field, sharded over all ranks exactly like the timed cube (same entry points, same
+    collectives), gathered on rank 0 and compared with the oracle's flag cube (contrack.py:646-772)."""
+    import torch
+    import torch.distributed as dist
+    Tp = max(128, 32 * world)
+    Tp -= Tp % world
+    per = Tp // world
+    x = torch.empty((per, H, W), dtype=torch.float32, device='cuda')
+    synth_fill(x, rank * per, Tp)
+    f, n = run_shard(x, rank * per, Tp)
+    torch.cuda.synchronize()
+    if world > 1:
+        xs = torch.empty((Tp, H, W), dtype=torch.float32, device='cuda') if rank == 0 else None
+        fs = torch.empty((Tp, H, W), dtype=torch.int32, device='cuda') if rank == 0 else None
+        dist.gather(x, list(xs.split(per)) if rank == 0 else None, dst=0)
+        dist.gather(f.contiguous(), list(fs.split(per)) if rank == 0 else None, dst=0)
+    else:
+        xs, fs = x, f
+    if rank != 0:
+        return None
+    t0 = time.perf_counter()
+    ref = oracle_run(xs.cpu().numpy(), lat, lon)
+    dt = time.perf_counter() - t0
+    got = fs.cpu().numpy()
+    return {'bit_exact_vs_oracle': bool(np.array_equal(got, ref)), 'features': int(n),
+            'features_oracle': int(len(np.unique(ref)) - 1), 'planes': Tp, 'cuts': world - 1, 'oracle_seconds': dt,
+            'sample': 'standalone %d-step cube of the benchmark field, %d planes per rank, through the same entry points '
+                      'as the timed steps; oracle = CPU restatement of contrack.py:646-772 on rank 0' % (Tp, per)}
+
+
+def oracle_run(x, lat, lon):
+    from oracle import contrack_oracle as oracle
+    return oracle.run_contrack(x, lat, lon, THRESHOLD, GORL, OVERLAP, PERSISTENCE, TWOSIDED, force=True)
 
 
 def main():
@@ -215,20 +296,22 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--T', type=int, default=0, help='time steps of the cube (default 10957: BASELINE.json configs[2..3])')
-    ap.add_argument('--config', type=int, default=0, choices=[0, 2, 5],
-                    help='BASELINE.json configs[i-1]: 2 = 2707 steps; 5 = 43828 steps, overlap 0.7, persistence 20, threshold = '
-                         '90th percentile of the 80N-50N band (needs >= 4 GPUs)')
+    ap.add_argument('--config', type=int, default=0, choices=[0, 2, 3, 5],
+                    help='BASELINE.json configs[i-1]: 2 = 2707 steps; 3 = calc_anom(smooth=2, window=31) + run_contrack at '
+                         '10957 steps (1 GPU); 5 = 43828 steps, overlap 0.7, persistence 20, threshold = 90th percentile of '
+                         'the 80N-50N band over ALL time steps (needs >= 4 GPUs)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-T', type=int, default=0, help='time steps of the CPU-baseline sample')
     ap.add_argument('--e2e-T', type=int, default=0, help='time steps of the end-to-end (host buffer) measurement')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--tma', type=int, default=-1)
     ap.add_argument('--opt', action='append', default=[], help='engine option key=value (ct_set_option), repeatable')
     args = ap.parse_args()
     global THRESHOLD, OVERLAP, PERSISTENCE
     if not args.T:
-        args.T = {0: 10957, 2: 2707, 5: 43828}[args.config]
+        args.T = {0: 10957, 2: 2707, 3: 10957, 5: 43828}[args.config]
     if args.config == 5:
         OVERLAP, PERSISTENCE = 0.7, 20
     if args.impl == 'reference':
@@ -247,10 +330,13 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (the product path has no CPU fallback)')
+    if args.config == 3 and world > 1:
+        raise SystemExit('--config 3 is the single-GPU configuration of BASELINE.json (configs[2])')
     torch.cuda.set_device(local)
     real_stdout = None
     if world > 1:
-        # NCCL / c10d print banners on stdout ("NCCL version ..."); the driver wants exactly one JSON line there
+        # NCCL (under NCCL_DEBUG=INFO without NCCL_DEBUG_FILE) and c10d log to stdout; the driver wants exactly one JSON
+        # line there: stdout points at stderr while the job runs, the line goes to the saved descriptor
         sys.stdout.flush()
         real_stdout = os.dup(1)
         os.dup2(2, 1)
@@ -280,33 +366,49 @@ def main():
 
     anom = torch.empty((t_hi - t_lo, H, W), dtype=torch.float32, device='cuda')
     t_gen = time.perf_counter()
-    synth_fill(anom, t_lo, T)
+    synth_fill(anom, t_lo, T, season=(args.config == 3))
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
     flag = torch.empty((t_hi - t_lo, H, W), dtype=torch.int32, device='cuda')
     thr_note = None
+    zcube = gidx = None
+    if args.config == 3:
+        # the generated cube is the geopotential HEIGHT z (anomaly field + seasonal cycle); the anomaly is computed per step
+        zcube, anom = anom, torch.empty_like(anom)
+        _, gidx, G = day_groups(T)
     if args.config == 5:
-        # README.rst:150-151: anom.sel(latitude=slice(80, 50)).quantile([0.9], dim='time').mean(), computed once before the
-        # timed region.  The cube is time-sharded, so every rank takes the quantile over ITS time steps and the ranks' band
-        # means are averaged: a harness-side stand-in for the global quantile (the field is stationary in time).
+        # README.rst:150-151: anom.sel(latitude=slice(80, 50)).quantile([0.9], dim='time').mean(), once before the timed
+        # region.  The cube is time-sharded: the exact order statistics over ALL time steps come from the distributed
+        # radix select (per-column histograms all-reduced over the ranks), bit-identical to np.nanquantile on the
+        # gathered cube (tests/test_gpu_extras.py)
         y0, y1 = int(round((90 - 80) / 0.25)), int(round((90 - 50) / 0.25)) + 1
-        q = eng.quantile_time(anom, [0.9], y0, y1)
-        m = torch.nanmean(q).reshape(1)
-        if world > 1:
-            dist.all_reduce(m)
-            m /= world
-        THRESHOLD = float(m.item())
-        thr_note = '90th percentile over time per grid point of the 80N-50N band, band mean, averaged over the time shards'
+        q = sharded.quantile_time_sharded(eng, anom, [0.9], y0, y1) if world > 1 else eng.quantile_time(anom, [0.9], y0, y1)
+        THRESHOLD = float(np.nanmean(q.cpu().numpy()))
+        thr_note = ('float(np.nanmean(quantile(0.9, dim=time) of the 80N-50N band)) over all %d time steps (distributed exact '
+                    'radix select)' % T)
 
     shard_info = []
 
-    def step():
+    def run_shard(x, t0, T_total, out=None):
+        """one run_contrack pass over this rank's planes [t0, t0 + len(x)) of a T_total-step cube -> (flag, features)"""
         if world == 1:
-            return eng.run_contrack(anom, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=flag)
-        f, n, info = sharded.run_contrack_sharded(eng, anom, t_lo, T, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED,
-                                                  out=flag)
+            return eng.run_contrack(x, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=out)
+        f, n, info = sharded.run_contrack_sharded(eng, x, t0, T_total, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE,
+                                                  TWOSIDED, out=out)
         shard_info.append(info)
         return f, n
+
+    ms_stage = {'calc_clim': [], 'calc_anom': []}
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def step():
+        if args.config == 3:
+            ev_s[0].record()
+            clim = eng.calc_clim(zcube, gidx, G, 31)
+            ev_s[1].record()
+            eng.calc_anom(zcube, gidx, G, clim, 2, out=anom)
+            ev_s[2].record()
+        return run_shard(anom, t_lo, T, out=flag)
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms_thr, ms_paint, ms_host, ms_tab, ms_zero = [], [], [], [], []
@@ -322,6 +424,9 @@ def main():
             ms_thr.append(st(b'ms_threshold')); ms_paint.append(st(b'ms_paint')); ms_host.append(st(b'ms_host_tables'))
             ms_tab.append(st(b'ms_tables_gpu') + st(b'ms_tables_host_roundtrip'))
             ms_zero.append(st(b'ms_zero_fill'))
+            if args.config == 3:                 # run_contrack ends with a stream synchronize: the events are complete
+                ms_stage['calc_clim'].append(ev_s[0].elapsed_time(ev_s[1]))
+                ms_stage['calc_anom'].append(ev_s[1].elapsed_time(ev_s[2]))
         ev1.record()
         barrier()
         t_timed1 = time.time()
@@ -335,17 +440,21 @@ def main():
     peak, peak_kind = measured_peak()
     cells = (t_hi - t_lo) * H * W                      # cells one launch of the cube-sized kernels processes (this rank)
     thr_ms, paint_ms = float(np.mean(ms_thr)), float(np.mean(ms_paint))
+    bytes_per_cell = 4
     dom = ('threshold_bits', thr_ms) if thr_ms >= paint_ms else ('paint', paint_ms)
-    achieved = cells * 4 / (dom[1] / 1e3) / 1e9
-    path_gbs = T * H * W * 8 / (ms / args.steps / 1e3) / 1e9
+    if args.config == 3 and float(np.mean(ms_stage['calc_anom'])) > dom[1]:
+        dom, bytes_per_cell = ('anom_chunks', float(np.mean(ms_stage['calc_anom']))), 8
+    achieved = cells * bytes_per_cell / (dom[1] / 1e3) / 1e9
+    path_bytes = 20 if args.config == 3 else 8
+    path_gbs = T * H * W * path_bytes / (ms / args.steps / 1e3) / 1e9
     traffic, traffic_src = ncu_traffic(dom[0], cells)
     # the same kernel timed alone (no table kernels beside it): two extra, untimed-for-`value` steps without the pipeline
     iso = None
-    if world == 1:
+    if world == 1 and dom[0] == 'threshold_bits':
         eng.set_option('chunks', 1)
         t_iso = []
         for _ in range(2):
-            step()
+            run_shard(anom, t_lo, T, out=flag)
             t_iso.append(eng.stats()['ms_threshold'])
         eng.set_option('chunks', 4)
         iso = cells * 4 / (min(t_iso) / 1e3) / 1e9
@@ -353,30 +462,39 @@ def main():
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32 compare / f64 areas / int32 labels', 'data': 'synthetic',
-            'config': workload_config(T, world),
+            'config': workload_config(T, world, args.config),
             'features': int(nfeat), 'gpu_launches': int(stats['kernel_launches']) * args.steps * world,
             'clocks': clocks.summary(t_timed0, t_timed1),
             'roofline': {'bound': 'hbm', 'kernel': dom[0], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': traffic,
                          'traffic_note': 'DRAM read+write bytes per cell of this kernel in %s x %d cells' % (traffic_src, cells),
-                         'algorithmic_bytes_per_launch': cells * 4,
-                         'note': '4 B/cell (float32 read for threshold_bits, int32 write for paint) x %d cells (rank 0) / '
-                                 'CUDA-event time of that kernel inside the timed steps, where the table kernels of the '
-                                 'previous time chunk run beside it (the cube is thresholded in %d chunk launches; '
-                                 'the time is first launch start -> last launch end)' % (cells, int(stats.get('chunks', 1))),
+                         'algorithmic_bytes_per_launch': cells * bytes_per_cell,
+                         'note': '%d B/cell x %d cells (rank 0) / CUDA-event time of that kernel inside the timed steps '
+                                 '(threshold_bits: float32 read, the table kernels of the previous time chunk run beside it, '
+                                 '%d chunk launches, first launch start -> last launch end; paint: int32 write; anom_chunks: '
+                                 'float32 read + write)' % (bytes_per_cell, cells, int(stats.get('chunks', 1))),
                          'achieved_alone': iso, 'frac_alone': iso / peak if iso else None,
                          'peak_note': 'peak = copy bandwidth of MEASURED_PEAKS.json (a read+write mix); a pure read stream such '
-                                      'as this kernel alone can exceed it',
+                                      'as the threshold kernel alone can exceed it',
                          'note_alone': 'same kernel as one launch with nothing beside it (option chunks=1), CUDA events'},
             'roofline_path': {'achieved': path_gbs, 'frac': path_gbs / (peak * world), 'unit': 'GB/s',
-                              'note': '8 B/cell (read anomaly once + write flag once) x all cells / whole step time; '
-                                      'frac against %d x the per-GPU peak' % world},
+                              'bytes_per_cell': path_bytes,
+                              'note': ('%d B/cell x all cells / whole step time (run_contrack: read anomaly once + write flag '
+                                       'once = 8; config 3 adds calc_clim 4 + calc_anom 8); frac against %d x the per-GPU peak'
+                                       % (path_bytes, world))},
             'breakdown_ms': {'threshold_bits': thr_ms, 'paint': paint_ms, 'tables_gpu_and_host': float(np.mean(ms_tab)),
                              'host_table_phase': float(np.mean(ms_host)),
                              'zero_fill_overlapped_with_tables': float(np.mean(ms_zero))},
             'tables': {k: int(stats[k]) for k in ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d',
                                                   'seam_events', 'seam_splits', 'neartie_resolved') if k in stats},
             'synth_seconds': t_gen}
+    if args.config == 3:
+        clim_ms, anom_ms = float(np.mean(ms_stage['calc_clim'])), float(np.mean(ms_stage['calc_anom']))
+        rc_ms = ms / args.steps - clim_ms - anom_ms
+        line['stages'] = {
+            'calc_clim': {'ms': clim_ms, 'bytes_per_cell': 4, 'gbs': cells * 4 / clim_ms / 1e6, 'frac': cells * 4 / clim_ms / 1e6 / peak},
+            'calc_anom': {'ms': anom_ms, 'bytes_per_cell': 8, 'gbs': cells * 8 / anom_ms / 1e6, 'frac': cells * 8 / anom_ms / 1e6 / peak},
+            'run_contrack': {'ms': rc_ms, 'bytes_per_cell': 8, 'gbs': cells * 8 / rc_ms / 1e6, 'frac': cells * 8 / rc_ms / 1e6 / peak}}
     if thr_note:
         line['config']['threshold_value'] = THRESHOLD
         line['config']['threshold_note'] = thr_note
@@ -384,26 +502,60 @@ def main():
         last = shard_info[-args.steps:]
         line['shard_ms'] = {k: float(np.mean([i['phase_ms'][k] for i in last])) for k in last[0]['phase_ms']}
         line['shard_ms']['note'] = ('rank 0 host wall clock per phase of the sharded step (phases end where the host has to '
-                                    'wait: halo exchange, table counts, gathered counts, global phase, paint)')
+                                    'wait)')
         line['shard_table_bytes'] = last[-1]['table_bytes']
         every = [None] * world
         dist.all_gather_object(every, {k: round(v, 3) for k, v in line['shard_ms'].items() if k != 'note'})
         line['shard_ms_all_ranks'] = every
 
+    # ---- parity: checksum of the timed run's flag cube (identical at every N) + oracle on a cube cut at every rank ----
+    if not args.no_parity:
+        cs = flag_checksum(flag, t_lo * H * W)
+        if world > 1:
+            dist.all_reduce(cs)                                  # int64 sum wraps modulo 2^64
+        line['parity'] = {'checksum': '%016x' % (int(cs.item()) & 0xffffffffffffffff),
+                          'checksum_note': 'sum over all cells of flag * (mix64(t*H*W + y*W + x) | 1) mod 2^64 of the flag cube of '
+                                           'the last timed step, summed over the ranks: independent of the sharding'}
+        shard_info_keep = list(shard_info)
+        pb = parity_block(eng, world, rank, w, lat, lon, run_shard)
+        del shard_info[:]
+        shard_info.extend(shard_info_keep)
+        if pb:
+            line['parity'].update(pb)
+
     # ---- CPU baseline + parity on a bounded sample (rank 0 of a single-GPU run only) ---------------------------------
     if not args.no_cpu and world == 1:
+        from oracle import contrack_oracle as oracle
         Ts = min(args.cpu_T, T)
-        sub = anom[:Ts].contiguous()
-        x = sub.cpu().numpy()
+        if args.config == 3:
+            doy, _, _ = day_groups(Ts)
+            zs = zcube[:Ts].contiguous()
+            zh = zs.cpu().numpy()
+            t0 = time.perf_counter()
+            xa = oracle.calc_anom(zh, doy, window=31, smooth=2)
+            dt_anom = time.perf_counter() - t0
+            _, gi, Gs = day_groups(Ts)
+            ga = eng.calc_anom(zs, gi, Gs, eng.calc_clim(zs, gi, Gs, 31), 2)
+            anom_close = bool(np.allclose(ga.cpu().numpy(), xa, rtol=1e-5, atol=4e-3, equal_nan=True))
+            sub = ga
+            x = sub.cpu().numpy()                                # the oracle tracks the GPU anomaly: flag parity is bit-exact
+        else:
+            sub = anom[:Ts].contiguous()
+            x = sub.cpu().numpy()
+            dt_anom = 0.0
         cpu_reference_run(np.ascontiguousarray(x[:min(8, Ts)]), lat, lon)          # warm-up (imports, allocator)
         ref, dt = cpu_reference_run(x, lat, lon)
         got, _ = eng.run_contrack(sub, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED)
-        line['cpu_baseline'] = {'value': Ts / dt, 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port',
-                                'host_cores': os.cpu_count(), 'seconds': dt,
+        line['cpu_baseline'] = {'value': Ts / (dt + dt_anom), 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port',
+                                'host_cores': os.cpu_count(), 'seconds': dt + dt_anom,
                                 'sample': 'first %d steps of the cube as a standalone cube (the reference holds int64 '
                                           'cubes and cannot run all %d steps on the host); single-threaded path: 1 core '
                                           'used of %d' % (Ts, T, os.cpu_count()),
                                 'bit_exact_vs_gpu': bool(np.array_equal(got.cpu().numpy(), ref))}
+        if args.config == 3:
+            line['cpu_baseline']['calc_anom_seconds'] = dt_anom
+            line['cpu_baseline']['calc_anom_within_tolerance'] = anom_close
+            line['cpu_baseline']['tolerance'] = 'rtol 1e-5, atol 4e-3 (float32 values of magnitude 5500)'
         del sub, got
         # the reference's step 3 walks every label slot of the CUBE for every plane (O(T^2)): a shorter sample is faster
         # per step, the full cube would be slower than either
@@ -426,12 +578,18 @@ def main():
         if avail:
             Te = max(16 * world, min(Te, int(0.45 * avail // per_plane)))
         n_e2e = max(1, min(args.steps, 3))
-        if world == 1:
-            xin = torch.empty((Te, H, W), dtype=torch.float32, pin_memory=True)
-            xin.copy_(anom[:Te])
-            fout = torch.empty((Te, H, W), dtype=torch.int32, pin_memory=True)
+        # the SAME standalone Te-step cube at every N: rank r holds planes shard_bounds(Te, N)[r] of it in pinned host memory
+        e_lo, e_hi = sharded.shard_bounds(Te, world)[rank]
+        dev_in = (zcube if args.config == 3 else anom)[:e_hi - e_lo]
+        synth_fill(dev_in, e_lo, Te, season=(args.config == 3))
+        xin = torch.empty((e_hi - e_lo, H, W), dtype=torch.float32, pin_memory=True)
+        xin.copy_(dev_in)
+        fout = torch.empty((e_hi - e_lo, H, W), dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+        if args.config == 3:
+            line['e2e'] = e2e_config3(xin.numpy(), Te, n_e2e, local)
+        elif world == 1:
             xin_np, fout_np = xin.numpy(), fout.numpy()
-            torch.cuda.synchronize()
             eng.run_contrack(xin_np, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=fout_np)      # warm-up
             t0 = time.perf_counter()
             for _ in range(n_e2e):
@@ -446,14 +604,8 @@ def main():
                              'around the call'}
             d2h = int(s.get('d2h_bytes', Te * H * W * 4))
         else:
-            # every rank holds its shard of a Te-step cube in pinned host memory; per step: H2D of the shard, the sharded
+            # every rank holds its shard of the Te-step cube in pinned host memory; per step: H2D of the shard, the sharded
             # run, D2H of the shard's flag planes
-            e_lo, e_hi = sharded.shard_bounds(Te, world)[rank]
-            dev_in = anom[:e_hi - e_lo]
-            synth_fill(dev_in, e_lo, Te)
-            xin = torch.empty((e_hi - e_lo, H, W), dtype=torch.float32, pin_memory=True)
-            xin.copy_(dev_in)
-            fout = torch.empty((e_hi - e_lo, H, W), dtype=torch.int32, pin_memory=True)
             dev_out = torch.empty((e_hi - e_lo, H, W), dtype=torch.int32, device='cuda')
 
             def e2e_step():
@@ -476,8 +628,10 @@ def main():
             extra = {'note': 'per rank: pinned host shard -> device, sharded run, flag shard -> pinned host; wall clock, '
                              'max over ranks'}
             d2h = Te * H * W * 4
-        line['e2e'] = dict({'value': Te * n_e2e / dt, 'unit': 'timesteps/s', 'h2d_bytes_per_step': Te * H * W * 4,
-                            'd2h_bytes_per_step': d2h, 'T': Te, 'steps': n_e2e, 'features': int(nf)}, **extra)
+        if args.config != 3:
+            line['e2e'] = dict({'value': Te * n_e2e / dt, 'unit': 'timesteps/s', 'h2d_bytes_per_step': Te * H * W * 4,
+                                'd2h_bytes_per_step': d2h, 'T': Te, 'steps': n_e2e, 'features': int(nf),
+                                'cube': 'standalone %d-step cube of the benchmark field, the same at every N' % Te}, **extra)
     if rank == 0:
         if real_stdout is not None:
             sys.stdout.flush()
@@ -488,6 +642,37 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def e2e_config3(z_host, Te, n, device):
+    """Config 3 end to end through the class API (the call a user of the reference makes): host z cube in a Dataset ->
+    calc_anom(smooth=2, window=31) -> run_contrack -> ds['flag'] on the host."""
+    from contrack_b200 import contrack
+    from contrack_b200 import dataset as ds_mod
+    lat, lon = grid()
+    times = (np.datetime64('1981-01-01') + np.arange(Te).astype('timedelta64[D]')).astype('datetime64[ns]')
+
+    def once():
+        ds = ds_mod.Dataset({'z': ds_mod.Variable(('time', 'latitude', 'longitude'), z_host,
+                                                  {'units': 'm', 'long_name': 'Geopotential Height'})},
+                            coords={'time': times, 'latitude': lat, 'longitude': lon})
+        c = contrack(ds=ds, device=device)
+        c.set_up(force=True, write=False)
+        c.calc_anom('z', window=31, smooth=2)
+        c.run_contrack('anom', THRESHOLD, GORL, OVERLAP, PERSISTENCE, TWOSIDED)
+        return c
+    once()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        c = once()
+    dt = time.perf_counter() - t0
+    f = np.asarray(c['flag'].data)
+    cells = Te * H * W
+    return {'value': Te * n / dt, 'unit': 'timesteps/s', 'h2d_bytes_per_step': cells * 8, 'd2h_bytes_per_step': cells * 4 + 0,
+            'T': Te, 'steps': n, 'features': int(len(np.unique(f)) - 1),
+            'note': 'contrack(ds).calc_anom(z, window=31, smooth=2) + run_contrack(anom) on a host Dataset: z crosses PCIe for '
+                    'calc_anom, the float32 anomaly comes back (4 B/cell) and is streamed in again by run_contrack, the flag '
+                    'returns as a row-run table; wall clock around the three calls'}
 
 
 if __name__ == '__main__':

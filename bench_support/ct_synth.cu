@@ -93,6 +93,18 @@ __global__ void k_smooth_t(const float* __restrict__ in, float* __restrict__ out
     }
 }
 
+// position-weighted 64-bit checksum of an int32 cube: sum over cells of value * mix64(global cell index), modulo 2^64.
+// Additive over disjoint parts of a cube, so time shards can be summed (all-reduce) to the checksum of the whole cube.
+__global__ void k_checksum(const int32_t* __restrict__ p, size_t n, uint64_t index0, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int32_t v = __ldcs(p + i);
+        if (v) acc += (unsigned long long)(uint32_t)v * (mix64(index0 + i) | 1ULL);
+    }
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 std::vector<float> gauss(double sigma, int* r_out) {
     int r = (int)(4.0 * sigma + 0.5);
     std::vector<double> w(2 * r + 1);
@@ -150,6 +162,15 @@ int ct_synth_fill(float* out_dev, unsigned long long seed, long t0, long nt, lon
     cudaFree(g_dev); cudaFree(a); cudaFree(b);
     if (e == cudaSuccess) e = cudaGetLastError();
     return (int)e;
+}
+
+// *out_dev (zeroed here) = checksum of p[0..n) as cells index0 .. index0+n-1 of a larger cube (see k_checksum)
+int ct_checksum_i32(const int32_t* p, size_t n, unsigned long long index0, unsigned long long* out_dev, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(out_dev, 0, 8, st);
+    if (e != cudaSuccess) return (int)e;
+    if (n) k_checksum<<<148 * 8, 256, 0, st>>>(p, n, index0, out_dev);
+    return (int)cudaGetLastError();
 }
 
 }  // extern "C"

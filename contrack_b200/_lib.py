@@ -79,6 +79,9 @@ _PROTOS = {
     'ct_numpy_pairwise_sum_rle': (C.c_double, [_f64p, _i64p, C.c_long]),
     'ct_calc_clim': (C.c_int, [_p, _p, C.c_long, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _p, _p]),
     'ct_calc_anom': (C.c_int, [_p, _p, C.c_long, C.c_int, C.c_int, _i32p, C.c_int, _p, C.c_int, _p, _p]),
+    'ct_calc_clim_t': (C.c_int, [_p, _p, C.c_int, C.c_long, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _p, _p]),
+    'ct_calc_anom_t': (C.c_int, [_p, _p, C.c_int, C.c_long, C.c_int, C.c_int, _i32p, C.c_int, _p, C.c_int, _p, _p]),
+    'ct_gather_planes_t': (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int, C.c_int, _p, _p]),
     'ct_run_lifecycle': (C.c_int, [_p, _p, _p, C.c_int, C.c_long, C.c_int, C.c_int, _f64p, _longp, _p]),
     'ct_lifecycle_fetch': (C.c_int, [_p, C.c_long] + [_i32p] * 4 + [_f64p] * 5),
 }

@@ -11,6 +11,8 @@ Differences kept deliberately small and documented:
   * ``ds[variable].data`` may be a torch CUDA tensor; then the cube never leaves the GPU and ``flag`` is a CUDA tensor.
   * ``flag`` is int32 (the reference's scipy label dtype is int32 below 2**31-2 cells and int64 above; pass
     ``reference_dtype=True`` to widen on the host exactly where scipy would).
+  * calc_clim / calc_anom / quantile keep the precision of their input like xarray does: float32 in -> float32 out,
+    float64 in -> float64 out (every mean is accumulated in float64 either way); other dtypes are computed as float64.
 """
 from __future__ import annotations
 
@@ -318,8 +320,8 @@ class contrack(object):
         rest = [d for d in dims if d != self._time_name]
         if rest != [self._latitude_name, self._longitude_name]:
             m = m.permute(1, 0) if hasattr(m, 'permute') else m.T
-        return _ds.DataArray(m, tuple(rest), coords={d: self.ds[d] for d in rest if d in self.ds},
-                             attrs=dict(self.ds[variable].attrs), name=variable)
+        return self._dataarray(m, rest, {d: self.ds[d] for d in rest if d in self.ds.variables},
+                               attrs=dict(self.ds[variable].attrs), name=variable)
 
     def _groups(self, groupby):
         keys = time_group_keys(self.ds[self._time_name].data, groupby)
@@ -331,11 +333,11 @@ class contrack(object):
         data, dims, sort = self._cube_tlatlon(variable)
         uniq, gidx = self._groups(groupby)
         clim = self._engine().calc_clim(data, gidx, len(uniq), int(window))
-        coords = {groupby: _ds.DataArray(uniq, (groupby,))}
+        coords = {groupby: uniq}
         for d in (self._latitude_name, self._longitude_name):
             coords[d] = self.ds[d]
-        return _ds.DataArray(clim, (groupby, self._latitude_name, self._longitude_name), coords=coords,
-                             attrs=dict(self.ds[variable].attrs), name=variable)
+        return self._dataarray(clim, (groupby, self._latitude_name, self._longitude_name), coords,
+                               attrs=dict(self.ds[variable].attrs), name=variable)
 
     def calc_anom(self, variable, window=1, smooth=1, groupby='dayofyear', clim=None):
         logger.info("Set up dimensions...")
@@ -414,10 +416,8 @@ class contrack(object):
             y0, y1 = sl.start, sl.stop
         qa = np.atleast_1d(np.asarray(q, np.float64))
         out = self._engine().quantile_time(data, qa, y0, y1)
-        coords = {'quantile': _ds.DataArray(qa, ('quantile',)),
-                  self._latitude_name: _ds.DataArray(lat[y0:y1], (self._latitude_name,)),
-                  self._longitude_name: self.ds[self._longitude_name]}
-        return _ds.DataArray(out, ('quantile', self._latitude_name, self._longitude_name), coords=coords, name=variable)
+        coords = {'quantile': qa, self._latitude_name: lat[y0:y1], self._longitude_name: self.ds[self._longitude_name]}
+        return self._dataarray(out, ('quantile', self._latitude_name, self._longitude_name), coords, name=variable)
 
     def quantile_threshold(self, variable, q, latitude=None):
         """README.rst:150-151: float(ds[variable].sel(latitude=...).quantile([q], dim='time').mean()) -- the objective
@@ -434,13 +434,23 @@ class contrack(object):
         ntime = int(data.shape[0])
         cnt64 = cnt.double() if hasattr(cnt, 'is_cuda') else cnt.astype(np.int64)      # numpy: int64 / int -> float64
         freq = cnt64 / ntime * 100
-        return _ds.DataArray(freq, (self._latitude_name, self._longitude_name),
-                             coords={d: self.ds[d] for d in (self._latitude_name, self._longitude_name)}, name=flag)
+        return self._dataarray(freq, (self._latitude_name, self._longitude_name),
+                               {d: self.ds[d] for d in (self._latitude_name, self._longitude_name)}, name=flag)
 
     def _variable(self, dims, data, attrs):
         if xr is not None and isinstance(self.ds, xr.Dataset):
             return xr.Variable(dims, _host(data), attrs=attrs)
         return _ds.Variable(dims, data, attrs)
+
+    def _dataarray(self, data, dims, coords, attrs=None, name=None):
+        """A DataArray of the dataset's own kind: xarray.DataArray (host data) when ``ds`` is an xarray.Dataset -- what
+        calc_clim / calc_mean return in the reference (tests/test_contrack.py:79-80) -- else the stand-in."""
+        if xr is not None and isinstance(self.ds, xr.Dataset):
+            return xr.DataArray(_host(data), dims=tuple(dims), coords={k: _host(getattr(v, 'data', v)) for k, v in coords.items()},
+                                attrs=dict(attrs or {}), name=name)
+        return _ds.DataArray(data, tuple(dims), coords={k: (v if isinstance(v, _ds.DataArray) else
+                                                           _ds.DataArray(_host(getattr(v, 'data', v)), (k,)))
+                                                        for k, v in coords.items()}, attrs=attrs, name=name)
 
     # ---- run_contrack (contrack.py:583-796) ------------------------------------------------------------------------
     def run_contrack(self, variable, threshold, gorl, overlap, persistence, twosided=True, reference_dtype=False):
@@ -459,23 +469,27 @@ class contrack(object):
             thr_keys = _host(threshold['dayofyear'].data)
             thr_vals = _host(threshold.data)
             doy = time_group_keys(self.ds[self._time_name].data, 'dayofyear')
-            pos = np.searchsorted(thr_keys, doy)
-            if (pos >= len(thr_keys)).any() or (thr_keys[np.minimum(pos, len(thr_keys) - 1)] != doy).any():
+            srt = np.argsort(thr_keys, kind='stable')      # xarray aligns the groups by LABEL: the coordinate may be unsorted
+            pos = np.searchsorted(thr_keys[srt], doy)
+            if (pos >= len(thr_keys)).any() or (thr_keys[srt][np.minimum(pos, len(thr_keys) - 1)] != doy).any():
                 raise KeyError('threshold has no value for some dayofyear of the time axis')
-            thr = thr_vals[pos].astype(np.float64)
+            thr = thr_vals[srt[pos]].astype(np.float64)
             thr_is_f32 = is_f32 and thr_vals.dtype == np.float32
         else:
             thr = np.array([threshold], np.float64)
             # numpy 2 promotion: python scalars are weak (compare in the array's float32), numpy float64 scalars are not
             weak = isinstance(threshold, (int, float)) and not isinstance(threshold, np.floating)
-            thr_is_f32 = is_f32 and (weak or isinstance(threshold, (np.float32, np.float16, np.integer)))
+            # (numpy integer scalars of 4+ bytes promote a float32 array to float64; the small ones keep float32)
+            small_int = isinstance(threshold, np.integer) and np.dtype(type(threshold)).itemsize <= 2
+            thr_is_f32 = is_f32 and (weak or small_int or isinstance(threshold, (np.float32, np.float16, np.bool_)))
 
         # steps 2-4 on the GPU
         logger.info("Apply overlap...")
         logger.info("Apply persistence...")
         flag, num_features = self._engine().run_contrack(
             data, self.area_weights(), thr, thr_is_f32, GORL_TO_OP[gorl], overlap, persistence, twosided)
-        if reference_dtype and flag.size >= 2 ** 31 - 2:
+        ncells = int(np.prod([int(n) for n in flag.shape]))       # (a torch tensor's .size is a method)
+        if reference_dtype and ncells >= 2 ** 31 - 2:
             flag = flag.long() if hasattr(flag, 'long') else flag.astype(np.int64)
 
         # step 5 (contrack.py:775-791): the reference applies `transpose(sort)` to the (time, lat, lon) result

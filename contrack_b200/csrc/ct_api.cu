@@ -29,13 +29,13 @@
 #include "ct_tables.h"
 
 namespace cta {
-cudaError_t group_mean(const float* z, long HW, int G, const int32_t* gptr_dev, const int32_t* gidx_dev, float* gmean,
+cudaError_t group_mean(const void* z, int f64, long HW, int G, const int32_t* gptr_dev, const int32_t* gidx_dev, void* gmean,
                        cudaStream_t st);
-cudaError_t clim_smooth(const float* gmean, long HW, int G, int window, float* clim, cudaStream_t st);
-cudaError_t anom(const float* z, long HW, long T, const int32_t* group_dev, const float* clim, int smooth, float* out,
+cudaError_t clim_smooth(const void* gmean, int f64, long HW, int G, int window, void* clim, cudaStream_t st);
+cudaError_t anom(const void* z, int f64, long HW, long T, const int32_t* group_dev, const void* clim, int smooth, void* out,
                  cudaStream_t st);
-cudaError_t anom_chunks(const float* z, long HW, long T, const int32_t* chunk_start_dev, int nchunks, const int32_t* group_dev,
-                        const float* clim, int smooth, float* out, cudaStream_t st);
+cudaError_t anom_chunks(const void* z, int f64, long HW, long T, const int32_t* chunk_start_dev, int nchunks,
+                        const int32_t* group_dev, const void* clim, int smooth, void* out, cudaStream_t st);
 }  // namespace cta
 
 namespace cte {
@@ -43,8 +43,8 @@ cudaError_t quantile_time(const float* x, long T, int H, int W, int y0, int y1, 
                           cudaStream_t st);
 cudaError_t flag_count(const int32_t* flag, long T, int H, int W, int v, int32_t* count, int sm_count, cudaStream_t st);
 cudaError_t divide_f32(const float* in, size_t n, float g, float* out, cudaStream_t st);
-cudaError_t gather_planes(const float* src, int G, int Hs, int Ws, const int32_t* iy_dev, const int32_t* ix_dev, int H, int W,
-                          float* dst, cudaStream_t st);
+cudaError_t gather_planes(const void* src, int f64, int G, int Hs, int Ws, const int32_t* iy_dev, const int32_t* ix_dev, int H,
+                          int W, void* dst, cudaStream_t st);
 }  // namespace cte
 
 namespace {
@@ -356,7 +356,8 @@ int prepare(ct_ctx* c, long T, int H, int W, const double* w_host, const double*
     CT_CUDA(c->slots.ensure((size_t)nrows * ctk::RUN_SLOTS_PER_ROW * sizeof(uint32_t)));
     CT_CUDA(c->counters.ensure(128));
     CT_CUDA(c->hp_counters.ensure(128));
-    CT_CUDA(cudaMemsetAsync(c->counters.as<uint32_t>() + 16, 0, 4, st));            // "a row has more runs than slots"
+    CT_CUDA(cudaMemsetAsync(c->counters.as<uint32_t>() + 16, 0, 12, st));           // 16: "a row has more runs than slots",
+                                                                                    // 17: overflow-row count, 18: run index wrapped
     for (auto& e : c->ev) if (!e) CT_CUDA(cudaEventCreate(&e));
     c->launches = 0;
     return CT_OK;
@@ -426,15 +427,19 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
 
     CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(n > 1024 ? n : 1024) * sizeof(uint32_t)));
     prof_mark(c, "start", st);
-    CT_CUDA(ctk::exclusive_scan_u32(U(c->row_cnt) + r0, U(c->row_ptr) + r0, n, U(c->scan_tmp), st, (uint32_t)c->tb_runs));
+    // counter 18: "the run total of the cube no longer fits the 32-bit run index" (dense / noisy masks on large cubes)
+    CT_CUDA(ctk::exclusive_scan_u32(U(c->row_cnt) + r0, U(c->row_ptr) + r0, n, U(c->scan_tmp), st, (uint32_t)c->tb_runs,
+                                    cnt_dev + 18));
     CT_CUDA(ctk::exclusive_scan_u32(U(c->seam_flag) + r0, U(c->seam_pos) + r0, n, U(c->scan_tmp), st,
                                     (uint32_t)c->tb_seams));
     c->launches += 6;
     CT_CUDA(cudaMemcpyAsync(cnt_host + 0, U(c->row_ptr) + r1, 4, cudaMemcpyDeviceToHost, st));
     CT_CUDA(cudaMemcpyAsync(cnt_host + 1, U(c->seam_pos) + r1, 4, cudaMemcpyDeviceToHost, st));
-    CT_CUDA(cudaMemcpyAsync(cnt_host + 16, cnt_dev + 16, 4, cudaMemcpyDeviceToHost, st));
+    CT_CUDA(cudaMemcpyAsync(cnt_host + 16, cnt_dev + 16, 12, cudaMemcpyDeviceToHost, st));
     prof_mark(c, "row_scans", st);
     CT_CUDA(cudaStreamSynchronize(st));
+    if (cnt_host[18] || cnt_host[0] >= 0xfffffff0u)
+        return fail(CT_ERR_CAPACITY, "more than 2^32 - 16 row-runs in the cube: the run tables are indexed with 32 bits");
     const long Rb = c->tb_runs, Re = cnt_host[0], Sb = c->tb_seams, Se = cnt_host[1];
 
     // ---- runs + 2-D components ----
@@ -2120,7 +2125,14 @@ double ct_numpy_pairwise_sum_rle(const double* value, const int64_t* count, long
 
 int ct_calc_clim(ct_ctx* c, const float* z_dev, long T, int H, int W, const int32_t* group_host, int G, int window,
                  float* clim_dev, void* stream) {
+    return ct_calc_clim_t(c, z_dev, CT_F32, T, H, W, group_host, G, window, clim_dev, stream);
+}
+
+int ct_calc_clim_t(ct_ctx* c, const void* z_dev, int dtype, long T, int H, int W, const int32_t* group_host, int G, int window,
+                   void* clim_dev, void* stream) {
     if (!c || !z_dev || !group_host || !clim_dev) return fail(CT_ERR_ARG, "null argument");
+    if (dtype != CT_F32 && dtype != CT_F64) return fail(CT_ERR_ARG, "dtype must be CT_F32 or CT_F64");
+    const int f64 = dtype == CT_F64;
     if (T <= 0 || H <= 0 || W <= 0 || G <= 0 || window <= 0) return fail(CT_ERR_ARG, "bad shape / window");
     CT_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -2137,18 +2149,25 @@ int ct_calc_clim(ct_ctx* c, const float* z_dev, long T, int H, int W, const int3
         for (long t = 0; t < T; ++t) gidx[pos[group_host[t]]++] = (int32_t)t;
     }
     CT_CUDA(c->a_gptr.ensure((size_t)(G + 1) * 4)); CT_CUDA(c->a_gidx.ensure((size_t)T * 4));
-    CT_CUDA(c->a_gmean.ensure((size_t)G * HW * 4));
+    CT_CUDA(c->a_gmean.ensure((size_t)G * HW * (f64 ? 8 : 4)));
     CT_CUDA(cudaMemcpyAsync(c->a_gptr.p, gptr.data(), (size_t)(G + 1) * 4, cudaMemcpyHostToDevice, st));
     CT_CUDA(cudaMemcpyAsync(c->a_gidx.p, gidx.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st));
     CT_CUDA(cudaStreamSynchronize(st));                               // gptr / gidx are locals
-    CT_CUDA(cta::group_mean(z_dev, HW, G, c->a_gptr.as<int32_t>(), c->a_gidx.as<int32_t>(), c->a_gmean.as<float>(), st));
-    CT_CUDA(cta::clim_smooth(c->a_gmean.as<float>(), HW, G, window, clim_dev, st));
+    CT_CUDA(cta::group_mean(z_dev, f64, HW, G, c->a_gptr.as<int32_t>(), c->a_gidx.as<int32_t>(), c->a_gmean.p, st));
+    CT_CUDA(cta::clim_smooth(c->a_gmean.p, f64, HW, G, window, clim_dev, st));
     return CT_OK;
 }
 
 int ct_calc_anom(ct_ctx* c, const float* z_dev, long T, int H, int W, const int32_t* group_host, int G,
                  const float* clim_dev, int smooth, float* anom_dev, void* stream) {
+    return ct_calc_anom_t(c, z_dev, CT_F32, T, H, W, group_host, G, clim_dev, smooth, anom_dev, stream);
+}
+
+int ct_calc_anom_t(ct_ctx* c, const void* z_dev, int dtype, long T, int H, int W, const int32_t* group_host, int G,
+                   const void* clim_dev, int smooth, void* anom_dev, void* stream) {
     if (!c || !z_dev || !group_host || !clim_dev || !anom_dev) return fail(CT_ERR_ARG, "null argument");
+    if (dtype != CT_F32 && dtype != CT_F64) return fail(CT_ERR_ARG, "dtype must be CT_F32 or CT_F64");
+    const int f64 = dtype == CT_F64;
     if (T <= 0 || H <= 0 || W <= 0 || G <= 0 || smooth <= 0) return fail(CT_ERR_ARG, "bad shape / smooth");
     for (long t = 0; t < T; ++t)
         if (group_host[t] < 0 || group_host[t] >= G) return fail(CT_ERR_ARG, "group index out of range at t=%ld", t);
@@ -2178,9 +2197,9 @@ int ct_calc_anom(ct_ctx* c, const float* z_dev, long T, int H, int W, const int3
     CT_CUDA(cudaMemcpyAsync(gdev + T, cs.data(), (size_t)(nchunks + 1) * 4, cudaMemcpyHostToDevice, st));
     CT_CUDA(cudaStreamSynchronize(st));                               // caller may free group_host after return; cs is local
     if (nchunks <= 65535)
-        CT_CUDA(cta::anom_chunks(z_dev, (long)H * W, T, gdev + T, nchunks, gdev, clim_dev, smooth, anom_dev, st));
+        CT_CUDA(cta::anom_chunks(z_dev, f64, (long)H * W, T, gdev + T, nchunks, gdev, clim_dev, smooth, anom_dev, st));
     else
-        CT_CUDA(cta::anom(z_dev, (long)H * W, T, gdev, clim_dev, smooth, anom_dev, st));
+        CT_CUDA(cta::anom(z_dev, f64, (long)H * W, T, gdev, clim_dev, smooth, anom_dev, st));
     return CT_OK;
 }
 
@@ -2218,7 +2237,13 @@ int ct_divide_f32(ct_ctx* c, const float* in_dev, size_t n, float divisor, float
 
 int ct_gather_planes(ct_ctx* c, const float* src_dev, int G, int Hs, int Ws, const int32_t* iy_host, const int32_t* ix_host,
                      int H, int W, float* dst_dev, void* stream) {
+    return ct_gather_planes_t(c, src_dev, CT_F32, G, Hs, Ws, iy_host, ix_host, H, W, dst_dev, stream);
+}
+
+int ct_gather_planes_t(ct_ctx* c, const void* src_dev, int dtype, int G, int Hs, int Ws, const int32_t* iy_host,
+                       const int32_t* ix_host, int H, int W, void* dst_dev, void* stream) {
     if (!c || !src_dev || !iy_host || !ix_host || !dst_dev) return fail(CT_ERR_ARG, "null argument");
+    if (dtype != CT_F32 && dtype != CT_F64) return fail(CT_ERR_ARG, "dtype must be CT_F32 or CT_F64");
     if (G <= 0 || Hs <= 0 || Ws <= 0 || H <= 0 || W <= 0 || H > 65535) return fail(CT_ERR_ARG, "bad shape");
     for (int y = 0; y < H; ++y) if (iy_host[y] < 0 || iy_host[y] >= Hs) return fail(CT_ERR_ARG, "row index out of range");
     for (int x = 0; x < W; ++x) if (ix_host[x] < 0 || ix_host[x] >= Ws) return fail(CT_ERR_ARG, "column index out of range");
@@ -2229,7 +2254,7 @@ int ct_gather_planes(ct_ctx* c, const float* src_dev, int G, int Hs, int Ws, con
     CT_CUDA(cudaMemcpyAsync(d, iy_host, (size_t)H * 4, cudaMemcpyHostToDevice, st));
     CT_CUDA(cudaMemcpyAsync(d + H, ix_host, (size_t)W * 4, cudaMemcpyHostToDevice, st));
     CT_CUDA(cudaStreamSynchronize(st));
-    CT_CUDA(cte::gather_planes(src_dev, G, Hs, Ws, d, d + H, H, W, dst_dev, st));
+    CT_CUDA(cte::gather_planes(src_dev, dtype == CT_F64, G, Hs, Ws, d, d + H, H, W, dst_dev, st));
     return CT_OK;
 }
 

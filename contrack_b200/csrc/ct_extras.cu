@@ -152,9 +152,10 @@ __global__ void __launch_bounds__(256) k_divide_f32(const float* __restrict__ in
 }
 
 // dst[g, y, x] = src[g, iy[y], ix[x]]
-__global__ void __launch_bounds__(256) k_gather_planes(const float* __restrict__ src, int Hs, int Ws,
+template <typename S>
+__global__ void __launch_bounds__(256) k_gather_planes(const S* __restrict__ src, int Hs, int Ws,
                                                        const int32_t* __restrict__ iy, const int32_t* __restrict__ ix, int H,
-                                                       int W, float* __restrict__ dst) {
+                                                       int W, S* __restrict__ dst) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const long g = blockIdx.z;
@@ -196,15 +197,22 @@ cudaError_t divide_f32(const float* in, size_t n, float g, float* out, cudaStrea
     return cudaGetLastError();
 }
 
-cudaError_t gather_planes(const float* src, int G, int Hs, int Ws, const int32_t* iy_dev, const int32_t* ix_dev, int H, int W,
-                          float* dst, cudaStream_t st) {
-    if (G <= 0 || H <= 0 || W <= 0) return cudaSuccess;
+template <typename S>
+static cudaError_t gather_planes_t(const S* src, int G, int Hs, int Ws, const int32_t* iy_dev, const int32_t* ix_dev, int H, int W,
+                                   S* dst, cudaStream_t st) {
     for (int g0 = 0; g0 < G; g0 += 65535) {
         const int ng = G - g0 < 65535 ? G - g0 : 65535;
-        k_gather_planes<<<dim3((unsigned)((W + 255) / 256), (unsigned)H, (unsigned)ng), 256, 0, st>>>(
+        k_gather_planes<S><<<dim3((unsigned)((W + 255) / 256), (unsigned)H, (unsigned)ng), 256, 0, st>>>(
             src + (size_t)g0 * Hs * Ws, Hs, Ws, iy_dev, ix_dev, H, W, dst + (size_t)g0 * H * W);
     }
     return cudaGetLastError();
+}
+
+cudaError_t gather_planes(const void* src, int f64, int G, int Hs, int Ws, const int32_t* iy_dev, const int32_t* ix_dev, int H,
+                          int W, void* dst, cudaStream_t st) {
+    if (G <= 0 || H <= 0 || W <= 0) return cudaSuccess;
+    return f64 ? gather_planes_t((const double*)src, G, Hs, Ws, iy_dev, ix_dev, H, W, (double*)dst, st)
+               : gather_planes_t((const float*)src, G, Hs, Ws, iy_dev, ix_dev, H, W, (float*)dst, st);
 }
 
 }  // namespace cte

@@ -415,17 +415,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __
     if (threadIdx.x == 0) sums[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, long nb, uint32_t* total_out, uint32_t base) {
+// wide_flag (may be null): set to 1 when base + total does not fit in 32 bits (the scanned values have wrapped)
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, long nb, uint32_t* total_out, uint32_t base,
+                                                    uint32_t* wide_flag) {
     __shared__ uint32_t s_warp[33];
     uint32_t running = base;
+    unsigned long long running64 = base;
     for (long b0 = 0; b0 < nb; b0 += 1024) {
         const long i = b0 + threadIdx.x;
         uint32_t v = i < nb ? sums[i] : 0, tot;
         uint32_t ex = block_excl_scan(v, s_warp, &tot);
         if (i < nb) sums[i] = running + ex;
         running += tot;
+        running64 += tot;
     }
-    if (threadIdx.x == 0) *total_out = running;
+    if (threadIdx.x == 0) {
+        *total_out = running;
+        if (wide_flag && (running64 >> 32)) *wide_flag = 1u;
+    }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
@@ -1123,14 +1130,15 @@ cudaError_t row_stats(const uint32_t* bits, long nrows, int W, int Ww, uint32_t*
 
 size_t scan_tmp_elems(long n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 2; }
 
-cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st, uint32_t base) {
+cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st, uint32_t base,
+                               uint32_t* wide_flag) {
     if (n == 0) {
-        k_scan_sums<<<1, 1024, 0, st>>>(tmp, 0, out, base);
+        k_scan_sums<<<1, 1024, 0, st>>>(tmp, 0, out, base, wide_flag);
         return cudaGetLastError();
     }
     const long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, tmp);
-    k_scan_sums<<<1, 1024, 0, st>>>(tmp, nb, out + n, base);
+    k_scan_sums<<<1, 1024, 0, st>>>(tmp, nb, out + n, base, wide_flag);
     k_scan_final<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, tmp);
     return cudaGetLastError();
 }

@@ -35,8 +35,9 @@ cudaError_t row_stats(const uint32_t* bits, long nrows, int W, int Ww, uint32_t*
 //
 // out[0..n] = base + exclusive prefix sums of in[0..n-1] (out[n] = base + total).  `tmp` needs scan_tmp_elems(n) uint32.
 size_t scan_tmp_elems(long n);
+// wide_flag (device, may be null) is set to 1 if base + total needs more than 32 bits (the output has wrapped).
 cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st,
-                               uint32_t base = 0);
+                               uint32_t base = 0, uint32_t* wide_flag = nullptr);
 
 // rows [row0, row0 + nrows) of the GLOBAL bit rows / row_ptr -> run_x, run_row (global row numbers) at row_ptr[row]...
 cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww, uint32_t* run_x,

@@ -114,15 +114,31 @@ class Engine(object):
 
 
     # ------------------------------------------------------------------------------------------------------------
-    def _to_device(self, x):
-        """(cuda float32 tensor, was_host)"""
+    def _to_device(self, x, like=None):
+        """(cuda tensor, was_host).  float32 and float64 keep their precision (xarray computes a float64 cube in float64:
+        climatology, anomaly and quantiles of packed ERA5 decoded with scale/offset are float64 in the reference); anything
+        else is converted to float64, numpy's result type for integer input.  `like`: another tensor whose dtype wins if it
+        is the wider one (numpy promotion of `x - clim`)."""
         import torch
         if _is_torch(x):
             if not x.is_cuda:
                 raise ValueError('torch input must live on a CUDA device (pass numpy for host data)')
-            return x.contiguous().float() if x.dtype != torch.float32 else x.contiguous(), False
-        a = np.ascontiguousarray(np.asarray(x), np.float32)
-        return torch.from_numpy(a).to('cuda:%d' % self.device), True
+            t, was_host = x, False
+        else:
+            a = np.asarray(x)
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            t, was_host = torch.from_numpy(np.ascontiguousarray(a)).to('cuda:%d' % self.device), True
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.double()
+        if like is not None and like.dtype == torch.float64 and t.dtype != torch.float64:
+            t = t.double()
+        return t.contiguous(), was_host
+
+    @staticmethod
+    def _ct_dtype(t):
+        import torch
+        return _lib.CT_F64 if t.dtype == torch.float64 else _lib.CT_F32
 
     def calc_clim(self, z, group_index, ngroups, window):
         """z [T,H,W] float32 (numpy or torch CUDA); group_index [T] int 0..ngroups-1.  Returns clim [G,H,W] of the same
@@ -133,27 +149,30 @@ class Engine(object):
         g = np.ascontiguousarray(group_index, np.int32)
         if g.shape != (T,):
             raise ValueError('group_index must have shape (T,)')
-        clim = torch.empty((int(ngroups), H, W), dtype=torch.float32, device=zd.device)
+        clim = torch.empty((int(ngroups), H, W), dtype=zd.dtype, device=zd.device)
         stream = torch.cuda.current_stream(zd.device).cuda_stream
-        _lib.check(self.lib.ct_calc_clim(self.handle, C.c_void_p(zd.data_ptr()), T, H, W, _lib.ptr(g, _lib._i32p),
-                                         int(ngroups), int(window), C.c_void_p(clim.data_ptr()), C.c_void_p(stream)))
+        _lib.check(self.lib.ct_calc_clim_t(self.handle, C.c_void_p(zd.data_ptr()), self._ct_dtype(zd), T, H, W,
+                                           _lib.ptr(g, _lib._i32p), int(ngroups), int(window), C.c_void_p(clim.data_ptr()),
+                                           C.c_void_p(stream)))
         return clim.cpu().numpy() if was_host else clim
 
     def calc_anom(self, z, group_index, ngroups, clim, smooth, out=None):
         """anom [T,H,W] = centred rolling mean (window `smooth`) of z[t] - clim[group_index[t]] (contrack.py:568-570)."""
         import torch
         zd, was_host = self._to_device(z)
-        cd, _ = self._to_device(clim)
+        cd, _ = self._to_device(clim, like=zd)
+        if cd.dtype != zd.dtype:                       # float32 z against a float64 climatology: numpy promotes to float64
+            zd = zd.double()
         T, H, W = (int(s) for s in zd.shape)
         g = np.ascontiguousarray(group_index, np.int32)
-        if out is None or was_host:
-            outd = torch.empty((T, H, W), dtype=torch.float32, device=zd.device)
+        if out is None or was_host or out.dtype != zd.dtype:
+            outd = torch.empty((T, H, W), dtype=zd.dtype, device=zd.device)
         else:
             outd = out
         stream = torch.cuda.current_stream(zd.device).cuda_stream
-        _lib.check(self.lib.ct_calc_anom(self.handle, C.c_void_p(zd.data_ptr()), T, H, W, _lib.ptr(g, _lib._i32p),
-                                         int(ngroups), C.c_void_p(cd.data_ptr()), int(smooth), C.c_void_p(outd.data_ptr()),
-                                         C.c_void_p(stream)))
+        _lib.check(self.lib.ct_calc_anom_t(self.handle, C.c_void_p(zd.data_ptr()), self._ct_dtype(zd), T, H, W,
+                                           _lib.ptr(g, _lib._i32p), int(ngroups), C.c_void_p(cd.data_ptr()), int(smooth),
+                                           C.c_void_p(outd.data_ptr()), C.c_void_p(stream)))
         return outd.cpu().numpy() if was_host else outd
 
     # ---- callers either side of the path (SURVEY.md 8f; ct_extras.cu) -----------------------------------------------
@@ -194,6 +213,8 @@ class Engine(object):
         """x / float32(divisor) in float32 (contrack.py:417-419)."""
         import torch
         xd, was_host = self._to_device(x)
+        if xd.dtype != torch.float32:
+            raise TypeError('divide() is the float32 kernel of calculate_gph_from_gp; float64 data divide on the caller side')
         out = torch.empty_like(xd)
         stream = torch.cuda.current_stream(xd.device).cuda_stream
         _lib.check(self.lib.ct_divide_f32(self.handle, C.c_void_p(xd.data_ptr()), int(xd.numel()), float(np.float32(divisor)),
@@ -207,11 +228,11 @@ class Engine(object):
         G, Hs, Ws = (int(s) for s in sd.shape)
         iy = np.ascontiguousarray(iy, np.int32)
         ix = np.ascontiguousarray(ix, np.int32)
-        out = torch.empty((G, len(iy), len(ix)), dtype=torch.float32, device=sd.device)
+        out = torch.empty((G, len(iy), len(ix)), dtype=sd.dtype, device=sd.device)
         stream = torch.cuda.current_stream(sd.device).cuda_stream
-        _lib.check(self.lib.ct_gather_planes(self.handle, C.c_void_p(sd.data_ptr()), G, Hs, Ws, _lib.ptr(iy, _lib._i32p),
-                                             _lib.ptr(ix, _lib._i32p), len(iy), len(ix), C.c_void_p(out.data_ptr()),
-                                             C.c_void_p(stream)))
+        _lib.check(self.lib.ct_gather_planes_t(self.handle, C.c_void_p(sd.data_ptr()), self._ct_dtype(sd), G, Hs, Ws,
+                                               _lib.ptr(iy, _lib._i32p), _lib.ptr(ix, _lib._i32p), len(iy), len(ix),
+                                               C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
         return out.cpu().numpy() if was_host else out
 
     # ------------------------------------------------------------------------------------------------------------

@@ -26,7 +26,9 @@ enum ct_status {
     CT_OK = 0,
     CT_ERR_ARG = -1,        /* bad argument (also: unknown `op`, the reference's ValueError at contrack.py:658/673) */
     CT_ERR_CUDA = -2,       /* CUDA runtime error, or no usable GPU */
-    CT_ERR_CAPACITY = -3,   /* a size exceeds what the index types support (H, W > 65535; > 2^31-1 row-runs) */
+    CT_ERR_CAPACITY = -3,   /* a size exceeds what the index types support: H, W > 65535; T*H >= 2^31; more than 2^32 - 16
+                               row-runs in the cube (a row holds up to W/2 runs: dense or noisy masks on very large cubes);
+                               more than 2^31 - 1 components or pairs */
     CT_ERR_NEARTIE = -4,    /* overlap decision within rounding distance of the threshold on rows whose area weights
                                are not exactly summable and the exact resolver could not decide */
     CT_ERR_INTERNAL = -5
@@ -277,6 +279,14 @@ int ct_calc_clim(ct_ctx* ctx, const float* z_dev, long T, int H, int W, const in
 int ct_calc_anom(ct_ctx* ctx, const float* z_dev, long T, int H, int W, const int32_t* group_host, int G,
                  const float* clim_dev, int smooth, float* anom_dev, void* stream);
 
+/* The same two calls for float32 OR float64 cubes (dtype = ct_dtype of z, the climatology and the anomaly alike): xarray
+ * keeps the precision of its input -- a float64 `z` (packed ERA5 decoded with scale/offset) gives a float64 climatology and
+ * anomaly, every mean accumulated in float64 (contrack.py:483-489, 568-570). */
+int ct_calc_clim_t(ct_ctx* ctx, const void* z_dev, int dtype, long T, int H, int W, const int32_t* group_host, int G,
+                   int window, void* clim_dev, void* stream);
+int ct_calc_anom_t(ct_ctx* ctx, const void* z_dev, int dtype, long T, int H, int W, const int32_t* group_host, int G,
+                   const void* clim_dev, int smooth, void* anom_dev, void* stream);
+
 /* ---- callers either side of the path -------------------------------------------------------------------
  * ct_quantile_time   README.rst:150-151: ds[var].sel(latitude=band).quantile(q, dim='time') -- numpy's nanquantile with the
  *                    'linear' method along time for every grid point of rows [y0, y1): out_dev [nq, y1-y0, W] float64, bit
@@ -293,6 +303,9 @@ int ct_flag_count(ct_ctx* ctx, const int32_t* flag_dev, long T, int H, int W, in
 int ct_divide_f32(ct_ctx* ctx, const float* in_dev, size_t n, float divisor, float* out_dev, void* stream);
 int ct_gather_planes(ct_ctx* ctx, const float* src_dev, int G, int Hs, int Ws, const int32_t* iy_host, const int32_t* ix_host,
                      int H, int W, float* dst_dev, void* stream);
+/* ... for float32 or float64 planes (dtype = ct_dtype) */
+int ct_gather_planes_t(ct_ctx* ctx, const void* src_dev, int dtype, int G, int Hs, int Ws, const int32_t* iy_host,
+                       const int32_t* ix_host, int H, int W, void* dst_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -188,13 +188,13 @@ def _rolling_mean_centered(x, window):
     if window <= 0 or window > n:
         return out
     left = window // 2
-    acc = np.cumsum(np.concatenate([np.zeros((1,) + x.shape[1:], np.float64), x.astype(np.float64)], axis=0), axis=0)
-    for i in range(n):
-        a = i - left
-        b = a + window
-        if a < 0 or b > n:
-            continue
-        out[i] = ((acc[b] - acc[a]) / window).astype(x.dtype)
+    m = n - window + 1                                     # complete windows: outputs left .. left + m - 1
+    # direct window sums (a NaN makes only the windows that contain it NaN, as xarray's rolling mean does; a cumulative
+    # sum would poison every later window)
+    acc = np.zeros((m,) + x.shape[1:], np.float64)
+    for k in range(window):
+        acc += x[k:k + m]
+    out[left:left + m] = (acc / window).astype(x.dtype)
     return out
 
 

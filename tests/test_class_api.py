@@ -132,6 +132,30 @@ def test_dayofyear_threshold_dataarray():
 
 
 @pytest.mark.gpu
+def test_dayofyear_threshold_with_unsorted_coordinate_and_reference_dtype():
+    """xarray aligns a day-of-year threshold by LABEL: a rolled coordinate gives the same result; reference_dtype=True must
+    work for host and device data (the cube is far below 2**31 - 2 cells, so the result stays int32)."""
+    import torch
+    d = np.load(dataset)
+    from contrack_b200.contrack import time_group_keys
+    doy = time_group_keys(d['time'], 'dayofyear')
+    thr_vals = np.linspace(120, 180, len(doy))
+    c = contrack(dataset)
+    c.run_contrack('anom', DataArray(thr_vals, ('dayofyear',), coords={'dayofyear': DataArray(doy, ('dayofyear',))}), '>=', 0.5, 3)
+    ref = np.asarray(c['flag']).copy()
+    c2 = contrack(dataset)
+    k = 4
+    rolled = DataArray(np.roll(thr_vals, k), ('dayofyear',), coords={'dayofyear': DataArray(np.roll(doy, k), ('dayofyear',))})
+    c2.run_contrack('anom', rolled, '>=', 0.5, 3, reference_dtype=True)
+    assert np.array_equal(np.asarray(c2['flag']), ref) and np.asarray(c2['flag']).dtype == np.int32
+    ds = Dataset({'anom': (('time', 'latitude', 'longitude'), torch.from_numpy(d['anom']).cuda())},
+                 coords={'time': d['time'], 'latitude': d['latitude'], 'longitude': d['longitude']})
+    c3 = contrack(ds=ds)
+    c3.run_contrack('anom', rolled, '>=', 0.5, 3, reference_dtype=True)
+    assert c3['flag'].data.is_cuda and np.array_equal(c3['flag'].values, ref)
+
+
+@pytest.mark.gpu
 def test_calc_clim_and_anom_via_class():
     from oracle import contrack_oracle as oracle
     T, H, W = 800, 9, 12

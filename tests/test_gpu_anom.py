@@ -83,3 +83,43 @@ def test_device_resident_and_odd_plane_size(eng):
     assert clim.is_cuda and an.is_cuda
     ref = oracle.calc_anom(z, keys, 5, 2)
     np.testing.assert_allclose(an.cpu().numpy(), ref, rtol=1e-5, atol=2 * ATOL, equal_nan=True)
+
+
+def test_float64_input_stays_float64(eng):
+    """xarray keeps a float64 cube in float64 (packed ERA5 decoded with scale/offset): climatology and anomaly are float64
+    and equal the float64 restatement to rounding, not merely to float32 precision."""
+    T, H, W = 2 * 365 + 40, 6, 10
+    z = make_z(T, H, W, 5).astype(np.float64) + 1e-7 * np.arange(H * W).reshape(H, W)     # not representable in float32
+    keys, uniq, idx = doy_groups(T)
+    _, cref = oracle.calc_clim(z, keys, 31)
+    ref = oracle.calc_anom(z, keys, 31, 2)
+    clim = eng.calc_clim(z, idx, len(uniq), 31)
+    got = eng.calc_anom(z, idx, len(uniq), clim, 2)
+    assert clim.dtype == np.float64 and got.dtype == np.float64
+    np.testing.assert_allclose(clim, cref, rtol=1e-13, atol=1e-9)
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-9, equal_nan=True)
+    # float32 cube against a float64 climatology: numpy promotes the difference to float64
+    got2 = eng.calc_anom(z.astype(np.float32), idx, len(uniq), clim, 1)
+    assert got2.dtype == np.float64
+    np.testing.assert_allclose(got2, z.astype(np.float32).astype(np.float64) - cref[np.searchsorted(uniq, keys)], rtol=1e-13,
+                               atol=1e-9)
+    # odd plane size: the scalar float64 path
+    z3 = z[:, :3, :7].copy()
+    c3 = eng.calc_clim(z3, idx, len(uniq), 5)
+    np.testing.assert_allclose(eng.calc_anom(z3, idx, len(uniq), c3, 3), oracle.calc_anom(z3, keys, 5, 3), rtol=1e-12,
+                               atol=1e-9, equal_nan=True)
+
+
+def test_nan_gap_in_time_only_poisons_its_windows(eng):
+    """A NaN at one time step makes exactly the rolling windows that contain it NaN (xarray's rolling mean), in the
+    climatology smoothing and in the anomaly smoothing alike."""
+    T, H, W = 365 + 60, 4, 8
+    z = make_z(T, H, W, 6)
+    z[100, 1, 2] = np.nan                                  # a single-sample group: the group mean itself is NaN
+    keys, uniq, idx = doy_groups(T)
+    ref = oracle.calc_anom(z, keys, 5, 3)
+    clim = eng.calc_clim(z, idx, len(uniq), 5)
+    got = eng.calc_anom(z, idx, len(uniq), clim, 3)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.isnan(ref[95:110, 1, 2]).sum() < 15 and not np.isnan(ref[120:, 1, 2]).any()
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2 * ATOL, equal_nan=True)

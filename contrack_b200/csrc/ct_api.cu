@@ -23,10 +23,9 @@
 #include <thread>
 #include <vector>
 
-#include "ct_host.h"
-#include "ct_kernels.h"
+#include "ct_ctx.h"
+#include "ct_fast.h"
 #include "ct_shard.h"
-#include "ct_tables.h"
 
 namespace cta {
 cudaError_t group_mean(const void* z, int f64, long HW, int G, const int32_t* gptr_dev, const int32_t* gidx_dev, void* gmean,
@@ -47,159 +46,15 @@ cudaError_t gather_planes(const void* src, int f64, int G, int Hs, int Ws, const
                           int W, void* dst, cudaStream_t st);
 }  // namespace cte
 
-namespace {
+using cti::fail;
+using cti::now_ms;
 
-thread_local std::string g_err;
-
-int fail(int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return code;
+namespace cti {
+std::string& last_error() {
+    thread_local std::string e;
+    return e;
 }
-
-#define CT_CUDA(expr)                                                                                                \
-    do {                                                                                                             \
-        cudaError_t e__ = (expr);                                                                                    \
-        if (e__ != cudaSuccess)                                                                                      \
-            return fail(CT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);   \
-    } while (0)
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    // grow to at least `bytes`, preserving the first `keep` bytes (copied on `st`); `hint` = expected final size
-    cudaError_t grow(size_t bytes, size_t keep, cudaStream_t st, size_t hint = 0) {
-        if (bytes <= cap) return cudaSuccess;
-        if (!p || keep == 0) {
-            cudaError_t e = ensure(hint > bytes ? hint : bytes);
-            return e == cudaSuccess ? e : ensure(bytes);
-        }
-        size_t want = std::max(bytes + bytes / 4 + 256, hint);
-        void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, want);
-        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&q, want); }
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpyAsync(q, p, std::min(keep, cap), cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        cudaFree(p);
-        p = q; cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <typename T> T* as() const { return static_cast<T*>(p); }
-};
-
-struct PinBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
-        size_t want = bytes + bytes / 4 + 4096;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-    template <typename T> T* as() const { return static_cast<T*>(p); }
-};
-
-}  // namespace
-
-struct ct_ctx {
-    int device = 0, sm_count = 148;
-    long opt_tma = 3, opt_paint_tma = 0;      // threshold kernel variant, see ctk::ThresholdArgs::variant
-    // geometry of the last run
-    long T = 0; int H = 0, W = 0, Ww = 0;
-    long nruns = 0, ncomp = 0, npair = 0, nseam = 0, novr = 0;
-    // device scratch
-    DevBuf bits, row_cnt, seam_flag, row_ptr, seam_pos, scan_tmp, counters, slots;
-    DevBuf run_x, run_row, parent, root_flag, rank, run_comp, run_val;
-    DevBuf c_t, c_y0, c_y1, c_x0, c_x1, c_E, c_S, c_nsp, c_cls, c_val;
-    DevBuf s_row, s_a, s_b;
-    DevBuf h_key, h_npix, h_nsp, h_E, h_S;
-    DevBuf p_b, p_npix, p_nsp, p_E, p_S;
-    DevBuf k_conE, k_conS, k_fE, k_fS, k_nsp, k_fnsp, pcnt, pfill, pptr;
-    DevBuf seg_start, seg_pos, g_t, g_y0, g_y1, g_a, g_b;
-    DevBuf o_t, o_y, o_x0, o_x1, o_val;
-    DevBuf w_dev, special_dev, thr_dev;
-    DevBuf chunk_in[2], chunk_out[2];
-    DevBuf a_gptr, a_gidx, a_gmean, a_group;
-    // pinned host staging
-    PinBuf hp_counters, hp_tables, hp_val, hp_ovr;
-    cth::Result host_result;
-    cth::FastTables host_tb;                 // tables of the last tables_gpu() call (pointers into hp_tables)
-    long nseg = 0, halo_comps = 0;
-    int has_prev = 0;                        // sharded run: plane 0 of the scratch is the previous rank's last plane
-    PinBuf hp_plane;
-    int32_t* zero_started_for = nullptr;
-    int special_uniform = 0;
-    long opt_paint_runs = 1;                 // sparse paint by runs (1) or by rows (0)
-    long opt_gpu_tables = 1;                 // step 3 + 3-D labels on the device (single-GPU path)
-    long opt_chunks = 4;                     // time chunks of the pipelined run (tables of chunk k under threshold k+1)
-    long opt_chunk_min_planes = 1024;        // ... but never fewer planes per chunk than this (launch latency of ~45 small
-                                             // kernels and 3 host round trips per chunk)
-    long tb_planes = 0, tb_runs = 0, tb_comps = 0, tb_seams = 0, tb_segs = 0, tb_pairs = 0;   // tables built so far
-    std::vector<cudaEvent_t> ev_chunk;
-    long opt_host_sparse = 1;                // host-buffer call: flag travels back as row-runs, not as a dense cube
-    long opt_host_zero_threads = 0;          // threads of the zeroing pass only (0: host_threads / automatic)
-    long opt_host_out_zeroed = 0;            // the caller guarantees that flag_host is all zero (fresh calloc / np.zeros pages)
-    long opt_host_threads = 0;               // host threads that zero / paint the host flag cube (0 = automatic)
-    DevBuf lc_st, lc_t, lc_label, lc_npix, lc_roll, lc_out, lc_bitmaps;    // run_lifecycle scratch
-    PinBuf hp_lc;
-    long lc_rows = 0;
-    PinBuf hp_runs;                          // row-run table of the last host-buffer call
-    DevBuf l_parent, l_flag, l_rank, l_label, l_kept, l_accE, l_accS, l_accN;
-    DevBuf b_t0, b_t1, b_y0, b_y1, b_x0, b_x1, b_cnt, b_fill, b_ptr, b_order, b_fin, b_mc, b_ml;
-    PinBuf hp_labels;     // flag cube whose zero fill is in flight on the side stream
-    cudaStream_t side_stream = nullptr;      // zero fill (lowest priority)
-    cudaStream_t tbl_stream = nullptr;       // table phase (highest priority): must get onto the SMs between fill blocks
-    cudaEvent_t ev_tbl[2] = {nullptr, nullptr};
-    cudaEvent_t ev_side[2] = {nullptr, nullptr};
-    long opt_overlap_zero = 1;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t copy_stream = nullptr, work_stream = nullptr;
-    std::map<std::string, double> stats;
-    std::vector<double> w_host, thr_cached;
-    long nspecial_cached = 0;
-    long launches = 0;
-    // time-sharded run: packed tables of all ranks -> global tables (ct_global_merge), plane runs served by the caller
-    DevBuf sh_desc, b_sla, b_slb, x_q, x_idx, ovf_rows;
-    PinBuf hp_desc;
-    ct_plane_runs_fn fetch_fn = nullptr;
-    void* fetch_user = nullptr;
-    // ct_shard_begin: thresholding of the own planes is deferred to ct_shard_tables_dev (pipelined with the table kernels)
-    long opt_fill_split = 100;                // per cent of the planes in the first of the two zero-fill launches
-    long opt_shard_fill_defer_ms = 2;         // ... and not before the export when the fill is shorter than this (ms)
-    int fill_pending = 0;
-    long opt_shard_fill_late = 1;             // sharded run: zero fill starts after the local tables (1) / after the threshold (0)
-    long opt_fused_runs = 1;                  // row-runs come out of the threshold kernel (0: re-extracted from the bit rows)
-    long opt_label_fast = 1;                  // steps 4c/4d at label granularity on the host (fallback: per component)
-    long opt_profile_tables = 0;              // debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"
-    std::vector<std::pair<std::string, cudaEvent_t>> prof;
-    size_t prof_used = 0;
-    const void* sh_anom = nullptr;
-    int sh_dtype = 0, sh_thr_is_f32 = 0, sh_op = 0, sh_deferred = 0;
-    long sh_thr_n = 0;
-    long sh_nchunk = 0, sh_cp = 0;            // chunking chosen by ct_shard_launch_threshold
-    int sh_side = 0;
-    int32_t* sh_flag = nullptr;
-    cudaEvent_t ev_halo = nullptr;           // halo plane imported (ct_shard_import_halo may run on another stream)
-    int halo_event_set = 0;
-};
+}  // namespace cti
 
 namespace {
 
@@ -302,9 +157,6 @@ uint32_t next_pow2(uint64_t v) {
     return (uint32_t)p;
 }
 
-double now_ms() {
-    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
 
 int check_args(long T, int H, int W, const double* w_host, const double* thr_host, long thr_n, int in_dtype, int op) {
     if (T < 0 || H <= 0 || W <= 0) return fail(CT_ERR_ARG, "bad shape T=%ld H=%d W=%d", T, H, W);
@@ -972,6 +824,61 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
     return CT_OK;
 }
 
+
+// Tables of the planes [0, T) of the context's scratch and the ordered phase on them.  `wait_chunk(k)` makes `ts` wait for
+// the thresholding of time chunk k (chunks of `cp` planes).  Fast path: plane kernel per chunk + cooperative global kernel
+// (ct_fast.cu); the global-memory table kernels and the host replays of table_phase() are the fallbacks.
+template <typename WaitFn>
+int solve_tables(ct_ctx* c, long T, long nchunk, long cp, WaitFn wait_chunk, double overlap, int persistence, int twosided,
+                 int stage, long* n_features, cudaStream_t ts) {
+    int rc = CT_OK;
+    c->fast_tables = 0;
+    const bool fast_ok = c->opt_plane_kernel && c->opt_fused_runs && c->opt_gpu_tables;
+    bool waited = false;
+    if (fast_ok) {
+        for (int attempt = 0; attempt < 4; ++attempt) {
+            if ((rc = ctf::begin(c, T, ts)) != CT_OK) return rc;
+            for (long k = 0; k < nchunk; ++k) {
+                const long t0 = k * cp, nt = std::min(cp, T - t0);
+                if (!waited && (rc = wait_chunk(k)) != CT_OK) return rc;
+                if ((rc = ctf::chunk(c, t0, t0 + nt, ts)) != CT_OK) return rc;
+            }
+            waited = true;
+            if ((rc = ctf::finish(c, ts)) != CT_OK) return rc;
+            int outcome = ctf::FAST_SLOW;
+            if (stage == CT_STAGE_FINAL) {
+                if ((rc = ctf::global(c, T, overlap, persistence, twosided, n_features, ts, &outcome)) != CT_OK) return rc;
+            } else {
+                if ((rc = ctf::totals_to_host(c, ts, &outcome)) != CT_OK) return rc;
+            }
+            c->stats["plane_attempts"] = (double)(attempt + 1);
+            if (outcome == ctf::FAST_OK) { c->fast_tables = 1; c->stats["fast_path"] = 1.0; return CT_OK; }
+            if (outcome == ctf::FAST_SLOW) {
+                // valid tables, but the decision needs an ordered host replay (debug stage, near-tie on non-exact rows, a
+                // label that straddles a stale box)
+                CT_CUDA(c->run_val.ensure((size_t)(c->nruns + 1) * 4));
+                c->nseam = 0;
+                c->stats["fast_path"] = 0.5;
+                return table_phase(c, overlap, persistence, twosided, stage, n_features, ts, true);
+            }
+            if (outcome == ctf::FAST_RETRY) continue;
+            if (outcome == ctf::FAST_FALLBACK && ctf::next_budget(c)) continue;
+            break;
+        }
+    }
+    // ---- global-memory table kernels ----
+    c->stats["fast_path"] = 0.0;
+    tables_begin(c);
+    for (long k = 0; k < nchunk && rc == CT_OK; ++k) {
+        const long t0 = k * cp, nt = std::min(cp, T - t0);
+        if (!waited && (rc = wait_chunk(k)) != CT_OK) return rc;
+        rc = tables_chunk(c, t0, t0 + nt, ts);
+    }
+    if (rc == CT_OK) rc = tables_finish(c, ts);
+    if (rc == CT_OK) rc = table_phase(c, overlap, persistence, twosided, stage, n_features, ts, true);
+    return rc;
+}
+
 // side streams: zero fill at the lowest priority, table phase at the highest
 int ensure_streams(ct_ctx* c) {
     int lo = 0, hi = 0;
@@ -993,6 +900,15 @@ int launch_paint(ct_ctx* c, long t0, long nt, int32_t* flag_dev, int sparse, cud
     a.nrows = nt * c->H; a.W = c->W; a.Ww = c->Ww; a.flag = flag_dev;
     a.sparse = sparse ? (c->opt_paint_runs ? 2 : 1) : 0;
     a.run_x = c->run_x.as<uint32_t>(); a.run_row = c->run_row.as<uint32_t>(); a.row0 = r0;
+    if (c->fast_tables && a.sparse == 2) { a.run_comp = c->run_comp.as<uint32_t>(); a.comp_val = c->c_val.as<int32_t>(); }
+    else if (c->fast_tables == 1) {
+        // the row-wise / dense paints go by a value per run: materialise it once
+        CT_CUDA(c->run_val.ensure((size_t)(c->nruns + 1) * 4));
+        a.run_val = c->run_val.as<int32_t>();
+        CT_CUDA(ctk::run_values(c->run_comp.as<uint32_t>(), c->c_val.as<int32_t>(), c->run_val.as<int32_t>(), c->nruns, st));
+        c->launches += 1;
+        c->fast_tables = 2;                                           // (run_val is valid from here on)
+    }
     CT_CUDA(ctk::paint(a, c->sm_count, st));
     c->launches += 1;
     return CT_OK;
@@ -1005,7 +921,7 @@ extern "C" {
 
 int ct_version(void) { return 100; }
 
-const char* ct_last_error(void) { return g_err.c_str(); }
+const char* ct_last_error(void) { return cti::last_error().c_str(); }
 
 int ct_create(int device, ct_ctx** out) {
     if (!out) return fail(CT_ERR_ARG, "null out pointer");
@@ -1078,6 +994,9 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "fused_runs")) { c->opt_fused_runs = value; return CT_OK; }
     if (!strcmp(key, "label_fast")) { c->opt_label_fast = value; return CT_OK; }
     if (!strcmp(key, "profile_tables")) { c->opt_profile_tables = value; return CT_OK; }
+    if (!strcmp(key, "plane_kernel")) { c->opt_plane_kernel = value; return CT_OK; }
+    if (!strcmp(key, "max_sweeps")) { c->opt_max_sweeps = value < 1 ? 1 : value; return CT_OK; }
+    if (!strcmp(key, "plane_smem")) { c->opt_plane_smem = value; c->pl_budget = 0; return CT_OK; }
     return fail(CT_ERR_ARG, "unknown option '%s'", key);
 }
 
@@ -1142,23 +1061,19 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
         CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
     }
     const double t_h0 = now_ms();
-    tables_begin(c);
-    for (long k = 0; k < nchunk && rc == CT_OK; ++k) {
-        const long t0 = k * cp, nt = std::min(cp, T - t0);
+    auto wait_chunk = [&](long k) -> int {
         if (sparse) CT_CUDA(cudaStreamWaitEvent(ts, c->ev_chunk[k], 0));
-        rc = tables_chunk(c, t0, t0 + nt, ts);
-    }
-    if (rc == CT_OK) rc = tables_finish(c, ts);
+        return CT_OK;
+    };
+    rc = solve_tables(c, T, nchunk, cp, wait_chunk, overlap, persistence, twosided, stage, n_features, ts);
     const double t_h1 = now_ms();
-    if (rc == CT_OK) rc = table_phase(c, overlap, persistence, twosided, stage, n_features, ts, true);
     if (rc != CT_OK) {
         if (sparse) { cudaStreamSynchronize(c->side_stream); cudaStreamSynchronize(c->tbl_stream); }
         cudaStreamSynchronize(st);
         return rc;
     }
     c->stats["chunks"] = (double)nchunk;
-    c->stats["ms_h_chunks"] = t_h1 - t_h0;                           // host wall clock: chunk tables (ends in a sync)
-    c->stats["ms_h_global"] = now_ms() - t_h1;                       // ... global part (last uploads still in flight)
+    c->stats["ms_h_tables"] = t_h1 - t_h0;                           // host wall clock of the table phase (ends in a sync)
     if (sparse) {
         CT_CUDA(cudaEventRecord(c->ev_tbl[0], ts));
         CT_CUDA(cudaStreamWaitEvent(st, c->ev_tbl[0], 0));
@@ -1263,7 +1178,14 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
     }
     CT_CUDA(cudaStreamSynchronize(ws));
     const double t1_ms = now_ms();
-    if ((rc = table_phase(c, overlap, persistence, twosided, CT_STAGE_FINAL, n_features, ws)) != CT_OK) return rc;
+    auto no_wait = [](long) -> int { return CT_OK; };
+    if ((rc = solve_tables(c, T, 1, T, no_wait, overlap, persistence, twosided, CT_STAGE_FINAL, n_features, ws)) != CT_OK) return rc;
+    if (c->fast_tables) {                                             // the sparse export ships a value per run
+        CT_CUDA(c->run_val.ensure((size_t)(c->nruns + 1) * 4));
+        CT_CUDA(ctk::run_values(c->run_comp.as<uint32_t>(), c->c_val.as<int32_t>(), c->run_val.as<int32_t>(), c->nruns, ws));
+        c->launches += 1;
+        c->fast_tables = 2;
+    }
     CT_CUDA(cudaStreamSynchronize(ws));
     const double t2_ms = now_ms();
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(in_ready[i]); cudaEventDestroy(in_free[i]); }

@@ -296,6 +296,34 @@ int track_phase(const FastTables& tb, const int32_t* label, int persistence, Run
             // test hook: the label-granular pass of the product path; returns 1 when a label straddles a stale box
             std::vector<int32_t> sla(tb.nseg), slb(tb.nseg), lab_fin;
             for (long s = 0; s < tb.nseg; ++s) { sla[s] = label[seg_a32[s]]; slb[s] = label[seg_b32[s]]; }
+            if (getenv("CT_TRACK_EVENTS")) {
+                // test hook: what the cooperative global kernel + track_events_fast do in the product path -- persistence of
+                // every label from its own box, the event list (segments whose ends carry different labels, with both
+                // boxes), the replay on the events alone, patches on top
+                std::vector<int32_t> ev;
+                for (long s = 0; s < tb.nseg; ++s) {
+                    const int la = sla[s], lb = slb[s];
+                    if (la == 0 || lb == 0 || la == lb) continue;
+                    const int32_t r[14] = {la, lb, t0[la], t1[la], y0[la], y1[la], x0[la], x1[la],
+                                           t0[lb], t1[lb], y0[lb], y1[lb], x0[lb], x1[lb]};
+                    ev.insert(ev.end(), r, r + 14);
+                }
+                std::vector<int32_t> pl, pv;
+                long delta = 0, feats = 0;
+                if (ctb::track_events_fast(persistence, (long)ev.size() / 14, ev.data(), pl, pv, &delta, stats) == 0) {
+                    lab_fin.assign(nlabel + 1, 0);
+                    for (int v = 1; v <= nlabel; ++v) {
+                        const bool keep = t1[v] > t0[v] && (t1[v] - t0[v]) >= persistence;
+                        lab_fin[v] = keep ? v : 0; feats += keep;
+                    }
+                    for (size_t i = 0; i < pl.size(); ++i) lab_fin[pl[i]] = pv[i];
+                    for (long c = 0; c < nc; ++c) comp_val[c] = lab_fin[label[c]];
+                    out.overrides.clear();
+                    out.n_features = feats + delta; out.n_seam_events = stats.n_events; out.n_seam_splits = 0;
+                    out.n_neartie += 1000000;
+                    return 0;
+                }
+            } else
             if (ctb::track_labels_fast(persistence, lt, tb.nseg, sla.data(), slb.data(), lab_fin, stats) == 0) {
                 for (long c = 0; c < nc; ++c) comp_val[c] = lab_fin[label[c]];
                 out.overrides.clear();

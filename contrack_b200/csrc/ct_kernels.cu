@@ -1054,10 +1054,13 @@ __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits
 // Sparse paint by runs (the cube is already zero): a warp takes 32 consecutive runs -- their (x0, x1), row and value come
 // in with coalesced loads -- and writes them one after the other, 32 cells per store instruction.  No bit rows, no
 // dependent gathers.  Runs of removed components (value 0) are skipped.
+// by_comp: the value of a run is comp_val[run_comp[r]] (no per-run value table is materialised).
 __global__ void __launch_bounds__(256) k_paint_runs(const uint32_t* __restrict__ row_ptr, long r0, long nrows,
                                                     const uint32_t* __restrict__ run_x,
                                                     const uint32_t* __restrict__ run_row,
-                                                    const int32_t* __restrict__ run_val, int W,
+                                                    const int32_t* __restrict__ run_val,
+                                                    const uint32_t* __restrict__ run_comp,
+                                                    const int32_t* __restrict__ comp_val, int W,
                                                     int32_t* __restrict__ flag) {
     const int lane = threadIdx.x & 31;
     const long run_begin = row_ptr[r0], run_end = row_ptr[r0 + nrows];
@@ -1069,7 +1072,7 @@ __global__ void __launch_bounds__(256) k_paint_runs(const uint32_t* __restrict__
         long dst = 0;
         if (r < run_end) {
             const uint32_t x = run_x[r];
-            x0 = x & 0xffff; x1 = x >> 16; v = run_val[r];
+            x0 = x & 0xffff; x1 = x >> 16; v = run_comp ? comp_val[run_comp[r]] : run_val[r];
             dst = ((long)run_row[r] - r0) * (long)W;
         }
         uint32_t todo = __ballot_sync(FULL, v != 0);
@@ -1259,8 +1262,8 @@ cudaError_t paint(const PaintArgs& a, int sm_count, cudaStream_t st) {
     int blocks = (int)(want < (long)sm_count * 8 ? want : (long)sm_count * 8);
     const bool vec = (a.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.flag) & 15) == 0);
     if (a.sparse == 2) {
-        k_paint_runs<<<sm_count * 8, 256, 0, st>>>(a.row_ptr - a.row0, a.row0, a.nrows, a.run_x, a.run_row, a.run_val, a.W,
-                                                   a.flag);
+        k_paint_runs<<<sm_count * 8, 256, 0, st>>>(a.row_ptr - a.row0, a.row0, a.nrows, a.run_x, a.run_row, a.run_val,
+                                                   a.run_comp, a.comp_val, a.W, a.flag);
     } else if (a.sparse) {
         if (vec) k_paint<true, true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
         else k_paint<false, true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);

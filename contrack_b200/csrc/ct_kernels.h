@@ -147,6 +147,8 @@ struct PaintArgs {
     int32_t* flag;                           // [nrows * W] out
     int sparse;                              // 0: dense; `flag` already zero: 1 = row-wise, cells of runs only; 2 = by runs
     const uint32_t* run_x; const uint32_t* run_row;   // sparse == 2
+    const uint32_t* run_comp = nullptr;      // sparse == 2, optional: value of run r = comp_val[run_comp[r]] instead of run_val[r]
+    const int32_t* comp_val = nullptr;
     long row0;                               // first row painted (row_ptr points at it)
 };
 cudaError_t paint(const PaintArgs& a, int sm_count, cudaStream_t st);

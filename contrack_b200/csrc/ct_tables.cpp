@@ -535,6 +535,91 @@ int track_labels_fast(int persistence, const LabelTables& lt, long nseg, const i
     return 0;
 }
 
+int track_events_fast(int persistence, long nev, const int32_t* ev, std::vector<int32_t>& patch_label,
+                      std::vector<int32_t>& patch_value, long* feat_delta, TrackStats& stats) {
+    stats = TrackStats();
+    patch_label.clear(); patch_value.clear();
+    *feat_delta = 0;
+    if (nev == 0) return 0;
+    // labels that occur in events -> dense local indices (sorted by label: min / max of values = min / max of indices)
+    struct Workspace {
+        std::vector<int32_t> labs; std::vector<Box3> box;
+        std::vector<int> value, head, nxt, touched; std::vector<uint8_t> built, settled;
+    };
+    static thread_local Workspace tls_ws;
+    Workspace& ws = tls_ws;
+    std::vector<int32_t>& labs = ws.labs;
+    labs.resize((size_t)2 * nev);
+    for (long e = 0; e < nev; ++e) { labs[2 * e] = ev[14 * e]; labs[2 * e + 1] = ev[14 * e + 1]; }
+    std::sort(labs.begin(), labs.end());
+    labs.erase(std::unique(labs.begin(), labs.end()), labs.end());
+    const int m = (int)labs.size();
+    auto local = [&](int32_t L) { return (int)(std::lower_bound(labs.begin(), labs.end(), L) - labs.begin()); };
+    std::vector<Box3>& box = ws.box;
+    box.resize(m);
+    for (long e = 0; e < nev; ++e) {
+        const int32_t* r = ev + 14 * e;
+        box[local(r[0])] = Box3{r[2], r[3], r[4], r[5], r[6], r[7]};
+        box[local(r[1])] = Box3{r[8], r[9], r[10], r[11], r[12], r[13]};
+    }
+    std::vector<int>&value = ws.value, &head = ws.head, &nxt = ws.nxt, &touched = ws.touched;
+    std::vector<uint8_t>&built = ws.built, &settled = ws.settled;
+    value.resize(m); head.resize(m); nxt.resize(m);
+    built.assign(m, 0); settled.assign(m, 0);
+    touched.clear();
+    auto val_of = [&](int L) { return built[L] ? value[L] : L; };
+    auto ensure_built = [&](int v) {                      // class v starts with label v alone
+        if (built[v]) return;
+        built[v] = 1; value[v] = v; head[v] = v; nxt[v] = -1;
+        touched.push_back(v);
+    };
+    for (long e = 0; e < nev; ++e) {
+        const int la = local(ev[14 * e]), lb = local(ev[14 * e + 1]);
+        const int va = val_of(la), vb = val_of(lb);
+        if (va == vb) continue;
+        stats.n_events++;
+        const int hi = std::max(va, vb), lo = std::min(va, vb);
+        ensure_built(hi); ensure_built(lo);
+        if (settled[hi]) continue;
+        const Box3 b = box[hi];
+        int L = head[hi], prev = -1;
+        bool moved = false;
+        while (L >= 0) {
+            const int next = nxt[L];
+            stats.n_walked++;
+            const Box3& q = box[L];
+            const bool inside = q.t0 >= b.t0 && q.t1 <= b.t1 && q.y0 >= b.y0 && q.y1 <= b.y1 && q.x0 >= b.x0 && q.x1 <= b.x1;
+            const bool outside = q.t1 <= b.t0 || q.t0 >= b.t1 || q.y1 <= b.y0 || q.y0 >= b.y1 || q.x1 <= b.x0 || q.x0 >= b.x1;
+            if (inside) {
+                if (prev < 0) head[hi] = next; else nxt[prev] = next;
+                nxt[L] = head[lo]; head[lo] = L; value[L] = lo;
+                moved = true;
+            } else if (outside) {
+                prev = L;
+            } else {
+                return 1;                                 // members of L may be on both sides of the box
+            }
+            L = next;
+        }
+        settled[hi] = 1;
+        if (moved) settled[lo] = 0;
+    }
+    // persistence (contrack.py:765-772) of the touched values from their current members; the device counted every label
+    // as a feature of its own box
+    for (int v : touched) {
+        const Box3& o = box[v];
+        if (o.t1 > o.t0 && (o.t1 - o.t0) >= persistence) --*feat_delta;
+    }
+    for (int v : touched) {
+        int lo = INT_MAX, hi = 0;
+        for (int L = head[v]; L >= 0; L = nxt[L]) { lo = std::min(lo, box[L].t0); hi = std::max(hi, box[L].t1); }
+        const bool keep = hi > lo && (hi - lo) >= persistence;
+        *feat_delta += keep;
+        for (int L = head[v]; L >= 0; L = nxt[L]) { patch_label.push_back(labs[L]); patch_value.push_back(keep ? labs[v] : 0); }
+    }
+    return 0;
+}
+
 // ---- numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src: @TYPE@_pairwise_sum, PW_BLOCKSIZE 128) ----
 static double pairwise(const double* a, long n) {
     if (n < 8) {

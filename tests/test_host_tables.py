@@ -134,11 +134,15 @@ def test_sparse_track_variant(monkeypatch, fixture_cube, golden):
         assert sha_i4(f) == r['sha256']
 
 
-def test_label_granular_track_variant(monkeypatch, fixture_cube, golden, reference_run):
-    """track_labels_fast (the product path's date-line merge + persistence at label granularity) through the all-host
-    entry point: same results as the reference, and the per-component replay takes over when a label straddles a box."""
+@pytest.mark.parametrize('events', [False, True])
+def test_label_granular_track_variant(monkeypatch, fixture_cube, golden, reference_run, events):
+    """track_labels_fast / track_events_fast (the product path's date-line merge + persistence at label granularity; the
+    second one works from the device's event list alone) through the all-host entry point: same results as the reference,
+    and the per-component replay takes over when a label straddles a box."""
     monkeypatch.setenv('CT_TRACK_SPARSE', '1')
     monkeypatch.setenv('CT_TRACK_LABELS', '1')
+    if events:
+        monkeypatch.setenv('CT_TRACK_EVENTS', '1')
     lat, lon = regular_grid(24, 16)
     w = row_weights(lat, lon)
     fast, slow = 0, 0

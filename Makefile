@@ -24,7 +24,7 @@ $(OUT)/%.o: $(SRC)/%.cpp $(wildcard $(SRC)/*.h)
 	@mkdir -p $(OUT)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(OUT)/ct_kernels.o $(OUT)/ct_plane.o $(OUT)/ct_global.o $(OUT)/ct_fast.o $(OUT)/ct_lifecycle.o $(OUT)/ct_shard.o $(OUT)/ct_extras.o $(OUT)/ct_anom.o $(OUT)/ct_api.o $(OUT)/ct_host.o $(OUT)/ct_tables.o
+$(LIB): $(OUT)/ct_kernels.o $(OUT)/ct_plane.o $(OUT)/ct_global.o $(OUT)/ct_fast.o $(OUT)/ct_comm.o $(OUT)/ct_dist.o $(OUT)/ct_lifecycle.o $(OUT)/ct_shard.o $(OUT)/ct_extras.o $(OUT)/ct_anom.o $(OUT)/ct_api.o $(OUT)/ct_host.o $(OUT)/ct_tables.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart_static -lpthread -ldl -lrt
 
 clean:

@@ -388,14 +388,17 @@ def main():
                     'radix select)' % T)
 
     shard_info = []
+    # the library's own NCCL communicator over the ranks of this job (unique id distributed through torch.distributed);
+    # created before the timed region
+    comm = sharded.default_comm(eng) if world > 1 else None
 
     def run_shard(x, t0, T_total, out=None):
         """one run_contrack pass over this rank's planes [t0, t0 + len(x)) of a T_total-step cube -> (flag, features)"""
         if world == 1:
             return eng.run_contrack(x, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE, TWOSIDED, out=out)
-        f, n, info = sharded.run_contrack_sharded(eng, x, t0, T_total, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE,
-                                                  TWOSIDED, out=out)
-        shard_info.append(info)
+        f, n, st = sharded.run_contrack_sharded(eng, x, t0, T_total, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE,
+                                                TWOSIDED, out=out, comm=comm)
+        shard_info.append(st)
         return f, n
 
     ms_stage = {'calc_clim': [], 'calc_anom': []}
@@ -500,14 +503,15 @@ def main():
         line['config']['threshold_note'] = thr_note
     if world > 1 and shard_info:
         last = shard_info[-args.steps:]
-        line['shard_ms'] = {k: float(np.mean([i['phase_ms'][k] for i in last])) for k in last[0]['phase_ms']}
-        line['shard_ms']['note'] = ('rank 0 host wall clock per phase of the sharded step (phases end where the host has to '
-                                    'wait)')
-        line['shard_table_bytes'] = last[-1]['table_bytes']
+        keys = ('ms_threshold', 'ms_zero_fill', 'ms_tables_after_threshold', 'ms_paint', 'ms_total', 'ms_g_kernel', 'ms_host_tables')
+        mine = {k: round(float(np.mean([i.get(k, 0.0) for i in last])), 3) for k in keys}
+        mine.update({k: last[-1].get(k) for k in ('exchange_bytes', 'shard_attempts', 'fast_path', 'sweeps', 'kernel_launches')})
         every = [None] * world
-        dist.all_gather_object(every, {k: round(v, 3) for k, v in line['shard_ms'].items() if k != 'note'})
+        dist.all_gather_object(every, mine)
         line['shard_ms_all_ranks'] = every
-
+        line['shard_ms_note'] = ('per rank, CUDA events of the sharded call: threshold (own planes), zero fill (beside the table '
+                                 'phase), tables_after_threshold = plane kernel + table all-gather + merge + global kernel + '
+                                 'host replay, paint; ms_total = the whole call on the device')
     # ---- parity: checksum of the timed run's flag cube (identical at every N) + oracle on a cube cut at every rank ----
     if not args.no_parity:
         cs = flag_checksum(flag, t_lo * H * W)
@@ -611,7 +615,7 @@ def main():
             def e2e_step():
                 dev_in.copy_(xin, non_blocking=True)
                 _, n, _ = sharded.run_contrack_sharded(eng, dev_in, e_lo, Te, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE,
-                                                       TWOSIDED, out=dev_out)
+                                                       TWOSIDED, out=dev_out, comm=comm)
                 fout.copy_(dev_out, non_blocking=True)
                 torch.cuda.synchronize()
                 return n

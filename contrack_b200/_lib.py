@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libcontrack_b200.so')
 
-CT_OK, CT_ERR_ARG, CT_ERR_CUDA, CT_ERR_CAPACITY, CT_ERR_NEARTIE, CT_ERR_INTERNAL = 0, -1, -2, -3, -4, -5
+CT_OK, CT_ERR_ARG, CT_ERR_CUDA, CT_ERR_CAPACITY, CT_ERR_NEARTIE, CT_ERR_INTERNAL, CT_ERR_COMM = 0, -1, -2, -3, -4, -5, -6
 CT_F32, CT_F64 = 0, 1
 CT_GE, CT_LE, CT_GT, CT_LT = 0, 1, 2, 3
 STAGE_FINAL, STAGE_LABEL2D, STAGE_SEAM2D, STAGE_FILTERED, STAGE_LABEL3D = 0, 1, 2, 3, 4
@@ -54,23 +54,15 @@ _PROTOS = {
                             + [_i32p] * 5 + [_u32p] + [_f64p] * 4 + [_u32p] * 5 + [_f64p] * 2
                             + [C.c_long] + [_i32p] * 3 + [_u32p] * 2 + [_p, _p]
                             + [_i32p, C.c_long] + [_i32p] * 5 + [_longp, _longp]),
-    'ct_shard_threshold': (C.c_int, [_p, _p, C.c_int, C.c_long, C.c_int, C.c_int, _f64p, _f64p, C.c_long, C.c_int,
-                                     C.c_int, C.c_int, _p]),
-    'ct_shard_boundary_words': (C.c_long, [_p]),
-    'ct_shard_export_boundary': (C.c_int, [_p, _u32p, _p]),
-    'ct_shard_import_halo': (C.c_int, [_p, _u32p, _p]),
-    'ct_shard_tables': (C.c_int, [_p, _i32p, _p, _p]),
-    'ct_shard_plane_runs': (C.c_int, [_p, C.c_long, _longp, C.POINTER(_i32p), C.POINTER(_i32p), C.POINTER(_i32p),
-                                      C.POINTER(_u32p), _p]),
-    'ct_shard_paint': (C.c_int, [_p, _i32p, C.c_long] + [_i32p] * 5 + [_i32p, _p]),
-    'ct_shard_begin': (C.c_int, [_p, _p, C.c_int, C.c_long, C.c_int, C.c_int, _f64p, _f64p, C.c_long, C.c_int,
-                                 C.c_int, C.c_int, _p, _p]),
-    'ct_shard_launch_threshold': (C.c_int, [_p, _p, _p]),
-    'ct_shard_tables_dev': (C.c_int, [_p, _p, _p, _longp, _longp]),
-    'ct_shard_export_tables': (C.c_int, [_p, _p, C.c_long, _p]),
-    'ct_global_merge': (C.c_int, [_p, C.c_int, _longp, _p, C.c_long, C.c_long, C.c_int, C.c_int, _f64p, _p]),
-    'ct_global_phase': (C.c_int, [_p, C.c_double, C.c_int, C.c_int, _p, _p, _longp, _p]),
-    'ct_shard_paint_global': (C.c_int, [_p, _p, C.c_long, C.c_long, _p, _p]),
+    'ct_nccl_unique_id': (C.c_int, [C.POINTER(C.c_ubyte)]),
+    'ct_comm_init_nccl': (C.c_int, [C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
+    'ct_comm_from_nccl': (C.c_int, [_p, C.c_int, C.c_int, C.POINTER(_p)]),
+    'ct_comm_init_local': (C.c_int, [C.c_int, C.POINTER(_p)]),
+    'ct_comm_destroy': (None, [_p]),
+    'ct_comm_rank': (C.c_int, [_p]),
+    'ct_comm_size': (C.c_int, [_p]),
+    'ct_run_contrack_sharded': (C.c_int, [_p, _p, _p, C.c_int, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int, _f64p, _f64p,
+                                          C.c_long, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _p, _longp, _p]),
     'ct_quantile_time': (C.c_int, [_p, _p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _p, _p]),
     'ct_flag_count': (C.c_int, [_p, _p, C.c_long, C.c_int, C.c_int, C.c_int, _p, _p]),
     'ct_divide_f32': (C.c_int, [_p, _p, C.c_size_t, C.c_float, _p, _p]),

@@ -825,17 +825,25 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
 }
 
 
+// Which table builder for T planes: the plane kernel (one launch, no host round trip; per-plane work is latency-bound, so its
+// throughput is ~T / 740 x 0.2 ms) for small T, e.g. the shard of a multi-GPU run; the global-memory table kernels (every
+// step fully parallel over all planes, pipelined under the threshold kernel) for long cubes on one GPU.
+bool use_plane_kernel(const ct_ctx* c, long T) {
+    if (!c->opt_fused_runs || !c->opt_gpu_tables) return false;
+    return c->opt_plane_kernel == 1 || (c->opt_plane_kernel == 2 && T <= c->opt_plane_max_planes);
+}
+
 // Tables of the planes [0, T) of the context's scratch and the ordered phase on them.  `wait_chunk(k)` makes `ts` wait for
-// the thresholding of time chunk k (chunks of `cp` planes).  Fast path: plane kernel per chunk + cooperative global kernel
-// (ct_fast.cu); the global-memory table kernels and the host replays of table_phase() are the fallbacks.
+// the thresholding of time chunk k (chunks of `cp` planes).  Tables: plane kernel (ct_plane.cu) or global-memory table
+// kernels; ordered phase: cooperative global kernel + event replay (ct_global.cu, ct_fast.cu), with the host replays of
+// table_phase() behind it (debug stages, near-ties on non-exact rows, labels that straddle a stale box).
 template <typename WaitFn>
 int solve_tables(ct_ctx* c, long T, long nchunk, long cp, WaitFn wait_chunk, double overlap, int persistence, int twosided,
                  int stage, long* n_features, cudaStream_t ts) {
     int rc = CT_OK;
     c->fast_tables = 0;
-    const bool fast_ok = c->opt_plane_kernel && c->opt_fused_runs && c->opt_gpu_tables;
     bool waited = false;
-    if (fast_ok) {
+    if (use_plane_kernel(c, T)) {
         for (int attempt = 0; attempt < 4; ++attempt) {
             if ((rc = ctf::begin(c, T, ts)) != CT_OK) return rc;
             for (long k = 0; k < nchunk; ++k) {
@@ -847,7 +855,7 @@ int solve_tables(ct_ctx* c, long T, long nchunk, long cp, WaitFn wait_chunk, dou
             if ((rc = ctf::finish(c, ts)) != CT_OK) return rc;
             int outcome = ctf::FAST_SLOW;
             if (stage == CT_STAGE_FINAL) {
-                if ((rc = ctf::global(c, T, overlap, persistence, twosided, n_features, ts, &outcome)) != CT_OK) return rc;
+                if ((rc = ctf::global(c, T, overlap, persistence, twosided, n_features, ts, &outcome, nullptr)) != CT_OK) return rc;
             } else {
                 if ((rc = ctf::totals_to_host(c, ts, &outcome)) != CT_OK) return rc;
             }
@@ -875,8 +883,20 @@ int solve_tables(ct_ctx* c, long T, long nchunk, long cp, WaitFn wait_chunk, dou
         rc = tables_chunk(c, t0, t0 + nt, ts);
     }
     if (rc == CT_OK) rc = tables_finish(c, ts);
-    if (rc == CT_OK) rc = table_phase(c, overlap, persistence, twosided, stage, n_features, ts, true);
-    return rc;
+    if (rc != CT_OK) return rc;
+    if (stage == CT_STAGE_FINAL && c->opt_gpu_tables && c->opt_coop_global) {
+        // the cooperative global kernel on these tables: their counts are known to the host, the control block is written here
+        if ((rc = ctf::ensure_global_scratch(c, (size_t)c->ncomp, (size_t)c->nseg)) != CT_OK) return rc;
+        struct { uint32_t w[4]; unsigned long long tot[4]; } ctl = {{0, 0, 0, 0},
+            {(unsigned long long)c->ncomp, (unsigned long long)c->nseg, (unsigned long long)c->nruns, (unsigned long long)c->npair}};
+        memcpy(c->hp_ctl.p, &ctl, sizeof ctl);
+        CT_CUDA(cudaMemcpyAsync(c->pl_ctl.p, c->hp_ctl.p, sizeof ctl, cudaMemcpyHostToDevice, ts));
+        int outcome = ctf::FAST_SLOW;
+        if ((rc = ctf::global(c, T, overlap, persistence, twosided, n_features, ts, &outcome, nullptr)) != CT_OK) return rc;
+        if (outcome == ctf::FAST_OK) { c->fast_tables = 1; return CT_OK; }
+        if (outcome != ctf::FAST_SLOW) return fail(CT_ERR_INTERNAL, "global phase: unexpected outcome %d", outcome);
+    }
+    return table_phase(c, overlap, persistence, twosided, stage, n_features, ts, true);
 }
 
 // side streams: zero fill at the lowest priority, table phase at the highest
@@ -915,6 +935,37 @@ int launch_paint(ct_ctx* c, long t0, long nt, int32_t* flag_dev, int sparse, cud
 }
 
 }  // namespace
+
+// ---- what the other translation units of the library use (ct_internal.h) ----
+namespace cti {
+int api_check_args(long T, int H, int W, const double* w_host, const double* thr_host, long thr_n, int in_dtype, int op) {
+    return check_args(T, H, W, w_host, thr_host, thr_n, in_dtype, op);
+}
+int api_prepare(ct_ctx* c, long T, int H, int W, const double* w_host, const double* thr_host, long thr_n, cudaStream_t st) {
+    return prepare(c, T, H, W, w_host, thr_host, thr_n, st);
+}
+int api_launch_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long t0, long nt, long thr_n, int thr_is_f32, int op,
+                         cudaStream_t st, int all_bits) {
+    return launch_threshold(c, anom_dev, in_dtype, t0, nt, thr_n, thr_is_f32, op, st, all_bits);
+}
+int api_launch_paint(ct_ctx* c, long t0, long nt, int32_t* flag_dev, int sparse, cudaStream_t st) {
+    return launch_paint(c, t0, nt, flag_dev, sparse, st);
+}
+int api_ensure_streams(ct_ctx* c) { return ensure_streams(c); }
+int api_table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int stage, long* n_features, cudaStream_t st) {
+    return table_phase(c, overlap, persistence, twosided, stage, n_features, st, true);
+}
+int api_classic_tables(ct_ctx* c, cudaStream_t st) {                // planes [0, c->T) with the global-memory table kernels
+    tables_begin(c);
+    int rc = c->T > 0 ? tables_chunk(c, 0, c->T, st) : CT_OK;
+    return rc != CT_OK ? rc : tables_finish(c, st);
+}
+bool api_plane_runs(ct_ctx* c, long plane, std::vector<cth::PlaneRun>& out, cudaStream_t st) {
+    DeviceRunSource src;
+    src.c = c; src.st = st;
+    return src.plane_runs(plane, out);
+}
+}  // namespace cti
 
 // ---------------------------------------------------------------------------------------------------------------------
 extern "C" {
@@ -960,9 +1011,14 @@ void ct_destroy(ct_ctx* c) {
                       &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN,
                       &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
                       &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml,
-                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots, &c->x_q, &c->x_idx, &c->ovf_rows};
+                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots, &c->x_q, &c->x_idx, &c->ovf_rows,
+                      &c->pl_chain, &c->pl_done, &c->pl_ctl, &c->g_dirty, &c->g_blocksum, &c->g_evflag, &c->g_ev, &c->g_lrec, &c->g_patch,
+                      &c->sh_export, &c->sh_gathered, &c->sh_mdesc};
     for (DevBuf* b : bufs) b->release();
     c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release(); c->hp_desc.release();
+    c->hp_ctl.release(); c->hp_ev.release(); c->hp_ev2.release(); c->hp_patch.release(); c->hp_hdr.release();
+    for (auto& e : c->ev_x) if (e) cudaEventDestroy(e);
+    if (c->gctx) ct_destroy(c->gctx);
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     for (auto& e : c->ev_tbl) if (e) cudaEventDestroy(e);
@@ -995,6 +1051,9 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "label_fast")) { c->opt_label_fast = value; return CT_OK; }
     if (!strcmp(key, "profile_tables")) { c->opt_profile_tables = value; return CT_OK; }
     if (!strcmp(key, "plane_kernel")) { c->opt_plane_kernel = value; return CT_OK; }
+    if (!strcmp(key, "plane_max_planes")) { c->opt_plane_max_planes = value; return CT_OK; }
+    if (!strcmp(key, "coop_global")) { c->opt_coop_global = value; return CT_OK; }
+    if (!strcmp(key, "fast_chunks")) { c->opt_fast_chunks = value < 1 ? 1 : value; return CT_OK; }
     if (!strcmp(key, "max_sweeps")) { c->opt_max_sweeps = value < 1 ? 1 : value; return CT_OK; }
     if (!strcmp(key, "plane_smem")) { c->opt_plane_smem = value; c->pl_budget = 0; return CT_OK; }
     return fail(CT_ERR_ARG, "unknown option '%s'", key);
@@ -1021,7 +1080,12 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     // of the table phase (overlap filter, 3-D labels, date-line merge, persistence); afterwards only the cells of
     // row-runs are painted.
     const int sparse = c->opt_overlap_zero ? 1 : 0;
-    long nchunk = sparse ? std::min<long>(c->opt_chunks, std::max<long>(1, T / c->opt_chunk_min_planes)) : 1;
+    // fast path: ONE threshold launch (it runs alone, at full speed); the plane kernel and the global kernel then run beside
+    // the zero fill, which is bound by HBM writes and leaves the issue slots to them ("fast_chunks" > 1 pipelines the plane
+    // kernel under the threshold kernel instead)
+    const bool fast = use_plane_kernel(c, T);
+    const long want_chunks = fast ? c->opt_fast_chunks : c->opt_chunks;
+    long nchunk = sparse ? std::min<long>(want_chunks, std::max<long>(1, T / c->opt_chunk_min_planes)) : 1;
     const long cp = (T + nchunk - 1) / nchunk;
     nchunk = (T + cp - 1) / cp;
     cudaStream_t ts = st;
@@ -1425,494 +1489,6 @@ int ct_host_tables_fast(long T, int H, int W, const double* w_host, double overl
         stats8[0] = res.n_features; stats8[1] = res.n_kept; stats8[2] = res.n_labels3d; stats8[3] = res.n_seam_events;
         stats8[4] = res.n_seam_splits; stats8[5] = res.n_neartie; stats8[6] = 0; stats8[7] = 0;
     }
-    return CT_OK;
-}
-
-// ---- time-sharded run ----------------------------------------------------------------------------------------------
-int ct_shard_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long T_local, int H, int W, const double* w_host,
-                       const double* thr_host, long thr_n, int thr_is_f32, int op, int has_prev, void* stream) {
-    if (!c) return fail(CT_ERR_ARG, "null context");
-    int rc = check_args(T_local, H, W, w_host, thr_host, thr_n, in_dtype, op);
-    if (rc != CT_OK) return rc;
-    if (T_local <= 0 || !anom_dev) return fail(CT_ERR_ARG, "a rank needs at least one plane");
-    has_prev = has_prev ? 1 : 0;
-    CT_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    c->stats.clear();
-    // thresholds are indexed by scratch plane: the halo plane gets a dummy entry
-    std::vector<double> thr(thr_host, thr_host + thr_n);
-    if (thr_n != 1 && has_prev) thr.insert(thr.begin(), 0.0);
-    if ((rc = prepare(c, T_local + has_prev, H, W, w_host, thr.data(), (long)thr.size(), st)) != CT_OK) return rc;
-    c->has_prev = has_prev;
-    CT_CUDA(cudaEventRecord(c->ev[0], st));
-    if ((rc = launch_threshold(c, anom_dev, in_dtype, has_prev, T_local, (long)thr.size(), thr_is_f32, op, st)) != CT_OK)
-        return rc;
-    CT_CUDA(cudaEventRecord(c->ev[1], st));
-    return CT_OK;
-}
-
-long ct_shard_boundary_words(ct_ctx* c) { return c ? (long)c->H * c->Ww : 0; }
-
-int ct_shard_export_boundary(ct_ctx* c, uint32_t* dst_dev, void* stream) {
-    if (!c || !dst_dev || c->T <= 0) return fail(CT_ERR_ARG, "null argument / no thresholded planes");
-    const size_t words = (size_t)c->H * c->Ww;
-    CT_CUDA(cudaMemcpyAsync(dst_dev, c->bits.as<uint32_t>() + (size_t)(c->T - 1) * words, words * 4,
-                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    return CT_OK;
-}
-
-int ct_shard_import_halo(ct_ctx* c, const uint32_t* src_dev, void* stream) {
-    if (!c || !src_dev) return fail(CT_ERR_ARG, "null argument");
-    if (!c->has_prev) return fail(CT_ERR_ARG, "this rank was set up without a previous rank");
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t words = (size_t)c->H * c->Ww;
-    CT_CUDA(cudaMemcpyAsync(c->bits.p, src_dev, words * 4, cudaMemcpyDeviceToDevice, st));
-    CT_CUDA(ctk::row_stats(c->bits.as<uint32_t>(), c->H, c->W, c->Ww, c->row_cnt.as<uint32_t>(),
-                           c->seam_flag.as<uint32_t>(), c->slots.as<uint32_t>(), c->counters.as<uint32_t>() + 16, st));
-    c->launches += 1;
-    if (!c->ev_halo) CT_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
-    CT_CUDA(cudaEventRecord(c->ev_halo, st));
-    c->halo_event_set = 1;
-    return CT_OK;
-}
-
-int ct_shard_tables(ct_ctx* c, int32_t* flag_dev, void* stream, ct_shard_view* v) {
-    if (!c || !v) return fail(CT_ERR_ARG, "null argument");
-    CT_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    c->zero_started_for = nullptr;
-    int rc;
-    cudaStream_t ts = st;
-    if (flag_dev && c->opt_overlap_zero) {
-        if ((rc = ensure_streams(c)) != CT_OK) return rc;
-        CT_CUDA(cudaEventRecord(c->ev_side[0], st));
-        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-        CT_CUDA(cudaStreamWaitEvent(c->tbl_stream, c->ev_side[0], 0));
-        CT_CUDA(ctk::zero_fill(flag_dev, (size_t)(c->T - c->has_prev) * c->H * c->W, c->sm_count, c->side_stream));
-        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
-        c->launches += 1;
-        c->zero_started_for = flag_dev;
-        ts = c->tbl_stream;
-    }
-    rc = tables_gpu(c, ts);                                       // ends with a synchronize of ts
-    if (rc != CT_OK) return rc;
-    const cth::FastTables& tb = c->host_tb;
-    long nh = 0;
-    if (c->has_prev) while (nh < tb.ncomp && tb.comp_t[nh] == 0) ++nh;
-    c->halo_comps = nh;
-    v->planes = c->T; v->ncomp = tb.ncomp; v->halo_comps = nh; v->npair = c->npair; v->nseg = tb.nseg; v->nruns = c->nruns;
-    v->comp_t = tb.comp_t; v->comp_y0 = tb.comp_y0; v->comp_y1 = tb.comp_y1; v->comp_x0 = tb.comp_x0;
-    v->comp_x1 = tb.comp_x1; v->comp_cls = tb.comp_cls; v->cls_conE = tb.cls_conE; v->cls_conS = tb.cls_conS;
-    v->cls_fE = tb.cls_fE; v->cls_fS = tb.cls_fS; v->cls_nsp = tb.cls_nsp; v->cls_fnsp = tb.cls_fnsp;
-    v->pair_ptr = tb.pair_ptr; v->pair_b = tb.pair_b; v->pair_npix = tb.pair_npix; v->pair_nsp = tb.pair_nsp;
-    v->pair_E = tb.pair_E; v->pair_S = tb.pair_S; v->seg_t = tb.seg_t; v->seg_y0 = tb.seg_y0; v->seg_y1 = tb.seg_y1;
-    v->seg_a = tb.seg_a; v->seg_b = tb.seg_b;
-    return CT_OK;
-}
-
-int ct_shard_plane_runs(ct_ctx* c, long local_plane, long* n, const int32_t** y, const int32_t** x0, const int32_t** x1,
-                        const uint32_t** comp, void* stream) {
-    if (!c || !n || !y || !x0 || !x1 || !comp) return fail(CT_ERR_ARG, "null argument");
-    if (local_plane < 0 || local_plane >= c->T) return fail(CT_ERR_ARG, "plane %ld outside 0..%ld", local_plane, c->T - 1);
-    CT_CUDA(cudaSetDevice(c->device));
-    DeviceRunSource src;
-    src.c = c; src.st = (cudaStream_t)stream;
-    std::vector<cth::PlaneRun> runs;
-    if (!src.plane_runs(local_plane, runs)) return fail(CT_ERR_CUDA, "could not fetch the runs of plane %ld", local_plane);
-    const size_t k = runs.size();
-    CT_CUDA(c->hp_plane.ensure((k + 1) * 16));
-    int32_t* py = c->hp_plane.as<int32_t>();
-    int32_t* px0 = py + k + 1; int32_t* px1 = px0 + k + 1; uint32_t* pc = reinterpret_cast<uint32_t*>(px1 + k + 1);
-    for (size_t i = 0; i < k; ++i) { py[i] = runs[i].y; px0[i] = runs[i].x0; px1[i] = runs[i].x1; pc[i] = runs[i].comp; }
-    *n = (long)k; *y = py; *x0 = px0; *x1 = px1; *comp = pc;
-    return CT_OK;
-}
-
-int ct_shard_paint(ct_ctx* c, const int32_t* comp_val_local, long novr, const int32_t* ovr_t, const int32_t* ovr_y,
-                   const int32_t* ovr_x0, const int32_t* ovr_x1, const int32_t* ovr_val, int32_t* flag_dev, void* stream) {
-    if (!c || !flag_dev || (c->ncomp && !comp_val_local)) return fail(CT_ERR_ARG, "null argument");
-    CT_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    const long nc = c->ncomp, T_own = c->T - c->has_prev;
-    CT_CUDA(c->hp_val.ensure((size_t)(nc + 1) * 4));
-    int32_t* hv = c->hp_val.as<int32_t>();
-    if (nc) memcpy(hv, comp_val_local, (size_t)nc * 4);
-    std::vector<ctb::Override> ovr((size_t)novr);
-    for (long i = 0; i < novr; ++i) ovr[i] = ctb::Override{ovr_t[i], ovr_y[i], ovr_x0[i], ovr_x1[i], ovr_val[i]};
-    int rc = upload_values(c, hv, ovr, st);
-    if (rc != CT_OK) return rc;
-    const int sparse = (c->zero_started_for == flag_dev && flag_dev) ? 1 : 0;
-    if (sparse) CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
-    CT_CUDA(cudaEventRecord(c->ev[3], st));
-    if ((rc = launch_paint(c, c->has_prev, T_own, flag_dev, sparse, st)) != CT_OK) return rc;
-    if (novr) {
-        CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
-                                     c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), novr, c->H, c->W, 0, T_own, flag_dev, st));
-        c->launches += 1;
-    }
-    CT_CUDA(cudaEventRecord(c->ev[4], st));
-    CT_CUDA(cudaStreamSynchronize(st));
-    c->zero_started_for = nullptr;
-    float ms = 0;
-    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats["ms_threshold"] = ms;
-    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats["ms_paint"] = ms;
-    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats["ms_total"] = ms;
-    c->stats["kernel_launches"] = (double)c->launches;
-    return CT_OK;
-}
-
-// ---- time-sharded run, device-resident tables ------------------------------------------------------------------------
-int ct_shard_begin(ct_ctx* c, const void* anom_dev, int in_dtype, long T_local, int H, int W, const double* w_host,
-                   const double* thr_host, long thr_n, int thr_is_f32, int op, int has_prev, uint32_t* boundary_dst_dev,
-                   void* stream) {
-    if (!c) return fail(CT_ERR_ARG, "null context");
-    int rc = check_args(T_local, H, W, w_host, thr_host, thr_n, in_dtype, op);
-    if (rc != CT_OK) return rc;
-    if (T_local <= 0 || !anom_dev) return fail(CT_ERR_ARG, "a rank needs at least one plane");
-    has_prev = has_prev ? 1 : 0;
-    CT_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    c->stats.clear();
-    std::vector<double> thr(thr_host, thr_host + thr_n);
-    if (thr_n != 1 && has_prev) thr.insert(thr.begin(), 0.0);         // thresholds are indexed by scratch plane
-    if ((rc = prepare(c, T_local + has_prev, H, W, w_host, thr.data(), (long)thr.size(), st)) != CT_OK) return rc;
-    c->has_prev = has_prev;
-    c->sh_anom = anom_dev; c->sh_dtype = in_dtype; c->sh_thr_n = (long)thr.size(); c->sh_thr_is_f32 = thr_is_f32;
-    c->sh_op = op; c->sh_deferred = 1; c->halo_event_set = 0; c->fill_pending = 0;
-    // the LAST own plane first: its bit rows are what the next rank is waiting for
-    const size_t plane_bytes = (size_t)H * W * (in_dtype == CT_F64 ? 8 : 4);
-    if ((rc = launch_threshold(c, (const char*)anom_dev + (size_t)(T_local - 1) * plane_bytes, in_dtype,
-                               has_prev + T_local - 1, 1, c->sh_thr_n, thr_is_f32, op, st)) != CT_OK) return rc;
-    if (boundary_dst_dev) {
-        const size_t words = (size_t)H * c->Ww;
-        CT_CUDA(cudaMemcpyAsync(boundary_dst_dev, c->bits.as<uint32_t>() + (size_t)(c->T - 1) * words, words * 4,
-                                cudaMemcpyDeviceToDevice, st));
-    }
-    return CT_OK;
-}
-
-// counts8 = {0 (caller fills in t_shift), components, halo components, pairs, date-line segments, pairs of the halo
-//            components, segments of the halo plane, components of the last plane}
-// first half of ct_shard_tables_dev when the caller wants the halo exchange to run beside the thresholding: enqueue the
-// threshold chunks of the own planes (and, unless the fill starts late, the zero fill) and return
-int ct_shard_launch_threshold(ct_ctx* c, int32_t* flag_dev, void* stream) {
-    if (!c) return fail(CT_ERR_ARG, "null context");
-    if (c->sh_deferred != 1) return fail(CT_ERR_ARG, "ct_shard_launch_threshold follows ct_shard_begin");
-    CT_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    const int side = flag_dev && c->opt_overlap_zero;
-    if (side && (rc = ensure_streams(c)) != CT_OK) return rc;
-    const long hp = c->has_prev, T_own = c->T - hp;
-    long nchunk = side ? std::min<long>(c->opt_chunks, std::max<long>(1, T_own / c->opt_chunk_min_planes)) : 1;
-    const long cp = (T_own + nchunk - 1) / nchunk;
-    nchunk = (T_own + cp - 1) / cp;
-    if (side) {
-        while ((long)c->ev_chunk.size() < nchunk) {
-            cudaEvent_t e;
-            CT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            c->ev_chunk.push_back(e);
-        }
-    }
-    const size_t plane_bytes = (size_t)c->H * c->W * (c->sh_dtype == CT_F64 ? 8 : 4);
-    CT_CUDA(cudaEventRecord(c->ev[0], st));
-    for (long k = 0; k < nchunk; ++k) {
-        const long t0 = k * cp, nt = std::min(cp, T_own - t0);
-        if ((rc = launch_threshold(c, (const char*)c->sh_anom + (size_t)t0 * plane_bytes, c->sh_dtype, hp + t0, nt,
-                                   c->sh_thr_n, c->sh_thr_is_f32, c->sh_op, st, /*all_bits=*/side ? 0 : 1)) != CT_OK) return rc;
-        if (side) CT_CUDA(cudaEventRecord(c->ev_chunk[k], st));
-    }
-    CT_CUDA(cudaEventRecord(c->ev[1], st));
-    c->zero_started_for = nullptr;
-    if (side && !c->opt_shard_fill_late) {
-        CT_CUDA(cudaEventRecord(c->ev_side[0], st));
-        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-        CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
-        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
-        c->launches += 1;
-        c->zero_started_for = flag_dev;
-    }
-    c->sh_nchunk = nchunk; c->sh_cp = cp; c->sh_side = side; c->sh_flag = flag_dev;
-    c->sh_deferred = 2;
-    return CT_OK;
-}
-
-int ct_shard_tables_dev(ct_ctx* c, int32_t* flag_dev, void* stream, long* counts8, long* export_bytes) {
-    if (!c || !counts8 || !export_bytes) return fail(CT_ERR_ARG, "null argument");
-    CT_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    cudaStream_t ts = st;
-    const long hp = c->has_prev, T_own = c->T - hp;
-    const double t_h0 = now_ms();
-    const int deferred = c->sh_deferred;
-    int side = flag_dev && c->opt_overlap_zero;
-    if (deferred == 1 && (rc = ct_shard_launch_threshold(c, flag_dev, stream)) != CT_OK) return rc;
-    if (deferred) {
-        // ---- own planes were thresholded in time chunks on `st`; the table kernels of chunk k (and of the halo plane) run
-        // on the high-priority stream while chunk k+1 is being thresholded ----
-        if (c->sh_flag != flag_dev) return fail(CT_ERR_ARG, "flag_dev differs from the one given to ct_shard_launch_threshold");
-        c->sh_deferred = 0;
-        side = c->sh_side;
-        const long nchunk = c->sh_nchunk, cp = c->sh_cp;
-        if (side) ts = c->tbl_stream;
-        if (hp && c->halo_event_set) CT_CUDA(cudaStreamWaitEvent(ts, c->ev_halo, 0));
-        tables_begin(c);
-        for (long k = 0; k < nchunk; ++k) {
-            const long t0 = k * cp, nt = std::min(cp, T_own - t0);
-            if (side) CT_CUDA(cudaStreamWaitEvent(ts, c->ev_chunk[k], 0));
-            if ((rc = tables_chunk(c, k == 0 ? 0 : hp + t0, hp + t0 + nt, ts)) != CT_OK) return rc;
-            if (k < 8) { char key[16]; snprintf(key, sizeof key, "ms_h_c%ld", k); c->stats[key] = now_ms() - t_h0; }
-        }
-        if ((rc = tables_finish(c, ts)) != CT_OK) return rc;
-        if (side && c->opt_shard_fill_late) {
-            // the fill runs under the gather and the global phase instead of under the local table kernels (which are bound
-            // by memory latency and run ~2.3x slower beside a kernel that saturates HBM).  A short fill (small shard) is held
-            // back a little longer, until the tables are exported: the small collective that gathers the table sizes and the
-            // host round trip behind it then run on an idle memory system, and the fill still fits under the global phase.
-            const double fill_ms_est = (double)T_own * c->H * c->W * 4.0 / 6.5e9;
-            c->zero_started_for = flag_dev;
-            if (fill_ms_est > (double)c->opt_shard_fill_defer_ms) {
-                CT_CUDA(cudaEventRecord(c->ev_side[0], ts));
-                CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-                CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
-                CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
-                c->launches += 1;
-            } else {
-                c->fill_pending = 1;
-            }
-        }
-        c->stats["chunks"] = (double)nchunk;
-    } else {
-        c->zero_started_for = nullptr;
-        if (side) {
-            if ((rc = ensure_streams(c)) != CT_OK) return rc;
-            CT_CUDA(cudaEventRecord(c->ev_side[0], st));
-            CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-            CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
-            CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
-            c->launches += 1;
-            c->zero_started_for = flag_dev;
-            CT_CUDA(cudaStreamWaitEvent(c->tbl_stream, c->ev_side[0], 0));
-            ts = c->tbl_stream;
-        }
-        if (hp && c->halo_event_set) CT_CUDA(cudaStreamWaitEvent(ts, c->ev_halo, 0));
-        if ((rc = tables_build(c, ts)) != CT_OK) return rc;
-    }
-    uint32_t* cnt_dev = c->counters.as<uint32_t>();
-    uint32_t* cnt_host = c->hp_counters.as<uint32_t>();
-    CT_CUDA(cts::shard_counts(c->c_t.as<int32_t>(), c->ncomp, c->pptr.as<uint32_t>(), c->g_t.as<int32_t>(), c->nseg,
-                              c->has_prev, c->T - 1, cnt_dev + 12, ts));
-    c->launches += 1;
-    CT_CUDA(cudaMemcpyAsync(cnt_host + 12, cnt_dev + 12, 16, cudaMemcpyDeviceToHost, ts));
-    if (side) CT_CUDA(cudaEventRecord(c->ev_tbl[0], ts));
-    CT_CUDA(cudaStreamSynchronize(ts));
-    c->stats["ms_h_chunks"] = now_ms() - t_h0;
-    if (side && deferred) {
-        float ms = 0;
-        CT_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev_tbl[0])); c->stats["ms_tables_after_threshold"] = ms;
-        CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats["ms_threshold"] = ms;
-    }
-    c->halo_comps = cnt_host[12];
-    counts8[0] = 0; counts8[1] = c->ncomp; counts8[2] = cnt_host[12]; counts8[3] = c->npair; counts8[4] = c->nseg;
-    counts8[5] = cnt_host[13]; counts8[6] = cnt_host[14]; counts8[7] = cnt_host[15];
-    size_t off[cts::A_COUNT];
-    *export_bytes = (long)cts::layout(c->ncomp, c->npair, c->nseg, off);
-    return CT_OK;
-}
-
-int ct_shard_export_tables(ct_ctx* c, void* dst_dev, long cap_bytes, void* stream) {
-    if (!c || !dst_dev) return fail(CT_ERR_ARG, "null argument");
-    CT_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->zero_started_for ? c->tbl_stream : (cudaStream_t)stream;
-    size_t off[cts::A_COUNT];
-    const long nc = c->ncomp, np = c->npair, ns = c->nseg;
-    if ((long)cts::layout(nc, np, ns, off) > cap_bytes) return fail(CT_ERR_ARG, "export buffer too small");
-    if (c->fill_pending) {                                           // deferred zero fill of a small shard (see above)
-        const long T_own = c->T - c->has_prev;
-        c->fill_pending = 0;
-        CT_CUDA(cudaEventRecord(c->ev_side[0], st));
-        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-        CT_CUDA(ctk::zero_fill(c->zero_started_for, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
-        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
-        c->launches += 1;
-    }
-    if (st != (cudaStream_t)stream) {
-        // whatever the caller's stream still does to dst (e.g. the fill of a fresh torch.zeros) comes first
-        CT_CUDA(cudaEventRecord(c->ev[5], (cudaStream_t)stream));
-        CT_CUDA(cudaStreamWaitEvent(st, c->ev[5], 0));
-    }
-    char* d = (char*)dst_dev;
-    struct Src { int k; const DevBuf* b; long n; int elt; };
-    const Src src[] = {{cts::A_T, &c->c_t, nc, 4}, {cts::A_Y0, &c->c_y0, nc, 4}, {cts::A_Y1, &c->c_y1, nc, 4},
-                       {cts::A_X0, &c->c_x0, nc, 4}, {cts::A_X1, &c->c_x1, nc, 4}, {cts::A_CLS, &c->c_cls, nc, 4},
-                       {cts::A_CONE, &c->k_conE, nc, 8}, {cts::A_CONS, &c->k_conS, nc, 8}, {cts::A_FE, &c->k_fE, nc, 8},
-                       {cts::A_FS, &c->k_fS, nc, 8}, {cts::A_NSP, &c->k_nsp, nc, 4}, {cts::A_FNSP, &c->k_fnsp, nc, 4},
-                       {cts::A_PPTR, &c->pptr, nc + 1, 4}, {cts::A_PB, &c->p_b, np, 4}, {cts::A_PNPIX, &c->p_npix, np, 4},
-                       {cts::A_PNSP, &c->p_nsp, np, 4}, {cts::A_PE, &c->p_E, np, 8}, {cts::A_PS, &c->p_S, np, 8},
-                       {cts::A_GT, &c->g_t, ns, 4}, {cts::A_GY0, &c->g_y0, ns, 4}, {cts::A_GY1, &c->g_y1, ns, 4},
-                       {cts::A_GA, &c->g_a, ns, 4}, {cts::A_GB, &c->g_b, ns, 4}};
-    for (const Src& a : src) {
-        if (a.k == cts::A_PPTR && nc == 0) { CT_CUDA(cudaMemsetAsync(d + off[a.k], 0, 4, st)); continue; }
-        if (a.n > 0) CT_CUDA(cudaMemcpyAsync(d + off[a.k], a.b->p, (size_t)a.n * a.elt, cudaMemcpyDeviceToDevice, st));
-    }
-    // the collective that follows runs on the caller's stream
-    if (st != (cudaStream_t)stream) {
-        CT_CUDA(cudaEventRecord(c->ev_tbl[1], st));
-        CT_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_tbl[1], 0));
-    }
-    return CT_OK;
-}
-
-int ct_global_merge(ct_ctx* g, int nranks, const long* counts, const void* gathered_dev, long stride_bytes, long T_total,
-                    int H, int W, const double* w_host, void* stream) {
-    if (!g || !counts || !gathered_dev || !w_host || nranks < 1) return fail(CT_ERR_ARG, "null argument");
-    if (T_total <= 0 || H <= 0 || W <= 0 || H > 65535 || W > 65535) return fail(CT_ERR_ARG, "bad shape");
-    CT_CUDA(cudaSetDevice(g->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    g->stats.clear();
-    g->T = T_total; g->H = H; g->W = W; g->Ww = (W + 31) / 32;
-    g->w_host.assign(w_host, w_host + H);
-    {
-        std::vector<uint8_t> special;
-        classify_rows(w_host, H, W, special);
-        g->special_uniform = special_rows_uniform(w_host, special);
-    }
-    CT_CUDA(g->counters.ensure(128));
-    CT_CUDA(g->hp_counters.ensure(128));
-    for (auto& e : g->ev) if (!e) CT_CUDA(cudaEventCreate(&e));
-    g->launches = 0;
-    g->has_prev = 0; g->nruns = 0; g->nseam = 0; g->novr = 0;
-    // ---- per-rank descriptors ----
-    CT_CUDA(g->hp_desc.ensure((size_t)nranks * (sizeof(cts::RankDesc) + 3 * sizeof(long)) + 64));
-    cts::RankDesc* hd = g->hp_desc.as<cts::RankDesc>();
-    long* hb = reinterpret_cast<long*>(hd + nranks);
-    long NC = 0, NP = 0, NS = 0;
-    for (int r = 0; r < nranks; ++r) {
-        const long* k = counts + 8 * r;
-        cts::RankDesc& d = hd[r];
-        d.t_shift = k[0]; d.nc = k[1]; d.nh = k[2]; d.np = k[3]; d.ns = k[4]; d.e0 = k[5]; d.ns_h = k[6];
-        if (d.nc < 0 || d.nh < 0 || d.nh > d.nc || d.e0 < 0 || d.e0 > d.np || d.ns_h < 0 || d.ns_h > d.ns)
-            return fail(CT_ERR_ARG, "rank %d: inconsistent table counts", r);
-        if (r == 0 && d.nh) return fail(CT_ERR_ARG, "rank 0 cannot have halo components");
-        if (r > 0 && counts[8 * (r - 1) + 7] != d.nh)
-            return fail(CT_ERR_INTERNAL, "rank %d sees %ld components in its halo plane, rank %d has %ld in its last plane",
-                        r, d.nh, r - 1, counts[8 * (r - 1) + 7]);
-        d.src = (size_t)r * (size_t)stride_bytes;
-        if ((long)cts::layout(d.nc, d.np, d.ns, d.off) > stride_bytes) return fail(CT_ERR_ARG, "rank %d: stride too small", r);
-        d.comp_base = NC; d.pair_base = NP; d.seg_base = NS;
-        hb[r] = NC; hb[nranks + r] = NP; hb[2 * nranks + r] = NS;
-        NC += d.nc - d.nh; NP += d.np - d.e0; NS += d.ns - d.ns_h;
-    }
-    if (NC >= 2147483647L || NP >= 2147483647L) return fail(CT_ERR_CAPACITY, "global tables exceed 2^31 entries");
-    const size_t desc_bytes = (size_t)nranks * (sizeof(cts::RankDesc) + 3 * sizeof(long));
-    CT_CUDA(g->sh_desc.ensure(desc_bytes));
-    CT_CUDA(cudaMemcpyAsync(g->sh_desc.p, hd, desc_bytes, cudaMemcpyHostToDevice, st));
-    // ---- global tables ----
-    {
-        DevBuf* b4[] = {&g->c_t, &g->c_y0, &g->c_y1, &g->c_x0, &g->c_x1, &g->c_cls, &g->c_val, &g->k_nsp, &g->k_fnsp, &g->pptr};
-        DevBuf* b8[] = {&g->k_conE, &g->k_conS, &g->k_fE, &g->k_fS};
-        for (DevBuf* b : b4) CT_CUDA(b->ensure((size_t)(NC + 3) * 4));
-        for (DevBuf* b : b8) CT_CUDA(b->ensure((size_t)(NC + 3) * 8));
-        DevBuf* p4[] = {&g->p_b, &g->p_npix, &g->p_nsp};
-        DevBuf* p8[] = {&g->p_E, &g->p_S};
-        for (DevBuf* b : p4) CT_CUDA(b->ensure((size_t)(NP + 2) * 4));
-        for (DevBuf* b : p8) CT_CUDA(b->ensure((size_t)(NP + 2) * 8));
-        DevBuf* s4[] = {&g->g_t, &g->g_y0, &g->g_y1, &g->g_a, &g->g_b};
-        for (DevBuf* b : s4) CT_CUDA(b->ensure((size_t)(NS + 3) * 4));
-        CT_CUDA(g->run_val.ensure(16));
-    }
-    cts::GlobalTables gt;
-    gt.t = g->c_t.as<int32_t>(); gt.y0 = g->c_y0.as<int32_t>(); gt.y1 = g->c_y1.as<int32_t>();
-    gt.x0 = g->c_x0.as<int32_t>(); gt.x1 = g->c_x1.as<int32_t>(); gt.cls = g->c_cls.as<uint32_t>();
-    gt.conE = g->k_conE.as<double>(); gt.conS = g->k_conS.as<double>(); gt.fE = g->k_fE.as<double>();
-    gt.fS = g->k_fS.as<double>(); gt.nsp = g->k_nsp.as<uint32_t>(); gt.fnsp = g->k_fnsp.as<uint32_t>();
-    gt.pptr = g->pptr.as<uint32_t>();
-    gt.p_b = g->p_b.as<uint32_t>(); gt.p_npix = g->p_npix.as<uint32_t>(); gt.p_nsp = g->p_nsp.as<uint32_t>();
-    gt.p_E = g->p_E.as<double>(); gt.p_S = g->p_S.as<double>();
-    gt.g_t = g->g_t.as<int32_t>(); gt.g_y0 = g->g_y0.as<int32_t>(); gt.g_y1 = g->g_y1.as<int32_t>();
-    gt.g_a = g->g_a.as<uint32_t>(); gt.g_b = g->g_b.as<uint32_t>();
-    const cts::RankDesc* dd = g->sh_desc.as<cts::RankDesc>();
-    CT_CUDA(cts::merge((const char*)gathered_dev, dd, reinterpret_cast<const long*>(dd + nranks), nranks, NC, NP, NS, gt, st));
-    g->launches += 3;
-    g->ncomp = NC; g->npair = NP; g->nseg = NS;
-    g->stats["comps2d"] = (double)NC; g->stats["pairs"] = (double)NP; g->stats["seam_segments"] = (double)NS;
-    return CT_OK;
-}
-
-int ct_global_phase(ct_ctx* g, double overlap, int persistence, int twosided, ct_plane_runs_fn fetch, void* user,
-                    long* n_features, void* stream) {
-    if (!g) return fail(CT_ERR_ARG, "null context");
-    CT_CUDA(cudaSetDevice(g->device));
-    g->fetch_fn = fetch; g->fetch_user = user;
-    CT_CUDA(cudaEventRecord(g->ev[1], (cudaStream_t)stream));
-    int rc = table_phase(g, overlap, persistence, twosided, CT_STAGE_FINAL, n_features, (cudaStream_t)stream, true);
-    g->fetch_fn = nullptr; g->fetch_user = nullptr;
-    g->stats["kernel_launches"] = (double)g->launches;
-    return rc;
-}
-
-int ct_shard_paint_global(ct_ctx* c, ct_ctx* g, long comp_offset, long t_begin, int32_t* flag_dev, void* stream) {
-    if (!c || !g || !flag_dev) return fail(CT_ERR_ARG, "null argument");
-    if (c->device != g->device) return fail(CT_ERR_ARG, "shard and global context must live on the same device");
-    CT_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    const long T_own = c->T - c->has_prev;
-    if (c->ncomp && (comp_offset + c->ncomp > g->ncomp || comp_offset + c->halo_comps < 0))
-        return fail(CT_ERR_ARG, "component offset %ld does not fit the global tables", comp_offset);
-    // overrides (sub-runs of split components) of this rank's planes, in local time
-    std::vector<ctb::Override> ovr;
-    for (const ctb::Override& o : g->host_result.overrides)
-        if (o.t >= t_begin && o.t < t_begin + T_own) ovr.push_back(ctb::Override{(int32_t)(o.t - t_begin), o.y, o.x0, o.x1, o.val});
-    const long novr = (long)ovr.size();
-    c->novr = novr;
-    if (novr) {
-        CT_CUDA(c->hp_ovr.ensure((size_t)novr * 5 * 4));
-        int32_t* ho = c->hp_ovr.as<int32_t>();
-        for (long i = 0; i < novr; ++i) {
-            ho[i] = ovr[i].t; ho[novr + i] = ovr[i].y; ho[2 * novr + i] = ovr[i].x0; ho[3 * novr + i] = ovr[i].x1;
-            ho[4 * novr + i] = ovr[i].val;
-        }
-        const size_t ob = (size_t)novr * 4;
-        DevBuf* ob5[] = {&c->o_t, &c->o_y, &c->o_x0, &c->o_x1, &c->o_val};
-        for (int k = 0; k < 5; ++k) {
-            CT_CUDA(ob5[k]->ensure(ob));
-            CT_CUDA(cudaMemcpyAsync(ob5[k]->p, ho + (size_t)k * novr, ob, cudaMemcpyHostToDevice, st));
-        }
-    }
-    CT_CUDA(ctk::run_values(c->run_comp.as<uint32_t>(), g->c_val.as<int32_t>() + comp_offset, c->run_val.as<int32_t>(),
-                            c->nruns, st));
-    c->launches += 1;
-    if (c->fill_pending) {                                           // the tables were never exported: fill now
-        c->fill_pending = 0;
-        CT_CUDA(cudaEventRecord(c->ev_side[0], st));
-        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-        CT_CUDA(ctk::zero_fill(c->zero_started_for, (size_t)T_own * c->H * c->W, c->sm_count, c->side_stream));
-        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
-        c->launches += 1;
-    }
-    const int sparse = (c->zero_started_for == flag_dev && flag_dev) ? 1 : 0;
-    if (sparse) CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
-    CT_CUDA(cudaEventRecord(c->ev[3], st));
-    int rc;
-    if ((rc = launch_paint(c, c->has_prev, T_own, flag_dev, sparse, st)) != CT_OK) return rc;
-    if (novr) {
-        CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
-                                     c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), novr, c->H, c->W, 0, T_own, flag_dev, st));
-        c->launches += 1;
-    }
-    CT_CUDA(cudaEventRecord(c->ev[4], st));
-    CT_CUDA(cudaStreamSynchronize(st));
-    c->zero_started_for = nullptr;
-    float ms = 0;
-    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats["ms_threshold"] = ms;
-    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats["ms_paint"] = ms;
-    CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats["ms_total"] = ms;
-    if (sparse) { CT_CUDA(cudaEventElapsedTime(&ms, c->ev_side[0], c->ev_side[1])); c->stats["ms_zero_fill"] = ms; }
-    c->stats["kernel_launches"] = (double)(c->launches + g->launches);
-    for (const char* k : {"kept_comps", "labels3d", "features", "seam_events", "seam_splits", "neartie_resolved",
-                          "neartie_flagged", "sweeps", "ms_host_tables", "ms_g_sweeps", "ms_g_link", "ms_g_labels_d2h"})
-        if (g->stats.count(k)) c->stats[k] = g->stats[k];
     return CT_OK;
 }
 

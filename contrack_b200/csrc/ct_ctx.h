@@ -177,15 +177,24 @@ struct ct_ctx {
     cudaEvent_t ev_halo = nullptr;           // halo plane imported (ct_shard_import_halo may run on another stream)
     int halo_event_set = 0;
     // ---- fast path (ct_fast.cu): per-plane table kernel + cooperative global kernel, no host round trip between them ----
-    long opt_plane_kernel = 1;               // 0 = always the global-memory table kernels of ct_kernels.cu
+    long opt_plane_kernel = 2;               // tables: 0 = global-memory kernels of ct_kernels.cu, 1 = plane kernel, 2 = by size
+    long opt_plane_max_planes = 4096;        // ... plane kernel up to this many planes per context
+    long opt_coop_global = 1;                // ordered phase: cooperative global kernel (0: per-step kernels + host round trips)
+    long opt_fast_chunks = 1;                // time chunks of the fast path (1: the plane kernel runs beside the zero fill)
     long opt_max_sweeps = 32;                // Jacobi sweeps of step 3 before the plane-ordered wavefront takes over
     long opt_plane_smem = 0;                 // shared-memory budget of the plane kernel in bytes (0 = automatic)
     size_t pl_budget = 0;                    // budget in use (grows from 40 KB to 200 KB when a plane does not fit)
     DevBuf pl_chain, pl_done, pl_ctl;        // look-back descriptors, "plane written" flags, ticket / status / totals / results
-    PinBuf hp_ctl, hp_ev, hp_patch;
-    DevBuf g_dirty, g_blocksum, g_evflag, g_ev, g_patch;
+    PinBuf hp_ctl, hp_ev, hp_ev2, hp_patch;
+    DevBuf g_dirty, g_blocksum, g_evflag, g_ev, g_lrec, g_patch;
     long pl_planes = 0;                      // planes the chain was set up for
     int coop_grid = 0;
-    int fast_tables = 0;                     // the tables of this context were built by the plane kernel (paint by component)
+    int fast_tables = 0;                     // the value of every component is in c_val on the device (paint by component)
+    // ---- time-sharded run (ct_dist.cu) ----
+    ct_ctx* gctx = nullptr;                  // the merged global tables live in a second context on the same device (owned)
+    DevBuf sh_export, sh_gathered, sh_mdesc; // packed tables of this rank / of all ranks, per-rank descriptors
+    PinBuf hp_hdr;
+    long sh_capC = 0, sh_capP = 0, sh_capS = 0;   // negotiated per-rank capacities of the table exchange (0 = not yet)
+    cudaEvent_t ev_x[2] = {nullptr, nullptr};
 };
 

@@ -15,7 +15,7 @@ using cti::fail;
 __global__ void k_plane_init(unsigned long long* chain, long stride, uint32_t* ctl) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         chain[0] = 2ull; chain[stride] = 2ull; chain[2 * stride] = 2ull;      // slot 0: inclusive prefix 0
-        ctl[0] = 0; ctl[1] = 0;
+        ctl[0] = 0; ctl[1] = 0; ctl[2] = 0;                                     // ticket, status, info
     }
 }
 
@@ -70,7 +70,8 @@ Caps current_caps(ct_ctx* c) {
     uint32_t ss = 0xfffffff0u;
     DevBuf* s4[] = {&c->g_t, &c->g_y0, &c->g_y1, &c->g_a, &c->g_b, &c->g_evflag};
     for (DevBuf* b : s4) ss = std::min(ss, cap_of(*b, 4, 3));
-    ss = std::min(ss, cap_of(c->g_ev, 14 * 4, 1));
+    ss = std::min(ss, cap_of(c->g_ev, 2 * 4, 1));
+    ss = std::min(ss, cap_of(c->g_lrec, 2 * 7 * 4, 1));           // at most two labels per event segment
     ss = std::min(ss, cap_of(c->l_flag, 4, 2));                 // (the root flags double as event positions)
     k.segs = ss;
     return k;
@@ -96,8 +97,24 @@ int ensure_tables(ct_ctx* c, size_t runs, size_t comps, size_t pairs, size_t seg
     for (DevBuf* b : p8) CT_CUDA(b->ensure((pairs + 2) * 8));
     DevBuf* s4[] = {&c->g_t, &c->g_y0, &c->g_y1, &c->g_a, &c->g_b, &c->g_evflag};
     for (DevBuf* b : s4) CT_CUDA(b->ensure((segs + 3) * 4));
-    CT_CUDA(c->g_ev.ensure((segs + 1) * 14 * 4));
+    CT_CUDA(c->g_ev.ensure((segs + 1) * 2 * 4));
+    CT_CUDA(c->g_lrec.ensure((segs + 1) * 2 * 7 * 4));
     return CT_OK;
+}
+
+// scratch of the global kernel only (the tables themselves are left alone: they may hold data)
+int ensure_global_scratch(ct_ctx* c, size_t comps, size_t segs) {
+    DevBuf* b4[] = {&c->c_val, &c->l_parent, &c->l_rank, &c->l_label, &c->l_accN, &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1,
+                    &c->b_x0, &c->b_x1, &c->b_fin};
+    DevBuf* b8[] = {&c->l_accE, &c->l_accS};
+    for (DevBuf* b : b4) CT_CUDA(b->ensure((comps + 4) * 4));
+    for (DevBuf* b : b8) CT_CUDA(b->ensure((comps + 4) * 8));
+    CT_CUDA(c->l_kept.ensure(comps + 16));
+    CT_CUDA(c->l_flag.ensure((std::max(comps, segs) + 4) * 4));
+    CT_CUDA(c->g_evflag.ensure((segs + 3) * 4));
+    CT_CUDA(c->g_ev.ensure((segs + 1) * 2 * 4));
+    CT_CUDA(c->g_lrec.ensure((segs + 1) * 2 * 7 * 4));
+    return ensure_control(c);
 }
 
 int ensure_control(ct_ctx* c) {
@@ -153,7 +170,7 @@ int chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
     const Caps k = current_caps(c);
     a.cap_runs = k.runs; a.cap_comps = k.comps; a.cap_pairs = k.pairs; a.cap_segs = k.segs;
     a.chain = c->pl_chain.as<unsigned long long>(); a.chain_stride = c->pl_planes + 1;
-    a.done = U(c->pl_done); a.ticket = U(c->pl_ctl); a.status = U(c->pl_ctl) + 1;
+    a.done = U(c->pl_done); a.ticket = U(c->pl_ctl); a.status = U(c->pl_ctl) + 1; a.info = U(c->pl_ctl) + 2;
     if (!ctp::plane_config(c->H, c->pl_budget, &a.smem_runs, &a.hash_cap))
         return fail(CT_ERR_CAPACITY, "H = %d rows do not fit the plane kernel's shared memory", c->H);
     const size_t smem = ctp::plane_smem_bytes(c->H, a.smem_runs, &a.smem_scan_off);
@@ -190,6 +207,8 @@ int totals_to_host(ct_ctx* c, cudaStream_t st, int* outcome) {
     c->ncomp = (long)tot[0]; c->nseg = (long)tot[1]; c->nruns = (long)tot[2]; c->npair = (long)tot[3];
     c->stats["runs"] = (double)c->nruns; c->stats["comps2d"] = (double)c->ncomp; c->stats["pairs"] = (double)c->npair;
     c->stats["seam_segments"] = (double)c->nseg;
+    if (hctl[2] & 1u) c->stats["slot_overflow"] = 1.0;
+    if (status & ctp::ST_TIMEOUT) return fail(CT_ERR_INTERNAL, "plane kernel: a predecessor plane never published its tables");
     if (status & ctp::ST_FALLBACK) { *outcome = FAST_FALLBACK; return CT_OK; }
     if (status & ctp::ST_CAPACITY) {
         if (tot[2] >= 0xfffffff0ull)
@@ -205,7 +224,8 @@ int totals_to_host(ct_ctx* c, cudaStream_t st, int* outcome) {
     return CT_OK;
 }
 
-int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, long* n_features, cudaStream_t st, int* outcome) {
+int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, long* n_features, cudaStream_t st, int* outcome,
+           uint32_t* raw_status) {
     *outcome = FAST_SLOW;
     int rc = ensure_control(c);
     if (rc != CT_OK) return rc;
@@ -216,6 +236,7 @@ int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, lon
     ctp::GlobalArgs a;
     a.totals = reinterpret_cast<const unsigned long long*>(c->pl_ctl.as<char>() + 16);
     a.T = T;
+    a.status = ctl + 1; a.cap_comps = k.comps; a.cap_segs = k.segs;
     a.comp_t = c->c_t.as<int32_t>(); a.comp_y0 = c->c_y0.as<int32_t>(); a.comp_y1 = c->c_y1.as<int32_t>();
     a.comp_x0 = c->c_x0.as<int32_t>(); a.comp_x1 = c->c_x1.as<int32_t>(); a.cls = U(c->c_cls);
     a.conE = c->k_conE.as<double>(); a.conS = c->k_conS.as<double>(); a.fE = c->k_fE.as<double>(); a.fS = c->k_fS.as<double>();
@@ -230,19 +251,22 @@ int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, lon
     a.parent = U(c->l_parent); a.rootflag = U(c->l_flag); a.rank = U(c->l_rank); a.label = c->l_label.as<int32_t>();
     a.bt0 = c->b_t0.as<int32_t>(); a.bt1 = c->b_t1.as<int32_t>(); a.by0 = c->b_y0.as<int32_t>(); a.by1 = c->b_y1.as<int32_t>();
     a.bx0 = c->b_x0.as<int32_t>(); a.bx1 = c->b_x1.as<int32_t>(); a.fin = c->b_fin.as<int32_t>();
-    a.blocksum = U(c->g_blocksum); a.evflag = U(c->g_evflag); a.ev = c->g_ev.as<int32_t>(); a.cap_events = k.segs;
+    a.blocksum = U(c->g_blocksum); a.evflag = U(c->g_evflag); a.ev = c->g_ev.as<int32_t>(); a.lrec = c->g_lrec.as<int32_t>();
     a.out8 = ctl + 12;
     const double t_g0 = cti::now_ms();
     CT_CUDA(ctp::global_phase(a, c->coop_grid, st));
     c->launches += 1;
-    // ---- control block + the first events in one round trip ----
-    constexpr long EV_FIRST = 8192;
+    // ---- control block + (speculatively) the first events and label records in one round trip ----
+    constexpr long EV_FIRST = 32768, REC_FIRST = 8192;
     uint32_t* hctl = c->hp_ctl.as<uint32_t>();
-    CT_CUDA(c->hp_ev.ensure((size_t)EV_FIRST * 14 * 4));
+    const long ev_first = std::min<long>(EV_FIRST, (long)k.segs), rec_first = std::min<long>(REC_FIRST, 2 * (long)k.segs);
+    CT_CUDA(c->hp_ev.ensure((size_t)EV_FIRST * 8 + (size_t)REC_FIRST * 28));
     CT_CUDA(cudaMemcpyAsync(hctl, ctl, 128, cudaMemcpyDeviceToHost, st));
-    const long ev_first = std::min<long>(EV_FIRST, (long)k.segs);
-    if (ev_first > 0)
-        CT_CUDA(cudaMemcpyAsync(c->hp_ev.p, c->g_ev.p, (size_t)ev_first * 14 * 4, cudaMemcpyDeviceToHost, st));
+    if (ev_first > 0) {
+        CT_CUDA(cudaMemcpyAsync(c->hp_ev.p, c->g_ev.p, (size_t)ev_first * 8, cudaMemcpyDeviceToHost, st));
+        CT_CUDA(cudaMemcpyAsync(c->hp_ev.as<char>() + (size_t)EV_FIRST * 8, c->g_lrec.p, (size_t)rec_first * 28,
+                                cudaMemcpyDeviceToHost, st));
+    }
     CT_CUDA(cudaEventRecord(c->ev[2], st));
     CT_CUDA(cudaStreamSynchronize(st));
     const double t_g1 = cti::now_ms();
@@ -252,6 +276,11 @@ int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, lon
     c->ncomp = (long)tot[0]; c->nseg = (long)tot[1]; c->nruns = (long)tot[2]; c->npair = (long)tot[3];
     c->stats["runs"] = (double)c->nruns; c->stats["comps2d"] = (double)c->ncomp; c->stats["pairs"] = (double)c->npair;
     c->stats["seam_segments"] = (double)c->nseg;
+    if (raw_status) {                                                // (sharded run: the caller interprets the merged status)
+        *raw_status = status;
+        if (status) { *outcome = FAST_STATUS; return CT_OK; }
+    }
+    if (status & ctp::ST_TIMEOUT) return fail(CT_ERR_INTERNAL, "plane kernel: a predecessor plane never published its tables");
     if (status & ctp::ST_FALLBACK) { *outcome = FAST_FALLBACK; return CT_OK; }
     if (status & ctp::ST_CAPACITY) {
         if (tot[2] >= 0xfffffff0ull)
@@ -262,24 +291,28 @@ int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, lon
         *outcome = FAST_RETRY;
         return CT_OK;
     }
+    if (hctl[2] & 1u) c->stats["slot_overflow"] = 1.0;
     c->stats["sweeps"] = (double)out8[0];
     c->stats["wavefront_planes"] = (double)out8[5];
     c->stats["neartie_flagged"] = (double)out8[1];
     c->stats["ms_g_kernel"] = t_g1 - t_g0;
     if (out8[1]) { *outcome = FAST_SLOW; return CT_OK; }            // near-tie on non-exact rows: the exact host resolver
-    const long nlab = out8[2], nev = out8[3];
+    const long nlab = out8[2], nev = out8[3], nrec = out8[6];
     // ---- date-line events -> host replay at label granularity ----
     const int32_t* ev = c->hp_ev.as<int32_t>();
-    if (nev > ev_first) {
-        CT_CUDA(c->hp_ev.ensure((size_t)nev * 14 * 4));
-        CT_CUDA(cudaMemcpyAsync(c->hp_ev.p, c->g_ev.p, (size_t)nev * 14 * 4, cudaMemcpyDeviceToHost, st));
+    const int32_t* lrec = reinterpret_cast<const int32_t*>(c->hp_ev.as<char>() + (size_t)EV_FIRST * 8);
+    if (nev > ev_first || nrec > rec_first) {
+        CT_CUDA(c->hp_ev2.ensure((size_t)nev * 8 + (size_t)nrec * 28 + 64));
+        CT_CUDA(cudaMemcpyAsync(c->hp_ev2.p, c->g_ev.p, (size_t)nev * 8, cudaMemcpyDeviceToHost, st));
+        CT_CUDA(cudaMemcpyAsync(c->hp_ev2.as<char>() + (size_t)nev * 8, c->g_lrec.p, (size_t)nrec * 28, cudaMemcpyDeviceToHost, st));
         CT_CUDA(cudaStreamSynchronize(st));
-        ev = c->hp_ev.as<int32_t>();
+        ev = c->hp_ev2.as<int32_t>();
+        lrec = reinterpret_cast<const int32_t*>(c->hp_ev2.as<char>() + (size_t)nev * 8);
     }
     static thread_local std::vector<int32_t> plab, pval;
     ctb::TrackStats ts;
     long feat_delta = 0;
-    if (ctb::track_events_fast(persistence, nev, ev, plab, pval, &feat_delta, ts) != 0) {
+    if (ctb::track_events_fast(persistence, nev, ev, nrec, lrec, plab, pval, &feat_delta, ts) != 0) {
         c->stats["label_fast"] = 0.0;
         *outcome = FAST_SLOW;                                        // a label straddles a stale box: per-component replay
         return CT_OK;

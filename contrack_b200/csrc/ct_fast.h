@@ -11,7 +11,8 @@ enum Outcome {
     FAST_OK = 0,        // the value of every component is in c_val on the device
     FAST_SLOW = 1,      // tables are valid (counts in the context); the caller continues with the ordered host phase
     FAST_RETRY = 2,     // a table was too small: buffers have been grown to the exact totals, build the tables again
-    FAST_FALLBACK = 3   // a plane does not fit the shared-memory budget: next_budget(), or the global-memory table kernels
+    FAST_FALLBACK = 3,  // a plane does not fit the shared-memory budget: next_budget(), or the global-memory table kernels
+    FAST_STATUS = 4     // global(..., raw_status): the status word was not zero, nothing was done (sharded run decides)
 };
 
 int begin(ct_ctx* c, long planes, cudaStream_t st);              // buffers, chain reset
@@ -20,8 +21,10 @@ int finish(ct_ctx* c, cudaStream_t st);                          // totals of th
 bool next_budget(ct_ctx* c);
 int ensure_tables(ct_ctx* c, size_t runs, size_t comps, size_t pairs, size_t segs);
 int ensure_control(ct_ctx* c);
+int ensure_global_scratch(ct_ctx* c, size_t comps, size_t segs);
 int totals_to_host(ct_ctx* c, cudaStream_t st, int* outcome);     // counts -> context (one synchronisation)
 // global phase on the tables of `c` (T = planes of the cube they describe); ends with one stream synchronisation
-int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, long* n_features, cudaStream_t st, int* outcome);
+int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, long* n_features, cudaStream_t st, int* outcome,
+           uint32_t* raw_status);
 
 }  // namespace ctf

@@ -181,9 +181,13 @@ __global__ void __launch_bounds__(GLOBAL_THREADS) k_global_phase(GlobalArgs a) {
     __shared__ uint32_t s_w[40];
     const long NC = (long)a.totals[0], NS = (long)a.totals[1];
     const long T = a.T;
+    // incomplete tables (a plane fell back / a table was too small): nothing to do, the host rebuilds them.  Every thread
+    // reads the same words, so the whole grid leaves before the first barrier.
+    if (*a.status != 0u || NC > (long)a.cap_comps || NS > (long)a.cap_segs) return;
     const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long)gridDim.x * blockDim.x;
-    uint32_t* ctr = a.out8 + 8;                                   // [0..1] changed (ping-pong), [2] near-tie flags,
-                                                                  // [3] features, [4] wavefront first plane
+    uint32_t* ctr = a.out8 + 8;                                   // [2] near-tie flags, [3] features, [4] wavefront planes,
+                                                                  // [5..7] "changed" of sweep k at 5 + k % 3: a flag is
+                                                                  // cleared two barriers after its last reader
     uint8_t* dirty0 = a.dirty;
     uint8_t* dirty1 = a.dirty + (T + 2);
 
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(GLOBAL_THREADS) k_global_phase(GlobalArgs a) {
         uint8_t* dc = cur ? dirty1 : dirty0;
         uint8_t* dn = cur ? dirty0 : dirty1;
         for (long t = gtid; t < T + 2; t += gsize) dn[t] = 0;
-        if (gtid == 0) { ctr[(sweeps + 1) & 1] = 0; ctr[2] = 0; }
+        if (gtid == 0) { ctr[5 + (sweeps + 1) % 3] = 0; ctr[2] = 0; }
         for (long c = gtid; c < NC; c += gsize) {
             const int tt = a.comp_t[c];
             if (tt < 1 || tt + 1 >= T || !dc[tt]) continue;
@@ -212,10 +216,10 @@ __global__ void __launch_bounds__(GLOBAL_THREADS) k_global_phase(GlobalArgs a) {
             if (a.cls[c] != (uint32_t)c) continue;
             const int tt = a.comp_t[c];
             if (tt < 1 || tt + 1 >= T || !dc[tt]) continue;
-            if (decide_one(a, c, full ? ctr + 2 : nullptr)) { dn[tt + 1] = 1; ctr[sweeps & 1] = 1u; }
+            if (decide_one(a, c, full ? ctr + 2 : nullptr)) { dn[tt + 1] = 1; ctr[5 + sweeps % 3] = 1u; }
         }
         grid.sync();
-        const bool changed = __ldcg(ctr + (sweeps & 1)) != 0u;
+        const bool changed = __ldcg(ctr + 5 + sweeps % 3) != 0u;
         ++sweeps;
         cur ^= 1;
         if (!changed) {
@@ -311,23 +315,34 @@ __global__ void __launch_bounds__(GLOBAL_THREADS) k_global_phase(GlobalArgs a) {
     }
     feats = block_sum(feats, s_w);
     if (threadIdx.x == 0 && feats) atomicAdd(ctr + 3, feats);
-    // ---- date-line events in (t, y) order, with the boxes of both labels ----
+    // ---- labels that occur in events -> compact records (label, box); events -> pairs of record indices, (t, y) order ----
+    uint32_t* mark = a.rank;                                      // (rank and parent are free once the labels are known)
+    uint32_t* lpos = a.parent;
+    for (long v = gtid; v <= (long)nlab; v += gsize) mark[v] = 0;
+    grid.sync();
+    for (long s = gtid; s < NS; s += gsize) {
+        if (!a.evflag[s]) continue;
+        mark[a.label[a.seg_a[s]]] = 1u; mark[a.label[a.seg_b[s]]] = 1u;
+    }
+    grid.sync();
+    const uint32_t nrec = grid_excl_scan(grid, mark, (long)nlab + 1, lpos, a.blocksum, s_w);
+    for (long v = gtid; v <= (long)nlab; v += gsize) {
+        if (!mark[v]) continue;
+        int32_t* r = a.lrec + (size_t)lpos[v] * 7;
+        r[0] = (int32_t)v; r[1] = a.bt0[v]; r[2] = a.bt1[v]; r[3] = a.by0[v]; r[4] = a.by1[v]; r[5] = a.bx0[v]; r[6] = a.bx1[v];
+    }
     uint32_t* evpos = a.rootflag;                                  // (the root flags are no longer needed; NS <= capacity)
     const uint32_t nev = grid_excl_scan(grid, a.evflag, NS, evpos, a.blocksum, s_w);
     for (long s = gtid; s < NS; s += gsize) {
         if (!a.evflag[s]) continue;
         const uint32_t e = evpos[s];
-        if (e >= a.cap_events) continue;
-        const int la = a.label[a.seg_a[s]], lb = a.label[a.seg_b[s]];
-        int32_t* r = a.ev + (size_t)e * 14;
-        r[0] = la; r[1] = lb;
-        r[2] = a.bt0[la]; r[3] = a.bt1[la]; r[4] = a.by0[la]; r[5] = a.by1[la]; r[6] = a.bx0[la]; r[7] = a.bx1[la];
-        r[8] = a.bt0[lb]; r[9] = a.bt1[lb]; r[10] = a.by0[lb]; r[11] = a.by1[lb]; r[12] = a.bx0[lb]; r[13] = a.bx1[lb];
+        a.ev[2 * (size_t)e] = (int32_t)lpos[a.label[a.seg_a[s]]];
+        a.ev[2 * (size_t)e + 1] = (int32_t)lpos[a.label[a.seg_b[s]]];
     }
     grid.sync();
     if (gtid == 0) {
         a.out8[0] = sweeps; a.out8[1] = 0; a.out8[2] = nlab; a.out8[3] = nev; a.out8[4] = __ldcg(ctr + 3);
-        a.out8[5] = __ldcg(ctr + 4);
+        a.out8[5] = __ldcg(ctr + 4); a.out8[6] = nrec;
     }
 }
 

@@ -300,17 +300,27 @@ int track_phase(const FastTables& tb, const int32_t* label, int persistence, Run
                 // test hook: what the cooperative global kernel + track_events_fast do in the product path -- persistence of
                 // every label from its own box, the event list (segments whose ends carry different labels, with both
                 // boxes), the replay on the events alone, patches on top
-                std::vector<int32_t> ev;
+                std::vector<int32_t> ev, lrec, lidx(nlabel + 1, -1);
                 for (long s = 0; s < tb.nseg; ++s) {
                     const int la = sla[s], lb = slb[s];
                     if (la == 0 || lb == 0 || la == lb) continue;
-                    const int32_t r[14] = {la, lb, t0[la], t1[la], y0[la], y1[la], x0[la], x1[la],
-                                           t0[lb], t1[lb], y0[lb], y1[lb], x0[lb], x1[lb]};
-                    ev.insert(ev.end(), r, r + 14);
+                    lidx[la] = 0; lidx[lb] = 0;
+                }
+                for (int v = 1; v <= nlabel; ++v) {
+                    if (lidx[v] < 0) continue;
+                    lidx[v] = (int32_t)(lrec.size() / 7);
+                    const int32_t r[7] = {v, t0[v], t1[v], y0[v], y1[v], x0[v], x1[v]};
+                    lrec.insert(lrec.end(), r, r + 7);
+                }
+                for (long s = 0; s < tb.nseg; ++s) {
+                    const int la = sla[s], lb = slb[s];
+                    if (la == 0 || lb == 0 || la == lb) continue;
+                    ev.push_back(lidx[la]); ev.push_back(lidx[lb]);
                 }
                 std::vector<int32_t> pl, pv;
                 long delta = 0, feats = 0;
-                if (ctb::track_events_fast(persistence, (long)ev.size() / 14, ev.data(), pl, pv, &delta, stats) == 0) {
+                if (ctb::track_events_fast(persistence, (long)ev.size() / 2, ev.data(), (long)lrec.size() / 7, lrec.data(), pl, pv,
+                                           &delta, stats) == 0) {
                     lab_fin.assign(nlabel + 1, 0);
                     for (int v = 1; v <= nlabel; ++v) {
                         const bool keep = t1[v] > t0[v] && (t1[v] - t0[v]) >= persistence;

@@ -100,7 +100,11 @@ __device__ __forceinline__ void uf_union(uint16_t* par, uint32_t a, uint32_t b) 
 // ---- decoupled look-back (one warp): publishes `agg` for slot `slot`, returns the sum of all earlier slots ----
 // word = value << 2 | flag; flag 1 = aggregate of this slot only, 2 = inclusive prefix.  Slot 0 is the sentinel the
 // host wrote (inclusive 0, or the totals the previous chunks reached: slots of earlier launches are all inclusive).
-__device__ __forceinline__ unsigned long long lookback(unsigned long long* words, long slot, unsigned long long agg, int lane) {
+// A predecessor that never publishes (which would be a bug: blocks take their plane from a ticket, so every predecessor is
+// already running) is reported in *status after SPIN_LIMIT polls instead of hanging the device.
+constexpr uint32_t SPIN_LIMIT = 1u << 25;
+__device__ __forceinline__ unsigned long long lookback(unsigned long long* words, long slot, unsigned long long agg, int lane,
+                                                       uint32_t* status) {
     if (lane == 0) st_release(words + slot, (agg << 2) | 1ull);
     unsigned long long excl = 0;
     long idx = slot - 1;
@@ -108,7 +112,11 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* words
         const long j = idx - lane;
         unsigned long long w = 2ull;                                // before slot 0: inclusive zero
         if (j >= 0) {
-            do { w = ld_acquire(words + j); } while ((w & 3ull) == 0ull);
+            uint32_t spins = 0;
+            do {
+                w = ld_acquire(words + j);
+                if (++spins == SPIN_LIMIT) { atomicOr(status, ST_TIMEOUT); w = 2ull; }
+            } while ((w & 3ull) == 0ull);
         }
         const unsigned inc_mask = __ballot_sync(FULL, (w & 3ull) == 2ull);
         const int first = inc_mask ? __ffs(inc_mask) - 1 : 32;     // nearest slot that already knows its inclusive prefix
@@ -223,6 +231,7 @@ __global__ void __launch_bounds__(PLANE_THREADS) k_plane_tables(PlaneArgs a) {
                 }
             } else {
                 runs_from_bits(a.bits + (row0 + y) * (long)a.Ww, W, a.Ww, sx + off, c);
+                *a.info = 1u;
             }
         }
     }
@@ -291,8 +300,8 @@ __global__ void __launch_bounds__(PLANE_THREADS) k_plane_tables(PlaneArgs a) {
 
     // ---- chain 1: global base of this plane's runs / components / segments ----
     if (tid < 32) {
-        const unsigned long long eA = lookback(chainA, slot, ((unsigned long long)nC << 31) | nS, lane);
-        const unsigned long long eR = lookback(chainR, slot, n_true, lane);
+        const unsigned long long eA = lookback(chainA, slot, ((unsigned long long)nC << 31) | nS, lane, a.status);
+        const unsigned long long eR = lookback(chainR, slot, n_true, lane, a.status);
         if (lane == 0) {
             s_w[34] = (uint32_t)(eA >> 31); s_w[35] = (uint32_t)(eA & 0x7fffffffu);
             s_w[36] = (uint32_t)eR; s_w[37] = (uint32_t)(eR >> 32);
@@ -364,11 +373,15 @@ __global__ void __launch_bounds__(PLANE_THREADS) k_plane_tables(PlaneArgs a) {
     const bool has_prev = plane > 0;
     uint32_t nP = 0;
     if (has_prev) {
-        if (tid == 0) { while (ld_acquire32(a.done + slot - 1) == 0u) {} }
+        if (tid == 0) {
+            uint32_t spins = 0;
+            while (ld_acquire32(a.done + slot - 1) == 0u)
+                if (++spins == SPIN_LIMIT) { atomicOr(a.status, ST_TIMEOUT | ST_FALLBACK); break; }
+        }
         for (uint32_t h = tid; h < HC; h += nthr) { hash[h].key = HASH_EMPTY; hash[h].npix = 0; hash[h].nsp = 0; hash[h].E = 0.0; hash[h].S = 0.0; }
         if (tid == 0) { s_w[38] = 0; s_w[39] = 0; }
         __syncthreads();
-        const bool prev_ok = (__ldcg(a.status) & (ST_FALLBACK | ST_CAPACITY)) == 0u;   // (tables of earlier planes exist)
+        const bool prev_ok = (__ldcg(a.status) & (ST_FALLBACK | ST_CAPACITY | ST_TIMEOUT)) == 0u;   // (tables of earlier planes exist)
         if (ok && prev_ok) {
             for (uint32_t i = tid; i < n; i += nthr) {
                 const int y = row_of(roff, H, i);
@@ -419,7 +432,7 @@ __global__ void __launch_bounds__(PLANE_THREADS) k_plane_tables(PlaneArgs a) {
     // ---- chain 2: global base of this plane's pairs; CSR ----
     __syncthreads();
     if (tid < 32) {
-        const unsigned long long eP = lookback(chainP, slot, nP, lane);
+        const unsigned long long eP = lookback(chainP, slot, nP, lane, a.status);
         if (lane == 0) { s_w[36] = (uint32_t)eP; s_w[37] = (uint32_t)(eP >> 32); }
     }
     __syncthreads();

@@ -14,6 +14,7 @@ constexpr int RUN_SLOTS = ctk::RUN_SLOTS_PER_ROW;
 // bits of *status
 constexpr uint32_t ST_FALLBACK = 1u;     // a plane does not fit the shared-memory budget / its pair hash overflowed
 constexpr uint32_t ST_CAPACITY = 2u;     // a table is smaller than the totals the chain reports: grow and run again
+constexpr uint32_t ST_TIMEOUT = 4u;      // a look-back / predecessor wait gave up (internal error, never expected)
 
 struct PlaneArgs {
     // what the threshold kernel left per row
@@ -33,6 +34,7 @@ struct PlaneArgs {
     unsigned long long* chain; long chain_stride;
     uint32_t* done;                          // [planes + 1] "runs / components / classes of this plane are written"
     uint32_t *ticket, *status;
+    uint32_t* info;                          // bit 0: some row had more runs than slots (its runs came from the bit row)
     // shared-memory configuration (plane_config)
     uint32_t smem_runs, hash_cap; size_t smem_scan_off;
 };
@@ -45,6 +47,8 @@ cudaError_t plane_tables(const PlaneArgs& a, size_t smem_bytes, cudaStream_t st)
 struct GlobalArgs {
     // tables (device); the counts are read from the chain totals at `totals` = {components, segments, runs, pairs} (u64 x 4)
     const unsigned long long* totals;
+    const uint32_t* status;                  // tables are garbage when any bit is set: the kernel returns at once
+    uint32_t cap_comps, cap_segs;            // what the scratch arrays hold
     long T;                                  // planes of the cube (components of plane 0 and T-1 are never filtered)
     const int32_t *comp_t, *comp_y0, *comp_y1, *comp_x0, *comp_x1;
     const uint32_t* cls;
@@ -61,11 +65,12 @@ struct GlobalArgs {
     int32_t *bt0, *bt1, *by0, *by1, *bx0, *bx1;   // label boxes [components + 2]
     int32_t* fin;                            // [components + 2] value painted for every label (persistence applied)
     uint32_t* blocksum;                      // [gridDim.x + 1] grid-wide scan scratch
-    // date-line events (segments whose two ends carry different labels), in (t, y) order
+    // date-line events (segments whose two ends carry different labels), in (t, y) order, as pairs of indices into the
+    // records of the labels that occur in events: lrec = {label, t0, t1, y0, y1, x0, x1} sorted by label
     uint32_t* evflag;                        // [segments + 1]
-    int32_t* ev;                             // [14 * cap_events]: la, lb, box(la) x6, box(lb) x6
-    uint32_t cap_events;
-    // results: {sweeps, near-tie flags, labels, events, features before the host pass, wavefront planes, 0, 0}
+    int32_t* ev;                             // [2 * segments]
+    int32_t* lrec;                           // [7 * min(2 * segments, components + 1)]
+    // results: {sweeps, near-tie flags, labels, events, features before the host pass, wavefront planes, records, 0}
     uint32_t* out8;
 };
 int global_grid(int sm_count);

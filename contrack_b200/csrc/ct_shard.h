@@ -1,4 +1,4 @@
-// ct_shard.h -- packed rank-local tables of a time-sharded run and their merge into global tables (ct_shard.cu).
+// ct_shard.h -- packed rank-local tables of a time-sharded run (layout) and the global tables they are merged into (ct_dist.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstddef>
@@ -19,15 +19,6 @@ enum Arr {
 };
 size_t layout(long nc, long np, long ns, size_t off[A_COUNT]);      // returns the total bytes
 
-struct RankDesc {
-    size_t src;                   // byte offset of this rank's export buffer in the gathered buffer
-    size_t off[A_COUNT];
-    long nc, nh, np, ns;          // local components (first nh: halo plane), pairs, segments
-    long e0, ns_h;                // pairs / segments that belong to the halo plane come first: skip them
-    long t_shift;                 // local plane index + t_shift = global time step
-    long comp_base, pair_base, seg_base;   // global index of the first OWN component / pair / segment
-};
-
 struct GlobalTables {
     int32_t *t, *y0, *y1, *x0, *x1; uint32_t* cls;
     double *conE, *conS, *fE, *fS; uint32_t *nsp, *fnsp;
@@ -35,14 +26,5 @@ struct GlobalTables {
     uint32_t *p_b, *p_npix, *p_nsp; double *p_E, *p_S;
     int32_t *g_t, *g_y0, *g_y1; uint32_t *g_a, *g_b;
 };
-
-// out4 = {components of plane 0 if has_prev else 0, pptr[that], segments of plane 0 if has_prev else 0,
-//         components of plane `last_plane`}
-cudaError_t shard_counts(const int32_t* comp_t, long nc, const uint32_t* pptr, const int32_t* seg_t, long ns, int has_prev,
-                         long last_plane, uint32_t* out4_dev, cudaStream_t st);
-
-// bases_dev: [3 * nranks] comp_base | pair_base | seg_base
-cudaError_t merge(const char* gathered, const RankDesc* desc_dev, const long* bases_dev, int nranks, long NC, long NP,
-                  long NS, const GlobalTables& g, cudaStream_t st);
 
 }  // namespace cts

@@ -535,33 +535,19 @@ int track_labels_fast(int persistence, const LabelTables& lt, long nseg, const i
     return 0;
 }
 
-int track_events_fast(int persistence, long nev, const int32_t* ev, std::vector<int32_t>& patch_label,
-                      std::vector<int32_t>& patch_value, long* feat_delta, TrackStats& stats) {
+int track_events_fast(int persistence, long nev, const int32_t* ev, long nrec, const int32_t* lrec,
+                      std::vector<int32_t>& patch_label, std::vector<int32_t>& patch_value, long* feat_delta,
+                      TrackStats& stats) {
     stats = TrackStats();
     patch_label.clear(); patch_value.clear();
     *feat_delta = 0;
     if (nev == 0) return 0;
-    // labels that occur in events -> dense local indices (sorted by label: min / max of values = min / max of indices)
-    struct Workspace {
-        std::vector<int32_t> labs; std::vector<Box3> box;
-        std::vector<int> value, head, nxt, touched; std::vector<uint8_t> built, settled;
-    };
+    // the records are sorted by label, so the order of record indices is the order of the label values
+    struct Workspace { std::vector<int> value, head, nxt, touched; std::vector<uint8_t> built, settled; };
     static thread_local Workspace tls_ws;
     Workspace& ws = tls_ws;
-    std::vector<int32_t>& labs = ws.labs;
-    labs.resize((size_t)2 * nev);
-    for (long e = 0; e < nev; ++e) { labs[2 * e] = ev[14 * e]; labs[2 * e + 1] = ev[14 * e + 1]; }
-    std::sort(labs.begin(), labs.end());
-    labs.erase(std::unique(labs.begin(), labs.end()), labs.end());
-    const int m = (int)labs.size();
-    auto local = [&](int32_t L) { return (int)(std::lower_bound(labs.begin(), labs.end(), L) - labs.begin()); };
-    std::vector<Box3>& box = ws.box;
-    box.resize(m);
-    for (long e = 0; e < nev; ++e) {
-        const int32_t* r = ev + 14 * e;
-        box[local(r[0])] = Box3{r[2], r[3], r[4], r[5], r[6], r[7]};
-        box[local(r[1])] = Box3{r[8], r[9], r[10], r[11], r[12], r[13]};
-    }
+    const int m = (int)nrec;
+    auto box = [&](int L) { const int32_t* r = lrec + 7 * (size_t)L; return Box3{r[1], r[2], r[3], r[4], r[5], r[6]}; };
     std::vector<int>&value = ws.value, &head = ws.head, &nxt = ws.nxt, &touched = ws.touched;
     std::vector<uint8_t>&built = ws.built, &settled = ws.settled;
     value.resize(m); head.resize(m); nxt.resize(m);
@@ -574,20 +560,21 @@ int track_events_fast(int persistence, long nev, const int32_t* ev, std::vector<
         touched.push_back(v);
     };
     for (long e = 0; e < nev; ++e) {
-        const int la = local(ev[14 * e]), lb = local(ev[14 * e + 1]);
+        const int la = ev[2 * e], lb = ev[2 * e + 1];
+        if (la < 0 || lb < 0 || la >= m || lb >= m) return 1;
         const int va = val_of(la), vb = val_of(lb);
         if (va == vb) continue;
         stats.n_events++;
         const int hi = std::max(va, vb), lo = std::min(va, vb);
         ensure_built(hi); ensure_built(lo);
         if (settled[hi]) continue;
-        const Box3 b = box[hi];
+        const Box3 b = box(hi);
         int L = head[hi], prev = -1;
         bool moved = false;
         while (L >= 0) {
             const int next = nxt[L];
             stats.n_walked++;
-            const Box3& q = box[L];
+            const Box3 q = box(L);
             const bool inside = q.t0 >= b.t0 && q.t1 <= b.t1 && q.y0 >= b.y0 && q.y1 <= b.y1 && q.x0 >= b.x0 && q.x1 <= b.x1;
             const bool outside = q.t1 <= b.t0 || q.t0 >= b.t1 || q.y1 <= b.y0 || q.y0 >= b.y1 || q.x1 <= b.x0 || q.x0 >= b.x1;
             if (inside) {
@@ -607,15 +594,17 @@ int track_events_fast(int persistence, long nev, const int32_t* ev, std::vector<
     // persistence (contrack.py:765-772) of the touched values from their current members; the device counted every label
     // as a feature of its own box
     for (int v : touched) {
-        const Box3& o = box[v];
+        const Box3 o = box(v);
         if (o.t1 > o.t0 && (o.t1 - o.t0) >= persistence) --*feat_delta;
     }
     for (int v : touched) {
         int lo = INT_MAX, hi = 0;
-        for (int L = head[v]; L >= 0; L = nxt[L]) { lo = std::min(lo, box[L].t0); hi = std::max(hi, box[L].t1); }
+        for (int L = head[v]; L >= 0; L = nxt[L]) { const Box3 q = box(L); lo = std::min(lo, q.t0); hi = std::max(hi, q.t1); }
         const bool keep = hi > lo && (hi - lo) >= persistence;
         *feat_delta += keep;
-        for (int L = head[v]; L >= 0; L = nxt[L]) { patch_label.push_back(labs[L]); patch_value.push_back(keep ? labs[v] : 0); }
+        for (int L = head[v]; L >= 0; L = nxt[L]) {
+            patch_label.push_back(lrec[7 * (size_t)L]); patch_value.push_back(keep ? lrec[7 * (size_t)v] : 0);
+        }
     }
     return 0;
 }

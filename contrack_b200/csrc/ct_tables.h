@@ -63,14 +63,16 @@ int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_
 int track_labels_fast(int persistence, const LabelTables& lt, long nseg, const int32_t* seg_la, const int32_t* seg_lb,
                       std::vector<int32_t>& lab_fin, TrackStats& stats);
 
-// The same label-granular replay from the device's event list alone: `ev` holds 14 ints per date-line segment whose two
-// ends carry different 3-D labels, in (t, y) order: la, lb, box(la) = t0 t1 y0 y1 x0 x1, box(lb).  Only labels that occur
-// in events can ever change value, so nothing else is needed.  Outputs: for every label an event touched, its final value
-// (patch_label / patch_value; 0 = removed by the persistence filter), and *feat_delta = the correction to the number of
-// features the device counted under the assumption that no event happened.  Returns 0, or 1 if a label straddles a stale
-// box (per-component replay needed; nothing written).
-int track_events_fast(int persistence, long nev, const int32_t* ev, std::vector<int32_t>& patch_label,
-                      std::vector<int32_t>& patch_value, long* feat_delta, TrackStats& stats);
+// The same label-granular replay from the device's event list alone.  `lrec`: one record {label, t0, t1, y0, y1, x0, x1}
+// per label that occurs in an event, sorted by label; `ev`: for every date-line segment whose two ends carry different 3-D
+// labels, in (t, y) order, the record indices of the label at x = 0 and at x = W-1.  Only labels that occur in events can
+// ever change value, so nothing else is needed.  Outputs: for every label an event touched, its final value (patch_label /
+// patch_value; 0 = removed by the persistence filter), and *feat_delta = the correction to the number of features the
+// device counted under the assumption that no event happened.  Returns 0, or 1 if a label straddles a stale box
+// (per-component replay needed; nothing written).
+int track_events_fast(int persistence, long nev, const int32_t* ev, long nrec, const int32_t* lrec,
+                      std::vector<int32_t>& patch_label, std::vector<int32_t>& patch_value, long* feat_delta,
+                      TrackStats& stats);
 
 // np.sum order on a contiguous float64 vector: 0 + pairwise(a, n) with 128-element blocks and 8 accumulators.
 double numpy_pairwise_sum(const double* a, long n);

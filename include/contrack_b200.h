@@ -31,7 +31,8 @@ enum ct_status {
                                more than 2^31 - 1 components or pairs */
     CT_ERR_NEARTIE = -4,    /* overlap decision within rounding distance of the threshold on rows whose area weights
                                are not exactly summable and the exact resolver could not decide */
-    CT_ERR_INTERNAL = -5
+    CT_ERR_INTERNAL = -5,
+    CT_ERR_COMM = -6        /* a collective of a time-sharded run failed (NCCL error, libnccl not found) */
 };
 
 enum ct_dtype { CT_F32 = 0, CT_F64 = 1 };
@@ -170,79 +171,38 @@ int ct_host_tables_fast(long T, int H, int W, const double* w_host, double overl
                         int32_t* comp_val, long ovr_cap, int32_t* ovr_t, int32_t* ovr_y, int32_t* ovr_x0, int32_t* ovr_x1,
                         int32_t* ovr_val, long* n_ovr, long* stats8);
 
-/* ---- time-sharded run (one context per rank / GPU) ---------------------------------------------------
- * Rank r owns planes [t_begin, t_end) of the cube.  Per rank:
- *   ct_shard_threshold      threshold the own planes (contrack.py:648-674); has_prev = 1 for every rank but the first
- *   ct_shard_export_boundary / ct_shard_import_halo
- *                           the bit rows (H * ceil(W/32) uint32) of the last own plane go to the next rank, which stores
- *                           them as its plane 0 ("halo"): the ONE exchange of boundary planes (NCCL send/recv by the caller)
- *   ct_shard_tables         table kernels over halo + own planes; the tables arrive in pinned host memory (ct_shard_view,
- *                           valid until the next call on this context).  Component ids are rank-local; the first
- *                           `halo_comps` components belong to the halo plane.  If flag_dev is given, its zero fill is
- *                           started on a side stream so that it overlaps the gather and the ordered phase.
- *   (caller)                all-gather the views, renumber to global ids, run ct_host_tables_fast on every rank
- *   ct_shard_plane_runs     row-runs of one local plane (0 = halo plane if has_prev) for the ct_plane_runs_fn callback
- *   ct_shard_paint          values of the local components -> flag planes of this rank (contrack.py:776-791)
- */
-typedef struct ct_shard_view {
-    long planes;              /* own planes + has_prev */
-    long ncomp, halo_comps, npair, nseg, nruns;
-    const int32_t *comp_t, *comp_y0, *comp_y1, *comp_x0, *comp_x1;     /* comp_t: local plane index (halo plane = 0) */
-    const uint32_t* comp_cls;
-    const double *cls_conE, *cls_conS, *cls_fE, *cls_fS;
-    const uint32_t *cls_nsp, *cls_fnsp;
-    const uint32_t* pair_ptr;
-    const uint32_t *pair_b, *pair_npix, *pair_nsp;
-    const double *pair_E, *pair_S;
-    const int32_t *seg_t, *seg_y0, *seg_y1;
-    const uint32_t *seg_a, *seg_b;
-} ct_shard_view;
-
-int ct_shard_threshold(ct_ctx* ctx, const void* anom_dev, int in_dtype, long T_local, int H, int W,
-                       const double* w_host, const double* thr_host, long thr_n, int thr_is_f32, int op, int has_prev,
-                       void* stream);
-long ct_shard_boundary_words(ct_ctx* ctx);
-int ct_shard_export_boundary(ct_ctx* ctx, uint32_t* dst_dev, void* stream);
-int ct_shard_import_halo(ct_ctx* ctx, const uint32_t* src_dev, void* stream);
-int ct_shard_tables(ct_ctx* ctx, int32_t* flag_dev, void* stream, ct_shard_view* view);
-int ct_shard_plane_runs(ct_ctx* ctx, long local_plane, long* n, const int32_t** y, const int32_t** x0,
-                        const int32_t** x1, const uint32_t** comp, void* stream);
-int ct_shard_paint(ct_ctx* ctx, const int32_t* comp_val_local, long novr, const int32_t* ovr_t, const int32_t* ovr_y,
-                   const int32_t* ovr_x0, const int32_t* ovr_x1, const int32_t* ovr_val, int32_t* flag_dev, void* stream);
-
-/* ---- time-sharded run with device-resident tables (the path bench.py --gpus N and sharded.run_contrack_sharded use) ----
- * The rank-local tables never visit the host: every rank packs them into one device buffer, the caller all-gathers the
- * buffers (NCCL), a merge kernel renumbers them into GLOBAL tables in a second context (`g`, same device), and the global
- * part of contrack.py:706-772 (overlap filter, 3-D labels, date-line merge, persistence) runs on every rank's copy -- the
- * "global relabel": every rank computes the same value for every component of the cube and paints its own planes.
- *   ct_shard_begin          like ct_shard_threshold, but only the LAST own plane is thresholded now and its bit rows are
- *                           copied to boundary_dst_dev (may be NULL): the next rank gets its halo before anything else is
- *                           computed.  The own planes are thresholded by ct_shard_tables_dev, in time chunks, with the table
- *                           kernels of one chunk running beside the thresholding of the next (options "chunks",
- *                           "chunk_min_planes").  Call ct_shard_import_halo between the two when has_prev.
- *   ct_shard_tables_dev     table kernels over halo + own planes (tables stay on the device); zero fill of flag_dev starts
- *                           on a side stream.  counts8 = {0 (caller: t_begin - has_prev), components, halo components,
- *                           pairs, segments, pairs of halo components, segments of the halo plane, components of the last
- *                           plane}; *export_bytes = size of this rank's packed tables
- *   ct_shard_export_tables  pack the tables into dst_dev (cap_bytes >= export_bytes)
- *   (caller)                all-gather counts8 and the packed tables (stride = max export_bytes)
- *   ct_global_merge         gathered tables -> global tables of context g (counts: [nranks * 8], rank order)
- *   ct_global_phase         contrack.py:706-772 on g's tables; `fetch` (may be NULL) serves the row-runs of a global plane
- *                           with global component ids when a near-tie decision or a stale-box split needs them
- *   ct_shard_paint_global   values of this rank's components (global id = local id + comp_offset) -> its flag planes */
-int ct_shard_begin(ct_ctx* ctx, const void* anom_dev, int in_dtype, long T_local, int H, int W, const double* w_host,
-                   const double* thr_host, long thr_n, int thr_is_f32, int op, int has_prev, uint32_t* boundary_dst_dev,
-                   void* stream);
-/* optional, between ct_shard_begin and ct_shard_tables_dev: enqueue the thresholding of the own planes now, so that the
- * halo exchange (on another stream; ct_shard_import_halo may be given that stream) runs beside it */
-int ct_shard_launch_threshold(ct_ctx* ctx, int32_t* flag_dev, void* stream);
-int ct_shard_tables_dev(ct_ctx* ctx, int32_t* flag_dev, void* stream, long* counts8, long* export_bytes);
-int ct_shard_export_tables(ct_ctx* ctx, void* dst_dev, long cap_bytes, void* stream);
-int ct_global_merge(ct_ctx* g, int nranks, const long* counts, const void* gathered_dev, long stride_bytes, long T_total,
-                    int H, int W, const double* w_host, void* stream);
-int ct_global_phase(ct_ctx* g, double overlap, int persistence, int twosided, ct_plane_runs_fn fetch, void* user,
-                    long* n_features, void* stream);
-int ct_shard_paint_global(ct_ctx* ctx, ct_ctx* g, long comp_offset, long t_begin, int32_t* flag_dev, void* stream);
+/* ---- time-sharded run: one context and one communicator per rank / GPU -------------------------------------
+ * Rank r of nranks owns planes [t_begin, t_begin + T_local) of the cube; ranks are ordered in time.  ct_run_contrack_sharded
+ * is ONE collective call per rank (contrack.py:646-772 across the shards): the last own plane's bit rows go to the next rank
+ * (the one halo exchange, send/recv of H * ceil(W/32) words), the rank tables are all-gathered (a few MB, one collective of
+ * fixed stride), merged by a kernel into global tables on every rank, and every rank replays the global part (overlap
+ * filter, 3-D numbering, stale-box date-line merge, persistence) on its copy: all ranks obtain the same global ids ("global
+ * relabel") and paint their own planes.  The cube never moves.  ids, dtype and semantics are those of ct_run_contrack on the
+ * concatenated cube, bit for bit.
+ *
+ * Communicator: NCCL, bound at run time (dlopen of the libnccl the process already uses, else the system one).
+ *   ct_nccl_unique_id    rank 0 makes the 128-byte ncclUniqueId; the caller distributes it (MPI_Bcast, a file, torch.distributed)
+ *   ct_comm_init_nccl    every rank joins (ncclCommInitRank on `device`)
+ *   ct_comm_from_nccl    ... or wraps a ncclComm_t the caller already owns (not destroyed by ct_comm_destroy)
+ *   ct_comm_init_local   nranks communicators of an in-process group (one host thread per rank, contexts on one or several GPUs
+ *                        of this process): the same stream-ordered semantics with events and peer copies -- for tests on a
+ *                        single-GPU box, not a product transport
+ * thr_host: one value, or the T_local values of this rank's planes.  `stream`: the caller's stream; the call returns after this
+ * rank's flag planes are written (it synchronises once for the date-line events, like ct_run_contrack).
+ * Runtime options of the context apply ("plane_kernel", "max_sweeps", ...); stats as for ct_run_contrack plus "exchange_bytes",
+ * "shard_attempts". */
+typedef struct ct_comm ct_comm;
+int ct_nccl_unique_id(unsigned char id[128]);
+int ct_comm_init_nccl(const unsigned char id[128], int rank, int nranks, int device, ct_comm** out);
+int ct_comm_from_nccl(void* nccl_comm, int rank, int nranks, ct_comm** out);
+int ct_comm_init_local(int nranks, ct_comm** out /* [nranks] */);
+void ct_comm_destroy(ct_comm* comm);
+int ct_comm_rank(ct_comm* comm);
+int ct_comm_size(ct_comm* comm);
+int ct_run_contrack_sharded(ct_ctx* ctx, ct_comm* comm, const void* anom_dev, int in_dtype, long T_local, long t_begin,
+                            long T_total, int H, int W, const double* w_host, const double* thr_host, long thr_n,
+                            int thr_is_f32, int op, double overlap, int persistence, int twosided, int32_t* flag_dev,
+                            long* n_features, void* stream);
 
 /* ---- run_lifecycle, contrack.py:799-907 -------------------------------------------------------------------------------
  * flag_dev [T,H,W] int32 (ds[flag]), var_dev [T,H,W] float32/float64 (ds[variable]), w_host [H] the float32-valued area

@@ -1,4 +1,5 @@
-"""One rank of the NCCL test of the time-sharded path (tests/test_gpu_sharded.py::test_sharded_torchrun_two_gpus)."""
+"""One rank of the NCCL test of the time-sharded path (tests/test_gpu_sharded.py::test_sharded_torchrun_two_gpus):
+ct_run_contrack_sharded over an NCCL communicator made inside the library (unique id distributed through torch.distributed)."""
 import os
 import sys
 
@@ -30,7 +31,7 @@ def main():
         ref = oracle.run_contrack(x, lat, lon, thr, '>=', ov, pers, two)
         t0, t1 = sharded.shard_bounds(x.shape[0], world)[rank]
         xl = torch.from_numpy(np.ascontiguousarray(x[t0:t1])).cuda()
-        flag, n, info = sharded.run_contrack_sharded(eng, xl, t0, x.shape[0], w, thr, True, 0, ov, pers, two)
+        flag, n, stats = sharded.run_contrack_sharded(eng, xl, t0, x.shape[0], w, thr, True, 0, ov, pers, two)
         torch.cuda.synchronize()
         if not np.array_equal(flag.cpu().numpy(), ref[t0:t1]) or n != len(np.unique(ref)) - 1:
             print('rank %d MISMATCH' % rank, flush=True)

@@ -17,6 +17,7 @@ def main():
     import torch.distributed as dist
     from oracle import contrack_oracle as oracle
     from contrack_b200 import sharded
+    import _shard_np as shard_np
     from _common import row_weights
     from _synth import synth_cube, regular_grid
     from _tables_np import build_tables, legacy_to_view
@@ -42,8 +43,8 @@ def main():
         mask = x[t0 - has_prev:t1] >= thr
         tb = build_tables(mask, w)
         mine = legacy_to_view(tb, has_prev, t0)
-        views = [sharded.unpack_view(b) for b in sharded.allgather_bytes(sharded.pack_view(mine))]
-        g, offs = sharded.merge_views(views)
+        views = [shard_np.unpack_view(b) for b in shard_np.allgather_bytes(shard_np.pack_view(mine))]
+        g, offs = shard_np.merge_views(views)
         bounds = sharded.shard_bounds(T, world)
 
         def fetch(t):
@@ -59,7 +60,7 @@ def main():
             dist.broadcast_object_list(obj, src=owner)
             return obj[0]
 
-        val, overrides, stats = sharded.host_tables_fast(T, H, W, w, g, ov, pers, two, fetch=fetch)
+        val, overrides, stats = shard_np.host_tables_fast(T, H, W, w, g, ov, pers, two, fetch=fetch)
         # paint the own planes from the label images of build_tables
         flag = np.zeros((t1 - t0, H, W), np.int32)
         for lp in range(has_prev, tb['T']):

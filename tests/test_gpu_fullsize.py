@@ -67,8 +67,9 @@ def test_variants_and_sharded_agree(cube, result):
     flag, n, _ = result
     eng = Engine.get(0)
     out = torch.empty_like(flag)
-    for opts in ({'chunks': 1}, {'tma': 0, 'fused_runs': 0}, {'overlap_zero': 0}, {'label_fast': 0, 'gpu_tables': 1}):
-        defaults = {'chunks': 4, 'tma': 3, 'fused_runs': 1, 'overlap_zero': 1, 'label_fast': 1, 'gpu_tables': 1}
+    for opts in ({'chunks': 1}, {'plane_kernel': 1}, {'plane_kernel': 1, 'fast_chunks': 3}, {'coop_global': 0}, {'overlap_zero': 0},
+                 {'max_sweeps': 2}):
+        defaults = {'chunks': 4, 'plane_kernel': 2, 'fast_chunks': 1, 'coop_global': 1, 'overlap_zero': 1, 'max_sweeps': 32}
         for k, v in opts.items():
             eng.set_option(k, v)
         try:
@@ -81,16 +82,14 @@ def test_variants_and_sharded_agree(cube, result):
     engines = [Engine(0) for _ in range(3)]
     try:
         bounds = sharded.shard_bounds(T, 3)
-        outs, n3, _ = sharded.run_contrack_sharded_local_dev(engines, [a[b0:b1] for b0, b1 in bounds], T, w, THR, True, 0, OV,
-                                                             PERS, True)
+        outs, n3, _ = sharded.run_local_group(engines, [a[b0:b1] for b0, b1 in bounds], T, w, THR, True, 0, OV, PERS, True)
         assert n3 == n
         for (b0, b1), o in zip(bounds, outs):
             assert bool(torch.equal(o, flag[b0:b1]))
     finally:
         for e in engines:
-            for h in (e, getattr(e, '_global', None)):
-                if h is not None and h.handle:
-                    h.lib.ct_destroy(h.handle); h.handle = None
+            if e.handle:
+                e.lib.ct_destroy(e.handle); e.handle = None
 
 
 def test_host_buffer_entry_point_agrees(cube, result):

@@ -279,12 +279,15 @@ def test_host_table_path_matches_device_table_path(eng, golden):
     assert sha_i4(f) == r['sha256'] and eng.stats()['sweeps'] >= 1
 
 
+@pytest.mark.parametrize('plane', [0, 1])
 @pytest.mark.parametrize('chunks', [2, 5, 12])
-def test_chunked_table_pipeline(eng, chunks):
-    """The table kernels run per time chunk (while later chunks are still being thresholded); every chunking must give
-    the bytes of the unchunked run: date-line-heavy cubes with stale-box splits, per-timestep thresholds, one-sided mode,
-    and the intermediate stages."""
+def test_chunked_table_pipeline(eng, chunks, plane):
+    """The table kernels (global-memory ones, or the plane kernel) run per time chunk while later chunks are still being
+    thresholded; every chunking must give the bytes of the unchunked run: date-line-heavy cubes with stale-box splits,
+    per-timestep thresholds, one-sided mode, and the intermediate stages."""
     eng.set_option('chunks', chunks)
+    eng.set_option('fast_chunks', chunks)
+    eng.set_option('plane_kernel', plane)
     eng.set_option('chunk_min_planes', 1)
     try:
         la, lo = regular_grid(24, 16)
@@ -309,6 +312,8 @@ def test_chunked_table_pipeline(eng, chunks):
         assert np.array_equal(f4, st['label3d'])
     finally:
         eng.set_option('chunks', 4)
+        eng.set_option('fast_chunks', 1)
+        eng.set_option('plane_kernel', 2)
         eng.set_option('chunk_min_planes', 1024)
 
 

@@ -487,7 +487,8 @@ def main():
                                        % (path_bytes, world))},
             'breakdown_ms': {'threshold_bits': thr_ms, 'paint': paint_ms, 'tables_gpu_and_host': float(np.mean(ms_tab)),
                              'host_table_phase': float(np.mean(ms_host)),
-                             'zero_fill_overlapped_with_tables': float(np.mean(ms_zero))},
+                             'zero_fill_overlapped_with_tables': float(np.mean(ms_zero)),
+                             'plane_kernel': stats.get('ms_plane_kernel'), 'global_kernel': stats.get('ms_global_kernel')},
             'tables': {k: int(stats[k]) for k in ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d',
                                                   'seam_events', 'seam_splits', 'neartie_resolved') if k in stats},
             'synth_seconds': t_gen}
@@ -503,7 +504,8 @@ def main():
         line['config']['threshold_note'] = thr_note
     if world > 1 and shard_info:
         last = shard_info[-args.steps:]
-        keys = ('ms_threshold', 'ms_zero_fill', 'ms_tables_after_threshold', 'ms_paint', 'ms_total', 'ms_g_kernel', 'ms_host_tables')
+        keys = ('ms_threshold', 'ms_zero_fill', 'ms_tables_after_threshold', 'ms_plane_kernel', 'ms_global_kernel', 'ms_host_tables',
+                'ms_paint', 'ms_total')
         mine = {k: round(float(np.mean([i.get(k, 0.0) for i in last])), 3) for k in keys}
         mine.update({k: last[-1].get(k) for k in ('exchange_bytes', 'shard_attempts', 'fast_path', 'sweeps', 'kernel_launches')})
         every = [None] * world

@@ -38,8 +38,6 @@ cudaError_t anom_chunks(const void* z, int f64, long HW, long T, const int32_t* 
 }  // namespace cta
 
 namespace cte {
-cudaError_t quantile_time(const float* x, long T, int H, int W, int y0, int y1, const double* q_dev, int nq, double* out,
-                          cudaStream_t st);
 cudaError_t flag_count(const int32_t* flag, long T, int H, int W, int v, int32_t* count, int sm_count, cudaStream_t st);
 cudaError_t divide_f32(const float* in, size_t n, float g, float* out, cudaStream_t st);
 cudaError_t gather_planes(const void* src, int f64, int G, int Hs, int Ws, const int32_t* iy_dev, const int32_t* ix_dev, int H,
@@ -509,13 +507,6 @@ int tables_d2h(ct_ctx* c, int full, cudaStream_t st) {
     tb.w = c->w_host.data();
     tb.special_uniform = c->special_uniform;
     return CT_OK;
-}
-
-int tables_gpu(ct_ctx* c, cudaStream_t st) {
-    int rc = tables_build(c, st);
-    if (rc != CT_OK) return rc;
-    CT_CUDA(cudaEventRecord(c->ev[2], st));
-    return tables_d2h(c, 1, st);
 }
 
 // Steps 3 and 4a/b on the device: Jacobi sweeps to the fixpoint of the keep/kill recurrence, then 3-D labels.
@@ -1011,13 +1002,14 @@ void ct_destroy(ct_ctx* c) {
                       &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN,
                       &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
                       &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml,
-                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots, &c->x_q, &c->x_idx, &c->ovf_rows,
+                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots, &c->x_q, &c->x_qscratch, &c->x_idx, &c->ovf_rows,
                       &c->pl_chain, &c->pl_done, &c->pl_ctl, &c->g_dirty, &c->g_blocksum, &c->g_evflag, &c->g_ev, &c->g_lrec, &c->g_patch,
                       &c->sh_export, &c->sh_gathered, &c->sh_mdesc};
     for (DevBuf* b : bufs) b->release();
     c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release(); c->hp_desc.release();
     c->hp_ctl.release(); c->hp_ev.release(); c->hp_ev2.release(); c->hp_patch.release(); c->hp_hdr.release();
     for (auto& e : c->ev_x) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_p) if (e) cudaEventDestroy(e);
     if (c->gctx) ct_destroy(c->gctx);
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
@@ -1704,17 +1696,7 @@ int ct_calc_anom_t(ct_ctx* c, const void* z_dev, int dtype, long T, int H, int W
 // ---- callers either side of the path: ct_extras.cu -------------------------------------------------------
 int ct_quantile_time(ct_ctx* c, const float* x_dev, long T, int H, int W, int y0, int y1, const double* q_host, int nq,
                      double* out_dev, void* stream) {
-    if (!c || !x_dev || !q_host || !out_dev) return fail(CT_ERR_ARG, "null argument");
-    if (T <= 0 || H <= 0 || W <= 0 || y0 < 0 || y1 > H || y0 >= y1 || nq <= 0) return fail(CT_ERR_ARG, "bad shape / row range");
-    for (int i = 0; i < nq; ++i)
-        if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0)) return fail(CT_ERR_ARG, "Quantiles must be in the range [0, 1]");
-    CT_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    CT_CUDA(c->x_q.ensure((size_t)nq * 8));
-    CT_CUDA(cudaMemcpyAsync(c->x_q.p, q_host, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
-    CT_CUDA(cudaStreamSynchronize(st));                               // q_host may be a temporary of the caller
-    CT_CUDA(cte::quantile_time(x_dev, T, H, W, y0, y1, c->x_q.as<double>(), nq, out_dev, st));
-    return CT_OK;
+    return ct_quantile_time_t(c, nullptr, x_dev, CT_F32, T, H, W, y0, y1, q_host, nq, out_dev, stream);
 }
 
 int ct_flag_count(ct_ctx* c, const int32_t* flag_dev, long T, int H, int W, int greater_than, int32_t* count_dev,

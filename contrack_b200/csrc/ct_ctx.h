@@ -154,7 +154,7 @@ struct ct_ctx {
     long nspecial_cached = 0;
     long launches = 0;
     // time-sharded run: packed tables of all ranks -> global tables (ct_global_merge), plane runs served by the caller
-    DevBuf sh_desc, b_sla, b_slb, x_q, x_idx, ovf_rows;
+    DevBuf sh_desc, b_sla, b_slb, x_q, x_qscratch, x_idx, ovf_rows;
     PinBuf hp_desc;
     ct_plane_runs_fn fetch_fn = nullptr;
     void* fetch_user = nullptr;
@@ -189,6 +189,7 @@ struct ct_ctx {
     DevBuf g_dirty, g_blocksum, g_evflag, g_ev, g_lrec, g_patch;
     long pl_planes = 0;                      // planes the chain was set up for
     int coop_grid = 0;
+    int plane_timed = 0;
     int fast_tables = 0;                     // the value of every component is in c_val on the device (paint by component)
     // ---- time-sharded run (ct_dist.cu) ----
     ct_ctx* gctx = nullptr;                  // the merged global tables live in a second context on the same device (owned)
@@ -196,5 +197,6 @@ struct ct_ctx {
     PinBuf hp_hdr;
     long sh_capC = 0, sh_capP = 0, sh_capS = 0;   // negotiated per-rank capacities of the table exchange (0 = not yet)
     cudaEvent_t ev_x[2] = {nullptr, nullptr};
+    cudaEvent_t ev_p[4] = {nullptr, nullptr, nullptr, nullptr};    // plane kernel begin / end, global kernel begin / end
 };
 

@@ -17,6 +17,7 @@
 #include <cstring>
 
 #include "ct_comm.h"
+#include "ct_extras.h"
 #include "ct_fast.h"
 #include "ct_internal.h"
 #include "ct_shard.h"
@@ -264,6 +265,13 @@ int dist_fetch_cb(void* user, long t, long* n, const int32_t** y, const int32_t*
     return 0;
 }
 
+int q_sum_u32(void* user, uint32_t* buf, size_t n, cudaStream_t st) {
+    return static_cast<ctc::Comm*>(user)->allreduce(buf, n, ctc::SUM_U32, st);
+}
+int q_min_i64(void* user, long long* buf, size_t n, cudaStream_t st) {
+    return static_cast<ctc::Comm*>(user)->allreduce(buf, n, ctc::MIN_I64, st);
+}
+
 int comm_fail(ctc::Comm* comm, const char* what) { return fail(CT_ERR_COMM, "%s: %s", what, comm->err.c_str()); }
 
 }  // namespace
@@ -322,6 +330,31 @@ void ct_comm_destroy(ct_comm* comm) {
 
 int ct_comm_rank(ct_comm* comm) { return comm && comm->impl ? comm->impl->rank() : -1; }
 int ct_comm_size(ct_comm* comm) { return comm && comm->impl ? comm->impl->size() : -1; }
+
+// ---- quantile over time, optionally over the time shards of all ranks (README.rst:150-151) -------------------------------
+int ct_quantile_time_t(ct_ctx* c, ct_comm* comm_h, const void* x_dev, int dtype, long T_local, int H, int W, int y0, int y1,
+                       const double* q_host, int nq, double* out_dev, void* stream) {
+    if (!c || !x_dev || !q_host || !out_dev) return fail(CT_ERR_ARG, "null argument");
+    if (dtype != CT_F32 && dtype != CT_F64) return fail(CT_ERR_ARG, "dtype must be CT_F32 or CT_F64");
+    if (T_local <= 0 || H <= 0 || W <= 0 || y0 < 0 || y1 > H || y0 >= y1 || nq <= 0) return fail(CT_ERR_ARG, "bad shape / row range");
+    for (int i = 0; i < nq; ++i)
+        if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0)) return fail(CT_ERR_ARG, "Quantiles must be in the range [0, 1]");
+    CT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long npts = (long)(y1 - y0) * W;
+    CT_CUDA(c->x_q.ensure((size_t)nq * 8));
+    CT_CUDA(c->x_qscratch.ensure(cte::quantile_scratch_bytes(npts, nq, dtype == CT_F64)));
+    CT_CUDA(cudaMemcpyAsync(c->x_q.p, q_host, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+    CT_CUDA(cudaStreamSynchronize(st));                               // q_host may be a temporary of the caller
+    cte::QuantileReduce red{q_sum_u32, q_min_i64, comm_h ? comm_h->impl : nullptr};
+    const cudaError_t e = cte::quantile_time(x_dev, dtype == CT_F64, T_local, H, W, y0, y1, c->x_q.as<double>(), nq, out_dev,
+                                             c->x_qscratch.p, comm_h && comm_h->impl && comm_h->impl->size() > 1 ? &red : nullptr, st);
+    if (e != cudaSuccess) {
+        if (comm_h && comm_h->impl && !comm_h->impl->err.empty()) return comm_fail(comm_h->impl, "quantile all-reduce");
+        return fail(CT_ERR_CUDA, "quantile_time failed: %s", cudaGetErrorString(e));
+    }
+    return CT_OK;
+}
 
 // ---- the sharded run ----------------------------------------------------------------------------------------------------
 int ct_run_contrack_sharded(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, int in_dtype, long T_local, long t_begin,
@@ -590,7 +623,7 @@ int ct_run_contrack_sharded(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, in
     c->stats["runs"] = (double)c->nruns; c->stats["comps2d"] = (double)c->ncomp;
     c->stats["exchange_bytes"] = (double)((HDR_BYTES + [&] { size_t off[cts::A_COUNT]; return cts::layout(c->sh_capC, c->sh_capP, c->sh_capS, off); }() + 255) / 256 * 256);
     for (const char* k : {"labels3d", "features", "seam_events", "seam_splits", "neartie_resolved", "neartie_flagged", "sweeps",
-                          "wavefront_planes", "ms_host_tables", "ms_g_kernel", "label_fast", "event_segments"})
+                          "wavefront_planes", "ms_host_tables", "ms_g_kernel", "label_fast", "event_segments", "ms_global_kernel"})
         if (g->stats.count(k)) c->stats[k] = g->stats[k];
     c->stats["fast_path"] = outcome == ctf::FAST_OK ? (classic ? 0.5 : 1.0) : 0.25;
     return CT_OK;

@@ -175,7 +175,11 @@ int chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
         return fail(CT_ERR_CAPACITY, "H = %d rows do not fit the plane kernel's shared memory", c->H);
     const size_t smem = ctp::plane_smem_bytes(c->H, a.smem_runs, &a.smem_scan_off);
     CT_CUDA(cudaMemsetAsync(c->pl_ctl.p, 0, 4, st));                 // ticket of this launch
+    for (auto& e : c->ev_p) if (!e) CT_CUDA(cudaEventCreate(&e));
+    if (p0 == 0) CT_CUDA(cudaEventRecord(c->ev_p[0], st));
     CT_CUDA(ctp::plane_tables(a, smem, st));
+    CT_CUDA(cudaEventRecord(c->ev_p[1], st));
+    c->plane_timed = 1;
     c->launches += 1;
     c->tb_planes = p1;
     return CT_OK;
@@ -254,7 +258,10 @@ int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, lon
     a.blocksum = U(c->g_blocksum); a.evflag = U(c->g_evflag); a.ev = c->g_ev.as<int32_t>(); a.lrec = c->g_lrec.as<int32_t>();
     a.out8 = ctl + 12;
     const double t_g0 = cti::now_ms();
+    for (auto& e : c->ev_p) if (!e) CT_CUDA(cudaEventCreate(&e));
+    CT_CUDA(cudaEventRecord(c->ev_p[2], st));
     CT_CUDA(ctp::global_phase(a, c->coop_grid, st));
+    CT_CUDA(cudaEventRecord(c->ev_p[3], st));
     c->launches += 1;
     // ---- control block + (speculatively) the first events and label records in one round trip ----
     constexpr long EV_FIRST = 32768, REC_FIRST = 8192;
@@ -270,6 +277,12 @@ int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, lon
     CT_CUDA(cudaEventRecord(c->ev[2], st));
     CT_CUDA(cudaStreamSynchronize(st));
     const double t_g1 = cti::now_ms();
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev_p[2], c->ev_p[3]) == cudaSuccess) c->stats["ms_global_kernel"] = ms;
+        if (c->plane_timed && cudaEventElapsedTime(&ms, c->ev_p[0], c->ev_p[1]) == cudaSuccess) c->stats["ms_plane_kernel"] = ms;
+        c->plane_timed = 0;
+    }
     const uint32_t status = hctl[1];
     const unsigned long long* tot = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(hctl) + 16);
     const uint32_t* out8 = hctl + 12;

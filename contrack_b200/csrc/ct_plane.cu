@@ -299,13 +299,12 @@ __global__ void __launch_bounds__(PLANE_THREADS) k_plane_tables(PlaneArgs a) {
     }
 
     // ---- chain 1: global base of this plane's runs / components / segments ----
-    if (tid < 32) {
+    if (tid < 32) {                                               // (two warps, two chains: the look-backs run side by side)
         const unsigned long long eA = lookback(chainA, slot, ((unsigned long long)nC << 31) | nS, lane, a.status);
+        if (lane == 0) { s_w[34] = (uint32_t)(eA >> 31); s_w[35] = (uint32_t)(eA & 0x7fffffffu); }
+    } else if (tid < 64) {
         const unsigned long long eR = lookback(chainR, slot, n_true, lane, a.status);
-        if (lane == 0) {
-            s_w[34] = (uint32_t)(eA >> 31); s_w[35] = (uint32_t)(eA & 0x7fffffffu);
-            s_w[36] = (uint32_t)eR; s_w[37] = (uint32_t)(eR >> 32);
-        }
+        if (lane == 0) { s_w[36] = (uint32_t)eR; s_w[37] = (uint32_t)(eR >> 32); }
     }
     __syncthreads();
     const uint32_t baseC = s_w[34], baseS = s_w[35];

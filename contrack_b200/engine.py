@@ -19,7 +19,7 @@ _STAT_KEYS = ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d',
               'd2h_bytes', 'host_sparse', 'host_threads', 'chunks', 'ms_h_chunks', 'ms_h_global', 'ms_g_sweeps', 'ms_g_link',
               'ms_g_labels_d2h', 'ms_tables_after_threshold', 'moved_comps', 'ms_lc_rows', 'ms_lc_tables_sums', 'lc_rows',
               'lc_rolled', 'ms_ht_init', 'ms_ht_events', 'ms_ht_persist', 'ht_walked', 'label_fast', 'slot_overflow', 'fast_path', 'plane_attempts', 'wavefront_planes',
-              'ms_g_kernel', 'event_segments', 'ms_h_tables') + tuple('ms_h_c%d' % i for i in range(8)) + tuple(
+              'ms_g_kernel', 'event_segments', 'ms_h_tables', 'shard_attempts', 'exchange_bytes', 'exchange_negotiated', 'ms_global_kernel', 'ms_plane_kernel') + tuple('ms_h_c%d' % i for i in range(8)) + tuple(
     'ms_t_' + k for k in ('row_scans', 'extract_runs', 'ccl_union', 'ccl_flatten', 'root_scan', 'comp_accumulate', 'seam_segs',
                           'class_sums', 'pairs_accumulate', 'pairs_csr'))
 
@@ -177,9 +177,10 @@ class Engine(object):
         return outd.cpu().numpy() if was_host else outd
 
     # ---- callers either side of the path (ct_extras.cu) -----------------------------------------------
-    def quantile_time(self, x, q, y0=0, y1=None):
-        """np.nanquantile(x[:, y0:y1, :], q, axis=0) ('linear') of a float32 cube (numpy or torch CUDA): float64
-        [len(q), y1-y0, W], same kind as x (README.rst:150-151)."""
+    def quantile_time(self, x, q, y0=0, y1=None, comm=None):
+        """np.nanquantile(x[:, y0:y1, :], q, axis=0) ('linear') of a float32 / float64 cube (numpy or torch CUDA): float64
+        [len(q), y1-y0, W], same kind as x (README.rst:150-151).  With `comm` (contrack_b200.sharded.Comm) x holds this
+        rank's time steps of a time-sharded cube and every rank receives the quantiles over ALL time steps (collective)."""
         import torch
         xd, was_host = self._to_device(x)
         T, H, W = (int(s) for s in xd.shape)
@@ -189,9 +190,10 @@ class Engine(object):
             raise ValueError('Quantiles must be in the range [0, 1]')
         out = torch.empty((len(qa), y1 - int(y0), W), dtype=torch.float64, device=xd.device)
         stream = torch.cuda.current_stream(xd.device).cuda_stream
-        _lib.check(self.lib.ct_quantile_time(self.handle, C.c_void_p(xd.data_ptr()), T, H, W, int(y0), y1,
-                                             _lib.ptr(qa, _lib._f64p), len(qa), C.c_void_p(out.data_ptr()),
-                                             C.c_void_p(stream)))
+        _lib.check(self.lib.ct_quantile_time_t(self.handle, comm.handle if comm is not None else None,
+                                               C.c_void_p(xd.data_ptr()), self._ct_dtype(xd), T, H, W, int(y0), y1,
+                                               _lib.ptr(qa, _lib._f64p), len(qa), C.c_void_p(out.data_ptr()),
+                                               C.c_void_p(stream)))
         return out.cpu().numpy() if was_host else out
 
     def flag_count(self, flag, greater_than=1):

@@ -113,6 +113,11 @@ def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, th
     return out, int(nfeat.value), engine.stats()
 
 
+def quantile_time_sharded(engine, x_local, q, y0=0, y1=None, comm=None, group=None):
+    """Quantiles over ALL time steps of a time-sharded cube (README.rst:150-151): collective, every rank gets the result."""
+    return engine.quantile_time(x_local, q, y0, y1, comm=comm if comm is not None else default_comm(engine, group))
+
+
 def run_local_group(engines, anom_parts, T_total, w, thresholds, thr_is_f32, op, overlap, persistence, twosided):
     """The sharded call on an in-process group: engines[r] plays rank r from its own host thread (the contexts may share one
     GPU).  Returns ([flag_r], n_features, [stats_r]).  Single-GPU tests and debugging."""

@@ -21,6 +21,7 @@ extern "C" {
 #endif
 
 typedef struct ct_ctx ct_ctx;
+typedef struct ct_comm ct_comm;     /* collectives of the time-sharded entry points, see ct_comm_init_nccl */
 
 enum ct_status {
     CT_OK = 0,
@@ -191,7 +192,6 @@ int ct_host_tables_fast(long T, int H, int W, const double* w_host, double overl
  * rank's flag planes are written (it synchronises once for the date-line events, like ct_run_contrack).
  * Runtime options of the context apply ("plane_kernel", "max_sweeps", ...); stats as for ct_run_contrack plus "exchange_bytes",
  * "shard_attempts". */
-typedef struct ct_comm ct_comm;
 int ct_nccl_unique_id(unsigned char id[128]);
 int ct_comm_init_nccl(const unsigned char id[128], int rank, int nranks, int device, ct_comm** out);
 int ct_comm_from_nccl(void* nccl_comm, int rank, int nranks, ct_comm** out);
@@ -258,6 +258,12 @@ int ct_calc_anom_t(ct_ctx* ctx, const void* z_dev, int dtype, long T, int H, int
  *                    nearest-neighbour index maps come from the caller (pandas Index.get_indexer, as xarray does) */
 int ct_quantile_time(ct_ctx* ctx, const float* x_dev, long T, int H, int W, int y0, int y1, const double* q_host, int nq,
                      double* out_dev, void* stream);
+/* ... for float32 or float64 cubes (dtype = ct_dtype; float64 in -> numpy's float64 arithmetic throughout) and, when `comm` is
+ * given, over ALL time steps of a time-sharded cube: x_dev holds this rank's T_local steps, the per-point tallies of the
+ * radix select are summed over the ranks between the passes (all-reduce), every rank receives the quantiles of the whole cube,
+ * bit-identical to np.nanquantile on the gathered cube.  Collective over `comm` (NULL: this rank alone). */
+int ct_quantile_time_t(ct_ctx* ctx, ct_comm* comm, const void* x_dev, int dtype, long T_local, int H, int W, int y0, int y1,
+                       const double* q_host, int nq, double* out_dev, void* stream);
 int ct_flag_count(ct_ctx* ctx, const int32_t* flag_dev, long T, int H, int W, int greater_than, int32_t* count_dev,
                   void* stream);
 int ct_divide_f32(ct_ctx* ctx, const float* in_dev, size_t n, float divisor, float* out_dev, void* stream);

@@ -62,6 +62,71 @@ def test_quantile_time_is_numpy_nanquantile_bit_for_bit(eng, T):
         eng.quantile_time(x, [1.5])
 
 
+def test_quantile_time_float64_input(eng):
+    """A float64 cube is ranked and interpolated in float64 (numpy keeps the input precision)."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((57, 5, 21)) * 100 + 1e-9 * rng.standard_normal((57, 5, 21))
+    x[rng.random(x.shape) < 0.1] = np.nan
+    x[:, 1, 2] = np.nan
+    x[:, 0, :4] = np.round(x[:, 0, :4] / 50) * 50
+    q = [0.0, 0.1, 0.5, 0.9, 1.0, 1 / 3]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = oracle.quantile_time(x, q)
+    got = eng.quantile_time(x, q)
+    assert got.dtype == np.float64 and np.array_equal(np.isnan(got), np.isnan(ref))
+    m = ~np.isnan(ref)
+    assert np.array_equal(got[m], ref[m])
+    assert not np.array_equal(got[m], oracle.quantile_time(x.astype(np.float32), q)[m])       # (float32 would differ)
+
+
+@pytest.mark.parametrize('parts,dtype', [((30, 21, 40), np.float32), ((1, 50, 40), np.float32), ((45, 46), np.float64)])
+def test_quantile_time_sharded_over_time_is_exact(parts, dtype):
+    """The cube split along time over several ranks (in-process group: one host thread and context per rank): the per-point
+    tallies are summed over the ranks between the passes, every rank gets np.nanquantile of the WHOLE cube bit for bit."""
+    import threading
+    import torch
+    from contrack_b200 import Engine
+    from contrack_b200.sharded import Comm
+    rng = np.random.default_rng(11)
+    T, H, W = sum(parts), 7, 33
+    x = (rng.standard_normal((T, H, W)) * 100).astype(dtype)
+    x[rng.random(x.shape) < 0.15] = np.nan
+    x[:parts[0], 3, 5] = np.nan                                            # a point with no valid value on the first rank
+    x[:, 4, 6] = np.nan
+    x[:, 0, :6] = np.round(x[:, 0, :6] / 50) * 50
+    q = [0.0, 0.1, 0.5, 0.9, 1.0, 1 / 3]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = oracle.quantile_time(x, q)[:, 1:6]
+    n = len(parts)
+    engines = [Engine(0) for _ in range(n)]
+    comms = Comm.local_group(n)
+    bounds = np.cumsum([0] + list(parts))
+    res, errs = [None] * n, [None] * n
+
+    def work(r):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                xd = torch.from_numpy(np.ascontiguousarray(x[bounds[r]:bounds[r + 1]])).cuda()
+                res[r] = engines[r].quantile_time(xd, q, 1, 6, comm=comms[r]).cpu().numpy()
+        except BaseException as e:                                         # noqa: BLE001
+            errs[r] = e
+    th = [threading.Thread(target=work, args=(r,)) for r in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for c in comms:
+        c.close()
+    for e in engines:
+        e.lib.ct_destroy(e.handle); e.handle = None
+    assert not any(errs), errs
+    m = ~np.isnan(ref)
+    for r in range(n):
+        assert np.array_equal(np.isnan(res[r]), np.isnan(ref)) and np.array_equal(res[r][m], ref[m]), r
+
+
 def test_quantile_threshold_recipe(eng):
     import torch
     T, H, W = 90, 91, 180

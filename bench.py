@@ -609,17 +609,16 @@ def main():
                              'table (12 B per run) and host threads expand it into the zero-filled host cube; wall clock '
                              'around the call'}
             d2h = int(s.get('d2h_bytes', Te * H * W * 4))
+            extra['checksum'] = '%016x' % (int(flag_checksum(torch.from_numpy(fout_np).cuda(), 0).item()) & 0xffffffffffffffff)
         else:
-            # every rank holds its shard of the Te-step cube in pinned host memory; per step: H2D of the shard, the sharded
-            # run, D2H of the shard's flag planes
-            dev_out = torch.empty((e_hi - e_lo, H, W), dtype=torch.int32, device='cuda')
+            # every rank holds its shard of the Te-step cube in pinned host memory and calls the host-buffer entry point: the
+            # shard streams through the GPU under the threshold kernel, the flag planes come back as a row-run table that host
+            # threads expand (ct_run_contrack_sharded_host)
+            xin_np, fout_np = xin.numpy(), fout.numpy()
 
             def e2e_step():
-                dev_in.copy_(xin, non_blocking=True)
-                _, n, _ = sharded.run_contrack_sharded(eng, dev_in, e_lo, Te, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE,
-                                                       TWOSIDED, out=dev_out, comm=comm)
-                fout.copy_(dev_out, non_blocking=True)
-                torch.cuda.synchronize()
+                _, n, _ = sharded.run_contrack_sharded(eng, xin_np, e_lo, Te, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE,
+                                                       TWOSIDED, out=fout_np, comm=comm)
                 return n
             e2e_step()
             barrier()
@@ -631,9 +630,18 @@ def main():
             t_dt = torch.tensor([dt], dtype=torch.float64, device='cuda')
             dist.all_reduce(t_dt, op=dist.ReduceOp.MAX)
             dt = float(t_dt.item())
-            extra = {'note': 'per rank: pinned host shard -> device, sharded run, flag shard -> pinned host; wall clock, '
-                             'max over ranks'}
-            d2h = Te * H * W * 4
+            s = eng.stats()
+            d2h_t = torch.tensor([float(s.get('d2h_bytes', 0.0))], dtype=torch.float64, device='cuda')
+            dist.all_reduce(d2h_t)
+            # parity of the host path: checksum of the flag planes that arrived on the hosts
+            cs_e = flag_checksum(torch.from_numpy(fout_np).cuda(), e_lo * H * W)
+            dist.all_reduce(cs_e)
+            extra = {'host_threads': int(s.get('host_threads', 0)), 'checksum': '%016x' % (int(cs_e.item()) & 0xffffffffffffffff),
+                     'note': 'ct_run_contrack_sharded_host per rank: pinned host shard in (chunked copies under the threshold '
+                             'kernel), flag planes out on the host as a row-run table expanded by host threads; wall clock, max '
+                             'over ranks; host memory bandwidth (reading the shards for PCIe, zeroing the results) is shared by '
+                             'all ranks of the box'}
+            d2h = int(d2h_t.item())
         if args.config != 3:
             line['e2e'] = dict({'value': Te * n_e2e / dt, 'unit': 'timesteps/s', 'h2d_bytes_per_step': Te * H * W * 4,
                                 'd2h_bytes_per_step': d2h, 'T': Te, 'steps': n_e2e, 'features': int(nf),

@@ -64,6 +64,8 @@ _PROTOS = {
     'ct_run_contrack_sharded': (C.c_int, [_p, _p, _p, C.c_int, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int, _f64p, _f64p,
                                           C.c_long, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _p, _longp, _p]),
     'ct_quantile_time': (C.c_int, [_p, _p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _p, _p]),
+    'ct_run_contrack_sharded_host': (C.c_int, [_p, _p, _p, C.c_int, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int, _f64p, _f64p,
+                                               C.c_long, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _p, _longp, C.c_long]),
     'ct_quantile_time_t': (C.c_int, [_p, _p, _p, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _p, _p]),
     'ct_flag_count': (C.c_int, [_p, _p, C.c_long, C.c_int, C.c_int, C.c_int, _p, _p]),
     'ct_divide_f32': (C.c_int, [_p, _p, C.c_size_t, C.c_float, _p, _p]),

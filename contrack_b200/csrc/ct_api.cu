@@ -25,6 +25,7 @@
 
 #include "ct_ctx.h"
 #include "ct_fast.h"
+#include "ct_internal.h"
 #include "ct_shard.h"
 
 namespace cta {
@@ -927,6 +928,59 @@ int launch_paint(ct_ctx* c, long t0, long nt, int32_t* flag_dev, int sparse, cud
 
 }  // namespace
 
+// ---- host side of the host-buffer entry points: zeroing and run expansion by host threads ----
+namespace cti {
+// zeroing threads: enough to finish under the host-to-device copy, few enough not to take host memory bandwidth away from it
+// (measured on a 16-core box: 4 threads leave the copy at its 55 GB/s but finish 65 ms late, 8 finish in time and slow the
+// copy to 51 GB/s); `share` = processes of this host doing the same at the same time (ranks of a sharded run)
+void api_host_zero_start(ct_ctx* c, int32_t* flag_host, size_t cells, int share, std::vector<std::thread>& threads) {
+    int nthreads = (int)(c->opt_host_zero_threads > 0 ? c->opt_host_zero_threads : c->opt_host_threads);
+    if (nthreads <= 0) {
+        const unsigned hc = std::thread::hardware_concurrency();
+        nthreads = hc >= 16 ? 6 : (hc >= 4 ? (int)hc / 2 : 1);
+        nthreads = std::max(1, nthreads / std::max(1, share) + (share > 1 ? 1 : 0));
+    }
+    const size_t per = ((cells + nthreads - 1) / nthreads + 1023) / 1024 * 1024;
+    for (int i = 0; i < nthreads; ++i) {
+        const size_t b = std::min(cells, per * i), e = std::min(cells, per * (i + 1));
+        if (e > b) threads.emplace_back([=] { memset(flag_host + b, 0, (e - b) * sizeof(int32_t)); });
+    }
+}
+// row-runs (x0 | x1 << 16, row, value) -> cells of flag_host; rows are shifted by -row_shift (rows below it are skipped: the
+// halo plane of a shard).  The painters are bound by cache / TLB misses on the 4 B/cell host cube (every run lands on another
+// page): all cores, and the destination of the run 16 ahead is prefetched while the current one is written.  Returns the
+// number of threads used.
+int api_host_expand_runs(ct_ctx* c, const uint32_t* h_x, const uint32_t* h_row, const int32_t* h_val, long R, long row_shift,
+                         int W, int32_t* flag_host) {
+    int npaint = (int)c->opt_host_threads;
+    if (npaint <= 0) npaint = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    const int np = (int)std::max(1L, std::min((long)npaint, R / 4096 + 1));
+    std::vector<std::thread> painters;
+    const long per = (R + np - 1) / np;
+    for (int i = 0; i < np; ++i) {
+        const long b = std::min(R, per * i), e = std::min(R, per * (i + 1));
+        if (e <= b) continue;
+        painters.emplace_back([=] {
+            constexpr long AHEAD = 16;
+            for (long r = b; r < e; ++r) {
+                if (r + AHEAD < e && h_val[r + AHEAD] != 0 && (long)h_row[r + AHEAD] >= row_shift) {
+                    const int32_t* p = flag_host + (size_t)((long)h_row[r + AHEAD] - row_shift) * W + (h_x[r + AHEAD] & 0xffff);
+                    __builtin_prefetch(p, 1, 0);
+                    __builtin_prefetch(p + 16, 1, 0);
+                }
+                const int32_t v = h_val[r];
+                if (v == 0 || (long)h_row[r] < row_shift) continue;
+                const uint32_t x = h_x[r];
+                int32_t* out = flag_host + (size_t)((long)h_row[r] - row_shift) * W;
+                for (uint32_t xx = x & 0xffff, x1 = x >> 16; xx < x1; ++xx) out[xx] = v;
+            }
+        });
+    }
+    for (auto& t : painters) t.join();
+    return np;
+}
+}  // namespace cti
+
 // ---- what the other translation units of the library use (ct_internal.h) ----
 namespace cti {
 int api_check_args(long T, int H, int W, const double* w_host, const double* thr_host, long thr_n, int in_dtype, int op) {
@@ -1004,13 +1058,14 @@ void ct_destroy(ct_ctx* c) {
                       &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml,
                       &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots, &c->x_q, &c->x_qscratch, &c->x_idx, &c->ovf_rows,
                       &c->pl_chain, &c->pl_done, &c->pl_ctl, &c->g_dirty, &c->g_blocksum, &c->g_evflag, &c->g_ev, &c->g_lrec, &c->g_patch,
-                      &c->sh_export, &c->sh_gathered, &c->sh_mdesc};
+                      &c->sh_export, &c->sh_gathered, &c->sh_mdesc, &c->sh_lastplane};
     for (DevBuf* b : bufs) b->release();
     c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release(); c->hp_desc.release();
     c->hp_ctl.release(); c->hp_ev.release(); c->hp_ev2.release(); c->hp_patch.release(); c->hp_hdr.release();
     for (auto& e : c->ev_x) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_p) if (e) cudaEventDestroy(e);
     if (c->gctx) ct_destroy(c->gctx);
+    if (c->host_stream) cudaStreamDestroy(c->host_stream);
     for (auto& e : c->ev_side) if (e) cudaEventDestroy(e);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     for (auto& e : c->ev_tbl) if (e) cudaEventDestroy(e);
@@ -1199,23 +1254,9 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
     // dense cube (4 B/cell) the result travels back as the row-run table (12 B per run, ~1 % of the dense bytes) and host
     // threads expand it into `flag_host`, which they zero-fill while the input chunks are still streaming in.
     const size_t cells = (size_t)T * plane;
-    // zeroing threads: enough to finish under the host-to-device copy, few enough not to take host memory bandwidth away
-    // from it (measured on a 16-core box: 4 threads leave the copy at its 55 GB/s but finish 65 ms late, 8 finish in time
-    // and slow the copy to 51 GB/s)
-    int nthreads = (int)(c->opt_host_zero_threads > 0 ? c->opt_host_zero_threads : c->opt_host_threads);
-    if (nthreads <= 0) {
-        const unsigned hc = std::thread::hardware_concurrency();
-        nthreads = hc >= 16 ? 6 : (hc >= 4 ? (int)hc / 2 : 1);
-    }
     const bool want_sparse = c->opt_host_sparse != 0;
     std::vector<std::thread> zero_threads;
-    if (want_sparse && !c->opt_host_out_zeroed) {
-        const size_t per = ((cells + nthreads - 1) / nthreads + 1023) / 1024 * 1024;
-        for (int i = 0; i < nthreads; ++i) {
-            const size_t b = std::min(cells, per * i), e = std::min(cells, per * (i + 1));
-            if (e > b) zero_threads.emplace_back([=] { memset(flag_host + b, 0, (e - b) * sizeof(int32_t)); });
-        }
-    }
+    if (want_sparse && !c->opt_host_out_zeroed) cti::api_host_zero_start(c, flag_host, cells, 1, zero_threads);
     struct Joiner {
         std::vector<std::thread>& v;
         ~Joiner() { for (auto& t : v) if (t.joinable()) t.join(); }
@@ -1262,33 +1303,7 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
         zero_threads.clear();
         CT_CUDA(cudaStreamSynchronize(ws));
         d2h_bytes = (size_t)R * 12;
-        // the painters are bound by cache / TLB misses on the 4 B/cell host cube (every run lands on another page): all
-        // cores, and the destination of the run 16 ahead is prefetched while the current one is written
-        int npaint = (int)c->opt_host_threads;
-        if (npaint <= 0) npaint = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
-        const int np = (int)std::max(1L, std::min((long)npaint, R / 4096 + 1));
-        std::vector<std::thread> painters;
-        const long per = (R + np - 1) / np;
-        for (int i = 0; i < np; ++i) {
-            const long b = std::min(R, per * i), e = std::min(R, per * (i + 1));
-            if (e <= b) continue;
-            painters.emplace_back([=] {
-                constexpr long AHEAD = 16;
-                for (long r = b; r < e; ++r) {
-                    if (r + AHEAD < e && h_val[r + AHEAD] != 0) {
-                        const int32_t* p = flag_host + (size_t)h_row[r + AHEAD] * W + (h_x[r + AHEAD] & 0xffff);
-                        __builtin_prefetch(p, 1, 0);
-                        __builtin_prefetch(p + 16, 1, 0);
-                    }
-                    const int32_t v = h_val[r];
-                    if (v == 0) continue;
-                    const uint32_t x = h_x[r];
-                    int32_t* out = flag_host + (size_t)h_row[r] * W;
-                    for (uint32_t xx = x & 0xffff, x1 = x >> 16; xx < x1; ++xx) out[xx] = v;
-                }
-            });
-        }
-        for (auto& t : painters) t.join();
+        const int np = cti::api_host_expand_runs(c, h_x, h_row, h_val, R, 0, W, flag_host);
         for (const ctb::Override& o : c->host_result.overrides) {  // pieces of components split at a stale box
             int32_t* out = flag_host + ((size_t)o.t * H + o.y) * W;
             for (int xx = o.x0; xx < o.x1; ++xx) out[xx] = o.val;

@@ -194,6 +194,8 @@ struct ct_ctx {
     // ---- time-sharded run (ct_dist.cu) ----
     ct_ctx* gctx = nullptr;                  // the merged global tables live in a second context on the same device (owned)
     DevBuf sh_export, sh_gathered, sh_mdesc; // packed tables of this rank / of all ranks, per-rank descriptors
+    DevBuf sh_lastplane;                     // host-buffer variant: staging of the shard's last plane
+    cudaStream_t host_stream = nullptr;      // ... and the stream it runs on
     PinBuf hp_hdr;
     long sh_capC = 0, sh_capP = 0, sh_capS = 0;   // negotiated per-rank capacities of the table exchange (0 = not yet)
     cudaEvent_t ev_x[2] = {nullptr, nullptr};

@@ -15,6 +15,7 @@
 // The host synchronises once (control block + date-line events), exactly like the single-GPU call.  The collectives go
 // through ctc::Comm (ct_comm.h): NCCL over NVLink in production, an in-process group on single-GPU test boxes.
 #include <cstring>
+#include <thread>
 
 #include "ct_comm.h"
 #include "ct_extras.h"
@@ -357,16 +358,23 @@ int ct_quantile_time_t(ct_ctx* c, ct_comm* comm_h, const void* x_dev, int dtype,
 }
 
 // ---- the sharded run ----------------------------------------------------------------------------------------------------
-int ct_run_contrack_sharded(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, int in_dtype, long T_local, long t_begin,
-                            long T_total, int H, int W, const double* w_host, const double* thr_host, long thr_n,
-                            int thr_is_f32, int op, double overlap, int persistence, int twosided, int32_t* flag_dev,
-                            long* n_features, void* stream) {
+}  // extern "C"
+
+// Device buffers (anom_dev / flag_dev) or host buffers (anom_host / flag_host): with host buffers the shard is streamed in
+// time chunks host -> device under the threshold kernel (the float shard is never resident) and the result leaves as the
+// row-run table, expanded by host threads into flag_host, which they zero while the input streams in.
+static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const void* anom_host, int in_dtype, long T_local,
+                       long t_begin, long T_total, int H, int W, const double* w_host, const double* thr_host, long thr_n,
+                       int thr_is_f32, int op, double overlap, int persistence, int twosided, int32_t* flag_dev,
+                       int32_t* flag_host, long chunk_planes, long* n_features, void* stream) {
     if (!c || !comm_h || !comm_h->impl) return fail(CT_ERR_ARG, "null context / communicator");
+    const bool host_io = anom_host != nullptr;
     ctc::Comm* comm = comm_h->impl;
     const int rank = comm->rank(), nranks = comm->size();
     int rc = cti::api_check_args(T_local, H, W, w_host, thr_host, thr_n, in_dtype, op);
     if (rc != CT_OK) return rc;
-    if (T_local <= 0 || !anom_dev || !flag_dev) return fail(CT_ERR_ARG, "a rank needs at least one plane and both cubes");
+    if (T_local <= 0 || (host_io ? (!anom_host || !flag_host) : (!anom_dev || !flag_dev)))
+        return fail(CT_ERR_ARG, "a rank needs at least one plane and both cubes");
     if (t_begin < 0 || t_begin + T_local > T_total) return fail(CT_ERR_ARG, "planes [%ld, %ld) outside the cube of %ld", t_begin,
                                                                 t_begin + T_local, T_total);
     if (n_features) *n_features = 0;
@@ -397,9 +405,27 @@ int ct_run_contrack_sharded(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, in
     const double t_h0 = cti::now_ms();
 
     // ---- 1. last own plane first; its bit rows travel to the next rank while the other planes are thresholded ----
+    std::vector<std::thread> zero_threads;
+    struct Joiner {
+        std::vector<std::thread>& v;
+        ~Joiner() { for (auto& t : v) if (t.joinable()) t.join(); }
+    } joiner{zero_threads};
+    const size_t cells = (size_t)T_local * H * W;
+    if (host_io) {
+        if (!c->work_stream) CT_CUDA(cudaStreamCreateWithFlags(&c->work_stream, cudaStreamNonBlocking));
+        if (!c->opt_host_out_zeroed) cti::api_host_zero_start(c, flag_host, cells, nranks, zero_threads);
+        CT_CUDA(c->sh_lastplane.ensure(plane_bytes));
+    }
     CT_CUDA(cudaEventRecord(c->ev[0], st));
-    if ((rc = cti::api_launch_threshold(c, (const char*)anom_dev + (size_t)(T_local - 1) * plane_bytes, in_dtype, planes - 1, 1,
-                                        (long)thr.size(), thr_is_f32, op, st, 1)) != CT_OK) return rc;
+    {
+        const void* last = (const char*)(host_io ? anom_host : anom_dev) + (size_t)(T_local - 1) * plane_bytes;
+        if (host_io) {
+            CT_CUDA(cudaMemcpyAsync(c->sh_lastplane.p, last, plane_bytes, cudaMemcpyHostToDevice, st));
+            last = c->sh_lastplane.p;
+        }
+        if ((rc = cti::api_launch_threshold(c, last, in_dtype, planes - 1, 1, (long)thr.size(), thr_is_f32, op, st, 1)) != CT_OK)
+            return rc;
+    }
     CT_CUDA(cudaEventRecord(c->ev_x[0], st));
     CT_CUDA(cudaStreamWaitEvent(aux, c->ev_x[0], 0));
     if (nranks > 1) {
@@ -414,17 +440,46 @@ int ct_run_contrack_sharded(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, in
         c->launches += 1;
     }
     CT_CUDA(cudaEventRecord(c->ev_x[1], aux));
-    if (T_local > 1) {
+    if (T_local > 1 && !host_io) {
         if ((rc = cti::api_launch_threshold(c, anom_dev, in_dtype, hp, T_local - 1, (long)thr.size(), thr_is_f32, op, st, 0)) != CT_OK)
             return rc;
+    } else if (T_local > 1) {
+        // host shard: copy chunk k + 1 while chunk k is thresholded (two staging buffers)
+        const long Tm = T_local - 1;
+        if (chunk_planes <= 0) chunk_planes = std::max<long>(1, (long)((256u << 20) / plane_bytes));
+        chunk_planes = std::min(chunk_planes, Tm);
+        const long nchunks = (Tm + chunk_planes - 1) / chunk_planes;
+        cudaStream_t cs = c->work_stream;
+        cudaEvent_t in_ready[2], in_free[2];
+        for (int i = 0; i < 2; ++i) {
+            CT_CUDA(cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming));
+            CT_CUDA(cudaEventCreateWithFlags(&in_free[i], cudaEventDisableTiming));
+            CT_CUDA(c->chunk_in[i].ensure((size_t)chunk_planes * plane_bytes));
+        }
+        CT_CUDA(cudaStreamWaitEvent(cs, c->ev_x[0], 0));                 // (orders the copies after whatever `st` did before)
+        for (long k = 0; k < nchunks; ++k) {
+            const int b = (int)(k & 1);
+            const long t0 = k * chunk_planes, nt = std::min(chunk_planes, Tm - t0);
+            if (k >= 2) CT_CUDA(cudaStreamWaitEvent(cs, in_free[b], 0));
+            CT_CUDA(cudaMemcpyAsync(c->chunk_in[b].p, (const char*)anom_host + (size_t)t0 * plane_bytes, (size_t)nt * plane_bytes,
+                                    cudaMemcpyHostToDevice, cs));
+            CT_CUDA(cudaEventRecord(in_ready[b], cs));
+            CT_CUDA(cudaStreamWaitEvent(st, in_ready[b], 0));
+            if ((rc = cti::api_launch_threshold(c, c->chunk_in[b].p, in_dtype, hp + t0, nt, (long)thr.size(), thr_is_f32, op, st, 0)) != CT_OK)
+                return rc;
+            CT_CUDA(cudaEventRecord(in_free[b], st));
+        }
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(in_ready[i]); cudaEventDestroy(in_free[i]); }
     }
     CT_CUDA(cudaEventRecord(c->ev[1], st));
     // ---- zero fill of the own flag planes on the low-priority stream, beside everything that follows ----
     CT_CUDA(cudaEventRecord(c->ev_side[0], st));
     CT_CUDA(cudaStreamWaitEvent(side, c->ev_side[0], 0));
-    CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_local * H * W, c->sm_count, side));
+    if (!host_io) {
+        CT_CUDA(ctk::zero_fill(flag_dev, cells, c->sm_count, side));
+        c->launches += 1;
+    }
     CT_CUDA(cudaEventRecord(c->ev_side[1], side));
-    c->launches += 1;
     CT_CUDA(cudaStreamWaitEvent(ts, c->ev_side[0], 0));
     CT_CUDA(cudaStreamWaitEvent(ts, c->ev_x[1], 0));
 
@@ -584,7 +639,7 @@ int ct_run_contrack_sharded(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, in
     CT_CUDA(cudaStreamWaitEvent(st, c->ev_tbl[0], 0));
     CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
     CT_CUDA(cudaEventRecord(c->ev[3], st));
-    {
+    if (!host_io) {
         ctk::PaintArgs a;
         const long r0 = (long)hp * H;
         a.bits = nullptr; a.row_ptr = c->row_ptr.as<uint32_t>() + r0; a.run_val = nullptr;
@@ -593,22 +648,48 @@ int ct_run_contrack_sharded(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, in
         a.run_comp = c->run_comp.as<uint32_t>(); a.comp_val = g->c_val.as<int32_t>() + comp_off;
         CT_CUDA(ctk::paint(a, c->sm_count, st));
         c->launches += 1;
-    }
-    if (!ovr.empty()) {
-        const long novr = (long)ovr.size();
-        CT_CUDA(c->hp_ovr.ensure((size_t)novr * 5 * 4));
-        int32_t* ho = c->hp_ovr.as<int32_t>();
-        for (long i = 0; i < novr; ++i) {
-            ho[i] = ovr[i].t; ho[novr + i] = ovr[i].y; ho[2 * novr + i] = ovr[i].x0; ho[3 * novr + i] = ovr[i].x1; ho[4 * novr + i] = ovr[i].val;
+        if (!ovr.empty()) {
+            const long novr = (long)ovr.size();
+            CT_CUDA(c->hp_ovr.ensure((size_t)novr * 5 * 4));
+            int32_t* ho = c->hp_ovr.as<int32_t>();
+            for (long i = 0; i < novr; ++i) {
+                ho[i] = ovr[i].t; ho[novr + i] = ovr[i].y; ho[2 * novr + i] = ovr[i].x0; ho[3 * novr + i] = ovr[i].x1; ho[4 * novr + i] = ovr[i].val;
+            }
+            DevBuf* ob5[] = {&c->o_t, &c->o_y, &c->o_x0, &c->o_x1, &c->o_val};
+            for (int k = 0; k < 5; ++k) {
+                CT_CUDA(ob5[k]->ensure((size_t)novr * 4));
+                CT_CUDA(cudaMemcpyAsync(ob5[k]->p, ho + (size_t)k * novr, (size_t)novr * 4, cudaMemcpyHostToDevice, st));
+            }
+            CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(), c->o_x1.as<int32_t>(),
+                                         c->o_val.as<int32_t>(), novr, H, W, 0, T_local, flag_dev, st));
+            c->launches += 1;
         }
-        DevBuf* ob5[] = {&c->o_t, &c->o_y, &c->o_x0, &c->o_x1, &c->o_val};
-        for (int k = 0; k < 5; ++k) {
-            CT_CUDA(ob5[k]->ensure((size_t)novr * 4));
-            CT_CUDA(cudaMemcpyAsync(ob5[k]->p, ho + (size_t)k * novr, (size_t)novr * 4, cudaMemcpyHostToDevice, st));
-        }
-        CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(), c->o_x1.as<int32_t>(),
-                                     c->o_val.as<int32_t>(), novr, H, W, 0, T_local, flag_dev, st));
+    } else {
+        // ---- the result leaves as the row-run table (12 B per run); host threads expand the surviving runs ----
+        const long R = c->nruns;
+        CT_CUDA(c->run_val.ensure((size_t)(R + 1) * 4));
+        CT_CUDA(ctk::run_values(c->run_comp.as<uint32_t>(), g->c_val.as<int32_t>() + comp_off, c->run_val.as<int32_t>(), R, st));
         c->launches += 1;
+        CT_CUDA(c->hp_runs.ensure((size_t)(R + 1) * 12));
+        uint32_t* h_x = c->hp_runs.as<uint32_t>();
+        uint32_t* h_row = h_x + R;
+        int32_t* h_val = reinterpret_cast<int32_t*>(h_row + R);
+        if (R) {
+            CT_CUDA(cudaMemcpyAsync(h_x, c->run_x.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+            CT_CUDA(cudaMemcpyAsync(h_row, c->run_row.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+            CT_CUDA(cudaMemcpyAsync(h_val, c->run_val.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+        }
+        for (auto& t : zero_threads) t.join();
+        zero_threads.clear();
+        CT_CUDA(cudaStreamSynchronize(st));
+        const int np = cti::api_host_expand_runs(c, h_x, h_row, h_val, R, (long)hp * H, W, flag_host);
+        for (const ctb::Override& o : ovr) {                           // pieces of components split at a stale box
+            int32_t* out = flag_host + ((size_t)o.t * H + o.y) * W;
+            for (int xx = o.x0; xx < o.x1; ++xx) out[xx] = o.val;
+        }
+        c->stats["host_threads"] = (double)np;
+        c->stats["h2d_bytes"] = (double)((size_t)T_local * plane_bytes);
+        c->stats["d2h_bytes"] = (double)((size_t)R * 12);
     }
     CT_CUDA(cudaEventRecord(c->ev[4], st));
     CT_CUDA(cudaStreamSynchronize(st));
@@ -619,6 +700,8 @@ int ct_run_contrack_sharded(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, in
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats["ms_total"] = ms;
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev_side[0], c->ev_side[1])); c->stats["ms_zero_fill"] = ms;
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev_tbl[0])); c->stats["ms_tables_after_threshold"] = ms;
+    if (c->plane_timed && cudaEventElapsedTime(&ms, c->ev_p[0], c->ev_p[1]) == cudaSuccess) c->stats["ms_plane_kernel"] = ms;
+    c->plane_timed = 0;
     c->stats["kernel_launches"] = (double)(c->launches + g->launches);
     c->stats["runs"] = (double)c->nruns; c->stats["comps2d"] = (double)c->ncomp;
     c->stats["exchange_bytes"] = (double)((HDR_BYTES + [&] { size_t off[cts::A_COUNT]; return cts::layout(c->sh_capC, c->sh_capP, c->sh_capS, off); }() + 255) / 256 * 256);
@@ -627,6 +710,29 @@ int ct_run_contrack_sharded(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, in
         if (g->stats.count(k)) c->stats[k] = g->stats[k];
     c->stats["fast_path"] = outcome == ctf::FAST_OK ? (classic ? 0.5 : 1.0) : 0.25;
     return CT_OK;
+}
+
+extern "C" {
+
+int ct_run_contrack_sharded(ct_ctx* c, ct_comm* comm, const void* anom_dev, int in_dtype, long T_local, long t_begin,
+                            long T_total, int H, int W, const double* w_host, const double* thr_host, long thr_n,
+                            int thr_is_f32, int op, double overlap, int persistence, int twosided, int32_t* flag_dev,
+                            long* n_features, void* stream) {
+    if (!anom_dev || !flag_dev) return fail(CT_ERR_ARG, "null device pointer");
+    return sharded_run(c, comm, anom_dev, nullptr, in_dtype, T_local, t_begin, T_total, H, W, w_host, thr_host, thr_n, thr_is_f32,
+                       op, overlap, persistence, twosided, flag_dev, nullptr, 0, n_features, stream);
+}
+
+int ct_run_contrack_sharded_host(ct_ctx* c, ct_comm* comm, const void* anom_host, int in_dtype, long T_local, long t_begin,
+                                 long T_total, int H, int W, const double* w_host, const double* thr_host, long thr_n,
+                                 int thr_is_f32, int op, double overlap, int persistence, int twosided, int32_t* flag_host,
+                                 long* n_features, long chunk_planes) {
+    if (!anom_host || !flag_host) return fail(CT_ERR_ARG, "null host pointer");
+    if (!c) return fail(CT_ERR_ARG, "null context");
+    CT_CUDA(cudaSetDevice(c->device));
+    if (!c->host_stream) CT_CUDA(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
+    return sharded_run(c, comm, nullptr, anom_host, in_dtype, T_local, t_begin, T_total, H, W, w_host, thr_host, thr_n, thr_is_f32,
+                       op, overlap, persistence, twosided, nullptr, flag_host, chunk_planes, n_features, c->host_stream);
 }
 
 }  // extern "C"

@@ -1,5 +1,7 @@
 // ct_internal.h -- pieces of ct_api.cu the other translation units of the library build on (the time-sharded drivers).
 #pragma once
+#include <thread>
+
 #include "ct_ctx.h"
 
 namespace cti {
@@ -15,4 +17,8 @@ int api_ensure_streams(ct_ctx* c);
 int api_table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int stage, long* n_features, cudaStream_t st);
 int api_classic_tables(ct_ctx* c, cudaStream_t st);
 bool api_plane_runs(ct_ctx* c, long plane, std::vector<cth::PlaneRun>& out, cudaStream_t st);
+// host side of the host-buffer entry points (zeroing threads, expansion of the row-run table into the host cube)
+void api_host_zero_start(ct_ctx* c, int32_t* flag_host, size_t cells, int share, std::vector<std::thread>& threads);
+int api_host_expand_runs(ct_ctx* c, const uint32_t* h_x, const uint32_t* h_row, const int32_t* h_val, long R, long row_shift,
+                         int W, int32_t* flag_host);
 }  // namespace cti

@@ -88,11 +88,27 @@ def default_comm(engine, group=None):
 def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, thr_is_f32, op, overlap, persistence,
                          twosided, out=None, comm=None, group=None):
     """Collective over ``comm`` (default: an NCCL communicator over the torch.distributed world / ``group``).
-    anom_local: torch CUDA tensor [T_local, H, W] holding planes [t_begin, t_begin + T_local) of the cube; ``thresholds``:
-    one value or T_local values (the local slice).  Returns (flag_local int32 CUDA tensor, n_features, info dict)."""
-    import torch
+    anom_local: torch CUDA tensor (device resident) or numpy array (host buffers, ideally page-locked) [T_local, H, W] holding
+    planes [t_begin, t_begin + T_local) of the cube; ``thresholds``: one value or T_local values (the local slice).  Returns
+    (flag_local int32, same kind as the input; n_features; stats dict)."""
     if comm is None:
         comm = default_comm(engine, group)
+    w = np.ascontiguousarray(w, np.float64)
+    thr = np.ascontiguousarray(np.atleast_1d(thresholds), np.float64)
+    nfeat = C.c_long(0)
+    if isinstance(anom_local, np.ndarray):
+        # host buffers: the shard streams through the GPU, the flag planes come back as a row-run table (see the header)
+        a = anom_local if anom_local.dtype in (np.float32, np.float64) else anom_local.astype(np.float64)
+        a = np.ascontiguousarray(a)
+        Tl, H, W = (int(s) for s in a.shape)
+        if out is None:
+            out = np.empty((Tl, H, W), np.int32)
+        _lib.check(engine.lib.ct_run_contrack_sharded_host(
+            engine.handle, comm.handle, C.c_void_p(a.ctypes.data), _lib.CT_F32 if a.dtype == np.float32 else _lib.CT_F64, Tl,
+            int(t_begin), int(T_total), H, W, _lib.ptr(w, _lib._f64p), _lib.ptr(thr, _lib._f64p), len(thr), int(thr_is_f32),
+            int(op), float(overlap), int(persistence), int(bool(twosided)), C.c_void_p(out.ctypes.data), C.byref(nfeat), 0))
+        return out, int(nfeat.value), engine.stats()
+    import torch
     x = anom_local if anom_local.is_contiguous() else anom_local.contiguous()
     if not x.is_cuda or x.device.index != engine.device:
         raise ValueError('the shard must live on cuda:%d' % engine.device)
@@ -102,9 +118,6 @@ def run_contrack_sharded(engine, anom_local, t_begin, T_total, w, thresholds, th
     Tl, H, W = (int(s) for s in x.shape)
     if out is None:
         out = torch.empty((Tl, H, W), dtype=torch.int32, device=x.device)
-    w = np.ascontiguousarray(w, np.float64)
-    thr = np.ascontiguousarray(np.atleast_1d(thresholds), np.float64)
-    nfeat = C.c_long(0)
     stream = torch.cuda.current_stream(x.device).cuda_stream
     _lib.check(engine.lib.ct_run_contrack_sharded(
         engine.handle, comm.handle, C.c_void_p(x.data_ptr()), dt, Tl, int(t_begin), int(T_total), H, W,

@@ -203,6 +203,15 @@ int ct_run_contrack_sharded(ct_ctx* ctx, ct_comm* comm, const void* anom_dev, in
                             long T_total, int H, int W, const double* w_host, const double* thr_host, long thr_n,
                             int thr_is_f32, int op, double overlap, int persistence, int twosided, int32_t* flag_dev,
                             long* n_features, void* stream);
+/* The same collective with HOST buffers (this rank's planes in anom_host, its flag planes out in flag_host; page-locked memory
+ * for full PCIe rate): the shard streams host -> device in time chunks under the threshold kernel, the result leaves as the
+ * row-run table (12 B per run) and host threads expand the surviving runs into flag_host, which they zero while the input is
+ * streaming in -- see ct_run_contrack_host.  With N ranks on one host the N PCIe links work in parallel; host memory bandwidth
+ * (reading the shards, zeroing the results) is the shared bound.  Stats "h2d_bytes" / "d2h_bytes" as for ct_run_contrack_host. */
+int ct_run_contrack_sharded_host(ct_ctx* ctx, ct_comm* comm, const void* anom_host, int in_dtype, long T_local, long t_begin,
+                                 long T_total, int H, int W, const double* w_host, const double* thr_host, long thr_n,
+                                 int thr_is_f32, int op, double overlap, int persistence, int twosided, int32_t* flag_host,
+                                 long* n_features, long chunk_planes);
 
 /* ---- run_lifecycle, contrack.py:799-907 -------------------------------------------------------------------------------
  * flag_dev [T,H,W] int32 (ds[flag]), var_dev [T,H,W] float32/float64 (ds[variable]), w_host [H] the float32-valued area

@@ -16,8 +16,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_local(x, w, parts, thr, gorl, ov, pers, two, opts=None, f32=True, engines=None):
-    """x split into len(parts) time shards, one in-process rank each.  Returns (flag cube, features, [stats])."""
+def run_local(x, w, parts, thr, gorl, ov, pers, two, opts=None, f32=True, engines=None, host=False):
+    """x split into len(parts) time shards, one in-process rank each (host=True: host buffers through
+    ct_run_contrack_sharded_host).  Returns (flag cube, features, [stats])."""
     import torch
     from contrack_b200 import Engine, sharded
     from contrack_b200._lib import GORL_TO_OP
@@ -29,10 +30,12 @@ def run_local(x, w, parts, thr, gorl, ov, pers, two, opts=None, f32=True, engine
             for e in engines:
                 e.set_option(k, v)
         bounds = np.cumsum([0] + list(parts))
-        xs = [torch.from_numpy(np.ascontiguousarray(x[a:b])).cuda() for a, b in zip(bounds[:-1], bounds[1:])]
+        xs = [np.ascontiguousarray(x[a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
+        if not host:
+            xs = [torch.from_numpy(a).cuda() for a in xs]
         outs, n, stats = sharded.run_local_group(engines, xs, x.shape[0], w, thr, f32, GORL_TO_OP[gorl], ov, pers, two)
         torch.cuda.synchronize()
-        return np.concatenate([o.cpu().numpy() for o in outs]), n, stats
+        return np.concatenate([o if host else o.cpu().numpy() for o in outs]), n, stats
     finally:
         if own:
             for e in engines:
@@ -149,6 +152,24 @@ def test_sharded_empty_shards(fixture_cube):
     x[:] = 1000.0                                     # one component per plane covering everything
     f, n, _ = run_local(x, w, (6, 5), 150, '>=', 0.5, 2, True)
     assert np.array_equal(f, oracle.run_contrack(x, lat, lon, 150, '>=', 0.5, 2, True))
+
+
+@pytest.mark.parametrize('parts', [(6, 5), (4, 3, 4), (1, 9, 1)])
+def test_sharded_host_buffers(fixture_cube, reference_run, parts):
+    """Host shards in, host flag planes out (sparse run-table export per rank), incl. a float64 cube and a stale-box cube."""
+    a, lat, lon = fixture_cube
+    w = row_weights(lat, lon)
+    for r in reference_run['fixture'][:2]:
+        f, n, st = run_local(a, w, parts, r['threshold'], r['gorl'], r['overlap'], r['persistence'], r['twosided'], host=True)
+        assert sha_i4(f) == r['sha256'] and n == len(r['ids']), (parts, r['key'])
+        assert st[0]['d2h_bytes'] < 0.1 * a[:parts[0]].size * 4
+    ref = oracle.run_contrack(a.astype(np.float64), lat, lon, 150, '>=', 0.5, 5, True)
+    f, n, _ = run_local(a.astype(np.float64), w, parts, 150, '>=', 0.5, 5, True, host=True)
+    assert np.array_equal(f, ref)
+    lat2, lon2 = regular_grid(24, 16)
+    x = synth_cube(1396, 12, 24, 16, (1.5, 2, 2))
+    f, _, _ = run_local(x, row_weights(lat2, lon2), (5, 4, 3), 60, '>=', 0.0, 1, False, host=True)
+    assert np.array_equal(f, oracle.track_persistence((x >= 60).astype(int), 1))
 
 
 def test_sharded_per_timestep_thresholds(fixture_cube):

@@ -1091,9 +1091,8 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "host_threads")) { c->opt_host_threads = value; return CT_OK; }
     if (!strcmp(key, "host_zero_threads")) { c->opt_host_zero_threads = value; return CT_OK; }
     if (!strcmp(key, "host_out_zeroed")) { c->opt_host_out_zeroed = value; return CT_OK; }
-    if (!strcmp(key, "fill_split")) { c->opt_fill_split = value < 1 ? 1 : value > 100 ? 100 : value; return CT_OK; }
-    if (!strcmp(key, "shard_fill_defer_ms")) { c->opt_shard_fill_defer_ms = value; return CT_OK; }
-    if (!strcmp(key, "shard_fill_late")) { c->opt_shard_fill_late = value; return CT_OK; }
+    if (!strcmp(key, "fill_late")) { c->opt_fill_late = value; return CT_OK; }
+    if (!strcmp(key, "fill_ctas")) { c->opt_fill_ctas = value; return CT_OK; }
     if (!strcmp(key, "fused_runs")) { c->opt_fused_runs = value; return CT_OK; }
     if (!strcmp(key, "label_fast")) { c->opt_label_fast = value; return CT_OK; }
     if (!strcmp(key, "profile_tables")) { c->opt_profile_tables = value; return CT_OK; }
@@ -1154,22 +1153,21 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
         if (sparse) CT_CUDA(cudaEventRecord(c->ev_chunk[k], st));
     }
     CT_CUDA(cudaEventRecord(c->ev[1], st));
-    // The zero fill is split in two launches: the sparse paint of the first part can start as soon as the values are known
-    // and runs beside the fill of the second part (the paint is bound by latency, the fill by bandwidth).
-    const long T_a = sparse ? std::min<long>(T, std::max<long>(1, (T * c->opt_fill_split) / 100)) : T;
+    // Zero fill of the flag cube on the low-priority stream.  Beside the plane kernel both slow down (the fill saturates HBM,
+    // the plane kernel lives on memory latency): with "fill_late" the fill starts when the plane kernel has finished and runs
+    // beside the global kernel and the host replay instead.
+    const bool fill_late = sparse && fast && c->opt_fill_late;
+    c->pend_fill = nullptr; c->pend_fill_cells = 0;
     if (sparse) {
-        const size_t plane_cells = (size_t)H * W;
         CT_CUDA(cudaEventRecord(c->ev_side[0], st));
-        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-        CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T_a * plane_cells, c->sm_count, c->side_stream));
-        CT_CUDA(cudaEventRecord(c->ev_tbl[1], c->side_stream));
-        c->launches += 1;
-        if (T_a < T) {
-            CT_CUDA(ctk::zero_fill(flag_dev + (size_t)T_a * plane_cells, (size_t)(T - T_a) * plane_cells, c->sm_count,
-                                   c->side_stream));
+        if (fill_late) {
+            c->pend_fill = flag_dev; c->pend_fill_cells = (size_t)T * H * W;      // enqueued by ctf::finish()
+        } else {
+            CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+            CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T * H * W, c->sm_count, c->side_stream, (int)c->opt_fill_ctas));
+            CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
             c->launches += 1;
         }
-        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
     }
     const double t_h0 = now_ms();
     auto wait_chunk = [&](long k) -> int {
@@ -1186,18 +1184,19 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     c->stats["chunks"] = (double)nchunk;
     c->stats["ms_h_tables"] = t_h1 - t_h0;                           // host wall clock of the table phase (ends in a sync)
     if (sparse) {
+        if (c->pend_fill) {                                            // (the tables came from the fallback path: fill now)
+            CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+            CT_CUDA(ctk::zero_fill(c->pend_fill, c->pend_fill_cells, c->sm_count, c->side_stream, (int)c->opt_fill_ctas));
+            CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+            c->launches += 1;
+            c->pend_fill = nullptr;
+        }
         CT_CUDA(cudaEventRecord(c->ev_tbl[0], ts));
         CT_CUDA(cudaStreamWaitEvent(st, c->ev_tbl[0], 0));
-        CT_CUDA(cudaStreamWaitEvent(st, c->ev_tbl[1], 0));           // first part of the cube is zero
+        CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));          // the cube is zero
     }
     CT_CUDA(cudaEventRecord(c->ev[3], st));
-    if ((rc = launch_paint(c, 0, T_a, flag_dev, sparse, st)) != CT_OK) return rc;
-    if (T_a < T) {
-        CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));          // ... now all of it
-        if ((rc = launch_paint(c, T_a, T - T_a, flag_dev + (size_t)T_a * H * W, sparse, st)) != CT_OK) return rc;
-    } else if (sparse) {
-        CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));
-    }
+    if ((rc = launch_paint(c, 0, T, flag_dev, sparse, st)) != CT_OK) return rc;
     if (c->novr) {
         CT_CUDA(ctk::paint_overrides(c->o_t.as<int32_t>(), c->o_y.as<int32_t>(), c->o_x0.as<int32_t>(),
                                      c->o_x1.as<int32_t>(), c->o_val.as<int32_t>(), c->novr, H, W, 0, T, flag_dev, st));

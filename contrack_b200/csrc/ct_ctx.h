@@ -159,10 +159,10 @@ struct ct_ctx {
     ct_plane_runs_fn fetch_fn = nullptr;
     void* fetch_user = nullptr;
     // ct_shard_begin: thresholding of the own planes is deferred to ct_shard_tables_dev (pipelined with the table kernels)
-    long opt_fill_split = 100;                // per cent of the planes in the first of the two zero-fill launches
-    long opt_shard_fill_defer_ms = 2;         // ... and not before the export when the fill is shorter than this (ms)
-    int fill_pending = 0;
-    long opt_shard_fill_late = 1;             // sharded run: zero fill starts after the local tables (1) / after the threshold (0)
+    long opt_fill_ctas = 2;                   // resident blocks per SM of the zero fill (room for the table kernels beside it)
+    long opt_fill_late = 0;                   // plane-kernel path: 1 = the zero fill starts after the plane kernel (0: beside it)
+    int32_t* pend_fill = nullptr;             // ... the fill ctf::finish() has to start
+    size_t pend_fill_cells = 0;
     long opt_fused_runs = 1;                  // row-runs come out of the threshold kernel (0: re-extracted from the bit rows)
     long opt_label_fast = 1;                  // steps 4c/4d at label granularity on the host (fallback: per component)
     long opt_profile_tables = 0;              // debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"

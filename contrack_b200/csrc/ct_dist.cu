@@ -475,16 +475,27 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
     // ---- zero fill of the own flag planes on the low-priority stream, beside everything that follows ----
     CT_CUDA(cudaEventRecord(c->ev_side[0], st));
     CT_CUDA(cudaStreamWaitEvent(side, c->ev_side[0], 0));
+    c->pend_fill = nullptr; c->pend_fill_cells = 0;
+    const bool plane_first = c->opt_fused_runs && c->opt_gpu_tables &&
+                             (c->opt_plane_kernel == 1 || (c->opt_plane_kernel == 2 && planes <= c->opt_plane_max_planes));
     if (!host_io) {
-        CT_CUDA(ctk::zero_fill(flag_dev, cells, c->sm_count, side));
-        c->launches += 1;
+        if (c->opt_fill_late && plane_first) {
+            c->pend_fill = flag_dev; c->pend_fill_cells = cells;      // started by ctf::finish(), after the plane kernel
+        } else {
+            CT_CUDA(ctk::zero_fill(flag_dev, cells, c->sm_count, side, (int)c->opt_fill_ctas));
+            c->launches += 1;
+        }
     }
     CT_CUDA(cudaEventRecord(c->ev_side[1], side));
     CT_CUDA(cudaStreamWaitEvent(ts, c->ev_side[0], 0));
     CT_CUDA(cudaStreamWaitEvent(ts, c->ev_x[1], 0));
 
     // ---- 2..5, repeated when a table or the exchange stride turns out too small ----
-    bool local_ok = false, classic = !(c->opt_plane_kernel && c->opt_fused_runs && c->opt_gpu_tables);
+    // table builder by shard size, like the single-GPU call: the plane kernel for short shards, the global-memory kernels for
+    // long ones (they run beside the zero fill, which is long enough to hide them there)
+    bool local_ok = false;
+    bool classic = !(c->opt_fused_runs && c->opt_gpu_tables &&
+                     (c->opt_plane_kernel == 1 || (c->opt_plane_kernel == 2 && planes <= c->opt_plane_max_planes)));
     int outcome = ctf::FAST_SLOW;
     std::vector<unsigned long long> mdesc_host((size_t)nranks * HDR_WORDS);
     CT_CUDA(c->hp_hdr.ensure((size_t)nranks * HDR_BYTES + 256));
@@ -635,6 +646,12 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
     std::vector<ctb::Override> ovr;
     for (const ctb::Override& ov : g->host_result.overrides)
         if (ov.t >= t_begin && ov.t < t_begin + T_local) ovr.push_back(ctb::Override{(int32_t)(ov.t - t_begin), ov.y, ov.x0, ov.x1, ov.val});
+    if (c->pend_fill) {                                                // (local tables came from the fallback kernels)
+        CT_CUDA(ctk::zero_fill(c->pend_fill, c->pend_fill_cells, c->sm_count, side, (int)c->opt_fill_ctas));
+        CT_CUDA(cudaEventRecord(c->ev_side[1], side));
+        c->launches += 1;
+        c->pend_fill = nullptr;
+    }
     CT_CUDA(cudaEventRecord(c->ev_tbl[0], ts));
     CT_CUDA(cudaStreamWaitEvent(st, c->ev_tbl[0], 0));
     CT_CUDA(cudaStreamWaitEvent(st, c->ev_side[1], 0));

@@ -191,6 +191,17 @@ int finish(ct_ctx* c, cudaStream_t st) {
                                      reinterpret_cast<unsigned long long*>(c->pl_ctl.as<char>() + 16));
     CT_CUDA(cudaGetLastError());
     c->launches += 1;
+    if (c->pend_fill) {
+        // the zero fill of the flag planes was held back until the plane kernel is done ("fill_late"): from here on it runs
+        // on the low-priority stream beside the global kernel and the host replay
+        CT_CUDA(cudaEventRecord(c->ev_tbl[1], st));
+        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_tbl[1], 0));
+        CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+        CT_CUDA(ctk::zero_fill(c->pend_fill, c->pend_fill_cells, c->sm_count, c->side_stream, (int)c->opt_fill_ctas));
+        CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
+        c->launches += 1;
+        c->pend_fill = nullptr;
+    }
     return CT_OK;
 }
 

@@ -105,7 +105,8 @@ cudaError_t seg_flags(const uint32_t* srow, const uint32_t* sa, const uint32_t* 
 cudaError_t seg_write(const uint32_t* srow, const uint32_t* sa, const uint32_t* sb, const uint32_t* start,
                       const uint32_t* segpos, long begin, long end, int H, const SegTables& o, cudaStream_t st);
 
-cudaError_t zero_fill(int32_t* p, size_t n, int sm_count, cudaStream_t st);
+// ctas_per_sm: 1..7 caps the resident blocks per SM (room for the table kernels beside the fill); 0 / 8 = no cap
+cudaError_t zero_fill(int32_t* p, size_t n, int sm_count, cudaStream_t st, int ctas_per_sm = 0);
 
 // ---- step 3 (overlap filter) and step 4a/b (3-D labels) on the device tables ----
 struct Step3Tables {

@@ -504,7 +504,7 @@ def main():
         line['config']['threshold_note'] = thr_note
     if world > 1 and shard_info:
         last = shard_info[-args.steps:]
-        keys = ('ms_threshold', 'ms_zero_fill', 'ms_tables_after_threshold', 'ms_plane_kernel', 'ms_global_kernel', 'ms_host_tables',
+        keys = ('ms_threshold', 'ms_zero_fill', 'ms_tables_after_threshold', 'ms_plane_kernel', 'ms_exchange', 'ms_global_kernel', 'ms_host_tables',
                 'ms_paint', 'ms_total')
         mine = {k: round(float(np.mean([i.get(k, 0.0) for i in last])), 3) for k in keys}
         mine.update({k: last[-1].get(k) for k in ('exchange_bytes', 'shard_attempts', 'fast_path', 'sweeps', 'kernel_launches')})

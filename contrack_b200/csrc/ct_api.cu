@@ -217,10 +217,9 @@ int prepare(ct_ctx* c, long T, int H, int W, const double* w_host, const double*
 int launch_threshold(ct_ctx* c, const void* anom_dev, int in_dtype, long t0, long nt, long thr_n, int thr_is_f32,
                      int op, cudaStream_t st, int all_bits = 1) {
     ctk::ThresholdArgs a;
-    // the bit rows are read by: run extraction from bits (fused_runs = 0), the paint variants that go by bit rows or are
-    // dense, the boundary export of a shard and the host-buffer call's dense fallback -- callers that need none of these
-    // pass all_bits = 0 and only rows with more runs than slots get their bit row
-    a.bits_overflow_only = (!all_bits && c->opt_fused_runs && c->opt_paint_runs && c->opt_overlap_zero) ? 1 : 0;
+    // the bit rows are read by: the dense paint, the boundary export of a shard and the host-buffer call's dense fallback --
+    // callers that need none of these pass all_bits = 0 and only rows with more runs than slots get their bit row
+    a.bits_overflow_only = (!all_bits && c->opt_overlap_zero) ? 1 : 0;
     a.anom = anom_dev; a.in_dtype = in_dtype; a.T = nt; a.H = c->H; a.W = c->W; a.Ww = c->Ww;
     a.thr_dev = thr_n == 1 ? c->thr_dev.as<double>() : c->thr_dev.as<double>() + t0;
     a.thr_n = thr_n; a.thr_is_f32 = thr_is_f32; a.op = op;
@@ -299,7 +298,7 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
         for (DevBuf* b : rb) CT_CUDA(b->grow((size_t)(Re + 2) * 4, (size_t)Rb * 4, st, hint(Re + 2, 4)));
     }
     CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(std::max(Re - Rb, n)) * sizeof(uint32_t)));
-    if (c->opt_fused_runs) {
+    {
         uint32_t* ovf = nullptr;
         if (cnt_host[16]) {                                      // some row of the cube has more runs than slots
             CT_CUDA(c->ovf_rows.ensure((size_t)n * 4));
@@ -308,8 +307,6 @@ int tables_chunk(ct_ctx* c, long p0, long p1, cudaStream_t st) {
         }
         CT_CUDA(ctk::compact_runs(U(c->slots), U(c->bits), U(c->row_ptr), r0, n, c->Ww, ovf, cnt_dev + 17, U(c->run_x),
                                   U(c->run_row), st));
-    } else {
-        CT_CUDA(ctk::extract_runs(U(c->bits), U(c->row_ptr), r0, n, c->Ww, U(c->run_x), U(c->run_row), st));
     }
     prof_mark(c, "extract_runs", st);
     CT_CUDA(ctk::ccl_init(U(c->parent), Rb, Re, st));
@@ -821,7 +818,7 @@ int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int st
 // throughput is ~T / 740 x 0.2 ms) for small T, e.g. the shard of a multi-GPU run; the global-memory table kernels (every
 // step fully parallel over all planes, pipelined under the threshold kernel) for long cubes on one GPU.
 bool use_plane_kernel(const ct_ctx* c, long T) {
-    if (!c->opt_fused_runs || !c->opt_gpu_tables) return false;
+    if (!c->opt_gpu_tables) return false;
     return c->opt_plane_kernel == 1 || (c->opt_plane_kernel == 2 && T <= c->opt_plane_max_planes);
 }
 
@@ -910,9 +907,9 @@ int launch_paint(ct_ctx* c, long t0, long nt, int32_t* flag_dev, int sparse, cud
     a.row_ptr = c->row_ptr.as<uint32_t>() + r0;
     a.run_val = c->run_val.as<int32_t>();
     a.nrows = nt * c->H; a.W = c->W; a.Ww = c->Ww; a.flag = flag_dev;
-    a.sparse = sparse ? (c->opt_paint_runs ? 2 : 1) : 0;
+    a.sparse = sparse ? 1 : 0;
     a.run_x = c->run_x.as<uint32_t>(); a.run_row = c->run_row.as<uint32_t>(); a.row0 = r0;
-    if (c->fast_tables && a.sparse == 2) { a.run_comp = c->run_comp.as<uint32_t>(); a.comp_val = c->c_val.as<int32_t>(); }
+    if (c->fast_tables && a.sparse) { a.run_comp = c->run_comp.as<uint32_t>(); a.comp_val = c->c_val.as<int32_t>(); }
     else if (c->fast_tables == 1) {
         // the row-wise / dense paints go by a value per run: materialise it once
         CT_CUDA(c->run_val.ensure((size_t)(c->nruns + 1) * 4));
@@ -938,7 +935,9 @@ void api_host_zero_start(ct_ctx* c, int32_t* flag_host, size_t cells, int share,
     if (nthreads <= 0) {
         const unsigned hc = std::thread::hardware_concurrency();
         nthreads = hc >= 16 ? 6 : (hc >= 4 ? (int)hc / 2 : 1);
-        nthreads = std::max(1, nthreads / std::max(1, share) + (share > 1 ? 1 : 0));
+        // several ranks on this host: their PCIe links work in parallel, so the copies are no longer the bound -- the zeroing
+        // is (host memory writes): all cores, shared among the ranks
+        if (share > 1) nthreads = std::max(1, (int)hc / share);
     }
     const size_t per = ((cells + nthreads - 1) / nthreads + 1023) / 1024 * 1024;
     for (int i = 0; i < nthreads; ++i) {
@@ -951,9 +950,9 @@ void api_host_zero_start(ct_ctx* c, int32_t* flag_host, size_t cells, int share,
 // page): all cores, and the destination of the run 16 ahead is prefetched while the current one is written.  Returns the
 // number of threads used.
 int api_host_expand_runs(ct_ctx* c, const uint32_t* h_x, const uint32_t* h_row, const int32_t* h_val, long R, long row_shift,
-                         int W, int32_t* flag_host) {
+                         int W, int32_t* flag_host, int share) {
     int npaint = (int)c->opt_host_threads;
-    if (npaint <= 0) npaint = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    if (npaint <= 0) npaint = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, share)));
     const int np = (int)std::max(1L, std::min((long)npaint, R / 4096 + 1));
     std::vector<std::thread> painters;
     const long per = (R + np - 1) / np;
@@ -1081,10 +1080,8 @@ void ct_destroy(ct_ctx* c) {
 int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!c || !key) return fail(CT_ERR_ARG, "null argument");
     if (!strcmp(key, "tma")) { c->opt_tma = value; return CT_OK; }
-    if (!strcmp(key, "paint_tma")) { c->opt_paint_tma = value; return CT_OK; }
     if (!strcmp(key, "overlap_zero")) { c->opt_overlap_zero = value; return CT_OK; }
     if (!strcmp(key, "gpu_tables")) { c->opt_gpu_tables = value; return CT_OK; }
-    if (!strcmp(key, "paint_runs")) { c->opt_paint_runs = value; return CT_OK; }
     if (!strcmp(key, "chunks")) { c->opt_chunks = value < 1 ? 1 : value; return CT_OK; }
     if (!strcmp(key, "chunk_min_planes")) { c->opt_chunk_min_planes = value < 1 ? 1 : value; return CT_OK; }
     if (!strcmp(key, "host_sparse")) { c->opt_host_sparse = value; return CT_OK; }
@@ -1093,7 +1090,6 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "host_out_zeroed")) { c->opt_host_out_zeroed = value; return CT_OK; }
     if (!strcmp(key, "fill_late")) { c->opt_fill_late = value; return CT_OK; }
     if (!strcmp(key, "fill_ctas")) { c->opt_fill_ctas = value; return CT_OK; }
-    if (!strcmp(key, "fused_runs")) { c->opt_fused_runs = value; return CT_OK; }
     if (!strcmp(key, "label_fast")) { c->opt_label_fast = value; return CT_OK; }
     if (!strcmp(key, "profile_tables")) { c->opt_profile_tables = value; return CT_OK; }
     if (!strcmp(key, "plane_kernel")) { c->opt_plane_kernel = value; return CT_OK; }
@@ -1302,7 +1298,7 @@ int ct_run_contrack_host(ct_ctx* c, const void* anom_host, int in_dtype, long T,
         zero_threads.clear();
         CT_CUDA(cudaStreamSynchronize(ws));
         d2h_bytes = (size_t)R * 12;
-        const int np = cti::api_host_expand_runs(c, h_x, h_row, h_val, R, 0, W, flag_host);
+        const int np = cti::api_host_expand_runs(c, h_x, h_row, h_val, R, 0, W, flag_host, 1);
         for (const ctb::Override& o : c->host_result.overrides) {  // pieces of components split at a stale box
             int32_t* out = flag_host + ((size_t)o.t * H + o.y) * W;
             for (int xx = o.x0; xx < o.x1; ++xx) out[xx] = o.val;

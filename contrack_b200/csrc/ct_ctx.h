@@ -98,7 +98,7 @@ using cti::PinBuf;
 
 struct ct_ctx {
     int device = 0, sm_count = 148;
-    long opt_tma = 3, opt_paint_tma = 0;      // threshold kernel variant, see ctk::ThresholdArgs::variant
+    long opt_tma = 1;                         // threshold kernel: rows staged by cp.async.bulk (0: plain coalesced loads)
     // geometry of the last run
     long T = 0; int H = 0, W = 0, Ww = 0;
     long nruns = 0, ncomp = 0, npair = 0, nseam = 0, novr = 0;
@@ -124,7 +124,6 @@ struct ct_ctx {
     PinBuf hp_plane;
     int32_t* zero_started_for = nullptr;
     int special_uniform = 0;
-    long opt_paint_runs = 1;                 // sparse paint by runs (1) or by rows (0)
     long opt_gpu_tables = 1;                 // step 3 + 3-D labels on the device (single-GPU path)
     long opt_chunks = 4;                     // time chunks of the pipelined run (tables of chunk k under threshold k+1)
     long opt_chunk_min_planes = 1024;        // ... but never fewer planes per chunk than this (launch latency of ~45 small
@@ -163,7 +162,6 @@ struct ct_ctx {
     long opt_fill_late = 0;                   // plane-kernel path: 1 = the zero fill starts after the plane kernel (0: beside it)
     int32_t* pend_fill = nullptr;             // ... the fill ctf::finish() has to start
     size_t pend_fill_cells = 0;
-    long opt_fused_runs = 1;                  // row-runs come out of the threshold kernel (0: re-extracted from the bit rows)
     long opt_label_fast = 1;                  // steps 4c/4d at label granularity on the host (fallback: per component)
     long opt_profile_tables = 0;              // debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"
     std::vector<std::pair<std::string, cudaEvent_t>> prof;
@@ -189,6 +187,8 @@ struct ct_ctx {
     DevBuf g_dirty, g_blocksum, g_evflag, g_ev, g_lrec, g_patch;
     long pl_planes = 0;                      // planes the chain was set up for
     int coop_grid = 0;
+    struct D2H { void* dst; const void* src; size_t bytes; } extra_d2h[2] = {{nullptr, nullptr, 0}, {nullptr, nullptr, 0}};
+                                             // small device-to-host copies ctf::global() queues behind its kernel
     int plane_timed = 0;
     int fast_tables = 0;                     // the value of every component is in c_val on the device (paint by component)
     // ---- time-sharded run (ct_dist.cu) ----

@@ -476,7 +476,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
     CT_CUDA(cudaEventRecord(c->ev_side[0], st));
     CT_CUDA(cudaStreamWaitEvent(side, c->ev_side[0], 0));
     c->pend_fill = nullptr; c->pend_fill_cells = 0;
-    const bool plane_first = c->opt_fused_runs && c->opt_gpu_tables &&
+    const bool plane_first = c->opt_gpu_tables &&
                              (c->opt_plane_kernel == 1 || (c->opt_plane_kernel == 2 && planes <= c->opt_plane_max_planes));
     if (!host_io) {
         if (c->opt_fill_late && plane_first) {
@@ -494,7 +494,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
     // table builder by shard size, like the single-GPU call: the plane kernel for short shards, the global-memory kernels for
     // long ones (they run beside the zero fill, which is long enough to hide them there)
     bool local_ok = false;
-    bool classic = !(c->opt_fused_runs && c->opt_gpu_tables &&
+    bool classic = !(c->opt_gpu_tables &&
                      (c->opt_plane_kernel == 1 || (c->opt_plane_kernel == 2 && planes <= c->opt_plane_max_planes)));
     int outcome = ctf::FAST_SLOW;
     std::vector<unsigned long long> mdesc_host((size_t)nranks * HDR_WORDS);
@@ -536,7 +536,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
             CT_CUDA(cudaStreamSynchronize(ts));
             unsigned long long mc = 0, mp = 0, ms = 0;
             for (int r = 0; r < nranks; ++r) { mc = std::max(mc, all[4 * r]); mp = std::max(mp, all[4 * r + 1]); ms = std::max(ms, all[4 * r + 2]); }
-            c->sh_capC = (long)(mc + mc / 4 + 1024); c->sh_capP = (long)(mp + mp / 4 + 1024); c->sh_capS = (long)(ms + ms / 4 + 1024);
+            c->sh_capC = (long)(mc + mc / 8 + 512); c->sh_capP = (long)(mp + mp / 8 + 512); c->sh_capS = (long)(ms + ms / 8 + 512);
             c->stats["exchange_negotiated"] = 1.0;
             // (a local capacity retry / fallback is reported through the header and handled below like any other)
         }
@@ -591,8 +591,9 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
             CT_CUDA(cudaGetLastError());
             g->launches += 4;
             // descriptors (+ need) and this rank's own control block come back with the global phase's one synchronisation
-            CT_CUDA(cudaMemcpyAsync(c->hp_hdr.p, md, (size_t)nranks * HDR_BYTES + 32, cudaMemcpyDeviceToHost, ts));
-            CT_CUDA(cudaMemcpyAsync(c->hp_ctl.p, c->pl_ctl.p, 128, cudaMemcpyDeviceToHost, ts));
+            // (queued behind the global kernel, not in front of it)
+            g->extra_d2h[0] = {c->hp_hdr.p, md, (size_t)nranks * HDR_BYTES + 32};
+            g->extra_d2h[1] = {c->hp_ctl.p, c->pl_ctl.p, 128};
         }
         // ---- 5. global phase on the merged tables (one synchronisation) ----
         uint32_t gstatus = 0;
@@ -660,7 +661,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
         ctk::PaintArgs a;
         const long r0 = (long)hp * H;
         a.bits = nullptr; a.row_ptr = c->row_ptr.as<uint32_t>() + r0; a.run_val = nullptr;
-        a.nrows = T_local * H; a.W = W; a.Ww = c->Ww; a.flag = flag_dev; a.sparse = 2;
+        a.nrows = T_local * H; a.W = W; a.Ww = c->Ww; a.flag = flag_dev; a.sparse = 1;
         a.run_x = c->run_x.as<uint32_t>(); a.run_row = c->run_row.as<uint32_t>(); a.row0 = r0;
         a.run_comp = c->run_comp.as<uint32_t>(); a.comp_val = g->c_val.as<int32_t>() + comp_off;
         CT_CUDA(ctk::paint(a, c->sm_count, st));
@@ -699,7 +700,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
         for (auto& t : zero_threads) t.join();
         zero_threads.clear();
         CT_CUDA(cudaStreamSynchronize(st));
-        const int np = cti::api_host_expand_runs(c, h_x, h_row, h_val, R, (long)hp * H, W, flag_host);
+        const int np = cti::api_host_expand_runs(c, h_x, h_row, h_val, R, (long)hp * H, W, flag_host, nranks);
         for (const ctb::Override& o : ovr) {                           // pieces of components split at a stale box
             int32_t* out = flag_host + ((size_t)o.t * H + o.y) * W;
             for (int xx = o.x0; xx < o.x1; ++xx) out[xx] = o.val;
@@ -718,6 +719,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev_side[0], c->ev_side[1])); c->stats["ms_zero_fill"] = ms;
     CT_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev_tbl[0])); c->stats["ms_tables_after_threshold"] = ms;
     if (c->plane_timed && cudaEventElapsedTime(&ms, c->ev_p[0], c->ev_p[1]) == cudaSuccess) c->stats["ms_plane_kernel"] = ms;
+    if (c->plane_timed && cudaEventElapsedTime(&ms, c->ev_p[1], g->ev_p[2]) == cudaSuccess) c->stats["ms_exchange"] = ms;   // pack + all-gather + merge
     c->plane_timed = 0;
     c->stats["kernel_launches"] = (double)(c->launches + g->launches);
     c->stats["runs"] = (double)c->nruns; c->stats["comps2d"] = (double)c->ncomp;

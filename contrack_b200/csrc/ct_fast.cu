@@ -280,6 +280,10 @@ int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, lon
     const long ev_first = std::min<long>(EV_FIRST, (long)k.segs), rec_first = std::min<long>(REC_FIRST, 2 * (long)k.segs);
     CT_CUDA(c->hp_ev.ensure((size_t)EV_FIRST * 8 + (size_t)REC_FIRST * 28));
     CT_CUDA(cudaMemcpyAsync(hctl, ctl, 128, cudaMemcpyDeviceToHost, st));
+    for (auto& x : c->extra_d2h) {
+        if (x.dst) CT_CUDA(cudaMemcpyAsync(x.dst, x.src, x.bytes, cudaMemcpyDeviceToHost, st));
+        x.dst = nullptr;
+    }
     if (ev_first > 0) {
         CT_CUDA(cudaMemcpyAsync(c->hp_ev.p, c->g_ev.p, (size_t)ev_first * 8, cudaMemcpyDeviceToHost, st));
         CT_CUDA(cudaMemcpyAsync(c->hp_ev.as<char>() + (size_t)EV_FIRST * 8, c->g_lrec.p, (size_t)rec_first * 28,

@@ -20,5 +20,5 @@ bool api_plane_runs(ct_ctx* c, long plane, std::vector<cth::PlaneRun>& out, cuda
 // host side of the host-buffer entry points (zeroing threads, expansion of the row-run table into the host cube)
 void api_host_zero_start(ct_ctx* c, int32_t* flag_host, size_t cells, int share, std::vector<std::thread>& threads);
 int api_host_expand_runs(ct_ctx* c, const uint32_t* h_x, const uint32_t* h_row, const int32_t* h_val, long R, long row_shift,
-                         int W, int32_t* flag_host);
+                         int W, int32_t* flag_host, int share);
 }  // namespace cti

@@ -290,8 +290,8 @@ template <typename TIn, bool F32CMP>
 cudaError_t launch_threshold_bulk(const ThresholdArgs& a, int sm_count, cudaStream_t st) {
     const long nrows = a.T * a.H;
     const int stage_bytes = (int)(((size_t)a.W * sizeof(TIn) + 127) / 128 * 128);
-    // variant 3: 16 warps per CTA when two row buffers per warp still fit (more warps to hide the LDS / ballot latency)
-    int nw = (a.variant == 3 && 16 * 2 * stage_bytes <= 199 * 1024) ? 16 : 8;
+    // 16 warps per CTA when two row buffers per warp still fit (more warps to hide the LDS / ballot latency), else 8
+    int nw = (16 * 2 * stage_bytes <= 199 * 1024) ? 16 : 8;
     int NS = (200 * 1024 - 1024) / (nw * stage_bytes);
     if (NS > 8) NS = 8;
     const size_t smem = ((size_t)nw * NS * 8 + 127) / 128 * 128 + (size_t)nw * NS * stage_bytes;
@@ -330,16 +330,9 @@ template <typename TIn, bool F32CMP>
 cudaError_t launch_threshold(const ThresholdArgs& a, int blocks, cudaStream_t st) {
     const long nrows = a.T * a.H;
 #define CT_LAUNCH_THR(OPV)                                                                                          \
-    do {                                                                                                            \
-        if (a.variant == 2)                                                                                         \
-            k_threshold<TIn, F32CMP, OPV, 16><<<blocks, 256, 0, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww,     \
-                                                                      a.thr_dev, a.thr_n, a.bits, a.row_cnt,        \
-                                                                      a.seam_flag, a.slots, a.overflow);            \
-        else                                                                                                        \
-            k_threshold<TIn, F32CMP, OPV, 8><<<blocks, 256, 0, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww,      \
-                                                                     a.thr_dev, a.thr_n, a.bits, a.row_cnt,         \
-                                                                     a.seam_flag, a.slots, a.overflow);             \
-    } while (0)
+    k_threshold<TIn, F32CMP, OPV, 16><<<blocks, 256, 0, st>>>((const TIn*)a.anom, nrows, a.H, a.W, a.Ww, a.thr_dev,  \
+                                                              a.thr_n, a.bits, a.row_cnt, a.seam_flag, a.slots,     \
+                                                              a.overflow)
     switch (a.op) {
         case 0: CT_LAUNCH_THR(0); break;
         case 1: CT_LAUNCH_THR(1); break;
@@ -478,8 +471,7 @@ __global__ void __launch_bounds__(256) k_compact_runs(const uint4* __restrict__ 
     }
 }
 
-// MIN_RUNS > 0: only the rows listed in ovf_rows[0 .. *ovf_count) (the ones the slots could not hold)
-template <int MIN_RUNS>
+// rows listed in ovf_rows[0 .. *ovf_count): the ones with more runs than the threshold kernel's slots hold
 __global__ void __launch_bounds__(256) k_extract_runs(const uint32_t* __restrict__ bits,
                                                       const uint32_t* __restrict__ row_ptr, long nrows, int Ww,
                                                       uint32_t* __restrict__ run_x, uint32_t* __restrict__ run_row,
@@ -489,9 +481,9 @@ __global__ void __launch_bounds__(256) k_extract_runs(const uint32_t* __restrict
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     uint16_t* rx = reinterpret_cast<uint16_t*>(run_x);
-    const long nwork = MIN_RUNS > 0 ? (long)*ovf_count : nrows;
+    const long nwork = (long)*ovf_count;
     for (long wi = warp0; wi < nwork; wi += nwarps) {
-        const long row = MIN_RUNS > 0 ? (long)ovf_rows[wi] : wi;
+        const long row = (long)ovf_rows[wi];
         // everything a 64-word row needs is requested before anything is consumed: one memory latency per row
         const uint32_t* b = bits + row * (long)Ww;
         const uint32_t base = row_ptr[row], next = row_ptr[row + 1];
@@ -970,8 +962,7 @@ __global__ void __launch_bounds__(256) k_zero_fill(int4* __restrict__ p, size_t 
     if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = 0;
 }
 
-// SPARSE: the cube is already zero; only 4-cell groups that contain a set cell are written.
-template <bool VEC4, bool SPARSE>
+template <bool VEC4>
 __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ row_ptr,
                                                const int32_t* __restrict__ run_val, long nrows, int W, int Ww,
                                                int32_t* __restrict__ flag) {
@@ -981,7 +972,6 @@ __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits
     for (long row = warp0; row < nrows; row += nwarps) {
         const uint32_t rbase = row_ptr[row];
         const bool empty = row_ptr[row + 1] == rbase;
-        if (SPARSE && empty) continue;
         int32_t* out = flag + row * (long)W;
         const uint32_t* b = bits + row * (long)Ww;
         uint32_t prev = 0, running = rbase;
@@ -1000,7 +990,6 @@ __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits
                 prev = __shfl_sync(FULL, m, 31);
             } else {
                 prev = 0;
-                if (SPARSE) continue;
             }
             const int xbase = k0 * 32;
             if (VEC4) {
@@ -1026,8 +1015,6 @@ __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits
                                 }
                             }
                             v = make_int4(vv[0], vv[1], vv[2], vv[3]);
-                        } else if (SPARSE) {
-                            continue;
                         }
                     }
                     if (x < W) __stcs(reinterpret_cast<int4*>(out + x), v);
@@ -1042,7 +1029,6 @@ __global__ void __launch_bounds__(256) k_paint(const uint32_t* __restrict__ bits
                         const uint32_t sw = __shfl_sync(FULL, starts, i);
                         const uint32_t bw = __shfl_sync(FULL, base, i);
                         if ((mw >> lane) & 1u) v = run_val[bw + __popc(sw & ((2u << lane) - 1u)) - 1u];
-                        else if (SPARSE) continue;
                     }
                     if (x < W) __stcs(out + x, v);
                 }
@@ -1111,7 +1097,7 @@ cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st
     if (nrows == 0) return cudaSuccess;
     long want = (nrows + 7) / 8;
     int blocks = (int)(want < (long)sm_count * 8 ? want : (long)sm_count * 8);
-    if (a.variant == 1 || a.variant == 3) {
+    if (a.variant != 0) {
         if (a.in_dtype == 1 && bulk_ok<double>(a)) return launch_threshold_bulk<double, false>(a, sm_count, st);
         if (a.in_dtype == 0 && bulk_ok<float>(a)) {
             if (a.thr_is_f32) return launch_threshold_bulk<float, true>(a, sm_count, st);
@@ -1119,12 +1105,9 @@ cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st
         }
     }
     // no bulk staging possible (row bytes not a multiple of 16, or rows too long for shared memory): deep plain loads
-    ThresholdArgs b = a;
-    if (b.variant == 1) b.variant = 0;
-    if (b.variant == 3) b.variant = 2;
-    if (b.in_dtype == 1) return launch_threshold<double, false>(b, blocks, st);
-    if (b.thr_is_f32) return launch_threshold<float, true>(b, blocks, st);
-    return launch_threshold<float, false>(b, blocks, st);
+    if (a.in_dtype == 1) return launch_threshold<double, false>(a, blocks, st);
+    if (a.thr_is_f32) return launch_threshold<float, true>(a, blocks, st);
+    return launch_threshold<float, false>(a, blocks, st);
 }
 
 cudaError_t row_stats(const uint32_t* bits, long nrows, int W, int Ww, uint32_t* row_cnt, uint32_t* seam_flag,
@@ -1149,16 +1132,6 @@ cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32
     return cudaGetLastError();
 }
 
-cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww, uint32_t* run_x,
-                         uint32_t* run_row, cudaStream_t st) {
-    if (nrows == 0) return cudaSuccess;
-    const long want = (nrows + 7) / 8;
-    k_extract_runs<0><<<(unsigned)std::min<long>(want, 148L * 16), 256, 0, st>>>(bits + row0 * (long)Ww, row_ptr + row0,
-                                                                                nrows, Ww, run_x, run_row, row0, nullptr,
-                                                                                nullptr);
-    return cudaGetLastError();
-}
-
 cudaError_t compact_runs(const uint32_t* slots, const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww,
                          uint32_t* ovf_rows, uint32_t* ovf_count, uint32_t* run_x, uint32_t* run_row, cudaStream_t st) {
     if (nrows == 0) return cudaSuccess;
@@ -1169,7 +1142,7 @@ cudaError_t compact_runs(const uint32_t* slots, const uint32_t* bits, const uint
     k_compact_runs<<<blocks_for(nrows, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(slots + row0 * (long)RUN_SLOTS),
                                                            row_ptr + row0, nrows, run_x, run_row, row0, ovf_rows, ovf_count);
     if (ovf_rows)
-        k_extract_runs<RUN_SLOTS><<<148 * 2, 256, 0, st>>>(bits + row0 * (long)Ww, row_ptr + row0, nrows, Ww, run_x, run_row,
+        k_extract_runs<<<148 * 2, 256, 0, st>>>(bits + row0 * (long)Ww, row_ptr + row0, nrows, Ww, run_x, run_row,
                                                            row0, ovf_rows, ovf_count);
     return cudaGetLastError();
 }
@@ -1264,15 +1237,12 @@ cudaError_t paint(const PaintArgs& a, int sm_count, cudaStream_t st) {
     long want = (a.nrows + 7) / 8;
     int blocks = (int)(want < (long)sm_count * 8 ? want : (long)sm_count * 8);
     const bool vec = (a.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.flag) & 15) == 0);
-    if (a.sparse == 2) {
+    if (a.sparse) {
         k_paint_runs<<<sm_count * 8, 256, 0, st>>>(a.row_ptr - a.row0, a.row0, a.nrows, a.run_x, a.run_row, a.run_val,
                                                    a.run_comp, a.comp_val, a.W, a.flag);
-    } else if (a.sparse) {
-        if (vec) k_paint<true, true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
-        else k_paint<false, true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
     } else {
-        if (vec) k_paint<true, false><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
-        else k_paint<false, false><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
+        if (vec) k_paint<true><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
+        else k_paint<false><<<blocks, 256, 0, st>>>(a.bits, a.row_ptr, a.run_val, a.nrows, a.W, a.Ww, a.flag);
     }
     return cudaGetLastError();
 }

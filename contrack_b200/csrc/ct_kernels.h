@@ -21,8 +21,8 @@ struct ThresholdArgs {
     uint32_t* overflow;                      // device flag, set if a row has more runs than slots
     int bits_overflow_only = 0;              // 1: bit rows are written only for rows with more runs than slots (nothing else
                                              // reads them when the runs come from the slots and the paint goes by runs)
-    int variant;                             // 0 / 2: 4-byte loads + ballot, 8 / 16 loads in flight per lane;
-                                             // 1 / 3: cp.async.bulk row staging, 8 / 16 warps per CTA (needs W % 4 == 0)
+    int variant;                             // 0: 4-byte loads + ballot, 16 loads in flight per lane; otherwise cp.async.bulk
+                                             // row staging (needs 16-byte aligned rows that fit shared memory, else as 0)
 };
 cudaError_t threshold_bits(const ThresholdArgs& a, int sm_count, cudaStream_t st);
 
@@ -39,11 +39,7 @@ size_t scan_tmp_elems(long n);
 cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, long n, uint32_t* tmp, cudaStream_t st,
                                uint32_t base = 0, uint32_t* wide_flag = nullptr);
 
-// rows [row0, row0 + nrows) of the GLOBAL bit rows / row_ptr -> run_x, run_row (global row numbers) at row_ptr[row]...
-cudaError_t extract_runs(const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww, uint32_t* run_x,
-                         uint32_t* run_row, cudaStream_t st);
-
-// the same from the row slots the threshold kernel filled; when ovf_rows is given ([nrows] scratch + a device counter), rows
+// rows [row0, row0 + nrows): row-runs from the row slots the threshold kernel filled -> run_x, run_row at row_ptr[row]...; when ovf_rows is given ([nrows] scratch + a device counter), rows
 // with more runs than slots are listed there and re-extracted from their bit rows
 cudaError_t compact_runs(const uint32_t* slots, const uint32_t* bits, const uint32_t* row_ptr, long row0, long nrows, int Ww,
                          uint32_t* ovf_rows, uint32_t* ovf_count, uint32_t* run_x, uint32_t* run_row, cudaStream_t st);
@@ -146,9 +142,10 @@ struct PaintArgs {
     const uint32_t* bits; const uint32_t* row_ptr; const int32_t* run_val;
     long nrows; int W, Ww;
     int32_t* flag;                           // [nrows * W] out
-    int sparse;                              // 0: dense; `flag` already zero: 1 = row-wise, cells of runs only; 2 = by runs
-    const uint32_t* run_x; const uint32_t* run_row;   // sparse == 2
-    const uint32_t* run_comp = nullptr;      // sparse == 2, optional: value of run r = comp_val[run_comp[r]] instead of run_val[r]
+    int sparse;                              // 0: dense (every cell written, from the bit rows); 1: `flag` is already zero, only
+                                             // the cells of row-runs with a value are written
+    const uint32_t* run_x; const uint32_t* run_row;   // sparse
+    const uint32_t* run_comp = nullptr;      // sparse, optional: value of run r = comp_val[run_comp[r]] instead of run_val[r]
     const int32_t* comp_val = nullptr;
     long row0;                               // first row painted (row_ptr points at it)
 };

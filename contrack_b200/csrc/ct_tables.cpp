@@ -553,16 +553,19 @@ int track_events_fast(int persistence, long nev, const int32_t* ev, long nrec, c
     value.resize(m); head.resize(m); nxt.resize(m);
     built.assign(m, 0); settled.assign(m, 0);
     touched.clear();
-    auto val_of = [&](int L) { return built[L] ? value[L] : L; };
+    for (int L = 0; L < m; ++L) value[L] = L;             // every label starts as its own value
     auto ensure_built = [&](int v) {                      // class v starts with label v alone
         if (built[v]) return;
-        built[v] = 1; value[v] = v; head[v] = v; nxt[v] = -1;
+        built[v] = 1; head[v] = v; nxt[v] = -1;
         touched.push_back(v);
     };
+    const int* val = value.data();
     for (long e = 0; e < nev; ++e) {
-        const int la = ev[2 * e], lb = ev[2 * e + 1];
-        if (la < 0 || lb < 0 || la >= m || lb >= m) return 1;
-        const int va = val_of(la), vb = val_of(lb);
+        // most segments repeat a merge that has already happened (a contour crosses the date line for many rows and days):
+        // two loads and a compare
+        const uint32_t la = (uint32_t)ev[2 * e], lb = (uint32_t)ev[2 * e + 1];
+        if (la >= (uint32_t)m || lb >= (uint32_t)m) return 1;
+        const int va = val[la], vb = val[lb];
         if (va == vb) continue;
         stats.n_events++;
         const int hi = std::max(va, vb), lo = std::min(va, vb);

@@ -56,25 +56,32 @@ const char* ct_last_error(void);
 /* One context per GPU; owns all scratch (bit planes, run tables, component tables). */
 int ct_create(int device, ct_ctx** out);
 void ct_destroy(ct_ctx* ctx);
-/* Runtime switches (defaults in brackets).  Returns CT_ERR_ARG for unknown keys.
- *   "tma"          threshold kernel: 3 [default] / 1 = rows staged by cp.async.bulk (16 / 8 warps per CTA),
- *                  0 / 2 = plain coalesced loads (8 / 16 in flight per lane)
- *   "overlap_zero" [1] zero fill of the flag cube on a side stream under the table phase + sparse paint; 0 = dense paint
- *   "paint_runs"   [1] sparse paint by row-runs; 0 = by bit rows
- *   "gpu_tables"   [1] steps 3 / 4a / 4b on the device; 0 = the whole ordered phase on the host (what a sharded run uses)
- *   "chunks"       [4] time chunks of ct_run_contrack's pipeline (table kernels of chunk k run while chunk k+1 is being
- *                  thresholded); "chunk_min_planes" [1024] = smallest chunk
+/* Runtime switches (defaults in brackets).  Returns CT_ERR_ARG for unknown keys.  Every combination gives the same bytes
+ * (tests/test_gpu_parity.py, test_gpu_fastpath.py); they select between the product path and the fallbacks it keeps.
+ *   "plane_kernel" [2] who builds the tables: 1 = the plane kernel (one thread block per time plane: union-find over the
+ *                  plane's row-runs in shared memory, look-back numbering, pair hash; one launch, no host round trip),
+ *                  0 = the global-memory table kernels (every step parallel over all planes, pipelined in time chunks under
+ *                  the threshold kernel), 2 = by size: the plane kernel up to "plane_max_planes" [4096] planes per context
+ *                  (the shards of a multi-GPU run), the global-memory kernels for longer cubes.  A plane that does not fit the
+ *                  plane kernel's shared memory ("plane_smem" [0 = 40 KB, then 200 KB]) falls back automatically.
+ *   "coop_global"  [1] ordered phase (contrack.py:706-751 + label boxes + date-line events) as ONE cooperative kernel and an
+ *                  O(events) host replay; 0 = one kernel per step with host round trips
+ *   "max_sweeps"   [32] Jacobi sweeps of the overlap filter before the plane-ordered wavefront takes over (bounded cost on
+ *                  adversarial keep/kill chains)
+ *   "gpu_tables"   [1] 0 = the whole ordered phase on the host (what the exact near-tie resolver falls back to)
+ *   "label_fast"   [1] 0 = date-line merge by per-component replay even when whole labels move (the fallback for labels that
+ *                  straddle a stale box)
+ *   "tma"          [1] threshold kernel: rows staged by cp.async.bulk + mbarrier; 0 = plain coalesced loads (also used
+ *                  automatically for rows that are not 16-byte aligned or too long for shared memory)
+ *   "overlap_zero" [1] zero fill of the flag cube on a side stream beside the table phase + sparse paint; 0 = dense paint
+ *   "fill_ctas"    [2] resident blocks per SM of the zero fill (room for the table kernels beside it); 0 = uncapped
+ *   "fill_late"    [0] plane-kernel path: 1 = the zero fill starts after the plane kernel instead of beside it
+ *   "chunks"       [4] time chunks of the global-memory table pipeline ("chunk_min_planes" [1024] = smallest chunk);
+ *                  "fast_chunks" [1] the same for the plane kernel (1: it runs beside the zero fill)
  *   "host_sparse"  [1] ct_run_contrack_host returns the result as row-runs expanded by host threads; 0 = dense copy
- *   "fused_runs"   [1] row-runs come out of the threshold kernel (8 slots per row); 0 = re-extracted from the bit rows
- *   "label_fast"   [1] date-line merge + persistence at label granularity on the host; 0 = always the per-component replay
- *   "shard_fill_late" [1] sharded run: zero fill after the local tables (0 = right after the threshold);
- *                  "shard_fill_defer_ms" [2] = fills shorter than this wait until the tables are exported
- *   "fill_split"   [100] per cent of the planes in the first of two zero-fill launches (the paint of that part starts early)
- *   "profile_tables" [0] debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"
- *   "host_zero_threads" [0 = automatic: 6] threads of the host-buffer call's zeroing pass
- *   "host_threads" [0 = automatic] host threads used by ct_run_contrack_host
- *   "host_out_zeroed" [0] 1 = the caller guarantees that flag_host is all zero on entry (fresh calloc / np.zeros pages): the
- *                  zeroing pass, which competes with the host-to-device copy for host memory bandwidth, is skipped */
+ *   "host_zero_threads" [0 = automatic], "host_threads" [0 = automatic] host threads of the host-buffer calls;
+ *   "host_out_zeroed" [0] 1 = the caller guarantees that flag_host is all zero on entry (the zeroing pass is skipped)
+ *   "profile_tables" [0] debug: CUDA-event time of every group of global-memory table kernels -> stats "ms_t_*" */
 int ct_set_option(ct_ctx* ctx, const char* key, long value);
 
 /* ---- run_contrack, contrack.py:646-772 -------------------------------------------------------------------------
@@ -105,9 +112,11 @@ int ct_run_contrack_host(ct_ctx* ctx, const void* anom_host, int in_dtype, long 
                          int32_t* flag_host, long* n_features, long chunk_planes);
 
 /* ---- statistics of the last run on this context (for bench.py / tests) ------------------------------------------
- * keys: "runs", "comps2d", "kept_comps", "labels3d", "features", "seam_segments", "seam_events", "seam_splits",
- *       "sweeps", "neartie_resolved", "kernel_launches",
- *       "ms_threshold", "ms_paint" (CUDA-event time of the two streaming kernels in the last run, microseconds*1000)
+ * keys: "runs", "comps2d", "pairs", "labels3d", "features", "seam_segments", "seam_events", "seam_splits", "sweeps",
+ *       "wavefront_planes", "neartie_resolved", "kernel_launches", "fast_path" (1 = plane kernel + cooperative kernel,
+ *       0 = global-memory table kernels, 0.5 / 0.25 = an ordered host replay took over), "plane_attempts",
+ *       "ms_threshold", "ms_zero_fill", "ms_plane_kernel", "ms_global_kernel", "ms_host_tables", "ms_paint", "ms_total"
+ *       (CUDA-event / host times of the last run in milliseconds)
  * returns the value, or -1 for an unknown key. */
 double ct_get_stat(ct_ctx* ctx, const char* key);
 

@@ -234,7 +234,7 @@ def test_bulk_copy_threshold_variant(eng, fixture_cube, golden):
         f, _ = gpu_run(eng, xd, la2, lo2, 40.0, '<', 0.3, 2, True)
         assert np.array_equal(f, ref)
     finally:
-        eng.set_option('tma', 3)
+        eng.set_option('tma', 1)
 
 
 def test_dense_paint_path(eng, fixture_cube, golden):
@@ -317,16 +317,17 @@ def test_chunked_table_pipeline(eng, chunks, plane):
         eng.set_option('chunk_min_planes', 1024)
 
 
-@pytest.mark.parametrize('opts', [{'tma': 0}, {'tma': 2}, {'tma': 1}, {'paint_runs': 0}, {'overlap_zero': 0, 'tma': 3},
-                                  {'gpu_tables': 0, 'paint_runs': 0}, {'chunks': 4, 'chunk_min_planes': 1},
+@pytest.mark.parametrize('opts', [{'tma': 0}, {'overlap_zero': 0}, {'gpu_tables': 0}, {'chunks': 4, 'chunk_min_planes': 1, 'plane_kernel': 0},
                                   {'chunks': 64, 'chunk_min_planes': 1, 'gpu_tables': 0},
-                                  {'chunks': 3, 'chunk_min_planes': 2, 'tma': 0}, {'label_fast': 0}, {'fused_runs': 0}, {'fused_runs': 0, 'tma': 0}])
+                                  {'chunks': 3, 'chunk_min_planes': 2, 'tma': 0, 'plane_kernel': 0}, {'label_fast': 0, 'coop_global': 0},
+                                  {'coop_global': 0}, {'fill_ctas': 0}, {'fill_late': 1, 'plane_kernel': 1}])
 def test_kernel_variants_give_identical_results(eng, fixture_cube, golden, opts):
-    """Every selectable kernel variant (load depth, bulk-copy staging with 16 warps, row-wise sparse paint, dense paint,
-    host table phase) must produce the same bytes."""
+    """Every selectable path (plain-load threshold kernel, dense paint, host table phase, chunked global-memory table
+    kernels, per-step ordered-phase kernels instead of the cooperative one, uncapped / late zero fill) must produce the same
+    bytes."""
     a, lat, lon = fixture_cube
-    defaults = {'tma': 3, 'paint_runs': 1, 'overlap_zero': 1, 'gpu_tables': 1, 'chunks': 4, 'chunk_min_planes': 1024,
-                'label_fast': 1, 'fused_runs': 1}
+    defaults = {'tma': 1, 'overlap_zero': 1, 'gpu_tables': 1, 'chunks': 4, 'chunk_min_planes': 1024, 'label_fast': 1,
+                'plane_kernel': 2, 'coop_global': 1, 'fill_ctas': 2, 'fill_late': 0}
     for k, v in opts.items():
         eng.set_option(k, v)
     try:
@@ -379,7 +380,7 @@ def test_label_granular_track_matches_component_replay(eng, reference_run):
     assert fast_used > 0 and fallback_used > 0, (fast_used, fallback_used)
 
 
-@pytest.mark.parametrize('tma', [3, 0])
+@pytest.mark.parametrize('tma', [1, 0])
 @pytest.mark.parametrize('W', [1440, 1024, 2048, 96, 33, 1028, 36])
 def test_runs_from_threshold_kernel_edge_cases(eng, W, tma):
     """Row-runs come out of the threshold kernel (8 slots per row): rows with more runs than slots (noise), runs that end
@@ -401,10 +402,10 @@ def test_runs_from_threshold_kernel_edge_cases(eng, W, tma):
     try:
         f, n = eng.run_contrack(torch.from_numpy(x).cuda(), w, 120, True, 0, 0.2, 1, True)
         st = eng.stats()
-        eng.set_option('fused_runs', 0)
+        eng.set_option('plane_kernel', 0)                                  # the global-memory table kernels read the same slots
         f0, n0 = eng.run_contrack(torch.from_numpy(x).cuda(), w, 120, True, 0, 0.2, 1, True)
     finally:
-        eng.set_option('tma', 3); eng.set_option('fused_runs', 1)
+        eng.set_option('tma', 1); eng.set_option('plane_kernel', 2)
     assert np.array_equal(f.cpu().numpy(), ref) and n == len(np.unique(ref)) - 1
     assert np.array_equal(f0.cpu().numpy(), ref)
     if W >= 96:

@@ -57,8 +57,6 @@ std::string& last_error() {
 
 namespace {
 
-inline int W_of(const ct_ctx* c) { return c->W; }
-
 struct DeviceRunSource : cth::RunSource {
     ct_ctx* c;
     cudaStream_t st;
@@ -507,58 +505,6 @@ int tables_d2h(ct_ctx* c, int full, cudaStream_t st) {
     return CT_OK;
 }
 
-// Steps 3 and 4a/b on the device: Jacobi sweeps to the fixpoint of the keep/kill recurrence, then 3-D labels.
-// *nflag_out = verdicts that would need the exact (numpy-order) resolver: the caller then falls back to the host phase.
-int gpu_step3_link(ct_ctx* c, double overlap, int twosided, long* nflag_out, long* nlabels_out, cudaStream_t st) {
-    const long nc = c->ncomp;
-    uint32_t* cnt_dev = c->counters.as<uint32_t>();
-    uint32_t* cnt_host = c->hp_counters.as<uint32_t>();
-    CT_CUDA(c->l_parent.ensure((size_t)(nc + 2) * 4)); CT_CUDA(c->l_flag.ensure((size_t)(nc + 2) * 4));
-    CT_CUDA(c->l_rank.ensure((size_t)(nc + 2) * 4)); CT_CUDA(c->l_label.ensure((size_t)(nc + 2) * 4));
-    CT_CUDA(c->l_kept.ensure((size_t)nc + 16)); CT_CUDA(c->l_accE.ensure((size_t)(nc + 2) * 8));
-    CT_CUDA(c->l_accS.ensure((size_t)(nc + 2) * 8)); CT_CUDA(c->l_accN.ensure((size_t)(nc + 2) * 4));
-    ctk::Step3Tables t;
-    t.comp_t = c->c_t.as<int32_t>(); t.cls = c->c_cls.as<uint32_t>();
-    t.conE = c->k_conE.as<double>(); t.conS = c->k_conS.as<double>(); t.fE = c->k_fE.as<double>();
-    t.fS = c->k_fS.as<double>(); t.nsp = c->k_nsp.as<uint32_t>(); t.fnsp = c->k_fnsp.as<uint32_t>();
-    t.pair_ptr = c->pptr.as<uint32_t>(); t.pair_b = c->p_b.as<uint32_t>(); t.pair_npix = c->p_npix.as<uint32_t>();
-    t.pair_nsp = c->p_nsp.as<uint32_t>(); t.pair_E = c->p_E.as<double>(); t.pair_S = c->p_S.as<double>();
-    t.kept = c->l_kept.as<uint8_t>(); t.accE = c->l_accE.as<double>(); t.accS = c->l_accS.as<double>();
-    t.accN = c->l_accN.as<uint32_t>();
-    const double t_g0 = now_ms();
-    CT_CUDA(ctk::step3_init(t, nc, st));
-    c->launches += 1;
-    // counters 8..8+BATCH-1: "changed" per sweep of a batch; counter 7: near-tie flags of the latest sweep
-    const int BATCH = 4;
-    long sweeps = 0;
-    for (;;) {
-        CT_CUDA(cudaMemsetAsync(cnt_dev + 8, 0, BATCH * 4, st));
-        for (int i = 0; i < BATCH; ++i) {
-            CT_CUDA(cudaMemsetAsync(cnt_dev + 7, 0, 4, st));
-            CT_CUDA(ctk::step3_sweep(t, nc, c->T, overlap, twosided, c->special_uniform, cnt_dev + 8 + i, cnt_dev + 7, st));
-            c->launches += 2;
-        }
-        sweeps += BATCH;
-        CT_CUDA(cudaMemcpyAsync(cnt_host + 7, cnt_dev + 7, (1 + BATCH) * 4, cudaMemcpyDeviceToHost, st));
-        CT_CUDA(cudaStreamSynchronize(st));
-        if (cnt_host[8 + BATCH - 1] == 0) break;                     // the last sweep of the batch changed nothing
-        if (sweeps > c->T + BATCH) return fail(CT_ERR_INTERNAL, "step-3 sweeps did not converge");
-    }
-    c->stats["sweeps"] = (double)sweeps;
-    c->stats["ms_g_sweeps"] = now_ms() - t_g0;
-    *nflag_out = cnt_host[7];
-    if (*nflag_out) return CT_OK;
-    CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(nc + 1) * 4));
-    CT_CUDA(ctk::link3d(t, nc, c->l_parent.as<uint32_t>(), c->l_flag.as<uint32_t>(), c->l_rank.as<uint32_t>(),
-                        c->scan_tmp.as<uint32_t>(), c->l_label.as<int32_t>(), st));
-    c->launches += 7;
-    CT_CUDA(cudaMemcpyAsync(cnt_host + 6, c->l_rank.as<uint32_t>() + nc, 4, cudaMemcpyDeviceToHost, st));
-    CT_CUDA(cudaStreamSynchronize(st));
-    *nlabels_out = nc ? cnt_host[6] : 0;
-    c->stats["ms_g_link"] = now_ms() - t_g0 - c->stats["ms_g_sweeps"];
-    return CT_OK;
-}
-
 // Upload the value of every component (and the override sub-runs) and resolve them to a value per row-run.
 int upload_values(ct_ctx* c, const int32_t* comp_val_pinned, const std::vector<ctb::Override>& overrides, cudaStream_t st) {
     const long nc = c->ncomp, R = c->nruns;
@@ -588,200 +534,16 @@ int upload_values(ct_ctx* c, const int32_t* comp_val_pinned, const std::vector<c
     return CT_OK;
 }
 
-// Everything between the two cube-sized kernels.  On return the value per row-run and the override sub-runs are on the
-// device.
+// The ordered phase on the HOST (ct_host.cpp: the reference's loops replayed on the tables, exact near-tie resolver, stale-box
+// splits at run granularity): what the device path (cooperative global kernel + event replay, ct_fast.cu) falls back to when
+// a verdict sits within rounding distance of `overlap` on rows that do not sum exactly or a label straddles a stale box, and
+// what the debug stages and "gpu_tables" = 0 use.  On return the value per row-run and the override sub-runs are on the device.
 int table_phase(ct_ctx* c, double overlap, int persistence, int twosided, int stage, long* n_features, cudaStream_t st,
                 bool tables_built = false) {
     int rc0 = tables_built ? CT_OK : tables_build(c, st);
     if (rc0 != CT_OK) return rc0;
     const long nc = c->ncomp;
     cth::FastTables& tb = c->host_tb;
-    if (c->opt_gpu_tables && stage != CT_STAGE_LABEL2D && stage != CT_STAGE_SEAM2D) {
-        // ---- steps 3 and 4a/b on the device; the host only replays the (few) date-line events and persistence ----
-        long nflag = 0, nlab = 0;
-        if ((rc0 = gpu_step3_link(c, overlap, twosided, &nflag, &nlab, st)) != CT_OK) return rc0;
-        c->stats["neartie_flagged"] = (double)nflag;
-        if (nflag == 0 && stage == CT_STAGE_FINAL) {
-            // ---- steps 4c/4d: per-label boxes and member lists on the device; the host replays only the date-line events
-            // that join two different labels and applies the persistence rule per label ----
-            const size_t lb = (size_t)(nlab + 4) * 4;
-            DevBuf* lbufs[] = {&c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
-                               &c->b_fin};
-            for (DevBuf* b : lbufs) CT_CUDA(b->ensure(lb));
-            CT_CUDA(c->b_order.ensure((size_t)(nc + 1) * 4));
-            ctk::LabelDev ld;
-            ld.t0 = c->b_t0.as<int32_t>(); ld.t1 = c->b_t1.as<int32_t>(); ld.y0 = c->b_y0.as<int32_t>();
-            ld.y1 = c->b_y1.as<int32_t>(); ld.x0 = c->b_x0.as<int32_t>(); ld.x1 = c->b_x1.as<int32_t>();
-            ld.cnt = c->b_cnt.as<uint32_t>(); ld.fill = c->b_fill.as<uint32_t>(); ld.ptr = c->b_ptr.as<uint32_t>();
-            ld.order = c->b_order.as<uint32_t>();
-            ctk::CompTables ctd;
-            ctd.t = c->c_t.as<int32_t>(); ctd.y0 = c->c_y0.as<int32_t>(); ctd.y1 = c->c_y1.as<int32_t>();
-            ctd.x0 = c->c_x0.as<int32_t>(); ctd.x1 = c->c_x1.as<int32_t>(); ctd.areaE = nullptr; ctd.areaS = nullptr;
-            ctd.nsp = nullptr; ctd.cls = nullptr;
-            CT_CUDA(c->scan_tmp.ensure(ctk::scan_tmp_elems(nlab + 2) * 4));
-            CT_CUDA(ctk::label_tables(ctd, c->l_label.as<int32_t>(), nc, ld, nlab, c->scan_tmp.as<uint32_t>(), st));
-            c->launches += 6;
-            const long nsg = c->nseg;
-            CT_CUDA(c->b_sla.ensure((size_t)(nsg + 1) * 4)); CT_CUDA(c->b_slb.ensure((size_t)(nsg + 1) * 4));
-            CT_CUDA(ctk::seg_labels(c->g_a.as<uint32_t>(), c->g_b.as<uint32_t>(), c->l_label.as<int32_t>(), nsg,
-                                    c->b_sla.as<int32_t>(), c->b_slb.as<int32_t>(), st));
-            c->launches += nsg ? 1 : 0;
-            CT_CUDA(cudaEventRecord(c->ev[2], st));
-            const size_t nl1 = (size_t)nlab + 2;
-            CT_CUDA(c->hp_labels.ensure((nl1 * 7 + (size_t)nc * 2 + 2 * (size_t)nsg + 16) * 4));
-            int32_t* hl = c->hp_labels.as<int32_t>();
-            int32_t *h_t0 = hl, *h_t1 = hl + nl1, *h_y0 = hl + 2 * nl1, *h_y1 = hl + 3 * nl1, *h_x0 = hl + 4 * nl1,
-                    *h_x1 = hl + 5 * nl1;
-            uint32_t* h_lptr = reinterpret_cast<uint32_t*>(hl + 6 * nl1);
-            uint32_t* h_lorder = reinterpret_cast<uint32_t*>(hl + 7 * nl1);
-            int32_t* hlabel = hl + 7 * nl1 + nc + 1;
-            int32_t* h_sla = hlabel + nc + 1;
-            int32_t* h_slb = h_sla + nsg;
-            const size_t lbytes = (size_t)(nlab + 1) * 4;
-            CT_CUDA(cudaMemcpyAsync(h_t0, ld.t0, lbytes, cudaMemcpyDeviceToHost, st));
-            CT_CUDA(cudaMemcpyAsync(h_t1, ld.t1, lbytes, cudaMemcpyDeviceToHost, st));
-            CT_CUDA(cudaMemcpyAsync(h_y0, ld.y0, lbytes, cudaMemcpyDeviceToHost, st));
-            CT_CUDA(cudaMemcpyAsync(h_y1, ld.y1, lbytes, cudaMemcpyDeviceToHost, st));
-            CT_CUDA(cudaMemcpyAsync(h_x0, ld.x0, lbytes, cudaMemcpyDeviceToHost, st));
-            CT_CUDA(cudaMemcpyAsync(h_x1, ld.x1, lbytes, cudaMemcpyDeviceToHost, st));
-            if (c->opt_label_fast) {
-                // ---- fast path: whole labels move; only the label boxes and the labels of the segment ends travel ----
-                if (nsg) {
-                    CT_CUDA(cudaMemcpyAsync(h_sla, c->b_sla.p, (size_t)nsg * 4, cudaMemcpyDeviceToHost, st));
-                    CT_CUDA(cudaMemcpyAsync(h_slb, c->b_slb.p, (size_t)nsg * 4, cudaMemcpyDeviceToHost, st));
-                }
-                const double t_f0 = now_ms();
-                CT_CUDA(cudaStreamSynchronize(st));
-                const double t_f1 = now_ms();
-                ctb::LabelTables lt;
-                lt.nlabel = (int)nlab; lt.t0 = h_t0; lt.t1 = h_t1; lt.y0 = h_y0; lt.y1 = h_y1; lt.x0 = h_x0; lt.x1 = h_x1;
-                static thread_local std::vector<int32_t> lab_fin;
-                ctb::TrackStats ts;
-                if (ctb::track_labels_fast(persistence, lt, nsg, h_sla, h_slb, lab_fin, ts) == 0) {
-                    cth::Result& res = c->host_result;
-                    res.overrides.clear();
-                    res.n_neartie = 0; res.n_labels3d = nlab; res.n_features = ts.n_features;
-                    res.n_seam_events = ts.n_events; res.n_seam_splits = 0;
-                    c->stats["ms_g_labels_d2h"] = t_f1 - t_f0;
-                    c->stats["ms_host_tables"] = now_ms() - t_f1;
-                    c->stats["ms_ht_events"] = ts.ms_events; c->stats["ms_ht_persist"] = ts.ms_persist;
-                    c->stats["ht_walked"] = (double)ts.n_walked; c->stats["label_fast"] = 1.0;
-                    CT_CUDA(c->hp_val.ensure(((size_t)nlab + 8) * 4));
-                    memcpy(c->hp_val.p, lab_fin.data(), (size_t)(nlab + 1) * 4);
-                    CT_CUDA(cudaMemcpyAsync(c->b_fin.p, c->hp_val.p, (size_t)(nlab + 1) * 4, cudaMemcpyHostToDevice, st));
-                    CT_CUDA(ctk::final_values(c->l_label.as<int32_t>(), c->b_fin.as<int32_t>(), nc, nullptr, nullptr, 0,
-                                              c->c_val.as<int32_t>(), st));
-                    c->launches += 1;
-                    int rcu;
-                    if ((rcu = upload_values(c, nullptr, res.overrides, st)) != CT_OK) return rcu;
-                    c->stats["labels3d"] = (double)nlab; c->stats["features"] = (double)res.n_features;
-                    c->stats["seam_events"] = (double)res.n_seam_events; c->stats["seam_splits"] = 0.0;
-                    c->stats["neartie_resolved"] = 0.0; c->stats["moved_comps"] = 0.0;
-                    if (n_features) *n_features = res.n_features;
-                    return CT_OK;
-                }
-                c->stats["label_fast"] = 0.0;         // a label straddles a stale box: replay per component below
-            }
-            CT_CUDA(cudaMemcpyAsync(h_lptr, ld.ptr, lbytes + 4, cudaMemcpyDeviceToHost, st));
-            if (nc) {
-                CT_CUDA(cudaMemcpyAsync(h_lorder, ld.order, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
-                CT_CUDA(cudaMemcpyAsync(hlabel, c->l_label.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
-            }
-            const double t_lab0 = now_ms();
-            if ((rc0 = tables_d2h(c, 0, st)) != CT_OK) return rc0;      // component boxes + segments; synchronizes
-            const double t_host0 = now_ms();
-            c->stats["ms_g_labels_d2h"] = t_host0 - t_lab0;
-            cth::Result& res = c->host_result;
-            res.n_neartie = 0; res.n_labels3d = nlab; res.n_kept = h_lptr[nlab + 1];
-            static thread_local std::vector<int32_t> sa32, sb32, fin, mc, ml;
-            sa32.resize(tb.nseg); sb32.resize(tb.nseg);
-            for (long i = 0; i < tb.nseg; ++i) { sa32[i] = (int32_t)tb.seg_a[i]; sb32[i] = (int32_t)tb.seg_b[i]; }
-            ctb::LabelTables lt;
-            lt.nlabel = (int)nlab; lt.t0 = h_t0; lt.t1 = h_t1; lt.y0 = h_y0; lt.y1 = h_y1; lt.x0 = h_x0; lt.x1 = h_x1;
-            lt.lptr = h_lptr; lt.lorder = h_lorder;
-            DeviceRunSource dsrc;
-            dsrc.c = c; dsrc.st = st;
-            CallbackRunSource csrc;
-            csrc.fn = c->fetch_fn; csrc.user = c->fetch_user;
-            cth::RunSource& src = c->fetch_fn ? static_cast<cth::RunSource&>(csrc) : static_cast<cth::RunSource&>(dsrc);
-            struct Fetch : ctb::RunFetcher {
-                cth::RunSource* src; const int32_t* comp_t; std::vector<cth::PlaneRun> buf;
-                bool fetch(long comp, std::vector<ctb::SubRun>& out) override {
-                    if (!src->plane_runs(comp_t[comp], buf)) return false;
-                    out.clear();
-                    for (const cth::PlaneRun& r : buf) if ((long)r.comp == comp) out.push_back(ctb::SubRun{r.y, r.x0, r.x1});
-                    return !out.empty();
-                }
-            } fetcher;
-            fetcher.src = &src; fetcher.comp_t = tb.comp_t;
-            ctb::TrackStats tstats;
-            int rc = ctb::track_tables_sparse(W_of(c), persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0,
-                                              tb.comp_x1, hlabel, lt, tb.nseg, tb.seg_y0, tb.seg_y1, sa32.data(),
-                                              sb32.data(), &fetcher, fin, mc, ml, res.overrides, tstats);
-            if (rc != 0) return fail(CT_ERR_INTERNAL, "date-line merge could not fetch the runs of a component to split");
-            res.n_features = tstats.n_features; res.n_seam_events = tstats.n_events; res.n_seam_splits = tstats.n_splits;
-            c->stats["ms_host_tables"] = now_ms() - t_host0;
-            c->stats["ms_ht_init"] = tstats.ms_init; c->stats["ms_ht_events"] = tstats.ms_events;
-            c->stats["ms_ht_persist"] = tstats.ms_persist; c->stats["ht_walked"] = (double)tstats.n_walked;
-            // surviving value per label + the re-labelled components -> value per component on the device
-            const long nm = (long)mc.size();
-            CT_CUDA(c->hp_val.ensure(((size_t)nlab + 2 + 2 * (size_t)nm + 8) * 4));
-            int32_t* hv = c->hp_val.as<int32_t>();
-            memcpy(hv, fin.data(), (size_t)(nlab + 1) * 4);
-            if (nm) { memcpy(hv + nlab + 1, mc.data(), (size_t)nm * 4); memcpy(hv + nlab + 1 + nm, ml.data(), (size_t)nm * 4); }
-            CT_CUDA(c->b_mc.ensure((size_t)(nm + 1) * 4)); CT_CUDA(c->b_ml.ensure((size_t)(nm + 1) * 4));
-            CT_CUDA(cudaMemcpyAsync(c->b_fin.p, hv, (size_t)(nlab + 1) * 4, cudaMemcpyHostToDevice, st));
-            if (nm) {
-                CT_CUDA(cudaMemcpyAsync(c->b_mc.p, hv + nlab + 1, (size_t)nm * 4, cudaMemcpyHostToDevice, st));
-                CT_CUDA(cudaMemcpyAsync(c->b_ml.p, hv + nlab + 1 + nm, (size_t)nm * 4, cudaMemcpyHostToDevice, st));
-            }
-            CT_CUDA(ctk::final_values(c->l_label.as<int32_t>(), c->b_fin.as<int32_t>(), nc, c->b_mc.as<int32_t>(),
-                                      c->b_ml.as<int32_t>(), nm, c->c_val.as<int32_t>(), st));
-            c->launches += nm ? 2 : 1;
-            if ((rc = upload_values(c, nullptr, res.overrides, st)) != CT_OK) return rc;
-            c->stats["kept_comps"] = (double)res.n_kept;
-            c->stats["labels3d"] = (double)res.n_labels3d; c->stats["features"] = (double)res.n_features;
-            c->stats["seam_events"] = (double)res.n_seam_events; c->stats["seam_splits"] = (double)res.n_seam_splits;
-            c->stats["neartie_resolved"] = 0.0; c->stats["moved_comps"] = (double)nm;
-            if (n_features) *n_features = res.n_features;
-            return CT_OK;
-        }
-        if (nflag == 0) {
-            CT_CUDA(cudaEventRecord(c->ev[2], st));
-            CT_CUDA(c->hp_val.ensure((size_t)(nc + 1) * 8 + (size_t)nc + 64));
-            int32_t* hv = c->hp_val.as<int32_t>();
-            int32_t* hlabel = hv + nc + 1;
-            uint8_t* hkept = reinterpret_cast<uint8_t*>(hlabel + nc + 1);
-            if (nc) {
-                CT_CUDA(cudaMemcpyAsync(hlabel, c->l_label.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
-                CT_CUDA(cudaMemcpyAsync(hkept, c->l_kept.p, (size_t)nc, cudaMemcpyDeviceToHost, st));
-            }
-            if ((rc0 = tables_d2h(c, 0, st)) != CT_OK) return rc0;      // synchronizes
-            const double t_host0 = now_ms();
-            cth::Result& res = c->host_result;
-            res.overrides.clear();
-            res.n_neartie = 0; res.n_features = 0; res.n_seam_events = 0; res.n_seam_splits = 0;
-            res.n_labels3d = c->hp_counters.as<uint32_t>()[6];
-            long nkept = 0;
-            for (long i = 0; i < nc; ++i) nkept += hkept[tb.comp_cls[i]];
-            res.n_kept = nkept;
-            if (stage == CT_STAGE_FILTERED) {
-                for (long i = 0; i < nc; ++i) hv[i] = hkept[tb.comp_cls[i]] ? (int32_t)(tb.comp_cls[i] + 1) : 0;
-            } else if (stage == CT_STAGE_LABEL3D) {
-                if (nc) memcpy(hv, hlabel, (size_t)nc * 4);
-            }
-            c->stats["ms_host_tables"] = now_ms() - t_host0;
-            int rc = upload_values(c, hv, res.overrides, st);
-            if (rc != CT_OK) return rc;
-            c->stats["kept_comps"] = (double)res.n_kept;
-            c->stats["labels3d"] = (double)res.n_labels3d; c->stats["features"] = (double)res.n_features;
-            c->stats["seam_events"] = (double)res.n_seam_events; c->stats["seam_splits"] = (double)res.n_seam_splits;
-            c->stats["neartie_resolved"] = 0.0;
-            if (n_features) *n_features = res.n_features;
-            return CT_OK;
-        }
-        // a verdict sits within rounding distance of `overlap` on rows that do not sum exactly: replay on the host
-    }
     CT_CUDA(cudaEventRecord(c->ev[2], st));
     if ((rc0 = tables_d2h(c, 1, st)) != CT_OK) return rc0;
 
@@ -873,7 +635,7 @@ int solve_tables(ct_ctx* c, long T, long nchunk, long cp, WaitFn wait_chunk, dou
     }
     if (rc == CT_OK) rc = tables_finish(c, ts);
     if (rc != CT_OK) return rc;
-    if (stage == CT_STAGE_FINAL && c->opt_gpu_tables && c->opt_coop_global) {
+    if (stage == CT_STAGE_FINAL && c->opt_gpu_tables) {
         // the cooperative global kernel on these tables: their counts are known to the host, the control block is written here
         if ((rc = ctf::ensure_global_scratch(c, (size_t)c->ncomp, (size_t)c->nseg)) != CT_OK) return rc;
         struct { uint32_t w[4]; unsigned long long tot[4]; } ctl = {{0, 0, 0, 0},
@@ -1090,11 +852,9 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "host_out_zeroed")) { c->opt_host_out_zeroed = value; return CT_OK; }
     if (!strcmp(key, "fill_late")) { c->opt_fill_late = value; return CT_OK; }
     if (!strcmp(key, "fill_ctas")) { c->opt_fill_ctas = value; return CT_OK; }
-    if (!strcmp(key, "label_fast")) { c->opt_label_fast = value; return CT_OK; }
     if (!strcmp(key, "profile_tables")) { c->opt_profile_tables = value; return CT_OK; }
     if (!strcmp(key, "plane_kernel")) { c->opt_plane_kernel = value; return CT_OK; }
     if (!strcmp(key, "plane_max_planes")) { c->opt_plane_max_planes = value; return CT_OK; }
-    if (!strcmp(key, "coop_global")) { c->opt_coop_global = value; return CT_OK; }
     if (!strcmp(key, "fast_chunks")) { c->opt_fast_chunks = value < 1 ? 1 : value; return CT_OK; }
     if (!strcmp(key, "max_sweeps")) { c->opt_max_sweeps = value < 1 ? 1 : value; return CT_OK; }
     if (!strcmp(key, "plane_smem")) { c->opt_plane_smem = value; c->pl_budget = 0; return CT_OK; }

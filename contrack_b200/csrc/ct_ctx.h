@@ -162,7 +162,6 @@ struct ct_ctx {
     long opt_fill_late = 0;                   // plane-kernel path: 1 = the zero fill starts after the plane kernel (0: beside it)
     int32_t* pend_fill = nullptr;             // ... the fill ctf::finish() has to start
     size_t pend_fill_cells = 0;
-    long opt_label_fast = 1;                  // steps 4c/4d at label granularity on the host (fallback: per component)
     long opt_profile_tables = 0;              // debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"
     std::vector<std::pair<std::string, cudaEvent_t>> prof;
     size_t prof_used = 0;
@@ -177,7 +176,6 @@ struct ct_ctx {
     // ---- fast path (ct_fast.cu): per-plane table kernel + cooperative global kernel, no host round trip between them ----
     long opt_plane_kernel = 2;               // tables: 0 = global-memory kernels of ct_kernels.cu, 1 = plane kernel, 2 = by size
     long opt_plane_max_planes = 4096;        // ... plane kernel up to this many planes per context
-    long opt_coop_global = 1;                // ordered phase: cooperative global kernel (0: per-step kernels + host round trips)
     long opt_fast_chunks = 1;                // time chunks of the fast path (1: the plane kernel runs beside the zero fill)
     long opt_max_sweeps = 32;                // Jacobi sweeps of step 3 before the plane-ordered wavefront takes over
     long opt_plane_smem = 0;                 // shared-memory budget of the plane kernel in bytes (0 = automatic)

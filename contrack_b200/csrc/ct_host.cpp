@@ -268,88 +268,57 @@ int track_phase(const FastTables& tb, const int32_t* label, int persistence, Run
     fetcher.pc = &pc; fetcher.comp_t = tb.comp_t;
     ctb::TrackStats stats;
     int rc;
-    if (getenv("CT_TRACK_SPARSE")) {
-        // test hook: reduce the per-label tables here (the device does it in the product path) and run the sparse variant
+    if (getenv("CT_TRACK_EVENTS")) {
+        // test hook: what the cooperative global kernel + track_events_fast do in the product path -- label boxes, persistence
+        // of every label from its own box, the event list (segments whose ends carry different labels, as indices into the
+        // records of the labels that occur in events), the replay on the events alone, patches on top.  Falls through to the
+        // per-component replay when a label straddles a stale box.
         int nlabel = 0;
         for (long c = 0; c < nc; ++c) nlabel = std::max(nlabel, (int)label[c]);
         std::vector<int32_t> t0(nlabel + 1, INT32_MAX), t1(nlabel + 1, 0), y0(nlabel + 1, INT32_MAX), y1(nlabel + 1, 0),
             x0(nlabel + 1, INT32_MAX), x1(nlabel + 1, 0);
-        std::vector<uint32_t> lptr(nlabel + 2, 0), lorder(nc);
         for (long c = 0; c < nc; ++c) {
             const int v = label[c];
             if (!v) continue;
             t0[v] = std::min(t0[v], tb.comp_t[c]); t1[v] = std::max(t1[v], tb.comp_t[c] + 1);
             y0[v] = std::min(y0[v], tb.comp_y0[c]); y1[v] = std::max(y1[v], tb.comp_y1[c]);
             x0[v] = std::min(x0[v], tb.comp_x0[c]); x1[v] = std::max(x1[v], tb.comp_x1[c]);
-            lptr[v + 1]++;
         }
-        for (int v = 0; v <= nlabel; ++v) lptr[v + 1] += lptr[v];
-        {
-            std::vector<uint32_t> pos(lptr.begin(), lptr.end() - 1);
-            for (long c = nc - 1; c >= 0; --c) if (label[c]) lorder[pos[label[c]]++] = (uint32_t)c;   // any order will do
+        std::vector<int32_t> ev, lrec, lidx(nlabel + 1, -1), lab_fin;
+        for (long s = 0; s < tb.nseg; ++s) {
+            const int la = label[seg_a32[s]], lb = label[seg_b32[s]];
+            if (la == 0 || lb == 0 || la == lb) continue;
+            lidx[la] = 0; lidx[lb] = 0;
         }
-        ctb::LabelTables lt;
-        lt.nlabel = nlabel; lt.t0 = t0.data(); lt.t1 = t1.data(); lt.y0 = y0.data(); lt.y1 = y1.data();
-        lt.x0 = x0.data(); lt.x1 = x1.data(); lt.lptr = lptr.data(); lt.lorder = lorder.data();
-        std::vector<int32_t> fin, mc, ml;
-        if (getenv("CT_TRACK_LABELS")) {
-            // test hook: the label-granular pass of the product path; returns 1 when a label straddles a stale box
-            std::vector<int32_t> sla(tb.nseg), slb(tb.nseg), lab_fin;
-            for (long s = 0; s < tb.nseg; ++s) { sla[s] = label[seg_a32[s]]; slb[s] = label[seg_b32[s]]; }
-            if (getenv("CT_TRACK_EVENTS")) {
-                // test hook: what the cooperative global kernel + track_events_fast do in the product path -- persistence of
-                // every label from its own box, the event list (segments whose ends carry different labels, with both
-                // boxes), the replay on the events alone, patches on top
-                std::vector<int32_t> ev, lrec, lidx(nlabel + 1, -1);
-                for (long s = 0; s < tb.nseg; ++s) {
-                    const int la = sla[s], lb = slb[s];
-                    if (la == 0 || lb == 0 || la == lb) continue;
-                    lidx[la] = 0; lidx[lb] = 0;
-                }
-                for (int v = 1; v <= nlabel; ++v) {
-                    if (lidx[v] < 0) continue;
-                    lidx[v] = (int32_t)(lrec.size() / 7);
-                    const int32_t r[7] = {v, t0[v], t1[v], y0[v], y1[v], x0[v], x1[v]};
-                    lrec.insert(lrec.end(), r, r + 7);
-                }
-                for (long s = 0; s < tb.nseg; ++s) {
-                    const int la = sla[s], lb = slb[s];
-                    if (la == 0 || lb == 0 || la == lb) continue;
-                    ev.push_back(lidx[la]); ev.push_back(lidx[lb]);
-                }
-                std::vector<int32_t> pl, pv;
-                long delta = 0, feats = 0;
-                if (ctb::track_events_fast(persistence, (long)ev.size() / 2, ev.data(), (long)lrec.size() / 7, lrec.data(), pl, pv,
-                                           &delta, stats) == 0) {
-                    lab_fin.assign(nlabel + 1, 0);
-                    for (int v = 1; v <= nlabel; ++v) {
-                        const bool keep = t1[v] > t0[v] && (t1[v] - t0[v]) >= persistence;
-                        lab_fin[v] = keep ? v : 0; feats += keep;
-                    }
-                    for (size_t i = 0; i < pl.size(); ++i) lab_fin[pl[i]] = pv[i];
-                    for (long c = 0; c < nc; ++c) comp_val[c] = lab_fin[label[c]];
-                    out.overrides.clear();
-                    out.n_features = feats + delta; out.n_seam_events = stats.n_events; out.n_seam_splits = 0;
-                    out.n_neartie += 1000000;
-                    return 0;
-                }
-            } else
-            if (ctb::track_labels_fast(persistence, lt, tb.nseg, sla.data(), slb.data(), lab_fin, stats) == 0) {
-                for (long c = 0; c < nc; ++c) comp_val[c] = lab_fin[label[c]];
-                out.overrides.clear();
-                out.n_features = stats.n_features; out.n_seam_events = stats.n_events; out.n_seam_splits = 0;
-                out.n_neartie += 1000000;           // marker for the test: the fast pass produced this result
-                return 0;
+        for (int v = 1; v <= nlabel; ++v) {
+            if (lidx[v] < 0) continue;
+            lidx[v] = (int32_t)(lrec.size() / 7);
+            const int32_t r[7] = {v, t0[v], t1[v], y0[v], y1[v], x0[v], x1[v]};
+            lrec.insert(lrec.end(), r, r + 7);
+        }
+        for (long s = 0; s < tb.nseg; ++s) {
+            const int la = label[seg_a32[s]], lb = label[seg_b32[s]];
+            if (la == 0 || lb == 0 || la == lb) continue;
+            ev.push_back(lidx[la]); ev.push_back(lidx[lb]);
+        }
+        std::vector<int32_t> pl, pv;
+        long delta = 0, feats = 0;
+        if (ctb::track_events_fast(persistence, (long)ev.size() / 2, ev.data(), (long)lrec.size() / 7, lrec.data(), pl, pv, &delta,
+                                   stats) == 0) {
+            lab_fin.assign(nlabel + 1, 0);
+            for (int v = 1; v <= nlabel; ++v) {
+                const bool keep = t1[v] > t0[v] && (t1[v] - t0[v]) >= persistence;
+                lab_fin[v] = keep ? v : 0; feats += keep;
             }
+            for (size_t i = 0; i < pl.size(); ++i) lab_fin[pl[i]] = pv[i];
+            for (long c = 0; c < nc; ++c) comp_val[c] = lab_fin[label[c]];
+            out.overrides.clear();
+            out.n_features = feats + delta; out.n_seam_events = stats.n_events; out.n_seam_splits = 0;
+            out.n_neartie += 1000000;           // marker for the test: the event replay produced this result
+            return 0;
         }
-        rc = ctb::track_tables_sparse(tb.W, persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0, tb.comp_x1,
-                                      label, lt, tb.nseg, tb.seg_y0, tb.seg_y1, seg_a32.data(), seg_b32.data(),
-                                      runs ? &fetcher : nullptr, fin, mc, ml, out.overrides, stats);
-        if (rc == 0) {
-            for (long c = 0; c < nc; ++c) comp_val[c] = fin[label[c]];
-            for (size_t i = 0; i < mc.size(); ++i) comp_val[mc[i]] = fin[ml[i]];
-        }
-    } else {
+    }
+    {
         rc = ctb::track_tables(tb.T, tb.H, tb.W, persistence, nc, tb.comp_t, tb.comp_y0, tb.comp_y1, tb.comp_x0,
                                tb.comp_x1, label, tb.nseg, tb.seg_t, tb.seg_y0, tb.seg_y1, seg_a32.data(),
                                seg_b32.data(), runs ? &fetcher : nullptr, comp_val, out.overrides, stats);

@@ -787,156 +787,6 @@ __global__ void __launch_bounds__(256) k_seg_write(const uint32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// step 3 on the device (contrack.py:706-742).  The keep/kill state of plane t depends on the FINAL state of plane t-1
-// only, so the recurrence has exactly one solution; Jacobi sweeps over all classes at once (state of the previous
-// sweep in, new state out) reach it: after sweep k every plane <= k is final, and in practice a handful of sweeps
-// suffice because a changed verdict rarely flips the verdict of its successors for more than a step or two.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool kill_decision_dev(double areacon, double fwd, double bwd, double ov, bool twosided,
-                                                  double* fb_out, double* ff_out) {
-    const double inv = __ddiv_rn(1.0, areacon);       // contrack.py:721-722: reciprocal, then multiply -- two roundings
-    const double fb = __dmul_rn(inv, bwd);
-    const double ff = __dmul_rn(inv, fwd);
-    *fb_out = fb; *ff_out = ff;
-    bool kill = false;
-    if (twosided) {
-        if (fb != 0 && ff != 0) { if ((fb < ov) || (ff < ov)) kill = true; }
-        if (fb != 0 && ff == 0) { if (fb < ov) kill = true; }
-        if (fb == 0 && ff != 0) { if (ff < ov) kill = true; }
-    } else {
-        if (ff < ov) kill = true;
-    }
-    return kill;
-}
-
-__global__ void __launch_bounds__(256) k_fill_u8(uint8_t* p, long n, uint8_t v) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
-// backward overlap with the components of plane t-1 that are currently kept, summed per class
-__global__ void __launch_bounds__(256) k_step3_acc(Step3Tables t, long ncomp, long T) {
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncomp) return;
-    const int tt = t.comp_t[c];
-    if (tt < 1 || tt + 1 >= T) return;
-    double e = 0.0, s2 = 0.0;
-    uint32_t n = 0;
-    const uint32_t k1 = t.pair_ptr[c + 1];
-    for (uint32_t k = t.pair_ptr[c]; k < k1; ++k) {
-        if (!t.kept[t.cls[t.pair_b[k]]]) continue;
-        e += t.pair_E[k]; s2 += t.pair_S[k]; n += t.pair_nsp[k];
-    }
-    const uint32_t rep = t.cls[c];
-    if (e != 0.0) atomicAdd(&t.accE[rep], e);
-    if (n) { atomicAdd(&t.accS[rep], s2); atomicAdd(&t.accN[rep], n); }
-}
-
-// one thread per class representative: verdict from the sums, reset of the accumulators, change / near-tie bookkeeping
-__global__ void __launch_bounds__(256) k_step3_decide(Step3Tables t, long ncomp, long T, double ov, int twosided,
-                                                      int special_uniform, uint32_t* __restrict__ changed,
-                                                      uint32_t* __restrict__ nflag) {
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncomp || t.cls[c] != (uint32_t)c) return;
-    const int tt = t.comp_t[c];
-    if (tt < 1 || tt + 1 >= T) return;
-    const double bE = t.accE[c], bS = t.accS[c];
-    const uint32_t bn = t.accN[c];
-    t.accE[c] = 0.0; t.accS[c] = 0.0; t.accN[c] = 0;
-    const double areacon = __dadd_rn(t.conE[c], t.conS[c]), fwd = __dadd_rn(t.fE[c], t.fS[c]), bwd = __dadd_rn(bE, bS);
-    double fb, ff;
-    const bool kill = kill_decision_dev(areacon, fwd, bwd, ov, twosided != 0, &fb, &ff);
-    if (t.nsp[c] + t.fnsp[c] + bn > 0) {
-        // sums with special-row weights are not exactly summable in general: a fraction within rounding distance of
-        // `overlap` must be decided in numpy's summation order (host).  Exception: a class that lies entirely in special
-        // rows of one common weight -- every sum is a small integer multiple of that weight, exact in any order.
-        const bool near = (fabs(ff - ov) <= 1e-9) || (twosided && fabs(fb - ov) <= 1e-9);
-        const bool exact = special_uniform && t.conE[c] == 0.0 && t.fE[c] == 0.0 && bE == 0.0;
-        if (near && !exact) atomicAdd(nflag, 1u);
-    }
-    const uint8_t nk = kill ? 0 : 1;
-    if (t.kept[c] != nk) { t.kept[c] = nk; *changed = 1u; }
-}
-
-// 3-D linking (contrack.py:747-751): kept components that share a pixel in adjacent planes
-__global__ void __launch_bounds__(256) k_link_union(Step3Tables t, long ncomp, uint32_t* parent) {
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncomp || !t.kept[t.cls[c]]) return;
-    const uint32_t k1 = t.pair_ptr[c + 1];
-    for (uint32_t k = t.pair_ptr[c]; k < k1; ++k) {
-        const uint32_t b = t.pair_b[k];
-        if (t.pair_npix[k] && t.kept[t.cls[b]]) uf_union(parent, (uint32_t)c, b);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_link_roots(Step3Tables t, long ncomp, uint32_t* parent,
-                                                    uint32_t* __restrict__ root_flag) {
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncomp) return;
-    if (!t.kept[t.cls[c]]) { root_flag[c] = 0; return; }
-    const uint32_t root = uf_find(parent, (uint32_t)c);
-    root_flag[c] = root == (uint32_t)c ? 1u : 0u;
-    if (root != (uint32_t)c) parent[c] = root;
-}
-
-// label = 1 + number of roots with a smaller id (scipy numbers 3-D components by first pixel); 0 for removed components
-__global__ void __launch_bounds__(256) k_link_labels(Step3Tables t, long ncomp, const uint32_t* __restrict__ parent,
-                                                     const uint32_t* __restrict__ rank, int32_t* __restrict__ label) {
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncomp) return;
-    label[c] = t.kept[t.cls[c]] ? (int32_t)(rank[uf_find(parent, (uint32_t)c)] + 1u) : 0;
-}
-
-// per-label tables for steps 4c/4d: 3-D box of every label, number of member components, members grouped by label
-__global__ void __launch_bounds__(256) k_label_init(LabelDev l, long n) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    l.t0[i] = INT_MAX; l.t1[i] = 0; l.y0[i] = INT_MAX; l.y1[i] = 0; l.x0[i] = INT_MAX; l.x1[i] = 0;
-    l.cnt[i] = 0; l.fill[i] = 0;
-}
-
-__global__ void __launch_bounds__(256) k_label_reduce(CompTables c, const int32_t* __restrict__ label, long ncomp,
-                                                      LabelDev l) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ncomp) return;
-    const int v = label[i];
-    if (v == 0) return;
-    atomicMin(&l.t0[v], c.t[i]); atomicMax(&l.t1[v], c.t[i] + 1);
-    atomicMin(&l.y0[v], c.y0[i]); atomicMax(&l.y1[v], c.y1[i]);
-    atomicMin(&l.x0[v], c.x0[i]); atomicMax(&l.x1[v], c.x1[i]);
-    atomicAdd(&l.cnt[v], 1u);
-}
-
-__global__ void __launch_bounds__(256) k_label_fill(const int32_t* __restrict__ label, long ncomp, LabelDev l) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ncomp) return;
-    const int v = label[i];
-    if (v == 0) return;
-    l.order[l.ptr[v] + atomicAdd(&l.fill[v], 1u)] = (uint32_t)i;
-}
-
-// value painted for a component = surviving value of its label; then the few re-labelled components
-__global__ void __launch_bounds__(256) k_final_values(const int32_t* __restrict__ label, const int32_t* __restrict__ fin,
-                                                      long ncomp, int32_t* __restrict__ val) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ncomp) val[i] = fin[label[i]];
-}
-
-// labels of the two components of every date-line segment (0 = removed)
-__global__ void __launch_bounds__(256) k_seg_labels(const uint32_t* __restrict__ seg_a, const uint32_t* __restrict__ seg_b,
-                                                    const int32_t* __restrict__ label, long nseg,
-                                                    int32_t* __restrict__ la, int32_t* __restrict__ lb) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nseg) { la[i] = label[seg_a[i]]; lb[i] = label[seg_b[i]]; }
-}
-
-__global__ void k_apply_moves(const int32_t* __restrict__ comp, const int32_t* __restrict__ newlabel,
-                              const int32_t* __restrict__ fin, long n, int32_t* __restrict__ val) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) val[comp[i]] = fin[newlabel[i]];
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // paint: bit rows + value per run -> int32 cube.  One warp per row, 1024 cells (32 mask words) per pass; a lane owns
 // four consecutive cells and stores them as one 16-byte streaming store.
 // ---------------------------------------------------------------------------------------------------------------
@@ -1301,60 +1151,6 @@ cudaError_t seg_write(const uint32_t* srow, const uint32_t* sa, const uint32_t* 
                       const uint32_t* segpos, long begin, long end, int H, const SegTables& o, cudaStream_t st) {
     if (end <= begin) return cudaSuccess;
     k_seg_write<<<blocks_for(end - begin, 256), 256, 0, st>>>(srow, sa, sb, start, segpos, begin, end, H, o);
-    return cudaGetLastError();
-}
-
-cudaError_t step3_init(const Step3Tables& t, long ncomp, cudaStream_t st) {
-    if (ncomp == 0) return cudaSuccess;
-    k_fill_u8<<<blocks_for(ncomp, 256), 256, 0, st>>>(t.kept, ncomp, 1);
-    cudaError_t e = cudaMemsetAsync(t.accE, 0, (size_t)ncomp * 8, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(t.accS, 0, (size_t)ncomp * 8, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(t.accN, 0, (size_t)ncomp * 4, st);
-    return e != cudaSuccess ? e : cudaGetLastError();
-}
-
-cudaError_t step3_sweep(const Step3Tables& t, long ncomp, long T, double overlap, int twosided, int special_uniform,
-                        uint32_t* changed, uint32_t* nflag, cudaStream_t st) {
-    if (ncomp == 0) return cudaSuccess;
-    k_step3_acc<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, T);
-    k_step3_decide<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, T, overlap, twosided, special_uniform, changed, nflag);
-    return cudaGetLastError();
-}
-
-cudaError_t link3d(const Step3Tables& t, long ncomp, uint32_t* parent, uint32_t* root_flag, uint32_t* rank,
-                   uint32_t* scan_tmp, int32_t* label, cudaStream_t st) {
-    if (ncomp == 0) return cudaMemsetAsync(rank, 0, 4, st);
-    k_iota<<<blocks_for(ncomp, 256), 256, 0, st>>>(parent, 0, ncomp);
-    k_link_union<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, parent);
-    k_link_roots<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, parent, root_flag);
-    cudaError_t e = exclusive_scan_u32(root_flag, rank, ncomp, scan_tmp, st);
-    if (e != cudaSuccess) return e;
-    k_link_labels<<<blocks_for(ncomp, 256), 256, 0, st>>>(t, ncomp, parent, rank, label);
-    return cudaGetLastError();
-}
-
-cudaError_t label_tables(const CompTables& c, const int32_t* label, long ncomp, const LabelDev& l, long nlabel,
-                         uint32_t* scan_tmp, cudaStream_t st) {
-    // entries 0 .. nlabel (label 0 = removed, stays empty); ptr gets nlabel + 2 entries
-    k_label_init<<<blocks_for(nlabel + 1, 256), 256, 0, st>>>(l, nlabel + 1);
-    if (ncomp) k_label_reduce<<<blocks_for(ncomp, 256), 256, 0, st>>>(c, label, ncomp, l);
-    cudaError_t e = exclusive_scan_u32(l.cnt, l.ptr, nlabel + 1, scan_tmp, st);
-    if (e != cudaSuccess) return e;
-    if (ncomp) k_label_fill<<<blocks_for(ncomp, 256), 256, 0, st>>>(label, ncomp, l);
-    return cudaGetLastError();
-}
-
-cudaError_t seg_labels(const uint32_t* seg_a, const uint32_t* seg_b, const int32_t* label, long nseg, int32_t* la,
-                       int32_t* lb, cudaStream_t st) {
-    if (nseg == 0) return cudaSuccess;
-    k_seg_labels<<<blocks_for(nseg, 256), 256, 0, st>>>(seg_a, seg_b, label, nseg, la, lb);
-    return cudaGetLastError();
-}
-
-cudaError_t final_values(const int32_t* label, const int32_t* fin, long ncomp, const int32_t* move_comp,
-                         const int32_t* move_label, long nmoves, int32_t* val, cudaStream_t st) {
-    if (ncomp) k_final_values<<<blocks_for(ncomp, 256), 256, 0, st>>>(label, fin, ncomp, val);
-    if (nmoves) k_apply_moves<<<blocks_for(nmoves, 256), 256, 0, st>>>(move_comp, move_label, fin, nmoves, val);
     return cudaGetLastError();
 }
 

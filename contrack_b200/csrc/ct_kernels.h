@@ -104,36 +104,6 @@ cudaError_t seg_write(const uint32_t* srow, const uint32_t* sa, const uint32_t* 
 // ctas_per_sm: 1..7 caps the resident blocks per SM (room for the table kernels beside the fill); 0 / 8 = no cap
 cudaError_t zero_fill(int32_t* p, size_t n, int sm_count, cudaStream_t st, int ctas_per_sm = 0);
 
-// ---- step 3 (overlap filter) and step 4a/b (3-D labels) on the device tables ----
-struct Step3Tables {
-    const int32_t* comp_t; const uint32_t* cls;
-    const double *conE, *conS, *fE, *fS; const uint32_t *nsp, *fnsp;          // per class, at the representative
-    const uint32_t *pair_ptr, *pair_b, *pair_npix, *pair_nsp; const double *pair_E, *pair_S;
-    uint8_t* kept;                           // [ncomp] verdict per class, stored at the representative (1 = kept)
-    double *accE, *accS; uint32_t* accN;     // [ncomp] backward sums of the running sweep (zero between sweeps)
-};
-cudaError_t step3_init(const Step3Tables& t, long ncomp, cudaStream_t st);
-// one Jacobi sweep: *changed is set to 1 if any verdict changed, *nflag counts verdicts that need the exact host resolver
-cudaError_t step3_sweep(const Step3Tables& t, long ncomp, long T, double overlap, int twosided, int special_uniform,
-                        uint32_t* changed, uint32_t* nflag, cudaStream_t st);
-// label[c] = scipy's 3-D label of component c (0 if removed); rank[ncomp] = number of labels
-cudaError_t link3d(const Step3Tables& t, long ncomp, uint32_t* parent, uint32_t* root_flag, uint32_t* rank,
-                   uint32_t* scan_tmp, int32_t* label, cudaStream_t st);
-
-// ---- per-label tables (boxes, member lists) and the final value per component ----
-struct LabelDev {
-    int32_t *t0, *t1, *y0, *y1, *x0, *x1;    // [nlabel + 1] half-open 3-D box of every label
-    uint32_t *cnt, *fill, *ptr, *order;      // cnt/fill [nlabel + 1], ptr [nlabel + 2], order [ncomp]
-};
-cudaError_t label_tables(const CompTables& c, const int32_t* label, long ncomp, const LabelDev& l, long nlabel,
-                         uint32_t* scan_tmp, cudaStream_t st);
-// la[s] / lb[s] = label of the component at x = 0 / x = W-1 of date-line segment s
-cudaError_t seg_labels(const uint32_t* seg_a, const uint32_t* seg_b, const int32_t* label, long nseg, int32_t* la,
-                       int32_t* lb, cudaStream_t st);
-// val[c] = fin[label[c]], then val[move_comp[i]] = fin[move_label[i]]
-cudaError_t final_values(const int32_t* label, const int32_t* fin, long ncomp, const int32_t* move_comp,
-                         const int32_t* move_label, long nmoves, int32_t* val, cudaStream_t st);
-
 // run_val[r] = comp_val[run_comp[r]]
 cudaError_t run_values(const uint32_t* run_comp, const int32_t* comp_val, int32_t* run_val, long nruns,
                        cudaStream_t st);

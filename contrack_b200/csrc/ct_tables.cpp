@@ -255,286 +255,6 @@ int track_tables(long T, int H, int W, int persistence,
     return 0;
 }
 
-int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_t, const int32_t* comp_y0,
-                        const int32_t* comp_y1, const int32_t* comp_x0, const int32_t* comp_x1,
-                        const int32_t* comp_label, const LabelTables& lt,
-                        long nseg, const int32_t* seg_y0, const int32_t* seg_y1, const int32_t* seg_a,
-                        const int32_t* seg_b, RunFetcher* fetcher, std::vector<int32_t>& fin,
-                        std::vector<int32_t>& move_comp, std::vector<int32_t>& move_label,
-                        std::vector<Override>& overrides, TrackStats& stats) {
-    overrides.clear(); move_comp.clear(); move_label.clear();
-    stats = TrackStats();
-    const int nlabel = lt.nlabel;
-    auto clock_ms = []() {
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-    };
-    const double t_0 = clock_ms();
-
-    // Dense per-component / per-label state in buffers that live across calls; member lists are intrusive linked lists
-    // (head per value, next per piece) built from the device's grouping only for the labels an event touches.
-    struct Workspace {
-        std::vector<int> value, head, touched;
-        std::vector<long> nxt, log;
-        std::vector<uint8_t> built, settled;
-    };
-    static thread_local Workspace tls_ws;
-    Workspace& ws = tls_ws;
-    std::vector<int>&value = ws.value, &head = ws.head, &touched = ws.touched;
-    std::vector<long>&nxt = ws.nxt, &log = ws.log;
-    std::vector<uint8_t>&built = ws.built, &settled = ws.settled;
-    value.assign(comp_label, comp_label + ncomp);
-    head.assign(nlabel + 1, -1);
-    built.assign(nlabel + 1, 0);
-    settled.assign(nlabel + 1, 0);
-    nxt.resize(ncomp);
-    touched.clear(); log.clear();
-
-    std::vector<Piece> extra;                                // pieces created by splits (index ncomp + k)
-    std::vector<Piece> whole_runs;
-    std::unordered_map<long, int> whole_runs_idx;
-    std::unordered_map<long, std::vector<long>> comp_pieces;
-
-    auto make_piece = [&](long c) {
-        Piece p;
-        p.comp = c; p.t = comp_t[c]; p.y0 = comp_y0[c]; p.y1 = comp_y1[c]; p.x0 = comp_x0[c]; p.x1 = comp_x1[c];
-        p.value = value[c]; p.has_runs = false;
-        return p;
-    };
-    auto ensure_built = [&](int v) {
-        if (built[v]) return;
-        built[v] = 1;
-        touched.push_back(v);
-        for (uint32_t k = lt.lptr[v]; k < lt.lptr[v + 1]; ++k) {
-            const long c = (long)lt.lorder[k];
-            nxt[c] = head[v]; head[v] = (int)c;
-        }
-    };
-    auto piece_ref = [&](long pid) -> Piece* {
-        if (pid >= ncomp) return &extra[pid - ncomp];
-        if (whole_runs_idx.empty()) return nullptr;
-        auto it = whole_runs_idx.find(pid);
-        return it == whole_runs_idx.end() ? nullptr : &whole_runs[it->second];
-    };
-    auto piece_value = [&](long pid) -> int { return pid >= ncomp ? extra[pid - ncomp].value : value[pid]; };
-    auto piece_of = [&](long c, int y, int x) -> long {
-        if (comp_pieces.empty()) return c;
-        auto it = comp_pieces.find(c);
-        if (it == comp_pieces.end()) return c;
-        for (long pid : it->second) {
-            const Piece* p = piece_ref(pid);
-            for (const SubRun& r : p->runs)
-                if (r.y == y && r.x0 <= x && x < r.x1) return pid;
-        }
-        return c;
-    };
-
-    int rc = 0;
-    std::vector<long> moved;
-    // After an event on `hi` every member that is left lies outside box[hi]: until new members arrive (hi being the `lo`
-    // of another event) a repeated event on hi cannot move anything.
-    auto do_event = [&](int hi, int lo) {
-        if (settled[hi]) return;
-        ensure_built(hi); ensure_built(lo);
-        const Box3 b{lt.t0[hi], lt.t1[hi], lt.y0[hi], lt.y1[hi], lt.x0[hi], lt.x1[hi]};
-        long pid = head[hi], prev = -1;
-        moved.clear();
-        while (pid >= 0) {
-            const long next = nxt[pid];
-            stats.n_walked++;
-            Rel rel;
-            Piece* pp = piece_ref(pid);
-            if (!pp) {
-                // whole component, runs not materialised: classify on its box without building a Piece
-                const int t = comp_t[pid];
-                if (t < b.t0 || t >= b.t1) rel = OUTSIDE;
-                else if (comp_y0[pid] >= b.y0 && comp_y1[pid] <= b.y1 && comp_x0[pid] >= b.x0 && comp_x1[pid] <= b.x1) rel = INSIDE;
-                else if (comp_y1[pid] <= b.y0 || comp_y0[pid] >= b.y1 || comp_x1[pid] <= b.x0 || comp_x0[pid] >= b.x1) rel = OUTSIDE;
-                else rel = PARTIAL;
-            } else {
-                rel = classify(*pp, b);
-            }
-            if (rel == PARTIAL) {
-                if (!pp || !pp->has_runs) {
-                    Piece np_ = make_piece(pid);
-                    if (!fetcher || !fetcher->fetch(pid, np_.runs)) { rc = -1; prev = pid; pid = next; continue; }
-                    np_.has_runs = true;
-                    whole_runs_idx[pid] = (int)whole_runs.size();
-                    whole_runs.push_back(std::move(np_));
-                    pp = &whole_runs.back();
-                }
-                std::vector<SubRun> in, out;
-                for (const SubRun& r : pp->runs) {
-                    if (r.y < b.y0 || r.y >= b.y1 || r.x1 <= b.x0 || r.x0 >= b.x1) { out.push_back(r); continue; }
-                    int a = std::max(r.x0, b.x0), e = std::min(r.x1, b.x1);
-                    if (r.x0 < a) out.push_back(SubRun{r.y, r.x0, a});
-                    in.push_back(SubRun{r.y, a, e});
-                    if (e < r.x1) out.push_back(SubRun{r.y, e, r.x1});
-                }
-                if (in.empty()) rel = OUTSIDE;
-                else if (out.empty()) rel = INSIDE;
-                else {
-                    Piece q;
-                    q.comp = pp->comp; q.t = pp->t; q.value = lo; q.has_runs = true; q.runs.swap(in);
-                    tight_box(q);
-                    pp->runs.swap(out);
-                    tight_box(*pp);
-                    const long comp = pp->comp;
-                    const long qid = ncomp + (long)extra.size();
-                    extra.push_back(std::move(q));
-                    nxt.push_back(-1);
-                    std::vector<long>& cp = comp_pieces[comp];
-                    if (cp.empty()) cp.push_back(comp);
-                    cp.push_back(qid);
-                    moved.push_back(qid);
-                    stats.n_splits++;
-                    prev = pid; pid = next;
-                    continue;
-                }
-            }
-            if (rel == INSIDE) {
-                if (pid >= ncomp) extra[pid - ncomp].value = lo;
-                else { value[pid] = lo; log.push_back(pid); if (Piece* w = piece_ref(pid)) w->value = lo; }
-                if (prev < 0) head[hi] = (int)next; else nxt[prev] = next;      // unlink
-                moved.push_back(pid);
-            } else {
-                prev = pid;
-            }
-            pid = next;
-        }
-        for (long m : moved) { nxt[m] = head[lo]; head[lo] = (int)m; }
-        settled[hi] = 1;
-        if (!moved.empty()) settled[lo] = 0;
-    };
-
-    const double t_1 = clock_ms();
-    for (long s = 0; s < nseg && rc == 0; ++s) {
-        const long a = seg_a[s], b = seg_b[s];
-        if (comp_label[a] == 0 || comp_label[b] == 0) continue;
-        for (int y = seg_y0[s]; y < seg_y1[s]; ++y) {
-            long pa = piece_of(a, y, 0), pb = piece_of(b, y, W - 1);
-            int va = piece_value(pa), vb = piece_value(pb);
-            if (va != vb) {
-                do_event(std::max(va, vb), std::min(va, vb));
-                stats.n_events++;
-            }
-            if (comp_pieces.empty() ||
-                (comp_pieces.find(a) == comp_pieces.end() && comp_pieces.find(b) == comp_pieces.end())) break;
-        }
-    }
-    if (rc != 0) return rc;
-    const double t_2 = clock_ms();
-
-    // persistence (contrack.py:765-772): untouched labels keep the t-extent of their box, touched ones are re-measured
-    fin.assign(nlabel + 1, 0);
-    for (int v = 1; v <= nlabel; ++v) {
-        const int lo = lt.t0[v], hi = lt.t1[v] - 1;
-        if (hi >= lo && (hi + 1 - lo) >= persistence) { fin[v] = v; stats.n_features++; }
-    }
-    for (int v : touched) {
-        if (fin[v]) { fin[v] = 0; stats.n_features--; }
-        int lo = INT_MAX, hi = -1;
-        for (long pid = head[v]; pid >= 0; pid = nxt[pid]) {
-            const int t = pid >= ncomp ? extra[pid - ncomp].t : comp_t[pid];
-            lo = std::min(lo, t); hi = std::max(hi, t);
-        }
-        if (hi >= lo && hi >= 0 && (hi + 1 - lo) >= persistence) { fin[v] = v; stats.n_features++; }
-    }
-    std::sort(log.begin(), log.end());
-    log.erase(std::unique(log.begin(), log.end()), log.end());
-    for (long c : log)
-        if (value[c] != comp_label[c] && comp_pieces.find(c) == comp_pieces.end()) {
-            move_comp.push_back((int32_t)c); move_label.push_back(value[c]);
-        }
-    for (auto& kv : comp_pieces) {
-        // a split component is painted piece by piece: its own value becomes 0
-        move_comp.push_back((int32_t)kv.first); move_label.push_back(0);
-        for (long pid : kv.second) {
-            const Piece* p = pid >= ncomp ? &extra[pid - ncomp] : &whole_runs[whole_runs_idx[pid]];
-            const int v = fin[pid >= ncomp ? p->value : value[pid]];
-            if (v == 0) continue;
-            for (const SubRun& r : p->runs) overrides.push_back(Override{p->t, r.y, r.x0, r.x1, v});
-        }
-    }
-    stats.ms_init = t_1 - t_0; stats.ms_events = t_2 - t_1; stats.ms_persist = clock_ms() - t_2;
-    return 0;
-}
-
-int track_labels_fast(int persistence, const LabelTables& lt, long nseg, const int32_t* seg_la, const int32_t* seg_lb,
-                      std::vector<int32_t>& lab_fin, TrackStats& stats) {
-    stats = TrackStats();
-    const int nlabel = lt.nlabel;
-    auto clock_ms = []() {
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-    };
-    const double t_0 = clock_ms();
-    // value[L]: id the members of label L carry now; class lists (labels by current value) exist only for touched values
-    struct Workspace { std::vector<int> value, head, nxt, touched; std::vector<uint8_t> built, settled; };
-    static thread_local Workspace tls_ws;
-    Workspace& ws = tls_ws;
-    std::vector<int>&value = ws.value, &head = ws.head, &nxt = ws.nxt, &touched = ws.touched;
-    std::vector<uint8_t>&built = ws.built, &settled = ws.settled;
-    value.resize(nlabel + 1); head.resize(nlabel + 1); nxt.resize(nlabel + 1);
-    built.assign(nlabel + 1, 0); settled.assign(nlabel + 1, 0);
-    touched.clear();
-    auto val_of = [&](int L) { return built[L] ? value[L] : L; };
-    auto ensure_built = [&](int v) {                      // class v starts with label v alone
-        if (built[v]) return;
-        built[v] = 1; value[v] = v; head[v] = v; nxt[v] = -1;
-        touched.push_back(v);
-    };
-    for (long s = 0; s < nseg; ++s) {
-        const int la = seg_la[s], lb = seg_lb[s];
-        if (la == 0 || lb == 0) continue;
-        const int va = val_of(la), vb = val_of(lb);
-        if (va == vb) continue;
-        stats.n_events++;
-        const int hi = std::max(va, vb), lo = std::min(va, vb);
-        ensure_built(hi); ensure_built(lo);
-        if (settled[hi]) continue;
-        const Box3 b{lt.t0[hi], lt.t1[hi], lt.y0[hi], lt.y1[hi], lt.x0[hi], lt.x1[hi]};
-        int L = head[hi], prev = -1;
-        bool moved = false;
-        while (L >= 0) {
-            const int next = nxt[L];
-            stats.n_walked++;
-            const bool inside = lt.t0[L] >= b.t0 && lt.t1[L] <= b.t1 && lt.y0[L] >= b.y0 && lt.y1[L] <= b.y1 &&
-                                lt.x0[L] >= b.x0 && lt.x1[L] <= b.x1;
-            const bool outside = lt.t1[L] <= b.t0 || lt.t0[L] >= b.t1 || lt.y1[L] <= b.y0 || lt.y0[L] >= b.y1 ||
-                                 lt.x1[L] <= b.x0 || lt.x0[L] >= b.x1;
-            if (inside) {
-                if (prev < 0) head[hi] = next; else nxt[prev] = next;
-                nxt[L] = head[lo]; head[lo] = L; value[L] = lo;
-                moved = true;
-            } else if (outside) {
-                prev = L;
-            } else {
-                return 1;                                 // members of L may be on both sides of the box: per-component replay
-            }
-            L = next;
-        }
-        settled[hi] = 1;
-        if (moved) settled[lo] = 0;
-    }
-    const double t_1 = clock_ms();
-    // persistence (contrack.py:765-772): the t-extent of a value's bounding box, gaps included
-    lab_fin.resize(nlabel + 1);
-    lab_fin[0] = 0;
-    for (int v = 1; v <= nlabel; ++v) {
-        const bool keep = lt.t1[v] > lt.t0[v] && (lt.t1[v] - lt.t0[v]) >= persistence;
-        lab_fin[v] = keep ? v : 0;
-        stats.n_features += keep && !built[v];
-    }
-    for (int v : touched) {
-        int lo = INT_MAX, hi = 0;
-        for (int L = head[v]; L >= 0; L = nxt[L]) { lo = std::min(lo, lt.t0[L]); hi = std::max(hi, lt.t1[L]); }
-        const bool keep = hi > lo && (hi - lo) >= persistence;
-        stats.n_features += keep;
-        for (int L = head[v]; L >= 0; L = nxt[L]) lab_fin[L] = keep ? v : 0;
-    }
-    stats.ms_init = 0; stats.ms_events = t_1 - t_0; stats.ms_persist = clock_ms() - t_1;
-    return 0;
-}
-
 int track_events_fast(int persistence, long nev, const int32_t* ev, long nrec, const int32_t* lrec,
                       std::vector<int32_t>& patch_label, std::vector<int32_t>& patch_value, long* feat_delta,
                       TrackStats& stats) {

@@ -35,35 +35,10 @@ int track_tables(long T, int H, int W, int persistence,
                  const int32_t* seg_a, const int32_t* seg_b,
                  RunFetcher* fetcher, int32_t* comp_val, std::vector<Override>& overrides, TrackStats& stats);
 
-// Same two steps when the per-label tables were already reduced elsewhere (on the device): 3-D boxes of the labels
-// (lt0..lx1, half-open, index = label), components grouped by label (lptr / lorder) and the segments.  Only labels that a
-// date-line event touches are visited.  Outputs: fin[label] = surviving value of every label (0 = removed by the
-// persistence filter), `moves` = (component, new label) for the components an event re-labelled (a split component gets
-// label 0 and its pieces come back as overrides).
-struct LabelTables {
-    int nlabel = 0;
-    const int32_t *t0 = nullptr, *t1 = nullptr, *y0 = nullptr, *y1 = nullptr, *x0 = nullptr, *x1 = nullptr;   // [nlabel+1]
-    const uint32_t* lptr = nullptr;      // [nlabel+2]: components of label v are lorder[lptr[v] .. lptr[v+1])
-    const uint32_t* lorder = nullptr;
-};
-int track_tables_sparse(int W, int persistence, long ncomp, const int32_t* comp_t, const int32_t* comp_y0,
-                        const int32_t* comp_y1, const int32_t* comp_x0, const int32_t* comp_x1,
-                        const int32_t* comp_label, const LabelTables& lt,
-                        long nseg, const int32_t* seg_y0, const int32_t* seg_y1, const int32_t* seg_a,
-                        const int32_t* seg_b, RunFetcher* fetcher, std::vector<int32_t>& fin,
-                        std::vector<int32_t>& move_comp, std::vector<int32_t>& move_label,
-                        std::vector<Override>& overrides, TrackStats& stats);
-
-// The same two steps at LABEL granularity: a date-line event relabels the members of value `hi` that lie inside the stale
-// box of label hi; when every 3-D label that currently carries `hi` is either completely inside or completely outside that
-// box, whole labels move and no component has to be looked at.  seg_la / seg_lb: label of the component at x = 0 / x = W-1
-// of every segment (0 = removed), segments in (t, y) order.  Output lab_fin[label] = value painted for every component of
-// that label (0 = removed by the persistence filter).  Returns 0 on success, 1 if some label lies partly inside a box --
-// the caller then replays the events per component with track_tables_sparse (nothing has been written).
-int track_labels_fast(int persistence, const LabelTables& lt, long nseg, const int32_t* seg_la, const int32_t* seg_lb,
-                      std::vector<int32_t>& lab_fin, TrackStats& stats);
-
-// The same label-granular replay from the device's event list alone.  `lrec`: one record {label, t0, t1, y0, y1, x0, x1}
+// The two steps at LABEL granularity, from the device's event list alone (the product path, ct_fast.cu): a date-line event
+// relabels the members of value `hi` that lie inside the stale box of label hi; when every 3-D label that currently carries
+// `hi` is either completely inside or completely outside that box, whole labels move and no component has to be looked at.
+// `lrec`: one record {label, t0, t1, y0, y1, x0, x1}
 // per label that occurs in an event, sorted by label; `ev`: for every date-line segment whose two ends carry different 3-D
 // labels, in (t, y) order, the record indices of the label at x = 0 and at x = W-1.  Only labels that occur in events can
 // ever change value, so nothing else is needed.  Outputs: for every label an event touched, its final value (patch_label /

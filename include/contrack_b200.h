@@ -64,13 +64,11 @@ void ct_destroy(ct_ctx* ctx);
  *                  the threshold kernel), 2 = by size: the plane kernel up to "plane_max_planes" [4096] planes per context
  *                  (the shards of a multi-GPU run), the global-memory kernels for longer cubes.  A plane that does not fit the
  *                  plane kernel's shared memory ("plane_smem" [0 = 40 KB, then 200 KB]) falls back automatically.
- *   "coop_global"  [1] ordered phase (contrack.py:706-751 + label boxes + date-line events) as ONE cooperative kernel and an
- *                  O(events) host replay; 0 = one kernel per step with host round trips
  *   "max_sweeps"   [32] Jacobi sweeps of the overlap filter before the plane-ordered wavefront takes over (bounded cost on
  *                  adversarial keep/kill chains)
- *   "gpu_tables"   [1] 0 = the whole ordered phase on the host (what the exact near-tie resolver falls back to)
- *   "label_fast"   [1] 0 = date-line merge by per-component replay even when whole labels move (the fallback for labels that
- *                  straddle a stale box)
+ *   "gpu_tables"   [1] ordered phase (contrack.py:706-751 + label boxes + date-line events) as ONE cooperative kernel and an
+ *                  O(events) host replay; 0 = the whole ordered phase on the host (the reference's loops on the tables: what
+ *                  near-ties on non-exact rows and labels that straddle a stale box fall back to)
  *   "tma"          [1] threshold kernel: rows staged by cp.async.bulk + mbarrier; 0 = plain coalesced loads (also used
  *                  automatically for rows that are not 16-byte aligned or too long for shared memory)
  *   "overlap_zero" [1] zero fill of the flag cube on a side stream beside the table phase + sparse paint; 0 = dense paint

@@ -67,9 +67,9 @@ def test_variants_and_sharded_agree(cube, result):
     flag, n, _ = result
     eng = Engine.get(0)
     out = torch.empty_like(flag)
-    for opts in ({'chunks': 1}, {'plane_kernel': 1}, {'plane_kernel': 1, 'fast_chunks': 3}, {'coop_global': 0}, {'overlap_zero': 0},
+    for opts in ({'chunks': 1}, {'plane_kernel': 1}, {'plane_kernel': 1, 'fast_chunks': 3}, {'overlap_zero': 0},
                  {'max_sweeps': 2}, {'tma': 0}):
-        defaults = {'chunks': 4, 'plane_kernel': 2, 'fast_chunks': 1, 'coop_global': 1, 'overlap_zero': 1, 'max_sweeps': 32, 'tma': 1}
+        defaults = {'chunks': 4, 'plane_kernel': 2, 'fast_chunks': 1, 'overlap_zero': 1, 'max_sweeps': 32, 'tma': 1}
         for k, v in opts.items():
             eng.set_option(k, v)
         try:

@@ -319,15 +319,15 @@ def test_chunked_table_pipeline(eng, chunks, plane):
 
 @pytest.mark.parametrize('opts', [{'tma': 0}, {'overlap_zero': 0}, {'gpu_tables': 0}, {'chunks': 4, 'chunk_min_planes': 1, 'plane_kernel': 0},
                                   {'chunks': 64, 'chunk_min_planes': 1, 'gpu_tables': 0},
-                                  {'chunks': 3, 'chunk_min_planes': 2, 'tma': 0, 'plane_kernel': 0}, {'label_fast': 0, 'coop_global': 0},
-                                  {'coop_global': 0}, {'fill_ctas': 0}, {'fill_late': 1, 'plane_kernel': 1}])
+                                  {'chunks': 3, 'chunk_min_planes': 2, 'tma': 0, 'plane_kernel': 0}, {'fill_ctas': 0},
+                                  {'fill_late': 1, 'plane_kernel': 1}])
 def test_kernel_variants_give_identical_results(eng, fixture_cube, golden, opts):
     """Every selectable path (plain-load threshold kernel, dense paint, host table phase, chunked global-memory table
-    kernels, per-step ordered-phase kernels instead of the cooperative one, uncapped / late zero fill) must produce the same
+    kernels, uncapped / late zero fill) must produce the same
     bytes."""
     a, lat, lon = fixture_cube
-    defaults = {'tma': 1, 'overlap_zero': 1, 'gpu_tables': 1, 'chunks': 4, 'chunk_min_planes': 1024, 'label_fast': 1,
-                'plane_kernel': 2, 'coop_global': 1, 'fill_ctas': 2, 'fill_late': 0}
+    defaults = {'tma': 1, 'overlap_zero': 1, 'gpu_tables': 1, 'chunks': 4, 'chunk_min_planes': 1024, 'plane_kernel': 2,
+                'fill_ctas': 2, 'fill_late': 0}
     for k, v in opts.items():
         eng.set_option(k, v)
     try:
@@ -347,10 +347,11 @@ def test_kernel_variants_give_identical_results(eng, fixture_cube, golden, opts)
             eng.set_option(k, defaults[k])
 
 
-def test_label_granular_track_matches_component_replay(eng, reference_run):
-    """Steps 4c/4d (date-line merge through stale boxes + persistence): the label-granular host pass (default) and the
-    per-component replay must agree, on the reference's own outputs for the stale-box cubes and on random cubes with many
-    date-line events; the per-component replay must still be reached when a label straddles a stale box."""
+def test_event_replay_matches_component_replay(eng, reference_run):
+    """Steps 4c/4d (date-line merge through stale boxes + persistence): the label-granular event replay (default) and the
+    all-host per-component replay ("gpu_tables" = 0) must agree, on the reference's own outputs for the stale-box cubes and
+    on random cubes with many date-line events; the per-component replay must still be reached from the default path when a
+    label straddles a stale box."""
     import torch
     fast_used, fallback_used = 0, 0
     cases = [(r['seed'], tuple(r['shape']), tuple(r['sigma']), r['threshold'], r['sha256']) for r in reference_run['quirk']]
@@ -361,14 +362,14 @@ def test_label_granular_track_matches_component_replay(eng, reference_run):
         w = row_weights(lat, lon)
         xd = torch.from_numpy(x).cuda()
         out = {}
-        for lf in (1, 0):
-            eng.set_option('label_fast', lf)
+        for gt in (1, 0):
+            eng.set_option('gpu_tables', gt)
             try:
                 f, n = eng.run_contrack(xd, w, thr, True, 0, 0.0, 1, False)
             finally:
-                eng.set_option('label_fast', 1)
-            out[lf] = (f.cpu().numpy(), n)
-            if lf == 1:
+                eng.set_option('gpu_tables', 1)
+            out[gt] = (f.cpu().numpy(), n)
+            if gt == 1:
                 used = eng.stats().get('label_fast', -1)
                 fast_used += used == 1
                 fallback_used += used == 0

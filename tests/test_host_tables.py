@@ -107,42 +107,11 @@ def test_near_tie_on_pole_rows_uses_numpy_summation_order(fixture_cube):
         host_tables(build_tables(a >= 100, w), pole_tie_overlaps(a, lat, lon, 100)[0], 1, True, with_runs=False)
 
 
-def test_sparse_track_variant(monkeypatch, fixture_cube, golden):
-    """track_tables_sparse (what the device-table path calls: per-label boxes / member lists reduced up front, only the
-    labels a date-line event touches are visited) against the same vectors."""
-    monkeypatch.setenv('CT_TRACK_SPARSE', '1')
-    lat, lon = regular_grid(24, 16)
-    w = row_weights(lat, lon)
-    splits = 0
-    for r in golden['quirk']:
-        x = synth_cube(r['seed'], 12, 24, 16, (1.5, 2, 2))
-        f, _ = host_tables(build_tables(x >= 60, w), 0.0, r['persistence'], False)
-        assert sha_i4(f) == r['sha256']
-    for seed in SPLIT_SEEDS + list(range(1000, 1040)):
-        x = synth_cube(seed, 12, 24, 16, (1.5, 2, 2))
-        tb = build_tables(x >= 60, w)
-        f, st = host_tables(tb, 0.0, 1, False)
-        assert np.array_equal(f, oracle.track_persistence((x >= 60).astype(int), 1)), seed
-        splits += st[4]
-        f, _ = host_tables(tb, 0.5, 2, True)
-        assert np.array_equal(f, oracle.run_contrack(x, lat, lon, 60, '>=', 0.5, 2, True)), seed
-    assert splits >= 14
-    a, la, lo = fixture_cube
-    for r in golden['fixture']:
-        f, _ = host_tables(build_tables(a >= r['threshold'], row_weights(la, lo)), r['overlap'], r['persistence'],
-                           r['twosided'])
-        assert sha_i4(f) == r['sha256']
-
-
-@pytest.mark.parametrize('events', [False, True])
-def test_label_granular_track_variant(monkeypatch, fixture_cube, golden, reference_run, events):
-    """track_labels_fast / track_events_fast (the product path's date-line merge + persistence at label granularity; the
-    second one works from the device's event list alone) through the all-host entry point: same results as the reference,
-    and the per-component replay takes over when a label straddles a box."""
-    monkeypatch.setenv('CT_TRACK_SPARSE', '1')
-    monkeypatch.setenv('CT_TRACK_LABELS', '1')
-    if events:
-        monkeypatch.setenv('CT_TRACK_EVENTS', '1')
+def test_label_granular_event_replay(monkeypatch, fixture_cube, golden, reference_run):
+    """track_events_fast (the product path's date-line merge + persistence at label granularity, from the event list the
+    cooperative kernel emits) through the all-host entry point: same results as the reference, and the per-component replay
+    takes over when a label straddles a box."""
+    monkeypatch.setenv('CT_TRACK_EVENTS', '1')
     lat, lon = regular_grid(24, 16)
     w = row_weights(lat, lon)
     fast, slow = 0, 0

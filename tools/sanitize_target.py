@@ -31,12 +31,12 @@ for x, lat, lon, thr, ov, pers, two in cases:
 from test_gpu_sharded import run_local
 a, lat, lon = cases[0][:3]
 f, n, _ = run_local(a, row_weights(lat, lon), (4, 3, 4), 150, '>=', 0.5, 5, True)
-for opts in ({'plane_kernel': 1}, {'plane_kernel': 0, 'coop_global': 0}):                      # both table builders / ordered phases
+for opts in ({'plane_kernel': 1}, {'plane_kernel': 0}, {'gpu_tables': 0}):                   # both table builders, host ordered phase
     for k, v in opts.items():
         eng.set_option(k, v)
     f1, _ = eng.run_contrack(torch.from_numpy(a).cuda(), row_weights(lat, lon), 150, True, 0, 0.5, 5, True)
     assert np.array_equal(f1.cpu().numpy(), f)
-eng.set_option('plane_kernel', 2); eng.set_option('coop_global', 1)
+eng.set_option('plane_kernel', 2); eng.set_option('gpu_tables', 1)
 assert np.array_equal(f, oracle.run_contrack(a, lat, lon, 150, '>=', 0.5, 5, True))
 print('sharded ok', flush=True)
 # calc_anom, quantile, lifecycle

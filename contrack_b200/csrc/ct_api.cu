@@ -815,13 +815,12 @@ void ct_destroy(ct_ctx* c) {
                       &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0], &c->chunk_out[1],
                       &c->a_gptr, &c->a_gidx, &c->a_gmean, &c->a_group,
                       &c->l_parent, &c->l_flag, &c->l_rank, &c->l_label, &c->l_kept, &c->l_accE, &c->l_accS, &c->l_accN,
-                      &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_cnt, &c->b_fill, &c->b_ptr,
-                      &c->b_order, &c->b_fin, &c->b_mc, &c->b_ml,
-                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->sh_desc, &c->b_sla, &c->b_slb, &c->slots, &c->x_q, &c->x_qscratch, &c->x_idx, &c->ovf_rows,
+                      &c->b_t0, &c->b_t1, &c->b_y0, &c->b_y1, &c->b_x0, &c->b_x1, &c->b_fin,
+                      &c->lc_st, &c->lc_t, &c->lc_label, &c->lc_npix, &c->lc_roll, &c->lc_out, &c->lc_bitmaps, &c->slots, &c->x_q, &c->x_qscratch, &c->x_idx, &c->ovf_rows,
                       &c->pl_chain, &c->pl_done, &c->pl_ctl, &c->g_dirty, &c->g_blocksum, &c->g_evflag, &c->g_ev, &c->g_lrec, &c->g_patch,
                       &c->sh_export, &c->sh_gathered, &c->sh_mdesc, &c->sh_lastplane};
     for (DevBuf* b : bufs) b->release();
-    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_plane.release(); c->hp_labels.release(); c->hp_runs.release(); c->hp_lc.release(); c->hp_desc.release();
+    c->hp_counters.release(); c->hp_tables.release(); c->hp_val.release(); c->hp_ovr.release(); c->hp_runs.release(); c->hp_lc.release();
     c->hp_ctl.release(); c->hp_ev.release(); c->hp_ev2.release(); c->hp_patch.release(); c->hp_hdr.release();
     for (auto& e : c->ev_x) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_p) if (e) cudaEventDestroy(e);
@@ -833,7 +832,6 @@ void ct_destroy(ct_ctx* c) {
     if (c->tbl_stream) cudaStreamDestroy(c->tbl_stream);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_chunk) if (e) cudaEventDestroy(e);
-    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->work_stream) cudaStreamDestroy(c->work_stream);
     delete c;

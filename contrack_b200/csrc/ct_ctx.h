@@ -121,8 +121,6 @@ struct ct_ctx {
     cth::FastTables host_tb;                 // tables of the last tables_gpu() call (pointers into hp_tables)
     long nseg = 0, halo_comps = 0;
     int has_prev = 0;                        // sharded run: plane 0 of the scratch is the previous rank's last plane
-    PinBuf hp_plane;
-    int32_t* zero_started_for = nullptr;
     int special_uniform = 0;
     long opt_gpu_tables = 1;                 // step 3 + 3-D labels on the device (single-GPU path)
     long opt_chunks = 4;                     // time chunks of the pipelined run (tables of chunk k under threshold k+1)
@@ -139,8 +137,7 @@ struct ct_ctx {
     long lc_rows = 0;
     PinBuf hp_runs;                          // row-run table of the last host-buffer call
     DevBuf l_parent, l_flag, l_rank, l_label, l_kept, l_accE, l_accS, l_accN;
-    DevBuf b_t0, b_t1, b_y0, b_y1, b_x0, b_x1, b_cnt, b_fill, b_ptr, b_order, b_fin, b_mc, b_ml;
-    PinBuf hp_labels;     // flag cube whose zero fill is in flight on the side stream
+    DevBuf b_t0, b_t1, b_y0, b_y1, b_x0, b_x1, b_fin;     // label boxes, value per label
     cudaStream_t side_stream = nullptr;      // zero fill (lowest priority)
     cudaStream_t tbl_stream = nullptr;       // table phase (highest priority): must get onto the SMs between fill blocks
     cudaEvent_t ev_tbl[2] = {nullptr, nullptr};
@@ -153,8 +150,7 @@ struct ct_ctx {
     long nspecial_cached = 0;
     long launches = 0;
     // time-sharded run: packed tables of all ranks -> global tables (ct_global_merge), plane runs served by the caller
-    DevBuf sh_desc, b_sla, b_slb, x_q, x_qscratch, x_idx, ovf_rows;
-    PinBuf hp_desc;
+    DevBuf x_q, x_qscratch, x_idx, ovf_rows;
     ct_plane_runs_fn fetch_fn = nullptr;
     void* fetch_user = nullptr;
     // ct_shard_begin: thresholding of the own planes is deferred to ct_shard_tables_dev (pipelined with the table kernels)
@@ -165,14 +161,6 @@ struct ct_ctx {
     long opt_profile_tables = 0;              // debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"
     std::vector<std::pair<std::string, cudaEvent_t>> prof;
     size_t prof_used = 0;
-    const void* sh_anom = nullptr;
-    int sh_dtype = 0, sh_thr_is_f32 = 0, sh_op = 0, sh_deferred = 0;
-    long sh_thr_n = 0;
-    long sh_nchunk = 0, sh_cp = 0;            // chunking chosen by ct_shard_launch_threshold
-    int sh_side = 0;
-    int32_t* sh_flag = nullptr;
-    cudaEvent_t ev_halo = nullptr;           // halo plane imported (ct_shard_import_halo may run on another stream)
-    int halo_event_set = 0;
     // ---- fast path (ct_fast.cu): per-plane table kernel + cooperative global kernel, no host round trip between them ----
     long opt_plane_kernel = 2;               // tables: 0 = global-memory kernels of ct_kernels.cu, 1 = plane kernel, 2 = by size
     long opt_plane_max_planes = 4096;        // ... plane kernel up to this many planes per context

@@ -57,7 +57,7 @@ def main():
     ir, iw, it = head.index('dram__bytes_read.sum'), head.index('dram__bytes_write.sum'), head.index('gpu__time_duration.sum')
     names = {'k_threshold': 'threshold_bits', 'k_zero_fill': 'zero_fill', 'k_paint': 'paint', 'k_anom': 'calc_anom',
              'k_group_mean': 'group_mean', 'k_clim_smooth': 'clim_smooth', 'k_flag_count': 'flag_count',
-             'k_compact_runs': 'compact_runs'}
+             'k_compact_runs': 'compact_runs', 'k_plane_tables': 'plane_tables', 'k_global_phase': 'global_phase'}
     for k, r in last.items():
         name = next((v for p, v in names.items() if p in k), k)
         rd, wrb = to_bytes(r[ir], units[ir]), to_bytes(r[iw], units[iw])
@@ -94,6 +94,22 @@ def main():
             f.write('%-48s %6d %12.3f %6.1f%%\n' % (k[:48], a[0], a[1] / 1e6, 100 * a[1] / tot))
         f.write('%-48s %6d %12.3f\n' % ('total', sum(a[0] for a in agg.values()), tot / 1e6))
     print(open(os.path.join(PROF, '%s_launch_shares_T10957.txt' % tag)).read())
+    src = os.path.join(OUT, '%s_launches_T1370.csv' % tag)
+    if os.path.exists(src):                       # shard-sized cube: launches of the last step (from its threshold launch on)
+        lines = [ln for ln in open(src) if not ln.startswith('==')]
+        rows = list(csv.reader(lines))
+        h = rows[0]
+        kn, mv = h.index('Kernel Name'), h.index('Metric Value')
+        body = [r for r in rows[1:] if len(r) > mv]
+        thr = [i for i, r in enumerate(body) if 'k_threshold' in r[kn]]
+        step = body[thr[1]:thr[2]] if len(thr) >= 3 else body
+        with open(os.path.join(PROF, '%s_launch_list_T1370.txt' % tag), 'w') as f:
+            f.write('one run_contrack step at T=1370 (the shard of one rank of an 8-GPU run), every launch in order; ncu '
+                    '--metrics gpu__time_duration.sum --clock-control none: serialised, cold cache\n')
+            for r in step:
+                f.write('%-48s %10.1f us\n' % (short(r[kn])[:48], float(r[mv].replace(',', '')) / 1e3))
+            f.write('%d launches, %.3f ms\n' % (len(step), sum(float(r[mv].replace(',', '')) for r in step) / 1e6))
+        print(open(os.path.join(PROF, '%s_launch_list_T1370.txt' % tag)).read())
     print(json.dumps(traffic, indent=1))
 
 

@@ -507,12 +507,12 @@ def main():
         keys = ('ms_threshold', 'ms_zero_fill', 'ms_tables_after_threshold', 'ms_plane_kernel', 'ms_exchange', 'ms_global_kernel', 'ms_host_tables',
                 'ms_paint', 'ms_total')
         mine = {k: round(float(np.mean([i.get(k, 0.0) for i in last])), 3) for k in keys}
-        mine.update({k: last[-1].get(k) for k in ('exchange_bytes', 'shard_attempts', 'fast_path', 'sweeps', 'kernel_launches')})
+        mine.update({k: last[-1].get(k) for k in ('exchange_bytes', 'shard_attempts', 'fast_path', 'sweeps', 'kernel_launches', 'p2p')})
         every = [None] * world
         dist.all_gather_object(every, mine)
         line['shard_ms_all_ranks'] = every
         line['shard_ms_note'] = ('per rank, CUDA events of the sharded call: threshold (own planes), zero fill (beside the table '
-                                 'phase), tables_after_threshold = plane kernel + table all-gather + merge + global kernel + '
+                                 'phase), tables_after_threshold = plane kernel + table exchange (p2p 1: peer-memory stores by the pack kernel, 0: all-gather) + merge + global kernel + '
                                  'host replay, paint; ms_total = the whole call on the device')
     # ---- parity: checksum of the timed run's flag cube (identical at every N) + oracle on a cube cut at every rank ----
     if not args.no_parity:

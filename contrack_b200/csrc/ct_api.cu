@@ -849,6 +849,8 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "host_zero_threads")) { c->opt_host_zero_threads = value; return CT_OK; }
     if (!strcmp(key, "host_out_zeroed")) { c->opt_host_out_zeroed = value; return CT_OK; }
     if (!strcmp(key, "fill_late")) { c->opt_fill_late = value; return CT_OK; }
+    if (!strcmp(key, "p2p")) { c->opt_p2p = value; return CT_OK; }
+    if (!strcmp(key, "fill_tail")) { c->opt_fill_tail = value < 0 ? 0 : value > 90 ? 90 : value; return CT_OK; }
     if (!strcmp(key, "fill_ctas")) { c->opt_fill_ctas = value; return CT_OK; }
     if (!strcmp(key, "profile_tables")) { c->opt_profile_tables = value; return CT_OK; }
     if (!strcmp(key, "plane_kernel")) { c->opt_plane_kernel = value; return CT_OK; }

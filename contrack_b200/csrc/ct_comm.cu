@@ -5,6 +5,7 @@
 #include <nccl.h>                              // types and prototypes only: every entry point is looked up at run time
 
 #include <condition_variable>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -82,7 +83,84 @@ struct NcclComm : Comm {
     int bcast(void* buf, size_t bytes, int root, cudaStream_t st) override {
         return check(api->Broadcast(buf, buf, bytes, ncclUint8, root, comm, st), "ncclBroadcast");
     }
-    ~NcclComm() override { if (owned && comm) api->CommDestroy(comm); }
+    // ---- peer windows through CUDA IPC (one process per GPU) ----
+    struct WinRec { cudaIpcMemHandle_t handle; unsigned long long offset, ok; };
+    std::vector<void*> opened;                 // bases returned by cudaIpcOpenMemHandle
+    void* stage = nullptr;                     // device staging for the exchange of the records
+    int cuda(cudaError_t e, const char* what) {
+        if (e == cudaSuccess) return 0;
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return -1;
+    }
+    void close_opened() {
+        for (void* p : opened) if (p) cudaIpcCloseMemHandle(p);
+        opened.clear();
+    }
+    // MIN over the ranks of one host value (blocks)
+    int agree_min(long long* v, cudaStream_t st) {
+        if (cuda(cudaMemcpyAsync(stage, v, 8, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync")) return -1;
+        if (allreduce(stage, 1, MIN_I64, st)) return -1;
+        if (cuda(cudaMemcpyAsync(v, stage, 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync")) return -1;
+        return cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    }
+    int window_map(void* local, size_t bytes, void** peers, cudaStream_t st) override {
+        (void)bytes;
+        static_assert(sizeof(WinRec) == 80, "64-byte IPC handle + offset + ok");
+        if (!stage && cuda(cudaMalloc(&stage, (size_t)(n + 1) * sizeof(WinRec) + 64), "cudaMalloc")) return -1;
+        WinRec mine;
+        memset(&mine, 0, sizeof(mine));
+        // the handle names the whole allocation the pointer lies in: ship the offset into it as well
+        {
+            using GetRange = int (*)(unsigned long long*, size_t*, unsigned long long);
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            unsigned long long base = 0; size_t sz = 0;
+            if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) == cudaSuccess && fn &&
+                reinterpret_cast<GetRange>(fn)(&base, &sz, (unsigned long long)(uintptr_t)local) == 0 && base)
+                mine.offset = (unsigned long long)(uintptr_t)local - base;
+            (void)cudaGetLastError();
+        }
+        mine.ok = cudaIpcGetMemHandle(&mine.handle, local) == cudaSuccess ? 1 : 0;
+        (void)cudaGetLastError();
+        std::vector<WinRec> all((size_t)n);
+        WinRec* dev = static_cast<WinRec*>(stage);
+        if (cuda(cudaMemcpyAsync(dev + n, &mine, sizeof(mine), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync")) return -1;
+        if (allgather(dev + n, dev, sizeof(WinRec), st)) return -1;
+        if (cuda(cudaMemcpyAsync(all.data(), dev, (size_t)n * sizeof(WinRec), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync")) return -1;
+        if (cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize")) return -1;
+        long long ok = 1;
+        for (int q = 0; q < n; ++q) ok = ok && all[q].ok;
+        close_opened();
+        if (ok) {
+            for (int q = 0; q < n && ok; ++q) {
+                if (q == r) { peers[q] = local; continue; }
+                void* base = nullptr;
+                if (cudaIpcOpenMemHandle(&base, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    ok = 0;
+                    break;
+                }
+                opened.push_back(base);
+                peers[q] = static_cast<char*>(base) + all[q].offset;
+            }
+        }
+        if (agree_min(&ok, st)) return -1;
+        if (!ok) { close_opened(); return 1; }
+        return 0;
+    }
+    int window_unmap(cudaStream_t st) override {
+        close_opened();
+        if (!stage) return 0;
+        long long one = 1;
+        return agree_min(&one, st);              // (a barrier: everybody has closed)
+    }
+    bool window_device_flags() const override { return true; }
+    int window_fence(cudaStream_t) override { return 0; }
+    ~NcclComm() override {
+        close_opened();
+        if (stage) cudaFree(stage);
+        if (owned && comm) api->CommDestroy(comm);
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -106,6 +184,7 @@ struct LocalGroup {
     int n = 0;
     std::mutex m; std::condition_variable cv; int arrived = 0; long gen = 0;
     std::vector<const void*> ptr;
+    long votes = 0;
     std::vector<cudaEvent_t> ready, done;
     void barrier() {
         std::unique_lock<std::mutex> lk(m);
@@ -200,6 +279,44 @@ struct LocalComm : Comm {
             if (cuda(cudaMemcpyAsync(buf, g->ptr[root], bytes, cudaMemcpyDefault, st), "cudaMemcpyAsync")) return -1;
         }
         return finish(st, r == root, -1);
+    }
+    // peer windows: the ranks share one address space; pointers of the other ranks are valid as they are (the ranks of a
+    // test group sit on one device; for several devices of one process peer access is switched on)
+    int window_map(void* local, size_t, void** peers, cudaStream_t) override {
+        g->ptr[r] = local;
+        g->barrier();
+        int mydev = 0;
+        long bad = 0;
+        if (cuda(cudaGetDevice(&mydev), "cudaGetDevice")) bad = 1;
+        for (int q = 0; q < g->n && !bad; ++q) {
+            peers[q] = const_cast<void*>(g->ptr[q]);
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, peers[q]) != cudaSuccess) { bad = 1; break; }
+            if (at.device != mydev) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) bad = 1;
+            }
+        }
+        (void)cudaGetLastError();
+        {
+            std::unique_lock<std::mutex> lk(g->m);
+            g->votes += bad;
+        }
+        g->barrier();
+        const long total = g->votes;
+        g->barrier();
+        if (r == 0) g->votes = 0;
+        g->barrier();
+        return total ? 1 : 0;
+    }
+    int window_unmap(cudaStream_t) override { g->barrier(); return 0; }
+    bool window_device_flags() const override { return false; }
+    int window_fence(cudaStream_t st) override {
+        if (publish(nullptr, st)) return -1;
+        for (int q = 0; q < g->n; ++q)
+            if (q != r && cuda(cudaStreamWaitEvent(st, g->ready[q], 0), "cudaStreamWaitEvent")) return -1;
+        g->barrier();                             // nobody re-records `ready` before everybody has enqueued its waits
+        return 0;
     }
     ~LocalComm() override { if (tmp) cudaFree(tmp); if (dev_ptrs) cudaFree(dev_ptrs); }
 };

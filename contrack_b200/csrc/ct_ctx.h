@@ -155,7 +155,10 @@ struct ct_ctx {
     void* fetch_user = nullptr;
     // ct_shard_begin: thresholding of the own planes is deferred to ct_shard_tables_dev (pipelined with the table kernels)
     long opt_fill_ctas = 2;                   // resident blocks per SM of the zero fill (room for the table kernels beside it)
+    long opt_p2p = 1;                         // sharded run: 1 = tables reach the other ranks through peer windows (NVLink stores), 0 = ncclAllGather
     long opt_fill_late = 0;                   // plane-kernel path: 1 = the zero fill starts after the plane kernel (0: beside it)
+    long opt_fill_tail = 0;                   // sharded plane-kernel path: percent of the zero fill that is held back until the global kernel has run (it then fills the GPU's idle time during the host replay)
+    struct TailFill { int32_t* p = nullptr; size_t cells = 0; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; } tail_fill;   // set on the context whose global() call starts it
     int32_t* pend_fill = nullptr;             // ... the fill ctf::finish() has to start
     size_t pend_fill_cells = 0;
     long opt_profile_tables = 0;              // debug: CUDA-event time of every group of table kernels -> stats "ms_t_*"
@@ -183,7 +186,6 @@ struct ct_ctx {
     DevBuf sh_lastplane;                     // host-buffer variant: staging of the shard's last plane
     cudaStream_t host_stream = nullptr;      // ... and the stream it runs on
     PinBuf hp_hdr;
-    long sh_capC = 0, sh_capP = 0, sh_capS = 0;   // negotiated per-rank capacities of the table exchange (0 = not yet)
     cudaEvent_t ev_x[2] = {nullptr, nullptr};
     cudaEvent_t ev_p[4] = {nullptr, nullptr, nullptr, nullptr};    // plane kernel begin / end, global kernel begin / end
 };

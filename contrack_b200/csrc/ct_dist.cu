@@ -4,9 +4,12 @@
 //   1. the LAST own plane is thresholded first and its bit rows go to rank r+1 (the one halo exchange: send/recv of
 //      H * ceil(W/32) words), while the other planes are being thresholded;
 //   2. the plane kernel (ct_plane.cu) builds the tables of halo + own planes beside the zero fill of the flag planes;
-//   3. the tables are packed behind a 128-byte header and ALL-GATHERED with one collective of fixed stride (the stride is
-//      negotiated once per problem size and kept; a rank whose tables outgrow it says so in its header and every rank
-//      repeats the exchange with a larger one);
+//   3. the tables are packed behind a 128-byte header into a slot of fixed stride and reach every rank in one step: the pack
+//      kernel STORES each element straight into the gathered buffers of all ranks (peer memory over NVLink / NVSwitch, mapped
+//      once per communicator) and raises a flag word at every peer when its last block is through -- pack and all-gather are
+//      one kernel, there is no collective launch and no staging copy; without peer memory (or with option p2p=0) the slot is
+//      packed locally and all-gathered with one ncclAllGather.  The stride is negotiated once per problem size and kept; a
+//      rank whose tables outgrow it says so in its header and every rank repeats the exchange with a larger one;
 //   4. a merge kernel renumbers the gathered tables into global tables -- local component i of rank r becomes
 //      i + comp_base_r - halo_r; halo components fall onto the ids the previous rank gave its last-plane components; forward
 //      sums accumulated on halo copies are added to their owners -- with the per-rank bases computed on the device;
@@ -32,6 +35,9 @@ constexpr size_t HDR_BYTES = HDR_WORDS * 8;
 enum Hdr { H_NC = 0, H_NH, H_NP, H_NS, H_E0, H_NSH, H_NLAST, H_TSHIFT, H_STATUS, H_NRUNS, H_CBASE, H_PBASE, H_SBASE, H_COFF };
 constexpr uint32_t ST_EXCHANGE = 8u;          // a rank's tables do not fit the negotiated stride
 constexpr uint32_t ST_MISMATCH = 16u;         // halo components of rank r != last-plane components of rank r-1 (internal)
+constexpr int MAX_PEERS = 16;                 // ranks that can exchange through peer windows (more: the collective)
+constexpr size_t WIN_DATA = 4096;             // window: [0, 256) flag words [parity][rank], [1024] pack counter, data from 4096
+constexpr unsigned long long FLAG_WAIT_NS = 4000000000ull;
 
 struct Offsets { size_t off[cts::A_COUNT]; };
 
@@ -44,8 +50,26 @@ struct PackArgs {
     const uint32_t* status;
     unsigned long long capC, capP, capS;
     int has_prev; int last_plane; long t_shift;
-    char* dst; Offsets o;
+    // destinations: this rank's slot in the gathered buffer of every rank (peer windows), or one local export buffer
+    char* dst[MAX_PEERS]; int ndst;
+    unsigned long long* flag[MAX_PEERS];       // peer windows: this rank's flag word at every rank (null = no signalling)
+    unsigned long long epoch; uint32_t* done_ctr;
+    Offsets o;
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ long lower_i32(const int32_t* a, long n, int v) {       // first index with a[i] >= v
     long lo = 0, hi = n;
@@ -59,7 +83,7 @@ __global__ void __launch_bounds__(256) k_pack_tables(PackArgs a) {
     const bool fits = st == 0u && (unsigned long long)nc <= a.capC && (unsigned long long)np <= a.capP &&
                       (unsigned long long)ns <= a.capS;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long* h = reinterpret_cast<unsigned long long*>(a.dst);
+        unsigned long long h[HDR_WORDS];
         const long nh = (a.has_prev && st == 0u) ? lower_i32(a.t, nc, 1) : 0;
         h[H_NC] = nc; h[H_NH] = nh; h[H_NP] = np; h[H_NS] = ns;
         h[H_E0] = (st == 0u && nc) ? a.pptr[nh] : 0;
@@ -69,36 +93,78 @@ __global__ void __launch_bounds__(256) k_pack_tables(PackArgs a) {
         h[H_STATUS] = st | (fits || st != 0u ? 0u : ST_EXCHANGE);
         h[H_NRUNS] = a.totals[2];
         for (int i = H_CBASE; i < HDR_WORDS; ++i) h[i] = 0;
+        for (int q = 0; q < a.ndst; ++q)
+            for (int i = 0; i < HDR_WORDS; ++i) reinterpret_cast<unsigned long long*>(a.dst[q])[i] = h[i];
     }
-    if (!fits) return;
-    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long)gridDim.x * blockDim.x;
-    char* d = a.dst + HDR_BYTES;
-#define CT_OUT(T, k) reinterpret_cast<T*>(d + a.o.off[cts::k])
-    for (long i = gtid; i < nc; i += gsize) {
-        CT_OUT(int32_t, A_T)[i] = a.t[i]; CT_OUT(int32_t, A_Y0)[i] = a.y0[i]; CT_OUT(int32_t, A_Y1)[i] = a.y1[i];
-        CT_OUT(int32_t, A_X0)[i] = a.x0[i]; CT_OUT(int32_t, A_X1)[i] = a.x1[i]; CT_OUT(uint32_t, A_CLS)[i] = a.cls[i];
-        CT_OUT(double, A_CONE)[i] = a.conE[i]; CT_OUT(double, A_CONS)[i] = a.conS[i]; CT_OUT(double, A_FE)[i] = a.fE[i];
-        CT_OUT(double, A_FS)[i] = a.fS[i]; CT_OUT(uint32_t, A_NSP)[i] = a.nsp[i]; CT_OUT(uint32_t, A_FNSP)[i] = a.fnsp[i];
+    if (fits) {
+        const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long)gridDim.x * blockDim.x;
+        const int nd = a.ndst;
+        // every value is read once and stored to all destinations (NVLink stores are fire-and-forget: no round trip)
+#define CT_PUT(T, k, i, v)                                                                          \
+    do {                                                                                            \
+        const T v_ = (v);                                                                           \
+        for (int q = 0; q < nd; ++q) reinterpret_cast<T*>(a.dst[q] + HDR_BYTES + a.o.off[cts::k])[i] = v_; \
+    } while (0)
+        for (long i = gtid; i < nc; i += gsize) {
+            CT_PUT(int32_t, A_T, i, a.t[i]); CT_PUT(int32_t, A_Y0, i, a.y0[i]); CT_PUT(int32_t, A_Y1, i, a.y1[i]);
+            CT_PUT(int32_t, A_X0, i, a.x0[i]); CT_PUT(int32_t, A_X1, i, a.x1[i]); CT_PUT(uint32_t, A_CLS, i, a.cls[i]);
+            CT_PUT(double, A_CONE, i, a.conE[i]); CT_PUT(double, A_CONS, i, a.conS[i]); CT_PUT(double, A_FE, i, a.fE[i]);
+            CT_PUT(double, A_FS, i, a.fS[i]); CT_PUT(uint32_t, A_NSP, i, a.nsp[i]); CT_PUT(uint32_t, A_FNSP, i, a.fnsp[i]);
+        }
+        for (long i = gtid; i <= nc; i += gsize) CT_PUT(uint32_t, A_PPTR, i, nc ? a.pptr[i] : 0u);
+        for (long i = gtid; i < np; i += gsize) {
+            CT_PUT(uint32_t, A_PB, i, a.pb[i]); CT_PUT(uint32_t, A_PNPIX, i, a.pnpix[i]); CT_PUT(uint32_t, A_PNSP, i, a.pnsp[i]);
+            CT_PUT(double, A_PE, i, a.pE[i]); CT_PUT(double, A_PS, i, a.pS[i]);
+        }
+        for (long i = gtid; i < ns; i += gsize) {
+            CT_PUT(int32_t, A_GT, i, a.gt[i]); CT_PUT(int32_t, A_GY0, i, a.gy0[i]); CT_PUT(int32_t, A_GY1, i, a.gy1[i]);
+            CT_PUT(uint32_t, A_GA, i, a.ga[i]); CT_PUT(uint32_t, A_GB, i, a.gb[i]);
+        }
+#undef CT_PUT
     }
-    for (long i = gtid; i <= nc; i += gsize) CT_OUT(uint32_t, A_PPTR)[i] = nc ? a.pptr[i] : 0u;
-    for (long i = gtid; i < np; i += gsize) {
-        CT_OUT(uint32_t, A_PB)[i] = a.pb[i]; CT_OUT(uint32_t, A_PNPIX)[i] = a.pnpix[i]; CT_OUT(uint32_t, A_PNSP)[i] = a.pnsp[i];
-        CT_OUT(double, A_PE)[i] = a.pE[i]; CT_OUT(double, A_PS)[i] = a.pS[i];
+    if (a.done_ctr) {
+        // the last block through raises this rank's flag at every peer: stores of all blocks are ordered before it
+        // (fence by every thread, block barrier, counter; then fence + release store by the last block)
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(a.done_ctr, 1u) == gridDim.x - 1) {
+            *a.done_ctr = 0;                                          // (the next launch follows in stream order)
+            __threadfence_system();
+            for (int q = 0; q < a.ndst; ++q)
+                if (a.flag[q]) st_release_sys(a.flag[q], a.epoch);
+        }
     }
-    for (long i = gtid; i < ns; i += gsize) {
-        CT_OUT(int32_t, A_GT)[i] = a.gt[i]; CT_OUT(int32_t, A_GY0)[i] = a.gy0[i]; CT_OUT(int32_t, A_GY1)[i] = a.gy1[i];
-        CT_OUT(uint32_t, A_GA)[i] = a.ga[i]; CT_OUT(uint32_t, A_GB)[i] = a.gb[i];
-    }
-#undef CT_OUT
 }
 
 // one block: headers of all ranks -> per-rank descriptors (header + bases) and the control block of the global context
+// (one warp).  With peer windows the kernel first waits until every rank's flag word carries this exchange's epoch.
 __global__ void k_merge_desc(const char* gathered, size_t stride, int nranks, unsigned long long* mdesc /*[nranks * 16]*/,
                              uint32_t* gctl /*ticket, status, info, -, totals u64 x 4 at word 4*/, unsigned long long* need4,
-                             unsigned long long capCg, unsigned long long capPg, unsigned long long capSg) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+                             unsigned long long capCg, unsigned long long capPg, unsigned long long capSg,
+                             const unsigned long long* flags /*[nranks] or null*/, unsigned long long epoch) {
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    int late = 0;
+    if (flags && (int)threadIdx.x < nranks) {
+        const unsigned long long t0 = global_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
+            __nanosleep(200);
+            if ((++spins & 255u) == 0u && global_ns() - t0 > FLAG_WAIT_NS) { late = 1; break; }
+        }
+    }
+    late = __any_sync(0xffffffffu, late);
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
     unsigned long long NC = 0, NP = 0, NS = 0, NR = 0, mc = 0, mp = 0, ms = 0;
     uint32_t status = 0;
+    if (late) {                                   // a rank never delivered its tables (it failed, or left the call early)
+        unsigned long long* totals = reinterpret_cast<unsigned long long*>(gctl + 4);
+        totals[0] = totals[1] = totals[2] = totals[3] = 0;
+        gctl[0] = 0; gctl[1] = ctp::ST_TIMEOUT; gctl[2] = 0;
+        for (int i = 0; i < nranks * HDR_WORDS; ++i) mdesc[i] = 0;
+        need4[0] = need4[1] = need4[2] = 0; need4[3] = ctp::ST_TIMEOUT;
+        return;
+    }
     for (int r = 0; r < nranks; ++r) {
         const unsigned long long* h = reinterpret_cast<const unsigned long long*>(gathered + (size_t)r * stride);
         unsigned long long* m = mdesc + (size_t)r * HDR_WORDS;
@@ -324,6 +390,16 @@ int ct_comm_init_local(int nranks, ct_comm** out /* [nranks] */) {
 
 void ct_comm_destroy(ct_comm* comm) {
     if (!comm) return;
+    if (comm->window) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (comm->window_device >= 0) cudaSetDevice(comm->window_device);
+        cudaDeviceSynchronize();
+        delete comm->impl;                     // (closes its mappings of the other ranks' windows first)
+        comm->impl = nullptr;
+        cudaFree(comm->window);
+        cudaSetDevice(dev);
+    }
     delete comm->impl;
     if (comm->group) ctc::local_group_destroy(comm->group);
     delete comm;
@@ -359,6 +435,39 @@ int ct_quantile_time_t(ct_ctx* c, ct_comm* comm_h, const void* x_dev, int dtype,
 
 // ---- the sharded run ----------------------------------------------------------------------------------------------------
 }  // extern "C"
+
+// Peer windows of the table exchange: one allocation per rank = flag words + two gathered buffers (double buffer by exchange
+// parity: a fast rank may already be packing exchange k+1 into a peer that is still merging exchange k).  Mapped once per
+// communicator, re-made (collectively) when the stride outgrows it.  All ranks take the same branches: the sizes derive from
+// the negotiated capacities, which are equal everywhere.
+static int window_prepare(ct_ctx* c, ct_comm* h, size_t stride, cudaStream_t ts) {
+    ctc::Comm* comm = h->impl;
+    const int nranks = comm->size();
+    const size_t need = WIN_DATA + 2 * (size_t)nranks * stride;
+    if (h->window_mode == 2) return CT_OK;
+    if (h->window_mode == 1 && need <= h->window_bytes) return CT_OK;
+    if (h->window_mode == 1) {
+        CT_CUDA(cudaStreamSynchronize(ts));
+        if (comm->window_unmap(ts)) return fail(CT_ERR_COMM, "peer windows: %s", comm->err.c_str());
+        CT_CUDA(cudaFree(h->window));
+        h->window = nullptr; h->window_bytes = 0; h->window_mode = 0;
+    }
+    const size_t bytes = need + need / 4;
+    CT_CUDA(cudaMalloc(&h->window, bytes));
+    CT_CUDA(cudaMemsetAsync(h->window, 0, WIN_DATA, ts));
+    CT_CUDA(cudaStreamSynchronize(ts));
+    h->window_device = c->device;
+    h->peers.assign((size_t)nranks, nullptr);
+    const int r = comm->window_map(h->window, bytes, h->peers.data(), ts);
+    if (r < 0) return fail(CT_ERR_COMM, "peer windows: %s", comm->err.c_str());
+    if (r == 1) {                                                      // no peer memory between some pair of ranks
+        CT_CUDA(cudaFree(h->window));
+        h->window = nullptr; h->window_mode = 2;
+        return CT_OK;
+    }
+    h->window_bytes = bytes; h->window_mode = 1; h->epoch = 0;
+    return CT_OK;
+}
 
 // Device buffers (anom_dev / flag_dev) or host buffers (anom_host / flag_host): with host buffers the shard is streamed in
 // time chunks host -> device under the threshold kernel (the float shard is never resident) and the result leaves as the
@@ -399,6 +508,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
     }
     ct_ctx* g = c->gctx;
     g->opt_max_sweeps = c->opt_max_sweeps;
+    g->tail_fill.p = nullptr;
     cudaStream_t ts = c->tbl_stream, aux = c->copy_stream, side = c->side_stream;
     const size_t plane_bytes = (size_t)H * W * (in_dtype == CT_F64 ? 8 : 4);
     const size_t words = (size_t)H * c->Ww;
@@ -482,8 +592,13 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
         if (c->opt_fill_late && plane_first) {
             c->pend_fill = flag_dev; c->pend_fill_cells = cells;      // started by ctf::finish(), after the plane kernel
         } else {
-            CT_CUDA(ctk::zero_fill(flag_dev, cells, c->sm_count, side, (int)c->opt_fill_ctas));
+            // short shards: part of the fill is held back for the GPU's idle time during the host replay (after the global
+            // kernel), so that less of it runs beside the latency-bound plane / merge / global kernels
+            size_t tail = plane_first ? cells / 100 * (size_t)c->opt_fill_tail / 4 * 4 : 0;
+            if (reinterpret_cast<uintptr_t>(flag_dev + (cells - tail)) & 15) tail = 0;
+            CT_CUDA(ctk::zero_fill(flag_dev, cells - tail, c->sm_count, side, (int)c->opt_fill_ctas));
             c->launches += 1;
+            if (tail) c->gctx->tail_fill = {flag_dev + (cells - tail), tail, side, c->ev_side[1]};
         }
     }
     CT_CUDA(cudaEventRecord(c->ev_side[1], side));
@@ -523,7 +638,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
             }
         }
         // ---- exchange stride: negotiated once per problem (the only extra round trip, first call only) ----
-        if (!c->sh_capC) {
+        if (!comm_h->capC) {
             int oc = ctf::FAST_SLOW;
             if (!classic && (rc = ctf::totals_to_host(c, ts, &oc)) != CT_OK) return rc;
             unsigned long long mine[4] = {(unsigned long long)c->ncomp, (unsigned long long)c->npair, (unsigned long long)c->nseg, 0};
@@ -536,15 +651,24 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
             CT_CUDA(cudaStreamSynchronize(ts));
             unsigned long long mc = 0, mp = 0, ms = 0;
             for (int r = 0; r < nranks; ++r) { mc = std::max(mc, all[4 * r]); mp = std::max(mp, all[4 * r + 1]); ms = std::max(ms, all[4 * r + 2]); }
-            c->sh_capC = (long)(mc + mc / 8 + 512); c->sh_capP = (long)(mp + mp / 8 + 512); c->sh_capS = (long)(ms + ms / 8 + 512);
+            comm_h->capC = (long)(mc + mc / 8 + 512); comm_h->capP = (long)(mp + mp / 8 + 512); comm_h->capS = (long)(ms + ms / 8 + 512);
             c->stats["exchange_negotiated"] = 1.0;
             // (a local capacity retry / fallback is reported through the header and handled below like any other)
         }
         Offsets o;
-        const size_t stride = (HDR_BYTES + cts::layout(c->sh_capC, c->sh_capP, c->sh_capS, o.off) + 255) / 256 * 256;
-        CT_CUDA(c->sh_export.ensure(stride));
-        CT_CUDA(c->sh_gathered.ensure(stride * nranks));
+        const size_t stride = (HDR_BYTES + cts::layout(comm_h->capC, comm_h->capP, comm_h->capS, o.off) + 255) / 256 * 256;
         CT_CUDA(c->sh_mdesc.ensure((size_t)(nranks + 1) * HDR_BYTES + 256));
+        // peer windows (pack kernel stores into every rank's gathered buffer) or local slot + all-gather
+        if (c->opt_p2p && nranks > 1 && nranks <= MAX_PEERS && (rc = window_prepare(c, comm_h, stride, ts)) != CT_OK) return rc;
+        const bool p2p = c->opt_p2p && nranks > 1 && nranks <= MAX_PEERS && comm_h->window_mode == 1;
+        const char* gathered = nullptr;
+        const unsigned long long* wait_flags = nullptr;
+        unsigned long long epoch = 0;
+        if (!p2p) {
+            CT_CUDA(c->sh_export.ensure(stride));
+            CT_CUDA(c->sh_gathered.ensure(stride * nranks));
+            gathered = c->sh_gathered.as<char>();
+        }
         // ---- 3. pack + all-gather ----
         {
             PackArgs a;
@@ -556,17 +680,40 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
             a.gt = c->g_t.as<int32_t>(); a.gy0 = c->g_y0.as<int32_t>(); a.gy1 = c->g_y1.as<int32_t>(); a.ga = U(c->g_a); a.gb = U(c->g_b);
             a.totals = reinterpret_cast<const unsigned long long*>(c->pl_ctl.as<char>() + 16);
             a.status = U(c->pl_ctl) + 1;
-            a.capC = (unsigned long long)c->sh_capC; a.capP = (unsigned long long)c->sh_capP; a.capS = (unsigned long long)c->sh_capS;
+            a.capC = (unsigned long long)comm_h->capC; a.capP = (unsigned long long)comm_h->capP; a.capS = (unsigned long long)comm_h->capS;
             a.has_prev = hp; a.last_plane = (int)(planes - 1); a.t_shift = t_begin - hp;
-            a.dst = c->sh_export.as<char>(); a.o = o;
+            a.o = o;
+            for (int q = 0; q < MAX_PEERS; ++q) { a.dst[q] = nullptr; a.flag[q] = nullptr; }
+            if (p2p) {
+                epoch = ++comm_h->epoch;
+                const size_t par = (size_t)(epoch & 1);
+                const size_t buf = WIN_DATA + par * (size_t)nranks * stride;
+                const bool flags = comm->window_device_flags();
+                for (int q = 0; q < nranks; ++q) {
+                    char* w = static_cast<char*>(comm_h->peers[(size_t)q]);
+                    a.dst[q] = w + buf + (size_t)rank * stride;
+                    if (flags) a.flag[q] = reinterpret_cast<unsigned long long*>(w) + par * MAX_PEERS + rank;
+                }
+                a.ndst = nranks; a.epoch = epoch;
+                a.done_ctr = flags ? reinterpret_cast<uint32_t*>(static_cast<char*>(comm_h->window) + 1024) : nullptr;
+                gathered = static_cast<char*>(comm_h->window) + buf;
+                if (flags) wait_flags = reinterpret_cast<unsigned long long*>(comm_h->window) + par * MAX_PEERS;
+            } else {
+                a.dst[0] = c->sh_export.as<char>(); a.ndst = 1; a.epoch = 0; a.done_ctr = nullptr;
+            }
             k_pack_tables<<<c->sm_count * 2, 256, 0, ts>>>(a);
             CT_CUDA(cudaGetLastError());
             c->launches += 1;
         }
-        if (comm->allgather(c->sh_export.p, c->sh_gathered.p, stride, ts)) return comm_fail(comm, "table all-gather");
-        c->launches += 1;
+        if (p2p) {
+            if (!comm->window_device_flags() && comm->window_fence(ts)) return comm_fail(comm, "peer window fence");
+        } else {
+            if (comm->allgather(c->sh_export.p, c->sh_gathered.p, stride, ts)) return comm_fail(comm, "table all-gather");
+            c->launches += 1;
+        }
+        c->stats["p2p"] = p2p ? 1.0 : 0.0;
         // ---- 4. merge into the global context ----
-        const size_t gC = (size_t)nranks * c->sh_capC, gP = (size_t)nranks * c->sh_capP, gS = (size_t)nranks * c->sh_capS;
+        const size_t gC = (size_t)nranks * comm_h->capC, gP = (size_t)nranks * comm_h->capP, gS = (size_t)nranks * comm_h->capS;
         if ((rc = ctf::ensure_tables(g, 0, gC, gP, gS)) != CT_OK) return rc;
         if ((rc = ctf::ensure_control(g)) != CT_OK) return rc;
         g->T = T_total; g->H = H; g->W = W; g->Ww = c->Ww; g->special_uniform = c->special_uniform;
@@ -583,8 +730,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
             gt.g_t = g->g_t.as<int32_t>(); gt.g_y0 = g->g_y0.as<int32_t>(); gt.g_y1 = g->g_y1.as<int32_t>(); gt.g_a = U(g->g_a); gt.g_b = U(g->g_b);
             unsigned long long* md = c->sh_mdesc.as<unsigned long long>();
             unsigned long long* need4 = md + (size_t)nranks * HDR_WORDS;
-            const char* gathered = c->sh_gathered.as<char>();
-            k_merge_desc<<<1, 32, 0, ts>>>(gathered, stride, nranks, md, U(g->pl_ctl), need4, gC, gP, gS);
+            k_merge_desc<<<1, 32, 0, ts>>>(gathered, stride, nranks, md, U(g->pl_ctl), need4, gC, gP, gS, wait_flags, epoch);
             k_merge_comps<<<blocks_for(gC + 1), 256, 0, ts>>>(gathered, stride, nranks, md, U(g->pl_ctl), o, gt);
             k_merge_pairs<<<blocks_for(gP), 256, 0, ts>>>(gathered, stride, nranks, md, U(g->pl_ctl), o, gt);
             k_merge_segs<<<blocks_for(gS), 256, 0, ts>>>(gathered, stride, nranks, md, U(g->pl_ctl), o, gt);
@@ -618,9 +764,9 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
             local_ok = true;
         }
         if (gstatus & (ST_EXCHANGE | ctp::ST_CAPACITY)) {            // the stride (or the global tables) must grow
-            c->sh_capC = (long)std::max<unsigned long long>(c->sh_capC, need4[0] + need4[0] / 4 + 1024);
-            c->sh_capP = (long)std::max<unsigned long long>(c->sh_capP, need4[1] + need4[1] / 4 + 1024);
-            c->sh_capS = (long)std::max<unsigned long long>(c->sh_capS, need4[2] + need4[2] / 4 + 1024);
+            comm_h->capC = (long)std::max<unsigned long long>(comm_h->capC, need4[0] + need4[0] / 4 + 1024);
+            comm_h->capP = (long)std::max<unsigned long long>(comm_h->capP, need4[1] + need4[1] / 4 + 1024);
+            comm_h->capS = (long)std::max<unsigned long long>(comm_h->capS, need4[2] + need4[2] / 4 + 1024);
         }
     }
     c->stats["shard_attempts"] = (double)(attempts + 1);
@@ -723,7 +869,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
     c->plane_timed = 0;
     c->stats["kernel_launches"] = (double)(c->launches + g->launches);
     c->stats["runs"] = (double)c->nruns; c->stats["comps2d"] = (double)c->ncomp;
-    c->stats["exchange_bytes"] = (double)((HDR_BYTES + [&] { size_t off[cts::A_COUNT]; return cts::layout(c->sh_capC, c->sh_capP, c->sh_capS, off); }() + 255) / 256 * 256);
+    c->stats["exchange_bytes"] = (double)((HDR_BYTES + [&] { size_t off[cts::A_COUNT]; return cts::layout(comm_h->capC, comm_h->capP, comm_h->capS, off); }() + 255) / 256 * 256);
     for (const char* k : {"labels3d", "features", "seam_events", "seam_splits", "neartie_resolved", "neartie_flagged", "sweeps",
                           "wavefront_planes", "ms_host_tables", "ms_g_kernel", "label_fast", "event_segments", "ms_global_kernel"})
         if (g->stats.count(k)) c->stats[k] = g->stats[k];

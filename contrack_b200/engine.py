@@ -19,7 +19,7 @@ _STAT_KEYS = ('runs', 'comps2d', 'pairs', 'seam_rows', 'kept_comps', 'labels3d',
               'd2h_bytes', 'host_sparse', 'host_threads', 'chunks', 'ms_h_chunks', 'ms_h_global', 'ms_g_sweeps', 'ms_g_link',
               'ms_g_labels_d2h', 'ms_tables_after_threshold', 'moved_comps', 'ms_lc_rows', 'ms_lc_tables_sums', 'lc_rows',
               'lc_rolled', 'ms_ht_init', 'ms_ht_events', 'ms_ht_persist', 'ht_walked', 'label_fast', 'slot_overflow', 'fast_path', 'plane_attempts', 'wavefront_planes',
-              'ms_g_kernel', 'event_segments', 'ms_h_tables', 'shard_attempts', 'exchange_bytes', 'exchange_negotiated', 'ms_global_kernel', 'ms_plane_kernel', 'ms_exchange') + tuple('ms_h_c%d' % i for i in range(8)) + tuple(
+              'ms_g_kernel', 'event_segments', 'ms_h_tables', 'shard_attempts', 'exchange_bytes', 'exchange_negotiated', 'ms_global_kernel', 'ms_plane_kernel', 'ms_exchange', 'p2p') + tuple('ms_h_c%d' % i for i in range(8)) + tuple(
     'ms_t_' + k for k in ('row_scans', 'extract_runs', 'ccl_union', 'ccl_flatten', 'root_scan', 'comp_accumulate', 'seam_segs',
                           'class_sums', 'pairs_accumulate', 'pairs_csr'))
 

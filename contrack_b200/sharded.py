@@ -131,13 +131,17 @@ def quantile_time_sharded(engine, x_local, q, y0=0, y1=None, comm=None, group=No
     return engine.quantile_time(x_local, q, y0, y1, comm=comm if comm is not None else default_comm(engine, group))
 
 
-def run_local_group(engines, anom_parts, T_total, w, thresholds, thr_is_f32, op, overlap, persistence, twosided):
+def run_local_group(engines, anom_parts, T_total, w, thresholds, thr_is_f32, op, overlap, persistence, twosided, comms=None,
+                    outs=None):
     """The sharded call on an in-process group: engines[r] plays rank r from its own host thread (the contexts may share one
-    GPU).  Returns ([flag_r], n_features, [stats_r]).  Single-GPU tests and debugging."""
+    GPU).  Returns ([flag_r], n_features, [stats_r]).  Single-GPU tests and debugging.  `comms`: communicators of an earlier
+    Comm.local_group(n) to reuse (the negotiated exchange capacities and the peer windows live with the communicator)."""
     import threading
     import torch
     n = len(engines)
-    comms = Comm.local_group(n)
+    own_comms = comms is None
+    if own_comms:
+        comms = Comm.local_group(n)
     thr = np.atleast_1d(np.asarray(thresholds, np.float64))
     bounds = np.cumsum([0] + [int(a.shape[0]) for a in anom_parts])
     res, errs = [None] * n, [None] * n
@@ -148,7 +152,8 @@ def run_local_group(engines, anom_parts, T_total, w, thresholds, thr_is_f32, op,
             with torch.cuda.stream(torch.cuda.Stream(device=engines[r].device)):
                 t = thr if len(thr) == 1 else thr[bounds[r]:bounds[r + 1]]
                 res[r] = run_contrack_sharded(engines[r], anom_parts[r], int(bounds[r]), T_total, w, t, thr_is_f32, op,
-                                              overlap, persistence, twosided, comm=comms[r])
+                                              overlap, persistence, twosided, comm=comms[r],
+                                              out=None if outs is None else outs[r])
                 torch.cuda.current_stream().synchronize()
         except BaseException as e:                      # noqa: BLE001  (reported by the caller; a dead rank would hang the rest)
             errs[r] = e
@@ -157,8 +162,9 @@ def run_local_group(engines, anom_parts, T_total, w, thresholds, thr_is_f32, op,
         t.start()
     for t in threads:
         t.join()
-    for c in comms:
-        c.close()
+    if own_comms:
+        for c in comms:
+            c.close()
     for e in errs:
         if e is not None:
             raise e

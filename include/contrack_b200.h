@@ -74,6 +74,10 @@ void ct_destroy(ct_ctx* ctx);
  *   "overlap_zero" [1] zero fill of the flag cube on a side stream beside the table phase + sparse paint; 0 = dense paint
  *   "fill_ctas"    [2] resident blocks per SM of the zero fill (room for the table kernels beside it); 0 = uncapped
  *   "fill_late"    [0] plane-kernel path: 1 = the zero fill starts after the plane kernel instead of beside it
+ *   "p2p"          [1] sharded run: the pack kernel stores every rank's tables straight into the gathered buffers of all
+ *                  ranks (peer memory over NVLink, mapped with CUDA IPC once per communicator) and signals with flag words;
+ *                  0 = local pack + one ncclAllGather (also used when peer memory is unavailable or with > 16 ranks).
+ *                  Must be the same on all ranks.
  *   "chunks"       [4] time chunks of the global-memory table pipeline ("chunk_min_planes" [1024] = smallest chunk);
  *                  "fast_chunks" [1] the same for the plane kernel (1: it runs beside the zero fill)
  *   "host_sparse"  [1] ct_run_contrack_host returns the result as row-runs expanded by host threads; 0 = dense copy

@@ -26,16 +26,21 @@ def main():
     cases = [(d['anom'], d['latitude'], d['longitude'], 150, 0.5, 5, True),
              (synth_cube(1396, 12, 24, 16, (1.5, 2, 2)),) + regular_grid(24, 16) + (60, 0.0, 1, False),
              (synth_cube(5, 24, 181, 360, (2.0, 4, 6)),) + regular_grid(181, 360) + (150, 0.7, 4, True)]
-    for x, lat, lon, thr, ov, pers, two in cases:
-        w = row_weights(lat, lon)
-        ref = oracle.run_contrack(x, lat, lon, thr, '>=', ov, pers, two)
-        t0, t1 = sharded.shard_bounds(x.shape[0], world)[rank]
-        xl = torch.from_numpy(np.ascontiguousarray(x[t0:t1])).cuda()
-        flag, n, stats = sharded.run_contrack_sharded(eng, xl, t0, x.shape[0], w, thr, True, 0, ov, pers, two)
-        torch.cuda.synchronize()
-        if not np.array_equal(flag.cpu().numpy(), ref[t0:t1]) or n != len(np.unique(ref)) - 1:
-            print('rank %d MISMATCH' % rank, flush=True)
-            sys.exit(3)
+    seen = set()
+    for p2p in (1, 0, 1):                      # peer windows (NVLink stores + flag words), ncclAllGather, peer windows again
+        eng.set_option('p2p', p2p)
+        for x, lat, lon, thr, ov, pers, two in cases:
+            w = row_weights(lat, lon)
+            ref = oracle.run_contrack(x, lat, lon, thr, '>=', ov, pers, two)
+            t0, t1 = sharded.shard_bounds(x.shape[0], world)[rank]
+            xl = torch.from_numpy(np.ascontiguousarray(x[t0:t1])).cuda()
+            flag, n, stats = sharded.run_contrack_sharded(eng, xl, t0, x.shape[0], w, thr, True, 0, ov, pers, two)
+            torch.cuda.synchronize()
+            seen.add((p2p, stats.get('p2p')))
+            if not np.array_equal(flag.cpu().numpy(), ref[t0:t1]) or n != len(np.unique(ref)) - 1:
+                print('rank %d MISMATCH (p2p=%d)' % (rank, p2p), flush=True)
+                sys.exit(3)
+    print('rank %d transports (asked, used): %s' % (rank, sorted(seen)), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     print('rank %d ok' % rank, flush=True)

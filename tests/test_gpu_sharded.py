@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_local(x, w, parts, thr, gorl, ov, pers, two, opts=None, f32=True, engines=None, host=False):
+def run_local(x, w, parts, thr, gorl, ov, pers, two, opts=None, f32=True, engines=None, host=False, comms=None):
     """x split into len(parts) time shards, one in-process rank each (host=True: host buffers through
     ct_run_contrack_sharded_host).  Returns (flag cube, features, [stats])."""
     import torch
@@ -33,7 +33,8 @@ def run_local(x, w, parts, thr, gorl, ov, pers, two, opts=None, f32=True, engine
         xs = [np.ascontiguousarray(x[a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
         if not host:
             xs = [torch.from_numpy(a).cuda() for a in xs]
-        outs, n, stats = sharded.run_local_group(engines, xs, x.shape[0], w, thr, f32, GORL_TO_OP[gorl], ov, pers, two)
+        outs, n, stats = sharded.run_local_group(engines, xs, x.shape[0], w, thr, f32, GORL_TO_OP[gorl], ov, pers, two,
+                                                 comms=comms)
         torch.cuda.synchronize()
         return np.concatenate([o if host else o.cpu().numpy() for o in outs]), n, stats
     finally:
@@ -112,24 +113,61 @@ def test_sharded_stale_box_split_and_seam_cases():
             assert np.array_equal(f, oracle.run_contrack(x, lat, lon, 60, '>=', 0.5, 2, True)), (seed, parts)
 
 
-def test_sharded_benchmark_grid_with_poles_and_exchange_renegotiation():
-    """721 x 1440 grid with pole rows on three ranks; then, on the SAME contexts, a cube with many more components: the
-    stride negotiated for the first cube is too small, every rank sees it in the headers and the exchange is repeated."""
-    from contrack_b200 import Engine
+@pytest.mark.parametrize('p2p', [1, 0])
+def test_sharded_benchmark_grid_with_poles_and_exchange_renegotiation(p2p):
+    """721 x 1440 grid with pole rows on three ranks; then, on the SAME contexts and communicators, a cube with many more
+    components: the stride negotiated for the first cube is too small, every rank sees it in the headers and the exchange is
+    repeated (p2p=1: the peer windows are re-made for the larger stride; p2p=0: the all-gather variant)."""
+    from contrack_b200 import Engine, sharded
     lat = np.linspace(90, -90, 721).astype(np.float32)
     lon = (np.arange(1440) * 0.25).astype(np.float32)
     w = oracle.weight_grid(lat, oracle.resolution(lat, True), oracle.resolution(lon, True), 1440)[:, 0].copy()
     engines = [Engine(0) for _ in range(3)]
+    comms = sharded.Comm.local_group(3)
     try:
         x = synth_cube(2, 12, 721, 1440, (2.5, 24, 40))
         ref = oracle.run_contrack(x, lat, lon, 160, '>=', 0.5, 5, True, force=True)
-        f, n, st = run_local(x, w, (5, 4, 3), 160, '>=', 0.5, 5, True, engines=engines)
-        assert np.array_equal(f, ref) and st[0]['shard_attempts'] == 1.0
+        f, n, st = run_local(x, w, (5, 4, 3), 160, '>=', 0.5, 5, True, engines=engines, comms=comms, opts={'p2p': p2p})
+        assert np.array_equal(f, ref) and st[0]['shard_attempts'] == 1.0 and st[0]['p2p'] == float(p2p)
         y = synth_cube(3, 12, 721, 1440, (1.0, 3, 4))             # small-scale field: thousands of components per plane
         ref = oracle.run_contrack(y, lat, lon, 100, '>=', 0.3, 2, True, force=True)
-        f, n, st = run_local(y, w, (5, 4, 3), 100, '>=', 0.3, 2, True, engines=engines)
+        f, n, st = run_local(y, w, (5, 4, 3), 100, '>=', 0.3, 2, True, engines=engines, comms=comms)
         assert np.array_equal(f, ref) and n == len(np.unique(ref)) - 1
         assert st[0]['shard_attempts'] >= 2.0, st[0]
+        for seed in (4, 5, 6):                                     # steady state: both halves of the double buffer in use
+            z = synth_cube(seed, 12, 721, 1440, (1.0, 3, 4))
+            f, n, st = run_local(z, w, (5, 4, 3), 100, '>=', 0.3, 2, True, engines=engines, comms=comms)
+            assert np.array_equal(f, oracle.run_contrack(z, lat, lon, 100, '>=', 0.3, 2, True, force=True)), seed
+    finally:
+        for c in comms:
+            c.close()
+        for e in engines:
+            e.lib.ct_destroy(e.handle)
+            e.handle = None
+
+
+@pytest.mark.parametrize('tail', [0, 40, 90])
+def test_sharded_fill_tail_zeroes_every_cell(tail):
+    """Option fill_tail holds part of the zero fill back until the global kernel has run: result buffers that arrive full of
+    garbage must come back exact."""
+    import torch
+    from contrack_b200 import Engine, sharded
+    from contrack_b200._lib import GORL_TO_OP
+    lat, lon = regular_grid(91, 180)
+    w = row_weights(lat, lon)
+    x = synth_cube(11, 13, 91, 180, (1.5, 4, 6))
+    ref = oracle.run_contrack(x, lat, lon, 80, '>=', 0.5, 3, True)
+    parts = (5, 1, 7)
+    engines = [Engine(0) for _ in parts]
+    try:
+        for e in engines:
+            e.set_option('fill_tail', tail)
+        bounds = np.cumsum([0] + list(parts))
+        xs = [torch.from_numpy(np.ascontiguousarray(x[a:b])).cuda() for a, b in zip(bounds[:-1], bounds[1:])]
+        outs = [torch.full(tuple(a.shape), -7, dtype=torch.int32, device='cuda') for a in xs]
+        res, n, _ = sharded.run_local_group(engines, xs, x.shape[0], w, 80, True, GORL_TO_OP['>='], 0.5, 3, True, outs=outs)
+        torch.cuda.synchronize()
+        assert np.array_equal(np.concatenate([o.cpu().numpy() for o in res]), ref)
     finally:
         for e in engines:
             e.lib.ct_destroy(e.handle)

@@ -850,7 +850,6 @@ int ct_set_option(ct_ctx* c, const char* key, long value) {
     if (!strcmp(key, "host_out_zeroed")) { c->opt_host_out_zeroed = value; return CT_OK; }
     if (!strcmp(key, "fill_late")) { c->opt_fill_late = value; return CT_OK; }
     if (!strcmp(key, "p2p")) { c->opt_p2p = value; return CT_OK; }
-    if (!strcmp(key, "fill_tail")) { c->opt_fill_tail = value < 0 ? 0 : value > 90 ? 90 : value; return CT_OK; }
     if (!strcmp(key, "fill_ctas")) { c->opt_fill_ctas = value; return CT_OK; }
     if (!strcmp(key, "profile_tables")) { c->opt_profile_tables = value; return CT_OK; }
     if (!strcmp(key, "plane_kernel")) { c->opt_plane_kernel = value; return CT_OK; }
@@ -920,7 +919,7 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
             c->pend_fill = flag_dev; c->pend_fill_cells = (size_t)T * H * W;      // enqueued by ctf::finish()
         } else {
             CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-            CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T * H * W, c->sm_count, c->side_stream, (int)c->opt_fill_ctas));
+            CT_CUDA(ctk::zero_fill(flag_dev, (size_t)T * H * W, c->sm_count, c->side_stream, cti::fill_ctas(c, fast)));
             CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
             c->launches += 1;
         }
@@ -942,7 +941,7 @@ int ct_run_contrack(ct_ctx* c, const void* anom_dev, int in_dtype, long T, int H
     if (sparse) {
         if (c->pend_fill) {                                            // (the tables came from the fallback path: fill now)
             CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-            CT_CUDA(ctk::zero_fill(c->pend_fill, c->pend_fill_cells, c->sm_count, c->side_stream, (int)c->opt_fill_ctas));
+            CT_CUDA(ctk::zero_fill(c->pend_fill, c->pend_fill_cells, c->sm_count, c->side_stream, cti::fill_ctas(c, false)));
             CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
             c->launches += 1;
             c->pend_fill = nullptr;

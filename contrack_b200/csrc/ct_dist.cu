@@ -508,7 +508,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
     }
     ct_ctx* g = c->gctx;
     g->opt_max_sweeps = c->opt_max_sweeps;
-    g->tail_fill.p = nullptr;
+
     cudaStream_t ts = c->tbl_stream, aux = c->copy_stream, side = c->side_stream;
     const size_t plane_bytes = (size_t)H * W * (in_dtype == CT_F64 ? 8 : 4);
     const size_t words = (size_t)H * c->Ww;
@@ -592,13 +592,8 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
         if (c->opt_fill_late && plane_first) {
             c->pend_fill = flag_dev; c->pend_fill_cells = cells;      // started by ctf::finish(), after the plane kernel
         } else {
-            // short shards: part of the fill is held back for the GPU's idle time during the host replay (after the global
-            // kernel), so that less of it runs beside the latency-bound plane / merge / global kernels
-            size_t tail = plane_first ? cells / 100 * (size_t)c->opt_fill_tail / 4 * 4 : 0;
-            if (reinterpret_cast<uintptr_t>(flag_dev + (cells - tail)) & 15) tail = 0;
-            CT_CUDA(ctk::zero_fill(flag_dev, cells - tail, c->sm_count, side, (int)c->opt_fill_ctas));
+            CT_CUDA(ctk::zero_fill(flag_dev, cells, c->sm_count, side, cti::fill_ctas(c, plane_first)));
             c->launches += 1;
-            if (tail) c->gctx->tail_fill = {flag_dev + (cells - tail), tail, side, c->ev_side[1]};
         }
     }
     CT_CUDA(cudaEventRecord(c->ev_side[1], side));
@@ -794,7 +789,7 @@ static int sharded_run(ct_ctx* c, ct_comm* comm_h, const void* anom_dev, const v
     for (const ctb::Override& ov : g->host_result.overrides)
         if (ov.t >= t_begin && ov.t < t_begin + T_local) ovr.push_back(ctb::Override{(int32_t)(ov.t - t_begin), ov.y, ov.x0, ov.x1, ov.val});
     if (c->pend_fill) {                                                // (local tables came from the fallback kernels)
-        CT_CUDA(ctk::zero_fill(c->pend_fill, c->pend_fill_cells, c->sm_count, side, (int)c->opt_fill_ctas));
+        CT_CUDA(ctk::zero_fill(c->pend_fill, c->pend_fill_cells, c->sm_count, side, cti::fill_ctas(c, false)));
         CT_CUDA(cudaEventRecord(c->ev_side[1], side));
         c->launches += 1;
         c->pend_fill = nullptr;

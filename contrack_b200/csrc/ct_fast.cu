@@ -197,7 +197,7 @@ int finish(ct_ctx* c, cudaStream_t st) {
         CT_CUDA(cudaEventRecord(c->ev_tbl[1], st));
         CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_tbl[1], 0));
         CT_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-        CT_CUDA(ctk::zero_fill(c->pend_fill, c->pend_fill_cells, c->sm_count, c->side_stream, (int)c->opt_fill_ctas));
+        CT_CUDA(ctk::zero_fill(c->pend_fill, c->pend_fill_cells, c->sm_count, c->side_stream, cti::fill_ctas(c, true)));
         CT_CUDA(cudaEventRecord(c->ev_side[1], c->side_stream));
         c->launches += 1;
         c->pend_fill = nullptr;
@@ -274,14 +274,6 @@ int global(ct_ctx* c, long T, double overlap, int persistence, int twosided, lon
     CT_CUDA(ctp::global_phase(a, c->coop_grid, st));
     CT_CUDA(cudaEventRecord(c->ev_p[3], st));
     c->launches += 1;
-    if (c->tail_fill.p) {
-        // the held-back part of the zero fill: from here to the paint the GPU would only wait for the host replay
-        CT_CUDA(cudaStreamWaitEvent(c->tail_fill.stream, c->ev_p[3], 0));
-        CT_CUDA(ctk::zero_fill(c->tail_fill.p, c->tail_fill.cells, c->sm_count, c->tail_fill.stream, 0));
-        CT_CUDA(cudaEventRecord(c->tail_fill.done, c->tail_fill.stream));
-        c->launches += 1;
-        c->tail_fill.p = nullptr;
-    }
     // ---- control block + (speculatively) the first events and label records in one round trip ----
     constexpr long EV_FIRST = 32768, REC_FIRST = 8192;
     uint32_t* hctl = c->hp_ctl.as<uint32_t>();

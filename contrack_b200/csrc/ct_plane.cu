@@ -257,7 +257,11 @@ __global__ void __launch_bounds__(PLANE_THREADS) k_plane_tables(PlaneArgs a) {
     }
     __syncthreads();
     // ---- D. roots -> local component index in raster order ----
-    for (uint32_t i = tid; i < n; i += nthr) par[i] = (uint16_t)uf_find(par, i);      // (benign races: all writes are roots)
+    // (flattened through `kid`: writing the roots into the array other threads are still walking would be harmless -- every
+    // value ever stored is an ancestor -- but it is a data race by the letter, and racecheck says so)
+    for (uint32_t i = tid; i < n; i += nthr) kid[i] = (uint16_t)uf_find(par, i);
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += nthr) par[i] = kid[i];
     __syncthreads();
     uint32_t nC = 0;
     for (uint32_t i0 = 0; i0 < n; i0 += nthr) {
@@ -286,8 +290,7 @@ __global__ void __launch_bounds__(PLANE_THREADS) k_plane_tables(PlaneArgs a) {
         sab[y] = ab;
     }
     __syncthreads();
-    for (uint32_t k = tid; k < nC; k += nthr) cls[k] = (uint16_t)uf_find(cls, k);
-    uint32_t nS = 0;
+    uint32_t nS = 0;                                                 // (class representatives: uf_find(cls, k) where they are used)
     for (int y0 = 0; y0 < H; y0 += nthr) {
         const int y = y0 + tid;
         uint32_t st = 0;
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(PLANE_THREADS) k_plane_tables(PlaneArgs a) {
         for (uint32_t k = tid; k < nC; k += nthr) {
             const uint32_t c = baseC + k;
             a.ct.t[c] = (int32_t)plane; a.ct.y0[c] = INT_MAX; a.ct.y1[c] = 0; a.ct.x0[c] = W; a.ct.x1[c] = 0;
-            a.ct.areaE[c] = 0.0; a.ct.areaS[c] = 0.0; a.ct.nsp[c] = 0; a.ct.cls[c] = baseC + cls[k];
+            a.ct.areaE[c] = 0.0; a.ct.areaS[c] = 0.0; a.ct.nsp[c] = 0; a.ct.cls[c] = baseC + uf_find(cls, k);
             a.kt.conE[c] = 0.0; a.kt.conS[c] = 0.0; a.kt.fE[c] = 0.0; a.kt.fS[c] = 0.0; a.kt.nsp[c] = 0; a.kt.fnsp[c] = 0;
             a.pcnt[c] = 0; a.pfill[c] = 0;
         }
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(PLANE_THREADS) k_plane_tables(PlaneArgs a) {
     __syncthreads();
     if (ok) {
         for (uint32_t k = tid; k < nC; k += nthr) {
-            const uint32_t c = baseC + k, rep = baseC + cls[k];
+            const uint32_t c = baseC + k, rep = baseC + uf_find(cls, k);
             atomicAdd(&a.kt.conE[rep], __ldcg(&a.ct.areaE[c]));
             const uint32_t ns = __ldcg(&a.ct.nsp[c]);
             if (ns) { atomicAdd(&a.kt.conS[rep], __ldcg(&a.ct.areaS[c])); atomicAdd(&a.kt.nsp[rep], ns); }

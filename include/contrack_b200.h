@@ -72,7 +72,8 @@ void ct_destroy(ct_ctx* ctx);
  *   "tma"          [1] threshold kernel: rows staged by cp.async.bulk + mbarrier; 0 = plain coalesced loads (also used
  *                  automatically for rows that are not 16-byte aligned or too long for shared memory)
  *   "overlap_zero" [1] zero fill of the flag cube on a side stream beside the table phase + sparse paint; 0 = dense paint
- *   "fill_ctas"    [2] resident blocks per SM of the zero fill (room for the table kernels beside it); 0 = uncapped
+ *   "fill_ctas"    [-1] resident blocks per SM of the zero fill (room for the table kernels beside it); -1 = automatic
+ *                  (1 beside the plane kernel, 2 beside the global-memory table kernels), 0 = uncapped
  *   "fill_late"    [0] plane-kernel path: 1 = the zero fill starts after the plane kernel instead of beside it
  *   "p2p"          [1] sharded run: the pack kernel stores every rank's tables straight into the gathered buffers of all
  *                  ranks (peer memory over NVLink, mapped with CUDA IPC once per communicator) and signals with flag words;

@@ -146,10 +146,9 @@ def test_sharded_benchmark_grid_with_poles_and_exchange_renegotiation(p2p):
             e.handle = None
 
 
-@pytest.mark.parametrize('tail', [0, 40, 90])
-def test_sharded_fill_tail_zeroes_every_cell(tail):
-    """Option fill_tail holds part of the zero fill back until the global kernel has run: result buffers that arrive full of
-    garbage must come back exact."""
+@pytest.mark.parametrize('ctas', [-1, 0, 1, 3])
+def test_sharded_result_buffers_full_of_garbage(ctas):
+    """Result buffers that arrive full of garbage come back exact, whatever the occupancy cap of the zero fill."""
     import torch
     from contrack_b200 import Engine, sharded
     from contrack_b200._lib import GORL_TO_OP
@@ -161,7 +160,7 @@ def test_sharded_fill_tail_zeroes_every_cell(tail):
     engines = [Engine(0) for _ in parts]
     try:
         for e in engines:
-            e.set_option('fill_tail', tail)
+            e.set_option('fill_ctas', ctas)
         bounds = np.cumsum([0] + list(parts))
         xs = [torch.from_numpy(np.ascontiguousarray(x[a:b])).cuda() for a, b in zip(bounds[:-1], bounds[1:])]
         outs = [torch.full(tuple(a.shape), -7, dtype=torch.int32, device='cuda') for a in xs]

@@ -30,7 +30,9 @@ for x, lat, lon, thr, ov, pers, two in cases:
 # sharded, three contexts on this GPU
 from test_gpu_sharded import run_local
 a, lat, lon = cases[0][:3]
-f, n, _ = run_local(a, row_weights(lat, lon), (4, 3, 4), 150, '>=', 0.5, 5, True)
+f, n, _ = run_local(a, row_weights(lat, lon), (4, 3, 4), 150, '>=', 0.5, 5, True)              # tables through peer windows
+f0, n0, _ = run_local(a, row_weights(lat, lon), (4, 3, 4), 150, '>=', 0.5, 5, True, opts={'p2p': 0})   # all-gather
+assert np.array_equal(f, f0) and n == n0
 for opts in ({'plane_kernel': 1}, {'plane_kernel': 0}, {'gpu_tables': 0}):                   # both table builders, host ordered phase
     for k, v in opts.items():
         eng.set_option(k, v)

@@ -620,6 +620,7 @@ def main():
                 _, n, _ = sharded.run_contrack_sharded(eng, xin_np, e_lo, Te, w, THRESHOLD, True, 0, OVERLAP, PERSISTENCE,
                                                        TWOSIDED, out=fout_np, comm=comm)
                 return n
+            barrier()                                    # (rank 0 may come late: it ran the CPU oracle of the parity block)
             e2e_step()
             barrier()
             t0 = time.perf_counter()

@@ -37,7 +37,9 @@ constexpr uint32_t ST_EXCHANGE = 8u;          // a rank's tables do not fit the 
 constexpr uint32_t ST_MISMATCH = 16u;         // halo components of rank r != last-plane components of rank r-1 (internal)
 constexpr int MAX_PEERS = 16;                 // ranks that can exchange through peer windows (more: the collective)
 constexpr size_t WIN_DATA = 4096;             // window: [0, 256) flag words [parity][rank], [1024] pack counter, data from 4096
-constexpr unsigned long long FLAG_WAIT_NS = 4000000000ull;
+// A rank may legitimately enter the call long after the others (host work, I/O): the wait for its flag is as patient as a
+// collective would be; only a rank that never arrives (it failed) ends the wait, with an error instead of a hang.
+constexpr unsigned long long FLAG_WAIT_NS = 600ull * 1000000000ull;
 
 struct Offsets { size_t off[cts::A_COUNT]; };
 
@@ -148,7 +150,7 @@ __global__ void k_merge_desc(const char* gathered, size_t stride, int nranks, un
         const unsigned long long t0 = global_ns();
         unsigned spins = 0;
         while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
-            __nanosleep(200);
+            __nanosleep(spins < 4096u ? 100u : 2000u);                // (one warp per GPU: cheap, and gentle when it is long)
             if ((++spins & 255u) == 0u && global_ns() - t0 > FLAG_WAIT_NS) { late = 1; break; }
         }
     }

@@ -41,6 +41,18 @@ def main():
                 print('rank %d MISMATCH (p2p=%d)' % (rank, p2p), flush=True)
                 sys.exit(3)
     print('rank %d transports (asked, used): %s' % (rank, sorted(seen)), flush=True)
+    # a rank that enters the call seconds after the others (host work, I/O) is waited for, as a collective would
+    import time
+    if rank == world - 1:
+        time.sleep(6.0)
+    x, lat, lon, thr, ov, pers, two = cases[0]
+    t0, t1 = sharded.shard_bounds(x.shape[0], world)[rank]
+    flag, n, _ = sharded.run_contrack_sharded(eng, torch.from_numpy(np.ascontiguousarray(x[t0:t1])).cuda(), t0, x.shape[0],
+                                              row_weights(lat, lon), thr, True, 0, ov, pers, two)
+    torch.cuda.synchronize()
+    if not np.array_equal(flag.cpu().numpy(), oracle.run_contrack(x, lat, lon, thr, '>=', ov, pers, two)[t0:t1]):
+        print('rank %d MISMATCH (late rank)' % rank, flush=True)
+        sys.exit(3)
     dist.barrier()
     dist.destroy_process_group()
     print('rank %d ok' % rank, flush=True)

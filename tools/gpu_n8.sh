@@ -5,7 +5,7 @@ N=${1:-8}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 timeout 600 $TR bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench rc=$?"
 tail -c 400 gpurun_out/r2_bench_n$N.err
-if [ "$N" = "8" ]; then
+if [ "$N" = "8" ] && [ -z "$2" ]; then
   timeout 600 $TR bench.py --gpus $N --config 5 --steps 5 --warmup 3 --no-e2e > gpurun_out/r2_bench_n${N}_config5.json 2> gpurun_out/r2_bench_n${N}_config5.err; echo "bench5 rc=$?"
   tail -c 400 gpurun_out/r2_bench_n${N}_config5.err
 fi

@@ -257,23 +257,22 @@ __global__ void __launch_bounds__(PLANE_THREADS) k_plane_tables(PlaneArgs a) {
     }
     __syncthreads();
     // ---- D. roots -> local component index in raster order ----
-    // (flattened through `kid`: writing the roots into the array other threads are still walking would be harmless -- every
-    // value ever stored is an ancestor -- but it is a data race by the letter, and racecheck says so)
+    // The roots go to `kid` (a read-only walk over `par`: flattening `par` in place while other threads still walk it would be
+    // harmless -- every value ever stored is an ancestor -- but it is a data race by the letter, and racecheck says so);
+    // the root positions of `par`, free from then on, take the component indices.
     for (uint32_t i = tid; i < n; i += nthr) kid[i] = (uint16_t)uf_find(par, i);
-    __syncthreads();
-    for (uint32_t i = tid; i < n; i += nthr) par[i] = kid[i];
     __syncthreads();
     uint32_t nC = 0;
     for (uint32_t i0 = 0; i0 < n; i0 += nthr) {
         const uint32_t i = i0 + tid;
-        const uint32_t isroot = (i < n && par[i] == i) ? 1u : 0u;
+        const uint32_t isroot = (i < n && kid[i] == i) ? 1u : 0u;
         uint32_t tot;
         const uint32_t ex = block_excl_scan(isroot, s_w, &tot);
-        if (isroot) kid[i] = (uint16_t)(nC + ex);
+        if (isroot) par[i] = (uint16_t)(nC + ex);
         nC += tot;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += nthr) { const uint32_t r = par[i]; if (r != i) kid[i] = kid[r]; }
+    for (uint32_t i = tid; i < n; i += nthr) kid[i] = par[kid[i]];  // (own entry of `kid`, root entries of `par`)
     __syncthreads();
 
     // ---- E. date-line rows: classes over the plane's components, segments of consecutive rows ----

@@ -8,7 +8,7 @@ so = os.path.join(ROOT, 'contrack_b200', 'lib', 'libcontrack_b200.so')
 out = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
 pats = {'UBLKCP': r'\bUBLKCP', 'SYNCS(mbarrier)': r'\bSYNCS', 'UTMALDG': r'\bUTMALDG', 'UTC*MMA': r'\bUTC\w*MMA', 'VOTE': r'\bVOTE', 'SHFL': r'\bSHFL',
         'ATOM/RED.global': r'\b(ATOMG|ATOM|REDG|RED)\b|\bATOM\.|\bRED\.', 'ATOMS(shared)': r'\bATOMS', 'BAR': r'\bBAR\.', 'LDG': r'\bLDG', 'STG': r'\bSTG',
-        'LDS': r'\bLDS', 'STS': r'\bSTS', 'DFMA/DMUL/DADD': r'\b(DFMA|DMUL|DADD)\b', 'MEMBAR/FENCE': r'\b(MEMBAR|FENCE)'}
+        'LDS': r'\bLDS', 'STS': r'\bSTS', 'DFMA/DMUL/DADD': r'\b(DFMA|DMUL|DADD)\b', 'MEMBAR/FENCE': r'\b(MEMBAR|FENCE)', 'STRONG.SYS (peer flags)': r'STRONG\.SYS', 'STRONG.GPU (chains)': r'STRONG\.GPU'}
 arch = re.findall(r'arch = (sm_\w+)', out)
 print('library:', os.path.relpath(so, ROOT), ' arch of every embedded cubin:', sorted(set(arch)))
 kern = None
@@ -26,7 +26,7 @@ for line in out.splitlines():
             kern = '%s #%d' % (base, n); n += 1
         tab[kern] = collections.Counter()
         continue
-    if kern and re.search(r'/\*[0-9a-f]{4}\*/', line):
+    if kern and re.search(r'/\*[0-9a-f]{4,}\*/', line):
         tab[kern]['instructions'] += 1
         for k, p in pats.items():
             if re.search(p, line):

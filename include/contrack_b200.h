@@ -187,8 +187,10 @@ int ct_host_tables_fast(long T, int H, int W, const double* w_host, double overl
 /* ---- time-sharded run: one context and one communicator per rank / GPU -------------------------------------
  * Rank r of nranks owns planes [t_begin, t_begin + T_local) of the cube; ranks are ordered in time.  ct_run_contrack_sharded
  * is ONE collective call per rank (contrack.py:646-772 across the shards): the last own plane's bit rows go to the next rank
- * (the one halo exchange, send/recv of H * ceil(W/32) words), the rank tables are all-gathered (a few MB, one collective of
- * fixed stride), merged by a kernel into global tables on every rank, and every rank replays the global part (overlap
+ * (the one halo exchange, send/recv of H * ceil(W/32) words), the rank tables (a few MB, slots of fixed stride) reach every
+ * rank in one step -- stored straight into the peers' buffers over NVLink by the kernel that packs them (option "p2p"; CUDA
+ * IPC windows set up once per communicator), or with one ncclAllGather -- are merged by a kernel into global tables on every
+ * rank, and every rank replays the global part (overlap
  * filter, 3-D numbering, stale-box date-line merge, persistence) on its copy: all ranks obtain the same global ids ("global
  * relabel") and paint their own planes.  The cube never moves.  ids, dtype and semantics are those of ct_run_contrack on the
  * concatenated cube, bit for bit.
@@ -202,8 +204,11 @@ int ct_host_tables_fast(long T, int H, int W, const double* w_host, double overl
  *                        single-GPU box, not a product transport
  * thr_host: one value, or the T_local values of this rank's planes.  `stream`: the caller's stream; the call returns after this
  * rank's flag planes are written (it synchronises once for the date-line events, like ct_run_contrack).
- * Runtime options of the context apply ("plane_kernel", "max_sweeps", ...); stats as for ct_run_contrack plus "exchange_bytes",
- * "shard_attempts". */
+ * Runtime options of the context apply ("plane_kernel", "max_sweeps", "p2p", ...) and must be equal on all ranks; stats as for
+ * ct_run_contrack plus "exchange_bytes", "shard_attempts", "ms_exchange", "p2p" (1 = peer windows were used).
+ * The negotiated slot sizes and the peer windows belong to the communicator: the ranks of a communicator must make the same
+ * sequence of sharded calls (as with any collective).  A rank that enters the call late is waited for; a rank that never
+ * arrives ends the others' wait with CT_ERR_INTERNAL after 10 minutes (peer windows) or blocks like any NCCL collective. */
 int ct_nccl_unique_id(unsigned char id[128]);
 int ct_comm_init_nccl(const unsigned char id[128], int rank, int nranks, int device, ct_comm** out);
 int ct_comm_from_nccl(void* nccl_comm, int rank, int nranks, ct_comm** out);

@@ -453,7 +453,15 @@ class contrack(object):
                                                         for k, v in coords.items()}, attrs=attrs, name=name)
 
     # ---- run_contrack (contrack.py:583-796) ------------------------------------------------------------------------
-    def run_contrack(self, variable, threshold, gorl, overlap, persistence, twosided=True, reference_dtype=False):
+    def run_contrack(self, variable, threshold, gorl, overlap, persistence, twosided=True, reference_dtype=False,
+                     time_shard=None, comm=None):
+        """The reference's call (contrack.py:583-590).  Two additions, both optional:
+        reference_dtype -- widen the int32 result to int64 where scipy would (cubes of 2^31 - 2 cells and more);
+        time_shard=(t_begin, T_total) -- this object holds planes [t_begin, t_begin + ntime) of a cube of T_total time steps
+        that is spread over several processes / GPUs in time order (one contrack object per rank, each with its own slice of
+        the time axis): the call is then collective over ``comm`` (a contrack_b200.sharded.Comm; default: an NCCL
+        communicator over the torch.distributed world) and every rank receives its own planes of the flag variable with
+        the ids of the unsharded run.  A dayofyear threshold is looked up on this rank's own time axis."""
         logger.info("\nRun ConTrack \n########### \n    threshold:    {} {} \n    overlap:      {} \n"
                     "    persistence:  {} time steps".format(gorl, threshold, overlap, persistence))
         logger.info("Set up dimensions...")
@@ -486,8 +494,18 @@ class contrack(object):
         # steps 2-4 on the GPU
         logger.info("Apply overlap...")
         logger.info("Apply persistence...")
-        flag, num_features = self._engine().run_contrack(
-            data, self.area_weights(), thr, thr_is_f32, GORL_TO_OP[gorl], overlap, persistence, twosided)
+        if time_shard is None:
+            flag, num_features = self._engine().run_contrack(
+                data, self.area_weights(), thr, thr_is_f32, GORL_TO_OP[gorl], overlap, persistence, twosided)
+        else:
+            from . import sharded
+            t_begin, T_total = (int(v) for v in time_shard)
+            if t_begin < 0 or t_begin + int(data.shape[0]) > T_total:
+                raise ValueError('time_shard: planes [%d, %d) are outside a cube of %d time steps'
+                                 % (t_begin, t_begin + int(data.shape[0]), T_total))
+            flag, num_features, _ = sharded.run_contrack_sharded(
+                self._engine(), data, t_begin, T_total, self.area_weights(), thr, thr_is_f32, GORL_TO_OP[gorl], overlap,
+                persistence, twosided, comm=comm)
         ncells = int(np.prod([int(n) for n in flag.shape]))       # (a torch tensor's .size is a method)
         if reference_dtype and ncells >= 2 ** 31 - 2:
             flag = flag.long() if hasattr(flag, 'long') else flag.astype(np.int64)

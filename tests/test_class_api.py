@@ -187,3 +187,37 @@ def test_single_time_step_raises_like_the_reference():
     c = contrack(ds=ds)
     with pytest.raises(IndexError):
         c.set_up()
+
+
+def test_time_shard_plumbing(monkeypatch):
+    """run_contrack(time_shard=(t_begin, T_total)) hands this rank's planes, its own slice of a dayofyear threshold, the shard
+    position and the communicator to the collective call, and stores what comes back as ds['flag'] (no GPU: the collective
+    itself is replaced here; tests/test_zz_examples.py runs it on the GPU)."""
+    from contrack_b200 import sharded
+    from contrack_b200.contrack import time_group_keys
+    d = np.load(dataset)
+    T, H, W = d['anom'].shape
+    doy = time_group_keys(d['time'], 'dayofyear')
+    thr_vals = np.linspace(120, 180, T)
+    thr = DataArray(thr_vals, ('dayofyear',), coords={'dayofyear': DataArray(doy, ('dayofyear',))})
+    seen = {}
+
+    def fake(engine, anom_local, t_begin, T_total, w, thresholds, thr_is_f32, op, overlap, persistence, twosided, out=None,
+             comm=None, group=None):
+        seen.update(engine=engine, shape=tuple(anom_local.shape), t_begin=t_begin, T_total=T_total, thr=np.array(thresholds),
+                    thr_is_f32=thr_is_f32, op=op, overlap=overlap, persistence=persistence, twosided=twosided, comm=comm, w=w)
+        return np.full(anom_local.shape, 7, np.int32), 1, {}
+    monkeypatch.setattr(sharded, 'run_contrack_sharded', fake)
+    lo, hi = 4, 9
+    ds = Dataset({'anom': (('time', 'latitude', 'longitude'), d['anom'][lo:hi])},
+                 coords={'time': d['time'][lo:hi], 'latitude': d['latitude'], 'longitude': d['longitude']})
+    c = contrack(ds=ds)
+    monkeypatch.setattr(c, '_engine', lambda: 'the engine')
+    c.run_contrack('anom', thr, '>=', 0.5, 3, time_shard=(lo, T), comm='the communicator')
+    assert seen['engine'] == 'the engine' and seen['comm'] == 'the communicator'
+    assert seen['shape'] == (hi - lo, H, W) and (seen['t_begin'], seen['T_total']) == (lo, T)
+    assert np.array_equal(seen['thr'], thr_vals[lo:hi]) and not seen['thr_is_f32']          # float64 thresholds
+    assert (seen['op'], seen['overlap'], seen['persistence'], seen['twosided']) == (0, 0.5, 3, True)
+    assert seen['w'].shape == (H,) and np.asarray(c['flag']).shape == (hi - lo, H, W) and (np.asarray(c['flag']) == 7).all()
+    with pytest.raises(ValueError):
+        c.run_contrack('anom', 150, '>=', 0.5, 3, time_shard=(T - 2, T))

@@ -60,3 +60,13 @@ def test_c_example_matches_the_oracle(tmp_path):
     got = np.fromfile(f, np.int32).reshape(T, H, W)
     assert np.array_equal(got, ref)
     assert r.stdout.startswith('features %d ' % (len(np.unique(ref)) - 1)), r.stdout
+
+
+@pytest.mark.gpu
+def test_class_api_on_a_time_sharded_cube():
+    """contrack.run_contrack(time_shard=...) on two in-process ranks (one with host data, one with device data); in a
+    subprocess with a time limit, because a rank that fails alone would leave the other one waiting."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_class_shard_worker.py')], capture_output=True, text=True,
+                       cwd=ROOT, timeout=300)
+    assert r.returncode == 0 and 'class sharded ok' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
